@@ -1,0 +1,66 @@
+#!/bin/bash
+# Fixture generator (test infrastructure).  Runs the UNMODIFIED reference to produce the
+# golden files committed under tests/golden/.  Needs:
+#   REF        reference source tree (default /root/reference, read-only)
+#   REF_BUILD  an out-of-tree CPU build of the reference (libparthenon.a + Kokkos libs),
+#              made with the recipe in SURVEY.md §8c (cmake, Kokkos OpenMP+Serial, no MPI,
+#              no HDF5, -O3, g++ 13.3).  Default /tmp/survey_ref_build_own.
+# Nothing is written into REF; all scratch goes to $WORK (default /tmp/pb2_refgen).
+set -euo pipefail
+REF=${REF:-/root/reference}
+REF_BUILD=${REF_BUILD:-/tmp/survey_ref_build_own}
+WORK=${WORK:-/tmp/pb2_refgen}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$(cd "$HERE/.." && pwd)
+mkdir -p "$WORK"
+
+INC="-I$REF/src -I$REF_BUILD/src/generated -I$REF_BUILD/Kokkos -I$REF_BUILD/Kokkos/core/src \
+ -I$REF/external/Kokkos/core/src -I$REF/external/Kokkos/tpls/desul/include \
+ -I$REF_BUILD/Kokkos/containers/src -I$REF/external/Kokkos/containers/src \
+ -I$REF_BUILD/Kokkos/algorithms/src -I$REF/external/Kokkos/algorithms/src \
+ -I$REF_BUILD/Kokkos/simd/src -I$REF/external/Kokkos/simd/src"
+LIBS="$REF_BUILD/src/libparthenon.a $REF_BUILD/Kokkos/containers/src/libkokkoscontainers.a \
+ $REF_BUILD/Kokkos/core/src/libkokkoscore.a $REF_BUILD/Kokkos/simd/src/libkokkossimd.a -ldl -fopenmp -lpthread"
+CXX=/usr/bin/g++
+FLAGS="-O3 -DNDEBUG -std=c++17 -fopenmp -DKOKKOS_DEPENDENCE"
+
+if [ ! -x "$WORK/burgers_dump" ] || [ "$HERE/burgers_dump_main.cpp" -nt "$WORK/burgers_dump" ]; then
+  B=$REF/benchmarks/burgers
+  $CXX $FLAGS $INC -I$B "$HERE/burgers_dump_main.cpp" $B/burgers_driver.cpp \
+     $B/burgers_package.cpp $B/parthenon_app_inputs.cpp $LIBS -o "$WORK/burgers_dump"
+fi
+
+export OMP_NUM_THREADS=${OMP_NUM_THREADS:-8} OMP_PROC_BIND=false
+
+run_burgers () { # name nx nb nscal recon nlim extra...
+  local name=$1 nx=$2 nb=$3 nscal=$4 recon=$5 nlim=$6; shift 6
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  PB2_DUMP_PREFIX="$d/U" "$WORK/burgers_dump" -i "$REF/benchmarks/burgers/burgers.pin" \
+    parthenon/mesh/nx1=$nx parthenon/mesh/nx2=$nx parthenon/mesh/nx3=$nx \
+    parthenon/meshblock/nx1=$nb parthenon/meshblock/nx2=$nb parthenon/meshblock/nx3=$nb \
+    parthenon/mesh/refinement=none parthenon/mesh/numlevel=1 \
+    parthenon/time/nlim=$nlim parthenon/time/tlim=1e9 parthenon/output0/dt=-1 \
+    parthenon/output1/dt=1e-9 burgers/num_scalars=$nscal burgers/recon=$recon "$@" \
+    > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
+  cp "$d/burgers.out1.hst" "$OUT/$name.hst"
+}
+
+# small uniform cases: full fields (ghosts included) after cycles 0..nlim
+run_burgers burgers_u16_b8_s1_weno5   16  8 1 weno5  3
+run_burgers burgers_u16_b8_s1_linear  16  8 1 linear 3 parthenon/mesh/nghost=2
+# history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
+HST_ONLY=1
+run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  PB2_DUMP_PREFIX="$d/U" PB2_NO_DUMP=1 "$REF_BUILD/benchmarks/burgers/burgers-benchmark" \
+    -i "$REF/benchmarks/burgers/burgers.pin" \
+    parthenon/mesh/nx1=$nx parthenon/mesh/nx2=$nx parthenon/mesh/nx3=$nx \
+    parthenon/meshblock/nx1=$nb parthenon/meshblock/nx2=$nb parthenon/meshblock/nx3=$nb \
+    parthenon/mesh/refinement=none parthenon/mesh/numlevel=1 \
+    parthenon/time/nlim=$nlim parthenon/time/tlim=1e9 parthenon/output0/dt=-1 \
+    parthenon/output1/dt=1e-9 > run.log 2>&1
+  cp "$d/burgers.out1.hst" "$OUT/$name.hst"
+}
+run_hst burgers_u64_b32_s8_weno5 64 32 10
+echo "fixtures written to $OUT"
