@@ -1,0 +1,233 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE ONLY — see pb2_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libpb2_oracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "pb2_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        L = _lib
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        L.orc_mesh_create.restype = C.c_void_p
+        L.orc_mesh_create.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, ip]
+        L.orc_mesh_create_uniform.restype = C.c_void_p
+        L.orc_mesh_create_uniform.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp]
+        L.orc_mesh_destroy.argtypes = [C.c_void_p]
+        L.orc_mesh_nblocks.argtypes = [C.c_void_p]
+        L.orc_mesh_multilevel.argtypes = [C.c_void_p]
+        L.orc_mesh_dims.argtypes = [C.c_void_p, ip, ip]
+        L.orc_mesh_block_loc.argtypes = [C.c_void_p, C.c_int, ip]
+        L.orc_mesh_block_bounds.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.orc_mesh_num_neighbors.argtypes = [C.c_void_p, C.c_int]
+        L.orc_mesh_neighbor.argtypes = [C.c_void_p, C.c_int, C.c_int, ip]
+        L.orc_calc_indices.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+        L.orc_exchange.restype = C.c_int64
+        L.orc_exchange.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
+        L.orc_count_regions.restype = C.c_int64
+        L.orc_count_regions.argtypes = [C.c_void_p]
+        L.orc_pack.restype = C.c_int64
+        L.orc_pack.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, C.POINTER(C.c_int64)]
+        L.orc_unpack.argtypes = [C.c_void_p, dp, dp, C.c_int, dp, C.POINTER(C.c_int64)]
+        L.orc_restrict_send.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_restrict_set.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_prolongate.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
+        L.orc_linear.argtypes = [C.c_double] * 3 + [dp, dp]
+        L.orc_lr_to_flux.argtypes = [C.c_double] * 8 + [dp] * 5
+        L.orc_burgers_ic.argtypes = [C.c_void_p, dp, C.c_int]
+        L.orc_burgers_create.restype = C.c_void_p
+        L.orc_burgers_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.orc_burgers_destroy.argtypes = [C.c_void_p]
+        for f in ("orc_burgers_U", "orc_burgers_derived"):
+            getattr(L, f).restype = dp
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_burgers_flux.restype = dp
+        L.orc_burgers_flux.argtypes = [C.c_void_p, C.c_int]
+        L.orc_burgers_init.argtypes = [C.c_void_p]
+        L.orc_burgers_dt.restype = C.c_double
+        L.orc_burgers_dt.argtypes = [C.c_void_p]
+        L.orc_burgers_time.restype = C.c_double
+        L.orc_burgers_time.argtypes = [C.c_void_p]
+        L.orc_burgers_step.argtypes = [C.c_void_p]
+        L.orc_burgers_calculate_fluxes.argtypes = [C.c_void_p, dp]
+        L.orc_burgers_stage.argtypes = [C.c_void_p, C.c_int]
+        L.orc_burgers_history.argtypes = [C.c_void_p, dp]
+        L.orc_burgers_cycle.argtypes = [C.c_void_p]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Mesh:
+    """Single-tree block-structured mesh; leaves=None => uniform root grid."""
+
+    def __init__(self, ndim, nx, ng, nrb, xmin=(-0.5,) * 3, xmax=(0.5,) * 3, leaves=None):
+        L = lib()
+        self.ndim, self.ng = ndim, ng
+        self._nx = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
+        self._nrb = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
+        self._xmin = np.array(xmin, dtype=np.float64)
+        self._xmax = np.array(xmax, dtype=np.float64)
+        if leaves is None:
+            self.h = L.orc_mesh_create_uniform(ndim, _ip(self._nx), ng, _ip(self._nrb),
+                                               _dp(self._xmin), _dp(self._xmax))
+        else:
+            lv = np.ascontiguousarray(leaves, dtype=np.int32)
+            self.h = L.orc_mesh_create(ndim, _ip(self._nx), ng, _ip(self._nrb),
+                                       _dp(self._xmin), _dp(self._xmax), lv.shape[0], _ip(lv))
+        if not self.h:
+            raise ValueError("unsupported mesh")
+        self.nblocks = L.orc_mesh_nblocks(self.h)
+        self.multilevel = bool(L.orc_mesh_multilevel(self.h))
+        d = np.zeros(3, dtype=np.int32)
+        c = np.zeros(3, dtype=np.int32)
+        L.orc_mesh_dims(self.h, _ip(d), _ip(c))
+        self.dims = tuple(int(x) for x in d)    # (nk, nj, ni)
+        self.cdims = tuple(int(x) for x in c)
+
+    def __del__(self):
+        try:
+            lib().orc_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+    def block_loc(self, b):
+        o = np.zeros(4, dtype=np.int32)
+        lib().orc_mesh_block_loc(self.h, b, _ip(o))
+        return tuple(int(x) for x in o)
+
+    def block_bounds(self, b):
+        lo = np.zeros(3)
+        hi = np.zeros(3)
+        lib().orc_mesh_block_bounds(self.h, b, _dp(lo), _dp(hi))
+        return lo, hi
+
+    def neighbors(self, b):
+        out = []
+        o = np.zeros(5, dtype=np.int32)
+        for n in range(lib().orc_mesh_num_neighbors(self.h, b)):
+            lib().orc_mesh_neighbor(self.h, b, n, _ip(o))
+            out.append(tuple(int(x) for x in o))
+        return out
+
+    def calc_indices(self, b, n, ir_type, prores=False):
+        s = np.zeros(3, dtype=np.int32)
+        e = np.zeros(3, dtype=np.int32)
+        lib().orc_calc_indices(self.h, b, n, ir_type, int(prores), _ip(s), _ip(e))
+        return tuple(int(x) for x in s), tuple(int(x) for x in e)
+
+    def field(self, ncomp):
+        return np.zeros((self.nblocks, ncomp) + self.dims)
+
+    def coarse_field(self, ncomp):
+        return np.zeros((self.nblocks, ncomp) + self.cdims)
+
+    def exchange(self, U, Uc=None, prolongate=False):
+        assert U.flags.c_contiguous
+        return lib().orc_exchange(self.h, _dp(U), _dp(Uc) if Uc is not None else None,
+                                  U.shape[1], int(prolongate))
+
+    def pack(self, U, Uc=None):
+        nreg = lib().orc_count_regions(self.h)
+        off = np.zeros(nreg + 1, dtype=np.int64)
+        offp = off.ctypes.data_as(C.POINTER(C.c_int64))
+        ucp = _dp(Uc) if Uc is not None else None
+        total = lib().orc_pack(self.h, _dp(U), ucp, U.shape[1], None, offp)
+        buf = np.zeros(total)
+        lib().orc_pack(self.h, _dp(U), ucp, U.shape[1], _dp(buf), offp)
+        return buf, off
+
+    def unpack(self, U, buf, off, Uc=None):
+        lib().orc_unpack(self.h, _dp(U), _dp(Uc) if Uc is not None else None, U.shape[1],
+                         _dp(buf), off.ctypes.data_as(C.POINTER(C.c_int64)))
+
+    def burgers_ic(self, U):
+        lib().orc_burgers_ic(self.h, _dp(U), U.shape[1])
+
+
+class Burgers:
+    def __init__(self, mesh, num_scalars=8, recon="weno5", cfl=0.8):
+        self.mesh = mesh
+        self.ncomp = 3 + num_scalars
+        self.h = lib().orc_burgers_create(mesh.h, num_scalars, 0 if recon == "weno5" else 1, cfl)
+
+    def __del__(self):
+        try:
+            lib().orc_burgers_destroy(self.h)
+        except Exception:
+            pass
+
+    def _view(self, p, shape):
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array(p, shape=(n,)).reshape(shape)
+
+    @property
+    def U(self):
+        return self._view(lib().orc_burgers_U(self.h),
+                          (self.mesh.nblocks, self.ncomp) + self.mesh.dims)
+
+    @property
+    def derived(self):
+        return self._view(lib().orc_burgers_derived(self.h), (self.mesh.nblocks,) + self.mesh.dims)
+
+    def flux(self, d):
+        return self._view(lib().orc_burgers_flux(self.h, d),
+                          (self.mesh.nblocks, self.ncomp) + self.mesh.dims)
+
+    def init(self):
+        lib().orc_burgers_init(self.h)
+
+    def step(self):
+        lib().orc_burgers_step(self.h)
+
+    def calculate_fluxes(self, U):
+        lib().orc_burgers_calculate_fluxes(self.h, _dp(U))
+
+    @property
+    def dt(self):
+        return lib().orc_burgers_dt(self.h)
+
+    @property
+    def time(self):
+        return lib().orc_burgers_time(self.h)
+
+    def history(self):
+        o = np.zeros(8)
+        lib().orc_burgers_history(self.h, _dp(o))
+        return o
+
+
+def weno5z(q):
+    ql, qr = C.c_double(), C.c_double()
+    lib().orc_weno5z(*[float(x) for x in q], C.byref(ql), C.byref(qr))
+    return ql.value, qr.value

@@ -1,0 +1,1109 @@
+/* pb2_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).  See pb2_oracle.h.
+ *
+ * Plain-C restatement of the reference's ghost-zone hot path: mesh topology for a
+ * single-tree forest, boundary index boxes, pack/unpack, restriction/prolongation at
+ * fine-coarse boundaries, and the benchmarks/burgers RK2 cycle.  Cell-centred fields only.
+ * Must be compiled with -ffp-contract=off (the reference CPU build emits no FMAs).
+ */
+#include "pb2_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXNB 64
+
+typedef struct {
+  int level;
+  long lx[3];
+} Loc;
+
+typedef struct {
+  int gid;
+  Loc loc;        /* wrapped location (as stored in the tree) */
+  Loc origin_loc; /* location in the frame of the owning block (may lie outside) */
+  int off[3];
+} Neighbor;
+
+typedef struct {
+  Loc loc;
+  int nnb;
+  Neighbor nb[MAXNB];
+  double xmin[3], xmax[3]; /* interior bounds */
+  double dx[3];            /* UniformCartesian dx_ */
+  double cxmin[3];         /* UniformCartesian xmin_ (includes ghost offset) */
+  double ccxmin[3], cdx[3]; /* coarse coords (uniform_cartesian.hpp:41-55) */
+} Block;
+
+struct OrcMesh {
+  int ndim, nx[3], ng, nrb[3], root_level, nblocks, multilevel;
+  int periodic[3];
+  double xmin[3], xmax[3];
+  int is[3], ie[3], n[3];    /* fine interior bounds and full extents (i,j,k order) */
+  int cis[3], cie[3], cn[3]; /* coarse */
+  Block *blocks;
+};
+
+/* ------------------------------------------------------------------------------------ */
+/* topology */
+
+/* src/mesh/forest/logical_location.cpp:61-74 */
+static double index_to_symmetrized_coordinate(long index, int bloc, long nrange) {
+  long noffset = index - nrange / 2;
+  long noffset_ceil = index - (nrange + 1) / 2;
+  return (double)(noffset + noffset_ceil + (long)bloc) / (2.0 * (double)nrange);
+}
+/* src/defs.hpp:98-101 */
+static double logical_to_actual(double u, double xmin, double xmax) {
+  return 0.5 * (xmin + xmax) + (u * xmax - u * xmin);
+}
+
+/* z-order key; src/utils/morton_number.hpp:43 (x in the lowest interleaved bit) */
+static uint64_t morton_key(const Loc *l, int maxlevel) {
+  uint64_t key = 0;
+  int sh = maxlevel - l->level;
+  for (int bit = 0; bit < maxlevel; ++bit)
+    for (int d = 0; d < 3; ++d) {
+      uint64_t c = ((uint64_t)l->lx[d]) << sh;
+      key |= ((c >> bit) & 1ull) << (3 * bit + d);
+    }
+  return key;
+}
+
+typedef struct {
+  uint64_t key;
+  Loc loc;
+} SortEnt;
+static int cmp_ent(const void *a, const void *b) {
+  const SortEnt *x = (const SortEnt *)a, *y = (const SortEnt *)b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return x->loc.level - y->loc.level;
+}
+
+static int find_leaf(const OrcMesh *m, const Loc *l) {
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Loc *q = &m->blocks[b].loc;
+    if (q->level == l->level && q->lx[0] == l->lx[0] && q->lx[1] == l->lx[1] &&
+        q->lx[2] == l->lx[2])
+      return b;
+  }
+  return -1;
+}
+/* is `l` an internal node, i.e. does some leaf lie strictly below it */
+static int is_internal(const OrcMesh *m, const Loc *l) {
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Loc *q = &m->blocks[b].loc;
+    if (q->level <= l->level) continue;
+    int sh = q->level - l->level;
+    if ((q->lx[0] >> sh) == l->lx[0] && (q->lx[1] >> sh) == l->lx[1] &&
+        (q->lx[2] >> sh) == l->lx[2])
+      return 1;
+  }
+  return 0;
+}
+
+static long nblocks_at(const OrcMesh *m, int level, int d) {
+  /* number of blocks spanning the tree in direction d at `level`; the single tree
+   * covers nrb root blocks at root_level */
+  if (d >= m->ndim) return 1;
+  return ((long)m->nrb[d]) << (level - m->root_level);
+}
+
+/* wrap an out-of-tree same-level location through the periodic boundary; returns 0 if
+ * it falls outside a non-periodic boundary */
+static int wrap_loc(const OrcMesh *m, const Loc *in, Loc *out) {
+  *out = *in;
+  for (int d = 0; d < 3; ++d) {
+    long n = nblocks_at(m, in->level, d);
+    if (in->lx[d] < 0 || in->lx[d] >= n) {
+      if (d >= m->ndim || !m->periodic[d]) return 0;
+      out->lx[d] = ((in->lx[d] % n) + n) % n;
+    }
+  }
+  return 1;
+}
+
+/* src/mesh/forest/logical_location.cpp:110-129 (on unwrapped coordinates) */
+static int is_neighbor(const Loc *a, const Loc *in) {
+  int max_level = a->level > in->level ? a->level : in->level;
+  long bs_in = 1L << (max_level - in->level), bs_this = 1L << (max_level - a->level);
+  for (int d = 0; d < 3; ++d) {
+    long low = a->lx[d] * bs_this - 1, hi = low + bs_this + 1;
+    long low_in = in->lx[d] * bs_in, hi_in = low_in + bs_in - 1;
+    if (hi < low_in || low > hi_in) return 0;
+  }
+  return 1;
+}
+
+static long floor_shift(long v, int sh) { return v >> sh; /* arithmetic shift */ }
+
+/* src/mesh/forest/logical_location.cpp:98-108 */
+static void same_level_offsets(const Loc *me, const Loc *nb, int off[3]) {
+  int sn = nb->level - me->level > 0 ? nb->level - me->level : 0;
+  int sm = me->level - nb->level > 0 ? me->level - nb->level : 0;
+  for (int d = 0; d < 3; ++d)
+    off[d] = (int)(floor_shift(nb->lx[d], sn) - floor_shift(me->lx[d], sm));
+}
+
+static void add_neighbor(const OrcMesh *m, Block *blk, int gid, const Loc *wrapped,
+                         const Loc *origin) {
+  if (blk->nnb >= MAXNB) {
+    fprintf(stderr, "oracle: too many neighbors\n");
+    abort();
+  }
+  Neighbor *nb = &blk->nb[blk->nnb++];
+  nb->gid = gid;
+  nb->loc = *wrapped;
+  nb->origin_loc = *origin;
+  same_level_offsets(&blk->loc, origin, nb->off); /* mesh-gmg.cpp:64 */
+  (void)m;
+}
+
+/* src/mesh/forest/tree.cpp:139-226 (leaf grid) */
+static void find_neighbors(OrcMesh *m, int b) {
+  Block *blk = &m->blocks[b];
+  const Loc *loc = &blk->loc;
+  blk->nnb = 0;
+  /* Indexer3D: first index (ox1) slowest?  tree.cpp:141-148 iterates offsets(o) over a
+   * 3D indexer built as ({ox1 range},{ox2 range},{ox3 range}) whose LAST entry varies
+   * fastest (indexer.hpp:117-144). */
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = d < m->ndim ? -1 : 0;
+    hi[d] = d < m->ndim ? 1 : 0;
+  }
+  for (int o1 = lo[0]; o1 <= hi[0]; ++o1)
+    for (int o2 = lo[1]; o2 <= hi[1]; ++o2)
+      for (int o3 = lo[2]; o3 <= hi[2]; ++o3) {
+        if (o1 == 0 && o2 == 0 && o3 == 0) continue;
+        Loc neigh = *loc, w;
+        neigh.lx[0] += o1;
+        neigh.lx[1] += o2;
+        neigh.lx[2] += o3;
+        if (!wrap_loc(m, &neigh, &w)) continue;
+        int g = find_leaf(m, &w);
+        if (g >= 0) {
+          add_neighbor(m, blk, g, &w, &neigh);
+        } else if (is_internal(m, &w)) {
+          /* daughters of the (unwrapped) neighbor that touch this block */
+          int nd[3] = {m->ndim > 0 ? 2 : 1, m->ndim > 1 ? 2 : 1, m->ndim > 2 ? 2 : 1};
+          /* GetDaughters order: logical_location.cpp (ox3 outer, ox2, ox1 inner) */
+          for (int d3 = 0; d3 < nd[2]; ++d3)
+            for (int d2 = 0; d2 < nd[1]; ++d2)
+              for (int d1 = 0; d1 < nd[0]; ++d1) {
+                Loc dn, dw;
+                dn.level = neigh.level + 1;
+                dn.lx[0] = (neigh.lx[0] << 1) + d1;
+                dn.lx[1] = m->ndim > 1 ? (neigh.lx[1] << 1) + d2 : neigh.lx[1];
+                dn.lx[2] = m->ndim > 2 ? (neigh.lx[2] << 1) + d3 : neigh.lx[2];
+                if (m->ndim < 2) dn.lx[1] = 0;
+                if (m->ndim < 3) dn.lx[2] = 0;
+                if (!is_neighbor(loc, &dn)) continue;
+                wrap_loc(m, &dn, &dw);
+                int gd = find_leaf(m, &dw);
+                if (gd < 0) {
+                  fprintf(stderr, "oracle: mesh violates 2:1 nesting\n");
+                  abort();
+                }
+                add_neighbor(m, blk, gd, &dw, &dn);
+              }
+        } else {
+          /* coarser neighbor: parent of neigh */
+          Loc par = neigh, pw;
+          par.level = neigh.level - 1;
+          for (int d = 0; d < 3; ++d) par.lx[d] = floor_shift(neigh.lx[d], 1);
+          if (m->ndim < 2) par.lx[1] = 0;
+          if (m->ndim < 3) par.lx[2] = 0;
+          if (!wrap_loc(m, &par, &pw)) continue;
+          int gp = find_leaf(m, &pw);
+          if (gp < 0) continue;
+          int so[3];
+          same_level_offsets(loc, &par, so);
+          if (so[0] == o1 && so[1] == o2 && so[2] == o3) add_neighbor(m, blk, gp, &pw, &par);
+        }
+      }
+}
+
+OrcMesh *orc_mesh_create(int ndim, const int nx[3], int ng, const int nrb[3],
+                         const double xmin[3], const double xmax[3], int nleaf,
+                         const int *leaves) {
+  OrcMesh *m = (OrcMesh *)calloc(1, sizeof(OrcMesh));
+  m->ndim = ndim;
+  m->ng = ng;
+  int maxrb = 1;
+  for (int d = 0; d < 3; ++d) {
+    m->nx[d] = d < ndim ? nx[d] : 1;
+    m->nrb[d] = d < ndim ? nrb[d] : 1;
+    m->xmin[d] = xmin[d];
+    m->xmax[d] = xmax[d];
+    m->periodic[d] = 1;
+    if (m->nrb[d] > maxrb) maxrb = m->nrb[d];
+  }
+  /* single tree: all non-symmetry directions must hold the same power-of-two number of
+   * root blocks (forest.cpp:73-105: ntree = nblock / max common power-of-2 divisor) */
+  int rl = 0;
+  while ((1 << rl) < maxrb) ++rl;
+  for (int d = 0; d < ndim; ++d)
+    if (m->nrb[d] != (1 << rl)) {
+      fprintf(stderr, "oracle: only single-tree (2^n cubed root grid) meshes supported\n");
+      free(m);
+      return NULL;
+    }
+  m->root_level = rl;
+  m->nblocks = nleaf;
+  m->blocks = (Block *)calloc((size_t)nleaf, sizeof(Block));
+  SortEnt *ent = (SortEnt *)malloc(sizeof(SortEnt) * (size_t)nleaf);
+  int maxlevel = 0;
+  for (int i = 0; i < nleaf; ++i)
+    if (leaves[4 * i] > maxlevel) maxlevel = leaves[4 * i];
+  for (int i = 0; i < nleaf; ++i) {
+    ent[i].loc.level = leaves[4 * i];
+    for (int d = 0; d < 3; ++d) ent[i].loc.lx[d] = leaves[4 * i + 1 + d];
+    ent[i].key = morton_key(&ent[i].loc, maxlevel);
+    if (ent[i].loc.level != rl) m->multilevel = 1;
+  }
+  qsort(ent, (size_t)nleaf, sizeof(SortEnt), cmp_ent);
+  for (int d = 0; d < 3; ++d) {
+    int sym = d >= ndim;
+    m->is[d] = sym ? 0 : ng;
+    m->ie[d] = sym ? 0 : ng + m->nx[d] - 1;
+    m->n[d] = sym ? 1 : m->nx[d] + 2 * ng;
+    int cnx = sym ? 0 : (m->nx[d] / 2 > 1 ? m->nx[d] / 2 : 1); /* meshblock.cpp:204-216 */
+    m->cis[d] = sym ? 0 : ng;
+    m->cie[d] = sym ? 0 : ng + cnx - 1;
+    m->cn[d] = sym ? 1 : cnx + 2 * ng;
+  }
+  for (int b = 0; b < nleaf; ++b) {
+    Block *blk = &m->blocks[b];
+    blk->loc = ent[b].loc;
+    for (int d = 0; d < 3; ++d) {
+      if (d < ndim) {
+        /* tree.cpp:297-312 + logical_location.cpp:76-79 */
+        long nb_tot = 1L << (blk->loc.level > 0 ? blk->loc.level : 0);
+        /* the tree domain equals the mesh domain (single tree) */
+        double ul = index_to_symmetrized_coordinate(blk->loc.lx[d], 0, nb_tot);
+        double ur = index_to_symmetrized_coordinate(blk->loc.lx[d], 2, nb_tot);
+        blk->xmin[d] = logical_to_actual(ul, xmin[d], xmax[d]);
+        blk->xmax[d] = logical_to_actual(ur, xmin[d], xmax[d]);
+      } else {
+        blk->xmin[d] = xmin[d];
+        blk->xmax[d] = xmax[d];
+      }
+      /* uniform_cartesian.hpp:30-40 */
+      blk->dx[d] = (blk->xmax[d] - blk->xmin[d]) / m->nx[d];
+      int istart = d < ndim ? ng : 0;
+      blk->cxmin[d] = blk->xmin[d] - istart * blk->dx[d];
+      /* uniform_cartesian.hpp:41-55, coarsen = 2 */
+      blk->ccxmin[d] = blk->cxmin[d] + istart * blk->dx[d] * (1 - 2);
+      blk->cdx[d] = blk->dx[d] * ((d == 0 || istart > 0) ? 2 : 1);
+    }
+  }
+  free(ent);
+  for (int b = 0; b < nleaf; ++b) find_neighbors(m, b);
+  return m;
+}
+
+OrcMesh *orc_mesh_create_uniform(int ndim, const int nx[3], int ng, const int nrb[3],
+                                 const double xmin[3], const double xmax[3]) {
+  int n[3] = {nrb[0], ndim > 1 ? nrb[1] : 1, ndim > 2 ? nrb[2] : 1};
+  int nleaf = n[0] * n[1] * n[2];
+  int rl = 0;
+  while ((1 << rl) < n[0]) ++rl;
+  int *leaves = (int *)malloc(sizeof(int) * 4 * (size_t)nleaf);
+  int c = 0;
+  for (int k = 0; k < n[2]; ++k)
+    for (int j = 0; j < n[1]; ++j)
+      for (int i = 0; i < n[0]; ++i) {
+        leaves[4 * c] = rl;
+        leaves[4 * c + 1] = i;
+        leaves[4 * c + 2] = j;
+        leaves[4 * c + 3] = k;
+        ++c;
+      }
+  OrcMesh *m = orc_mesh_create(ndim, nx, ng, nrb, xmin, xmax, nleaf, leaves);
+  free(leaves);
+  return m;
+}
+
+void orc_mesh_destroy(OrcMesh *m) {
+  if (!m) return;
+  free(m->blocks);
+  free(m);
+}
+int orc_mesh_nblocks(const OrcMesh *m) { return m->nblocks; }
+int orc_mesh_multilevel(const OrcMesh *m) { return m->multilevel; }
+void orc_mesh_dims(const OrcMesh *m, int dims[3], int cdims[3]) {
+  for (int d = 0; d < 3; ++d) {
+    dims[d] = m->n[2 - d];
+    cdims[d] = m->cn[2 - d];
+  }
+}
+void orc_mesh_block_loc(const OrcMesh *m, int b, int loc[4]) {
+  loc[0] = m->blocks[b].loc.level;
+  for (int d = 0; d < 3; ++d) loc[1 + d] = (int)m->blocks[b].loc.lx[d];
+}
+void orc_mesh_block_bounds(const OrcMesh *m, int b, double xmin[3], double xmax[3]) {
+  for (int d = 0; d < 3; ++d) {
+    xmin[d] = m->blocks[b].xmin[d];
+    xmax[d] = m->blocks[b].xmax[d];
+  }
+}
+int orc_mesh_num_neighbors(const OrcMesh *m, int b) { return m->blocks[b].nnb; }
+void orc_mesh_neighbor(const OrcMesh *m, int b, int n, int out[5]) {
+  const Neighbor *nb = &m->blocks[b].nb[n];
+  out[0] = nb->gid;
+  out[1] = nb->loc.level;
+  out[2] = nb->off[0];
+  out[3] = nb->off[1];
+  out[4] = nb->off[2];
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* index boxes: src/bvals/comms/bnd_info.cpp:105-252, cell centred (top_offset = 0),
+ * non-flux, identity logical coordinate transform, full ownership. */
+enum { IR_SEND = 0, IR_RECV = 1 };
+
+void orc_calc_indices(const OrcMesh *m, int b, int n, int ir_type, int prores, int s[3],
+                      int e[3]) {
+  const Block *blk = &m->blocks[b];
+  const Neighbor *nb = &blk->nb[n];
+  const Loc *loc = &blk->loc;
+  const int ng = m->ng;
+  int use_coarse = prores || nb->loc.level < loc->level; /* :124-125 */
+  int bs[3], be[3], nbs[3], nbe[3];
+  int coarse_fac = nb->loc.level > loc->level ? 2 : 1; /* :130 */
+  for (int d = 0; d < 3; ++d) {
+    bs[d] = use_coarse ? m->cis[d] : m->is[d];
+    be[d] = use_coarse ? m->cie[d] : m->ie[d];
+    /* neighbor_shape = IndexShape(nb.block_size.nx / coarse_fac, nghost)  :131-135 */
+    int sym = d >= m->ndim;
+    int nnx = m->nx[d] / coarse_fac;
+    nbs[d] = sym ? 0 : ng;
+    nbe[d] = sym ? 0 : ng + nnx - 1;
+    if (sym) nbe[d] = 0;
+  }
+  int interior_offset = ir_type == IR_SEND ? ng : 0; /* :157-160 */
+  int exterior_offset = ir_type == IR_RECV ? ng : 0;
+  if (prores) exterior_offset /= 2; /* :161-166 */
+  for (int d = 0; d < 3; ++d) {
+    int not_sym = d < m->ndim;
+    if (nb->off[d] == 0) {
+      s[d] = bs[d];
+      e[d] = be[d];
+      if (loc->level < nb->origin_loc.level && not_sym) { /* :173-192 */
+        int extra = (be[d] - bs[d] + 1) - (nbe[d] - nbs[d] + 1);
+        s[d] += (nb->origin_loc.lx[d] % 2 + 2) % 2 == 1 ? extra - interior_offset : 0;
+        e[d] -= (nb->origin_loc.lx[d] % 2 + 2) % 2 == 0 ? extra - interior_offset : 0;
+      }
+      if (loc->level > nb->origin_loc.level && not_sym) { /* :193-204 */
+        s[d] -= loc->lx[d] % 2 == 1 ? exterior_offset : 0;
+        e[d] += loc->lx[d] % 2 == 0 ? exterior_offset : 0;
+      }
+    } else if (nb->off[d] > 0) { /* :211-214 */
+      s[d] = be[d] + (-interior_offset + 1);
+      e[d] = be[d] + exterior_offset;
+    } else { /* :215-218 */
+      s[d] = bs[d] - exterior_offset;
+      e[d] = bs[d] + (interior_offset - 1);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* exchange */
+
+static inline size_t fidx(const OrcMesh *m, int ncomp, int b, int c, int k, int j, int i) {
+  return ((((size_t)b * ncomp + c) * m->n[2] + k) * m->n[1] + j) * m->n[0] + i;
+}
+static inline size_t cidx(const OrcMesh *m, int ncomp, int b, int c, int k, int j, int i) {
+  return ((((size_t)b * ncomp + c) * m->cn[2] + k) * m->cn[1] + j) * m->cn[0] + i;
+}
+
+int64_t orc_count_regions(const OrcMesh *m) {
+  int64_t n = 0;
+  for (int b = 0; b < m->nblocks; ++b) n += m->blocks[b].nnb;
+  return n;
+}
+
+/* RestrictAverage::Do  src/prolong_restrict/pr_ops.hpp:105-165 (cell centred, DIM =
+ * m->ndim).  Volumes are the (constant) fine cell volume of the block. */
+static void restrict_cell(const OrcMesh *m, const double *U, double *Uc, int ncomp, int b,
+                          int c, int ck, int cj, int ci) {
+  const Block *blk = &m->blocks[b];
+  const int DIM = m->ndim;
+  const int i = (ci - m->cis[0]) * 2 + m->is[0];
+  const int j = DIM > 1 ? (cj - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int k = DIM > 2 ? (ck - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  double vol[2][2][2], terms[2][2][2];
+  memset(vol, 0, sizeof(vol));
+  memset(terms, 0, sizeof(terms));
+  const double cellvol = blk->dx[0] * blk->dx[1] * blk->dx[2]; /* uniform_cartesian.hpp:39 */
+  for (int ok = 0; ok < 1 + (DIM > 2); ++ok)
+    for (int oj = 0; oj < 1 + (DIM > 1); ++oj)
+      for (int oi = 0; oi < 2; ++oi) {
+        vol[ok][oj][oi] = cellvol;
+        terms[ok][oj][oi] = vol[ok][oj][oi] * U[fidx(m, ncomp, b, c, k + ok, j + oj, i + oi)];
+      }
+  const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                      ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+  Uc[cidx(m, ncomp, b, c, ck, cj, ci)] =
+      (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+       ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+      tvol;
+}
+
+static void restrict_region(const OrcMesh *m, const double *U, double *Uc, int ncomp, int b,
+                            const int s[3], const int e[3]) {
+  for (int c = 0; c < ncomp; ++c)
+    for (int k = s[2]; k <= e[2]; ++k)
+      for (int j = s[1]; j <= e[1]; ++j)
+        for (int i = s[0]; i <= e[0]; ++i) restrict_cell(m, U, Uc, ncomp, b, c, k, j, i);
+}
+
+/* ProResInfo::GetSend (bnd_info.cpp:387-403) + refinement::Restrict called from
+ * SendBoundBufs (boundary_communication.cpp:82-87) */
+void orc_restrict_send(const OrcMesh *m, const double *U, double *Uc, int ncomp) {
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      if (blk->nb[n].origin_loc.level < blk->loc.level) {
+        int s[3], e[3];
+        orc_calc_indices(m, b, n, IR_SEND, 1, s, e);
+        restrict_region(m, U, Uc, ncomp, b, s, e);
+      }
+    }
+  }
+}
+
+/* pack kernel: boundary_communication.cpp:95-140; region source selection
+ * bnd_info.cpp:285-289 (coarse buffer if the neighbor is coarser) */
+int64_t orc_pack(const OrcMesh *m, const double *U, const double *Uc, int ncomp,
+                 double *buf, int64_t *buf_off) {
+  int64_t off = 0, r = 0;
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_SEND, 0, s, e);
+      buf_off[r++] = off;
+      off += (int64_t)ncomp * (e[2] - s[2] + 1) * (e[1] - s[1] + 1) * (e[0] - s[0] + 1);
+    }
+  }
+  buf_off[r] = off;
+  if (!buf) return off;
+  int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
+  first[0] = 0;
+  for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_SEND, 0, s, e);
+      int coarse = blk->nb[n].origin_loc.level < blk->loc.level;
+      double *p = buf + buf_off[first[b] + n];
+      for (int c = 0; c < ncomp; ++c)
+        for (int k = s[2]; k <= e[2]; ++k)
+          for (int j = s[1]; j <= e[1]; ++j)
+            for (int i = s[0]; i <= e[0]; ++i)
+              *p++ = coarse ? Uc[cidx(m, ncomp, b, c, k, j, i)]
+                            : U[fidx(m, ncomp, b, c, k, j, i)];
+    }
+  }
+  free(first);
+  return off;
+}
+
+/* unpack kernel: boundary_communication.cpp:273-334; the sending buffer is the one keyed
+ * (sender gid, receiver gid, reverse offset index): bvals_utils.hpp:43-67 */
+void orc_unpack(const OrcMesh *m, double *U, double *Uc, int ncomp, const double *buf,
+                const int64_t *buf_off) {
+  int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
+  first[0] = 0;
+  for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      /* find the sender's matching region */
+      const Block *sb = &m->blocks[nb->gid];
+      int sn = -1;
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          sn = q;
+          break;
+        }
+      if (sn < 0) {
+        fprintf(stderr, "oracle: no matching send region for block %d nb %d\n", b, n);
+        abort();
+      }
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 0, s, e);
+      int64_t r = first[nb->gid] + sn;
+      int64_t cnt = (int64_t)ncomp * (e[2] - s[2] + 1) * (e[1] - s[1] + 1) * (e[0] - s[0] + 1);
+      if (cnt != buf_off[r + 1] - buf_off[r]) {
+        fprintf(stderr, "oracle: send/recv size mismatch block %d nb %d: %ld vs %ld\n", b, n,
+                (long)cnt, (long)(buf_off[r + 1] - buf_off[r]));
+        abort();
+      }
+      int coarse = nb->origin_loc.level < blk->loc.level;
+      const double *p = buf + buf_off[r];
+      for (int c = 0; c < ncomp; ++c)
+        for (int k = s[2]; k <= e[2]; ++k)
+          for (int j = s[1]; j <= e[1]; ++j)
+            for (int i = s[0]; i <= e[0]; ++i) {
+              if (coarse)
+                Uc[cidx(m, ncomp, b, c, k, j, i)] = *p++;
+              else
+                U[fidx(m, ncomp, b, c, k, j, i)] = *p++;
+            }
+    }
+  }
+  free(first);
+}
+
+/* ProResInfo::GetSet (bnd_info.cpp:405-448) restriction part + SetBounds :338-346 */
+void orc_restrict_set(const OrcMesh *m, const double *U, double *Uc, int ncomp) {
+  if (!m->multilevel) return;
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    int restricted = 0;
+    if (blk->loc.level > 0)
+      for (int n = 0; n < blk->nnb; ++n)
+        restricted = restricted || (blk->nb[n].origin_loc.level == blk->loc.level - 1);
+    if (!restricted) continue;
+    for (int n = 0; n < blk->nnb; ++n) {
+      if (blk->nb[n].origin_loc.level < blk->loc.level) continue;
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 1, s, e);
+      restrict_region(m, U, Uc, ncomp, b, s, e);
+    }
+  }
+}
+
+static inline double sgn(double x) { return (x > 0) - (x < 0); } /* utils/utils.hpp SIGN */
+
+/* util::GradMinMod pr_ops.hpp:95-101 */
+static inline double grad_minmod(double fc, double fm, double fp, double dxm, double dxp) {
+  double gxm = (fc - fm) / dxm;
+  double gxp = (fp - fc) / dxp;
+  return 0.5 * (sgn(gxm) + sgn(gxp)) * fmin(fabs(gxm), fabs(gxp));
+}
+
+/* ProlongateSharedGeneral<true,false>::Do pr_ops.hpp:167-280 (MinMod, cell centred) with
+ * util::GetGridSpacings pr_ops.hpp:76-93 */
+static void prolongate_cell(const OrcMesh *m, double *U, const double *Uc, int ncomp, int b,
+                            int c, int k, int j, int i) {
+  const Block *blk = &m->blocks[b];
+  const int DIM = m->ndim;
+  const int fi = (i - m->cis[0]) * 2 + m->is[0];
+  const int fj = DIM > 1 ? (j - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int fk = DIM > 2 ? (k - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  const double fc = Uc[cidx(m, ncomp, b, c, k, j, i)];
+  double g[3] = {0, 0, 0}, dxfm[3] = {0, 0, 0}, dxfp[3] = {0, 0, 0};
+  const int cc[3] = {i, j, k}, ff[3] = {fi, fj, fk};
+  for (int d = 0; d < DIM; ++d) {
+    const double xm = blk->ccxmin[d] + ((cc[d] - 1) + 0.5) * blk->cdx[d];
+    const double xc = blk->ccxmin[d] + (cc[d] + 0.5) * blk->cdx[d];
+    const double xp = blk->ccxmin[d] + ((cc[d] + 1) + 0.5) * blk->cdx[d];
+    const double dxm = xc - xm, dxp = xp - xc;
+    const double fxm = blk->cxmin[d] + (ff[d] + 0.5) * blk->dx[d];
+    const double fxp = blk->cxmin[d] + ((ff[d] + 1) + 0.5) * blk->dx[d];
+    dxfm[d] = xc - fxm;
+    dxfp[d] = fxp - xc;
+    int o[3] = {0, 0, 0};
+    o[d] = 1;
+    const double fm = Uc[cidx(m, ncomp, b, c, k - o[2], j - o[1], i - o[0])];
+    const double fp = Uc[cidx(m, ncomp, b, c, k + o[2], j + o[1], i + o[0])];
+    g[d] = grad_minmod(fc, fm, fp, dxm, dxp);
+  }
+  const double gx1m = g[0], gx1p = g[0], gx2m = g[1], gx2p = g[1], gx3m = g[2], gx3p = g[2];
+  const double dx1fm = dxfm[0], dx1fp = dxfp[0], dx2fm = dxfm[1], dx2fp = dxfp[1],
+               dx3fm = dxfm[2], dx3fp = dxfp[2];
+  U[fidx(m, ncomp, b, c, fk, fj, fi)] = fc - (gx1m * dx1fm + gx2m * dx2fm + gx3m * dx3fm);
+  U[fidx(m, ncomp, b, c, fk, fj, fi + 1)] =
+      fc + (gx1p * dx1fp - gx2m * dx2fm - gx3m * dx3fm);
+  if (DIM > 1) {
+    U[fidx(m, ncomp, b, c, fk, fj + 1, fi)] =
+        fc - (gx1m * dx1fm - gx2p * dx2fp + gx3m * dx3fm);
+    U[fidx(m, ncomp, b, c, fk, fj + 1, fi + 1)] =
+        fc + (gx1p * dx1fp + gx2p * dx2fp - gx3m * dx3fm);
+  }
+  if (DIM > 2) {
+    U[fidx(m, ncomp, b, c, fk + 1, fj, fi)] =
+        fc - (gx1m * dx1fm + gx2m * dx2fm - gx3p * dx3fp);
+    U[fidx(m, ncomp, b, c, fk + 1, fj, fi + 1)] =
+        fc + (gx1p * dx1fp - gx2m * dx2fm + gx3p * dx3fp);
+    U[fidx(m, ncomp, b, c, fk + 1, fj + 1, fi)] =
+        fc - (gx1m * dx1fm - gx2p * dx2fp - gx3p * dx3fp);
+    U[fidx(m, ncomp, b, c, fk + 1, fj + 1, fi + 1)] =
+        fc + (gx1p * dx1fp + gx2p * dx2fp + gx3p * dx3fp);
+  }
+}
+
+/* ProlongateBounds boundary_communication.cpp:361-393 over GetSet regions whose
+ * neighbor is coarser (bnd_info.cpp:421-446) */
+void orc_prolongate(const OrcMesh *m, double *U, const double *Uc, int ncomp) {
+  if (!m->multilevel) return;
+#pragma omp parallel for schedule(dynamic)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      if (!(blk->nb[n].origin_loc.level < blk->loc.level)) continue;
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 1, s, e);
+      for (int c = 0; c < ncomp; ++c)
+        for (int k = s[2]; k <= e[2]; ++k)
+          for (int j = s[1]; j <= e[1]; ++j)
+            for (int i = s[0]; i <= e[0]; ++i) prolongate_cell(m, U, Uc, ncomp, b, c, k, j, i);
+    }
+  }
+}
+
+int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int prolongate) {
+  int64_t nreg = orc_count_regions(m);
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
+  int64_t total = orc_pack(m, U, Uc, ncomp, NULL, off);
+  double *buf = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
+  if (m->multilevel) orc_restrict_send(m, U, Uc, ncomp);
+  orc_pack(m, U, Uc, ncomp, buf, off);
+  orc_unpack(m, U, Uc, ncomp, buf, off);
+  orc_restrict_set(m, U, Uc, ncomp);
+  if (prolongate) orc_prolongate(m, U, Uc, ncomp);
+  free(buf);
+  free(off);
+  return total;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* burgers: benchmarks/burgers/recon.hpp, burgers_package.{hpp,cpp} */
+
+#define ORC_EPS (10.0 * DBL_EPSILON) /* src/utils/robust.hpp:39-42 */
+
+/* recon.hpp:27-32 */
+static inline double mc(double dm, double dp) {
+  const double dc = (dm * dp > 0.0) * 0.5 * (dm + dp);
+  return copysign(fmin(fabs(dc), 2.0 * fmin(fabs(dm), fabs(dp))), dc);
+}
+
+/* recon.hpp:34-40 */
+void orc_linear(double qm, double q0, double qp, double *ql, double *qr) {
+  double dq = qp - q0;
+  dq = 0.5 * mc(q0 - qm, dq);
+  *ql = q0 + dq;
+  *qr = q0 - dq;
+}
+
+/* recon.hpp:42-99 */
+void orc_weno5z(double q0, double q1, double q2, double q3, double q4, double *pql,
+                double *pqr) {
+  static const double w5alpha[3][3] = {{1.0 / 3.0, -7.0 / 6.0, 11.0 / 6.0},
+                                       {-1.0 / 6.0, 5.0 / 6.0, 1.0 / 3.0},
+                                       {1.0 / 3.0, 5.0 / 6.0, -1.0 / 6.0}};
+  static const double w5gamma[3] = {0.1, 0.6, 0.3};
+  const double eps = ORC_EPS;
+  const double thirteen_thirds = 13.0 / 3.0;
+  double ql, qr;
+
+  double a = q0 - 2 * q1 + q2;
+  double b = q0 - 4.0 * q1 + 3.0 * q2;
+  double beta0 = thirteen_thirds * a * a + b * b + eps;
+  a = q1 - 2.0 * q2 + q3;
+  b = q3 - q1;
+  double beta1 = thirteen_thirds * a * a + b * b + eps;
+  a = q2 - 2.0 * q3 + q4;
+  b = q4 - 4.0 * q3 + 3.0 * q2;
+  double beta2 = thirteen_thirds * a * a + b * b + eps;
+  const double tau5 = fabs(beta2 - beta0);
+
+  beta0 = (beta0 + tau5) / beta0;
+  beta1 = (beta1 + tau5) / beta1;
+  beta2 = (beta2 + tau5) / beta2;
+
+  double w0 = w5gamma[0] * beta0 + eps;
+  double w1 = w5gamma[1] * beta1 + eps;
+  double w2 = w5gamma[2] * beta2 + eps;
+  double wsum = 1.0 / (w0 + w1 + w2);
+  ql = w0 * (w5alpha[0][0] * q0 + w5alpha[0][1] * q1 + w5alpha[0][2] * q2);
+  ql += w1 * (w5alpha[1][0] * q1 + w5alpha[1][1] * q2 + w5alpha[1][2] * q3);
+  ql += w2 * (w5alpha[2][0] * q2 + w5alpha[2][1] * q3 + w5alpha[2][2] * q4);
+  ql *= wsum;
+  const double alpha_l =
+      3.0 * wsum * w0 * w1 * w2 /
+          (w5gamma[2] * w0 * w1 + w5gamma[1] * w0 * w2 + w5gamma[0] * w1 * w2) +
+      eps;
+
+  w0 = w5gamma[0] * beta2 + eps;
+  w1 = w5gamma[1] * beta1 + eps;
+  w2 = w5gamma[2] * beta0 + eps;
+  wsum = 1.0 / (w0 + w1 + w2);
+  qr = w0 * (w5alpha[0][0] * q4 + w5alpha[0][1] * q3 + w5alpha[0][2] * q2);
+  qr += w1 * (w5alpha[1][0] * q3 + w5alpha[1][1] * q2 + w5alpha[1][2] * q1);
+  qr += w2 * (w5alpha[2][0] * q2 + w5alpha[2][1] * q1 + w5alpha[2][2] * q0);
+  qr *= wsum;
+  const double alpha_r =
+      3.0 * wsum * w0 * w1 * w2 /
+          (w5gamma[2] * w0 * w1 + w5gamma[1] * w0 * w2 + w5gamma[0] * w1 * w2) +
+      eps;
+
+  double dq = q3 - q2;
+  dq = 0.5 * mc(q2 - q1, dq);
+
+  const double alpha_lin = 2.0 * alpha_l * alpha_r / (alpha_l + alpha_r);
+  ql = alpha_lin * ql + (1.0 - alpha_lin) * (q2 + dq);
+  qr = alpha_lin * qr + (1.0 - alpha_lin) * (q2 - dq);
+  *pql = ql;
+  *pqr = qr;
+}
+
+/* burgers_package.hpp:31-43 */
+void orc_lr_to_flux(double uxl, double uxr, double uyl, double uyr, double uzl,
+                    double uzr, double upl, double upr, double *psl, double *psr,
+                    double *fux, double *fuy, double *fuz) {
+  const double sl = fmin(fmin(upl, upr), 0.0);
+  const double sr = fmax(fmax(upl, upr), 0.0);
+  const double islsr = 1.0 / (sr - sl + (sl * sr == 0.0));
+  *fux = 0.5 * (sr * uxl * upl - sl * uxr * upr + sl * sr * (uxr - uxl)) * islsr;
+  *fuy = 0.5 * (sr * uyl * upl - sl * uyr * upr + sl * sr * (uyr - uyl)) * islsr;
+  *fuz = 0.5 * (sr * uzl * upl - sl * uzr * upr + sl * sr * (uzr - uzl)) * islsr;
+  *psl = sl;
+  *psr = sr;
+}
+
+struct OrcBurgers {
+  const OrcMesh *m;
+  int ncomp, recon;
+  double cfl;
+  size_t nfield; /* nblocks*ncomp*ncell */
+  double *U;     /* base */
+  double *U1;    /* stage "1" */
+  double *dUdt;
+  double *rec[6]; /* Ulx Urx Uly Ury Ulz Urz */
+  double *flux[3];
+  double *derived;
+  double dt, time, allowed_dt;
+  int ncycle;
+};
+
+/* uniform_cartesian.hpp:94-97 */
+static inline double xc(const Block *blk, int d, int idx) {
+  return blk->cxmin[d] + (idx + 0.5) * blk->dx[d];
+}
+
+/* benchmarks/burgers/parthenon_app_inputs.cpp:35-78 (kx_fact etc. are unused there) */
+void orc_burgers_ic(const OrcMesh *m, double *U, int ncomp) {
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int k = m->is[2]; k <= m->ie[2]; ++k)
+      for (int j = m->is[1]; j <= m->ie[1]; ++j)
+        for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+          const double x = xc(blk, 0, i), y = xc(blk, 1, j), z = xc(blk, 2, k);
+          const double qx = (tanh(-20.0 * x) * cos(M_PI * x) + 1.0) * exp(-30.0 * y * y) *
+                            exp(-30.0 * z * z);
+          const double qy =
+              (sin(M_PI * y) + 0.2) * exp(-30.0 * x * x) * exp(-30.0 * z * z);
+          const double qz = (tanh(-20. * z) * cos(M_PI * z) + 0.5) * exp(-30.0 * x * x) *
+                            exp(-30.0 * y * y);
+          U[fidx(m, ncomp, b, 0, k, j, i)] = qx;
+          U[fidx(m, ncomp, b, 1, k, j, i)] = qy;
+          U[fidx(m, ncomp, b, 2, k, j, i)] = qz;
+          for (int n = 3; n < ncomp; ++n) {
+            double q = 1;
+            if (fabs(x) < 0.025 && fabs(y) < 0.15 && fabs(z) < 0.025) q += 10.0;
+            U[fidx(m, ncomp, b, n, k, j, i)] = q;
+          }
+        }
+  }
+}
+
+OrcBurgers *orc_burgers_create(const OrcMesh *m, int num_scalars, int recon, double cfl) {
+  OrcBurgers *s = (OrcBurgers *)calloc(1, sizeof(OrcBurgers));
+  s->m = m;
+  s->ncomp = 3 + num_scalars;
+  s->recon = recon;
+  s->cfl = cfl;
+  size_t ncell = (size_t)m->n[0] * m->n[1] * m->n[2];
+  s->nfield = (size_t)m->nblocks * s->ncomp * ncell;
+  s->U = (double *)calloc(s->nfield, sizeof(double));
+  s->U1 = (double *)calloc(s->nfield, sizeof(double));
+  s->dUdt = (double *)calloc(s->nfield, sizeof(double));
+  for (int r = 0; r < 6; ++r) s->rec[r] = (double *)calloc(s->nfield, sizeof(double));
+  for (int d = 0; d < 3; ++d) s->flux[d] = (double *)calloc(s->nfield, sizeof(double));
+  s->derived = (double *)calloc((size_t)m->nblocks * ncell, sizeof(double));
+  s->dt = DBL_MAX;
+  return s;
+}
+void orc_burgers_destroy(OrcBurgers *s) {
+  if (!s) return;
+  free(s->U);
+  free(s->U1);
+  free(s->dUdt);
+  for (int r = 0; r < 6; ++r) free(s->rec[r]);
+  for (int d = 0; d < 3; ++d) free(s->flux[d]);
+  free(s->derived);
+  free(s);
+}
+double *orc_burgers_U(OrcBurgers *s) { return s->U; }
+double *orc_burgers_derived(OrcBurgers *s) { return s->derived; }
+double *orc_burgers_flux(OrcBurgers *s, int dir) { return s->flux[dir]; }
+double orc_burgers_dt(const OrcBurgers *s) { return s->dt; }
+double orc_burgers_time(const OrcBurgers *s) { return s->time; }
+int orc_burgers_cycle(const OrcBurgers *s) { return s->ncycle; }
+
+/* CalculateFluxes burgers_package.cpp:202-404 (3-D, ndim-aware like the reference) */
+void orc_burgers_calculate_fluxes(OrcBurgers *st, const double *U) {
+  const OrcMesh *m = st->m;
+  const int nc = st->ncomp, ndim = m->ndim;
+  const int is = m->is[0], ie = m->ie[0], js = m->is[1], je = m->ie[1], ks = m->is[2],
+            ke = m->ie[2];
+  const int dk = ndim > 2 ? 1 : 0, dj = ndim > 1 ? 1 : 0;
+  const size_t sj = (size_t)m->n[0], sk = (size_t)m->n[0] * m->n[1];
+  double *Ulx = st->rec[0], *Urx = st->rec[1], *Uly = st->rec[2], *Ury = st->rec[3],
+         *Ulz = st->rec[4], *Urz = st->rec[5];
+  /* reconstruction :236-303 */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int k = ks - dk; k <= ke + dk; ++k)
+      for (int j = js - dj; j <= je + dj; ++j) {
+        const int xrec = (k >= ks && k <= ke) && (j >= js && j <= je);
+        const int yrec = (k >= ks && k <= ke) && (ndim > 1);
+        const int zrec = (j >= js && j <= je) && (ndim > 2);
+        for (int n = 0; n < nc; ++n) {
+          const size_t row = fidx(m, nc, b, n, k, j, 0);
+          const double *pq = U + row;
+          if (xrec)
+            for (int i = is - 1; i <= ie + 1; ++i) {
+              if (st->recon == 0)
+                orc_weno5z(pq[i - 2], pq[i - 1], pq[i], pq[i + 1], pq[i + 2],
+                           &Ulx[row + i + 1], &Urx[row + i]);
+              else
+                orc_linear(pq[i - 1], pq[i], pq[i + 1], &Ulx[row + i + 1], &Urx[row + i]);
+            }
+          if (yrec)
+            for (int i = is; i <= ie; ++i) {
+              if (st->recon == 0)
+                orc_weno5z(pq[i - 2 * sj], pq[i - sj], pq[i], pq[i + sj], pq[i + 2 * sj],
+                           &Uly[row + sj + i], &Ury[row + i]);
+              else
+                orc_linear(pq[i - sj], pq[i], pq[i + sj], &Uly[row + sj + i], &Ury[row + i]);
+            }
+          if (zrec)
+            for (int i = is; i <= ie; ++i) {
+              if (st->recon == 0)
+                orc_weno5z(pq[i - 2 * sk], pq[i - sk], pq[i], pq[i + sk], pq[i + 2 * sk],
+                           &Ulz[row + sk + i], &Urz[row + i]);
+              else
+                orc_linear(pq[i - sk], pq[i], pq[i + sk], &Ulz[row + sk + i], &Urz[row + i]);
+            }
+        }
+      }
+  /* Riemann :307-401 */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int k = ks; k <= ke + dk; ++k)
+      for (int j = js; j <= je + dj; ++j) {
+        const int xflux = (k <= ke && j <= je);
+        const int yflux = (ndim > 1 && k <= ke);
+        const int zflux = (ndim > 2 && j <= je);
+        const size_t r0 = fidx(m, nc, b, 0, k, j, 0);
+        const size_t cs = (size_t)m->n[0] * m->n[1] * m->n[2]; /* component stride */
+        for (int dir = 0; dir < 3; ++dir) {
+          if (dir == 0 && !xflux) continue;
+          if (dir == 1 && !yflux) continue;
+          if (dir == 2 && !zflux) continue;
+          const double *L = st->rec[2 * dir], *R = st->rec[2 * dir + 1];
+          double *F = st->flux[dir];
+          const int iend = dir == 0 ? ie + 1 : ie;
+          for (int i = is; i <= iend; ++i) {
+            const size_t p = r0 + i;
+            double sl, sr;
+            orc_lr_to_flux(L[p], R[p], L[p + cs], R[p + cs], L[p + 2 * cs], R[p + 2 * cs],
+                           L[p + dir * cs], R[p + dir * cs], &sl, &sr, &F[p], &F[p + cs],
+                           &F[p + 2 * cs]);
+            const double upl = L[p + dir * cs], upr = R[p + dir * cs];
+            for (int n = 3; n < nc; ++n) {
+              const double ql = L[p + n * cs], qr = R[p + n * cs];
+              F[p + n * cs] = (sr * upl * ql - sl * upr * qr + sl * sr * (qr - ql)) /
+                              (sr - sl + (sl * sr == 0.0));
+            }
+          }
+        }
+      }
+}
+
+/* CalculateDerived burgers_package.cpp:143-167 : pack {derived, U} => d = U component 3 */
+static void calculate_derived(OrcBurgers *st, const double *U) {
+  const OrcMesh *m = st->m;
+  const int nc = st->ncomp;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int k = m->is[2]; k <= m->ie[2]; ++k)
+      for (int j = m->is[1]; j <= m->ie[1]; ++j)
+        for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+          const double u1 = U[fidx(m, nc, b, 0, k, j, i)];
+          const double u2 = U[fidx(m, nc, b, 1, k, j, i)];
+          const double u3 = U[fidx(m, nc, b, 2, k, j, i)];
+          const double d = U[fidx(m, nc, b, 3, k, j, i)];
+          st->derived[fidx(m, 1, b, 0, k, j, i)] = 0.5 * d * (u1 * u1 + u2 * u2 + u3 * u3);
+        }
+}
+
+/* EstimateTimestepMesh burgers_package.cpp:170-200 */
+static double estimate_timestep(const OrcBurgers *st, const double *U) {
+  const OrcMesh *m = st->m;
+  const int nc = st->ncomp, ndim = m->ndim;
+  double min_dt = DBL_MAX;
+#pragma omp parallel for collapse(2) schedule(static) reduction(min : min_dt)
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int k = m->is[2]; k <= m->ie[2]; ++k)
+      for (int j = m->is[1]; j <= m->ie[1]; ++j) {
+        const Block *blk = &m->blocks[b];
+        for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+          const double v =
+              1.0 / ((fabs(U[fidx(m, nc, b, 0, k, j, i)])) / blk->dx[0] +
+                     (ndim > 1) * (fabs(U[fidx(m, nc, b, 1, k, j, i)])) / blk->dx[1] +
+                     (ndim > 2) * (fabs(U[fidx(m, nc, b, 2, k, j, i)])) / blk->dx[2]);
+          min_dt = fmin(min_dt, v);
+        }
+      }
+  return st->cfl * min_dt;
+}
+
+/* FluxDivergence update.cpp:63-86 with FluxDivHelper update.hpp:43-58 */
+static void flux_divergence(OrcBurgers *st) {
+  const OrcMesh *m = st->m;
+  const int nc = st->ncomp, ndim = m->ndim;
+  const size_t sj = (size_t)m->n[0], sk = (size_t)m->n[0] * m->n[1];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int l = 0; l < nc; ++l) {
+      const Block *blk = &m->blocks[b];
+      const double a1 = blk->dx[1] * blk->dx[2], a2 = blk->dx[0] * blk->dx[2],
+                   a3 = blk->dx[0] * blk->dx[1];
+      const double vol = blk->dx[0] * blk->dx[1] * blk->dx[2];
+      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+        for (int j = m->is[1]; j <= m->ie[1]; ++j)
+          for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+            const size_t p = fidx(m, nc, b, l, k, j, i);
+            double du = (a1 * st->flux[0][p + 1] - a1 * st->flux[0][p]);
+            if (ndim >= 2) du += (a2 * st->flux[1][p + sj] - a2 * st->flux[1][p]);
+            if (ndim == 3) du += (a3 * st->flux[2][p + sk] - a3 * st->flux[2][p]);
+            st->dUdt[p] = -du / vol;
+          }
+    }
+}
+
+/* WeightedSumData update.hpp:71-91: z = w1*x + w2*y over the ENTIRE extents */
+static void weighted_sum(size_t n, const double *x, const double *y, double w1, double w2,
+                         double *z) {
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) z[i] = w1 * x[i] + w2 * y[i];
+}
+
+/* one stage of BurgersDriver::MakeTaskCollection burgers_driver.cpp:53-148 with rk2
+ * coefficients (low_storage_integrator.cpp:67-86) and stage names
+ * (staged_integrator.cpp:23-30): stage 1: mc0 = base, mc1 = "1"; stage 2: mc0 = "1",
+ * mc1 = base. */
+void orc_burgers_stage(OrcBurgers *st, int stage) {
+  const double beta = stage == 1 ? 1.0 : 0.5;
+  double *mc0 = stage == 1 ? st->U : st->U1;
+  double *mc1 = stage == 1 ? st->U1 : st->U;
+  double *base = st->U;
+  orc_burgers_calculate_fluxes(st, mc0);
+  flux_divergence(st);
+  weighted_sum(st->nfield, mc0, base, beta, 1.0 - beta, mc0);        /* AverageIndependentData */
+  weighted_sum(st->nfield, mc0, st->dUdt, 1.0, beta * st->dt, mc1); /* UpdateIndependentData */
+  orc_exchange(st->m, mc1, NULL, st->ncomp, 0);
+  calculate_derived(st, mc1);
+  if (stage == 2) st->allowed_dt = estimate_timestep(st, mc1);
+}
+
+/* EvolutionDriver::SetGlobalTimeStep driver.cpp:210-270 with default limits */
+static void set_global_timestep(OrcBurgers *st) {
+  if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;
+  st->dt = fmin(st->dt, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+}
+
+void orc_burgers_init(OrcBurgers *st) {
+  orc_burgers_ic(st->m, st->U, st->ncomp);
+  orc_exchange(st->m, st->U, NULL, st->ncomp, 0);
+  calculate_derived(st, st->U);
+  st->allowed_dt = estimate_timestep(st, st->U); /* InitializeBlockTimeSteps driver.cpp:194 */
+  st->dt = DBL_MAX;
+  set_global_timestep(st);
+  st->time = 0;
+  st->ncycle = 0;
+}
+
+void orc_burgers_step(OrcBurgers *st) {
+  orc_burgers_stage(st, 1);
+  orc_burgers_stage(st, 2);
+  st->ncycle++;
+  st->time += st->dt;
+  set_global_timestep(st);
+}
+
+/* MassHistory burgers_package.cpp:406-439, octant order :94-107 */
+void orc_burgers_history(const OrcBurgers *st, double out[8]) {
+  const OrcMesh *m = st->m;
+  const int nc = st->ncomp;
+  double mesh_vol = 1;
+  double mid[3];
+  for (int d = 0; d < 3; ++d) {
+    mesh_vol *= (m->xmax[d] - m->xmin[d]);
+    mid[d] = 0.5 * (m->xmin[d] + m->xmax[d]);
+  }
+  int oct = 0;
+  for (int s1 = 0; s1 < 2; ++s1)
+    for (int s2 = 0; s2 < 2; ++s2)
+      for (int s3 = 0; s3 < 2; ++s3) {
+        const double lo[3] = {s1 ? mid[0] : m->xmin[0], s2 ? mid[1] : m->xmin[1],
+                              s3 ? mid[2] : m->xmin[2]};
+        const double hi[3] = {s1 ? m->xmax[0] : mid[0], s2 ? m->xmax[1] : mid[1],
+                              s3 ? m->xmax[2] : mid[2]};
+        double result = 0.0;
+#pragma omp parallel for collapse(2) schedule(static) reduction(+ : result)
+        for (int b = 0; b < m->nblocks; ++b)
+          for (int v = 0; v < nc; ++v) {
+            const Block *blk = &m->blocks[b];
+            const double vol = blk->dx[0] * blk->dx[1] * blk->dx[2];
+            const double weight = vol / (mesh_vol + 1e-20);
+            for (int k = m->is[2]; k <= m->ie[2]; ++k)
+              for (int j = m->is[1]; j <= m->ie[1]; ++j)
+                for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+                  const double x1 = xc(blk, 0, i), x2 = xc(blk, 1, j), x3 = xc(blk, 2, k);
+                  const double mask = (lo[0] <= x1) && (x1 <= hi[0]) && (lo[1] <= x2) &&
+                                      (x2 <= hi[1]) && (lo[2] <= x3) && (x3 <= hi[2]);
+                  const double q = st->U[fidx(m, nc, b, v, k, j, i)];
+                  result += mask * q * q * weight;
+                }
+          }
+        out[oct++] = result;
+      }
+}
+
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+int orc_get_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
