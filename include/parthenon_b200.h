@@ -1,0 +1,245 @@
+/* parthenon_b200.h — C ABI of the B200-native ghost-zone hot path.
+ *
+ * This is the drop-in boundary.  The reference (parthenon-hpc-lab/parthenon @79d5d30) has no
+ * FFI: its hot path is a set of C++ task functions that launch Kokkos lambdas.  Each entry
+ * point below replaces the DEVICE part of one of those functions; the host-side shims in
+ * parthenon_b200/host/ keep the reference's C++ signatures and call only this header (see
+ * INTEGRATION.md for the binding a Parthenon maintainer would add).
+ *
+ * Conventions: plain pointers and sizes, POD structs, no C++/torch types; every function
+ * returns 0 (PB2_OK) or a negative error code and never throws; the caller owns all field
+ * memory, the library owns only tables/slabs created through it; all launches are
+ * asynchronous on the given stream (a cudaStream_t passed as void*; NULL = default stream).
+ * All field arithmetic is FP64 (`Real` = double, reference basic_types.hpp:30-39); arrays
+ * are row-major with i fastest (reference kokkos_abstraction.hpp:52).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * PB2_ERR_NO_DEVICE.
+ */
+#ifndef PARTHENON_B200_H_
+#define PARTHENON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_OK 0
+#define PB2_ERR_INVALID (-1)
+#define PB2_ERR_CUDA (-2)
+#define PB2_ERR_NO_DEVICE (-3)
+#define PB2_ERR_NCCL (-4)
+#define PB2_ERR_UNSUPPORTED (-5)
+
+typedef void *pb2_stream_t; /* cudaStream_t */
+typedef void *pb2_event_t;  /* cudaEvent_t */
+
+/* ---------------------------------------------------------------------------------------
+ * plumbing: device, memory, streams, events (so host C++ never links the CUDA runtime)
+ * ------------------------------------------------------------------------------------- */
+int pb2_version(void);
+const char *pb2_last_error(void);
+int pb2_device_count(int *count);
+int pb2_set_device(int device);
+int pb2_device_sm_count(int *count);
+int pb2_malloc(void **ptr, size_t bytes);
+int pb2_free(void *ptr);
+int pb2_host_alloc(void **ptr, size_t bytes); /* pinned */
+int pb2_host_free(void *ptr);
+int pb2_memset(void *ptr, int value, size_t bytes, pb2_stream_t stream);
+int pb2_memcpy_h2d(void *dst, const void *src, size_t bytes, pb2_stream_t stream);
+int pb2_memcpy_d2h(void *dst, const void *src, size_t bytes, pb2_stream_t stream);
+int pb2_memcpy_d2d(void *dst, const void *src, size_t bytes, pb2_stream_t stream);
+int pb2_stream_create(pb2_stream_t *stream);
+int pb2_stream_destroy(pb2_stream_t stream);
+int pb2_stream_sync(pb2_stream_t stream);
+int pb2_device_sync(void);
+int pb2_event_create(pb2_event_t *ev);
+int pb2_event_destroy(pb2_event_t ev);
+int pb2_event_record(pb2_event_t ev, pb2_stream_t stream);
+int pb2_event_sync(pb2_event_t ev);
+int pb2_event_query(pb2_event_t ev); /* 0 done, 1 not yet */
+int pb2_stream_wait_event(pb2_stream_t stream, pb2_event_t ev);
+int pb2_event_elapsed_ms(pb2_event_t start, pb2_event_t stop, float *ms);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+int64_t pb2_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * ghost exchange: boundary-region tables
+ * replaces BndInfo (src/bvals/comms/bnd_info.hpp:51-83) and the pack / unpack kernels of
+ * SendBoundBufs (src/bvals/comms/boundary_communication.cpp:95-140) and SetBounds (:273-334)
+ * ------------------------------------------------------------------------------------- */
+#define PB2_REGION_ALLOCATED 1u     /* BndInfo::allocated */
+#define PB2_REGION_BUF_ALLOCATED 2u /* BndInfo::buf_allocated (receive side) */
+#define PB2_REGION_SAME_TO_SAME 4u  /* BndInfo::same_to_same */
+
+/* One side of a boundary channel: an index box of one block's array <-> a contiguous run
+ * of the buffer slab.  Buffer order is [comp][k][j][i] (Indexer6D, src/utils/indexer.hpp). */
+typedef struct pb2_bnd_region {
+  double *var;       /* component 0 of the array the box indexes (fine data, or the coarse
+                        buffer when the neighbour is coarser: bnd_info.cpp:285-289) */
+  int64_t buf_off;   /* offset in Reals into the buffer slab given at launch */
+  int32_t s[3];      /* box start (i, j, k) — CalcIndices, bnd_info.cpp:105-252 */
+  int32_t n[3];      /* box extent (i, j, k) */
+  int32_t ncomp;     /* flattened tensor components (t,u,v) */
+  int32_t stride_j;  /* array strides in Reals */
+  int32_t stride_k;
+  int32_t stride_c;
+  int32_t flag_slot; /* send: slot of sending_nonzero_flags; recv: slot of the flag that
+                        says whether the buffer holds data (<0: always data) */
+  uint32_t status;   /* PB2_REGION_* */
+  double value;      /* send: allocation threshold; recv: sparse default value */
+} pb2_bnd_region;
+
+/* Fused same-device channel: sender box -> receiver box with no intermediate buffer
+ * (BuffCommType::both channels, src/utils/communication_buffer.hpp:145-147, 390-400). */
+typedef struct pb2_copy_region {
+  const double *src;
+  double *dst;
+  int32_t ss[3]; /* source box start (i,j,k) */
+  int32_t ds[3]; /* destination box start */
+  int32_t n[3];  /* common extent */
+  int32_t ncomp;
+  int32_t src_stride_j, src_stride_k, src_stride_c;
+  int32_t dst_stride_j, dst_stride_k, dst_stride_c;
+  int32_t flag_slot; /* sparse: slot receiving "any |x| >= threshold" (or <0) */
+  uint32_t status;   /* PB2_REGION_ALLOCATED refers to the source */
+  double threshold;
+  double default_value; /* written when the source is unallocated / all below threshold */
+} pb2_copy_region;
+
+typedef struct pb2_bnd_table pb2_bnd_table; /* opaque, device resident */
+
+/* Upload `n` regions (host array) and build the work decomposition.  Called on cache
+ * rebuild only (reference: RebuildBufferCache, src/bvals/comms/bvals_utils.hpp:212-260). */
+int pb2_bnd_table_create(pb2_bnd_table **table, const pb2_bnd_region *regions, int64_t n);
+int pb2_copy_table_create(pb2_bnd_table **table, const pb2_copy_region *regions, int64_t n);
+int pb2_bnd_table_destroy(pb2_bnd_table *table);
+/* total Reals covered by the table's boxes */
+int64_t pb2_bnd_table_elements(const pb2_bnd_table *table);
+
+/* One launch packs every region of the table: buf[buf_off + m] = var(box)[m];
+ * nonzero_flags[flag_slot] |= any(|x| >= value) when nonzero_flags != NULL
+ * (boundary_communication.cpp:95-140).  nonzero_flags is int32 per slot, zeroed by caller. */
+int pb2_pack(const pb2_bnd_table *table, double *buf, int32_t *nonzero_flags,
+             pb2_stream_t stream);
+/* One launch unpacks every region: var(box)[m] = buf[buf_off + m]; regions whose
+ * data_flags[flag_slot] == 0 are filled with `value` (boundary_communication.cpp:273-334). */
+int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *data_flags,
+               pb2_stream_t stream);
+/* One launch moves every same-device channel straight from sender box to receiver box. */
+int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * prolongation / restriction at fine-coarse boundaries
+ * replaces ProResInfo (bnd_info.hpp:85-125) + refinement::Restrict / ProlongateShared
+ * (src/prolong_restrict/prolong_restrict.cpp:37-79, pr_loops.hpp:113-155, pr_ops.hpp)
+ * ------------------------------------------------------------------------------------- */
+typedef struct pb2_prores_region {
+  double *fine;   /* component 0 of the block's fine array */
+  double *coarse; /* component 0 of the block's coarse buffer */
+  int32_t s[3];   /* box in COARSE index space (i,j,k) */
+  int32_t n[3];
+  int32_t ncomp;
+  int32_t fine_stride_j, fine_stride_k, fine_stride_c;
+  int32_t coarse_stride_j, coarse_stride_k, coarse_stride_c;
+  int32_t fine_is[3];   /* interior start of the fine index space  (ib.s, jb.s, kb.s) */
+  int32_t coarse_is[3]; /* interior start of the coarse index space (cib.s, ...) */
+  int32_t ndim;
+  uint32_t status;
+  double fine_xmin[3], fine_dx[3];     /* UniformCartesian xmin_, dx_ of the block */
+  double coarse_xmin[3], coarse_dx[3]; /* and of its coarse coordinates */
+} pb2_prores_region;
+
+#define PB2_PROLONG_MINMOD 0             /* ProlongateSharedMinMod (default, metadata.hpp:337) */
+#define PB2_PROLONG_LINEAR 1             /* ProlongateSharedLinear */
+#define PB2_PROLONG_PIECEWISE_CONSTANT 2 /* ProlongatePiecewiseConstant */
+
+int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regions,
+                            int64_t n);
+/* RestrictAverage over every region of the table (pr_ops.hpp:105-165) */
+int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream);
+/* ProlongateSharedGeneral over every region of the table (pr_ops.hpp:167-280) */
+int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * dense per-stage updates: src/interface/update.hpp:43-91, update.cpp:63-86
+ * ------------------------------------------------------------------------------------- */
+/* z = w1*x + w2*y over n Reals (WeightedSumData, update.hpp:71-91) */
+int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, double *z,
+                     int64_t n, pb2_stream_t stream);
+
+/* Block-batched field geometry shared by the stencil entry points. */
+typedef struct pb2_pack_geom {
+  int32_t nblocks, ncomp, ndim;
+  int32_t nx[3];   /* interior cells (i,j,k) */
+  int32_t ng;      /* ghost width (0 in symmetry directions) */
+  int64_t block_stride; /* Reals between blocks; component stride is ni*nj*nk */
+  const double *dx;     /* device [nblocks][3] cell widths */
+} pb2_pack_geom;
+
+/* dudt = -div(F) (FluxDivergence + FluxDivHelper), interior cells */
+int pb2_flux_divergence(const pb2_pack_geom *g, const double *const flux[3], double *dudt,
+                        pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * benchmarks/burgers stencil: CalculateFluxes (burgers_package.cpp:202-404), fused with
+ * FluxDivergence / AverageIndependentData / UpdateIndependentData / CalculateDerived /
+ * EstimateTimestepMesh (burgers_driver.cpp:92-127)
+ * ------------------------------------------------------------------------------------- */
+#define PB2_RECON_WENO5 0
+#define PB2_RECON_LINEAR 1
+/* arithmetic mode: STRICT keeps the reference's expression order with FMA contraction off
+ * (bit-identical to the reference's CPU build); FAST allows FMA contraction (<=1e-12 rel) */
+#define PB2_MATH_STRICT 0
+#define PB2_MATH_FAST 1
+
+typedef struct pb2_burgers_args {
+  pb2_pack_geom geom;
+  int32_t recon; /* PB2_RECON_* */
+  int32_t math;  /* PB2_MATH_* */
+  const double *u;    /* stage input  mc0  [nblocks][ncomp][nk][nj][ni] */
+  const double *base; /* base container (== u in stage 1) */
+  double *out;        /* stage output mc1 */
+  double *flux[3];    /* face fluxes, same extents as u (WithFluxes, metadata.cpp:185) */
+  double *derived;    /* [nblocks][nk][nj][ni] or NULL */
+  double *dt_min;     /* device scalar: min over cells of 1/sum(|u_d|/dx_d), or NULL.
+                         Must be initialised to +huge by the caller. */
+  double beta;        /* integrator->beta[stage-1] */
+  double dt;
+} pb2_burgers_args;
+
+/* fluxes only: writes args->flux[0..ndim-1] from args->u */
+int pb2_burgers_calculate_fluxes(const pb2_burgers_args *args, pb2_stream_t stream);
+/* out = (beta*u + (1-beta)*base) + beta*dt*(-div flux); derived; dt_min — interior cells */
+int pb2_burgers_update(const pb2_burgers_args *args, pb2_stream_t stream);
+/* both of the above, one call per stage */
+int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream);
+/* 8 octant mass histories (MassHistory, burgers_package.cpp:406-439) -> host out[8] */
+int pb2_burgers_history(const pb2_pack_geom *g, const double *u, const double *block_xmin,
+                        const double mesh_xmin[3], const double mesh_xmax[3],
+                        double out[8], pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * inter-GPU halo slabs: replaces CommBuffer's MPI_Isend/Irecv
+ * (src/utils/communication_buffer.hpp:209-406) with one grouped NCCL send/recv per peer
+ * ------------------------------------------------------------------------------------- */
+typedef struct pb2_comm pb2_comm;
+#define PB2_NCCL_UNIQUE_ID_BYTES 128
+int pb2_comm_unique_id(uint8_t id[PB2_NCCL_UNIQUE_ID_BYTES]);
+int pb2_comm_create(pb2_comm **comm, int rank, int nranks,
+                    const uint8_t id[PB2_NCCL_UNIQUE_ID_BYTES]);
+int pb2_comm_destroy(pb2_comm *comm);
+/* send_off/recv_off: [nranks+1] offsets in Reals into the slabs (peer p owns
+ * [off[p], off[p+1])); empty ranges are skipped. */
+int pb2_comm_exchange(pb2_comm *comm, const double *send_slab, const int64_t *send_off,
+                      double *recv_slab, const int64_t *recv_off, pb2_stream_t stream);
+/* in-place min all-reduce of one double (replaces MPI_Allreduce, driver.cpp:237) */
+int pb2_comm_allreduce_min(pb2_comm *comm, double *dev_value, pb2_stream_t stream);
+int pb2_comm_barrier(pb2_comm *comm, pb2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARTHENON_B200_H_ */

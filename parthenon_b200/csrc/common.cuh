@@ -1,0 +1,74 @@
+// common.cuh — shared helpers for the C-ABI implementation (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "parthenon_b200.h"
+
+namespace pb2 {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline cudaStream_t as_stream(pb2_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define PB2_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      ::pb2::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                 \
+                       cudaGetErrorString(err__));                                        \
+      return (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver)         \
+                 ? PB2_ERR_NO_DEVICE                                                      \
+                 : PB2_ERR_CUDA;                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define PB2_REQUIRE(cond, msg)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::pb2::set_error("%s:%d: %s", __FILE__, __LINE__, msg);                             \
+      return PB2_ERR_INVALID;                                                             \
+    }                                                                                     \
+  } while (0)
+
+// call after every kernel launch
+#define PB2_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    ::pb2::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+    PB2_CUDA_CHECK(cudaGetLastError());                                                   \
+  } while (0)
+
+int require_device();
+
+// Division by a runtime-constant 32-bit divisor with a precomputed magic number
+// (n must be < 2^31).  q = (umulhi(n, magic) + n) >> shift.
+struct FastDiv {
+  uint32_t d, magic, shift;
+  __host__ void init(uint32_t div) {
+    d = div;
+    if (div <= 1) {
+      magic = 0;
+      shift = 0;
+      d = 1;
+      return;
+    }
+    uint32_t s = 0;
+    while ((1u << s) < div) ++s;
+    shift = s;
+    magic = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - div)) / div + 1);
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    return (__umulhi(n, magic) + n) >> shift;
+  }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+} // namespace pb2

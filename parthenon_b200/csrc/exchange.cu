@@ -1,0 +1,352 @@
+// exchange.cu — ghost-zone pack / unpack / fused same-device copy.
+//
+// Replaces the Kokkos TeamPolicy kernels of SendBoundBufs
+// (reference src/bvals/comms/boundary_communication.cpp:95-140) and SetBounds (:273-334).
+// Design (B200): one launch per table covers every region of a MeshData.  Regions are cut
+// on the host into fixed-size chunks (one CTA each) so that a 360 KB face region and a
+// 5.6 KB corner region load the SMs evenly; each thread moves 16-byte vectors, issues all
+// its loads before its stores (4 independent 16 B loads in flight per thread), and turns
+// the flat buffer index into (c,k,j,i) with precomputed multiply-shift divisions.  The
+// buffer side is fully coalesced; the array side touches whole 32 B sectors (ghost rows of
+// 4 doubles are sector aligned because is, ie+1 and the row pitch are multiples of 4).
+#include <vector>
+
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace pb2 {
+
+__device__ __forceinline__ void decompose(const DevRegion &r, uint32_t v, uint32_t &c,
+                                          uint32_t &k, uint32_t &j, uint32_t &iv) {
+  uint32_t t;
+  r.dni.divmod(v, t, iv);
+  uint32_t t2;
+  r.dnj.divmod(t, t2, j);
+  r.dnk.divmod(t2, c, k);
+}
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<1> {
+  using type = double;
+};
+template <>
+struct Vec<2> {
+  using type = double2;
+};
+
+__device__ __forceinline__ bool above(double x, double thr) { return fabs(x) >= thr; }
+__device__ __forceinline__ bool above(double2 x, double thr) {
+  return fabs(x.x) >= thr || fabs(x.y) >= thr;
+}
+__device__ __forceinline__ void splat(double &x, double v) { x = v; }
+__device__ __forceinline__ void splat(double2 &x, double v) { x.x = x.y = v; }
+
+// ---- pack: buf <- var ------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void pack_chunk(const DevRegion &r, uint32_t first, double *buf,
+                                           int32_t *flags) {
+  using T = typename Vec<V>::type;
+  T val[kUnroll];
+  bool ok[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t v = first + u * kThreads + threadIdx.x;
+    ok[u] = v < r.total_vec;
+    if (ok[u]) {
+      uint32_t c, k, j, iv;
+      decompose(r, v, c, k, j, iv);
+      const int64_t off = (int64_t)c * r.sc + (int64_t)(k + r.s[2]) * r.sk +
+                          (int64_t)(j + r.s[1]) * r.sj + (r.s[0] + (int32_t)iv * V);
+      val[u] = __ldg(reinterpret_cast<const T *>(r.var + off));
+    }
+  }
+  bool nz = false;
+  T *out = reinterpret_cast<T *>(buf + r.buf_off);
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t v = first + u * kThreads + threadIdx.x;
+    if (ok[u]) {
+      __stcs(out + v, val[u]);
+      nz = nz || above(val[u], r.value);
+    }
+  }
+  if (flags != nullptr && r.flag_slot >= 0) {
+    if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flags + r.flag_slot, 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    pack_kernel(const DevRegion *__restrict__ regions, const Chunk *__restrict__ chunks,
+                double *__restrict__ buf, int32_t *__restrict__ flags) {
+  const Chunk ch = chunks[blockIdx.x];
+  const DevRegion &r = regions[ch.region];
+  // unallocated / same_to_same regions send nothing (boundary_communication.cpp:100-104)
+  if (!(r.status & PB2_REGION_ALLOCATED) || (r.status & PB2_REGION_SAME_TO_SAME)) return;
+  if (r.vec == 2)
+    pack_chunk<2>(r, ch.first_vec, buf, flags);
+  else
+    pack_chunk<1>(r, ch.first_vec, buf, flags);
+}
+
+// ---- unpack: var <- buf (or the sparse default when the message was null) ----------------
+template <int V>
+__device__ __forceinline__ void unpack_chunk(const DevRegion &r, uint32_t first,
+                                             const double *buf, bool has_data) {
+  using T = typename Vec<V>::type;
+  T val[kUnroll];
+  const T *in = reinterpret_cast<const T *>(buf + r.buf_off);
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t v = first + u * kThreads + threadIdx.x;
+    if (v < r.total_vec) {
+      if (has_data)
+        val[u] = __ldcs(in + v);
+      else
+        splat(val[u], r.value);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t v = first + u * kThreads + threadIdx.x;
+    if (v < r.total_vec) {
+      uint32_t c, k, j, iv;
+      decompose(r, v, c, k, j, iv);
+      const int64_t off = (int64_t)c * r.sc + (int64_t)(k + r.s[2]) * r.sk +
+                          (int64_t)(j + r.s[1]) * r.sj + (r.s[0] + (int32_t)iv * V);
+      *reinterpret_cast<T *>(r.var + off) = val[u];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    unpack_kernel(const DevRegion *__restrict__ regions, const Chunk *__restrict__ chunks,
+                  const double *__restrict__ buf, const int32_t *__restrict__ data_flags) {
+  const Chunk ch = chunks[blockIdx.x];
+  const DevRegion &r = regions[ch.region];
+  if (r.status & PB2_REGION_SAME_TO_SAME) return; // :280
+  if (!(r.status & PB2_REGION_ALLOCATED)) return; // :290,:311
+  bool has_data = (r.status & PB2_REGION_BUF_ALLOCATED) != 0;
+  if (data_flags != nullptr && r.flag_slot >= 0) has_data = data_flags[r.flag_slot] != 0;
+  if (r.vec == 2)
+    unpack_chunk<2>(r, ch.first_vec, buf, has_data);
+  else
+    unpack_chunk<1>(r, ch.first_vec, buf, has_data);
+}
+
+// ---- fused copy: receiver box <- sender box ------------------------------------------------
+template <int V>
+__device__ __forceinline__ void copy_chunk(const DevRegion &r, uint32_t first,
+                                           int32_t *flags) {
+  using T = typename Vec<V>::type;
+  T val[kUnroll];
+  int64_t doff[kUnroll];
+  bool ok[kUnroll];
+  const bool src_alloc = (r.status & PB2_REGION_ALLOCATED) != 0;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t v = first + u * kThreads + threadIdx.x;
+    ok[u] = v < r.total_vec;
+    if (ok[u]) {
+      uint32_t c, k, j, iv;
+      decompose(r, v, c, k, j, iv);
+      const int64_t soff = (int64_t)c * r.ssc + (int64_t)(k + r.ss[2]) * r.ssk +
+                           (int64_t)(j + r.ss[1]) * r.ssj + (r.ss[0] + (int32_t)iv * V);
+      doff[u] = (int64_t)c * r.sc + (int64_t)(k + r.s[2]) * r.sk +
+                (int64_t)(j + r.s[1]) * r.sj + (r.s[0] + (int32_t)iv * V);
+      if (src_alloc)
+        val[u] = __ldg(reinterpret_cast<const T *>(r.src + soff));
+      else
+        splat(val[u], r.default_value);
+    }
+  }
+  bool nz = false;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    if (ok[u]) {
+      *reinterpret_cast<T *>(r.var + doff[u]) = val[u];
+      nz = nz || above(val[u], r.value);
+    }
+  }
+  if (flags != nullptr && r.flag_slot >= 0) {
+    if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flags + r.flag_slot, 1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    copy_kernel(const DevRegion *__restrict__ regions, const Chunk *__restrict__ chunks,
+                int32_t *__restrict__ flags) {
+  const Chunk ch = chunks[blockIdx.x];
+  const DevRegion &r = regions[ch.region];
+  if (r.status & PB2_REGION_SAME_TO_SAME) return;
+  if (r.vec == 2)
+    copy_chunk<2>(r, ch.first_vec, flags);
+  else
+    copy_chunk<1>(r, ch.first_vec, flags);
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int build_table(pb2_bnd_table **out, std::vector<DevRegion> &regs, int kind) {
+  std::vector<Chunk> chunks;
+  int64_t elements = 0;
+  for (size_t r = 0; r < regs.size(); ++r) {
+    const uint32_t per_chunk = kThreads * kUnroll;
+    elements += (int64_t)regs[r].total_vec * regs[r].vec;
+    for (uint32_t v = 0; v < regs[r].total_vec; v += per_chunk)
+      chunks.push_back(Chunk{static_cast<int32_t>(r), v});
+  }
+  auto *t = new pb2_bnd_table();
+  t->kind = kind;
+  t->nregions = static_cast<int64_t>(regs.size());
+  t->nchunks = static_cast<int64_t>(chunks.size());
+  t->elements = elements;
+  t->d_regions = nullptr;
+  t->d_chunks = nullptr;
+  t->d_prores = nullptr;
+  if (!regs.empty()) {
+    cudaError_t e = cudaMalloc(&t->d_regions, regs.size() * sizeof(DevRegion));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(t->d_regions, regs.data(), regs.size() * sizeof(DevRegion),
+                     cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !chunks.empty())
+      e = cudaMemcpy(t->d_chunks, chunks.data(), chunks.size() * sizeof(Chunk),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error("table upload failed: %s", cudaGetErrorString(e));
+      cudaFree(t->d_regions);
+      cudaFree(t->d_chunks);
+      delete t;
+      return PB2_ERR_CUDA;
+    }
+  }
+  *out = t;
+  return PB2_OK;
+}
+
+} // namespace pb2
+
+using namespace pb2;
+
+extern "C" {
+
+int pb2_bnd_table_create(pb2_bnd_table **table, const pb2_bnd_region *regions, int64_t n) {
+  PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
+  if (int rc = require_device()) return rc;
+  std::vector<DevRegion> regs(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; ++i) {
+    const pb2_bnd_region &a = regions[i];
+    DevRegion &d = regs[i];
+    memset(&d, 0, sizeof(d));
+    PB2_REQUIRE(a.n[0] >= 0 && a.n[1] >= 0 && a.n[2] >= 0 && a.ncomp >= 0, "negative extent");
+    const int64_t total = (int64_t)a.ncomp * a.n[0] * a.n[1] * a.n[2];
+    PB2_REQUIRE(total < (1ll << 31), "region too large");
+    d.var = a.var;
+    d.buf_off = a.buf_off;
+    for (int q = 0; q < 3; ++q) d.s[q] = a.s[q];
+    d.sj = a.stride_j;
+    d.sk = a.stride_k;
+    d.sc = a.stride_c;
+    const bool v2 = (a.n[0] % 2 == 0) && (a.s[0] % 2 == 0) && (a.stride_j % 2 == 0) &&
+                    (a.stride_k % 2 == 0) && (a.stride_c % 2 == 0) && (a.buf_off % 2 == 0) &&
+                    aligned16(a.var);
+    d.vec = v2 ? 2 : 1;
+    d.dni.init(static_cast<uint32_t>(a.n[0] / (int)d.vec > 0 ? a.n[0] / (int)d.vec : 1));
+    d.dnj.init(static_cast<uint32_t>(a.n[1] > 0 ? a.n[1] : 1));
+    d.dnk.init(static_cast<uint32_t>(a.n[2] > 0 ? a.n[2] : 1));
+    d.total_vec = static_cast<uint32_t>(total / d.vec);
+    d.flag_slot = a.flag_slot;
+    d.status = a.status;
+    d.value = a.value;
+  }
+  return build_table(table, regs, kBnd);
+}
+
+int pb2_copy_table_create(pb2_bnd_table **table, const pb2_copy_region *regions, int64_t n) {
+  PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
+  if (int rc = require_device()) return rc;
+  std::vector<DevRegion> regs(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; ++i) {
+    const pb2_copy_region &a = regions[i];
+    DevRegion &d = regs[i];
+    memset(&d, 0, sizeof(d));
+    PB2_REQUIRE(a.n[0] >= 0 && a.n[1] >= 0 && a.n[2] >= 0 && a.ncomp >= 0, "negative extent");
+    const int64_t total = (int64_t)a.ncomp * a.n[0] * a.n[1] * a.n[2];
+    PB2_REQUIRE(total < (1ll << 31), "region too large");
+    d.var = a.dst;
+    d.src = a.src;
+    for (int q = 0; q < 3; ++q) {
+      d.s[q] = a.ds[q];
+      d.ss[q] = a.ss[q];
+    }
+    d.sj = a.dst_stride_j;
+    d.sk = a.dst_stride_k;
+    d.sc = a.dst_stride_c;
+    d.ssj = a.src_stride_j;
+    d.ssk = a.src_stride_k;
+    d.ssc = a.src_stride_c;
+    const bool v2 = (a.n[0] % 2 == 0) && (a.ss[0] % 2 == 0) && (a.ds[0] % 2 == 0) &&
+                    (a.src_stride_j % 2 == 0) && (a.src_stride_k % 2 == 0) &&
+                    (a.src_stride_c % 2 == 0) && (a.dst_stride_j % 2 == 0) &&
+                    (a.dst_stride_k % 2 == 0) && (a.dst_stride_c % 2 == 0) &&
+                    aligned16(a.src) && aligned16(a.dst);
+    d.vec = v2 ? 2 : 1;
+    d.dni.init(static_cast<uint32_t>(a.n[0] / (int)d.vec > 0 ? a.n[0] / (int)d.vec : 1));
+    d.dnj.init(static_cast<uint32_t>(a.n[1] > 0 ? a.n[1] : 1));
+    d.dnk.init(static_cast<uint32_t>(a.n[2] > 0 ? a.n[2] : 1));
+    d.total_vec = static_cast<uint32_t>(total / d.vec);
+    d.flag_slot = a.flag_slot;
+    d.status = a.status;
+    d.value = a.threshold;
+    d.default_value = a.default_value;
+  }
+  return build_table(table, regs, kCopy);
+}
+
+int pb2_bnd_table_destroy(pb2_bnd_table *table) {
+  if (!table) return PB2_OK;
+  cudaFree(table->d_regions);
+  cudaFree(table->d_chunks);
+  cudaFree(table->d_prores);
+  delete table;
+  return PB2_OK;
+}
+
+int64_t pb2_bnd_table_elements(const pb2_bnd_table *table) {
+  return table ? table->elements : 0;
+}
+
+int pb2_pack(const pb2_bnd_table *table, double *buf, int32_t *nonzero_flags,
+             pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kBnd, "pack needs a boundary table");
+  if (table->nchunks == 0) return PB2_OK;
+  PB2_REQUIRE(buf, "null buffer");
+  pack_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+      table->d_regions, table->d_chunks, buf, nonzero_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *data_flags,
+               pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kBnd, "unpack needs a boundary table");
+  if (table->nchunks == 0) return PB2_OK;
+  PB2_REQUIRE(buf, "null buffer");
+  unpack_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+      table->d_regions, table->d_chunks, buf, data_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kCopy, "copy needs a copy table");
+  if (table->nchunks == 0) return PB2_OK;
+  copy_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+      table->d_regions, table->d_chunks, nonzero_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,221 @@
+// prores.cu — restriction and prolongation at fine-coarse boundaries, cell-centred fields.
+//
+// Replaces refinement::Restrict / ProlongateShared (reference
+// src/prolong_restrict/prolong_restrict.cpp:37-79) and the team loops of
+// src/prolong_restrict/pr_loops.hpp:113-155: one launch covers every ProResInfo region of a
+// MeshData.  Operators follow src/prolong_restrict/pr_ops.hpp:105-165 (RestrictAverage) and
+// :167-280 (ProlongateSharedGeneral) with the same expression order; this file is compiled
+// with -fmad=false so results are bit-identical to the reference's CPU build.
+#include <vector>
+
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace pb2 {
+
+constexpr int kPrThreads = 128;
+constexpr int kPrPerThread = 2;
+
+__device__ __forceinline__ double sign_of(double x) { return (x > 0) - (x < 0); }
+
+// util::GradMinMod pr_ops.hpp:95-101
+__device__ __forceinline__ double grad_minmod(double fc, double fm, double fp, double dxm,
+                                              double dxp, double &gxm, double &gxp) {
+  gxm = (fc - fm) / dxm;
+  gxp = (fp - fc) / dxp;
+  return 0.5 * (sign_of(gxm) + sign_of(gxp)) * fmin(fabs(gxm), fabs(gxp));
+}
+
+__device__ __forceinline__ bool cell_of(const pb2_prores_region &r, uint32_t e, int &c, int &k,
+                                        int &j, int &i) {
+  const uint32_t total = (uint32_t)r.ncomp * r.n[0] * r.n[1] * r.n[2];
+  if (e >= total) return false;
+  i = e % r.n[0];
+  uint32_t t = e / r.n[0];
+  j = t % r.n[1];
+  t /= r.n[1];
+  k = t % r.n[2];
+  c = t / r.n[2];
+  i += r.s[0];
+  j += r.s[1];
+  k += r.s[2];
+  return true;
+}
+
+// RestrictAverage::Do pr_ops.hpp:105-165 (uniform Cartesian: every fine cell has the same
+// volume dx1*dx2*dx3, uniform_cartesian.hpp:39; the weighted form is kept for bit parity)
+__global__ void __launch_bounds__(kPrThreads)
+    restrict_kernel(const pb2_prores_region *__restrict__ regions,
+                    const Chunk *__restrict__ chunks) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_prores_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+  const double cellvol = r.fine_dx[0] * r.fine_dx[1] * r.fine_dx[2];
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    int c, ck, cj, ci;
+    if (!cell_of(r, ch.first_vec + u * kPrThreads + threadIdx.x, c, ck, cj, ci)) continue;
+    const int i = (ci - r.coarse_is[0]) * 2 + r.fine_is[0];
+    const int j = DIM > 1 ? (cj - r.coarse_is[1]) * 2 + r.fine_is[1] : r.fine_is[1];
+    const int k = DIM > 2 ? (ck - r.coarse_is[2]) * 2 + r.fine_is[2] : r.fine_is[2];
+    const double *f = r.fine + (int64_t)c * r.fine_stride_c;
+    double vol[2][2][2], terms[2][2][2];
+#pragma unroll
+    for (int ok = 0; ok < 2; ++ok)
+#pragma unroll
+      for (int oj = 0; oj < 2; ++oj)
+#pragma unroll
+        for (int oi = 0; oi < 2; ++oi) {
+          const bool on = (ok == 0 || DIM > 2) && (oj == 0 || DIM > 1);
+          vol[ok][oj][oi] = on ? cellvol : 0.0;
+          terms[ok][oj][oi] =
+              on ? vol[ok][oj][oi] * f[(int64_t)(k + ok) * r.fine_stride_k +
+                                       (int64_t)(j + oj) * r.fine_stride_j + (i + oi)]
+                 : 0.0;
+        }
+    const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                        ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+    r.coarse[(int64_t)c * r.coarse_stride_c + (int64_t)ck * r.coarse_stride_k +
+             (int64_t)cj * r.coarse_stride_j + ci] =
+        (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+         ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+        tvol;
+  }
+}
+
+// ProlongateSharedGeneral::Do pr_ops.hpp:167-280, cell centred; GetGridSpacings :76-93 with
+// UniformCartesian::X (uniform_cartesian.hpp:166-178)
+__global__ void __launch_bounds__(kPrThreads)
+    prolongate_kernel(const pb2_prores_region *__restrict__ regions,
+                      const Chunk *__restrict__ chunks, int op) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_prores_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    int c, k, j, i;
+    if (!cell_of(r, ch.first_vec + u * kPrThreads + threadIdx.x, c, k, j, i)) continue;
+    const int fi = (i - r.coarse_is[0]) * 2 + r.fine_is[0];
+    const int fj = DIM > 1 ? (j - r.coarse_is[1]) * 2 + r.fine_is[1] : r.fine_is[1];
+    const int fk = DIM > 2 ? (k - r.coarse_is[2]) * 2 + r.fine_is[2] : r.fine_is[2];
+    const double *cs = r.coarse + (int64_t)c * r.coarse_stride_c +
+                       (int64_t)k * r.coarse_stride_k + (int64_t)j * r.coarse_stride_j + i;
+    const double fc = cs[0];
+    double gm[3] = {0, 0, 0}, gp[3] = {0, 0, 0}, dxfm[3] = {0, 0, 0}, dxfp[3] = {0, 0, 0};
+    const int cc[3] = {i, j, k}, ff[3] = {fi, fj, fk};
+    const int64_t cstr[3] = {1, r.coarse_stride_j, r.coarse_stride_k};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d < DIM) {
+        const double xm = r.coarse_xmin[d] + ((cc[d] - 1) + 0.5) * r.coarse_dx[d];
+        const double xc = r.coarse_xmin[d] + (cc[d] + 0.5) * r.coarse_dx[d];
+        const double xp = r.coarse_xmin[d] + ((cc[d] + 1) + 0.5) * r.coarse_dx[d];
+        const double dxm = xc - xm, dxp = xp - xc;
+        const double fxm = r.fine_xmin[d] + (ff[d] + 0.5) * r.fine_dx[d];
+        const double fxp = r.fine_xmin[d] + ((ff[d] + 1) + 0.5) * r.fine_dx[d];
+        dxfm[d] = xc - fxm;
+        dxfp[d] = fxp - xc;
+        double gxm, gxp;
+        const double gc = grad_minmod(fc, cs[-cstr[d]], cs[cstr[d]], dxm, dxp, gxm, gxp);
+        if (op == PB2_PROLONG_MINMOD) {
+          gm[d] = gc;
+          gp[d] = gc;
+        } else if (op == PB2_PROLONG_LINEAR) {
+          gm[d] = gxm;
+          gp[d] = gxp;
+        } // piecewise constant: zero slopes
+      }
+    }
+    const double gx1m = gm[0], gx1p = gp[0], gx2m = gm[1], gx2p = gp[1], gx3m = gm[2],
+                 gx3p = gp[2];
+    const double dx1fm = dxfm[0], dx1fp = dxfp[0], dx2fm = dxfm[1], dx2fp = dxfp[1],
+                 dx3fm = dxfm[2], dx3fp = dxfp[2];
+    double *f = r.fine + (int64_t)c * r.fine_stride_c + (int64_t)fk * r.fine_stride_k +
+                (int64_t)fj * r.fine_stride_j + fi;
+    const int64_t sj = r.fine_stride_j, sk = r.fine_stride_k;
+    f[0] = fc - (gx1m * dx1fm + gx2m * dx2fm + gx3m * dx3fm);
+    f[1] = fc + (gx1p * dx1fp - gx2m * dx2fm - gx3m * dx3fm);
+    if (DIM > 1) {
+      f[sj] = fc - (gx1m * dx1fm - gx2p * dx2fp + gx3m * dx3fm);
+      f[sj + 1] = fc + (gx1p * dx1fp + gx2p * dx2fp - gx3m * dx3fm);
+    }
+    if (DIM > 2) {
+      f[sk] = fc - (gx1m * dx1fm + gx2m * dx2fm - gx3p * dx3fp);
+      f[sk + 1] = fc + (gx1p * dx1fp - gx2m * dx2fm + gx3p * dx3fp);
+      f[sk + sj] = fc - (gx1m * dx1fm - gx2p * dx2fp - gx3p * dx3fp);
+      f[sk + sj + 1] = fc + (gx1p * dx1fp + gx2p * dx2fp + gx3p * dx3fp);
+    }
+  }
+}
+
+} // namespace pb2
+
+using namespace pb2;
+
+extern "C" {
+
+int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regions,
+                            int64_t n) {
+  PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
+  if (int rc = require_device()) return rc;
+  std::vector<Chunk> chunks;
+  int64_t elements = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    const int64_t total =
+        (int64_t)regions[r].ncomp * regions[r].n[0] * regions[r].n[1] * regions[r].n[2];
+    PB2_REQUIRE(total >= 0 && total < (1ll << 31), "bad region extent");
+    elements += total;
+    for (int64_t v = 0; v < total; v += kPrThreads * kPrPerThread)
+      chunks.push_back(Chunk{static_cast<int32_t>(r), static_cast<uint32_t>(v)});
+  }
+  auto *t = new pb2_bnd_table();
+  t->kind = kProRes;
+  t->nregions = n;
+  t->nchunks = static_cast<int64_t>(chunks.size());
+  t->elements = elements;
+  t->d_regions = nullptr;
+  t->d_chunks = nullptr;
+  t->d_prores = nullptr;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc(&t->d_prores, n * sizeof(pb2_prores_region));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(t->d_prores, regions, n * sizeof(pb2_prores_region),
+                     cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !chunks.empty())
+      e = cudaMemcpy(t->d_chunks, chunks.data(), chunks.size() * sizeof(Chunk),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error("prores table upload failed: %s", cudaGetErrorString(e));
+      cudaFree(t->d_prores);
+      cudaFree(t->d_chunks);
+      delete t;
+      return PB2_ERR_CUDA;
+    }
+  }
+  *table = t;
+  return PB2_OK;
+}
+
+int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kProRes, "restrict needs a prores table");
+  if (table->nchunks == 0) return PB2_OK;
+  restrict_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                    as_stream(stream)>>>(table->d_prores, table->d_chunks);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
+  PB2_REQUIRE(op >= 0 && op <= 2, "unknown prolongation operator");
+  if (table->nchunks == 0) return PB2_OK;
+  prolongate_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                      as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,113 @@
+// update.cu — dense per-stage updates (reference src/interface/update.hpp:43-91,
+// update.cpp:63-86).  Compiled with -fmad=false: these are memory-bound, so keeping the
+// reference's rounding costs nothing.
+#include "common.cuh"
+
+namespace pb2 {
+
+// z = w1*x + w2*y (WeightedSumData update.hpp:71-91); 16-byte vectors, grid-stride
+__global__ void __launch_bounds__(256)
+    weighted_sum_kernel(const double *__restrict__ x, const double *__restrict__ y, double w1,
+                        double w2, double *__restrict__ z, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                     reinterpret_cast<uintptr_t>(z)) & 15u) == 0;
+  if (vec) {
+    const int64_t nv = n / 2;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    const double2 *y2 = reinterpret_cast<const double2 *>(y);
+    double2 *z2 = reinterpret_cast<double2 *>(z);
+    for (int64_t v = i; v < nv; v += stride) {
+      const double2 a = x2[v], b = y2[v];
+      double2 c;
+      c.x = w1 * a.x + w2 * b.x;
+      c.y = w1 * a.y + w2 * b.y;
+      z2[v] = c;
+    }
+    if (i == 0 && (n & 1)) z[n - 1] = w1 * x[n - 1] + w2 * y[n - 1];
+  } else {
+    for (; i < n; i += stride) z[i] = w1 * x[i] + w2 * y[i];
+  }
+}
+
+struct DivGeom {
+  int nblocks, ncomp, ndim;
+  int nx[3], is[3], n[3];
+  int64_t sj, sk, sc, sb;
+};
+
+// FluxDivergence<MeshData> update.cpp:63-86 + FluxDivHelper update.hpp:43-58
+__global__ void __launch_bounds__(256)
+    flux_div_kernel(const DivGeom g, const double *__restrict__ fx,
+                    const double *__restrict__ fy, const double *__restrict__ fz,
+                    const double *__restrict__ dx, double *__restrict__ dudt) {
+  const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
+  const int ctas_per_block = (ncell + 255) / 256;
+  const int b = blockIdx.x / ctas_per_block;
+  const int t = (blockIdx.x % ctas_per_block) * 256 + threadIdx.x;
+  if (t >= ncell) return;
+  const int i = g.is[0] + t % g.nx[0];
+  const int tj = t / g.nx[0];
+  const int j = g.is[1] + tj % g.nx[1];
+  const int k = g.is[2] + tj / g.nx[1];
+  const int64_t p = (int64_t)b * g.sb + (int64_t)k * g.sk + (int64_t)j * g.sj + i;
+  const double dx0 = dx[3 * b], dx1 = dx[3 * b + 1], dx2 = dx[3 * b + 2];
+  const double a1 = dx1 * dx2, a2 = dx0 * dx2, a3 = dx0 * dx1, vol = dx0 * dx1 * dx2;
+  for (int n = 0; n < g.ncomp; ++n) {
+    const int64_t q = p + n * g.sc;
+    double du = (a1 * fx[q + 1] - a1 * fx[q]);
+    if (g.ndim >= 2) du += (a2 * fy[q + g.sj] - a2 * fy[q]);
+    if (g.ndim == 3) du += (a3 * fz[q + g.sk] - a3 * fz[q]);
+    dudt[q] = -du / vol;
+  }
+}
+
+} // namespace pb2
+
+using namespace pb2;
+
+extern "C" {
+
+int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, double *z,
+                     int64_t n, pb2_stream_t stream) {
+  PB2_REQUIRE(x && y && z && n >= 0, "bad arguments");
+  if (int rc = require_device()) return rc;
+  if (n == 0) return PB2_OK;
+  int64_t ctas = (n / 2 + 255) / 256;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  if (ctas < 1) ctas = 1;
+  weighted_sum_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(x, y, w1, w2,
+                                                                                 z, n);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_flux_divergence(const pb2_pack_geom *pg, const double *const flux[3], double *dudt,
+                        pb2_stream_t stream) {
+  PB2_REQUIRE(pg && flux && dudt && pg->dx, "bad arguments");
+  if (int rc = require_device()) return rc;
+  DivGeom g;
+  g.nblocks = pg->nblocks;
+  g.ncomp = pg->ncomp;
+  g.ndim = pg->ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg->ndim;
+    g.nx[d] = sym ? 1 : pg->nx[d];
+    g.is[d] = sym ? 0 : pg->ng;
+    g.n[d] = sym ? 1 : pg->nx[d] + 2 * pg->ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg->block_stride;
+  const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
+  const int ctas = g.nblocks * ((ncell + 255) / 256);
+  if (ctas == 0) return PB2_OK;
+  flux_div_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, flux[0], flux[1], flux[2], pg->dx,
+                                                      dudt);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,143 @@
+"""Test helpers: build C-ABI region tables for a mesh from the ORACLE's index boxes.
+
+(The product's own table builder lives in the C++ host library and is tested separately;
+these helpers let the kernels be checked in isolation through the C ABI.)
+"""
+import numpy as np
+
+import oracle
+from parthenon_b200 import capi
+
+
+def dev_ptr(t):
+    return t.data_ptr()
+
+
+def strides(dims):
+    nk, nj, ni = dims
+    return ni, ni * nj, ni * nj * nk
+
+
+def region_boxes(mesh, ir_type, prores=False):
+    """[(block, nbr_index, (gid, level, ox1, ox2, ox3), s, n)] in (block, neighbor) order."""
+    out = []
+    for b in range(mesh.nblocks):
+        for n, nb in enumerate(mesh.neighbors(b)):
+            s, e = mesh.calc_indices(b, n, ir_type, prores)
+            ext = tuple(e[d] - s[d] + 1 for d in range(3))
+            out.append((b, n, nb, s, ext))
+    return out
+
+
+def match_send_region(mesh, b, nb):
+    """index (in (block, neighbor) order) of the region nb's block sends to b"""
+    first = np.cumsum([0] + [len(mesh.neighbors(q)) for q in range(mesh.nblocks)])
+    gid, _lvl, o1, o2, o3 = nb
+    for q, snb in enumerate(mesh.neighbors(gid)):
+        if snb[0] == b and snb[2:] == (-o1, -o2, -o3):
+            return int(first[gid] + q)
+    raise AssertionError("no matching send region")
+
+
+def build_bnd_tables(mesh, U_t, Uc_t, ncomp):
+    """send and recv pb2_bnd_region lists whose buffer layout equals oracle.pack's"""
+    loc_level = [mesh.block_loc(b)[0] for b in range(mesh.nblocks)]
+    sj, sk, sc = strides(mesh.dims)
+    csj, csk, csc = strides(mesh.cdims)
+    bs, cbs = ncomp * sc, ncomp * csc
+    send, recv = [], []
+    off = 0
+    offs = []
+    for (b, n, nb, s, ext) in region_boxes(mesh, 0):
+        coarse = nb[1] < loc_level[b]
+        r = capi.BndRegion()
+        r.var = (dev_ptr(Uc_t) + 8 * b * cbs) if coarse else (dev_ptr(U_t) + 8 * b * bs)
+        r.buf_off = off
+        r.s[:] = s
+        r.n[:] = ext
+        r.ncomp = ncomp
+        r.stride_j, r.stride_k, r.stride_c = (csj, csk, csc) if coarse else (sj, sk, sc)
+        r.flag_slot = -1
+        r.status = capi.REGION_ALLOCATED
+        r.value = 0.0
+        send.append(r)
+        offs.append(off)
+        off += ncomp * ext[0] * ext[1] * ext[2]
+    offs.append(off)
+    for (b, n, nb, s, ext) in region_boxes(mesh, 1):
+        coarse = nb[1] < loc_level[b]
+        r = capi.BndRegion()
+        r.var = (dev_ptr(Uc_t) + 8 * b * cbs) if coarse else (dev_ptr(U_t) + 8 * b * bs)
+        r.buf_off = offs[match_send_region(mesh, b, nb)]
+        r.s[:] = s
+        r.n[:] = ext
+        r.ncomp = ncomp
+        r.stride_j, r.stride_k, r.stride_c = (csj, csk, csc) if coarse else (sj, sk, sc)
+        r.flag_slot = -1
+        r.status = capi.REGION_ALLOCATED | capi.REGION_BUF_ALLOCATED
+        r.value = 0.0
+        recv.append(r)
+    return send, recv, off
+
+
+def build_copy_table(mesh, U_t, ncomp):
+    """fused sender-box -> receiver-box regions (uniform meshes)"""
+    sj, sk, sc = strides(mesh.dims)
+    bs = ncomp * sc
+    sends = region_boxes(mesh, 0)
+    regs = []
+    for (b, n, nb, s, ext) in region_boxes(mesh, 1):
+        sb, _sn, _snb, ss, sext = sends[match_send_region(mesh, b, nb)]
+        assert sext == ext
+        r = capi.CopyRegion()
+        r.src = dev_ptr(U_t) + 8 * sb * bs
+        r.dst = dev_ptr(U_t) + 8 * b * bs
+        r.ss[:] = ss
+        r.ds[:] = s
+        r.n[:] = ext
+        r.ncomp = ncomp
+        r.src_stride_j, r.src_stride_k, r.src_stride_c = sj, sk, sc
+        r.dst_stride_j, r.dst_stride_k, r.dst_stride_c = sj, sk, sc
+        r.flag_slot = -1
+        r.status = capi.REGION_ALLOCATED
+        regs.append(r)
+    return regs
+
+
+def block_dx(mesh):
+    dx = np.zeros((mesh.nblocks, 3))
+    xmin = np.zeros((mesh.nblocks, 3))
+    nx = [mesh._nx[0], mesh._nx[1], mesh._nx[2]]
+    for b in range(mesh.nblocks):
+        lo, hi = mesh.block_bounds(b)
+        dx[b] = (hi - lo) / np.array(nx)
+        xmin[b] = lo
+    return dx, xmin
+
+
+def make_geom(mesh, ncomp, dx_t):
+    g = capi.PackGeom()
+    g.nblocks, g.ncomp, g.ndim = mesh.nblocks, ncomp, mesh.ndim
+    g.nx[:] = [int(x) for x in mesh._nx]
+    g.ng = mesh.ng
+    g.block_stride = ncomp * int(np.prod(mesh.dims))
+    g.dx = dev_ptr(dx_t)
+    return g
+
+
+def refined_leaves(nrb, refine):
+    """leaves of a root grid of nrb^3 blocks where the root blocks listed in `refine`
+    (tuples lx1,lx2,lx3) are split once (2:1 balance is the caller's business)"""
+    rl = int(np.log2(nrb))
+    leaves = []
+    for k in range(nrb):
+        for j in range(nrb):
+            for i in range(nrb):
+                if (i, j, k) in refine:
+                    for dk in range(2):
+                        for dj in range(2):
+                            for di in range(2):
+                                leaves.append((rl + 1, 2 * i + di, 2 * j + dj, 2 * k + dk))
+                else:
+                    leaves.append((rl, i, j, k))
+    return np.array(leaves, dtype=np.int32)

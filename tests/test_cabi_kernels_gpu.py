@@ -1,0 +1,256 @@
+"""GPU parity tests of the hand-written kernels, called through the C ABI
+(include/parthenon_b200.h) and compared with the CPU oracle on the same seeded inputs.
+Bit-exact for pack/unpack/copy/restrict/prolongate and for the STRICT burgers build;
+<= 1e-12 relative for the FAST (FMA-contracted) burgers build."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from parthenon_b200 import capi
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rand_field(mesh, ncomp, seed, coarse=False):
+    rng = np.random.default_rng(seed)
+    shape = (mesh.nblocks, ncomp) + (mesh.cdims if coarse else mesh.dims)
+    return rng.standard_normal(shape)
+
+
+@pytest.mark.parametrize("ndim,nx,ng,nrb,ncomp", [
+    (3, (8, 8, 8), 4, (2, 2, 2), 3),
+    (3, (16, 8, 4), 2, (4, 4, 4), 2),
+    (3, (7, 9, 5), 2, (2, 2, 2), 1),     # odd extents: scalar path, non-power-of-2 divisors
+    (2, (16, 16), 2, (4, 4), 4),
+    (3, (32, 32, 32), 4, (2, 2, 2), 11),  # burgers block shape
+])
+def test_pack_unpack_copy_uniform(ndim, nx, ng, nrb, ncomp):
+    m = oracle.Mesh(ndim, nx, ng, nrb)
+    U = rand_field(m, ncomp, 1)
+    buf_ref, off = m.pack(U)
+    Uref = U.copy()
+    m.exchange(Uref)
+
+    Ud = torch.from_numpy(U).to(DEV)
+    dummy = torch.zeros(8, dtype=torch.float64, device=DEV)
+    send, recv, total = H.build_bnd_tables(m, Ud, dummy, ncomp)
+    assert total == buf_ref.size
+    ts, tr = capi.Table(send, "bnd"), capi.Table(recv, "bnd")
+    assert ts.elements == total and tr.elements == total
+    buf = torch.full((total,), float("nan"), dtype=torch.float64, device=DEV)
+    capi.check(capi.lib().pb2_pack(ts.h, buf.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy(), buf_ref)
+    capi.check(capi.lib().pb2_unpack(tr.h, buf.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(Ud.cpu().numpy(), Uref)
+
+    # fused same-device path
+    Ud2 = torch.from_numpy(U).to(DEV)
+    tc = capi.Table(H.build_copy_table(m, Ud2, ncomp), "copy")
+    capi.check(capi.lib().pb2_copy(tc.h, None, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(Ud2.cpu().numpy(), Uref)
+
+
+def test_exchange_idempotent_full_size():
+    """size-independent property at benchmark block shape: a second exchange changes
+    nothing, and ghost cells equal the periodic image of the interior"""
+    m = oracle.Mesh(3, (32, 32, 32), 4, (4, 4, 4))
+    ncomp = 11
+    Ud = torch.randn((m.nblocks, ncomp) + m.dims, dtype=torch.float64, device=DEV)
+    tc = capi.Table(H.build_copy_table(m, Ud, ncomp), "copy")
+    capi.check(capi.lib().pb2_copy(tc.h, None, None))
+    torch.cuda.synchronize()
+    once = Ud.clone()
+    capi.check(capi.lib().pb2_copy(tc.h, None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(once, Ud)
+    # block 0 (lx=0,0,0): its -x ghost slab equals the +x interior slab of block lx=(3,0,0)
+    locs = [m.block_loc(b)[1:] for b in range(m.nblocks)]
+    src = locs.index((3, 0, 0))
+    assert torch.equal(Ud[0, :, 4:36, 4:36, 0:4], Ud[src, :, 4:36, 4:36, 32:36])
+
+
+@pytest.mark.parametrize("recon,ng", [("weno5", 4), ("linear", 2)])
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_burgers_stage_vs_oracle(recon, ng, math):
+    m = oracle.Mesh(3, (16, 8, 8), ng, (2, 2, 2))
+    nscal = 3
+    ncomp = 3 + nscal
+    B = oracle.Burgers(m, num_scalars=nscal, recon=recon)
+    B.init()
+    B.step()  # a developed, non-trivial state with filled ghosts
+    U0 = B.U.copy()
+    dt = B.dt
+    # oracle: fluxes + stage 1 output (before exchange: compare interiors only)
+    B.calculate_fluxes(U0)
+    Fref = [B.flux(d).copy() for d in range(3)]
+
+    dx, _ = H.block_dx(m)
+    dxd = torch.from_numpy(dx).to(DEV)
+    Ud = torch.from_numpy(U0).to(DEV)
+    out = torch.zeros_like(Ud)
+    flux = [torch.zeros_like(Ud) for _ in range(3)]
+    derived = torch.zeros((m.nblocks,) + m.dims, dtype=torch.float64, device=DEV)
+    dtmin = torch.full((1,), np.finfo(np.float64).max, dtype=torch.float64, device=DEV)
+    a = capi.BurgersArgs()
+    a.geom = H.make_geom(m, ncomp, dxd)
+    a.recon = capi.RECON_WENO5 if recon == "weno5" else capi.RECON_LINEAR
+    a.math = capi.MATH_STRICT if math == "strict" else capi.MATH_FAST
+    a.u, a.base, a.out = Ud.data_ptr(), Ud.data_ptr(), out.data_ptr()
+    for d in range(3):
+        a.flux[d] = flux[d].data_ptr()
+    a.derived, a.dt_min = derived.data_ptr(), dtmin.data_ptr()
+    a.beta, a.dt = 1.0, dt
+    capi.check(capi.lib().pb2_burgers_stage(C.byref(a), None))
+    torch.cuda.synchronize()
+
+    g = m.ng
+    nk, nj, ni = m.dims
+    I = (slice(None), slice(None), slice(g, nk - g), slice(g, nj - g), slice(g, ni - g))
+    # flux faces the reference computes: x: i in [is, ie+1]; y: j in [js, je+1]; z likewise
+    Fx = (slice(None), slice(None), slice(g, nk - g), slice(g, nj - g), slice(g, ni - g + 1))
+    Fy = (slice(None), slice(None), slice(g, nk - g), slice(g, nj - g + 1), slice(g, ni - g))
+    Fz = (slice(None), slice(None), slice(g, nk - g + 1), slice(g, nj - g), slice(g, ni - g))
+    # oracle stage-1 result
+    lib = oracle.lib()
+    lib.orc_burgers_stage(B.h, 1)
+    # U1 is private to the oracle; recompute expected interior here from its pieces
+    a1, a2, a3 = dx[:, 1] * dx[:, 2], dx[:, 0] * dx[:, 2], dx[:, 0] * dx[:, 1]
+    vol = dx[:, 0] * dx[:, 1] * dx[:, 2]
+    sh = (-1, 1, 1, 1, 1)
+    fx, fy, fz = Fref
+    du = (a1.reshape(sh) * fx[:, :, g:nk - g, g:nj - g, g + 1:ni - g + 1]
+          - a1.reshape(sh) * fx[:, :, g:nk - g, g:nj - g, g:ni - g])
+    du = du + (a2.reshape(sh) * fy[:, :, g:nk - g, g + 1:nj - g + 1, g:ni - g]
+               - a2.reshape(sh) * fy[:, :, g:nk - g, g:nj - g, g:ni - g])
+    du = du + (a3.reshape(sh) * fz[:, :, g + 1:nk - g + 1, g:nj - g, g:ni - g]
+               - a3.reshape(sh) * fz[:, :, g:nk - g, g:nj - g, g:ni - g])
+    dudt = -du / vol.reshape(sh)
+    expect = 1.0 * (1.0 * U0[I] + 0.0 * U0[I]) + (1.0 * dt) * dudt
+
+    got_f = [f.cpu().numpy() for f in flux]
+    got = out.cpu().numpy()
+    if math == "strict":
+        assert np.array_equal(got_f[0][Fx], Fref[0][Fx])
+        assert np.array_equal(got_f[1][Fy], Fref[1][Fy])
+        assert np.array_equal(got_f[2][Fz], Fref[2][Fz])
+        assert np.array_equal(got[I], expect)
+    else:
+        tol = 1e-12  # north_star: evolved fields within 1e-12 relative
+        for gf, rf, S in zip(got_f, Fref, (Fx, Fy, Fz)):
+            scale = np.abs(rf[S]).max()
+            assert np.abs(gf[S] - rf[S]).max() <= tol * scale
+        assert np.abs(got[I] - expect).max() <= tol * np.abs(expect).max()
+    # derived and dt
+    v = got[I]
+    dref = 0.5 * v[:, 3] * (v[:, 0] ** 2 + v[:, 1] ** 2 + v[:, 2] ** 2)
+    np.testing.assert_allclose(derived.cpu().numpy()[:, g:nk - g, g:nj - g, g:ni - g], dref,
+                               rtol=1e-14, atol=0)
+    inv = 1.0 / (np.abs(v[:, 0]) / dx[:, 0].reshape(-1, 1, 1, 1)
+                 + np.abs(v[:, 1]) / dx[:, 1].reshape(-1, 1, 1, 1)
+                 + np.abs(v[:, 2]) / dx[:, 2].reshape(-1, 1, 1, 1))
+    assert dtmin.item() == inv.min()
+
+
+def test_burgers_history_vs_oracle():
+    m = oracle.Mesh(3, (8, 8, 8), 4, (2, 2, 2))
+    B = oracle.Burgers(m, num_scalars=2)
+    B.init()
+    B.step()
+    ref = B.history()
+    dx, xmin = H.block_dx(m)
+    dxd, xmd = torch.from_numpy(dx).to(DEV), torch.from_numpy(xmin).to(DEV)
+    Ud = torch.from_numpy(B.U.copy()).to(DEV)
+    g = H.make_geom(m, 5, dxd)
+    out = np.zeros(8)
+    lo, hi = np.full(3, -0.5), np.full(3, 0.5)
+    dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+    capi.check(capi.lib().pb2_burgers_history(C.byref(g), Ud.data_ptr(), xmd.data_ptr(), dp(lo),
+                                              dp(hi), dp(out), None))
+    np.testing.assert_allclose(out, ref, rtol=1e-13)
+
+
+def test_restrict_prolongate_multilevel():
+    """3-D two-level mesh: full exchange incl. restriction on send/set and min-mod
+    prolongation, bit-exact against the oracle (kernels are built with -fmad=false)."""
+    nrb, nx, ng, ncomp = 2, (8, 8, 8), 2, 2
+    leaves = H.refined_leaves(nrb, {(0, 0, 0)})
+    m = oracle.Mesh(3, nx, ng, (nrb,) * 3, leaves=leaves)
+    assert m.multilevel and m.nblocks == 15
+    U = rand_field(m, ncomp, 7)
+    Uc = np.zeros((m.nblocks, ncomp) + m.cdims)
+    Uref, Ucref = U.copy(), Uc.copy()
+    m.exchange(Uref, Ucref, prolongate=True)
+
+    Ud, Ucd = torch.from_numpy(U).to(DEV), torch.from_numpy(Uc).to(DEV)
+    send, recv, total = H.build_bnd_tables(m, Ud, Ucd, ncomp)
+    lvl = [m.block_loc(b)[0] for b in range(m.nblocks)]
+    sj, sk, sc = H.strides(m.dims)
+    csj, csk, csc = H.strides(m.cdims)
+    dx, xmin = H.block_dx(m)
+
+    def prores(b, s, ext):
+        r = capi.ProResRegion()
+        r.fine = Ud.data_ptr() + 8 * b * ncomp * sc
+        r.coarse = Ucd.data_ptr() + 8 * b * ncomp * csc
+        r.s[:] = s
+        r.n[:] = ext
+        r.ncomp = ncomp
+        r.fine_stride_j, r.fine_stride_k, r.fine_stride_c = sj, sk, sc
+        r.coarse_stride_j, r.coarse_stride_k, r.coarse_stride_c = csj, csk, csc
+        r.fine_is[:] = [ng] * 3
+        r.coarse_is[:] = [ng] * 3
+        r.ndim = 3
+        r.status = capi.REGION_ALLOCATED
+        for d in range(3):
+            r.fine_dx[d] = dx[b, d]
+            r.fine_xmin[d] = xmin[b, d] - ng * dx[b, d]
+            r.coarse_xmin[d] = (xmin[b, d] - ng * dx[b, d]) + ng * dx[b, d] * (1 - 2)
+            r.coarse_dx[d] = dx[b, d] * 2
+        return r
+
+    rs, rset, pro = [], [], []
+    for (b, n, nb, s, ext) in H.region_boxes(m, 0, prores=True):
+        if nb[1] < lvl[b]:
+            rs.append(prores(b, s, ext))
+    for b in range(m.nblocks):
+        nbs = m.neighbors(b)
+        restricted = any(nb[1] == lvl[b] - 1 for nb in nbs)
+        for n, nb in enumerate(nbs):
+            s, e = m.calc_indices(b, n, 1, True)
+            ext = tuple(e[d] - s[d] + 1 for d in range(3))
+            if nb[1] < lvl[b]:
+                pro.append(prores(b, s, ext))
+            elif restricted:
+                rset.append(prores(b, s, ext))
+    assert rs and rset and pro
+    L = capi.lib()
+    t_rs, t_rset, t_pro = (capi.Table(x, "prores") for x in (rs, rset, pro))
+    ts, tr = capi.Table(send, "bnd"), capi.Table(recv, "bnd")
+    buf = torch.zeros((total,), dtype=torch.float64, device=DEV)
+    capi.check(L.pb2_restrict(t_rs.h, None))
+    capi.check(L.pb2_pack(ts.h, buf.data_ptr(), None, None))
+    capi.check(L.pb2_unpack(tr.h, buf.data_ptr(), None, None))
+    capi.check(L.pb2_restrict(t_rset.h, None))
+    capi.check(L.pb2_prolongate(t_pro.h, capi.PROLONG_MINMOD, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(Ucd.cpu().numpy(), Ucref)
+    assert np.array_equal(Ud.cpu().numpy(), Uref)
+
+
+def test_weighted_sum_and_flux_div():
+    n = 100003
+    x = torch.randn(n, dtype=torch.float64, device=DEV)
+    y = torch.randn(n, dtype=torch.float64, device=DEV)
+    z = torch.empty_like(x)
+    capi.check(capi.lib().pb2_weighted_sum(x.data_ptr(), y.data_ptr(), 0.5, 0.25, z.data_ptr(),
+                                           n, None))
+    torch.cuda.synchronize()
+    assert torch.equal(z, 0.5 * x + 0.25 * y)
