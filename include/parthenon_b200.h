@@ -62,6 +62,14 @@ int pb2_event_sync(pb2_event_t ev);
 int pb2_event_query(pb2_event_t ev); /* 0 done, 1 not yet */
 int pb2_stream_wait_event(pb2_stream_t stream, pb2_event_t ev);
 int pb2_event_elapsed_ms(pb2_event_t start, pb2_event_t stop, float *ms);
+/* optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline
+ * figures).  enable(1) brackets every launch with an event pair; get() synchronises the
+ * device and returns the accumulated device time and launch count of kernel class `id`
+ * (0 <= id < pb2_profile_kernels()). */
+int pb2_profile_enable(int on);
+int pb2_profile_reset(void);
+int pb2_profile_kernels(void);
+int pb2_profile_get(int id, const char **name, double *total_ms, int64_t *launches);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 int64_t pb2_launch_count(void);
 
@@ -216,6 +224,11 @@ int pb2_burgers_calculate_fluxes(const pb2_burgers_args *args, pb2_stream_t stre
 int pb2_burgers_update(const pb2_burgers_args *args, pb2_stream_t stream);
 /* both of the above, one call per stage */
 int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream);
+/* stand-alone CalculateDerived (burgers_package.cpp:143-167) and/or EstimateTimestepMesh
+ * (:170-200) over interior cells: derived [nblocks][nk][nj][ni] or NULL; dt_min device scalar
+ * (initialised to +huge by the caller) or NULL */
+int pb2_burgers_derived_dt(const pb2_pack_geom *g, const double *u, double *derived,
+                           double *dt_min, pb2_stream_t stream);
 /* 8 octant mass histories (MassHistory, burgers_package.cpp:406-439) -> host out[8] */
 int pb2_burgers_history(const pb2_pack_geom *g, const double *u, const double *block_xmin,
                         const double mesh_xmin[3], const double mesh_xmax[3],
@@ -237,6 +250,8 @@ int pb2_comm_exchange(pb2_comm *comm, const double *send_slab, const int64_t *se
                       double *recv_slab, const int64_t *recv_off, pb2_stream_t stream);
 /* in-place min all-reduce of one double (replaces MPI_Allreduce, driver.cpp:237) */
 int pb2_comm_allreduce_min(pb2_comm *comm, double *dev_value, pb2_stream_t stream);
+/* in-place sum all-reduce of n doubles (history reductions, MPI_Reduce in outputs/history.cpp) */
+int pb2_comm_allreduce_sum(pb2_comm *comm, double *dev_values, int64_t n, pb2_stream_t stream);
 int pb2_comm_barrier(pb2_comm *comm, pb2_stream_t stream);
 
 #ifdef __cplusplus

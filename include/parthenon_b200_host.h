@@ -1,0 +1,91 @@
+/* parthenon_b200_host.h — C entry points of the C++ host framework (libpb200_host.so).
+ *
+ * The host framework mirrors Parthenon's application API in C++ (namespace parthenon:
+ * ParameterInput, Metadata, StateDescriptor, Mesh, MeshData, TaskList, MultiStageDriver,
+ * SendBoundBufs/ReceiveBoundBufs/SetBounds/ProlongateBounds — headers under
+ * parthenon_b200/host/pb2/) and reaches the GPU only through include/parthenon_b200.h.
+ * These functions expose a running application (ParthenonManager + driver, reference
+ * src/parthenon_manager.cpp, src/driver/driver.cpp:67-193) to non-C++ callers: bench.py,
+ * the parity tests, language bindings.  All return 0 on success, <0 on error
+ * (pb2h_last_error()); exceptions never cross this boundary.
+ */
+#ifndef PARTHENON_B200_HOST_H_
+#define PARTHENON_B200_HOST_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb2h_sim pb2h_sim;
+
+const char *pb2h_last_error(void);
+
+/* Build an application: parse `deck` (Athena++-style input text, reference
+ * src/parameter_input.cpp) plus newline-separated "block/key=value" overrides, create the
+ * packages, the mesh (rank `rank` of `nranks` GPUs; nccl_id = 128-byte id from
+ * pb2_comm_unique_id when nranks > 1), run the problem generator, the first ghost exchange
+ * and FillDerived (Mesh::Initialize, mesh.cpp:745).  app: "burgers".
+ * leaves: optional explicit leaf list (level, lx1, lx2, lx3) x nleaves, else NULL/0. */
+int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const char *overrides,
+                    int rank, int nranks, const uint8_t *nccl_id, const int *leaves,
+                    int nleaves);
+/* Mesh topology only (no device is touched): for CPU-side tests of partitioning,
+ * neighbour lists, index boxes and slab layouts. */
+int pb2h_topology_create(pb2h_sim **sim, const char *deck, const char *overrides, int rank,
+                         int nranks, const int *leaves, int nleaves);
+int pb2h_sim_destroy(pb2h_sim *sim);
+
+/* EvolutionDriver pieces (driver.cpp:67-193): what Execute does before its loop, N cycles
+ * of the loop body, or the whole thing */
+int pb2h_sim_pre_execute(pb2h_sim *sim);
+int pb2h_sim_cycle(pb2h_sim *sim, int ncycles);
+int pb2h_sim_execute(pb2h_sim *sim);
+int pb2h_sim_sync(pb2h_sim *sim);
+void *pb2h_sim_stream(pb2h_sim *sim); /* cudaStream_t the application enqueues on */
+double pb2h_sim_time(pb2h_sim *sim);
+double pb2h_sim_dt(pb2h_sim *sim);
+int pb2h_sim_ncycle(pb2h_sim *sim);
+int pb2h_sim_set_dt(pb2h_sim *sim, double dt);
+double pb2h_sim_zone_cycles_per_second(pb2h_sim *sim);
+
+/* out: ndim, nbtotal, nblocks on this rank, ni, nj, nk (with ghosts), coarse ni, nj, nk,
+ * multilevel, first gid of this rank, nghost */
+int pb2h_sim_info(pb2h_sim *sim, int out[12]);
+int pb2h_sim_block(pb2h_sim *sim, int lid, int loc[4], double xmin[3], double xmax[3],
+                   int *gid, int *nneighbors);
+/* out: gid, level, ox1, ox2, ox3, rank */
+int pb2h_sim_neighbor(pb2h_sim *sim, int lid, int n, int out[6]);
+/* ir_type 0 = BoundaryInteriorSend, 1 = BoundaryExteriorRecv (bnd_info.cpp:105-252) */
+int pb2h_sim_calc_indices(pb2h_sim *sim, int lid, int n, int ir_type, int prores, int s[3],
+                          int e[3]);
+int pb2h_sim_ranklist(pb2h_sim *sim, int *ranks, int n);
+/* channel plan of this rank for one ncomp-component field.  kind 0 local, 1 send, 2 recv;
+ * rows (7 int64 each): sender gid, receiver gid, var, offset index, slab offset, Reals,
+ * peer rank.  seg_off: [npeers+1] slab segment offsets (kinds 1,2).  Returns the count. */
+int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t max_rows,
+                      int64_t *seg_off);
+
+/* field access: which = 0 data, 1..3 flux X1..X3, 4 coarse buffer.  Layout
+ * [block][component][k][j][i] over this rank's blocks. */
+int pb2h_sim_field_ptr(pb2h_sim *sim, const char *container, const char *field, int which,
+                       void **dev_ptr, int64_t *nreal);
+int pb2h_sim_get_field(pb2h_sim *sim, const char *container, const char *field, int which,
+                       double *host, int64_t nreal);
+int pb2h_sim_set_field(pb2h_sim *sim, const char *container, const char *field, int which,
+                       const double *host, int64_t nreal);
+
+/* one full ghost exchange of a container (Send -> Receive -> Set [-> Prolongate]),
+ * Mesh::CommunicateBoundaries mesh.cpp:640-706 */
+int pb2h_sim_exchange(pb2h_sim *sim, const char *container, int prolongate);
+int pb2h_sim_exchange_phase(pb2h_sim *sim, const char *container, int phase);
+/* Reals one exchange moves on this rank (ghost cells filled x components) */
+int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t *local,
+                                   int64_t *nonlocal);
+/* the history columns "MS Mass 0..7" of the burgers benchmark, reduced over ranks */
+int pb2h_sim_history(pb2h_sim *sim, double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARTHENON_B200_HOST_H_ */

@@ -70,12 +70,14 @@ SYMBOLS = [
     "pb2_stream_destroy", "pb2_stream_sync", "pb2_device_sync", "pb2_event_create",
     "pb2_event_destroy", "pb2_event_record", "pb2_event_sync", "pb2_event_query",
     "pb2_stream_wait_event", "pb2_event_elapsed_ms", "pb2_launch_count",
+    "pb2_profile_enable", "pb2_profile_reset", "pb2_profile_kernels", "pb2_profile_get",
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
     "pb2_restrict", "pb2_prolongate", "pb2_weighted_sum", "pb2_flux_divergence",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
-    "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
-    "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_barrier",
+    "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
+    "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
+    "pb2_comm_barrier",
 ]
 
 
@@ -127,6 +129,23 @@ def lib():
 def check(rc):
     if rc != PB2_OK:
         raise RuntimeError(f"libpb200 error {rc}: {lib().pb2_last_error().decode()}")
+
+
+def profile(enable=None, reset=False):
+    """per-kernel device time measured with CUDA events: {name: (total_ms, launches)}"""
+    L = lib()
+    if reset:
+        check(L.pb2_profile_reset())
+    if enable is not None:
+        check(L.pb2_profile_enable(int(enable)))
+        return None
+    out = {}
+    for i in range(L.pb2_profile_kernels()):
+        name, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+        check(L.pb2_profile_get(i, C.byref(name), C.byref(ms), C.byref(n)))
+        if n.value:
+            out[name.value.decode()] = (ms.value, n.value)
+    return out
 
 
 def launch_count():

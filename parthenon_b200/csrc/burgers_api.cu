@@ -25,6 +25,62 @@ static int check_args(const pb2_burgers_args *a, bool need_update) {
   return PB2_OK;
 }
 
+struct CellGeom {
+  int nblocks, ncomp, ndim;
+  int nx[3], is[3], n[3];
+  int64_t sj, sk, sc, sb;
+};
+
+static void make_cell_geom(const pb2_pack_geom &pg, CellGeom &g) {
+  g.nblocks = pg.nblocks;
+  g.ncomp = pg.ncomp;
+  g.ndim = pg.ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg.ndim;
+    g.nx[d] = sym ? 1 : pg.nx[d];
+    g.is[d] = sym ? 0 : pg.ng;
+    g.n[d] = sym ? 1 : pg.nx[d] + 2 * pg.ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg.block_stride;
+}
+
+// CalculateDerived burgers_package.cpp:143-167 and EstimateTimestepMesh :170-200 as
+// stand-alone passes (the fused stage kernel produces both on the fly)
+__global__ void __launch_bounds__(256)
+    derived_dt_kernel(const CellGeom g, const double *__restrict__ u,
+                      const double *__restrict__ dx, double *__restrict__ derived,
+                      unsigned long long *__restrict__ dtmin) {
+  const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
+  const int ctas_per_block = (ncell + 255) / 256;
+  const int b = blockIdx.x / ctas_per_block;
+  const int t = (blockIdx.x % ctas_per_block) * 256 + threadIdx.x;
+  double inv = DBL_MAX;
+  if (t < ncell) {
+    const int i = g.is[0] + t % g.nx[0];
+    const int tj = t / g.nx[0];
+    const int j = g.is[1] + tj % g.nx[1];
+    const int k = g.is[2] + tj / g.nx[1];
+    const int64_t cell = (int64_t)k * g.sk + (int64_t)j * g.sj + i;
+    const int64_t p = (int64_t)b * g.sb + cell;
+    const double u0 = u[p], u1 = u[p + g.sc], u2 = u[p + 2 * g.sc];
+    if (derived) derived[(int64_t)b * g.sc + cell] = 0.5 * u[p + 3 * g.sc] * (u0 * u0 + u1 * u1 + u2 * u2);
+    const double dx0 = dx[3 * b], dx1 = dx[3 * b + 1], dx2 = dx[3 * b + 2];
+    inv = 1.0 / ((fabs(u0)) / dx0 + (g.ndim > 1) * (fabs(u1)) / dx1 + (g.ndim > 2) * (fabs(u2)) / dx2);
+  }
+  if (dtmin) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, inv, s);
+      inv = (o < inv) ? o : inv;
+    }
+    if ((threadIdx.x & 31) == 0)
+      atomicMin(dtmin, static_cast<unsigned long long>(__double_as_longlong(inv)));
+  }
+}
+
 // MassHistory burgers_package.cpp:406-439: out[o] = sum mask_o * q^2 * vol / (mesh_vol+1e-20)
 struct HistGeom {
   int nblocks, ncomp, ndim;
@@ -124,6 +180,23 @@ int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream) {
   return pb2_burgers_update(args, stream);
 }
 
+int pb2_burgers_derived_dt(const pb2_pack_geom *pg, const double *u, double *derived,
+                           double *dt_min, pb2_stream_t stream) {
+  PB2_REQUIRE(pg && u && pg->dx && (derived || dt_min), "bad arguments");
+  PB2_REQUIRE(pg->ncomp >= 4, "ncomp must be >= 4");
+  if (int rc = require_device()) return rc;
+  if (pg->nblocks == 0) return PB2_OK;
+  CellGeom g;
+  make_cell_geom(*pg, g);
+  const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
+  const int ctas = g.nblocks * ((ncell + 255) / 256);
+  ProfScope prof(K_DERIVED_DT, as_stream(stream));
+  derived_dt_kernel<<<ctas, 256, 0, as_stream(stream)>>>(
+      g, u, pg->dx, derived, reinterpret_cast<unsigned long long *>(dt_min));
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
 int pb2_burgers_history(const pb2_pack_geom *pg, const double *u, const double *block_xmin,
                         const double mesh_xmin[3], const double mesh_xmax[3], double out[8],
                         pb2_stream_t stream) {
@@ -155,6 +228,7 @@ int pb2_burgers_history(const pb2_pack_geom *pg, const double *u, const double *
   double *partial = nullptr, *dout = nullptr;
   PB2_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(double) * 8 * (size_t)nct, as_stream(stream)));
   PB2_CUDA_CHECK(cudaMallocAsync(&dout, sizeof(double) * 8, as_stream(stream)));
+  ProfScope prof(K_HISTORY, as_stream(stream));
   history_kernel<<<nct, 256, 0, as_stream(stream)>>>(g, u, pg->dx, block_xmin, partial);
   PB2_LAUNCH_CHECK();
   history_final_kernel<<<8, 256, 0, as_stream(stream)>>>(partial, nct, dout);

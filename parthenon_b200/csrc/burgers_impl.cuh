@@ -378,6 +378,7 @@ int launch_fluxes_t(const pb2_burgers_args *args, cudaStream_t st) {
     const int nrows = g.nx[1] * g.nx[2];
     const int warps = g.nblocks * ((nrows + kRowsPerWarp - 1) / kRowsPerWarp);
     const int wpc = kFluxThreads / 32;
+    ProfScope prof(K_FLUX_X, st);
     flux_x_kernel<RECON><<<(warps + wpc - 1) / wpc, kFluxThreads, 0, st>>>(g, args->u,
                                                                           args->flux[0]);
     PB2_LAUNCH_CHECK();
@@ -385,12 +386,14 @@ int launch_fluxes_t(const pb2_burgers_args *args, cudaStream_t st) {
   if (g.ndim > 1) {
     const int ncol = g.nx[2] * g.nx[0];
     const int ctas = g.nblocks * ((ncol + kFluxThreads - 1) / kFluxThreads);
+    ProfScope prof(K_FLUX_Y, st);
     flux_march_kernel<RECON, 1><<<ctas, kFluxThreads, 0, st>>>(g, args->u, args->flux[1]);
     PB2_LAUNCH_CHECK();
   }
   if (g.ndim > 2) {
     const int ncol = g.nx[1] * g.nx[0];
     const int ctas = g.nblocks * ((ncol + kFluxThreads - 1) / kFluxThreads);
+    ProfScope prof(K_FLUX_Z, st);
     flux_march_kernel<RECON, 2><<<ctas, kFluxThreads, 0, st>>>(g, args->u, args->flux[2]);
     PB2_LAUNCH_CHECK();
   }
@@ -418,6 +421,7 @@ inline int launch_update(const pb2_burgers_args *args, cudaStream_t st) {
   a.dt = args->dt;
   const int ncell = a.g.nx[0] * a.g.nx[1] * a.g.nx[2];
   const int ctas = a.g.nblocks * ((ncell + kUpdThreads - 1) / kUpdThreads);
+  ProfScope prof(K_UPDATE, st);
   update_kernel<<<ctas, kUpdThreads, 0, st>>>(a);
   PB2_LAUNCH_CHECK();
   return PB2_OK;

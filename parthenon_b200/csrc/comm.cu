@@ -23,7 +23,7 @@ typedef struct {
   char internal[128];
 } ncclUniqueId_t;
 typedef void *ncclComm_p;
-enum { kNcclFloat64 = 8, kNcclMin = 3 };
+enum { kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3 };
 
 struct NcclApi {
   void *handle = nullptr;
@@ -145,6 +145,14 @@ int pb2_comm_allreduce_min(pb2_comm *comm, double *dev_value, pb2_stream_t strea
   PB2_REQUIRE(comm && dev_value, "bad arguments");
   PB2_NCCL_CHECK(g_nccl.AllReduce(dev_value, dev_value, 1, kNcclFloat64, kNcclMin, comm->comm,
                                   as_stream(stream)));
+  return PB2_OK;
+}
+
+int pb2_comm_allreduce_sum(pb2_comm *comm, double *dev_values, int64_t n, pb2_stream_t stream) {
+  PB2_REQUIRE(comm && dev_values && n >= 0, "bad arguments");
+  if (n == 0) return PB2_OK;
+  PB2_NCCL_CHECK(g_nccl.AllReduce(dev_values, dev_values, static_cast<size_t>(n), kNcclFloat64,
+                                  kNcclSum, comm->comm, as_stream(stream)));
   return PB2_OK;
 }
 

@@ -45,6 +45,25 @@ inline cudaStream_t as_stream(pb2_stream_t s) { return reinterpret_cast<cudaStre
 
 int require_device();
 
+// ---- optional per-kernel timing with CUDA events (pb2_profile_* of the C ABI) ----------
+enum KernelId {
+  K_PACK = 0, K_UNPACK, K_COPY, K_RESTRICT, K_PROLONGATE, K_WEIGHTED_SUM, K_FLUX_DIV,
+  K_FLUX_X, K_FLUX_Y, K_FLUX_Z, K_UPDATE, K_DERIVED_DT, K_HISTORY, K_STAGE_FUSED, K_COUNT
+};
+extern std::atomic<int> g_profile_on;
+void profile_begin(int id, cudaStream_t s, void **token);
+void profile_end(void *token, cudaStream_t s);
+struct ProfScope {
+  void *token = nullptr;
+  cudaStream_t s;
+  ProfScope(int id, cudaStream_t st) : s(st) {
+    if (g_profile_on.load(std::memory_order_relaxed)) profile_begin(id, st, &token);
+  }
+  ~ProfScope() {
+    if (token) profile_end(token, s);
+  }
+};
+
 // Division by a runtime-constant 32-bit divisor with a precomputed magic number
 // (n must be < 2^31).  q = (umulhi(n, magic) + n) >> shift.
 struct FastDiv {

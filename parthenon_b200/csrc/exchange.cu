@@ -323,6 +323,7 @@ int pb2_pack(const pb2_bnd_table *table, double *buf, int32_t *nonzero_flags,
   PB2_REQUIRE(table && table->kind == kBnd, "pack needs a boundary table");
   if (table->nchunks == 0) return PB2_OK;
   PB2_REQUIRE(buf, "null buffer");
+  ProfScope prof(K_PACK, as_stream(stream));
   pack_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, buf, nonzero_flags);
   PB2_LAUNCH_CHECK();
@@ -334,6 +335,7 @@ int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *dat
   PB2_REQUIRE(table && table->kind == kBnd, "unpack needs a boundary table");
   if (table->nchunks == 0) return PB2_OK;
   PB2_REQUIRE(buf, "null buffer");
+  ProfScope prof(K_UNPACK, as_stream(stream));
   unpack_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, buf, data_flags);
   PB2_LAUNCH_CHECK();
@@ -343,6 +345,7 @@ int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *dat
 int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kCopy, "copy needs a copy table");
   if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_COPY, as_stream(stream));
   copy_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, nonzero_flags);
   PB2_LAUNCH_CHECK();

@@ -202,6 +202,7 @@ int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regi
 int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "restrict needs a prores table");
   if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_RESTRICT, as_stream(stream));
   restrict_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                     as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
@@ -212,6 +213,7 @@ int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
   PB2_REQUIRE(op >= 0 && op <= 2, "unknown prolongation operator");
   if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_PROLONGATE, as_stream(stream));
   prolongate_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                       as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
   PB2_LAUNCH_CHECK();

@@ -1,5 +1,7 @@
 // runtime.cu — plumbing entry points of the C ABI (device, memory, streams, events).
 #include <cstdarg>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -12,6 +14,63 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+std::atomic<int> g_profile_on{0};
+namespace {
+struct ProfPair {
+  int id;
+  cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+std::vector<ProfPair *> g_prof_pending, g_prof_free;
+double g_prof_ms[K_COUNT];
+int64_t g_prof_n[K_COUNT];
+const char *kKernelNames[K_COUNT] = {
+    "pack_kernel", "unpack_kernel", "copy_kernel", "restrict_kernel", "prolongate_kernel",
+    "weighted_sum_kernel", "flux_div_kernel", "flux_x_kernel", "flux_march_kernel<y>",
+    "flux_march_kernel<z>", "update_kernel", "derived_dt_kernel", "history_kernel",
+    "stage_fused_kernel"};
+} // namespace
+
+void profile_begin(int id, cudaStream_t s, void **token) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfPair *p = nullptr;
+  if (!g_prof_free.empty()) {
+    p = g_prof_free.back();
+    g_prof_free.pop_back();
+  } else {
+    p = new ProfPair();
+    if (cudaEventCreate(&p->a) != cudaSuccess || cudaEventCreate(&p->b) != cudaSuccess) {
+      cudaGetLastError();
+      delete p;
+      return;
+    }
+  }
+  p->id = id;
+  cudaEventRecord(p->a, s);
+  *token = p;
+}
+void profile_end(void *token, cudaStream_t s) {
+  ProfPair *p = static_cast<ProfPair *>(token);
+  cudaEventRecord(p->b, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_pending.push_back(p);
+}
+static void profile_collect() {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (ProfPair *p : g_prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p->a, p->b) == cudaSuccess) {
+      g_prof_ms[p->id] += ms;
+      g_prof_n[p->id] += 1;
+    } else {
+      cudaGetLastError();
+    }
+    g_prof_free.push_back(p);
+  }
+  g_prof_pending.clear();
 }
 
 int require_device() {
@@ -33,6 +92,28 @@ extern "C" {
 int pb2_version(void) { return 100; }
 const char *pb2_last_error(void) { return g_err; }
 int64_t pb2_launch_count(void) { return g_launches.load(); }
+
+int pb2_profile_enable(int on) {
+  g_profile_on.store(on ? 1 : 0);
+  return PB2_OK;
+}
+int pb2_profile_reset(void) {
+  profile_collect();
+  for (int i = 0; i < K_COUNT; ++i) {
+    g_prof_ms[i] = 0;
+    g_prof_n[i] = 0;
+  }
+  return PB2_OK;
+}
+int pb2_profile_kernels(void) { return K_COUNT; }
+int pb2_profile_get(int id, const char **name, double *total_ms, int64_t *launches) {
+  PB2_REQUIRE(id >= 0 && id < K_COUNT, "bad kernel id");
+  profile_collect();
+  if (name) *name = kKernelNames[id];
+  if (total_ms) *total_ms = g_prof_ms[id];
+  if (launches) *launches = g_prof_n[id];
+  return PB2_OK;
+}
 
 int pb2_device_count(int *count) {
   PB2_REQUIRE(count, "null argument");

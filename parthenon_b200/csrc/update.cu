@@ -77,6 +77,7 @@ int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, dou
   int64_t ctas = (n / 2 + 255) / 256;
   if (ctas > 148 * 16) ctas = 148 * 16;
   if (ctas < 1) ctas = 1;
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
   weighted_sum_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(x, y, w1, w2,
                                                                                  z, n);
   PB2_LAUNCH_CHECK();
@@ -104,6 +105,7 @@ int pb2_flux_divergence(const pb2_pack_geom *pg, const double *const flux[3], do
   const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
   const int ctas = g.nblocks * ((ncell + 255) / 256);
   if (ctas == 0) return PB2_OK;
+  ProfScope prof(K_FLUX_DIV, as_stream(stream));
   flux_div_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, flux[0], flux[1], flux[2], pg->dx,
                                                       dudt);
   PB2_LAUNCH_CHECK();

@@ -1,0 +1,294 @@
+"""ctypes binding of libpb200_host.so (include/parthenon_b200_host.h): the C++ host framework
+(ParameterInput / StateDescriptor / Mesh / MeshData / TaskList / BurgersDriver mirroring
+Parthenon's API) driven from Python for bench.py and the tests.
+
+Plumbing only — there is no Python fallback for anything: a missing library or a failing call
+raises RuntimeError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpb200_host.so")
+
+SYMBOLS = [
+    "pb2h_last_error", "pb2h_sim_create", "pb2h_topology_create", "pb2h_sim_destroy",
+    "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_execute", "pb2h_sim_sync",
+    "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
+    "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
+    "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_field_ptr",
+    "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
+    "pb2h_sim_exchange_elements", "pb2h_sim_history",
+]
+
+BURGERS_DECK = """
+<parthenon/job>
+problem_id = burgers
+<parthenon/mesh>
+nghost = 4
+refinement = none
+numlevel = 1
+nx1 = 64
+x1min = -0.5
+x1max = 0.5
+ix1_bc = periodic
+ox1_bc = periodic
+nx2 = 64
+x2min = -0.5
+x2max = 0.5
+ix2_bc = periodic
+ox2_bc = periodic
+nx3 = 64
+x3min = -0.5
+x3max = 0.5
+ix3_bc = periodic
+ox3_bc = periodic
+<parthenon/meshblock>
+nx1 = 32
+nx2 = 32
+nx3 = 32
+<parthenon/time>
+nlim = -1
+tlim = 1e9
+integrator = rk2
+ncycle_out = 0
+perf_cycle_offset = 0
+<burgers>
+cfl = 0.8
+recon = weno5
+num_scalars = 8
+"""
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                           "(there is no Python/CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64 = C.c_void_p, C.c_int64
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    L.pb2h_last_error.restype = C.c_char_p
+    L.pb2h_sim_create.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
+                                  C.c_int, C.c_char_p, ip, C.c_int]
+    L.pb2h_topology_create.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                       ip, C.c_int]
+    for f in ("pb2h_sim_destroy", "pb2h_sim_pre_execute", "pb2h_sim_execute", "pb2h_sim_sync"):
+        getattr(L, f).argtypes = [vp]
+    L.pb2h_sim_cycle.argtypes = [vp, C.c_int]
+    L.pb2h_sim_stream.restype = vp
+    L.pb2h_sim_stream.argtypes = [vp]
+    for f in ("pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_zone_cycles_per_second"):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [vp]
+    L.pb2h_sim_ncycle.argtypes = [vp]
+    L.pb2h_sim_set_dt.argtypes = [vp, C.c_double]
+    L.pb2h_sim_info.argtypes = [vp, ip]
+    L.pb2h_sim_block.argtypes = [vp, C.c_int, ip, dp, dp, ip, ip]
+    L.pb2h_sim_neighbor.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.pb2h_sim_calc_indices.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+    L.pb2h_sim_ranklist.argtypes = [vp, ip, C.c_int]
+    L.pb2h_sim_plan.restype = i64
+    L.pb2h_sim_plan.argtypes = [vp, C.c_int, C.c_int, C.POINTER(i64), i64, C.POINTER(i64)]
+    L.pb2h_sim_field_ptr.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp),
+                                     C.POINTER(i64)]
+    L.pb2h_sim_get_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
+    L.pb2h_sim_set_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
+    L.pb2h_sim_exchange.argtypes = [vp, C.c_char_p, C.c_int]
+    L.pb2h_sim_exchange_phase.argtypes = [vp, C.c_char_p, C.c_int]
+    L.pb2h_sim_exchange_elements.restype = i64
+    L.pb2h_sim_exchange_elements.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
+    L.pb2h_sim_history.argtypes = [vp, dp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libpb200_host: " + lib().pb2h_last_error().decode())
+
+
+def _overrides(ov):
+    if ov is None:
+        return b""
+    if isinstance(ov, dict):
+        ov = [f"{k}={v}" for k, v in ov.items()]
+    return "\n".join(ov).encode()
+
+
+def _leaves(leaves):
+    if leaves is None:
+        return None, 0
+    a = np.ascontiguousarray(leaves, dtype=np.int32)
+    return a, a.shape[0]
+
+
+FIELD_DATA, FIELD_FLUX1, FIELD_FLUX2, FIELD_FLUX3, FIELD_COARSE = 0, 1, 2, 3, 4
+
+
+class _Base:
+    h = None
+
+    def info(self):
+        o = (C.c_int * 12)()
+        check(lib().pb2h_sim_info(self.h, o))
+        keys = ["ndim", "nbtotal", "nblocks", "ni", "nj", "nk", "cni", "cnj", "cnk",
+                "multilevel", "first_gid", "nghost"]
+        return dict(zip(keys, [int(x) for x in o]))
+
+    def block(self, lid):
+        loc = (C.c_int * 4)()
+        lo, hi = (C.c_double * 3)(), (C.c_double * 3)()
+        gid, nn = C.c_int(), C.c_int()
+        check(lib().pb2h_sim_block(self.h, lid, loc, lo, hi, C.byref(gid), C.byref(nn)))
+        return dict(loc=tuple(loc), xmin=np.array(lo), xmax=np.array(hi), gid=gid.value,
+                    nneighbors=nn.value)
+
+    def neighbors(self, lid):
+        out = []
+        o = (C.c_int * 6)()
+        for n in range(self.block(lid)["nneighbors"]):
+            check(lib().pb2h_sim_neighbor(self.h, lid, n, o))
+            out.append(tuple(int(x) for x in o))
+        return out
+
+    def calc_indices(self, lid, n, ir_type, prores=False):
+        s, e = (C.c_int * 3)(), (C.c_int * 3)()
+        check(lib().pb2h_sim_calc_indices(self.h, lid, n, ir_type, int(prores), s, e))
+        return tuple(s), tuple(e)
+
+    def ranklist(self):
+        n = self.info()["nbtotal"]
+        a = np.zeros(n, dtype=np.int32)
+        check(lib().pb2h_sim_ranklist(self.h, a.ctypes.data_as(C.POINTER(C.c_int)), n))
+        return a
+
+    def plan(self, ncomp, kind):
+        """kind: 'local' | 'send' | 'recv' -> (rows[n,7], seg_off)"""
+        k = {"local": 0, "send": 1, "recv": 2}[kind]
+        n = lib().pb2h_sim_plan(self.h, ncomp, k, None, 0, None)
+        if n < 0:
+            check(-1)
+        rows = np.zeros((max(n, 1), 7), dtype=np.int64)
+        seg = np.zeros(4096, dtype=np.int64)
+        p64 = C.POINTER(C.c_int64)
+        lib().pb2h_sim_plan(self.h, ncomp, k, rows.ctypes.data_as(p64), n, seg.ctypes.data_as(p64))
+        return rows[:n], seg
+
+    def close(self):
+        if self.h:
+            lib().pb2h_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Topology(_Base):
+    """Mesh topology only; touches no device (CPU tests)."""
+
+    def __init__(self, deck=BURGERS_DECK, overrides=None, rank=0, nranks=1, leaves=None):
+        self.h = C.c_void_p()
+        la, n = _leaves(leaves)
+        check(lib().pb2h_topology_create(C.byref(self.h), deck.encode(), _overrides(overrides),
+                                         rank, nranks,
+                                         la.ctypes.data_as(C.POINTER(C.c_int)) if n else None, n))
+
+
+class Simulation(_Base):
+    """A running application on the GPU (ParthenonManager + BurgersDriver)."""
+
+    def __init__(self, app="burgers", deck=BURGERS_DECK, overrides=None, rank=0, nranks=1,
+                 nccl_id=None, leaves=None):
+        self.h = C.c_void_p()
+        la, n = _leaves(leaves)
+        check(lib().pb2h_sim_create(C.byref(self.h), app.encode(), deck.encode(),
+                                    _overrides(overrides), rank, nranks, nccl_id,
+                                    la.ctypes.data_as(C.POINTER(C.c_int)) if n else None, n))
+
+    def pre_execute(self):
+        check(lib().pb2h_sim_pre_execute(self.h))
+
+    def cycle(self, n=1):
+        check(lib().pb2h_sim_cycle(self.h, n))
+
+    def execute(self):
+        check(lib().pb2h_sim_execute(self.h))
+
+    def sync(self):
+        check(lib().pb2h_sim_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib().pb2h_sim_stream(self.h)
+
+    @property
+    def time(self):
+        return lib().pb2h_sim_time(self.h)
+
+    @property
+    def dt(self):
+        return lib().pb2h_sim_dt(self.h)
+
+    @property
+    def ncycle(self):
+        return lib().pb2h_sim_ncycle(self.h)
+
+    def field_shape(self, container, field, which=FIELD_DATA):
+        i = self.info()
+        _, n = self.field_ptr(container, field, which)
+        if which == FIELD_COARSE:
+            cell = (i["cnk"], i["cnj"], i["cni"])
+        else:
+            cell = (i["nk"], i["nj"], i["ni"])
+        ncomp = n // (i["nblocks"] * cell[0] * cell[1] * cell[2])
+        return (i["nblocks"], ncomp) + cell
+
+    def field_ptr(self, container, field, which=FIELD_DATA):
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib().pb2h_sim_field_ptr(self.h, container.encode(), field.encode(), which,
+                                       C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def get_field(self, container, field, which=FIELD_DATA, out=None):
+        shape = self.field_shape(container, field, which)
+        if out is None:
+            out = np.empty(shape)
+        check(lib().pb2h_sim_get_field(self.h, container.encode(), field.encode(), which,
+                                       out.ctypes.data, out.size))
+        return out
+
+    def set_field(self, container, field, array, which=FIELD_DATA):
+        a = np.ascontiguousarray(array, dtype=np.float64)
+        check(lib().pb2h_sim_set_field(self.h, container.encode(), field.encode(), which,
+                                       a.ctypes.data, a.size))
+
+    def exchange(self, container="base", prolongate=True):
+        check(lib().pb2h_sim_exchange(self.h, container.encode(), int(prolongate)))
+
+    def exchange_phase(self, container, phase):
+        check(lib().pb2h_sim_exchange_phase(self.h, container.encode(), phase))
+
+    def exchange_elements(self, container="base"):
+        lo, nl = C.c_int64(), C.c_int64()
+        t = lib().pb2h_sim_exchange_elements(self.h, container.encode(), C.byref(lo), C.byref(nl))
+        if t < 0:
+            check(-1)
+        return lo.value, nl.value
+
+    def history(self):
+        o = np.zeros(8)
+        check(lib().pb2h_sim_history(self.h, o.ctypes.data_as(C.POINTER(C.c_double))))
+        return o
+
+    def zone_cycles_per_second(self):
+        return lib().pb2h_sim_zone_cycles_per_second(self.h)

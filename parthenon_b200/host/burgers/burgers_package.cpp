@@ -1,0 +1,168 @@
+// burgers_package.cpp — Parthenon-VIBE package: field registration and the tasks that hand
+// a whole MeshData batch to the sm_100a kernels (see burgers_package.hpp).
+#include "burgers_package.hpp"
+
+#include <cfloat>
+#include <string>
+
+namespace burgers_package {
+
+namespace {
+struct KernelConfig {
+  int recon; // PB2_RECON_*
+  int math;  // PB2_MATH_*
+};
+
+pb2_burgers_args MakeArgs(MeshData<Real> *md, Variable &u) {
+  auto pkg = md->GetMeshPointer()->packages.Get("burgers_package");
+  const auto &cfg = pkg->Param<KernelConfig>("kernel_config");
+  pb2_burgers_args a{};
+  a.geom = md->Geometry(u);
+  a.recon = cfg.recon;
+  a.math = cfg.math;
+  a.u = u.data();
+  return a;
+}
+
+// one device scalar per MeshData batch that the update kernel min-reduces into
+Real *DtScratch(MeshData<Real> *md) { return md->GetMeshPointer()->ScratchReal() + 8 + md->partition_id() % 32; }
+
+void ResetDt(MeshData<Real> *md) {
+  static const Real huge = DBL_MAX;
+  PB2_CHECK(pb2_memcpy_h2d(DtScratch(md), &huge, sizeof(Real), md->stream()));
+}
+Real ReadDt(MeshData<Real> *md) {
+  Real v = 0;
+  PB2_CHECK(pb2_memcpy_d2h(&v, DtScratch(md), sizeof(Real), md->stream()));
+  PB2_CHECK(pb2_stream_sync(md->stream()));
+  return v;
+}
+} // namespace
+
+std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
+  auto pkg = std::make_shared<StateDescriptor>("burgers_package");
+
+  const Real cfl = pin->GetOrAddReal("burgers", "cfl", 0.8);
+  pkg->AddParam("cfl", cfl);
+
+  KernelConfig cfg{};
+  const std::string recon = pin->GetOrAddString("burgers", "recon", "weno5");
+  const int nghost = pin->GetInteger("parthenon/mesh", "nghost");
+  if (recon == "weno5") {
+    cfg.recon = PB2_RECON_WENO5;
+    PARTHENON_REQUIRE_THROWS(nghost >= 4, "weno5 reconstruction requires 4 or more ghost "
+                                          "cells.  Set <parthenon/mesh>/nghost = 4");
+  } else if (recon == "linear") {
+    cfg.recon = PB2_RECON_LINEAR;
+    if (nghost > 2)
+      PARTHENON_WARN("Using more ghost cells than required.  Consider setting "
+                     "<parthenon/mesh>/nghost = 2");
+  } else {
+    PARTHENON_THROW(recon + " is an invalid option for <burgers>/recon.  Valid options are "
+                            "weno5 and linear.");
+  }
+  // arithmetic mode of the stencil kernels: "strict" reproduces the reference's CPU build
+  // bit for bit (no FMA contraction); "fast" allows contraction (<= 1e-12 relative)
+  const std::string math = pin->GetOrAddString("pb2", "math", "fast", {"fast", "strict"});
+  cfg.math = math == "strict" ? PB2_MATH_STRICT : PB2_MATH_FAST;
+  pkg->AddParam("kernel_config", cfg);
+  pkg->AddParam("fused_stage", pin->GetOrAddBoolean("pb2", "fused_stage", true));
+
+  const int num_scalars = pin->GetOrAddInteger("burgers", "num_scalars", 1);
+  pkg->AddParam("num_scalars", num_scalars);
+  PARTHENON_REQUIRE_THROWS(num_scalars > 0, "Burgers benchmark requires num_scalars >= 1");
+
+  // always a three dimensional velocity + the passive scalars (burgers_package.cpp:75-80)
+  const std::vector<int> vec_components(1, 3 + num_scalars);
+  Metadata m({Metadata::Cell, Metadata::Independent, Metadata::Intensive, Metadata::Conserved,
+              Metadata::FillGhost, Metadata::WithFluxes},
+             vec_components);
+  pkg->AddField("U", m);
+  // The reference also registers six reconstruction scratch fields Ulx..Urz (:82-89).
+  // They exist here too so packs by name resolve, but storage is lazy and the kernels keep
+  // left/right states in registers, so they never occupy HBM.
+  m = Metadata({Metadata::Cell, Metadata::Derived, Metadata::OneCopy}, vec_components);
+  for (const char *n : {"Ulx", "Urx", "Uly", "Ury", "Ulz", "Urz"}) pkg->AddField(n, m);
+  m = Metadata({Metadata::Cell, Metadata::Derived, Metadata::OneCopy});
+  pkg->AddField("derived", m);
+
+  Real mesh_vol = 1;
+  for (int d = 1; d <= 3; ++d) {
+    const std::string x = "x" + std::to_string(d);
+    mesh_vol *= pin->GetReal("parthenon/mesh", x + "max") - pin->GetReal("parthenon/mesh", x + "min");
+  }
+  pkg->AddParam("mesh_volume", mesh_vol);
+
+  // history: the eight octant masses, labels as in the reference (:110-135)
+  HistoryOutputVec hv;
+  hv.hst_op = UserHistoryOperation::sum;
+  hv.hst_fun = MassHistory;
+  for (int o = 0; o < 8; ++o) hv.labels.push_back("MS Mass " + std::to_string(o));
+  pkg->AddParam(hist_vec_param_key, std::vector<HistoryOutputVec>{hv});
+
+  pkg->EstimateTimestepMesh = EstimateTimestepMesh;
+  pkg->FillDerivedMesh = CalculateDerived;
+  return pkg;
+}
+
+TaskStatus CalculateFluxes(MeshData<Real> *md) {
+  Variable &u = md->Get("U");
+  pb2_burgers_args a = MakeArgs(md, u);
+  for (int d = 0; d < a.geom.ndim; ++d) a.flux[d] = u.flux(d + 1);
+  PB2_CHECK(pb2_burgers_calculate_fluxes(&a, md->stream()));
+  return TaskStatus::complete;
+}
+
+void CalculateDerived(MeshData<Real> *md) {
+  Variable &u = md->Get("U");
+  pb2_pack_geom g = md->Geometry(u);
+  PB2_CHECK(pb2_burgers_derived_dt(&g, u.data(), md->Get("derived").data(), nullptr, md->stream()));
+}
+
+Real EstimateTimestepMesh(MeshData<Real> *md) {
+  auto pkg = md->GetMeshPointer()->packages.Get("burgers_package");
+  Variable &u = md->Get("U");
+  pb2_pack_geom g = md->Geometry(u);
+  ResetDt(md);
+  PB2_CHECK(pb2_burgers_derived_dt(&g, u.data(), nullptr, DtScratch(md), md->stream()));
+  return pkg->Param<Real>("cfl") * ReadDt(md);
+}
+
+std::vector<Real> MassHistory(MeshData<Real> *md) {
+  Mesh *pm = md->GetMeshPointer();
+  Variable &u = md->Get("U");
+  pb2_pack_geom g = md->Geometry(u);
+  std::vector<Real> out(8, 0.0);
+  PB2_CHECK(pb2_burgers_history(&g, u.data(), md->DeviceXmin(), pm->mesh_size.xmin_.data(),
+                                pm->mesh_size.xmax_.data(), out.data(), md->stream()));
+  return out;
+}
+
+TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real> *mc1,
+                      Real beta, Real dt, bool last_stage) {
+  auto pkg = mc0->GetMeshPointer()->packages.Get("burgers_package");
+  Variable &u = mc0->Get("U");
+  pb2_burgers_args a = MakeArgs(mc0, u);
+  a.base = mbase->Get("U").data();
+  a.out = mc1->Get("U").data();
+  for (int d = 0; d < a.geom.ndim; ++d) a.flux[d] = u.flux(d + 1);
+  a.derived = mc1->Get("derived").data();
+  a.beta = beta;
+  a.dt = dt;
+  if (last_stage) {
+    ResetDt(mc1);
+    a.dt_min = DtScratch(mc1);
+  }
+  PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+  return TaskStatus::complete;
+}
+
+// EstimateTimestep task of the fused path: the stage kernel already reduced min dt
+TaskStatus CollectFusedTimestep(MeshData<Real> *mc1) {
+  auto pkg = mc1->GetMeshPointer()->packages.Get("burgers_package");
+  const Real dt_min = pkg->Param<Real>("cfl") * ReadDt(mc1);
+  for (auto &pmb : mc1->GetBlockList()) pmb->SetAllowedDt(std::min(dt_min, pmb->NewDt()));
+  return TaskStatus::complete;
+}
+
+} // namespace burgers_package

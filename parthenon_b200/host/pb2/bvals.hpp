@@ -1,0 +1,135 @@
+// bvals.hpp — ghost-zone exchange "in one" (host side).
+//
+// Same task functions as the reference's src/bvals/comms/bvals_in_one.hpp:41-92:
+//   SendBoundBufs<bt>, StartReceiveBoundBufs<bt>, ReceiveBoundBufs<bt>, SetBounds<bt>,
+//   ProlongateBounds<bt>, AddBoundaryExchangeTasks, and the flux-correction aliases.
+// What changes underneath (B200 design):
+//   * BndInfo / ProResInfo become flat POD region tables (include/parthenon_b200.h) built
+//     once per MeshData and rebuilt only when its allocation generation changes — there is
+//     no per-call host walk over 13 312 regions (bvals_utils.hpp:140-202).
+//   * local channels (sender and receiver on the same GPU) are ONE fused launch that moves
+//     sender box -> receiver ghost box with no intermediate buffer: half the HBM traffic of
+//     pack + unpack.  SendBoundBufs<local> only publishes "sent"; SetBounds<local> copies.
+//   * nonlocal channels are packed straight into one contiguous slab per peer GPU, shipped
+//     by one grouped ncclSend/ncclRecv per peer on a communication stream, and unpacked
+//     after a stream-side event wait (no host polling; the CommBuffer state machine of
+//     utils/communication_buffer.hpp collapses to two events).
+//   * restriction runs before pack / after unpack, prolongation in ProlongateBounds, each
+//     as one launch over all regions (boundary_communication.cpp:82-87, 338-346, 361-393).
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "mesh_data.hpp"
+#include "tasks.hpp"
+
+namespace parthenon {
+
+enum class IndexRangeType { BoundaryInteriorSend, BoundaryExteriorRecv, InteriorSend, InteriorRecv };
+
+// index box of a boundary region, cell centred (bnd_info.cpp:105-252): s/e in (i,j,k) order
+struct IndexBox {
+  int s[3], e[3];
+  int n(int d) const { return e[d] - s[d] + 1; }
+  int64_t size() const { return static_cast<int64_t>(n(0)) * n(1) * n(2); }
+};
+IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeType ir_type,
+                     bool prores);
+
+// one boundary channel as the host sees it (pure topology: testable without a device)
+struct Channel {
+  int sender_gid, receiver_gid;
+  int var;          // index into the MeshData's FillGhost variable list
+  int offset_index; // sender-perspective offset index (0..26): the channel key
+  IndexBox send_box, recv_box;
+  bool send_coarse; // sender reads its coarse buffer (receiver is coarser)
+  bool recv_coarse; // receiver writes its coarse buffer (sender is coarser)
+  int sender_rank, receiver_rank;   // real ranks (GPUs)
+  int sender_vrank, receiver_vrank; // virtual ranks inside one GPU (test knob)
+  int64_t slab_off = -1;            // nonlocal: offset in Reals inside the peer segment
+};
+
+// Everything one exchange of one MeshData needs, derived from topology alone.
+struct ExchangePlan {
+  std::vector<Channel> local;     // received by this MeshData from the same (virtual) rank
+  std::vector<Channel> send;      // nonlocal, sent by this MeshData; sorted by peer, key
+  std::vector<Channel> recv;      // nonlocal, received by this MeshData
+  std::vector<int64_t> send_off;  // [npeers + 1] slab segment offsets in Reals
+  std::vector<int64_t> recv_off;
+  int npeers = 1;                 // real ranks, or virtual ranks in the test mode
+  int64_t local_elements = 0, send_elements = 0, recv_elements = 0;
+};
+// vars_ncomp: components of each FillGhost variable (sizes the slabs)
+ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
+                               const std::vector<int> &vars_ncomp);
+
+struct BvarsCache {
+  ~BvarsCache();
+  void Clear();
+  uint64_t built_generation = 0;
+  ExchangePlan plan;
+  std::vector<Variable *> vars;
+  pb2_bnd_table *copy_local = nullptr;
+  pb2_bnd_table *pack = nullptr, *unpack = nullptr;
+  // [0]: regions whose neighbour is local, [1]: nonlocal
+  pb2_bnd_table *restrict_send[2] = {nullptr, nullptr}, *restrict_set[2] = {nullptr, nullptr};
+  pb2_bnd_table *prolongate[2][3] = {{nullptr, nullptr, nullptr},
+                                     {nullptr, nullptr, nullptr}}; // per prolongation op
+  DeviceBuffer send_slab, recv_slab;
+  pb2_event_t packed = nullptr, received = nullptr, sent = nullptr;
+  bool nonlocal_in_flight = false;
+  // local channels: SendBoundBufs<local> publishes a generation; receivers consume it
+  uint64_t send_generation = 0;
+  std::map<int, uint64_t> consumed_generation; // by sender partition
+  // traffic accounting for bench.py: Reals moved by the last exchange
+  int64_t elements_local = 0, elements_nonlocal = 0;
+};
+
+void BuildBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md);
+
+template <BoundaryType bound_type>
+TaskStatus StartReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md);
+template <BoundaryType bound_type>
+TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md);
+template <BoundaryType bound_type>
+TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md);
+template <BoundaryType bound_type>
+TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md);
+template <BoundaryType bound_type>
+TaskStatus ProlongateBounds(std::shared_ptr<MeshData<Real>> &md);
+
+inline TaskStatus SendBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md) {
+  return SendBoundBufs<BoundaryType::any>(md);
+}
+inline TaskStatus StartReceiveBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md) {
+  return StartReceiveBoundBufs<BoundaryType::any>(md);
+}
+inline TaskStatus ReceiveBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md) {
+  return ReceiveBoundBufs<BoundaryType::any>(md);
+}
+inline TaskStatus SetBoundaries(std::shared_ptr<MeshData<Real>> &md) {
+  return SetBounds<BoundaryType::any>(md);
+}
+// flux corrections only exist at fine-coarse faces; on meshes without them these complete
+// immediately (boundary_communication.cpp:454-461)
+TaskStatus StartReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
+TaskStatus LoadAndSendFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
+TaskStatus ReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
+TaskStatus SetFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
+
+// physical boundaries: all supported meshes are periodic, handled as neighbour exchange
+// (bvals/boundary_conditions.cpp:197 is a no-op for periodic)
+TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &rc);
+TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &md,
+                                                   bool coarse);
+
+// boundary_communication.cpp:406-452: Send -> Receive -> Set -> [Prolongate] in the
+// local / nonlocal split
+TaskID AddBoundaryExchangeTasks(TaskID dependency, TaskList &tl,
+                                std::shared_ptr<MeshData<Real>> &md, bool multilevel);
+
+// one blocking exchange (Mesh::CommunicateBoundaries, mesh.cpp:640-706)
+void CommunicateBoundaries(std::shared_ptr<MeshData<Real>> &md, bool prolongate);
+
+} // namespace parthenon

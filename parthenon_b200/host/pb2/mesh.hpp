@@ -1,0 +1,243 @@
+// mesh.hpp — block-structured mesh topology (host only).
+//
+// What the ghost-zone hot path needs from the reference's src/mesh + src/mesh/forest:
+// Morton-ordered leaf list (logical_location.hpp:125-131, forest.cpp:145), contiguous gid
+// ranges per rank (AssignBlocks, mesh-amr_loadbalance.cpp:362-386), the neighbour list of
+// every block with same-level offsets (tree.cpp:139-226, mesh-gmg.cpp:48-101), index shapes
+// (meshblock.cpp:204-216) and uniform Cartesian geometry (uniform_cartesian.hpp:27-190).
+// One rank <-> one B200; the blocks of a rank are one (or `pack_size`-sized) MeshData batch.
+// Supported: single-tree forests (2^n root blocks in every active direction), periodic
+// boundaries, uniform or statically refined leaves with 2:1 nesting.
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "device.hpp"
+#include "parameter_input.hpp"
+#include "state.hpp"
+#include "types.hpp"
+
+struct pb2_comm;
+
+namespace parthenon {
+
+namespace Globals {
+extern int my_rank, nranks, nghost;
+} // namespace Globals
+
+struct LogicalLocation {
+  int level = 0;
+  int64_t lx[3] = {0, 0, 0};
+  int64_t lx1() const { return lx[0]; }
+  int64_t lx2() const { return lx[1]; }
+  int64_t lx3() const { return lx[2]; }
+  bool operator==(const LogicalLocation &o) const {
+    return level == o.level && lx[0] == o.lx[0] && lx[1] == o.lx[1] && lx[2] == o.lx[2];
+  }
+  LogicalLocation GetParent() const {
+    LogicalLocation p;
+    p.level = level - 1;
+    for (int d = 0; d < 3; ++d) p.lx[d] = lx[d] >> 1;
+    return p;
+  }
+  // z-order key at `maxlevel` resolution, x in the lowest interleaved bit
+  // (utils/morton_number.hpp:43)
+  uint64_t MortonKey(int maxlevel) const;
+  // logical_location.cpp:98-108
+  std::array<int, 3> GetSameLevelOffsets(const LogicalLocation &neighbor) const;
+  // logical_location.cpp:110-129
+  bool IsNeighbor(const LogicalLocation &in) const;
+};
+
+struct LogicalLocationHash {
+  size_t operator()(const LogicalLocation &l) const {
+    uint64_t h = static_cast<uint64_t>(l.level) * 0x9E3779B97F4A7C15ull;
+    for (int d = 0; d < 3; ++d)
+      h ^= (static_cast<uint64_t>(l.lx[d]) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
+
+// bvals/neighbor_block.hpp:48: what a block knows about one neighbour
+struct NeighborBlock {
+  int gid = -1, rank = 0, lid = -1; // lid: index on the owning rank
+  LogicalLocation loc;              // wrapped location (as stored in the tree)
+  LogicalLocation origin_loc;       // location in the frame of this block (may lie outside)
+  int offsets[3] = {0, 0, 0};       // same-level offsets ox1, ox2, ox3
+  // index of the offset in the 27-cube, the channel key element "loc idx"
+  // (cell_center_offsets.hpp:98)
+  int OffsetIndex() const { return (offsets[0] + 1) + 3 * (offsets[1] + 1) + 9 * (offsets[2] + 1); }
+};
+
+// coordinates/uniform_cartesian.hpp:27-190
+class UniformCartesian {
+ public:
+  UniformCartesian() = default;
+  UniformCartesian(const RegionSize &rs, int nghost) {
+    for (int d = 0; d < 3; ++d) {
+      dx_[d] = (rs.xmax_[d] - rs.xmin_[d]) / rs.nx_[d];
+      istart_[d] = rs.symmetry_[d] ? 0 : nghost;
+      xmin_[d] = rs.xmin_[d] - istart_[d] * dx_[d];
+    }
+  }
+  UniformCartesian(const UniformCartesian &src, int coarsen) {
+    istart_ = src.istart_;
+    dx_ = src.dx_;
+    xmin_ = src.xmin_;
+    for (int d = 0; d < 3; ++d) xmin_[d] += istart_[d] * dx_[d] * (1 - coarsen);
+    dx_[0] *= coarsen;
+    dx_[1] *= (istart_[1] > 0 ? coarsen : 1);
+    dx_[2] *= (istart_[2] > 0 ? coarsen : 1);
+  }
+  template <int dir>
+  Real Dxc() const { return dx_[dir - 1]; }
+  Real DxcFA(int dir) const { return dx_[dir - 1]; }
+  template <int dir>
+  Real Xc(int idx) const { return xmin_[dir - 1] + (idx + 0.5) * dx_[dir - 1]; }
+  template <int dir>
+  Real Xf(int idx) const { return xmin_[dir - 1] + idx * dx_[dir - 1]; }
+  Real CellVolume() const { return dx_[0] * dx_[1] * dx_[2]; }
+  Real FaceArea(int dir) const {
+    return dir == 1 ? dx_[1] * dx_[2] : (dir == 2 ? dx_[0] * dx_[2] : dx_[0] * dx_[1]);
+  }
+  const std::array<Real, 3> &Dx() const { return dx_; }
+  const std::array<Real, 3> &GetXmin() const { return xmin_; }
+  const std::array<int, 3> &GetStartIndex() const { return istart_; }
+
+ private:
+  std::array<Real, 3> dx_{1, 1, 1}, xmin_{0, 0, 0};
+  std::array<int, 3> istart_{0, 0, 0};
+};
+using Coordinates_t = UniformCartesian;
+
+class Mesh;
+
+class MeshBlock {
+ public:
+  int gid = 0, lid = 0; // global id (Morton order) and index on this rank
+  LogicalLocation loc;
+  RegionSize block_size;
+  IndexShape cellbounds, c_cellbounds;
+  Coordinates_t coords;
+  std::vector<NeighborBlock> neighbors;
+  Mesh *pmy_mesh = nullptr;
+  int partition = 0; // MeshData batch holding this block
+  int pack_index = 0; // position inside that batch
+
+  Real NewDt() const { return new_block_dt_; }
+  void SetAllowedDt(Real dt) { new_block_dt_ = dt; }
+  int GetNumberOfMeshBlockCells() const {
+    return cellbounds.GetTotal(IndexDomain::interior);
+  }
+
+ private:
+  Real new_block_dt_ = std::numeric_limits<Real>::max();
+};
+using BlockList_t = std::vector<std::shared_ptr<MeshBlock>>;
+
+// interface/data_collection.hpp:46: named MeshData containers ("base", "1", "dUdt", ...) per
+// block partition.  A new container shares OneCopy fields with "base" and gets its own
+// arrays for everything else (meshblock_data.Add semantics, burgers_driver.cpp:64-73).
+class MeshDataCollection {
+ public:
+  explicit MeshDataCollection(Mesh *pm) : pmesh_(pm) {}
+  std::shared_ptr<MeshData<Real>> &GetOrAdd(const std::string &label, int partition_id);
+  std::shared_ptr<MeshData<Real>> &Add(const std::string &label, int partition_id) {
+    return GetOrAdd(label, partition_id);
+  }
+  std::shared_ptr<MeshData<Real>> &Get(const std::string &label = "base", int partition_id = 0) {
+    return GetOrAdd(label, partition_id);
+  }
+  bool Contains(const std::string &label, int partition_id) const {
+    return map_.count(label + "_part-" + std::to_string(partition_id)) > 0;
+  }
+  void PurgeNonBase();
+  std::map<std::string, std::shared_ptr<MeshData<Real>>> &All() { return map_; }
+
+ private:
+  Mesh *pmesh_;
+  std::map<std::string, std::shared_ptr<MeshData<Real>>> map_;
+};
+
+// application hooks (application_input.hpp)
+struct ApplicationInput {
+  std::function<Packages_t(std::unique_ptr<ParameterInput> &)> ProcessPackages = nullptr;
+  // fills the interior of every block of a MeshData batch on the device
+  std::function<void(MeshData<Real> *, ParameterInput *)> MeshProblemGenerator = nullptr;
+  std::function<void(Mesh *, ParameterInput *, SimTime &)> UserWorkBeforeLoop = nullptr;
+  std::function<void(Mesh *, ParameterInput *, SimTime &)> UserWorkAfterLoop = nullptr;
+};
+
+class Mesh {
+ public:
+  // leaves: explicit (level, lx1, lx2, lx3) list, or empty => root grid + the deck's
+  // <parthenon/static_refinementN> regions
+  Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &packages, int rank = 0,
+       int nranks = 1, const std::vector<LogicalLocation> &leaves = {});
+  ~Mesh();
+
+  int ndim = 3;
+  RegionSize mesh_size, base_block_size;
+  BoundaryFlag mesh_bcs[6];
+  int root_level = 0, current_level = 0;
+  int nrbx[3] = {1, 1, 1};
+  bool multilevel = false, adaptive = false;
+  int nbtotal = 0;
+  int my_rank = 0, nranks = 1;
+  int64_t mbcnt = 0; // block-cycles since the timer reset (driver.cpp:124)
+  Packages_t packages;
+  std::vector<FieldEntry> resolved_fields; // all packages, registration order
+
+  std::vector<LogicalLocation> loclist; // every leaf, Morton order: index = gid
+  std::vector<int> ranklist, nslist, nblist;
+  BlockList_t block_list; // this rank's blocks, gid order
+  MeshDataCollection mesh_data{this};
+  void *stream = nullptr;      // compute stream of this rank (pb2_stream_t); NULL = default
+  void *comm_stream = nullptr; // stream the NCCL halo exchange runs on
+  Real *ScratchReal(); // 64 device doubles for tiny reductions
+  // in-place sum over ranks of a host vector (MPI_Reduce of outputs/history.cpp)
+  void ReduceHistory(std::vector<Real> &vals);
+  // true if some block of this rank has a neighbour on another level
+  bool HasFineCoarseFaces() const;
+
+  pb2_comm *comm = nullptr; // NCCL communicator (nranks > 1), owned by the creator
+  // test knob: split this rank's blocks over `virtual_ranks` pretend devices so the
+  // slab (nonlocal) path runs on one GPU (the reference tests its MPI path the same way
+  // with one-rank runs of BuffCommType::both)
+  int virtual_ranks = 1;
+  int VirtualRankOf(int gid) const;
+
+  int GetNumMeshBlocksThisRank() const { return static_cast<int>(block_list.size()); }
+  int DefaultPackSize() const; // mesh.hpp:151-153
+  int DefaultPackSizeFor(int nblocks) const;
+  int DefaultNumPartitions() const;
+  int GetNumberOfMeshBlockCells() const {
+    return base_block_size.nx_[0] * base_block_size.nx_[1] * base_block_size.nx_[2];
+  }
+  int64_t GetTotalCells() const { return static_cast<int64_t>(nbtotal) * GetNumberOfMeshBlockCells(); }
+  int GetGidRank(int gid) const { return ranklist[gid]; }
+  int GetLid(int gid) const { return gid - nslist[ranklist[gid]]; }
+  RegionSize GetBlockSize(const LogicalLocation &loc) const;
+
+  // ProblemGenerator + first ghost exchange + FillDerived (mesh.cpp:745)
+  void Initialize(bool init_problem, ParameterInput *pin, ApplicationInput *app_in);
+
+  // pure topology helpers (also used by the CPU-only tests)
+  static void AssignBlocks(const std::vector<double> &costlist, int nranks,
+                           std::vector<int> &ranklist);
+
+ private:
+  int pack_size_ = -1;
+  DeviceBuffer scratch_;
+  std::unordered_map<LogicalLocation, int, LogicalLocationHash> leaf_gid_;
+  std::unordered_map<LogicalLocation, int, LogicalLocationHash> internal_;
+  void BuildTree(ParameterInput *pin, const std::vector<LogicalLocation> &leaves);
+  void FindNeighbors(MeshBlock &mb) const;
+  bool WrapLocation(const LogicalLocation &in, LogicalLocation &out) const;
+  int64_t BlocksAtLevel(int level, int d) const;
+};
+
+} // namespace parthenon

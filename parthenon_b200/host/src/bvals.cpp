@@ -1,0 +1,567 @@
+// bvals.cpp — ghost-zone exchange: index boxes, channel plan, device tables, task functions.
+// See pb2/bvals.hpp for the design and the reference files each piece replaces.
+#include "pb2/bvals.hpp"
+
+#include <algorithm>
+#include <tuple>
+
+namespace parthenon {
+
+// ---------------------------------------------------------------------------------------
+// CalcIndices for cell-centred, non-flux fields with the identity logical-coordinate
+// transform and full ownership (what a single-tree mesh produces): bnd_info.cpp:105-252
+// ---------------------------------------------------------------------------------------
+IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeType ir_type,
+                     bool prores) {
+  const LogicalLocation &loc = pmb->loc;
+  const int ng = Globals::nghost;
+  // prolongation/restriction work in the coarse index space; so does any exchange with a
+  // coarser neighbour (:121-125)
+  const bool use_coarse = prores || nb.loc.level < loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int coarse_fac = nb.loc.level > loc.level ? 2 : 1; // :130
+  const int interior_offset = ir_type == IndexRangeType::BoundaryInteriorSend ? ng : 0;
+  int exterior_offset = ir_type == IndexRangeType::BoundaryExteriorRecv ? ng : 0;
+  if (prores) exterior_offset /= 2; // only coarse ghosts that have fine ghosts (:161-166)
+  IndexBox box;
+  for (int d = 0; d < 3; ++d) {
+    const bool not_sym = !pmb->block_size.symmetry_[d];
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior);
+    // the neighbour's interior extent in the index space we exchange in (:131-135)
+    const int nb_n = not_sym ? pmb->block_size.nx_[d] / coarse_fac : 1;
+    int &s = box.s[d], &e = box.e[d];
+    if (nb.offsets[d] == 0) {
+      s = b.s;
+      e = b.e;
+      if (loc.level < nb.origin_loc.level && not_sym) {
+        // finer neighbour abuts half of this face; send ng extra interior zones so the
+        // receiver can prolongate (:173-192)
+        const int extra = (b.e - b.s + 1) - nb_n;
+        const bool upper_half = ((nb.origin_loc.lx[d] % 2) + 2) % 2 == 1;
+        s += upper_half ? extra - interior_offset : 0;
+        e -= upper_half ? 0 : extra - interior_offset;
+        if (ir_type == IndexRangeType::InteriorSend && !prores) {
+          s -= ng;
+          e += ng;
+        }
+      }
+      if (loc.level > nb.origin_loc.level && not_sym) {
+        // coarser neighbour: it sent extra zones on the side away from our corner (:193-204)
+        s -= loc.lx[d] % 2 == 1 ? exterior_offset : 0;
+        e += loc.lx[d] % 2 == 0 ? exterior_offset : 0;
+        if (ir_type == IndexRangeType::InteriorRecv && !prores) {
+          s -= ng;
+          e += ng;
+        }
+      }
+      if (prores && not_sym && ir_type == IndexRangeType::InteriorRecv) {
+        s -= ng / 2;
+        e += ng / 2;
+      }
+    } else if (nb.offsets[d] > 0) {
+      s = b.e + (-interior_offset + 1);
+      e = b.e + exterior_offset;
+    } else {
+      s = b.s - exterior_offset;
+      e = b.s + (interior_offset - 1);
+    }
+  }
+  return box;
+}
+
+// ---------------------------------------------------------------------------------------
+// channel plan (pure topology)
+// ---------------------------------------------------------------------------------------
+namespace {
+int OffsetIndexOf(int o1, int o2, int o3) { return (o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1); }
+
+// the entry of `sender`'s neighbour list that describes the channel towards `receiver_gid`
+// seen from the receiver at offsets `roff` (bvals_utils.hpp:43-67: channels are keyed by
+// sender gid, receiver gid and the location index)
+const NeighborBlock *MatchingNeighbor(const MeshBlock *sender, int receiver_gid,
+                                      const int roff[3]) {
+  for (auto &q : sender->neighbors)
+    if (q.gid == receiver_gid && q.offsets[0] == -roff[0] && q.offsets[1] == -roff[1] &&
+        q.offsets[2] == -roff[2])
+      return &q;
+  return nullptr;
+}
+auto ChannelKey(const Channel &c) {
+  return std::make_tuple(c.sender_gid, c.receiver_gid, c.var, c.offset_index);
+}
+} // namespace
+
+ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
+                               const std::vector<int> &vars_ncomp) {
+  ExchangePlan plan;
+  const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
+  PARTHENON_REQUIRE(!(V > 1 && pm->nranks > 1), "pb2/virtual_ranks needs a single real rank");
+  plan.npeers = V > 1 ? V * V : pm->nranks;
+  const int nvar = static_cast<int>(vars_ncomp.size());
+  std::vector<std::pair<int, Channel>> send, recv; // (segment, channel)
+  for (auto &pmb : blocks) {
+    const int my_vr = pm->VirtualRankOf(pmb->gid);
+    for (auto &nb : pmb->neighbors) {
+      const int nb_vr = nb.rank == pm->my_rank ? pm->VirtualRankOf(nb.gid) : 0;
+      const bool local = nb.rank == pm->my_rank && nb_vr == my_vr;
+      for (int v = 0; v < nvar; ++v) {
+        // this block as RECEIVER of the channel nb -> pmb
+        Channel rc;
+        rc.sender_gid = nb.gid;
+        rc.receiver_gid = pmb->gid;
+        rc.var = v;
+        rc.offset_index = OffsetIndexOf(-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]);
+        rc.recv_box = CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, false);
+        rc.recv_coarse = nb.loc.level < pmb->loc.level; // bnd_info.cpp:285-289
+        rc.send_coarse = pmb->loc.level < nb.loc.level;
+        rc.sender_rank = nb.rank;
+        rc.receiver_rank = pm->my_rank;
+        rc.sender_vrank = nb_vr;
+        rc.receiver_vrank = my_vr;
+        rc.send_box = rc.recv_box;
+        if (local) {
+          const MeshBlock *sender = pm->block_list[nb.lid].get();
+          const NeighborBlock *q = MatchingNeighbor(sender, pmb->gid, nb.offsets);
+          PARTHENON_REQUIRE(q != nullptr, "no matching send region for a local channel");
+          rc.send_box = CalcIndices(*q, sender, IndexRangeType::BoundaryInteriorSend, false);
+          for (int d = 0; d < 3; ++d)
+            PARTHENON_REQUIRE(rc.send_box.n(d) == rc.recv_box.n(d),
+                              "send/receive extents of a channel differ");
+          plan.local_elements += rc.recv_box.size() * vars_ncomp[v];
+          plan.local.push_back(rc);
+        } else {
+          const int seg = V > 1 ? nb_vr * V + my_vr : nb.rank;
+          recv.emplace_back(seg, rc);
+        }
+        // this block as SENDER of the channel pmb -> nb
+        if (!local) {
+          Channel sc;
+          sc.sender_gid = pmb->gid;
+          sc.receiver_gid = nb.gid;
+          sc.var = v;
+          sc.offset_index = nb.OffsetIndex();
+          sc.send_box = CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryInteriorSend, false);
+          sc.recv_box = sc.send_box;
+          sc.send_coarse = nb.loc.level < pmb->loc.level;
+          sc.recv_coarse = pmb->loc.level < nb.loc.level;
+          sc.sender_rank = pm->my_rank;
+          sc.receiver_rank = nb.rank;
+          sc.sender_vrank = my_vr;
+          sc.receiver_vrank = nb_vr;
+          const int seg = V > 1 ? my_vr * V + nb_vr : nb.rank;
+          send.emplace_back(seg, sc);
+        }
+      }
+    }
+  }
+  // both sides of a peer segment order its channels by the same key, so slab offsets agree
+  // without any handshake
+  auto layout = [&](std::vector<std::pair<int, Channel>> &chs, std::vector<Channel> &out,
+                    std::vector<int64_t> &seg_off, int64_t &total) {
+    std::stable_sort(chs.begin(), chs.end(), [](const auto &a, const auto &b) {
+      if (a.first != b.first) return a.first < b.first;
+      return ChannelKey(a.second) < ChannelKey(b.second);
+    });
+    seg_off.assign(plan.npeers + 1, 0);
+    std::vector<int64_t> seg_size(plan.npeers, 0);
+    for (auto &sc : chs) {
+      Channel c = sc.second;
+      c.slab_off = seg_size[sc.first];
+      int64_t n = c.send_box.size() * vars_ncomp[c.var];
+      n += n & 1; // keep every channel 16-byte aligned for vector access
+      seg_size[sc.first] += n;
+      out.push_back(c);
+    }
+    for (int p = 0; p < plan.npeers; ++p) seg_off[p + 1] = seg_off[p] + seg_size[p];
+    total = seg_off[plan.npeers];
+    // make slab_off absolute
+    size_t i = 0;
+    for (auto &sc : chs) out[i++].slab_off += seg_off[sc.first];
+  };
+  layout(send, plan.send, plan.send_off, plan.send_elements);
+  layout(recv, plan.recv, plan.recv_off, plan.recv_elements);
+  return plan;
+}
+
+// ---------------------------------------------------------------------------------------
+// device tables
+// ---------------------------------------------------------------------------------------
+BvarsCache::~BvarsCache() { Clear(); }
+
+void BvarsCache::Clear() {
+  for (int c = 0; c < 2; ++c) {
+    pb2_bnd_table_destroy(restrict_send[c]);
+    pb2_bnd_table_destroy(restrict_set[c]);
+    restrict_send[c] = restrict_set[c] = nullptr;
+    for (int o = 0; o < 3; ++o) {
+      pb2_bnd_table_destroy(prolongate[c][o]);
+      prolongate[c][o] = nullptr;
+    }
+  }
+  pb2_bnd_table_destroy(copy_local);
+  pb2_bnd_table_destroy(pack);
+  pb2_bnd_table_destroy(unpack);
+  copy_local = pack = unpack = nullptr;
+  built_generation = 0;
+}
+
+namespace {
+
+MeshData<Real> *ContainerOf(MeshData<Real> *md, const MeshBlock *pmb) {
+  if (pmb->partition == md->partition_id()) return md;
+  return md->GetMeshPointer()->mesh_data.GetOrAdd(md->label(), pmb->partition).get();
+}
+
+pb2_prores_region MakeProRes(Variable &v, const MeshBlock *pmb, const IndexBox &box, int ndim) {
+  pb2_prores_region r{};
+  r.fine = v.data() + pmb->pack_index * v.block_stride;
+  r.coarse = v.coarse() + pmb->pack_index * v.cblock_stride;
+  for (int d = 0; d < 3; ++d) {
+    r.s[d] = box.s[d];
+    r.n[d] = box.n(d);
+    r.fine_is[d] = pmb->cellbounds.Bounds(d, IndexDomain::interior).s;
+    r.coarse_is[d] = pmb->c_cellbounds.Bounds(d, IndexDomain::interior).s;
+  }
+  r.ncomp = v.NumComponents();
+  r.fine_stride_j = v.ni;
+  r.fine_stride_k = v.ni * v.nj;
+  r.fine_stride_c = static_cast<int32_t>(v.comp_stride);
+  r.coarse_stride_j = v.cni;
+  r.coarse_stride_k = v.cni * v.cnj;
+  r.coarse_stride_c = static_cast<int32_t>(v.ccomp_stride);
+  r.ndim = ndim;
+  r.status = PB2_REGION_ALLOCATED;
+  const UniformCartesian cc(pmb->coords, 2); // MeshRefinement::GetCoarseCoords
+  for (int d = 0; d < 3; ++d) {
+    r.fine_xmin[d] = pmb->coords.GetXmin()[d];
+    r.fine_dx[d] = pmb->coords.Dx()[d];
+    r.coarse_xmin[d] = cc.GetXmin()[d];
+    r.coarse_dx[d] = cc.Dx()[d];
+  }
+  return r;
+}
+
+void Rebuild(MeshData<Real> *md) {
+  BvarsCache &c = md->bvars();
+  c.Clear();
+  Mesh *pm = md->GetMeshPointer();
+  c.vars = md->GetVariablesByFlag({Metadata::FillGhost});
+  std::vector<int> ncomp;
+  for (Variable *v : c.vars) ncomp.push_back(v->NumComponents());
+  c.plan = BuildExchangePlan(pm, md->GetBlockList(), ncomp);
+  const bool slabs = c.plan.send_elements > 0 || c.plan.recv_elements > 0;
+  PARTHENON_REQUIRE(!slabs || pm->DefaultNumPartitions() == 1,
+                    "inter-device halos need one MeshData per rank (parthenon/mesh/pack_size=-1)");
+
+  // fused local channels: receiver ghost box <- sender interior box
+  std::vector<pb2_copy_region> copies;
+  copies.reserve(c.plan.local.size());
+  for (const Channel &ch : c.plan.local) {
+    const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
+    const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
+    Variable &rv = *c.vars[ch.var];
+    Variable &sv = ContainerOf(md, sb)->Get(rv.label());
+    pb2_copy_region r{};
+    if (ch.send_coarse) {
+      r.src = sv.coarse() + sb->pack_index * sv.cblock_stride;
+      r.src_stride_j = sv.cni;
+      r.src_stride_k = sv.cni * sv.cnj;
+      r.src_stride_c = static_cast<int32_t>(sv.ccomp_stride);
+    } else {
+      r.src = sv.data() + sb->pack_index * sv.block_stride;
+      r.src_stride_j = sv.ni;
+      r.src_stride_k = sv.ni * sv.nj;
+      r.src_stride_c = static_cast<int32_t>(sv.comp_stride);
+    }
+    if (ch.recv_coarse) {
+      r.dst = rv.coarse() + rb->pack_index * rv.cblock_stride;
+      r.dst_stride_j = rv.cni;
+      r.dst_stride_k = rv.cni * rv.cnj;
+      r.dst_stride_c = static_cast<int32_t>(rv.ccomp_stride);
+    } else {
+      r.dst = rv.data() + rb->pack_index * rv.block_stride;
+      r.dst_stride_j = rv.ni;
+      r.dst_stride_k = rv.ni * rv.nj;
+      r.dst_stride_c = static_cast<int32_t>(rv.comp_stride);
+    }
+    for (int d = 0; d < 3; ++d) {
+      r.ss[d] = ch.send_box.s[d];
+      r.ds[d] = ch.recv_box.s[d];
+      r.n[d] = ch.recv_box.n(d);
+    }
+    r.ncomp = rv.NumComponents();
+    r.flag_slot = -1;
+    r.status = PB2_REGION_ALLOCATED;
+    r.threshold = 0.0;
+    r.default_value = rv.metadata().GetDefaultValue();
+    copies.push_back(r);
+  }
+  PB2_CHECK(pb2_copy_table_create(&c.copy_local, copies.data(), static_cast<int64_t>(copies.size())));
+
+  // slab channels
+  auto bnd = [&](const Channel &ch, bool send) {
+    const int gid = send ? ch.sender_gid : ch.receiver_gid;
+    const MeshBlock *pmb = pm->block_list[pm->GetLid(gid)].get();
+    Variable &v = *c.vars[ch.var];
+    const bool coarse = send ? ch.send_coarse : ch.recv_coarse;
+    const IndexBox &box = send ? ch.send_box : ch.recv_box;
+    pb2_bnd_region r{};
+    if (coarse) {
+      r.var = v.coarse() + pmb->pack_index * v.cblock_stride;
+      r.stride_j = v.cni;
+      r.stride_k = v.cni * v.cnj;
+      r.stride_c = static_cast<int32_t>(v.ccomp_stride);
+    } else {
+      r.var = v.data() + pmb->pack_index * v.block_stride;
+      r.stride_j = v.ni;
+      r.stride_k = v.ni * v.nj;
+      r.stride_c = static_cast<int32_t>(v.comp_stride);
+    }
+    r.buf_off = ch.slab_off;
+    for (int d = 0; d < 3; ++d) {
+      r.s[d] = box.s[d];
+      r.n[d] = box.n(d);
+    }
+    r.ncomp = v.NumComponents();
+    r.flag_slot = -1;
+    r.status = PB2_REGION_ALLOCATED | (send ? 0u : PB2_REGION_BUF_ALLOCATED);
+    r.value = send ? v.metadata().GetAllocationThreshold() : v.metadata().GetDefaultValue();
+    return r;
+  };
+  std::vector<pb2_bnd_region> packs, unpacks;
+  for (const Channel &ch : c.plan.send) packs.push_back(bnd(ch, true));
+  for (const Channel &ch : c.plan.recv) unpacks.push_back(bnd(ch, false));
+  PB2_CHECK(pb2_bnd_table_create(&c.pack, packs.data(), static_cast<int64_t>(packs.size())));
+  PB2_CHECK(pb2_bnd_table_create(&c.unpack, unpacks.data(), static_cast<int64_t>(unpacks.size())));
+  if (c.plan.send_elements > 0)
+    c.send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.send_elements), md->stream());
+  if (c.plan.recv_elements > 0)
+    c.recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.recv_elements), md->stream());
+
+  // restriction / prolongation regions (ProResInfo::GetSend / GetSet, bnd_info.cpp:387-448),
+  // split by whether the neighbour is local so the local / nonlocal task split still works
+  if (pm->multilevel) {
+    std::vector<pb2_prores_region> rsend[2], rset[2], pro[2][3];
+    for (auto &pmb : md->GetBlockList()) {
+      const int my_vr = pm->VirtualRankOf(pmb->gid);
+      bool restricted = false;
+      if (pmb->loc.level > 0)
+        for (auto &nb : pmb->neighbors)
+          restricted = restricted || nb.origin_loc.level == pmb->loc.level - 1;
+      for (auto &nb : pmb->neighbors) {
+        const bool local =
+            nb.rank == pm->my_rank && pm->VirtualRankOf(nb.gid) == my_vr;
+        const int cls = local ? 0 : 1;
+        for (Variable *v : c.vars) {
+          if (nb.origin_loc.level < pmb->loc.level) {
+            rsend[cls].push_back(MakeProRes(
+                *v, pmb.get(),
+                CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryInteriorSend, true), pm->ndim));
+            pro[cls][v->metadata().ProlongationOp()].push_back(MakeProRes(
+                *v, pmb.get(),
+                CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, true), pm->ndim));
+          } else if (restricted) {
+            rset[cls].push_back(MakeProRes(
+                *v, pmb.get(),
+                CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, true), pm->ndim));
+          }
+        }
+      }
+    }
+    for (int cls = 0; cls < 2; ++cls) {
+      PB2_CHECK(pb2_prores_table_create(&c.restrict_send[cls], rsend[cls].data(),
+                                        static_cast<int64_t>(rsend[cls].size())));
+      PB2_CHECK(pb2_prores_table_create(&c.restrict_set[cls], rset[cls].data(),
+                                        static_cast<int64_t>(rset[cls].size())));
+      for (int o = 0; o < 3; ++o)
+        PB2_CHECK(pb2_prores_table_create(&c.prolongate[cls][o], pro[cls][o].data(),
+                                          static_cast<int64_t>(pro[cls][o].size())));
+    }
+  }
+  if (!c.packed) {
+    PB2_CHECK(pb2_event_create(&c.packed));
+    PB2_CHECK(pb2_event_create(&c.received));
+    PB2_CHECK(pb2_event_create(&c.sent));
+  }
+  c.built_generation = md->alloc_generation;
+}
+
+inline BvarsCache &Cache(std::shared_ptr<MeshData<Real>> &md) {
+  if (md->bvars().built_generation != md->alloc_generation) Rebuild(md.get());
+  return md->bvars();
+}
+
+constexpr bool DoesLocal(BoundaryType bt) {
+  return bt == BoundaryType::local || bt == BoundaryType::any;
+}
+constexpr bool DoesNonlocal(BoundaryType bt) {
+  return bt == BoundaryType::nonlocal || bt == BoundaryType::any;
+}
+
+} // namespace
+
+void BuildBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md) { Cache(md); }
+
+template <BoundaryType bt>
+TaskStatus StartReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
+  // receives are posted together with the sends inside one NCCL group; nothing to pre-post
+  Cache(md);
+  return TaskStatus::complete;
+}
+
+template <BoundaryType bt>
+TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
+  BvarsCache &c = Cache(md);
+  Mesh *pm = md->GetMeshPointer();
+  pb2_stream_t st = md->stream();
+  if (DoesLocal(bt)) {
+    // boundary_communication.cpp:82-87: restrict before anything reads the coarse buffers
+    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_send[0], st));
+    c.send_generation++; // the copy itself happens in SetBounds<local> of the receiver
+  }
+  if (DoesNonlocal(bt) && c.plan.send_elements + c.plan.recv_elements > 0) {
+    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_send[1], st));
+    // the previous exchange must have left the slabs (send done, unpack done: same stream)
+    if (c.nonlocal_in_flight) PB2_CHECK(pb2_stream_wait_event(st, c.sent));
+    PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), nullptr, st));
+    if (pm->nranks > 1) {
+      PARTHENON_REQUIRE(pm->comm != nullptr, "multi-rank mesh without a communicator");
+      pb2_stream_t cs = pm->comm_stream;
+      PB2_CHECK(pb2_event_record(c.packed, st));
+      PB2_CHECK(pb2_stream_wait_event(cs, c.packed));
+      PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_slab.get<Real>(), c.plan.send_off.data(),
+                                  c.recv_slab.get<Real>(), c.plan.recv_off.data(), cs));
+      PB2_CHECK(pb2_event_record(c.received, cs));
+      PB2_CHECK(pb2_event_record(c.sent, cs));
+    } else {
+      // virtual ranks on one device: the "wire" is a device-to-device copy of the slab
+      PB2_CHECK(pb2_memcpy_d2d(c.recv_slab.get(), c.send_slab.get(),
+                               sizeof(Real) * static_cast<size_t>(c.plan.send_elements), st));
+      PB2_CHECK(pb2_event_record(c.received, st));
+      PB2_CHECK(pb2_event_record(c.sent, st));
+    }
+    c.nonlocal_in_flight = true;
+  }
+  return TaskStatus::complete;
+}
+
+template <BoundaryType bt>
+TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
+  BvarsCache &c = Cache(md);
+  Mesh *pm = md->GetMeshPointer();
+  if (DoesLocal(bt)) {
+    // every partition that sends to us must have published this exchange
+    // (CommBuffer::TryReceive for same-rank buffers, communication_buffer.hpp:390-400)
+    for (const Channel &ch : c.plan.local) {
+      const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
+      if (sb->partition == md->partition_id()) continue;
+      MeshData<Real> *smd = ContainerOf(md.get(), sb);
+      if (smd->bvars().send_generation <= c.consumed_generation[sb->partition])
+        return TaskStatus::incomplete;
+    }
+    if (c.send_generation <= c.consumed_generation[md->partition_id()])
+      return TaskStatus::incomplete;
+  }
+  // nonlocal: completion is a stream-side event wait in SetBounds — no host polling
+  return TaskStatus::complete;
+}
+
+template <BoundaryType bt>
+TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
+  BvarsCache &c = Cache(md);
+  Mesh *pm = md->GetMeshPointer();
+  pb2_stream_t st = md->stream();
+  if (DoesLocal(bt)) {
+    PB2_CHECK(pb2_copy(c.copy_local, nullptr, st));
+    c.elements_local = c.plan.local_elements;
+    for (int p = 0; p < pm->DefaultNumPartitions(); ++p) {
+      MeshData<Real> *smd =
+          p == md->partition_id() ? md.get() : pm->mesh_data.GetOrAdd(md->label(), p).get();
+      c.consumed_generation[p] = smd->bvars().send_generation;
+    }
+    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_set[0], st)); // :338-346
+  }
+  if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
+    PB2_CHECK(pb2_stream_wait_event(st, c.received));
+    PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(), nullptr, st));
+    c.elements_nonlocal = c.plan.recv_elements;
+    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_set[1], st));
+  }
+  return TaskStatus::complete;
+}
+
+template <BoundaryType bt>
+TaskStatus ProlongateBounds(std::shared_ptr<MeshData<Real>> &md) {
+  BvarsCache &c = Cache(md);
+  Mesh *pm = md->GetMeshPointer();
+  if (!pm->multilevel) return TaskStatus::complete;
+  for (int cls = 0; cls < 2; ++cls) {
+    if (cls == 0 && !DoesLocal(bt)) continue;
+    if (cls == 1 && !DoesNonlocal(bt)) continue;
+    for (int o = 0; o < 3; ++o) PB2_CHECK(pb2_prolongate(c.prolongate[cls][o], o, md->stream()));
+  }
+  return TaskStatus::complete;
+}
+
+#define PB2_INSTANTIATE(bt)                                                               \
+  template TaskStatus StartReceiveBoundBufs<bt>(std::shared_ptr<MeshData<Real>> &);       \
+  template TaskStatus SendBoundBufs<bt>(std::shared_ptr<MeshData<Real>> &);               \
+  template TaskStatus ReceiveBoundBufs<bt>(std::shared_ptr<MeshData<Real>> &);            \
+  template TaskStatus SetBounds<bt>(std::shared_ptr<MeshData<Real>> &);                   \
+  template TaskStatus ProlongateBounds<bt>(std::shared_ptr<MeshData<Real>> &);
+PB2_INSTANTIATE(BoundaryType::any)
+PB2_INSTANTIATE(BoundaryType::local)
+PB2_INSTANTIATE(BoundaryType::nonlocal)
+#undef PB2_INSTANTIATE
+
+TaskStatus StartReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &) {
+  return TaskStatus::complete;
+}
+TaskStatus LoadAndSendFluxCorrections(std::shared_ptr<MeshData<Real>> &md) {
+  PARTHENON_REQUIRE(!md->GetMeshPointer()->HasFineCoarseFaces(),
+                    "flux correction at fine-coarse faces is not implemented yet");
+  return TaskStatus::complete;
+}
+TaskStatus ReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &) {
+  return TaskStatus::complete;
+}
+TaskStatus SetFluxCorrections(std::shared_ptr<MeshData<Real>> &) { return TaskStatus::complete; }
+
+TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &) {
+  return TaskStatus::complete; // periodic: filled by the neighbour exchange
+}
+TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &, bool) {
+  return TaskStatus::complete;
+}
+
+TaskID AddBoundaryExchangeTasks(TaskID dependency, TaskList &tl,
+                                std::shared_ptr<MeshData<Real>> &md, bool multilevel) {
+  const auto any = BoundaryType::any;
+  auto send = tl.AddTask(dependency, SendBoundBufs<any>, md);
+  auto recv = tl.AddTask(dependency | send, ReceiveBoundBufs<any>, md);
+  auto set = tl.AddTask(recv, SetBounds<any>, md);
+  auto pro = set;
+  if (multilevel) {
+    auto cbound = tl.AddTask(set, ApplyBoundaryConditionsOnCoarseOrFineMD, md, true);
+    pro = tl.AddTask(cbound, ProlongateBounds<any>, md);
+  }
+  return tl.AddTask(pro, ApplyBoundaryConditionsOnCoarseOrFineMD, md, false);
+}
+
+void CommunicateBoundaries(std::shared_ptr<MeshData<Real>> &md, bool prolongate) {
+  // all partitions of the container send first, then receive/set (mesh.cpp:640-706)
+  Mesh *pm = md->GetMeshPointer();
+  std::vector<std::shared_ptr<MeshData<Real>>> parts;
+  for (int p = 0; p < pm->DefaultNumPartitions(); ++p)
+    parts.push_back(pm->mesh_data.GetOrAdd(md->label(), p));
+  for (auto &m : parts) SendBoundBufs<BoundaryType::any>(m);
+  for (auto &m : parts) {
+    PARTHENON_REQUIRE(ReceiveBoundBufs<BoundaryType::any>(m) == TaskStatus::complete,
+                      "local boundary buffers were not published");
+    SetBounds<BoundaryType::any>(m);
+  }
+  if (prolongate && pm->multilevel)
+    for (auto &m : parts) ProlongateBounds<BoundaryType::any>(m);
+}
+
+} // namespace parthenon

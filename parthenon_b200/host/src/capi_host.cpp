@@ -1,0 +1,342 @@
+// capi_host.cpp — C entry points of the host library (include/parthenon_b200_host.h).
+// They let bench.py, the parity tests and foreign-language callers drive the C++ framework
+// (ParthenonManager + BurgersDriver) without a C++ toolchain; exceptions never cross the
+// boundary: every function returns 0 or a negative code and records the message.
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../burgers/burgers_driver.hpp"
+#include "../burgers/burgers_package.hpp"
+#include "parthenon_b200_host.h"
+#include "pb2/parthenon.hpp"
+
+using namespace parthenon;
+
+namespace {
+thread_local std::string g_error;
+
+template <class F>
+int Guard(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -1;
+  } catch (...) {
+    g_error = "unknown exception";
+    return -1;
+  }
+}
+
+std::vector<std::string> SplitLines(const char *s) {
+  std::vector<std::string> out;
+  if (!s) return out;
+  std::istringstream in(s);
+  std::string line;
+  while (std::getline(in, line))
+    if (!line.empty()) out.push_back(line);
+  return out;
+}
+
+std::vector<LogicalLocation> Leaves(const int *leaves, int n) {
+  std::vector<LogicalLocation> out;
+  for (int i = 0; i < n; ++i) {
+    LogicalLocation l;
+    l.level = leaves[4 * i];
+    for (int d = 0; d < 3; ++d) l.lx[d] = leaves[4 * i + 1 + d];
+    out.push_back(l);
+  }
+  return out;
+}
+} // namespace
+
+struct pb2h_sim {
+  ParthenonManager pman;
+  std::unique_ptr<MultiStageDriver> driver;
+  bool topology_only = false;
+  // topology-only objects
+  std::unique_ptr<ParameterInput> pin;
+  std::unique_ptr<Mesh> mesh;
+  Mesh *pm() { return topology_only ? mesh.get() : pman.pmesh.get(); }
+};
+
+extern "C" {
+
+const char *pb2h_last_error(void) { return g_error.c_str(); }
+
+int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const char *overrides,
+                    int rank, int nranks, const uint8_t *nccl_id, const int *leaves,
+                    int nleaves) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && app && deck, "null argument");
+    PARTHENON_REQUIRE(std::string(app) == "burgers", "unknown application (have: burgers)");
+    auto s = std::make_unique<pb2h_sim>();
+    s->pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
+    s->pman.app_input->MeshProblemGenerator = burgers_benchmark::MeshProblemGenerator;
+    s->pman.ParthenonInitEnvFromString(deck, SplitLines(overrides));
+    s->pman.SetRank(rank, nranks, nccl_id);
+    s->pman.ParthenonInitPackagesAndMesh(Leaves(leaves, nleaves));
+    auto drv = std::make_unique<burgers_benchmark::BurgersDriver>(
+        s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
+    drv->quiet = true;
+    s->driver = std::move(drv);
+    *sim = s.release();
+  });
+}
+
+int pb2h_topology_create(pb2h_sim **sim, const char *deck, const char *overrides, int rank,
+                         int nranks, const int *leaves, int nleaves) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && deck, "null argument");
+    auto s = std::make_unique<pb2h_sim>();
+    s->topology_only = true;
+    s->pin = std::make_unique<ParameterInput>();
+    s->pin->LoadFromString(deck);
+    for (auto &o : SplitLines(overrides)) s->pin->ModifyFromString(o);
+    Packages_t none;
+    s->mesh = std::make_unique<Mesh>(s->pin.get(), nullptr, none, rank, nranks,
+                                     Leaves(leaves, nleaves));
+    *sim = s.release();
+  });
+}
+
+int pb2h_sim_destroy(pb2h_sim *sim) {
+  return Guard([&] {
+    if (!sim) return;
+    sim->driver.reset();
+    delete sim;
+  });
+}
+
+int pb2h_sim_pre_execute(pb2h_sim *sim) {
+  return Guard([&] { sim->driver->PreExecute(); });
+}
+
+int pb2h_sim_cycle(pb2h_sim *sim, int ncycles) {
+  return Guard([&] {
+    for (int c = 0; c < ncycles; ++c)
+      PARTHENON_REQUIRE(sim->driver->DoCycle() == TaskListStatus::complete,
+                        "Step failed to complete all tasks.");
+  });
+}
+
+int pb2h_sim_sync(pb2h_sim *sim) {
+  return Guard([&] { PB2_CHECK(pb2_stream_sync(sim->pm()->stream)); });
+}
+
+void *pb2h_sim_stream(pb2h_sim *sim) { return sim->pm()->stream; }
+double pb2h_sim_time(pb2h_sim *sim) { return sim->driver->tm.time; }
+double pb2h_sim_dt(pb2h_sim *sim) { return sim->driver->tm.dt; }
+int pb2h_sim_ncycle(pb2h_sim *sim) { return sim->driver->tm.ncycle; }
+int pb2h_sim_set_dt(pb2h_sim *sim, double dt) {
+  sim->driver->tm.dt = dt;
+  return 0;
+}
+
+int pb2h_sim_info(pb2h_sim *sim, int out[12]) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    const IndexShape &cb = pm->block_list[0]->cellbounds, &ccb = pm->block_list[0]->c_cellbounds;
+    out[0] = pm->ndim;
+    out[1] = pm->nbtotal;
+    out[2] = pm->GetNumMeshBlocksThisRank();
+    out[3] = cb.ncellsi(IndexDomain::entire);
+    out[4] = cb.ncellsj(IndexDomain::entire);
+    out[5] = cb.ncellsk(IndexDomain::entire);
+    out[6] = ccb.ncellsi(IndexDomain::entire);
+    out[7] = ccb.ncellsj(IndexDomain::entire);
+    out[8] = ccb.ncellsk(IndexDomain::entire);
+    out[9] = pm->multilevel ? 1 : 0;
+    out[10] = pm->block_list[0]->gid;
+    out[11] = Globals::nghost;
+  });
+}
+
+int pb2h_sim_block(pb2h_sim *sim, int lid, int loc[4], double xmin[3], double xmax[3],
+                   int *gid, int *nneighbors) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    PARTHENON_REQUIRE(lid >= 0 && lid < pm->GetNumMeshBlocksThisRank(), "bad block index");
+    const MeshBlock &mb = *pm->block_list[lid];
+    loc[0] = mb.loc.level;
+    for (int d = 0; d < 3; ++d) {
+      loc[1 + d] = static_cast<int>(mb.loc.lx[d]);
+      xmin[d] = mb.block_size.xmin_[d];
+      xmax[d] = mb.block_size.xmax_[d];
+    }
+    *gid = mb.gid;
+    *nneighbors = static_cast<int>(mb.neighbors.size());
+  });
+}
+
+int pb2h_sim_neighbor(pb2h_sim *sim, int lid, int n, int out[6]) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    const NeighborBlock &nb = pm->block_list.at(lid)->neighbors.at(n);
+    out[0] = nb.gid;
+    out[1] = nb.loc.level;
+    out[2] = nb.offsets[0];
+    out[3] = nb.offsets[1];
+    out[4] = nb.offsets[2];
+    out[5] = nb.rank;
+  });
+}
+
+int pb2h_sim_calc_indices(pb2h_sim *sim, int lid, int n, int ir_type, int prores, int s[3],
+                          int e[3]) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    const MeshBlock &mb = *pm->block_list.at(lid);
+    const IndexBox box = CalcIndices(mb.neighbors.at(n), &mb,
+                                     ir_type == 0 ? IndexRangeType::BoundaryInteriorSend
+                                                  : IndexRangeType::BoundaryExteriorRecv,
+                                     prores != 0);
+    for (int d = 0; d < 3; ++d) {
+      s[d] = box.s[d];
+      e[d] = box.e[d];
+    }
+  });
+}
+
+int pb2h_sim_ranklist(pb2h_sim *sim, int *ranks, int n) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    PARTHENON_REQUIRE(n == pm->nbtotal, "ranklist length mismatch");
+    for (int g = 0; g < n; ++g) ranks[g] = pm->ranklist[g];
+  });
+}
+
+// kind: 0 local, 1 send, 2 recv.  rows: [sender_gid, receiver_gid, var, offset_index,
+// slab_off, nelem, peer] as int64
+int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t max_rows,
+                      int64_t *seg_off) {
+  int64_t count = -1;
+  Guard([&] {
+    Mesh *pm = sim->pm();
+    const ExchangePlan plan = BuildExchangePlan(pm, pm->block_list, {ncomp});
+    const std::vector<Channel> &chs = kind == 0 ? plan.local : (kind == 1 ? plan.send : plan.recv);
+    count = static_cast<int64_t>(chs.size());
+    if (rows) {
+      for (int64_t i = 0; i < std::min<int64_t>(count, max_rows); ++i) {
+        const Channel &c = chs[i];
+        int64_t *r = rows + 7 * i;
+        r[0] = c.sender_gid;
+        r[1] = c.receiver_gid;
+        r[2] = c.var;
+        r[3] = c.offset_index;
+        r[4] = c.slab_off;
+        r[5] = (kind == 2 ? c.recv_box.size() : c.send_box.size()) * ncomp;
+        r[6] = kind == 1 ? c.receiver_rank : c.sender_rank;
+      }
+    }
+    if (seg_off && kind != 0) {
+      const auto &off = kind == 1 ? plan.send_off : plan.recv_off;
+      for (size_t p = 0; p < off.size(); ++p) seg_off[p] = off[p];
+    }
+  });
+  return count;
+}
+
+static Variable &FindVar(pb2h_sim *sim, const char *container, const char *field) {
+  PARTHENON_REQUIRE(sim->pm()->DefaultNumPartitions() == 1,
+                    "field access through the C interface needs pack_size = -1");
+  return sim->pm()->mesh_data.GetOrAdd(container, 0)->Get(field);
+}
+
+int pb2h_sim_field_ptr(pb2h_sim *sim, const char *container, const char *field, int which,
+                       void **ptr, int64_t *nreal) {
+  return Guard([&] {
+    Variable &v = FindVar(sim, container, field);
+    const int nb = sim->pm()->GetNumMeshBlocksThisRank();
+    if (which == 0) {
+      *ptr = v.data();
+      *nreal = v.block_stride * nb;
+    } else if (which == 4) {
+      *ptr = v.coarse();
+      *nreal = v.cblock_stride * nb;
+    } else {
+      *ptr = v.flux(which);
+      *nreal = v.block_stride * nb;
+    }
+  });
+}
+
+int pb2h_sim_get_field(pb2h_sim *sim, const char *container, const char *field, int which,
+                       double *host, int64_t nreal) {
+  return Guard([&] {
+    void *p = nullptr;
+    int64_t n = 0;
+    PARTHENON_REQUIRE(pb2h_sim_field_ptr(sim, container, field, which, &p, &n) == 0, g_error);
+    PARTHENON_REQUIRE(n == nreal, "field size mismatch");
+    PB2_CHECK(pb2_memcpy_d2h(host, p, sizeof(double) * n, sim->pm()->stream));
+    PB2_CHECK(pb2_stream_sync(sim->pm()->stream));
+  });
+}
+
+int pb2h_sim_set_field(pb2h_sim *sim, const char *container, const char *field, int which,
+                       const double *host, int64_t nreal) {
+  return Guard([&] {
+    void *p = nullptr;
+    int64_t n = 0;
+    PARTHENON_REQUIRE(pb2h_sim_field_ptr(sim, container, field, which, &p, &n) == 0, g_error);
+    PARTHENON_REQUIRE(n == nreal, "field size mismatch");
+    PB2_CHECK(pb2_memcpy_h2d(p, host, sizeof(double) * n, sim->pm()->stream));
+    PB2_CHECK(pb2_stream_sync(sim->pm()->stream));
+  });
+}
+
+int pb2h_sim_exchange(pb2h_sim *sim, const char *container, int prolongate) {
+  return Guard([&] {
+    auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+    CommunicateBoundaries(md, prolongate != 0);
+  });
+}
+
+// the three phases separately (for timing / overlap tests): 0 send, 1 receive+set, 2 prolongate
+int pb2h_sim_exchange_phase(pb2h_sim *sim, const char *container, int phase) {
+  return Guard([&] {
+    auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+    if (phase == 0) SendBoundBufs<BoundaryType::any>(md);
+    if (phase == 1) {
+      ReceiveBoundBufs<BoundaryType::any>(md);
+      SetBounds<BoundaryType::any>(md);
+    }
+    if (phase == 2) ProlongateBounds<BoundaryType::any>(md);
+  });
+}
+
+int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t *local,
+                                   int64_t *nonlocal) {
+  int64_t total = -1;
+  Guard([&] {
+    auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+    BuildBoundaryBuffers(md);
+    const ExchangePlan &p = md->bvars().plan;
+    if (local) *local = p.local_elements;
+    if (nonlocal) *nonlocal = p.recv_elements;
+    total = p.local_elements + p.recv_elements;
+  });
+  return total;
+}
+
+int pb2h_sim_history(pb2h_sim *sim, double out[8]) {
+  return Guard([&] {
+    auto v = burgers_package::MassHistory(sim->pm()->mesh_data.GetOrAdd("base", 0).get());
+    sim->pm()->ReduceHistory(v);
+    for (int o = 0; o < 8; ++o) out[o] = v[o];
+  });
+}
+
+double pb2h_sim_zone_cycles_per_second(pb2h_sim *sim) { return sim->driver->ZoneCyclesPerSecond(); }
+
+int pb2h_sim_execute(pb2h_sim *sim) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim->driver->Execute() != DriverStatus::failed, "driver failed");
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,430 @@
+// mesh.cpp — mesh topology: tree of leaves, Morton order, rank assignment, neighbour lists.
+// See pb2/mesh.hpp for the reference files this follows.
+#include "pb2/mesh.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "pb2/mesh_data.hpp"
+
+namespace parthenon {
+
+namespace Globals {
+int my_rank = 0, nranks = 1, nghost = 2;
+}
+
+uint64_t LogicalLocation::MortonKey(int maxlevel) const {
+  uint64_t key = 0;
+  const int sh = maxlevel - level;
+  for (int bit = 0; bit < maxlevel; ++bit)
+    for (int d = 0; d < 3; ++d) {
+      const uint64_t c = static_cast<uint64_t>(lx[d]) << sh;
+      key |= ((c >> bit) & 1ull) << (3 * bit + d);
+    }
+  return key;
+}
+
+std::array<int, 3> LogicalLocation::GetSameLevelOffsets(const LogicalLocation &nb) const {
+  std::array<int, 3> off;
+  const int sn = std::max(nb.level - level, 0), sm = std::max(level - nb.level, 0);
+  for (int d = 0; d < 3; ++d) off[d] = static_cast<int>((nb.lx[d] >> sn) - (lx[d] >> sm));
+  return off;
+}
+
+bool LogicalLocation::IsNeighbor(const LogicalLocation &in) const {
+  const int max_level = std::max(in.level, level);
+  const int64_t bs_in = int64_t{1} << (max_level - in.level);
+  const int64_t bs_this = int64_t{1} << (max_level - level);
+  for (int d = 0; d < 3; ++d) {
+    const int64_t low = lx[d] * bs_this - 1, hi = low + bs_this + 1;
+    const int64_t low_in = in.lx[d] * bs_in, hi_in = low_in + bs_in - 1;
+    if (hi < low_in || low > hi_in) return false;
+  }
+  return true;
+}
+
+namespace {
+// logical_location.cpp:61-74: position in [-0.5, 0.5] built from integers so that the
+// mesh is bitwise symmetric about its centre
+Real SymmetrizedCoordinate(int64_t index, int bloc, int64_t nrange) {
+  const int64_t noffset = index - nrange / 2;
+  const int64_t noffset_ceil = index - (nrange + 1) / 2;
+  return static_cast<Real>(noffset + noffset_ceil + static_cast<int64_t>(bloc)) /
+         (2.0 * static_cast<Real>(nrange));
+}
+// defs.hpp:98-101
+Real LogicalToActual(Real u, Real xmin, Real xmax) {
+  return static_cast<Real>(0.5) * (xmin + xmax) + (u * xmax - u * xmin);
+}
+BoundaryFlag ParseBoundary(const std::string &s) {
+  if (s == "periodic") return BoundaryFlag::periodic;
+  if (s == "outflow") return BoundaryFlag::outflow;
+  if (s == "reflecting" || s == "reflect") return BoundaryFlag::reflect;
+  if (s == "user") return BoundaryFlag::user;
+  PARTHENON_FAIL("unknown boundary condition '" + s + "'");
+}
+} // namespace
+
+void Mesh::AssignBlocks(const std::vector<double> &costlist, int nranks,
+                        std::vector<int> &ranklist) {
+  // equal-cost contiguous gid ranges filled from the last rank backwards, so rank 0 gets
+  // the lighter share (mesh-amr_loadbalance.cpp:362-386)
+  ranklist.assign(costlist.size(), 0);
+  const double total = std::accumulate(costlist.begin(), costlist.end(), 0.0);
+  int rank = nranks - 1;
+  double target = total / nranks, mine = 0.0, remaining = total;
+  for (int b = static_cast<int>(costlist.size()) - 1; b >= 0; --b) {
+    PARTHENON_REQUIRE(target != 0.0, "There is at least one process which has no MeshBlock");
+    mine += costlist[b];
+    ranklist[b] = rank;
+    if (mine >= target && rank > 0) {
+      --rank;
+      remaining -= mine;
+      mine = 0.0;
+      target = remaining / (rank + 1);
+    }
+  }
+}
+
+int64_t Mesh::BlocksAtLevel(int level, int d) const {
+  if (d >= ndim) return 1;
+  return static_cast<int64_t>(nrbx[d]) << (level - root_level);
+}
+
+bool Mesh::WrapLocation(const LogicalLocation &in, LogicalLocation &out) const {
+  out = in;
+  for (int d = 0; d < 3; ++d) {
+    const int64_t n = BlocksAtLevel(in.level, d);
+    if (in.lx[d] < 0 || in.lx[d] >= n) {
+      if (d >= ndim) return false;
+      if (mesh_bcs[2 * d] != BoundaryFlag::periodic) return false;
+      out.lx[d] = ((in.lx[d] % n) + n) % n;
+    }
+  }
+  return true;
+}
+
+RegionSize Mesh::GetBlockSize(const LogicalLocation &loc) const {
+  RegionSize rs = base_block_size;
+  for (int d = 0; d < 3; ++d) {
+    if (d < ndim) {
+      // blocks spanning the mesh at this level.  Single tree (cubic 2^n root grid): 2^level,
+      // exactly the reference's tree.cpp:297-312; other root grids use the same formula on
+      // the mesh as a whole
+      const int64_t ntot = BlocksAtLevel(std::max(loc.level, root_level), d);
+      rs.xmin_[d] = LogicalToActual(SymmetrizedCoordinate(loc.lx[d], 0, ntot), mesh_size.xmin_[d],
+                                    mesh_size.xmax_[d]);
+      rs.xmax_[d] = LogicalToActual(SymmetrizedCoordinate(loc.lx[d], 2, ntot), mesh_size.xmin_[d],
+                                    mesh_size.xmax_[d]);
+    } else {
+      rs.xmin_[d] = mesh_size.xmin_[d];
+      rs.xmax_[d] = mesh_size.xmax_[d];
+    }
+  }
+  return rs;
+}
+
+void Mesh::BuildTree(ParameterInput *pin, const std::vector<LogicalLocation> &leaves_in) {
+  std::vector<LogicalLocation> leaves = leaves_in;
+  if (leaves.empty()) {
+    for (int64_t k = 0; k < nrbx[2]; ++k)
+      for (int64_t j = 0; j < nrbx[1]; ++j)
+        for (int64_t i = 0; i < nrbx[0]; ++i) {
+          LogicalLocation l;
+          l.level = root_level;
+          l.lx[0] = i;
+          l.lx[1] = j;
+          l.lx[2] = k;
+          leaves.push_back(l);
+        }
+    // <parthenon/static_refinementN>: refine every leaf that overlaps the region down to
+    // the requested level (mesh.cpp:1084-1170), then restore 2:1 nesting
+    std::unordered_map<LogicalLocation, int, LogicalLocationHash> set;
+    for (auto &l : leaves) set[l] = 1;
+    auto refine = [&](const LogicalLocation &l) {
+      set.erase(l);
+      for (int dk = 0; dk < (ndim > 2 ? 2 : 1); ++dk)
+        for (int dj = 0; dj < (ndim > 1 ? 2 : 1); ++dj)
+          for (int di = 0; di < 2; ++di) {
+            LogicalLocation c;
+            c.level = l.level + 1;
+            c.lx[0] = 2 * l.lx[0] + di;
+            c.lx[1] = ndim > 1 ? 2 * l.lx[1] + dj : 0;
+            c.lx[2] = ndim > 2 ? 2 * l.lx[2] + dk : 0;
+            set[c] = 1;
+          }
+    };
+    bool any_static = false;
+    for (auto &bname : pin->BlockNames()) {
+      if (bname.compare(0, 27, "parthenon/static_refinement") != 0) continue;
+      any_static = true;
+      Real rmin[3], rmax[3];
+      for (int d = 0; d < 3; ++d) {
+        const std::string x = "x" + std::to_string(d + 1);
+        rmin[d] = d < ndim ? pin->GetReal(bname, x + "min") : mesh_size.xmin_[d];
+        rmax[d] = d < ndim ? pin->GetReal(bname, x + "max") : mesh_size.xmax_[d];
+      }
+      const int ref_lev = pin->GetInteger(bname, "level");
+      PARTHENON_REQUIRE(ref_lev >= 1, "Refinement level must be larger than 0 (root level = 0)");
+      for (int lev = root_level; lev < root_level + ref_lev; ++lev) {
+        std::vector<LogicalLocation> todo;
+        for (auto &kv : set) {
+          if (kv.first.level != lev) continue;
+          const RegionSize rs = GetBlockSize(kv.first);
+          bool overlap = true;
+          for (int d = 0; d < ndim; ++d)
+            overlap = overlap && rs.xmax_[d] > rmin[d] && rs.xmin_[d] < rmax[d];
+          if (overlap) todo.push_back(kv.first);
+        }
+        for (auto &l : todo) refine(l);
+      }
+    }
+    if (any_static) {
+      // 2:1 balance: a leaf must not touch a leaf more than one level finer
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        std::vector<LogicalLocation> cur;
+        for (auto &kv : set) cur.push_back(kv.first);
+        for (auto &l : cur) {
+          if (!set.count(l) || l.level <= root_level + 0) continue;
+          // every neighbour position of l's parent must exist at level >= l.level - 1
+          const LogicalLocation par = l.GetParent();
+          for (int o3 = (ndim > 2 ? -1 : 0); o3 <= (ndim > 2 ? 1 : 0); ++o3)
+            for (int o2 = (ndim > 1 ? -1 : 0); o2 <= (ndim > 1 ? 1 : 0); ++o2)
+              for (int o1 = -1; o1 <= 1; ++o1) {
+                LogicalLocation n = par, w;
+                n.lx[0] += o1;
+                n.lx[1] += o2;
+                n.lx[2] += o3;
+                if (!WrapLocation(n, w)) continue;
+                // walk up: if an ancestor of w (coarser than w) is a leaf, refine it
+                LogicalLocation a = w;
+                while (a.level > root_level) {
+                  a = a.GetParent();
+                  if (set.count(a)) {
+                    refine(a);
+                    changed = true;
+                    break;
+                  }
+                }
+              }
+        }
+      }
+      leaves.clear();
+      for (auto &kv : set) leaves.push_back(kv.first);
+    }
+  }
+  int maxlevel = 0;
+  for (auto &l : leaves) maxlevel = std::max(maxlevel, l.level);
+  std::vector<std::pair<uint64_t, LogicalLocation>> ent;
+  ent.reserve(leaves.size());
+  for (auto &l : leaves) ent.emplace_back(l.MortonKey(maxlevel), l);
+  std::sort(ent.begin(), ent.end(), [](const auto &a, const auto &b) {
+    if (a.first != b.first) return a.first < b.first;
+    return a.second.level < b.second.level;
+  });
+  loclist.clear();
+  leaf_gid_.clear();
+  internal_.clear();
+  current_level = maxlevel;
+  multilevel = false;
+  for (size_t g = 0; g < ent.size(); ++g) {
+    loclist.push_back(ent[g].second);
+    leaf_gid_[ent[g].second] = static_cast<int>(g);
+    if (ent[g].second.level != root_level) multilevel = true;
+    LogicalLocation a = ent[g].second;
+    while (a.level > 0) {
+      a = a.GetParent();
+      internal_[a] = 1;
+    }
+  }
+  nbtotal = static_cast<int>(loclist.size());
+}
+
+// neighbour search on the leaf grid, tree.cpp:139-226; offsets iterate ox1 slowest like the
+// reference's 3-D indexer (indexer.hpp:117-144)
+void Mesh::FindNeighbors(MeshBlock &mb) const {
+  mb.neighbors.clear();
+  const LogicalLocation &loc = mb.loc;
+  auto add = [&](int gid, const LogicalLocation &wrapped, const LogicalLocation &origin) {
+    NeighborBlock nb;
+    nb.gid = gid;
+    nb.rank = ranklist[gid];
+    nb.lid = gid - nslist[nb.rank];
+    nb.loc = wrapped;
+    nb.origin_loc = origin;
+    const auto off = loc.GetSameLevelOffsets(origin); // mesh-gmg.cpp:64
+    for (int d = 0; d < 3; ++d) nb.offsets[d] = off[d];
+    mb.neighbors.push_back(nb);
+  };
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = d < ndim ? -1 : 0;
+    hi[d] = d < ndim ? 1 : 0;
+  }
+  for (int o1 = lo[0]; o1 <= hi[0]; ++o1)
+    for (int o2 = lo[1]; o2 <= hi[1]; ++o2)
+      for (int o3 = lo[2]; o3 <= hi[2]; ++o3) {
+        if (o1 == 0 && o2 == 0 && o3 == 0) continue;
+        LogicalLocation neigh = loc, w;
+        neigh.lx[0] += o1;
+        neigh.lx[1] += o2;
+        neigh.lx[2] += o3;
+        if (!WrapLocation(neigh, w)) continue;
+        auto leaf = leaf_gid_.find(w);
+        if (leaf != leaf_gid_.end()) {
+          add(leaf->second, w, neigh);
+        } else if (internal_.count(w)) {
+          // finer neighbours: the daughters of the position that touch this block
+          for (int d3 = 0; d3 < (ndim > 2 ? 2 : 1); ++d3)
+            for (int d2 = 0; d2 < (ndim > 1 ? 2 : 1); ++d2)
+              for (int d1 = 0; d1 < 2; ++d1) {
+                LogicalLocation dn, dw;
+                dn.level = neigh.level + 1;
+                dn.lx[0] = (neigh.lx[0] << 1) + d1;
+                dn.lx[1] = ndim > 1 ? (neigh.lx[1] << 1) + d2 : 0;
+                dn.lx[2] = ndim > 2 ? (neigh.lx[2] << 1) + d3 : 0;
+                if (!loc.IsNeighbor(dn)) continue;
+                WrapLocation(dn, dw);
+                auto dl = leaf_gid_.find(dw);
+                PARTHENON_REQUIRE(dl != leaf_gid_.end(), "mesh violates 2:1 nesting");
+                add(dl->second, dw, dn);
+              }
+        } else {
+          // coarser neighbour: the parent of the position, if it sits at this offset
+          LogicalLocation par = neigh.GetParent(), pw;
+          if (ndim < 2) par.lx[1] = 0;
+          if (ndim < 3) par.lx[2] = 0;
+          if (!WrapLocation(par, pw)) continue;
+          auto pl = leaf_gid_.find(pw);
+          if (pl == leaf_gid_.end()) continue;
+          const auto so = loc.GetSameLevelOffsets(par);
+          if (so[0] == o1 && so[1] == o2 && so[2] == o3) add(pl->second, pw, par);
+        }
+      }
+}
+
+Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, int nranks_in,
+           const std::vector<LogicalLocation> &leaves)
+    : my_rank(rank), nranks(nranks_in), packages(pkgs) {
+  Globals::my_rank = rank;
+  Globals::nranks = nranks_in;
+  Globals::nghost = pin->GetOrAddInteger("parthenon/mesh", "nghost", 2);
+  const int ng = Globals::nghost;
+  const char *bc_names[6] = {"ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc"};
+  for (int d = 0; d < 3; ++d) {
+    const std::string n = std::to_string(d + 1);
+    mesh_size.nx_[d] = pin->GetOrAddInteger("parthenon/mesh", "nx" + n, 1);
+    mesh_size.xmin_[d] = pin->GetOrAddReal("parthenon/mesh", "x" + n + "min", -0.5);
+    mesh_size.xmax_[d] = pin->GetOrAddReal("parthenon/mesh", "x" + n + "max", 0.5);
+  }
+  ndim = mesh_size.nx_[2] > 1 ? 3 : (mesh_size.nx_[1] > 1 ? 2 : 1);
+  for (int d = 0; d < 3; ++d) {
+    mesh_size.symmetry_[d] = d >= ndim;
+    const std::string n = std::to_string(d + 1);
+    base_block_size.nx_[d] =
+        d < ndim ? pin->GetOrAddInteger("parthenon/meshblock", "nx" + n, mesh_size.nx_[d]) : 1;
+    base_block_size.symmetry_[d] = d >= ndim;
+    PARTHENON_REQUIRE(mesh_size.nx_[d] % base_block_size.nx_[d] == 0,
+                      "the Mesh must be evenly divisible by the MeshBlock");
+    nrbx[d] = mesh_size.nx_[d] / base_block_size.nx_[d];
+    mesh_bcs[2 * d] = ParseBoundary(pin->GetOrAddString("parthenon/mesh", bc_names[2 * d], "periodic"));
+    mesh_bcs[2 * d + 1] =
+        ParseBoundary(pin->GetOrAddString("parthenon/mesh", bc_names[2 * d + 1], "periodic"));
+    if (d < ndim)
+      PARTHENON_REQUIRE(mesh_bcs[2 * d] == BoundaryFlag::periodic &&
+                            mesh_bcs[2 * d + 1] == BoundaryFlag::periodic,
+                        "only periodic mesh boundaries are supported by this build");
+  }
+  // Leaves are ordered by their Morton key in the smallest 2^n cube that holds the root
+  // grid.  For a cubic 2^n root grid this is the reference's single-tree order
+  // (forest.cpp:73-145); elongated root grids (512x256x256 ...) come out as consecutive
+  // cubic sub-trees, which is what keeps each rank's gid range a compact brick.
+  int maxrb = 1;
+  for (int d = 0; d < ndim; ++d) maxrb = std::max(maxrb, nrbx[d]);
+  root_level = 0;
+  while ((1 << root_level) < maxrb) ++root_level;
+  const std::string refinement = pin->GetOrAddString("parthenon/mesh", "refinement", "none");
+  adaptive = refinement == "adaptive";
+  pack_size_ = pin->GetOrAddInteger("parthenon/mesh", "pack_size", -1);
+  virtual_ranks = pin->GetOrAddInteger("pb2", "virtual_ranks", 1);
+
+  BuildTree(pin, leaves);
+  if (refinement != "none") multilevel = true; // coarse buffers exist (mesh.cpp:118-140)
+
+  std::vector<double> cost(nbtotal, 1.0);
+  AssignBlocks(cost, nranks, ranklist);
+  nblist.assign(nranks, 0);
+  for (int r : ranklist) nblist[r]++;
+  nslist.assign(nranks, 0);
+  for (int r = 1; r < nranks; ++r) nslist[r] = nslist[r - 1] + nblist[r - 1];
+
+  for (int gid = nslist[rank]; gid < nslist[rank] + nblist[rank]; ++gid) {
+    auto mb = std::make_shared<MeshBlock>();
+    mb->gid = gid;
+    mb->lid = gid - nslist[rank];
+    mb->loc = loclist[gid];
+    mb->block_size = GetBlockSize(mb->loc);
+    const int nx1 = base_block_size.nx_[0], nx2 = ndim > 1 ? base_block_size.nx_[1] : 0,
+              nx3 = ndim > 2 ? base_block_size.nx_[2] : 0;
+    mb->cellbounds = IndexShape(nx3, nx2, nx1, ng);
+    // meshblock.cpp:204-216
+    mb->c_cellbounds = IndexShape(ndim > 2 ? std::max(1, nx3 / 2) : 0,
+                                  ndim > 1 ? std::max(1, nx2 / 2) : 0, std::max(1, nx1 / 2), ng);
+    mb->coords = UniformCartesian(mb->block_size, ng);
+    mb->pmy_mesh = this;
+    const int ps = DefaultPackSizeFor(static_cast<int>(nblist[rank]));
+    mb->partition = mb->lid / ps;
+    mb->pack_index = mb->lid % ps;
+    FindNeighbors(*mb);
+    block_list.push_back(mb);
+  }
+  for (auto &name : packages.Order())
+    for (auto &f : packages.Get(name)->AllFields()) resolved_fields.push_back(f);
+}
+
+Mesh::~Mesh() = default;
+
+int Mesh::DefaultPackSizeFor(int nblocks) const {
+  return pack_size_ < 1 ? std::max(nblocks, 1) : pack_size_;
+}
+int Mesh::DefaultPackSize() const { return DefaultPackSizeFor(GetNumMeshBlocksThisRank()); }
+int Mesh::DefaultNumPartitions() const {
+  const int ps = DefaultPackSize();
+  return (GetNumMeshBlocksThisRank() + ps - 1) / ps;
+}
+
+Real *Mesh::ScratchReal() {
+  if (!scratch_) scratch_.Allocate(64 * sizeof(Real), stream);
+  return scratch_.get<Real>();
+}
+
+void Mesh::ReduceHistory(std::vector<Real> &vals) {
+  if (nranks == 1 || vals.empty()) return;
+  PARTHENON_REQUIRE(vals.size() <= 64, "too many history columns");
+  PARTHENON_REQUIRE(comm != nullptr, "multi-rank mesh without a communicator");
+  Real *d = ScratchReal();
+  PB2_CHECK(pb2_memcpy_h2d(d, vals.data(), sizeof(Real) * vals.size(), stream));
+  PB2_CHECK(pb2_comm_allreduce_sum(comm, d, static_cast<int64_t>(vals.size()), stream));
+  PB2_CHECK(pb2_memcpy_d2h(vals.data(), d, sizeof(Real) * vals.size(), stream));
+  PB2_CHECK(pb2_stream_sync(stream));
+}
+
+bool Mesh::HasFineCoarseFaces() const {
+  for (auto &pmb : block_list)
+    for (auto &nb : pmb->neighbors)
+      if (nb.loc.level != pmb->loc.level) return true;
+  return false;
+}
+
+int Mesh::VirtualRankOf(int gid) const {
+  if (virtual_ranks <= 1) return 0;
+  // contiguous Morton ranges inside this rank, like the real partition
+  const int r = ranklist[gid];
+  const int64_t l = gid - nslist[r];
+  return static_cast<int>(l * virtual_ranks / std::max(nblist[r], 1));
+}
+
+} // namespace parthenon

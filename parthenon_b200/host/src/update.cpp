@@ -1,0 +1,65 @@
+// update.cpp — dense per-stage update tasks (see pb2/update.hpp).
+#include "pb2/update.hpp"
+
+#include <algorithm>
+
+namespace parthenon {
+namespace Update {
+
+template <>
+TaskStatus FluxDivergence(MeshData<Real> *in, MeshData<Real> *dudt_cont) {
+  for (Variable *v : in->GetVariablesByFlag({Metadata::Independent, Metadata::WithFluxes})) {
+    Variable &d = dudt_cont->Get(v->label());
+    pb2_pack_geom g = in->Geometry(*v);
+    const double *flux[3] = {v->flux(1), g.ndim > 1 ? v->flux(2) : nullptr,
+                             g.ndim > 2 ? v->flux(3) : nullptr};
+    PB2_CHECK(pb2_flux_divergence(&g, flux, d.data(), in->stream()));
+  }
+  return TaskStatus::complete;
+}
+
+template <>
+TaskStatus WeightedSumData(const std::vector<MetadataFlag> &flags, MeshData<Real> *in1,
+                           MeshData<Real> *in2, const Real w1, const Real w2,
+                           MeshData<Real> *out) {
+  for (Variable *x : in1->GetVariablesByFlag(flags)) {
+    Variable &y = in2->Get(x->label());
+    Variable &z = out->Get(x->label());
+    const int64_t n = x->block_stride * in1->NumBlocks();
+    PB2_CHECK(pb2_weighted_sum(x->data(), y.data(), w1, w2, z.data(), n, in1->stream()));
+  }
+  return TaskStatus::complete;
+}
+
+template <>
+TaskStatus EstimateTimestep(MeshData<Real> *rc) {
+  Real dt_min = std::numeric_limits<Real>::max();
+  for (const auto &pkg : rc->GetMeshPointer()->packages.AllPackages())
+    if (pkg.second->EstimateTimestepMesh != nullptr)
+      dt_min = std::min(dt_min, pkg.second->EstimateTimestepMesh(rc));
+  // update.hpp:277-283: every block of the batch votes with the batch minimum
+  for (auto &pmb : rc->GetBlockList()) pmb->SetAllowedDt(std::min(dt_min, pmb->NewDt()));
+  return TaskStatus::complete;
+}
+
+template <>
+TaskStatus PreCommFillDerived(MeshData<Real> *rc) {
+  for (const auto &pkg : rc->GetMeshPointer()->packages.AllPackages())
+    if (pkg.second->PreCommFillDerivedMesh != nullptr) pkg.second->PreCommFillDerivedMesh(rc);
+  return TaskStatus::complete;
+}
+
+template <>
+TaskStatus FillDerived(MeshData<Real> *rc) {
+  auto &pkgs = rc->GetMeshPointer()->packages.AllPackages();
+  for (const auto &pkg : pkgs)
+    if (pkg.second->PreFillDerivedMesh != nullptr) pkg.second->PreFillDerivedMesh(rc);
+  for (const auto &pkg : pkgs)
+    if (pkg.second->FillDerivedMesh != nullptr) pkg.second->FillDerivedMesh(rc);
+  for (const auto &pkg : pkgs)
+    if (pkg.second->PostFillDerivedMesh != nullptr) pkg.second->PostFillDerivedMesh(rc);
+  return TaskStatus::complete;
+}
+
+} // namespace Update
+} // namespace parthenon

@@ -1,0 +1,147 @@
+"""GPU parity tests of the whole path through the C++ host framework (ParthenonManager +
+BurgersDriver task lists -> C ABI -> sm_100a kernels) against
+  * the committed outputs of the reference itself (tests/golden/*.npz, *.hst), and
+  * the CPU oracle on the same inputs.
+pb2/math=strict must be BIT-EXACT; pb2/math=fast (FMA contraction) must stay within the
+1e-12 relative tolerance BASELINE.json's north_star states for evolved FP64 fields."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from parthenon_b200 import host
+from tests import helpers as H
+from tests.test_host_topology import deck_overrides
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-12  # north_star: "evolved fields must match within 1e-12 relative in FP64"
+
+
+def burgers_overrides(nx, nrb, ng, nscal, recon, math, fused, extra=None):
+    ov = deck_overrides(3, (nx,) * 3, ng, (nrb,) * 3)
+    ov.update({"burgers/num_scalars": nscal, "burgers/recon": recon, "pb2/math": math,
+               "pb2/fused_stage": "true" if fused else "false"})
+    if extra:
+        ov.update(extra)
+    return ov
+
+
+def read_hst(path):
+    rows = [l.split() for l in open(path) if not l.startswith("#")]
+    return np.array(rows, dtype=np.float64)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name,ng,recon", [("burgers_u16_b8_s1_weno5", 4, "weno5"),
+                                           ("burgers_u16_b8_s1_linear", 2, "linear")])
+def test_strict_cycles_bit_exact_vs_reference_dumps(name, ng, recon, fused):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sim = host.Simulation(overrides=burgers_overrides(8, 2, ng, 1, recon, "strict", fused))
+    for b in range(8):  # block order = Morton order of the reference's gids
+        assert sim.block(b)["loc"] == tuple(int(x) for x in g["meta"][b, 1:])
+    sim.pre_execute()
+    assert sim.dt == g["dts"][0]
+    assert np.array_equal(sim.get_field("base", "U"), g["U_0"])  # IC + first exchange
+    for c in (1, 2, 3):
+        sim.cycle()
+        assert np.array_equal(sim.get_field("base", "U"), g[f"U_{c}"]), f"cycle {c}"
+        assert sim.time == g["times"][c]
+        if c < 3:  # the dump of cycle c+1 records the dt that cycle was advanced with
+            assert sim.dt == g["dts"][c + 1]
+
+
+@pytest.mark.parametrize("recon,ng", [("weno5", 4), ("linear", 2)])
+def test_fast_cycles_within_tolerance_of_reference_dumps(recon, ng):
+    g = np.load(os.path.join(GOLD, f"burgers_u16_b8_s1_{recon}.npz"))
+    sim = host.Simulation(overrides=burgers_overrides(8, 2, ng, 1, recon, "fast", True))
+    sim.pre_execute()
+    for c in (1, 2, 3):
+        sim.cycle()
+        ref = g[f"U_{c}"]
+        err = np.abs(sim.get_field("base", "U") - ref).max() / np.abs(ref).max()
+        assert err <= TOL, (c, err)
+        assert abs(sim.time - g["times"][c]) <= TOL * g["times"][c]
+
+
+@pytest.mark.parametrize("math,rtol", [("strict", 2e-14), ("fast", 1e-12)])
+def test_history_vs_reference_hst(math, rtol):
+    """benchmark shape (32^3 blocks, 8 scalars, weno5) for 10 cycles against the reference's
+    own .hst (%.14e text, so strict is compared at text precision)"""
+    h = read_hst(os.path.join(GOLD, "burgers_u64_b32_s8_weno5.hst"))
+    sim = host.Simulation(overrides=burgers_overrides(32, 2, 4, 8, "weno5", math, True))
+    sim.pre_execute()
+    for c in range(11):
+        row = h[c]
+        assert abs(sim.time - row[0]) <= rtol * max(1.0, abs(row[0]))
+        assert abs(sim.dt - row[1]) <= max(rtol, 2e-14) * row[1]
+        np.testing.assert_allclose(sim.history(), row[4:12], rtol=rtol)
+        if c < 10:
+            sim.cycle()
+
+
+def test_sim_matches_oracle_multiblock_strict():
+    """4x4x4 blocks of 8^3, 3 scalars: several cycles, bit-exact against the oracle; also the
+    slab (nonlocal) path forced by virtual ranks must give identical bits"""
+    m = oracle.Mesh(3, (8, 8, 8), 4, (4, 4, 4))
+    B = oracle.Burgers(m, num_scalars=3)
+    B.init()
+    sims = [host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True)),
+            host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
+                                                        {"pb2/virtual_ranks": 3}))]
+    lo, nl = sims[1].exchange_elements("base")
+    assert nl > 0 and lo > 0 and lo + nl == sum(sims[0].exchange_elements("base"))
+    for s in sims:
+        s.pre_execute()
+        assert s.dt == B.dt
+    for c in range(4):
+        B.step()
+        for s in sims:
+            s.cycle()
+            assert np.array_equal(s.get_field("base", "U"), B.U), c
+            assert s.dt == B.dt and s.time == B.time
+    np.testing.assert_allclose(sims[0].history(), B.history(), rtol=1e-13)
+    d = sims[0].get_field("base", "derived")[:, 0]
+    g = 4
+    assert np.array_equal(d[:, g:-g, g:-g, g:-g], B.derived[:, g:-g, g:-g, g:-g])
+
+
+def test_multilevel_exchange_matches_oracle():
+    """static two-level mesh: Send (restrict + copy/pack) -> Set (+ restrict) -> Prolongate
+    through the host framework's own tables, bit-exact against the oracle; both the fused
+    local path and the slab path"""
+    nrb, nx, ng = 2, (8, 8, 8), 4
+    leaves = H.refined_leaves(nrb, {(0, 0, 0)})
+    m = oracle.Mesh(3, nx, ng, (nrb,) * 3, leaves=leaves)
+    ncomp = 4  # burgers with one scalar
+    rng = np.random.default_rng(5)
+    U = rng.standard_normal((m.nblocks, ncomp) + m.dims)
+    Uref, Ucref = U.copy(), np.zeros((m.nblocks, ncomp) + m.cdims)
+    m.exchange(Uref, Ucref, prolongate=True)
+    for extra in (None, {"pb2/virtual_ranks": 2}):
+        ov = burgers_overrides(8, nrb, ng, 1, "weno5", "strict", True, extra)
+        ov["parthenon/mesh/refinement"] = "static"
+        sim = host.Simulation(overrides=ov, leaves=leaves)
+        sim.set_field("base", "U", U)
+        sim.set_field("base", "U", np.zeros_like(Ucref), which=host.FIELD_COARSE)
+        sim.exchange("base", prolongate=True)
+        assert np.array_equal(sim.get_field("base", "U", which=host.FIELD_COARSE), Ucref)
+        assert np.array_equal(sim.get_field("base", "U"), Uref)
+
+
+def test_full_block_shape_conservation_and_idempotence():
+    """size-independent properties at the benchmark's block shape (128^3 mesh, 32^3 blocks,
+    11 components): the flux-form update conserves every component's total to rounding, and a
+    second ghost exchange changes nothing"""
+    sim = host.Simulation(overrides=burgers_overrides(32, 4, 4, 8, "weno5", "fast", True))
+    sim.pre_execute()
+    g = 4
+    U0 = sim.get_field("base", "U")
+    tot0 = U0[:, :, g:-g, g:-g, g:-g].sum(axis=(0, 2, 3, 4))
+    sim.cycle(3)
+    U1 = sim.get_field("base", "U")
+    tot1 = U1[:, :, g:-g, g:-g, g:-g].sum(axis=(0, 2, 3, 4))
+    np.testing.assert_allclose(tot1, tot0, rtol=1e-11)
+    sim.exchange("base", prolongate=False)
+    assert np.array_equal(sim.get_field("base", "U"), U1)

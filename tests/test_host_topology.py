@@ -1,0 +1,178 @@
+"""CPU tests of the C++ host framework's topology (no device touched): block order,
+coordinates, neighbour lists and boundary index boxes must equal the oracle's (which is pinned
+to the reference), rank assignment must follow the reference's AssignBlocks, and the per-peer
+slab layouts computed independently by two ranks must agree."""
+import numpy as np
+import pytest
+
+import oracle
+from parthenon_b200 import host
+from tests import helpers as H
+
+
+def deck_overrides(ndim, nx, ng, nrb, refinement="none"):
+    ov = {"parthenon/mesh/nghost": ng, "parthenon/mesh/refinement": refinement}
+    for d in range(3):
+        n = d + 1
+        if d < ndim:
+            ov[f"parthenon/mesh/nx{n}"] = nx[d] * nrb[d]
+            ov[f"parthenon/meshblock/nx{n}"] = nx[d]
+        else:
+            ov[f"parthenon/mesh/nx{n}"] = 1
+            ov[f"parthenon/meshblock/nx{n}"] = 1
+    return ov
+
+
+def compare_topology(t, m):
+    info = t.info()
+    assert info["nbtotal"] == m.nblocks
+    assert (info["nk"], info["nj"], info["ni"]) == m.dims
+    if m.multilevel:
+        assert (info["cnk"], info["cnj"], info["cni"]) == m.cdims
+    for b in range(m.nblocks):
+        blk = t.block(b)
+        assert blk["loc"] == m.block_loc(b)
+        lo, hi = m.block_bounds(b)
+        assert np.array_equal(blk["xmin"], lo) and np.array_equal(blk["xmax"], hi)
+        nbs = t.neighbors(b)
+        ref = m.neighbors(b)
+        assert [x[:5] for x in nbs] == ref
+        for n in range(len(ref)):
+            for ir in (0, 1):
+                for pr in (False, True):
+                    assert t.calc_indices(b, n, ir, pr) == m.calc_indices(b, n, ir, pr), (b, n, ir, pr)
+
+
+@pytest.mark.parametrize("ndim,nx,ng,nrb", [
+    (3, (8, 8, 8), 4, (2, 2, 2)),
+    (3, (16, 8, 4), 2, (4, 4, 4)),
+    (2, (16, 16), 2, (8, 8)),
+    (3, (32, 32, 32), 4, (4, 4, 4)),
+])
+def test_uniform_topology_matches_oracle(ndim, nx, ng, nrb):
+    m = oracle.Mesh(ndim, nx, ng, nrb)
+    t = host.Topology(overrides=deck_overrides(ndim, nx, ng, nrb))
+    compare_topology(t, m)
+
+
+@pytest.mark.parametrize("nrb,refine", [(2, {(0, 0, 0)}), (4, {(1, 1, 1), (2, 1, 1)}),
+                                        (2, {(0, 0, 0), (1, 1, 1)})])
+def test_refined_topology_matches_oracle(nrb, refine):
+    nx, ng = (8, 8, 8), 2
+    leaves = H.refined_leaves(nrb, refine)
+    m = oracle.Mesh(3, nx, ng, (nrb,) * 3, leaves=leaves)
+    t = host.Topology(overrides=deck_overrides(3, nx, ng, (nrb,) * 3, "static"), leaves=leaves)
+    assert t.info()["multilevel"] == 1
+    compare_topology(t, m)
+
+
+def test_rank_assignment_follows_reference():
+    # mesh-amr_loadbalance.cpp:362-386: contiguous ranges, filled from the last rank down,
+    # so with 27 blocks on 4 ranks rank 0 holds the short share
+    ov = deck_overrides(3, (8, 8, 8), 2, (4, 4, 4))
+    t = host.Topology(overrides=ov, rank=0, nranks=8)
+    r = t.ranklist()
+    assert np.array_equal(r, np.repeat(np.arange(8), 8))
+    # 512^3 / 32^3 on 8 GPUs: one octant (512 consecutive Morton ids) per GPU
+    ov = deck_overrides(3, (4, 4, 4), 2, (16, 16, 16))
+    t = host.Topology(overrides=ov, rank=3, nranks=8)
+    r = t.ranklist()
+    assert np.array_equal(np.bincount(r), np.full(8, 512))
+    first = t.info()["first_gid"]
+    assert first == 3 * 512
+    locs = np.array([t.block(b)["loc"] for b in range(512)])
+    # rank 3 owns the octant x high, y high, z low (Morton: x lowest bit)
+    assert locs[:, 1].min() >= 8 and locs[:, 2].min() >= 8 and locs[:, 3].max() < 8
+    # uneven split: remainder goes to the high ranks
+    leaves = H.refined_leaves(2, {(0, 0, 0)})
+    t = host.Topology(overrides=deck_overrides(3, (8, 8, 8), 2, (2, 2, 2), "static"), leaves=leaves,
+                      nranks=4)
+    counts = np.bincount(t.ranklist(), minlength=4)
+    assert counts.sum() == 15 and list(counts) == [3, 4, 4, 4]
+
+
+def plans_consistent(ov, nranks, ncomp, leaves=None):
+    """every (sender rank -> receiver rank) slab segment must have identical channel order,
+    offsets and sizes on both sides, and cover all inter-rank channels exactly once"""
+    tops = [host.Topology(overrides=ov, rank=r, nranks=nranks, leaves=leaves)
+            for r in range(nranks)]
+    sends, recvs = {}, {}
+    for r, t in enumerate(tops):
+        rows, seg = t.plan(ncomp, "send")
+        for row in rows:
+            sends.setdefault((r, int(row[6])), []).append((tuple(row[:4]), row[4] - seg[row[6]], row[5]))
+        rows, seg = t.plan(ncomp, "recv")
+        for row in rows:
+            recvs.setdefault((int(row[6]), r), []).append((tuple(row[:4]), row[4] - seg[row[6]], row[5]))
+    assert sends.keys() == recvs.keys()
+    total = 0
+    for key in sends:
+        assert sends[key] == recvs[key], key
+        total += sum(x[2] for x in sends[key])
+    return total, tops
+
+
+def test_slab_layouts_agree_between_ranks():
+    ov = deck_overrides(3, (8, 8, 8), 4, (4, 4, 4))
+    total, tops = plans_consistent(ov, 4, 3)
+    # uniform mesh: every ghost cell is filled exactly once, locally or through a slab
+    local = sum(int(t.plan(3, "local")[0][:, 5].sum()) for t in tops)
+    ghosts = 64 * 3 * (16 ** 3 - 8 ** 3)
+    assert total + local == ghosts
+    # multilevel
+    leaves = H.refined_leaves(2, {(0, 0, 0)})
+    plans_consistent(deck_overrides(3, (8, 8, 8), 2, (2, 2, 2), "static"), 3, 2, leaves)
+
+
+def test_virtual_ranks_split_local_and_slab_channels():
+    ov = deck_overrides(3, (8, 8, 8), 4, (2, 2, 2))
+    t1 = host.Topology(overrides=ov)
+    ov2 = dict(ov)
+    ov2["pb2/virtual_ranks"] = 2
+    t2 = host.Topology(overrides=ov2)
+    l1 = t1.plan(1, "local")[0]
+    l2, s2, r2 = (t2.plan(1, k)[0] for k in ("local", "send", "recv"))
+    assert len(l1) == 8 * 26 and len(t1.plan(1, "send")[0]) == 0
+    assert len(l2) + len(r2) == len(l1) and len(s2) == len(r2) > 0
+    # send and receive slabs of the virtual ranks share one layout
+    assert np.array_equal(s2[:, :6], r2[:, :6])
+
+
+def test_static_refinement_from_deck():
+    deck = host.BURGERS_DECK + """
+<parthenon/static_refinement0>
+x1min = -0.5
+x1max = -0.25
+x2min = -0.5
+x2max = -0.25
+x3min = -0.5
+x3max = -0.25
+level = 1
+"""
+    ov = deck_overrides(3, (8, 8, 8), 2, (4, 4, 4), "static")
+    t = host.Topology(deck=deck, overrides=ov)
+    info = t.info()
+    assert info["multilevel"] == 1 and info["nbtotal"] == 64 - 1 + 8
+    levels = [t.block(b)["loc"][0] for b in range(info["nbtotal"])]
+    assert levels.count(3) == 8 and levels.count(2) == 63
+
+
+def test_elongated_mesh_partitions_into_cubes():
+    """512x256x256-style root grids (bench.py's weak-scaling meshes): Morton order in the
+    enclosing cube gives each of 2 / 4 ranks one compact cubic brick of blocks"""
+    for nrb, nranks in (((4, 2, 2), 2), ((4, 4, 2), 4)):
+        ov = deck_overrides(3, (4, 4, 4), 2, nrb)
+        for rank in range(nranks):
+            t = host.Topology(overrides=ov, rank=rank, nranks=nranks)
+            info = t.info()
+            assert info["nbtotal"] == nrb[0] * nrb[1] * nrb[2] and info["nblocks"] == 8
+            locs = np.array([t.block(b)["loc"][1:] for b in range(8)])
+            assert (locs.max(axis=0) - locs.min(axis=0) == 1).all()  # a 2x2x2 brick
+            for b in range(8):
+                assert len(t.neighbors(b)) == 26
+        plans_consistent(ov, nranks, 2)
+    # coordinates of an elongated mesh still tile the domain exactly
+    t = host.Topology(overrides=deck_overrides(3, (4, 4, 4), 2, (4, 2, 2)))
+    xs = sorted({(t.block(b)["xmin"][0], t.block(b)["xmax"][0]) for b in range(16)})
+    assert xs[0][0] == -0.5 and xs[-1][1] == 0.5
+    assert all(xs[i][1] == xs[i + 1][0] for i in range(3))
