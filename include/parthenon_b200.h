@@ -70,6 +70,9 @@ int pb2_profile_enable(int on);
 int pb2_profile_reset(void);
 int pb2_profile_kernels(void);
 int pb2_profile_get(int id, const char **name, double *total_ms, int64_t *launches);
+/* FP64 FMA throughput of the current device in TFLOP/s (2 flops per FMA), measured with a
+ * register-resident microbenchmark: the FP64-pipe roofline of the burgers stencil */
+int pb2_measure_fp64_peak(double *tflops);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 int64_t pb2_launch_count(void);
 
@@ -222,7 +225,10 @@ typedef struct pb2_burgers_args {
 int pb2_burgers_calculate_fluxes(const pb2_burgers_args *args, pb2_stream_t stream);
 /* out = (beta*u + (1-beta)*base) + beta*dt*(-div flux); derived; dt_min — interior cells */
 int pb2_burgers_update(const pb2_burgers_args *args, pb2_stream_t stream);
-/* both of the above, one call per stage */
+/* One call per stage.  PB2_MATH_STRICT: the two calls above (needs args->flux).
+ * PB2_MATH_FAST: three direction sweeps that keep every flux in registers and accumulate its
+ * divergence straight into `out` (args->flux is ignored and may be NULL; out must not alias
+ * u or base). */
 int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream);
 /* stand-alone CalculateDerived (burgers_package.cpp:143-167) and/or EstimateTimestepMesh
  * (:170-200) over interior cells: derived [nblocks][nk][nj][ni] or NULL; dt_min device scalar

@@ -71,6 +71,7 @@ SYMBOLS = [
     "pb2_event_destroy", "pb2_event_record", "pb2_event_sync", "pb2_event_query",
     "pb2_stream_wait_event", "pb2_event_elapsed_ms", "pb2_launch_count",
     "pb2_profile_enable", "pb2_profile_reset", "pb2_profile_kernels", "pb2_profile_get",
+    "pb2_measure_fp64_peak",
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
     "pb2_restrict", "pb2_prolongate", "pb2_weighted_sum", "pb2_flux_divergence",
@@ -146,6 +147,12 @@ def profile(enable=None, reset=False):
         if n.value:
             out[name.value.decode()] = (ms.value, n.value)
     return out
+
+
+def fp64_peak_tflops():
+    v = C.c_double()
+    check(lib().pb2_measure_fp64_peak(C.byref(v)))
+    return v.value
 
 
 def launch_count():

@@ -8,8 +8,9 @@ int burgers_fluxes_strict(const pb2_burgers_args *, cudaStream_t);
 int burgers_update_strict(const pb2_burgers_args *, cudaStream_t);
 int burgers_fluxes_fast(const pb2_burgers_args *, cudaStream_t);
 int burgers_update_fast(const pb2_burgers_args *, cudaStream_t);
+int burgers_stage_sweep(const pb2_burgers_args *, cudaStream_t);
 
-static int check_args(const pb2_burgers_args *a, bool need_update) {
+static int check_args(const pb2_burgers_args *a, bool need_update, bool need_flux = true) {
   PB2_REQUIRE(a, "null args");
   const pb2_pack_geom &g = a->geom;
   PB2_REQUIRE(g.ndim >= 1 && g.ndim <= 3, "ndim must be 1..3");
@@ -19,8 +20,9 @@ static int check_args(const pb2_burgers_args *a, bool need_update) {
   PB2_REQUIRE(a->math == PB2_MATH_STRICT || a->math == PB2_MATH_FAST, "unknown math mode");
   PB2_REQUIRE(g.ng >= (a->recon == PB2_RECON_WENO5 ? 3 : 2),
               "not enough ghost cells for the reconstruction stencil");
-  PB2_REQUIRE(a->u && a->flux[0], "null field pointer");
-  for (int d = 1; d < g.ndim; ++d) PB2_REQUIRE(a->flux[d], "null flux pointer");
+  PB2_REQUIRE(a->u, "null field pointer");
+  if (need_flux)
+    for (int d = 0; d < g.ndim; ++d) PB2_REQUIRE(a->flux[d], "null flux pointer");
   if (need_update) PB2_REQUIRE(a->base && a->out && g.dx, "null update pointer");
   return PB2_OK;
 }
@@ -176,6 +178,16 @@ int pb2_burgers_update(const pb2_burgers_args *args, pb2_stream_t stream) {
 }
 
 int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream) {
+  // FAST: three flux-free direction sweeps (burgers_sweep.cu); STRICT: the reference's
+  // dataflow with stored fluxes, bit-exact
+  if (args && args->math == PB2_MATH_FAST) {
+    if (int rc = check_args(args, true, false)) return rc;
+    if (int rc = require_device()) return rc;
+    if (args->geom.nblocks == 0) return PB2_OK;
+    PB2_REQUIRE(args->out != args->u && args->out != args->base,
+                "the fused stage cannot update in place");
+    return burgers_stage_sweep(args, as_stream(stream));
+  }
   if (int rc = pb2_burgers_calculate_fluxes(args, stream)) return rc;
   return pb2_burgers_update(args, stream);
 }

@@ -1,0 +1,463 @@
+// burgers_sweep.cu — the FAST burgers stage: three direction sweeps that never store a flux.
+//
+// Replaces, for PB2_MATH_FAST, the whole dense part of a stage of the reference's task list
+// (benchmarks/burgers/burgers_driver.cpp:92-127): CalculateFluxes (burgers_package.cpp:202-404)
+// + FluxDivergence (update.cpp:63-86) + AverageIndependentData + UpdateIndependentData
+// (update.hpp:71-137) + CalculateDerived (:143-167) + EstimateTimestepMesh (:170-200).
+//
+// The reference writes 6 x 11 reconstructed fields, reads them back, writes 3 x 11 fluxes,
+// reads them back and then runs three more full-array passes.  Here each direction is ONE
+// kernel in which the flux of a face lives only in registers:
+//   x sweep:  out  = beta*u + (1-beta)*base - (beta*dt/dx1) * (F1(i+1) - F1(i))
+//   y sweep:  out -= (beta*dt/dx2) * (F2(j+1) - F2(j))
+//   z sweep:  out -= (beta*dt/dx3) * (F3(k+1) - F3(k));  derived;  min dt
+// (algebraically update.hpp:43-58 with A_d / V = 1 / dx_d on a uniform Cartesian block).
+// The kernels are bound by the FP64 pipe (33 WENO5-Z reconstructions per zone and stage),
+// so the arithmetic is reorganised to issue fewer FP64 instructions than the reference's
+// expression tree: the 8 divisions of WENO5-Z collapse into 4 Newton-refined reciprocals
+// (shared denominators), the HLL denominators of a face are inverted once for all 11
+// components, and stencil values are software-prefetched one component ahead.  Results stay
+// within 1e-12 relative of the reference (tests/test_burgers_sim_gpu.py); the bit-exact
+// arithmetic lives in burgers_strict.cu.  Valid for |q| < ~1e40 (products of three
+// smoothness indicators must not overflow).
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace pb2 {
+namespace sweep {
+
+constexpr int kThreads = 128;
+constexpr int kMaxComp = 16;
+
+struct Geom {
+  int nblocks, ncomp, ndim;
+  int nx[3], is[3], n[3];
+  int64_t sj, sk, sc, sb;
+};
+
+struct Args {
+  Geom g;
+  const double *u, *base;
+  double *out;
+  double *derived;           // LAST sweep only, or null
+  unsigned long long *dtmin; // LAST sweep only, or null
+  const double *dx;          // [nblocks][3]
+  double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
+};
+
+__device__ __forceinline__ double min_std(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double max_std(double a, double b) { return (a < b) ? b : a; }
+
+// 1/a to ~1 ulp: hardware seed (2^-23) + two Newton steps, no special-case branches
+__device__ __forceinline__ double rcp_nr(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+// recon.hpp:27-32
+__device__ __forceinline__ double mc(const double dm, const double dp) {
+  const double dc = (dm * dp > 0.0) ? 0.5 * (dm + dp) : 0.0;
+  return copysign(min_std(fabs(dc), 2.0 * min_std(fabs(dm), fabs(dp))), dc);
+}
+
+__device__ __forceinline__ void Linear(const double qm, const double q0, const double qp,
+                                       double &ql, double &qr) {
+  const double dq = 0.5 * mc(q0 - qm, qp - q0);
+  ql = q0 + dq;
+  qr = q0 - dq;
+}
+
+// WENO5-Z of recon.hpp:42-99 with shared reciprocals
+__device__ __forceinline__ void WENO5Z(const double q0, const double q1, const double q2,
+                                       const double q3, const double q4, double &ql,
+                                       double &qr) {
+  constexpr double a00 = 1.0 / 3.0, a01 = -7.0 / 6.0, a02 = 11.0 / 6.0;
+  constexpr double a10 = -1.0 / 6.0, a11 = 5.0 / 6.0, a12 = 1.0 / 3.0;
+  constexpr double a20 = 1.0 / 3.0, a21 = 5.0 / 6.0, a22 = -1.0 / 6.0;
+  constexpr double g0 = 0.1, g1 = 0.6, g2 = 0.3;
+  constexpr double eps = 10.0 * DBL_EPSILON;
+  constexpr double c13 = 13.0 / 3.0;
+
+  double a = q0 - 2.0 * q1 + q2;
+  double b = q0 - 4.0 * q1 + 3.0 * q2;
+  const double b0 = fma(c13 * a, a, fma(b, b, eps));
+  a = q1 - 2.0 * q2 + q3;
+  b = q3 - q1;
+  const double b1 = fma(c13 * a, a, fma(b, b, eps));
+  a = q2 - 2.0 * q3 + q4;
+  b = q4 - 4.0 * q3 + 3.0 * q2;
+  const double b2 = fma(c13 * a, a, fma(b, b, eps));
+  const double tau5 = fabs(b2 - b0);
+
+  // r_k = (b_k + tau5) / b_k = 1 + tau5 * (prod of the other two) / (b0 b1 b2)
+  const double b01 = b0 * b1, b12 = b1 * b2, b02 = b0 * b2;
+  const double t = tau5 * rcp_nr(b01 * b2);
+  const double r0 = fma(t, b12, 1.0), r1 = fma(t, b02, 1.0), r2 = fma(t, b01, 1.0);
+
+  const double p0 = fma(a00, q0, fma(a01, q1, a02 * q2));
+  const double p1 = fma(a10, q1, fma(a11, q2, a12 * q3));
+  const double p2 = fma(a20, q2, fma(a21, q3, a22 * q4));
+  const double m0 = fma(a00, q4, fma(a01, q3, a02 * q2));
+  const double m1 = fma(a10, q3, fma(a11, q2, a12 * q1));
+  const double m2 = fma(a20, q2, fma(a21, q1, a22 * q0));
+
+  // left state: weights w_k = g_k r_k + eps; ql = sum(w p)/S; alpha = 3 w0w1w2/(S D) + eps
+  double w0 = fma(g0, r0, eps), w1 = fma(g1, r1, eps), w2 = fma(g2, r2, eps);
+  double w12 = w1 * w2;
+  double S = w0 + w1 + w2;
+  double D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
+  double iSD = rcp_nr(S * D);
+  const double alpha_l = fma(3.0 * w0 * w12, iSD, eps);
+  const double qlw = fma(w0, p0, fma(w1, p1, w2 * p2)) * (D * iSD);
+
+  w0 = fma(g0, r2, eps);
+  w1 = fma(g1, r1, eps);
+  w2 = fma(g2, r0, eps);
+  w12 = w1 * w2;
+  S = w0 + w1 + w2;
+  D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
+  iSD = rcp_nr(S * D);
+  const double alpha_r = fma(3.0 * w0 * w12, iSD, eps);
+  const double qrw = fma(w0, m0, fma(w1, m1, w2 * m2)) * (D * iSD);
+
+  const double dq = 0.5 * mc(q2 - q1, q3 - q2);
+  const double alpha_lin = 2.0 * alpha_l * alpha_r * rcp_nr(alpha_l + alpha_r);
+  const double om = 1.0 - alpha_lin;
+  ql = fma(alpha_lin, qlw, om * (q2 + dq));
+  qr = fma(alpha_lin, qrw, om * (q2 - dq));
+}
+
+// per-face HLL coefficients shared by all components (burgers_package.hpp:31-43 and
+// burgers_package.cpp:326-333):  F = A*qL - B*qR + C*(qR - qL), velocities carry an extra 1/2
+struct FaceCoef {
+  double A, B, C;
+};
+__device__ __forceinline__ FaceCoef face_coef(const double upl, const double upr) {
+  const double sl = min_std(min_std(upl, upr), 0.0);
+  const double sr = max_std(max_std(upl, upr), 0.0);
+  const double slsr = sl * sr;
+  const double inv = rcp_nr(sr - sl + (slsr == 0.0 ? 1.0 : 0.0));
+  FaceCoef f;
+  f.A = sr * upl * inv;
+  f.B = sl * upr * inv;
+  f.C = slsr * inv;
+  return f;
+}
+__device__ __forceinline__ double face_flux(const FaceCoef &f, const double ql, const double qr) {
+  return fma(f.A, ql, fma(-f.B, qr, f.C * (qr - ql)));
+}
+
+template <int RECON>
+__device__ __forceinline__ void load_stencil(const double *__restrict__ p, const int64_t sd,
+                                             double q[5]) {
+  if (RECON == PB2_RECON_WENO5) {
+    q[0] = __ldg(p - 2 * sd);
+    q[4] = __ldg(p + 2 * sd);
+  }
+  q[1] = __ldg(p - sd);
+  q[2] = __ldg(p);
+  q[3] = __ldg(p + sd);
+}
+template <int RECON>
+__device__ __forceinline__ void recon(const double q[5], double &ql, double &qr) {
+  if (RECON == PB2_RECON_WENO5)
+    WENO5Z(q[0], q[1], q[2], q[3], q[4], ql, qr);
+  else
+    Linear(q[1], q[2], q[3], ql, qr);
+}
+
+__device__ __forceinline__ void finish_cell(const Args &a, const int b, const int64_t cell,
+                                            const double v0, const double v1, const double v2,
+                                            const double v3, const double idx0,
+                                            const double idx1, const double idx2,
+                                            double &inv) {
+  if (a.derived)
+    a.derived[(int64_t)b * a.g.sc + cell] = 0.5 * v3 * (v0 * v0 + v1 * v1 + v2 * v2);
+  const double rate = fabs(v0) * idx0 + (a.g.ndim > 1 ? fabs(v1) * idx1 : 0.0) +
+                      (a.g.ndim > 2 ? fabs(v2) * idx2 : 0.0);
+  inv = max_std(inv, rate); // min of 1/rate == 1 / max(rate)
+}
+
+__device__ __forceinline__ void reduce_dt(const Args &a, double rate) {
+  if (!a.dtmin) return;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) rate = max_std(rate, __shfl_xor_sync(0xffffffffu, rate, s));
+  if ((threadIdx.x & 31) == 0) {
+    const double inv = 1.0 / rate;
+    atomicMin(a.dtmin, static_cast<unsigned long long>(__double_as_longlong(inv)));
+  }
+}
+
+// ---- y / z sweeps: a thread owns one (i, other) column and marches along DIR ---------------
+template <int RECON, int DIR, bool LAST>
+__global__ void __launch_bounds__(kThreads) sweep_march_kernel(const Args a) {
+  const Geom &g = a.g;
+  const int ncol_other = (DIR == 1) ? g.nx[2] : g.nx[1];
+  const int ncol = ncol_other * g.nx[0];
+  const int ctas_per_block = (ncol + kThreads - 1) / kThreads;
+  const int b = blockIdx.x / ctas_per_block;
+  const int col = (blockIdx.x % ctas_per_block) * kThreads + threadIdx.x;
+  __shared__ double sL[kMaxComp][kThreads], sF[kMaxComp][kThreads];
+  double rate = 0.0;
+  if (col < ncol) {
+    const int i = g.is[0] + col % g.nx[0];
+    const int o = col / g.nx[0];
+    const int64_t sd = (DIR == 1) ? g.sj : g.sk;
+    const int64_t so = (DIR == 1) ? g.sk : g.sj;
+    const int os = (DIR == 1) ? g.is[2] : g.is[1];
+    const int ds = g.is[DIR], nd = g.nx[DIR];
+    const int64_t col0 = (int64_t)(os + o) * so + i; // offset inside one component
+    const double *__restrict__ ub = a.u + (int64_t)b * g.sb + col0;
+    double *__restrict__ ob = a.out + (int64_t)b * g.sb + col0;
+    const int nc = g.ncomp;
+    const double idx0 = 1.0 / a.dx[3 * b], idx1 = 1.0 / a.dx[3 * b + 1],
+                 idx2 = 1.0 / a.dx[3 * b + 2];
+    const double cdir = -a.bdt * (DIR == 1 ? idx1 : idx2);
+
+    double Lc[3] = {0, 0, 0}, Fc[3] = {0, 0, 0};
+    for (int n = 3; n < nc; ++n) {
+      sL[n][threadIdx.x] = 0.0;
+      sF[n][threadIdx.x] = 0.0;
+    }
+    // cells ds-1 .. ds+nd, faces ds .. ds+nd; cell s-1 is complete once face s is known
+    for (int s = -1; s <= nd; ++s) {
+      const int64_t off = (int64_t)(ds + s) * sd;
+      const bool face = s >= 0, upd = s >= 1;
+      double q[5], qn[5];
+      double ql[3], qr[3];
+      load_stencil<RECON>(ub + off, sd, q);
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn); // prefetch next component
+        recon<RECON>(q, ql[n], qr[n]);
+#pragma unroll
+        for (int t = 0; t < 5; ++t) q[t] = qn[t];
+      }
+      const FaceCoef fc = face_coef(Lc[DIR], qr[DIR]);
+      double v[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const double f = 0.5 * face_flux(fc, Lc[n], qr[n]);
+        if (upd) {
+          double *po = ob + n * g.sc + off - sd;
+          v[n] = fma(cdir, f - Fc[n], *po);
+          *po = v[n];
+        }
+        Fc[n] = f;
+        Lc[n] = ql[n];
+      }
+#pragma unroll 1
+      for (int n = 3; n < nc; ++n) {
+        if (n + 1 < nc) load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn);
+        double l, r;
+        recon<RECON>(q, l, r);
+        const double f = face_flux(fc, sL[n][threadIdx.x], r);
+        if (upd) {
+          double *po = ob + n * g.sc + off - sd;
+          const double val = fma(cdir, f - sF[n][threadIdx.x], *po);
+          *po = val;
+          if (n == 3) v[3] = val;
+        }
+        sF[n][threadIdx.x] = f;
+        sL[n][threadIdx.x] = l;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) q[t] = qn[t];
+      }
+      if (LAST && upd) finish_cell(a, b, col0 + off - sd, v[0], v[1], v[2], v[3], idx0, idx1, idx2, rate);
+      (void)face;
+    }
+  }
+  if (LAST) reduce_dt(a, rate);
+}
+
+// ---- x sweep: (row, cell) items flattened over the lanes of a warp --------------------------
+constexpr int kRowsPerWarp = 16;
+
+template <int RECON, bool LAST>
+__global__ void __launch_bounds__(kThreads) sweep_x_kernel(const Args a) {
+  const Geom &g = a.g;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warp_global = blockIdx.x * (kThreads / 32) + wid;
+  const int nrows = g.nx[1] * g.nx[2];
+  const int warps_per_block = (nrows + kRowsPerWarp - 1) / kRowsPerWarp;
+  const int b = warp_global / warps_per_block;
+  double rate = 0.0;
+  __shared__ double sL[kThreads / 32][kMaxComp], sF[kThreads / 32][kMaxComp];
+  if (b < g.nblocks) { // whole warp together
+    const int row0 = (warp_global % warps_per_block) * kRowsPerWarp;
+    const int rows = min(kRowsPerWarp, nrows - row0);
+    const int ncell = g.nx[0] + 2;
+    const int items = rows * ncell;
+    const int nc = g.ncomp;
+    const double *__restrict__ ub = a.u + (int64_t)b * g.sb;
+    const double *__restrict__ bb = a.base + (int64_t)b * g.sb;
+    double *__restrict__ ob = a.out + (int64_t)b * g.sb;
+    const double idx0 = 1.0 / a.dx[3 * b], idx1 = 1.0 / a.dx[3 * b + 1],
+                 idx2 = 1.0 / a.dx[3 * b + 2];
+    const double cdir = -a.bdt * idx0;
+    const bool use_base = a.w2 != 0.0;
+    const int src = (lane + 31) & 31;
+
+    // values of lane 31 in the previous pass, handed to lane 0 of this pass
+    double pL[3] = {0, 0, 0}, pF[3] = {0, 0, 0};
+    if (lane < kMaxComp) {
+      sL[wid][lane] = 0.0;
+      sF[wid][lane] = 0.0;
+    }
+    __syncwarp();
+    for (int f0 = 0; f0 < items; f0 += 32) {
+      const int f = f0 + lane;
+      const bool cell = f < items;
+      const int fr = cell ? f : items - 1; // inactive lanes recompute a valid cell
+      const int r = fr / ncell, c = fr - r * ncell;
+      const int row = row0 + r;
+      const int k = g.is[2] + row / g.nx[1], j = g.is[1] + row % g.nx[1];
+      const int i = g.is[0] - 1 + c;
+      const int64_t off = (int64_t)k * g.sk + (int64_t)j * g.sj + i;
+      const bool upd = cell && c >= 2; // this lane completes cell i-1
+      double q[5], qn[5];
+      double ql[3], qr[3], um[3];
+      load_stencil<RECON>(ub + off, 1, q);
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        load_stencil<RECON>(ub + (n + 1) * g.sc + off, 1, qn);
+        um[n] = q[1];
+        recon<RECON>(q, ql[n], qr[n]);
+#pragma unroll
+        for (int t = 0; t < 5; ++t) q[t] = qn[t];
+      }
+      double Lp[3];
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        Lp[n] = __shfl_sync(full, lane == 31 ? pL[n] : ql[n], src);
+        pL[n] = ql[n];
+      }
+      const FaceCoef fc = face_coef(Lp[0], qr[0]);
+      double v[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const double fl = 0.5 * face_flux(fc, Lp[n], qr[n]);
+        const double fprev = __shfl_sync(full, lane == 31 ? pF[n] : fl, src);
+        pF[n] = fl;
+        if (upd) {
+          double avg = a.beta * um[n];
+          if (use_base) avg = fma(a.w2, __ldg(bb + n * g.sc + off - 1), avg);
+          v[n] = fma(cdir, fl - fprev, avg);
+          ob[n * g.sc + off - 1] = v[n];
+        }
+      }
+#pragma unroll 1
+      for (int n = 3; n < nc; ++n) {
+        if (n + 1 < nc) load_stencil<RECON>(ub + (n + 1) * g.sc + off, 1, qn);
+        double l, rr;
+        recon<RECON>(q, l, rr);
+        // lane 31 offers what it held in the previous pass (parked in shared memory)
+        const double carryL = sL[wid][n], carryF = sF[wid][n];
+        const double Lq = __shfl_sync(full, lane == 31 ? carryL : l, src);
+        const double fl = face_flux(fc, Lq, rr);
+        const double fprev = __shfl_sync(full, lane == 31 ? carryF : fl, src);
+        __syncwarp();
+        if (lane == 31) {
+          sL[wid][n] = l;
+          sF[wid][n] = fl;
+        }
+        __syncwarp();
+        if (upd) {
+          double avg = a.beta * q[1];
+          if (use_base) avg = fma(a.w2, __ldg(bb + n * g.sc + off - 1), avg);
+          const double val = fma(cdir, fl - fprev, avg);
+          ob[n * g.sc + off - 1] = val;
+          if (n == 3) v[3] = val;
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t) q[t] = qn[t];
+      }
+      if (LAST && upd) finish_cell(a, b, off - 1, v[0], v[1], v[2], v[3], idx0, idx1, idx2, rate);
+    }
+  }
+  if (LAST) reduce_dt(a, rate);
+}
+
+template <int RECON>
+int launch(const pb2_burgers_args *args, cudaStream_t st) {
+  Args a;
+  const pb2_pack_geom &pg = args->geom;
+  Geom &g = a.g;
+  g.nblocks = pg.nblocks;
+  g.ncomp = pg.ncomp;
+  g.ndim = pg.ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg.ndim;
+    g.nx[d] = sym ? 1 : pg.nx[d];
+    g.is[d] = sym ? 0 : pg.ng;
+    g.n[d] = sym ? 1 : pg.nx[d] + 2 * pg.ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg.block_stride;
+  a.u = args->u;
+  a.base = args->base;
+  a.out = args->out;
+  a.dx = pg.dx;
+  a.beta = args->beta;
+  a.w2 = 1.0 - args->beta;
+  a.bdt = args->beta * args->dt;
+  a.derived = nullptr;
+  a.dtmin = nullptr;
+  auto last = [&](Args &x) {
+    x.derived = args->derived;
+    x.dtmin = reinterpret_cast<unsigned long long *>(args->dt_min);
+  };
+  {
+    const int nrows = g.nx[1] * g.nx[2];
+    const int warps = g.nblocks * ((nrows + kRowsPerWarp - 1) / kRowsPerWarp);
+    const int wpc = kThreads / 32;
+    const int ctas = (warps + wpc - 1) / wpc;
+    ProfScope prof(K_SWEEP_X, st);
+    if (g.ndim == 1) {
+      last(a);
+      sweep_x_kernel<RECON, true><<<ctas, kThreads, 0, st>>>(a);
+    } else {
+      sweep_x_kernel<RECON, false><<<ctas, kThreads, 0, st>>>(a);
+    }
+    PB2_LAUNCH_CHECK();
+  }
+  if (g.ndim > 1) {
+    const int ncol = g.nx[2] * g.nx[0];
+    const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
+    ProfScope prof(K_SWEEP_Y, st);
+    if (g.ndim == 2) {
+      last(a);
+      sweep_march_kernel<RECON, 1, true><<<ctas, kThreads, 0, st>>>(a);
+    } else {
+      sweep_march_kernel<RECON, 1, false><<<ctas, kThreads, 0, st>>>(a);
+    }
+    PB2_LAUNCH_CHECK();
+  }
+  if (g.ndim > 2) {
+    const int ncol = g.nx[1] * g.nx[0];
+    const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
+    last(a);
+    ProfScope prof(K_SWEEP_Z, st);
+    sweep_march_kernel<RECON, 2, true><<<ctas, kThreads, 0, st>>>(a);
+    PB2_LAUNCH_CHECK();
+  }
+  return PB2_OK;
+}
+
+} // namespace sweep
+
+int burgers_stage_sweep(const pb2_burgers_args *args, cudaStream_t st) {
+  if (args->recon == PB2_RECON_WENO5) return sweep::launch<PB2_RECON_WENO5>(args, st);
+  return sweep::launch<PB2_RECON_LINEAR>(args, st);
+}
+
+} // namespace pb2

@@ -30,7 +30,7 @@ const char *kKernelNames[K_COUNT] = {
     "pack_kernel", "unpack_kernel", "copy_kernel", "restrict_kernel", "prolongate_kernel",
     "weighted_sum_kernel", "flux_div_kernel", "flux_x_kernel", "flux_march_kernel<y>",
     "flux_march_kernel<z>", "update_kernel", "derived_dt_kernel", "history_kernel",
-    "stage_fused_kernel"};
+    "sweep_x_kernel", "sweep_march_kernel<y>", "sweep_march_kernel<z>"};
 } // namespace
 
 void profile_begin(int id, cudaStream_t s, void **token) {
@@ -85,9 +85,57 @@ int require_device() {
 }
 } // namespace pb2
 
+namespace pb2 {
+// FP64 FMA throughput microbenchmark: 8 independent dependency chains per thread
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b);
+    x1 = fma(x1, a, b);
+    x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b);
+    x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b);
+    x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+} // namespace pb2
+
 using namespace pb2;
 
 extern "C" {
+
+int pb2_measure_fp64_peak(double *tflops) {
+  PB2_REQUIRE(tflops, "null argument");
+  if (int rc = require_device()) return rc;
+  int dev = 0, sms = 0;
+  PB2_CUDA_CHECK(cudaGetDevice(&dev));
+  PB2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ctas = sms * 8, iters = 1 << 15;
+  double *out = nullptr;
+  PB2_CUDA_CHECK(cudaMalloc(&out, sizeof(double) * ctas * 256));
+  cudaEvent_t e0, e1;
+  PB2_CUDA_CHECK(cudaEventCreate(&e0));
+  PB2_CUDA_CHECK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    PB2_CUDA_CHECK(cudaEventRecord(e0));
+    fp64_peak_kernel<<<ctas, 256>>>(out, iters, 0.999999, 1e-6);
+    PB2_CUDA_CHECK(cudaEventRecord(e1));
+    PB2_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    PB2_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = 2.0 * 8.0 * iters * double(ctas) * 256.0 / (best * 1e-3) / 1e12;
+  return PB2_OK;
+}
 
 int pb2_version(void) { return 100; }
 const char *pb2_last_error(void) { return g_err; }

@@ -65,10 +65,12 @@ def test_fast_cycles_within_tolerance_of_reference_dumps(recon, ng):
         assert abs(sim.time - g["times"][c]) <= TOL * g["times"][c]
 
 
-@pytest.mark.parametrize("math,rtol", [("strict", 2e-14), ("fast", 1e-12)])
+@pytest.mark.parametrize("math,rtol", [("strict", 2e-13), ("fast", 1e-12)])
 def test_history_vs_reference_hst(math, rtol):
     """benchmark shape (32^3 blocks, 8 scalars, weno5) for 10 cycles against the reference's
-    own .hst (%.14e text, so strict is compared at text precision)"""
+    own .hst.  The fields are bit-exact in strict mode, but the history columns are sums of
+    262 144 x 11 terms whose order differs between the device tree reduction and the
+    reference's OpenMP reduction, hence 2e-13 rather than the text precision of %.14e."""
     h = read_hst(os.path.join(GOLD, "burgers_u64_b32_s8_weno5.hst"))
     sim = host.Simulation(overrides=burgers_overrides(32, 2, 4, 8, "weno5", math, True))
     sim.pre_execute()
