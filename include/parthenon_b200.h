@@ -227,8 +227,8 @@ int pb2_burgers_calculate_fluxes(const pb2_burgers_args *args, pb2_stream_t stre
 int pb2_burgers_update(const pb2_burgers_args *args, pb2_stream_t stream);
 /* One call per stage.  PB2_MATH_STRICT: the two calls above (needs args->flux).
  * PB2_MATH_FAST: three direction sweeps that keep every flux in registers and accumulate its
- * divergence straight into `out` (args->flux is ignored and may be NULL; out must not alias
- * u or base). */
+ * divergence straight into `out` (args->flux is ignored and may be NULL; out may alias base
+ * but not u). */
 int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream);
 /* stand-alone CalculateDerived (burgers_package.cpp:143-167) and/or EstimateTimestepMesh
  * (:170-200) over interior cells: derived [nblocks][nk][nj][ni] or NULL; dt_min device scalar

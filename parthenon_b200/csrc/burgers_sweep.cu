@@ -24,8 +24,17 @@
 
 #include "common.cuh"
 
+#ifndef PB2_SWEEP_MINB
+#define PB2_SWEEP_MINB 5
+#endif
+#ifndef PB2_SWEEP_NS
+#define PB2_SWEEP_NS sweep
+#endif
+#define PB2_CAT_(a, b) a##b
+#define PB2_CAT(a, b) PB2_CAT_(a, b)
+
 namespace pb2 {
-namespace sweep {
+namespace PB2_SWEEP_NS {
 
 constexpr int kThreads = 128;
 constexpr int kMaxComp = 16;
@@ -58,6 +67,11 @@ __device__ __forceinline__ double rcp_nr(double a) {
   e = fma(-a, x, 1.0);
   x = fma(x, e, x);
   return x;
+}
+
+// pull the line holding p into L1 ahead of the pass / march step that will read it
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 // recon.hpp:27-32
@@ -196,7 +210,7 @@ __device__ __forceinline__ void reduce_dt(const Args &a, double rate) {
 
 // ---- y / z sweeps: a thread owns one (i, other) column and marches along DIR ---------------
 template <int RECON, int DIR, bool LAST>
-__global__ void __launch_bounds__(kThreads) sweep_march_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_march_kernel(const Args a) {
   const Geom &g = a.g;
   const int ncol_other = (DIR == 1) ? g.nx[2] : g.nx[1];
   const int ncol = ncol_other * g.nx[0];
@@ -229,43 +243,58 @@ __global__ void __launch_bounds__(kThreads) sweep_march_kernel(const Args a) {
     for (int s = -1; s <= nd; ++s) {
       const int64_t off = (int64_t)(ds + s) * sd;
       const bool face = s >= 0, upd = s >= 1;
-      double q[5], qn[5];
+      // stencil values and the old value of the cell this step completes are fetched one
+      // component ahead of their use, so loads overlap a whole reconstruction
+      double q[5], qn[5], old[3], oldn = 0.0, oldc = 0.0;
       double ql[3], qr[3];
+      double *po = ob + off - sd; // cell s-1, component 0
+      if (s < nd) {
+        // the next step's new row (and the `out` cell it completes) start their trip from
+        // HBM now, a whole march step before they are needed
+        const double *pn = ub + off + (RECON == PB2_RECON_WENO5 ? 3 : 2) * sd;
+        for (int n = 0; n < nc; ++n) prefetch_l1(pn + n * g.sc);
+        if (face)
+          for (int n = 0; n < nc; ++n) prefetch_l1(po + sd + n * g.sc);
+      }
       load_stencil<RECON>(ub + off, sd, q);
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
         load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn); // prefetch next component
+        old[n] = upd ? po[n * g.sc] : 0.0;
         recon<RECON>(q, ql[n], qr[n]);
 #pragma unroll
         for (int t = 0; t < 5; ++t) q[t] = qn[t];
       }
+      if (upd) oldc = po[3 * g.sc];
       const FaceCoef fc = face_coef(Lc[DIR], qr[DIR]);
       double v[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
         const double f = 0.5 * face_flux(fc, Lc[n], qr[n]);
         if (upd) {
-          double *po = ob + n * g.sc + off - sd;
-          v[n] = fma(cdir, f - Fc[n], *po);
-          *po = v[n];
+          v[n] = fma(cdir, f - Fc[n], old[n]);
+          po[n * g.sc] = v[n];
         }
         Fc[n] = f;
         Lc[n] = ql[n];
       }
 #pragma unroll 1
       for (int n = 3; n < nc; ++n) {
-        if (n + 1 < nc) load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn);
+        if (n + 1 < nc) {
+          load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn);
+          if (upd) oldn = po[(n + 1) * g.sc];
+        }
         double l, r;
         recon<RECON>(q, l, r);
         const double f = face_flux(fc, sL[n][threadIdx.x], r);
         if (upd) {
-          double *po = ob + n * g.sc + off - sd;
-          const double val = fma(cdir, f - sF[n][threadIdx.x], *po);
-          *po = val;
+          const double val = fma(cdir, f - sF[n][threadIdx.x], oldc);
+          po[n * g.sc] = val;
           if (n == 3) v[3] = val;
         }
         sF[n][threadIdx.x] = f;
         sL[n][threadIdx.x] = l;
+        oldc = oldn;
 #pragma unroll
         for (int t = 0; t < 5; ++t) q[t] = qn[t];
       }
@@ -280,7 +309,7 @@ __global__ void __launch_bounds__(kThreads) sweep_march_kernel(const Args a) {
 constexpr int kRowsPerWarp = 16;
 
 template <int RECON, bool LAST>
-__global__ void __launch_bounds__(kThreads) sweep_x_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_x_kernel(const Args a) {
   const Geom &g = a.g;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -297,8 +326,10 @@ __global__ void __launch_bounds__(kThreads) sweep_x_kernel(const Args a) {
     const int items = rows * ncell;
     const int nc = g.ncomp;
     const double *__restrict__ ub = a.u + (int64_t)b * g.sb;
-    const double *__restrict__ bb = a.base + (int64_t)b * g.sb;
-    double *__restrict__ ob = a.out + (int64_t)b * g.sb;
+    // `out` may alias `base` (second RK stage: base <- 0.5*"1" + 0.5*base + ...): each cell of
+    // base is read by the one thread that then writes it, so neither pointer is restrict
+    const double *bb = a.base + (int64_t)b * g.sb;
+    double *ob = a.out + (int64_t)b * g.sb;
     const double idx0 = 1.0 / a.dx[3 * b], idx1 = 1.0 / a.dx[3 * b + 1],
                  idx2 = 1.0 / a.dx[3 * b + 2];
     const double cdir = -a.bdt * idx0;
@@ -322,12 +353,24 @@ __global__ void __launch_bounds__(kThreads) sweep_x_kernel(const Args a) {
       const int i = g.is[0] - 1 + c;
       const int64_t off = (int64_t)k * g.sk + (int64_t)j * g.sj + i;
       const bool upd = cell && c >= 2; // this lane completes cell i-1
-      double q[5], qn[5];
+      double q[5], qn[5], bv[3] = {0, 0, 0}, bvc = 0.0, bvn = 0.0;
       double ql[3], qr[3], um[3];
+      const bool ldb = use_base && upd; // base(i-1) is fetched together with the stencil
+      if (f0 + 32 < items) {
+        // lines of the NEXT pass (32 items further along the flattened rows)
+        const int f2 = min(f + 32, items - 1);
+        const int r2 = f2 / ncell, c2 = f2 - r2 * ncell, row2 = row0 + r2;
+        const int64_t off2 = (int64_t)(g.is[2] + row2 / g.nx[1]) * g.sk +
+                             (int64_t)(g.is[1] + row2 % g.nx[1]) * g.sj + (g.is[0] - 1 + c2);
+        for (int n = 0; n < nc; ++n) prefetch_l1(ub + n * g.sc + off2);
+        if (use_base)
+          for (int n = 0; n < nc; ++n) prefetch_l1(bb + n * g.sc + off2);
+      }
       load_stencil<RECON>(ub + off, 1, q);
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
         load_stencil<RECON>(ub + (n + 1) * g.sc + off, 1, qn);
+        if (ldb) bv[n] = bb[n * g.sc + off - 1];
         um[n] = q[1];
         recon<RECON>(q, ql[n], qr[n]);
 #pragma unroll
@@ -347,15 +390,18 @@ __global__ void __launch_bounds__(kThreads) sweep_x_kernel(const Args a) {
         const double fprev = __shfl_sync(full, lane == 31 ? pF[n] : fl, src);
         pF[n] = fl;
         if (upd) {
-          double avg = a.beta * um[n];
-          if (use_base) avg = fma(a.w2, __ldg(bb + n * g.sc + off - 1), avg);
+          const double avg = fma(a.w2, bv[n], a.beta * um[n]);
           v[n] = fma(cdir, fl - fprev, avg);
           ob[n * g.sc + off - 1] = v[n];
         }
       }
+      if (ldb) bvc = bb[3 * g.sc + off - 1];
 #pragma unroll 1
       for (int n = 3; n < nc; ++n) {
-        if (n + 1 < nc) load_stencil<RECON>(ub + (n + 1) * g.sc + off, 1, qn);
+        if (n + 1 < nc) {
+          load_stencil<RECON>(ub + (n + 1) * g.sc + off, 1, qn);
+          if (ldb) bvn = bb[(n + 1) * g.sc + off - 1];
+        }
         double l, rr;
         recon<RECON>(q, l, rr);
         // lane 31 offers what it held in the previous pass (parked in shared memory)
@@ -370,12 +416,12 @@ __global__ void __launch_bounds__(kThreads) sweep_x_kernel(const Args a) {
         }
         __syncwarp();
         if (upd) {
-          double avg = a.beta * q[1];
-          if (use_base) avg = fma(a.w2, __ldg(bb + n * g.sc + off - 1), avg);
+          const double avg = fma(a.w2, bvc, a.beta * q[1]);
           const double val = fma(cdir, fl - fprev, avg);
           ob[n * g.sc + off - 1] = val;
           if (n == 3) v[3] = val;
         }
+        bvc = bvn;
 #pragma unroll
         for (int t = 0; t < 5; ++t) q[t] = qn[t];
       }
@@ -453,11 +499,11 @@ int launch(const pb2_burgers_args *args, cudaStream_t st) {
   return PB2_OK;
 }
 
-} // namespace sweep
+} // namespace PB2_SWEEP_NS
 
-int burgers_stage_sweep(const pb2_burgers_args *args, cudaStream_t st) {
-  if (args->recon == PB2_RECON_WENO5) return sweep::launch<PB2_RECON_WENO5>(args, st);
-  return sweep::launch<PB2_RECON_LINEAR>(args, st);
+int PB2_CAT(burgers_stage_, PB2_SWEEP_NS)(const pb2_burgers_args *args, cudaStream_t st) {
+  if (args->recon == PB2_RECON_WENO5) return PB2_SWEEP_NS::launch<PB2_RECON_WENO5>(args, st);
+  return PB2_SWEEP_NS::launch<PB2_RECON_LINEAR>(args, st);
 }
 
 } // namespace pb2
