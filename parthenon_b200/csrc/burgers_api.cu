@@ -10,8 +10,6 @@ int burgers_update_strict(const pb2_burgers_args *, cudaStream_t);
 int burgers_fluxes_fast(const pb2_burgers_args *, cudaStream_t);
 int burgers_update_fast(const pb2_burgers_args *, cudaStream_t);
 int burgers_stage_sweep(const pb2_burgers_args *, cudaStream_t);
-int burgers_stage_sweep6(const pb2_burgers_args *, cudaStream_t);
-int burgers_stage_sweep8(const pb2_burgers_args *, cudaStream_t);
 
 static int check_args(const pb2_burgers_args *a, bool need_update, bool need_flux = true) {
   PB2_REQUIRE(a, "null args");
@@ -188,9 +186,6 @@ int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream) {
     if (int rc = require_device()) return rc;
     if (args->geom.nblocks == 0) return PB2_OK;
     PB2_REQUIRE(args->out != args->u, "the fused stage cannot write its stencil input");
-    static const int variant = getenv("PB2_SWEEP_VARIANT") ? atoi(getenv("PB2_SWEEP_VARIANT")) : 0;
-    if (variant == 6) return burgers_stage_sweep6(args, as_stream(stream));
-    if (variant == 8) return burgers_stage_sweep8(args, as_stream(stream));
     return burgers_stage_sweep(args, as_stream(stream));
   }
   if (int rc = pb2_burgers_calculate_fluxes(args, stream)) return rc;

@@ -25,7 +25,10 @@
 #include "common.cuh"
 
 #ifndef PB2_SWEEP_MINB
-#define PB2_SWEEP_MINB 5
+#define PB2_SWEEP_MINB 4
+#endif
+#ifndef PB2_SWEEP_UNR
+#define PB2_SWEEP_UNR 2
 #endif
 #ifndef PB2_SWEEP_NS
 #define PB2_SWEEP_NS sweep
@@ -278,6 +281,38 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_march_kernel(c
         Fc[n] = f;
         Lc[n] = ql[n];
       }
+#if PB2_SWEEP_UNR == 2
+      // two scalars per trip: their reconstructions are independent instruction streams
+      (void)oldn;
+#pragma unroll 1
+      for (int n = 3; n < nc; n += 2) {
+        const bool two = n + 1 < nc;
+        const int n2 = two ? n + 1 : n;
+        load_stencil<RECON>(ub + n2 * g.sc + off, sd, qn);
+        const double old2 = upd ? po[n2 * g.sc] : 0.0;
+        double l, r, l2, r2;
+        recon<RECON>(q, l, r);
+        recon<RECON>(qn, l2, r2);
+        const double f = face_flux(fc, sL[n][threadIdx.x], r);
+        const double f2 = face_flux(fc, sL[n2][threadIdx.x], r2);
+        if (upd) {
+          const double val = fma(cdir, f - sF[n][threadIdx.x], oldc);
+          po[n * g.sc] = val;
+          if (n == 3) v[3] = val;
+          if (two) po[n2 * g.sc] = fma(cdir, f2 - sF[n2][threadIdx.x], old2);
+        }
+        sF[n][threadIdx.x] = f;
+        sL[n][threadIdx.x] = l;
+        if (two) {
+          sF[n2][threadIdx.x] = f2;
+          sL[n2][threadIdx.x] = l2;
+        }
+        if (n + 2 < nc) {
+          load_stencil<RECON>(ub + (n + 2) * g.sc + off, sd, q);
+          if (upd) oldc = po[(n + 2) * g.sc];
+        }
+      }
+#else
 #pragma unroll 1
       for (int n = 3; n < nc; ++n) {
         if (n + 1 < nc) {
@@ -298,6 +333,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_march_kernel(c
 #pragma unroll
         for (int t = 0; t < 5; ++t) q[t] = qn[t];
       }
+#endif
       if (LAST && upd) finish_cell(a, b, col0 + off - sd, v[0], v[1], v[2], v[3], idx0, idx1, idx2, rate);
       (void)face;
     }
@@ -396,6 +432,46 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_x_kernel(const
         }
       }
       if (ldb) bvc = bb[3 * g.sc + off - 1];
+#if PB2_SWEEP_UNR == 2
+      (void)bvn;
+#pragma unroll 1
+      for (int n = 3; n < nc; n += 2) {
+        const bool two = n + 1 < nc;
+        const int n2 = two ? n + 1 : n;
+        load_stencil<RECON>(ub + n2 * g.sc + off, 1, qn);
+        const double bv2 = ldb ? bb[n2 * g.sc + off - 1] : 0.0;
+        double l, rr, l2, rr2;
+        recon<RECON>(q, l, rr);
+        recon<RECON>(qn, l2, rr2);
+        const double cL = sL[wid][n], cF = sF[wid][n], cL2 = sL[wid][n2], cF2 = sF[wid][n2];
+        const double Lq = __shfl_sync(full, lane == 31 ? cL : l, src);
+        const double Lq2 = __shfl_sync(full, lane == 31 ? cL2 : l2, src);
+        const double fl = face_flux(fc, Lq, rr), fl2 = face_flux(fc, Lq2, rr2);
+        const double fprev = __shfl_sync(full, lane == 31 ? cF : fl, src);
+        const double fprev2 = __shfl_sync(full, lane == 31 ? cF2 : fl2, src);
+        __syncwarp();
+        if (lane == 31) {
+          sL[wid][n] = l;
+          sF[wid][n] = fl;
+          if (two) {
+            sL[wid][n2] = l2;
+            sF[wid][n2] = fl2;
+          }
+        }
+        __syncwarp();
+        if (upd) {
+          const double val = fma(cdir, fl - fprev, fma(a.w2, bvc, a.beta * q[1]));
+          ob[n * g.sc + off - 1] = val;
+          if (n == 3) v[3] = val;
+          if (two)
+            ob[n2 * g.sc + off - 1] = fma(cdir, fl2 - fprev2, fma(a.w2, bv2, a.beta * qn[1]));
+        }
+        if (n + 2 < nc) {
+          load_stencil<RECON>(ub + (n + 2) * g.sc + off, 1, q);
+          if (ldb) bvc = bb[(n + 2) * g.sc + off - 1];
+        }
+      }
+#else
 #pragma unroll 1
       for (int n = 3; n < nc; ++n) {
         if (n + 1 < nc) {
@@ -425,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_x_kernel(const
 #pragma unroll
         for (int t = 0; t < 5; ++t) q[t] = qn[t];
       }
+#endif
       if (LAST && upd) finish_cell(a, b, off - 1, v[0], v[1], v[2], v[3], idx0, idx1, idx2, rate);
     }
   }
