@@ -20,6 +20,9 @@ import sys
 import threading
 import time
 
+# rank 0 must print exactly one JSON line on stdout: keep NCCL's banner off it
+os.environ["NCCL_DEBUG"] = os.environ.get("PB2_NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
