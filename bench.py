@@ -270,16 +270,18 @@ def main():
     # ---- end to end: state uploaded from pinned host memory and read back every step --------
     e2e = None
     if not args.no_e2e:
-        ptr, nreal = sim.field_ptr("base", "U")
+        # the application's state lives in HOST memory (interior cells, pinned); every step
+        # uploads it, fills ghosts, advances one cycle and reads the new state back
+        nreal = sim.interior_size("base", "U")
         hbuf = torch.empty(nreal, dtype=torch.float64).pin_memory()
         hp = hbuf.data_ptr()
-        capi.check(L.pb2_memcpy_d2h(hp, ptr, 8 * nreal, sim.stream))
+        sim.download_interior("base", "U", hp, nreal)
         sim.sync()
 
         def e2e_step():
-            capi.check(L.pb2_memcpy_h2d(ptr, hp, 8 * nreal, sim.stream))
+            sim.upload_interior("base", "U", hp, nreal)
             sim.cycle()
-            capi.check(L.pb2_memcpy_d2h(hp, ptr, 8 * nreal, sim.stream))
+            sim.download_interior("base", "U", hp, nreal)
 
         e2e_step()
         esec = timed(e2e_step, args.steps)
@@ -289,7 +291,9 @@ def main():
         e2e = {"value": args.steps * zones / esec, "unit": UNIT,
                "h2d_bytes_per_step": int(8 * tot.item()), "d2h_bytes_per_step": int(8 * tot.item()),
                "ms_per_step": 1e3 * esec / args.steps,
-               "what": "pinned host U -> H2D -> one RK2 cycle -> D2H U, every step"}
+               "what": "pinned host U (interior cells) -> H2D -> scatter + ghost exchange -> one RK2 "
+                       "cycle -> gather -> D2H, every step, through pb2h_sim_upload_interior / "
+                       "pb2h_sim_cycle / pb2h_sim_download_interior"}
 
     if rank != 0:
         if world > 1:

@@ -75,6 +75,14 @@ int pb2h_sim_get_field(pb2h_sim *sim, const char *container, const char *field, 
 int pb2h_sim_set_field(pb2h_sim *sim, const char *container, const char *field, int which,
                        const double *host, int64_t nreal);
 
+/* state through HOST buffers holding interior cells only, [block][comp][nx3][nx2][nx1] over
+ * this rank's blocks (pinned memory recommended).  upload = H2D + scatter + ghost exchange;
+ * download = gather + D2H.  Asynchronous on the application's stream: call pb2h_sim_sync
+ * before reading `host` after a download. */
+int pb2h_sim_upload_interior(pb2h_sim *sim, const char *container, const char *field,
+                             const double *host, int64_t nreal);
+int pb2h_sim_download_interior(pb2h_sim *sim, const char *container, const char *field,
+                               double *host, int64_t nreal);
 /* one full ghost exchange of a container (Send -> Receive -> Set [-> Prolongate]),
  * Mesh::CommunicateBoundaries mesh.cpp:640-706 */
 int pb2h_sim_exchange(pb2h_sim *sim, const char *container, int prolongate);

@@ -74,7 +74,7 @@ SYMBOLS = [
     "pb2_measure_fp64_peak",
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
-    "pb2_restrict", "pb2_prolongate", "pb2_weighted_sum", "pb2_flux_divergence",
+    "pb2_restrict", "pb2_prolongate", "pb2_weighted_sum", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",

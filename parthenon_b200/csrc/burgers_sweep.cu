@@ -212,15 +212,31 @@ __device__ __forceinline__ void reduce_dt(const Args &a, double rate) {
 }
 
 // ---- y / z sweeps: a thread owns one (i, other) column and marches along DIR ---------------
+// The five stencil rows of every component live in a per-thread ring in shared memory
+// (ring[comp][slot][thread]: thread-private columns, so no barriers and no bank conflicts).
+// Each march step reads ONE new row per component from global memory — issued before the
+// reconstruction whose oldest row it will overwrite, so HBM/L2 latency hides behind ~300 FP64
+// instructions — and takes its 5-point stencil from the ring.  (With plain global loads the
+// 11 x 5 rows of 4 resident CTAs overflow L1: 10 % hit rate, every stencil load an L2 trip.)
+constexpr int kRing = 5;
+
+__host__ __device__ inline size_t march_smem_bytes(int ncomp) {
+  return sizeof(double) * kThreads * (static_cast<size_t>(ncomp) * kRing + 2 * (ncomp - 3));
+}
+
 template <int RECON, int DIR, bool LAST>
-__global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_march_kernel(const Args a) {
+__global__ void __launch_bounds__(kThreads, 3) sweep_march_kernel(const Args a) {
   const Geom &g = a.g;
   const int ncol_other = (DIR == 1) ? g.nx[2] : g.nx[1];
   const int ncol = ncol_other * g.nx[0];
   const int ctas_per_block = (ncol + kThreads - 1) / kThreads;
   const int b = blockIdx.x / ctas_per_block;
   const int col = (blockIdx.x % ctas_per_block) * kThreads + threadIdx.x;
-  __shared__ double sL[kMaxComp][kThreads], sF[kMaxComp][kThreads];
+  const int nc = g.ncomp;
+  extern __shared__ double smem[];
+  double *ring = smem + threadIdx.x;                      // + (n * kRing + slot) * kThreads
+  double *sL = smem + (size_t)nc * kRing * kThreads + threadIdx.x; // + (n - 3) * kThreads
+  double *sF = sL + (size_t)(nc - 3) * kThreads;
   double rate = 0.0;
   if (col < ncol) {
     const int i = g.is[0] + col % g.nx[0];
@@ -232,43 +248,48 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_march_kernel(c
     const int64_t col0 = (int64_t)(os + o) * so + i; // offset inside one component
     const double *__restrict__ ub = a.u + (int64_t)b * g.sb + col0;
     double *__restrict__ ob = a.out + (int64_t)b * g.sb + col0;
-    const int nc = g.ncomp;
     const double idx0 = 1.0 / a.dx[3 * b], idx1 = 1.0 / a.dx[3 * b + 1],
                  idx2 = 1.0 / a.dx[3 * b + 2];
     const double cdir = -a.bdt * (DIR == 1 ? idx1 : idx2);
 
+    // fill the ring with rows ds-3 .. ds+1 (the stencil of cell ds-1); slot t <-> row ds-3+t
+    for (int n = 0; n < nc; ++n) {
+#pragma unroll
+      for (int t = 0; t < kRing; ++t)
+        ring[(n * kRing + t) * kThreads] =
+            __ldg(ub + n * g.sc + (int64_t)max(ds - 3 + t, 0) * sd); // (linear: row -1 unused)
+    }
     double Lc[3] = {0, 0, 0}, Fc[3] = {0, 0, 0};
     for (int n = 3; n < nc; ++n) {
-      sL[n][threadIdx.x] = 0.0;
-      sF[n][threadIdx.x] = 0.0;
+      sL[(n - 3) * kThreads] = 0.0;
+      sF[(n - 3) * kThreads] = 0.0;
     }
+    int s0 = 0; // slot holding row s-2
     // cells ds-1 .. ds+nd, faces ds .. ds+nd; cell s-1 is complete once face s is known
     for (int s = -1; s <= nd; ++s) {
       const int64_t off = (int64_t)(ds + s) * sd;
-      const bool face = s >= 0, upd = s >= 1;
-      // stencil values and the old value of the cell this step completes are fetched one
-      // component ahead of their use, so loads overlap a whole reconstruction
-      double q[5], qn[5], old[3], oldn = 0.0, oldc = 0.0;
-      double ql[3], qr[3];
-      double *po = ob + off - sd; // cell s-1, component 0
-      if (s < nd) {
-        // the next step's new row (and the `out` cell it completes) start their trip from
-        // HBM now, a whole march step before they are needed
-        const double *pn = ub + off + (RECON == PB2_RECON_WENO5 ? 3 : 2) * sd;
-        for (int n = 0; n < nc; ++n) prefetch_l1(pn + n * g.sc);
-        if (face)
-          for (int n = 0; n < nc; ++n) prefetch_l1(po + sd + n * g.sc);
-      }
-      load_stencil<RECON>(ub + off, sd, q);
+      const bool upd = s >= 1, more = s < nd;
+      int sl[kRing]; // ring slots of rows s-2 .. s+2, in units of kThreads doubles
+#pragma unroll
+      for (int t = 0; t < kRing; ++t) sl[t] = ((s0 + t) % kRing) * kThreads;
+      double *po = ob + off - sd;              // cell s-1, component 0
+      // row s+3, component 0 (clamped: with nghost 2 the linear stencil never reads it)
+      const double *pn = ub + (int64_t)min(ds + s + 3, g.n[DIR] - 1) * sd;
+      if (upd && more)
+        for (int n = 0; n < nc; ++n) prefetch_l1(po + sd + n * g.sc);
+
+      double ql[3], qr[3], old[3];
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
-        load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn); // prefetch next component
+        const double nw = more ? __ldg(pn + n * g.sc) : 0.0;
         old[n] = upd ? po[n * g.sc] : 0.0;
-        recon<RECON>(q, ql[n], qr[n]);
+        double q[5];
+        const double *rg = ring + n * kRing * kThreads;
 #pragma unroll
-        for (int t = 0; t < 5; ++t) q[t] = qn[t];
+        for (int t = 0; t < kRing; ++t) q[t] = rg[sl[t]];
+        recon<RECON>(q, ql[n], qr[n]);
+        ring[n * kRing * kThreads + sl[0]] = nw; // row s-2 is dead: it becomes row s+3
       }
-      if (upd) oldc = po[3 * g.sc];
       const FaceCoef fc = face_coef(Lc[DIR], qr[DIR]);
       double v[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -281,61 +302,46 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_march_kernel(c
         Fc[n] = f;
         Lc[n] = ql[n];
       }
-#if PB2_SWEEP_UNR == 2
       // two scalars per trip: their reconstructions are independent instruction streams
-      (void)oldn;
 #pragma unroll 1
       for (int n = 3; n < nc; n += 2) {
         const bool two = n + 1 < nc;
         const int n2 = two ? n + 1 : n;
-        load_stencil<RECON>(ub + n2 * g.sc + off, sd, qn);
+        const double nw = more ? __ldg(pn + n * g.sc) : 0.0;
+        const double nw2 = more ? __ldg(pn + n2 * g.sc) : 0.0;
+        const double old1 = upd ? po[n * g.sc] : 0.0;
         const double old2 = upd ? po[n2 * g.sc] : 0.0;
+        double q[5], q2[5];
+        double *rg = ring + n * kRing * kThreads, *rg2 = ring + n2 * kRing * kThreads;
+#pragma unroll
+        for (int t = 0; t < kRing; ++t) {
+          q[t] = rg[sl[t]];
+          q2[t] = rg2[sl[t]];
+        }
         double l, r, l2, r2;
         recon<RECON>(q, l, r);
-        recon<RECON>(qn, l2, r2);
-        const double f = face_flux(fc, sL[n][threadIdx.x], r);
-        const double f2 = face_flux(fc, sL[n2][threadIdx.x], r2);
+        recon<RECON>(q2, l2, r2);
+        double *pL = sL + (n - 3) * kThreads, *pF = sF + (n - 3) * kThreads;
+        double *pL2 = sL + (n2 - 3) * kThreads, *pF2 = sF + (n2 - 3) * kThreads;
+        const double f = face_flux(fc, *pL, r);
+        const double f2 = face_flux(fc, *pL2, r2);
         if (upd) {
-          const double val = fma(cdir, f - sF[n][threadIdx.x], oldc);
+          const double val = fma(cdir, f - *pF, old1);
           po[n * g.sc] = val;
           if (n == 3) v[3] = val;
-          if (two) po[n2 * g.sc] = fma(cdir, f2 - sF[n2][threadIdx.x], old2);
+          if (two) po[n2 * g.sc] = fma(cdir, f2 - *pF2, old2);
         }
-        sF[n][threadIdx.x] = f;
-        sL[n][threadIdx.x] = l;
+        *pF = f;
+        *pL = l;
+        rg[sl[0]] = nw;
         if (two) {
-          sF[n2][threadIdx.x] = f2;
-          sL[n2][threadIdx.x] = l2;
-        }
-        if (n + 2 < nc) {
-          load_stencil<RECON>(ub + (n + 2) * g.sc + off, sd, q);
-          if (upd) oldc = po[(n + 2) * g.sc];
+          *pF2 = f2;
+          *pL2 = l2;
+          rg2[sl[0]] = nw2;
         }
       }
-#else
-#pragma unroll 1
-      for (int n = 3; n < nc; ++n) {
-        if (n + 1 < nc) {
-          load_stencil<RECON>(ub + (n + 1) * g.sc + off, sd, qn);
-          if (upd) oldn = po[(n + 1) * g.sc];
-        }
-        double l, r;
-        recon<RECON>(q, l, r);
-        const double f = face_flux(fc, sL[n][threadIdx.x], r);
-        if (upd) {
-          const double val = fma(cdir, f - sF[n][threadIdx.x], oldc);
-          po[n * g.sc] = val;
-          if (n == 3) v[3] = val;
-        }
-        sF[n][threadIdx.x] = f;
-        sL[n][threadIdx.x] = l;
-        oldc = oldn;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) q[t] = qn[t];
-      }
-#endif
       if (LAST && upd) finish_cell(a, b, col0 + off - sd, v[0], v[1], v[2], v[3], idx0, idx1, idx2, rate);
-      (void)face;
+      s0 = (s0 + 1) % kRing;
     }
   }
   if (LAST) reduce_dt(a, rate);
@@ -535,6 +541,16 @@ int launch(const pb2_burgers_args *args, cudaStream_t st) {
   a.bdt = args->beta * args->dt;
   a.derived = nullptr;
   a.dtmin = nullptr;
+  // the march kernels keep their stencil rows in dynamic shared memory (opt-in above 48 KB)
+  const size_t smem = march_smem_bytes(g.ncomp);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int maxb = 200 * 1024;
+    PB2_CUDA_CHECK(cudaFuncSetAttribute(sweep_march_kernel<RECON, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    PB2_CUDA_CHECK(cudaFuncSetAttribute(sweep_march_kernel<RECON, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    PB2_CUDA_CHECK(cudaFuncSetAttribute(sweep_march_kernel<RECON, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    attr_set = true;
+  }
   auto last = [&](Args &x) {
     x.derived = args->derived;
     x.dtmin = reinterpret_cast<unsigned long long *>(args->dt_min);
@@ -559,9 +575,9 @@ int launch(const pb2_burgers_args *args, cudaStream_t st) {
     ProfScope prof(K_SWEEP_Y, st);
     if (g.ndim == 2) {
       last(a);
-      sweep_march_kernel<RECON, 1, true><<<ctas, kThreads, 0, st>>>(a);
+      sweep_march_kernel<RECON, 1, true><<<ctas, kThreads, smem, st>>>(a);
     } else {
-      sweep_march_kernel<RECON, 1, false><<<ctas, kThreads, 0, st>>>(a);
+      sweep_march_kernel<RECON, 1, false><<<ctas, kThreads, smem, st>>>(a);
     }
     PB2_LAUNCH_CHECK();
   }
@@ -570,7 +586,7 @@ int launch(const pb2_burgers_args *args, cudaStream_t st) {
     const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
     last(a);
     ProfScope prof(K_SWEEP_Z, st);
-    sweep_march_kernel<RECON, 2, true><<<ctas, kThreads, 0, st>>>(a);
+    sweep_march_kernel<RECON, 2, true><<<ctas, kThreads, smem, st>>>(a);
     PB2_LAUNCH_CHECK();
   }
   return PB2_OK;

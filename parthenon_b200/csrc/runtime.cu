@@ -30,7 +30,8 @@ const char *kKernelNames[K_COUNT] = {
     "pack_kernel", "unpack_kernel", "copy_kernel", "restrict_kernel", "prolongate_kernel",
     "weighted_sum_kernel", "flux_div_kernel", "flux_x_kernel", "flux_march_kernel<y>",
     "flux_march_kernel<z>", "update_kernel", "derived_dt_kernel", "history_kernel",
-    "sweep_x_kernel", "sweep_march_kernel<y>", "sweep_march_kernel<z>"};
+    "sweep_x_kernel", "sweep_march_kernel<y>", "sweep_march_kernel<z>",
+    "interior_kernel"};
 } // namespace
 
 void profile_begin(int id, cudaStream_t s, void **token) {

@@ -1,6 +1,8 @@
 // update.cu — dense per-stage updates (reference src/interface/update.hpp:43-91,
 // update.cpp:63-86).  Compiled with -fmad=false: these are memory-bound, so keeping the
 // reference's rounding costs nothing.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pb2 {
@@ -63,6 +65,33 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// interior cells <-> packed host-layout staging buffer [block][comp][nx3][nx2][nx1]
+// (what an application's host arrays hold: no ghosts).  16-byte vectors when nx1 is even.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+    interior_kernel(const DivGeom g, double *__restrict__ field, double *__restrict__ packed,
+                    int64_t total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int nx0 = g.nx[0], nx1 = g.nx[1], nx2 = g.nx[2];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t t = e;
+    const int i = (int)(t % nx0);
+    t /= nx0;
+    const int j = (int)(t % nx1);
+    t /= nx1;
+    const int k = (int)(t % nx2);
+    t /= nx2;
+    const int c = (int)(t % g.ncomp);
+    const int64_t b = t / g.ncomp;
+    const int64_t f = b * g.sb + c * g.sc + (int64_t)(k + g.is[2]) * g.sk +
+                      (int64_t)(j + g.is[1]) * g.sj + (i + g.is[0]);
+    if (SCATTER)
+      field[f] = packed[e];
+    else
+      packed[e] = field[f];
+  }
+}
+
 } // namespace pb2
 
 using namespace pb2;
@@ -82,6 +111,45 @@ int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, dou
                                                                                  z, n);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
+}
+
+static int interior_copy(const pb2_pack_geom *pg, double *field, double *packed, bool scatter,
+                         pb2_stream_t stream) {
+  PB2_REQUIRE(pg && field && packed, "bad arguments");
+  if (int rc = require_device()) return rc;
+  DivGeom g;
+  g.nblocks = pg->nblocks;
+  g.ncomp = pg->ncomp;
+  g.ndim = pg->ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg->ndim;
+    g.nx[d] = sym ? 1 : pg->nx[d];
+    g.is[d] = sym ? 0 : pg->ng;
+    g.n[d] = sym ? 1 : pg->nx[d] + 2 * pg->ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg->block_stride;
+  const int64_t total = (int64_t)g.nblocks * g.ncomp * g.nx[0] * g.nx[1] * g.nx[2];
+  if (total == 0) return PB2_OK;
+  const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
+  ProfScope prof(K_INTERIOR, as_stream(stream));
+  if (scatter)
+    interior_kernel<true><<<ctas, 256, 0, as_stream(stream)>>>(g, field, packed, total);
+  else
+    interior_kernel<false><<<ctas, 256, 0, as_stream(stream)>>>(g, field, packed, total);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_interior_scatter(const pb2_pack_geom *g, const double *packed, double *field,
+                         pb2_stream_t stream) {
+  return interior_copy(g, field, const_cast<double *>(packed), true, stream);
+}
+int pb2_interior_gather(const pb2_pack_geom *g, const double *field, double *packed,
+                        pb2_stream_t stream) {
+  return interior_copy(g, const_cast<double *>(field), packed, false, stream);
 }
 
 int pb2_flux_divergence(const pb2_pack_geom *pg, const double *const flux[3], double *dudt,

@@ -20,7 +20,8 @@ SYMBOLS = [
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_field_ptr",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
-    "pb2h_sim_exchange_elements", "pb2h_sim_history",
+    "pb2h_sim_exchange_elements", "pb2h_sim_history", "pb2h_sim_upload_interior",
+    "pb2h_sim_download_interior",
 ]
 
 BURGERS_DECK = """
@@ -100,6 +101,8 @@ def lib():
                                      C.POINTER(i64)]
     L.pb2h_sim_get_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
     L.pb2h_sim_set_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
+    L.pb2h_sim_upload_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64]
+    L.pb2h_sim_download_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64]
     L.pb2h_sim_exchange.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_phase.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_elements.restype = i64
@@ -271,6 +274,24 @@ class Simulation(_Base):
         a = np.ascontiguousarray(array, dtype=np.float64)
         check(lib().pb2h_sim_set_field(self.h, container.encode(), field.encode(), which,
                                        a.ctypes.data, a.size))
+
+    def interior_size(self, container, field):
+        shape = self.field_shape(container, field)
+        g = self.info()["nghost"]
+        nd = self.info()["ndim"]
+        cells = 1
+        for d, n in enumerate(reversed(shape[2:])):
+            cells *= (n - 2 * g) if d < nd else n
+        return shape[0] * shape[1] * cells
+
+    def upload_interior(self, container, field, host_ptr, nreal):
+        """host_ptr: address of nreal doubles [block][comp][nx3][nx2][nx1]; asynchronous"""
+        check(lib().pb2h_sim_upload_interior(self.h, container.encode(), field.encode(),
+                                             host_ptr, nreal))
+
+    def download_interior(self, container, field, host_ptr, nreal):
+        check(lib().pb2h_sim_download_interior(self.h, container.encode(), field.encode(),
+                                               host_ptr, nreal))
 
     def exchange(self, container="base", prolongate=True):
         check(lib().pb2h_sim_exchange(self.h, container.encode(), int(prolongate)))

@@ -58,6 +58,7 @@ struct pb2h_sim {
   ParthenonManager pman;
   std::unique_ptr<MultiStageDriver> driver;
   bool topology_only = false;
+  DeviceBuffer staging; // packed-interior staging for upload / download through host buffers
   // topology-only objects
   std::unique_ptr<ParameterInput> pin;
   std::unique_ptr<Mesh> mesh;
@@ -286,6 +287,43 @@ int pb2h_sim_set_field(pb2h_sim *sim, const char *container, const char *field, 
     PARTHENON_REQUIRE(n == nreal, "field size mismatch");
     PB2_CHECK(pb2_memcpy_h2d(p, host, sizeof(double) * n, sim->pm()->stream));
     PB2_CHECK(pb2_stream_sync(sim->pm()->stream));
+  });
+}
+
+// Upload / read back the INTERIOR cells of a field through host buffers laid out
+// [block][comp][nx3][nx2][nx1]: H2D into a device staging buffer, one scatter launch, one ghost
+// exchange (upload); one gather launch, D2H (download).  All asynchronous on the app stream.
+static DeviceBuffer &Staging(pb2h_sim *sim, size_t bytes) {
+  if (sim->staging.bytes() < bytes) sim->staging.Allocate(bytes, sim->pm()->stream);
+  return sim->staging;
+}
+
+int pb2h_sim_upload_interior(pb2h_sim *sim, const char *container, const char *field,
+                             const double *host, int64_t nreal) {
+  return Guard([&] {
+    Variable &v = FindVar(sim, container, field);
+    auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+    pb2_pack_geom g = md->Geometry(v);
+    const int64_t n = static_cast<int64_t>(g.nblocks) * g.ncomp * sim->pm()->GetNumberOfMeshBlockCells();
+    PARTHENON_REQUIRE(n == nreal, "interior size mismatch");
+    DeviceBuffer &st = Staging(sim, sizeof(double) * n);
+    PB2_CHECK(pb2_memcpy_h2d(st.get(), host, sizeof(double) * n, md->stream()));
+    PB2_CHECK(pb2_interior_scatter(&g, st.get<double>(), v.data(), md->stream()));
+    CommunicateBoundaries(md, true);
+  });
+}
+
+int pb2h_sim_download_interior(pb2h_sim *sim, const char *container, const char *field,
+                               double *host, int64_t nreal) {
+  return Guard([&] {
+    Variable &v = FindVar(sim, container, field);
+    auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+    pb2_pack_geom g = md->Geometry(v);
+    const int64_t n = static_cast<int64_t>(g.nblocks) * g.ncomp * sim->pm()->GetNumberOfMeshBlockCells();
+    PARTHENON_REQUIRE(n == nreal, "interior size mismatch");
+    DeviceBuffer &st = Staging(sim, sizeof(double) * n);
+    PB2_CHECK(pb2_interior_gather(&g, v.data(), st.get<double>(), md->stream()));
+    PB2_CHECK(pb2_memcpy_d2h(host, st.get(), sizeof(double) * n, md->stream()));
   });
 }
 

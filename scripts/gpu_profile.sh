@@ -3,7 +3,7 @@
 # usage: scripts/gpu_profile.sh <tag> [kernel-regex]
 set -u
 TAG=${1:-r01}
-KREGEX=${2:-flux_x_kernel}
+KREGEX=${2:-sweep_x_kernel|sweep_march_kernel|copy_kernel}
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $OUT/pytest_$TAG.log
@@ -16,7 +16,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   > $OUT/ncu_launches_$TAG.log 2>&1
 tail -2 $OUT/ncu_launches_$TAG.log
 # full capture of the top kernel (one launch after warm-up)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 6 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 8 -c 4 \
   -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline \
   > $OUT/ncu_full_$TAG.log 2>&1
 tail -2 $OUT/ncu_full_$TAG.log

@@ -147,3 +147,26 @@ def test_full_block_shape_conservation_and_idempotence():
     np.testing.assert_allclose(tot1, tot0, rtol=1e-11)
     sim.exchange("base", prolongate=False)
     assert np.array_equal(sim.get_field("base", "U"), U1)
+
+
+def test_interior_upload_download_roundtrip():
+    """host-buffer path used by bench.py's e2e leg: interior cells only cross PCIe, ghosts come
+    from one exchange; bit-exact against the oracle's exchange of the same interior"""
+    import torch
+    m = oracle.Mesh(3, (8, 8, 8), 4, (2, 2, 2))
+    sim = host.Simulation(overrides=burgers_overrides(8, 2, 4, 2, "weno5", "strict", True))
+    n = sim.interior_size("base", "U")
+    assert n == 8 * 5 * 8 ** 3
+    rng = np.random.default_rng(11)
+    interior = rng.standard_normal((8, 5, 8, 8, 8))
+    hbuf = torch.from_numpy(interior.copy()).pin_memory()
+    sim.upload_interior("base", "U", hbuf.data_ptr(), n)
+    sim.sync()
+    Uref = np.zeros((8, 5) + m.dims)
+    Uref[:, :, 4:-4, 4:-4, 4:-4] = interior
+    m.exchange(Uref)
+    assert np.array_equal(sim.get_field("base", "U"), Uref)
+    out = torch.zeros(n, dtype=torch.float64).pin_memory()
+    sim.download_interior("base", "U", out.data_ptr(), n)
+    sim.sync()
+    assert np.array_equal(out.numpy().reshape(interior.shape), interior)
