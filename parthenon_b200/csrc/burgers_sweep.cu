@@ -77,6 +77,10 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // recon.hpp:27-32
 __device__ __forceinline__ double mc(const double dm, const double dp) {
   const double dc = (dm * dp > 0.0) ? 0.5 * (dm + dp) : 0.0;
@@ -275,8 +279,14 @@ __global__ void __launch_bounds__(kThreads, 3) sweep_march_kernel(const Args a) 
       double *po = ob + off - sd;              // cell s-1, component 0
       // row s+3, component 0 (clamped: with nghost 2 the linear stencil never reads it)
       const double *pn = ub + (int64_t)min(ds + s + 3, g.n[DIR] - 1) * sd;
-      if (upd && more)
-        for (int n = 0; n < nc; ++n) prefetch_l1(po + sd + n * g.sc);
+      if (more) {
+        // next step's lines start their trip from HBM now: its new stencil row into L2 (L1 is
+        // mostly carved out as shared memory here), the `out` cell it completes into L1
+        const double *pf = ub + (int64_t)min(ds + s + 4, g.n[DIR] - 1) * sd;
+        for (int n = 0; n < nc; ++n) prefetch_l2(pf + n * g.sc);
+        if (upd)
+          for (int n = 0; n < nc; ++n) prefetch_l1(po + sd + n * g.sc);
+      }
 
       double ql[3], qr[3], old[3];
 #pragma unroll
