@@ -227,6 +227,11 @@ typedef struct pb2_burgers_args {
                          Must be initialised to +huge by the caller. */
   double beta;        /* integrator->beta[stage-1] */
   double dt;
+  /* pb2_burgers_stage (FAST) only: restrict the launch to these blocks of the batch (device
+   * array of num_block_ids indices), or NULL for all geom.nblocks blocks.  Lets a caller run
+   * the blocks that feed inter-GPU halos first and overlap their exchange with the rest. */
+  const int32_t *block_ids;
+  int32_t num_block_ids;
 } pb2_burgers_args;
 
 /* fluxes only: writes args->flux[0..ndim-1] from args->u */

@@ -57,7 +57,8 @@ class BurgersArgs(C.Structure):
     _fields_ = [("geom", PackGeom), ("recon", C.c_int32), ("math", C.c_int32),
                 ("u", C.c_void_p), ("base", C.c_void_p), ("out", C.c_void_p),
                 ("flux", C.c_void_p * 3), ("derived", C.c_void_p), ("dt_min", C.c_void_p),
-                ("beta", C.c_double), ("dt", C.c_double)]
+                ("beta", C.c_double), ("dt", C.c_double),
+                ("block_ids", C.c_void_p), ("num_block_ids", C.c_int32)]
 
 
 _lib = None

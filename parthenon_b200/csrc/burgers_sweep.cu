@@ -55,6 +55,7 @@ struct Args {
   double *derived;           // LAST sweep only, or null
   unsigned long long *dtmin; // LAST sweep only, or null
   const double *dx;          // [nblocks][3]
+  const int *block_ids;      // launch block -> block of the batch, or null (identity)
   double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
 };
 
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(kThreads, 3) sweep_march_kernel(const Args a) 
   const int ncol_other = (DIR == 1) ? g.nx[2] : g.nx[1];
   const int ncol = ncol_other * g.nx[0];
   const int ctas_per_block = (ncol + kThreads - 1) / kThreads;
-  const int b = blockIdx.x / ctas_per_block;
+  const int bi = blockIdx.x / ctas_per_block;
+  const int b = a.block_ids ? a.block_ids[bi] : bi;
   const int col = (blockIdx.x % ctas_per_block) * kThreads + threadIdx.x;
   const int nc = g.ncomp;
   extern __shared__ double smem[];
@@ -368,10 +370,11 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_x_kernel(const
   const int warp_global = blockIdx.x * (kThreads / 32) + wid;
   const int nrows = g.nx[1] * g.nx[2];
   const int warps_per_block = (nrows + kRowsPerWarp - 1) / kRowsPerWarp;
-  const int b = warp_global / warps_per_block;
+  const int bi = warp_global / warps_per_block;
   double rate = 0.0;
   __shared__ double sL[kThreads / 32][kMaxComp], sF[kThreads / 32][kMaxComp];
-  if (b < g.nblocks) { // whole warp together
+  if (bi < g.nblocks) { // whole warp together
+    const int b = a.block_ids ? a.block_ids[bi] : bi;
     const int row0 = (warp_global % warps_per_block) * kRowsPerWarp;
     const int rows = min(kRowsPerWarp, nrows - row0);
     const int ncell = g.nx[0] + 2;
@@ -546,6 +549,9 @@ int launch(const pb2_burgers_args *args, cudaStream_t st) {
   a.base = args->base;
   a.out = args->out;
   a.dx = pg.dx;
+  a.block_ids = args->block_ids;
+  if (args->block_ids) g.nblocks = args->num_block_ids;
+  if (g.nblocks == 0) return PB2_OK;
   a.beta = args->beta;
   a.w2 = 1.0 - args->beta;
   a.bdt = args->beta * args->dt;

@@ -156,7 +156,25 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
     ResetDt(mc1);
     a.dt_min = DtScratch(mc1);
   }
-  PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+  // Blocks whose results travel to another GPU go first; their halo is then packed and
+  // shipped on the communication stream while the interior blocks are advanced
+  // (the local / nonlocal overlap of burgers_driver.cpp:106-119, without host polling).
+  BvarsCache &bc = GetBvarsCache(mc1);
+  Mesh *pm = mc0->GetMeshPointer();
+  const bool split = a.math == PB2_MATH_FAST && !pm->multilevel && bc.n_boundary > 0 &&
+                     bc.n_interior > 0 && bc.plan.send_elements > 0;
+  if (split) {
+    a.block_ids = bc.ids_boundary.get<int32_t>();
+    a.num_block_ids = bc.n_boundary;
+    PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+    PB2_CHECK(pb2_event_record(bc.early_ready, mc0->stream()));
+    bc.early_valid = true;
+    a.block_ids = bc.ids_interior.get<int32_t>();
+    a.num_block_ids = bc.n_interior;
+    PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+  } else {
+    PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+  }
   return TaskStatus::complete;
 }
 

@@ -79,6 +79,14 @@ struct BvarsCache {
   DeviceBuffer send_slab, recv_slab;
   pb2_event_t packed = nullptr, received = nullptr, sent = nullptr;
   bool nonlocal_in_flight = false;
+  // Overlap of inter-GPU halos with interior work (uniform meshes): blocks with a nonlocal
+  // neighbour ("boundary") are advanced first and signal `early_ready`; SendBoundBufs<nonlocal>
+  // then packs and ships on the communication stream while the remaining ("interior") blocks
+  // are still being advanced on the compute stream.
+  DeviceBuffer ids_boundary, ids_interior;
+  int n_boundary = 0, n_interior = 0;
+  pb2_event_t early_ready = nullptr, unpacked = nullptr;
+  bool early_valid = false, unpacked_valid = false;
   // local channels: SendBoundBufs<local> publishes a generation; receivers consume it
   uint64_t send_generation = 0;
   std::map<int, uint64_t> consumed_generation; // by sender partition
@@ -87,6 +95,8 @@ struct BvarsCache {
 };
 
 void BuildBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md);
+// the (re)built exchange cache of a batch
+BvarsCache &GetBvarsCache(MeshData<Real> *md);
 
 template <BoundaryType bound_type>
 TaskStatus StartReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md);

@@ -378,7 +378,30 @@ void Rebuild(MeshData<Real> *md) {
                                           static_cast<int64_t>(pro[cls][o].size())));
     }
   }
+  // boundary / interior split of the batch for comm-compute overlap
+  {
+    std::vector<int32_t> bnd, inr;
+    for (auto &pmb : md->GetBlockList()) {
+      const int my_vr = pm->VirtualRankOf(pmb->gid);
+      bool nonlocal = false;
+      for (auto &nb : pmb->neighbors)
+        nonlocal = nonlocal || nb.rank != pm->my_rank || pm->VirtualRankOf(nb.gid) != my_vr;
+      (nonlocal ? bnd : inr).push_back(pmb->pack_index);
+    }
+    c.n_boundary = static_cast<int>(bnd.size());
+    c.n_interior = static_cast<int>(inr.size());
+    auto upload = [&](DeviceBuffer &buf, const std::vector<int32_t> &v) {
+      if (v.empty()) return;
+      buf.Allocate(sizeof(int32_t) * v.size(), md->stream());
+      PB2_CHECK(pb2_memcpy_h2d(buf.get(), v.data(), sizeof(int32_t) * v.size(), md->stream()));
+      PB2_CHECK(pb2_stream_sync(md->stream()));
+    };
+    upload(c.ids_boundary, bnd);
+    upload(c.ids_interior, inr);
+  }
   if (!c.packed) {
+    PB2_CHECK(pb2_event_create(&c.early_ready));
+    PB2_CHECK(pb2_event_create(&c.unpacked));
     PB2_CHECK(pb2_event_create(&c.packed));
     PB2_CHECK(pb2_event_create(&c.received));
     PB2_CHECK(pb2_event_create(&c.sent));
@@ -402,6 +425,11 @@ constexpr bool DoesNonlocal(BoundaryType bt) {
 
 void BuildBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md) { Cache(md); }
 
+BvarsCache &GetBvarsCache(MeshData<Real> *md) {
+  if (md->bvars().built_generation != md->alloc_generation) Rebuild(md);
+  return md->bvars();
+}
+
 template <BoundaryType bt>
 TaskStatus StartReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
   // receives are posted together with the sends inside one NCCL group; nothing to pre-post
@@ -421,25 +449,37 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
   }
   if (DoesNonlocal(bt) && c.plan.send_elements + c.plan.recv_elements > 0) {
     if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_send[1], st));
-    // the previous exchange must have left the slabs (send done, unpack done: same stream)
-    if (c.nonlocal_in_flight) PB2_CHECK(pb2_stream_wait_event(st, c.sent));
-    PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), nullptr, st));
-    if (pm->nranks > 1) {
-      PARTHENON_REQUIRE(pm->comm != nullptr, "multi-rank mesh without a communicator");
-      pb2_stream_t cs = pm->comm_stream;
+    pb2_stream_t cs = pm->comm_stream;
+    // Where the pack runs: normally on the compute stream, after everything enqueued so far.
+    // If the producer signalled `early_ready` (all blocks that feed nonlocal channels are
+    // final), pack on the communication stream right behind that event so that packing and
+    // the transfer overlap whatever the compute stream still has to do.
+    pb2_stream_t ps = st;
+    if (c.early_valid && !pm->multilevel) {
+      ps = cs;
+      PB2_CHECK(pb2_stream_wait_event(cs, c.early_ready));
+    }
+    c.early_valid = false;
+    // the previous exchange must have left the slabs: its sends (same stream order on cs, or
+    // the `sent` event) and its unpack (`unpacked`, recorded on the compute stream)
+    if (c.nonlocal_in_flight && ps == st) PB2_CHECK(pb2_stream_wait_event(st, c.sent));
+    PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), nullptr, ps));
+    if (ps == st) {
       PB2_CHECK(pb2_event_record(c.packed, st));
       PB2_CHECK(pb2_stream_wait_event(cs, c.packed));
+    }
+    if (c.unpacked_valid) PB2_CHECK(pb2_stream_wait_event(cs, c.unpacked));
+    if (pm->nranks > 1) {
+      PARTHENON_REQUIRE(pm->comm != nullptr, "multi-rank mesh without a communicator");
       PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_slab.get<Real>(), c.plan.send_off.data(),
                                   c.recv_slab.get<Real>(), c.plan.recv_off.data(), cs));
-      PB2_CHECK(pb2_event_record(c.received, cs));
-      PB2_CHECK(pb2_event_record(c.sent, cs));
     } else {
       // virtual ranks on one device: the "wire" is a device-to-device copy of the slab
       PB2_CHECK(pb2_memcpy_d2d(c.recv_slab.get(), c.send_slab.get(),
-                               sizeof(Real) * static_cast<size_t>(c.plan.send_elements), st));
-      PB2_CHECK(pb2_event_record(c.received, st));
-      PB2_CHECK(pb2_event_record(c.sent, st));
+                               sizeof(Real) * static_cast<size_t>(c.plan.send_elements), cs));
     }
+    PB2_CHECK(pb2_event_record(c.received, cs));
+    PB2_CHECK(pb2_event_record(c.sent, cs));
     c.nonlocal_in_flight = true;
   }
   return TaskStatus::complete;
@@ -484,6 +524,8 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
   if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
     PB2_CHECK(pb2_stream_wait_event(st, c.received));
     PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(), nullptr, st));
+    PB2_CHECK(pb2_event_record(c.unpacked, st));
+    c.unpacked_valid = true;
     c.elements_nonlocal = c.plan.recv_elements;
     if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_set[1], st));
   }
