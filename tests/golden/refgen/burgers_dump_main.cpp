@@ -11,7 +11,8 @@
 //
 // Dump layout (little endian):  int32 magic=0x50423230, nblocks, ncomp, nk, nj, ni, cycle
 //   float64 time, dt
-//   then per block: int32 gid, level, lx1, lx2, lx3 ; float64 data[ncomp][nk][nj][ni]
+//   then per block: int32 gid, level, lx1, lx2, lx3 (tree-relative, forest.cpp:104-141);
+//   float64 xmin[3], xmax[3] ; float64 data[ncomp][nk][nj][ni]
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -43,6 +44,10 @@ void DumpU(parthenon::Mesh *pmesh, int cycle, double time, double dt) {
     int bh[5] = {pmb->gid, pmb->loc.level(), static_cast<int>(pmb->loc.lx1()),
                  static_cast<int>(pmb->loc.lx2()), static_cast<int>(pmb->loc.lx3())};
     std::fwrite(bh, sizeof(int), 5, fp);
+    double bb[6] = {pmb->block_size.xmin(parthenon::X1DIR), pmb->block_size.xmin(parthenon::X2DIR),
+                    pmb->block_size.xmin(parthenon::X3DIR), pmb->block_size.xmax(parthenon::X1DIR),
+                    pmb->block_size.xmax(parthenon::X2DIR), pmb->block_size.xmax(parthenon::X3DIR)};
+    std::fwrite(bb, sizeof(double), 6, fp);
     for (int n = 0; n < hdr[2]; ++n)
       for (int k = 0; k < hdr[3]; ++k)
         for (int j = 0; j < hdr[4]; ++j)

@@ -11,7 +11,7 @@ REF=${REF:-/root/reference}
 REF_BUILD=${REF_BUILD:-/tmp/survey_ref_build_own}
 WORK=${WORK:-/tmp/pb2_refgen}
 HERE=$(cd "$(dirname "$0")" && pwd)
-OUT=$(cd "$HERE/.." && pwd)
+OUT=${OUT:-$(cd "$HERE/.." && pwd)}
 mkdir -p "$WORK"
 
 INC="-I$REF/src -I$REF_BUILD/src/generated -I$REF_BUILD/Kokkos -I$REF_BUILD/Kokkos/core/src \
@@ -49,6 +49,37 @@ run_burgers () { # name nx nb nscal recon nlim extra...
 # small uniform cases: full fields (ghosts included) after cycles 0..nlim
 run_burgers burgers_u16_b8_s1_weno5   16  8 1 weno5  3
 run_burgers burgers_u16_b8_s1_linear  16  8 1 linear 3 parthenon/mesh/nghost=2
+# static-refinement (multilevel) cases: restrict / prolongate ghost fill (cycle 0) and, after
+# the first cycles, flux correction.  The deck is the reference deck plus
+# <parthenon/static_refinementN> blocks written into $WORK (never into $REF).
+run_burgers_static () { # name nx nb nscal recon nlim numlevel "regions" extra...
+  local name=$1 nx=$2 nb=$3 nscal=$4 recon=$5 nlim=$6 numlevel=$7 regions=$8; shift 8
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  cp "$REF/benchmarks/burgers/burgers.pin" deck.pin
+  local n=0
+  for r in $regions; do # level:x1min:x1max:x2min:x2max:x3min:x3max
+    IFS=: read -r lev a b c e f g <<< "$r"
+    printf '\n<parthenon/static_refinement%d>\nlevel = %s\nx1min = %s\nx1max = %s\nx2min = %s\nx2max = %s\nx3min = %s\nx3max = %s\n' \
+      $n $lev $a $b $c $e $f $g >> deck.pin
+    n=$((n+1))
+  done
+  PB2_DUMP_PREFIX="$d/U" "$WORK/burgers_dump" -i deck.pin \
+    parthenon/mesh/nx1=$nx parthenon/mesh/nx2=$nx parthenon/mesh/nx3=$nx \
+    parthenon/meshblock/nx1=$nb parthenon/meshblock/nx2=$nb parthenon/meshblock/nx3=$nb \
+    parthenon/mesh/refinement=static parthenon/mesh/numlevel=$numlevel \
+    parthenon/time/nlim=$nlim parthenon/time/tlim=1e9 parthenon/output0/dt=-1 \
+    parthenon/output1/dt=1e-9 burgers/num_scalars=$nscal burgers/recon=$recon "$@" \
+    > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
+  cp "$d/burgers.out1.hst" "$OUT/$name.hst"
+}
+if [ -z "${SKIP_STATIC:-}" ]; then
+run_burgers_static burgers_s16_b8_l2_weno5 16 8 1 weno5 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
+# 2-D, three levels (x3 extents of the regions are ignored in 2-D)
+run_burgers_static burgers_s64_b8_l3_2d_weno5 64 8 1 weno5 2 3 \
+  "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0" \
+  parthenon/mesh/nx3=1 parthenon/meshblock/nx3=1
+fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1
 run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4

@@ -2,7 +2,8 @@
 
 Test infrastructure only.  Layout of the dumps is documented in burgers_dump_main.cpp.
 The .npz holds, per dumped cycle c:  U_c [nblocks, ncomp, nk, nj, ni] float64,
-plus block metadata (gid, level, lx1, lx2, lx3), times and dts.
+plus block metadata (gid, level, lx1, lx2, lx3 — tree-relative), block bounds
+(xmin[3], xmax[3]), times and dts.
 """
 import glob
 import os
@@ -18,12 +19,14 @@ def read_dump(path):
         nb, nc, nk, nj, ni, cycle = (int(x) for x in hdr[1:])
         time, dt = np.frombuffer(f.read(16), dtype="<f8")
         meta = np.zeros((nb, 5), dtype=np.int32)
+        bounds = np.zeros((nb, 6), dtype=np.float64)
         data = np.zeros((nb, nc, nk, nj, ni), dtype=np.float64)
         n = nc * nk * nj * ni
         for b in range(nb):
             meta[b] = np.frombuffer(f.read(20), dtype="<i4")
+            bounds[b] = np.frombuffer(f.read(48), dtype="<f8")
             data[b] = np.frombuffer(f.read(8 * n), dtype="<f8").reshape(nc, nk, nj, ni)
-    return cycle, time, dt, meta, data
+    return cycle, time, dt, meta, bounds, data
 
 
 def main(src_dir, out):
@@ -32,9 +35,10 @@ def main(src_dir, out):
     arrays = {}
     times, dts, cycles = [], [], []
     for p in files:
-        cycle, time, dt, meta, data = read_dump(p)
+        cycle, time, dt, meta, bounds, data = read_dump(p)
         arrays[f"U_{cycle}"] = data
         arrays["meta"] = meta
+        arrays["bounds"] = bounds
         cycles.append(cycle)
         times.append(time)
         dts.append(dt)

@@ -141,3 +141,19 @@ def refined_leaves(nrb, refine):
                 else:
                     leaves.append((rl, i, j, k))
     return np.array(leaves, dtype=np.int32)
+
+
+def leaves_from_bounds(bounds, nx_mesh, nx_block, xmin=-0.5, xmax=0.5):
+    """(level, lx1, lx2, lx3) in single-tree (global) logical coordinates from the block
+    bounds a reference dump records (tests/golden/refgen/burgers_dump_main.cpp).  The
+    reference's own levels are tree-relative (forest.cpp:104-141), so they are rebuilt
+    from the block widths instead."""
+    nrb = [max(nx_mesh[d] // nx_block[d], 1) for d in range(3)]
+    out = []
+    for b in bounds:
+        level = max(int(round(np.log2((xmax - xmin) / (b[3 + d] - b[d])))) if nrb[d] > 1 else 0
+                    for d in range(3))
+        lx = [int(round((b[d] - xmin) / (xmax - xmin) * (1 << level))) if nrb[d] > 1 else 0
+              for d in range(3)]
+        out.append((level, *lx))
+    return np.array(out, dtype=np.int32), nrb
