@@ -14,15 +14,16 @@
 // (algebraically update.hpp:43-58 with A_d / V = 1 / dx_d on a uniform Cartesian block).
 // The kernels are bound by the FP64 pipe (33 WENO5-Z reconstructions per zone and stage),
 // so the arithmetic is reorganised to issue fewer FP64 instructions than the reference's
-// expression tree: the 8 divisions of WENO5-Z collapse into 4 Newton-refined reciprocals
-// (shared denominators), the HLL denominators of a face are inverted once for all 11
-// components, and stencil values are software-prefetched one component ahead.  Results stay
+// expression tree (weno_fast.cuh: difference form, 4 shared reciprocals instead of 8
+// divisions), the HLL denominators of a face are inverted once for all 11 components, and
+// stencil values are software-prefetched one component ahead.  Results stay
 // within 1e-12 relative of the reference (tests/test_burgers_sim_gpu.py); the bit-exact
 // arithmetic lives in burgers_strict.cu.  Valid for |q| < ~1e40 (products of three
 // smoothness indicators must not overflow).
 #include <cfloat>
 
 #include "common.cuh"
+#include "weno_fast.cuh"
 
 #ifndef PB2_SWEEP_MINB
 #define PB2_SWEEP_MINB 4
@@ -59,19 +60,11 @@ struct Args {
   double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
 };
 
-__device__ __forceinline__ double min_std(double a, double b) { return (b < a) ? b : a; }
-__device__ __forceinline__ double max_std(double a, double b) { return (a < b) ? b : a; }
-
-// 1/a to ~1 ulp: hardware seed (2^-23) + two Newton steps, no special-case branches
-__device__ __forceinline__ double rcp_nr(double a) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  double e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  return x;
-}
+using fastmath::Linear;
+using fastmath::max_std;
+using fastmath::min_std;
+using fastmath::rcp_fast;
+using fastmath::WENO5Z;
 
 // pull the line holding p into L1 ahead of the pass / march step that will read it
 __device__ __forceinline__ void prefetch_l1(const void *p) {
@@ -80,79 +73,6 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// recon.hpp:27-32
-__device__ __forceinline__ double mc(const double dm, const double dp) {
-  const double dc = (dm * dp > 0.0) ? 0.5 * (dm + dp) : 0.0;
-  return copysign(min_std(fabs(dc), 2.0 * min_std(fabs(dm), fabs(dp))), dc);
-}
-
-__device__ __forceinline__ void Linear(const double qm, const double q0, const double qp,
-                                       double &ql, double &qr) {
-  const double dq = 0.5 * mc(q0 - qm, qp - q0);
-  ql = q0 + dq;
-  qr = q0 - dq;
-}
-
-// WENO5-Z of recon.hpp:42-99 with shared reciprocals
-__device__ __forceinline__ void WENO5Z(const double q0, const double q1, const double q2,
-                                       const double q3, const double q4, double &ql,
-                                       double &qr) {
-  constexpr double a00 = 1.0 / 3.0, a01 = -7.0 / 6.0, a02 = 11.0 / 6.0;
-  constexpr double a10 = -1.0 / 6.0, a11 = 5.0 / 6.0, a12 = 1.0 / 3.0;
-  constexpr double a20 = 1.0 / 3.0, a21 = 5.0 / 6.0, a22 = -1.0 / 6.0;
-  constexpr double g0 = 0.1, g1 = 0.6, g2 = 0.3;
-  constexpr double eps = 10.0 * DBL_EPSILON;
-  constexpr double c13 = 13.0 / 3.0;
-
-  double a = q0 - 2.0 * q1 + q2;
-  double b = q0 - 4.0 * q1 + 3.0 * q2;
-  const double b0 = fma(c13 * a, a, fma(b, b, eps));
-  a = q1 - 2.0 * q2 + q3;
-  b = q3 - q1;
-  const double b1 = fma(c13 * a, a, fma(b, b, eps));
-  a = q2 - 2.0 * q3 + q4;
-  b = q4 - 4.0 * q3 + 3.0 * q2;
-  const double b2 = fma(c13 * a, a, fma(b, b, eps));
-  const double tau5 = fabs(b2 - b0);
-
-  // r_k = (b_k + tau5) / b_k = 1 + tau5 * (prod of the other two) / (b0 b1 b2)
-  const double b01 = b0 * b1, b12 = b1 * b2, b02 = b0 * b2;
-  const double t = tau5 * rcp_nr(b01 * b2);
-  const double r0 = fma(t, b12, 1.0), r1 = fma(t, b02, 1.0), r2 = fma(t, b01, 1.0);
-
-  const double p0 = fma(a00, q0, fma(a01, q1, a02 * q2));
-  const double p1 = fma(a10, q1, fma(a11, q2, a12 * q3));
-  const double p2 = fma(a20, q2, fma(a21, q3, a22 * q4));
-  const double m0 = fma(a00, q4, fma(a01, q3, a02 * q2));
-  const double m1 = fma(a10, q3, fma(a11, q2, a12 * q1));
-  const double m2 = fma(a20, q2, fma(a21, q1, a22 * q0));
-
-  // left state: weights w_k = g_k r_k + eps; ql = sum(w p)/S; alpha = 3 w0w1w2/(S D) + eps
-  double w0 = fma(g0, r0, eps), w1 = fma(g1, r1, eps), w2 = fma(g2, r2, eps);
-  double w12 = w1 * w2;
-  double S = w0 + w1 + w2;
-  double D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
-  double iSD = rcp_nr(S * D);
-  const double alpha_l = fma(3.0 * w0 * w12, iSD, eps);
-  const double qlw = fma(w0, p0, fma(w1, p1, w2 * p2)) * (D * iSD);
-
-  w0 = fma(g0, r2, eps);
-  w1 = fma(g1, r1, eps);
-  w2 = fma(g2, r0, eps);
-  w12 = w1 * w2;
-  S = w0 + w1 + w2;
-  D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
-  iSD = rcp_nr(S * D);
-  const double alpha_r = fma(3.0 * w0 * w12, iSD, eps);
-  const double qrw = fma(w0, m0, fma(w1, m1, w2 * m2)) * (D * iSD);
-
-  const double dq = 0.5 * mc(q2 - q1, q3 - q2);
-  const double alpha_lin = 2.0 * alpha_l * alpha_r * rcp_nr(alpha_l + alpha_r);
-  const double om = 1.0 - alpha_lin;
-  ql = fma(alpha_lin, qlw, om * (q2 + dq));
-  qr = fma(alpha_lin, qrw, om * (q2 - dq));
 }
 
 // per-face HLL coefficients shared by all components (burgers_package.hpp:31-43 and
@@ -164,7 +84,7 @@ __device__ __forceinline__ FaceCoef face_coef(const double upl, const double upr
   const double sl = min_std(min_std(upl, upr), 0.0);
   const double sr = max_std(max_std(upl, upr), 0.0);
   const double slsr = sl * sr;
-  const double inv = rcp_nr(sr - sl + (slsr == 0.0 ? 1.0 : 0.0));
+  const double inv = rcp_fast(sr - sl + (slsr == 0.0 ? 1.0 : 0.0));
   FaceCoef f;
   f.A = sr * upl * inv;
   f.B = sl * upr * inv;

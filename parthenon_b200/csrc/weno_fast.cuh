@@ -1,0 +1,141 @@
+// weno_fast.cuh — the FAST-math reconstruction of the burgers stage (device; also compiles
+// as plain C++ so tests/test_fast_math_cpu.py can check it against the oracle on the CPU).
+//
+// WENO5-Z + MC-limited linear blend of benchmarks/burgers/recon.hpp:27-99, reorganised to
+// issue ~104 FP64 instructions instead of the ~165 of the reference's expression tree:
+//   * everything is written in the four first differences d_k = q_k - q_{k-1}: the
+//     smoothness indicators need one op per term instead of two, the candidate values
+//     become offsets from q2 (two ops each, and q2 is added once at the very end inside
+//     the final FMA chain), and the limiter reuses d2, d3 and d2 + d3;
+//   * the 8 divisions collapse into 4 reciprocals with shared denominators
+//     (1/(b0 b1 b2), 1/(S D) per side, 1/(alpha_l + alpha_r)), each a hardware seed
+//     (MUFU.RCP64H, 20+ bits) plus ONE cubically convergent step (3 FMAs, error e^3 < 2^-60);
+//   * the centre weight g1 r1 + eps is the same on both sides;
+//   * the limiter's sign test (dm dp > 0) is an integer test on the sign bits.
+// Results stay within a few ulp of the reference expression (<= 1e-12 relative is the
+// contract).  Valid while products of three smoothness indicators do not overflow (|q| < ~1e40).
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define PB2_HD __device__ __forceinline__
+#else
+#define PB2_HD inline
+#endif
+
+namespace pb2 {
+namespace fastmath {
+
+PB2_HD double min_std(double a, double b) { return (b < a) ? b : a; }
+PB2_HD double max_std(double a, double b) { return (a < b) ? b : a; }
+
+// 1/a: hardware seed + one third-order step  x = x0 (1 + e + e^2),  e = 1 - a x0
+PB2_HD double rcp_fast(double a) {
+#if defined(__CUDA_ARCH__)
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  const double e = fma(-a, x, 1.0);
+  const double t = fma(e, e, e);
+  return fma(x, t, x);
+#else
+  // host stand-in for the hardware seed: the exact quotient cut to 20 mantissa bits
+  double x = 1.0 / a;
+  uint64_t bits;
+  std::memcpy(&bits, &x, 8);
+  bits &= ~((uint64_t(1) << 32) - 1);
+  std::memcpy(&x, &bits, 8);
+  const double e = std::fma(-a, x, 1.0);
+  const double t = std::fma(e, e, e);
+  return std::fma(x, t, x);
+#endif
+}
+
+PB2_HD bool same_sign(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return (__double2hiint(a) ^ __double2hiint(b)) >= 0;
+#else
+  int64_t x, y;
+  std::memcpy(&x, &a, 8);
+  std::memcpy(&y, &b, 8);
+  return (x ^ y) >= 0;
+#endif
+}
+
+// 0.5 * mc(dm, dp) of recon.hpp:27-32 given s = dm + dp:
+//   copysign(min(|s|/4, min(|dm|, |dp|)), s) when dm and dp have the same sign, else 0
+// (exact: only powers of two are moved through the min; a zero difference gives 0 either way)
+PB2_HD double half_mc(double dm, double dp, double s) {
+  const double m = min_std(min_std(fabs(dm), fabs(dp)), 0.25 * fabs(s));
+  return same_sign(dm, dp) ? copysign(m, s) : 0.0;
+}
+
+PB2_HD void Linear(const double qm, const double q0, const double qp, double &ql, double &qr) {
+  const double dm = q0 - qm, dp = qp - q0;
+  const double dq = half_mc(dm, dp, dm + dp);
+  ql = q0 + dq;
+  qr = q0 - dq;
+}
+
+PB2_HD void WENO5Z(const double q0, const double q1, const double q2, const double q3,
+                   const double q4, double &ql, double &qr) {
+  constexpr double g0 = 0.1, g1 = 0.6, g2 = 0.3;
+  constexpr double eps = 10.0 * DBL_EPSILON; // robust.hpp:39-42
+  constexpr double c13 = 13.0 / 3.0;
+  constexpr double k13 = 1.0 / 3.0, k16 = 1.0 / 6.0, k56 = 5.0 / 6.0, k23 = 2.0 / 3.0;
+
+  const double d1 = q1 - q0, d2 = q2 - q1, d3 = q3 - q2, d4 = q4 - q3;
+  const double s23 = d2 + d3; // q3 - q1
+
+  // smoothness indicators (recon.hpp:52-60): second difference a, one-sided slope b
+  double a = d2 - d1, b = fma(3.0, d2, -d1);
+  const double b0 = fma(c13 * a, a, fma(b, b, eps));
+  a = d3 - d2;
+  const double b1 = fma(c13 * a, a, fma(s23, s23, eps));
+  a = d4 - d3;
+  b = fma(-3.0, d3, d4);
+  const double b2 = fma(c13 * a, a, fma(b, b, eps));
+  const double tau5 = fabs(b2 - b0);
+
+  // r_k = (b_k + tau5) / b_k = 1 + tau5 * (product of the other two) / (b0 b1 b2)
+  const double b01 = b0 * b1, b12 = b1 * b2, b02 = b0 * b2;
+  const double t = tau5 * rcp_fast(b01 * b2);
+  const double r0 = fma(t, b12, 1.0), r1 = fma(t, b02, 1.0), r2 = fma(t, b01, 1.0);
+
+  // candidate values minus q2 (rows of w5alpha applied to the differences)
+  const double e0 = fma(k56, d2, -k13 * d1), e1 = fma(k16, d2, k13 * d3),
+               e2 = fma(k23, d3, -k16 * d4);
+  const double f0 = fma(-k56, d3, k13 * d4), f1 = fma(-k16, d3, -k13 * d2),
+               f2 = fma(-k23, d2, k16 * d1);
+
+  const double w1 = fma(g1, r1, eps); // centre weight, both sides
+  // left: weights w_k = g_k r_k + eps;  (ql - q2) = sum(w e)/S;  alpha = 3 w0 w1 w2/(S D) + eps
+  double w0 = fma(g0, r0, eps), w2 = fma(g2, r2, eps);
+  double w12 = w1 * w2;
+  double S = w0 + w1 + w2;
+  double D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
+  double iSD = rcp_fast(S * D);
+  const double alpha_l2 = fma(6.0 * w0 * w12, iSD, 2.0 * eps); // 2 alpha_l
+  const double dl = fma(w0, e0, fma(w1, e1, w2 * e2)) * (D * iSD);
+
+  w0 = fma(g0, r2, eps);
+  w2 = fma(g2, r0, eps);
+  w12 = w1 * w2;
+  S = w0 + w1 + w2;
+  D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
+  iSD = rcp_fast(S * D);
+  const double alpha_r = fma(3.0 * w0 * w12, iSD, eps);
+  const double dr = fma(w0, f0, fma(w1, f1, w2 * f2)) * (D * iSD);
+
+  const double dq = half_mc(d2, d3, s23);
+  // alpha_lin = 2 al ar / (al + ar)
+  const double alpha_lin = alpha_l2 * alpha_r * rcp_fast(fma(0.5, alpha_l2, alpha_r));
+  const double om = 1.0 - alpha_lin;
+  ql = fma(alpha_lin, dl, fma(om, dq, q2));
+  qr = fma(alpha_lin, dr, fma(-om, dq, q2));
+}
+
+} // namespace fastmath
+} // namespace pb2
