@@ -198,6 +198,16 @@ int pb2_interior_scatter(const pb2_pack_geom *g, const double *packed, double *f
                          pb2_stream_t stream);
 int pb2_interior_gather(const pb2_pack_geom *g, const double *field, double *packed,
                         pb2_stream_t stream);
+/* Uniform-mesh fast path of SetBounds<local> (boundary_communication.cpp:251-348 with the
+ * same-level index boxes of bnd_info.cpp:205-212): every ghost cell of every block of a dense
+ * field is pulled straight from the interior cell of the same-level neighbour that owns it.
+ * No region table: the work decomposition is arithmetic over (block, component, ghost-shell
+ * vector), the only indirection is `nbr` (device, [nblocks][27] block indices of the batch by
+ * receiver-side offset index (ox1+1) + 3 (ox2+1) + 9 (ox3+1); < 0: no same-device neighbour in
+ * that direction, those ghosts are left to pb2_unpack).  Periodic wrap onto the block itself
+ * is allowed. */
+int pb2_halo_copy_uniform(const pb2_pack_geom *g, double *field, const int32_t *nbr,
+                          pb2_stream_t stream);
 /* dudt = -div(F) (FluxDivergence + FluxDivHelper), interior cells */
 int pb2_flux_divergence(const pb2_pack_geom *g, const double *const flux[3], double *dudt,
                         pb2_stream_t stream);

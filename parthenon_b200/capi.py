@@ -76,6 +76,7 @@ SYMBOLS = [
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
     "pb2_restrict", "pb2_prolongate", "pb2_weighted_sum", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
+    "pb2_halo_copy_uniform",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
@@ -110,6 +111,7 @@ def lib():
     L.pb2_pack.argtypes = [vp, vp, vp, vp]
     L.pb2_unpack.argtypes = [vp, vp, vp, vp]
     L.pb2_copy.argtypes = [vp, vp, vp]
+    L.pb2_halo_copy_uniform.argtypes = [vp, vp, vp, vp]
     L.pb2_restrict.argtypes = [vp, vp]
     L.pb2_prolongate.argtypes = [vp, C.c_int, vp]
     L.pb2_weighted_sum.argtypes = [vp, vp, C.c_double, C.c_double, vp, i64, vp]

@@ -186,6 +186,93 @@ __global__ void __launch_bounds__(kThreads)
     copy_chunk<1>(r, ch.first_vec, flags);
 }
 
+
+// ---- uniform meshes: descriptor-free ghost fill ---------------------------------------------
+// One CTA per (block, component, part of the ghost shell).  The shell is enumerated as
+//   [low k planes][high k planes][per interior plane: low j rows, high j rows, x pieces]
+// in units of V doubles; a thread turns its flat index into (k, j, i) with multiply-shift
+// divisions, picks the owning neighbour from the 27-entry table of its block (shared memory)
+// and copies V doubles.  All kHaloUnroll loads of a thread are issued before its stores.
+constexpr int kHaloUnroll = 8;
+
+struct HaloGeom {
+  int32_t nblocks, ncomp, parts;
+  int32_t nx[3], ng[3], n[3]; // interior, ghost width (0 in symmetry directions), total
+  int64_t sj, sk, sc, sb;
+  uint32_t nivec;     // vectors per full row
+  uint32_t xg;        // x-ghost vectors per row (both sides)
+  uint32_t xg_half;   // ... per side
+  uint32_t plane_full; // vectors in a full k plane
+  uint32_t plane_in;   // ghost vectors in an interior k plane
+  uint32_t rows_full;  // vectors in the 2 ng_j full rows of an interior plane
+  uint32_t nA;         // vectors in the low (== high) k-ghost planes
+  uint32_t total;      // ghost vectors per (block, component)
+  uint32_t per_part;
+  FastDiv d_nivec, d_plane_full, d_plane_in, d_xg;
+};
+
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+    halo_uniform_kernel(const HaloGeom g, double *__restrict__ field,
+                        const int32_t *__restrict__ nbr) {
+  using T = typename Vec<V>::type;
+  __shared__ int32_t s_nbr[27];
+  const uint32_t part = blockIdx.x % g.parts;
+  const uint32_t bc = blockIdx.x / g.parts;
+  const uint32_t c = bc % g.ncomp, b = bc / g.ncomp;
+  if (threadIdx.x < 27) s_nbr[threadIdx.x] = nbr[b * 27 + threadIdx.x];
+  __syncthreads();
+  const int64_t dbase = (int64_t)b * g.sb + (int64_t)c * g.sc;
+  const uint32_t end = min(g.total, (part + 1) * g.per_part);
+  for (uint32_t v0 = part * g.per_part + threadIdx.x; v0 < end; v0 += kThreads * kHaloUnroll) {
+    T val[kHaloUnroll];
+    int64_t doff[kHaloUnroll];
+    bool ok[kHaloUnroll];
+#pragma unroll
+    for (int u = 0; u < kHaloUnroll; ++u) {
+      const uint32_t v = v0 + u * kThreads;
+      ok[u] = v < end;
+      if (ok[u]) {
+        uint32_t k, j, iv, r;
+        if (v < 2 * g.nA) { // k-ghost planes
+          const uint32_t w = v < g.nA ? v : v - g.nA;
+          g.d_plane_full.divmod(w, k, r);
+          if (v >= g.nA) k += g.ng[2] + g.nx[2];
+          g.d_nivec.divmod(r, j, iv);
+        } else {
+          g.d_plane_in.divmod(v - 2 * g.nA, k, r);
+          k += g.ng[2];
+          if (r < g.rows_full) { // j-ghost rows
+            g.d_nivec.divmod(r, j, iv);
+            if (j >= (uint32_t)g.ng[1]) j += g.nx[1];
+          } else { // x-ghost pieces of interior rows
+            g.d_xg.divmod(r - g.rows_full, j, iv);
+            j += g.ng[1];
+            if (iv >= g.xg_half) iv += g.nivec - g.xg;
+          }
+        }
+        const int i = (int)iv * V;
+        const int ox = i < g.ng[0] ? -1 : (i >= g.ng[0] + g.nx[0] ? 1 : 0);
+        const int oy = (int)j < g.ng[1] ? -1 : ((int)j >= g.ng[1] + g.nx[1] ? 1 : 0);
+        const int oz = (int)k < g.ng[2] ? -1 : ((int)k >= g.ng[2] + g.nx[2] ? 1 : 0);
+        const int sb = s_nbr[(ox + 1) + 3 * (oy + 1) + 9 * (oz + 1)];
+        ok[u] = sb >= 0;
+        if (ok[u]) {
+          const int64_t cell = (int64_t)k * g.sk + (int64_t)j * g.sj + i;
+          doff[u] = dbase + cell;
+          const int64_t soff = (int64_t)sb * g.sb + (int64_t)c * g.sc + cell -
+                               ((int64_t)oz * g.nx[2] * g.sk + (int64_t)oy * g.nx[1] * g.sj +
+                                ox * g.nx[0]);
+          val[u] = __ldg(reinterpret_cast<const T *>(field + soff));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kHaloUnroll; ++u)
+      if (ok[u]) *reinterpret_cast<T *>(field + doff[u]) = val[u];
+  }
+}
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int build_table(pb2_bnd_table **out, std::vector<DevRegion> &regs, int kind) {
@@ -348,6 +435,61 @@ int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t st
   ProfScope prof(K_COPY, as_stream(stream));
   copy_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, nonzero_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_halo_copy_uniform(const pb2_pack_geom *pg, double *field, const int32_t *nbr,
+                          pb2_stream_t stream) {
+  PB2_REQUIRE(pg && field && nbr, "bad arguments");
+  if (int rc = require_device()) return rc;
+  if (pg->nblocks == 0 || pg->ncomp == 0) return PB2_OK;
+  HaloGeom g;
+  memset(&g, 0, sizeof(g));
+  g.nblocks = pg->nblocks;
+  g.ncomp = pg->ncomp;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg->ndim;
+    g.nx[d] = sym ? 1 : pg->nx[d];
+    g.ng[d] = sym ? 0 : pg->ng;
+    g.n[d] = g.nx[d] + 2 * g.ng[d];
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg->block_stride;
+  const bool v2 = g.nx[0] % 2 == 0 && g.ng[0] % 2 == 0 && g.sb % 2 == 0 && aligned16(field);
+  const uint32_t V = v2 ? 2 : 1;
+  g.nivec = g.n[0] / V;
+  g.xg_half = g.ng[0] / V;
+  g.xg = 2 * g.xg_half;
+  g.plane_full = g.n[1] * g.nivec;
+  g.rows_full = 2 * g.ng[1] * g.nivec;
+  g.plane_in = g.rows_full + g.nx[1] * g.xg;
+  g.nA = g.ng[2] * g.plane_full;
+  const int64_t total = 2 * (int64_t)g.nA + (int64_t)g.nx[2] * g.plane_in;
+  PB2_REQUIRE(total < (1ll << 31), "block too large");
+  g.total = static_cast<uint32_t>(total);
+  if (g.total == 0) return PB2_OK;
+  g.d_nivec.init(g.nivec);
+  g.d_plane_full.init(g.plane_full > 0 ? g.plane_full : 1);
+  g.d_plane_in.init(g.plane_in > 0 ? g.plane_in : 1);
+  g.d_xg.init(g.xg > 0 ? g.xg : 1);
+  // enough CTAs for ~8 waves of 8 resident CTAs on 148 SMs, each part a whole number of trips
+  const uint32_t trip = kThreads * kHaloUnroll;
+  int64_t parts = (148 * 8 * 8 + (int64_t)g.nblocks * g.ncomp - 1) / ((int64_t)g.nblocks * g.ncomp);
+  const int64_t max_parts = (g.total + trip - 1) / trip;
+  if (parts > max_parts) parts = max_parts;
+  if (parts < 1) parts = 1;
+  g.per_part = ((g.total + parts - 1) / parts + trip - 1) / trip * trip;
+  g.parts = (g.total + g.per_part - 1) / g.per_part;
+  const int64_t ctas = (int64_t)g.nblocks * g.ncomp * g.parts;
+  PB2_REQUIRE(ctas < (1ll << 31), "grid too large");
+  ProfScope prof(K_COPY, as_stream(stream));
+  if (v2)
+    halo_uniform_kernel<2><<<static_cast<unsigned>(ctas), kThreads, 0, as_stream(stream)>>>(g, field, nbr);
+  else
+    halo_uniform_kernel<1><<<static_cast<unsigned>(ctas), kThreads, 0, as_stream(stream)>>>(g, field, nbr);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -2,7 +2,7 @@
 // as plain C++ so tests/test_fast_math_cpu.py can check it against the oracle on the CPU).
 //
 // WENO5-Z + MC-limited linear blend of benchmarks/burgers/recon.hpp:27-99, reorganised to
-// issue ~104 FP64 instructions instead of the ~165 of the reference's expression tree:
+// issue ~98 FP64 instructions instead of the ~165 of the reference's expression tree:
 //   * everything is written in the four first differences d_k = q_k - q_{k-1}: the
 //     smoothness indicators need one op per term instead of two, the candidate values
 //     become offsets from q2 (two ops each, and q2 is added once at the very end inside
@@ -79,12 +79,27 @@ PB2_HD void Linear(const double qm, const double q0, const double qp, double &ql
   qr = q0 - dq;
 }
 
+// Constants that do not fit the short-immediate form of an FP64 instruction live in constant
+// memory, so they are read as c[bank][offset] operands instead of being rebuilt with two moves
+// in front of every use.
+struct WenoConst {
+  double c13;           // 13/3
+  double g0, g1, g2;    // linear weights 0.1, 0.6, 0.3
+  double h0, h1, h2;    // g / 6
+  double eps3;          // eps / 3
+};
+#if defined(__CUDACC__)
+__constant__ WenoConst kW = {13.0 / 3.0, 0.1, 0.6, 0.3, 0.1 / 6.0, 0.6 / 6.0, 0.3 / 6.0,
+                             10.0 * DBL_EPSILON / 3.0};
+#else
+static const WenoConst kW = {13.0 / 3.0, 0.1, 0.6, 0.3, 0.1 / 6.0, 0.6 / 6.0, 0.3 / 6.0,
+                             10.0 * DBL_EPSILON / 3.0};
+#endif
+
 PB2_HD void WENO5Z(const double q0, const double q1, const double q2, const double q3,
                    const double q4, double &ql, double &qr) {
-  constexpr double g0 = 0.1, g1 = 0.6, g2 = 0.3;
   constexpr double eps = 10.0 * DBL_EPSILON; // robust.hpp:39-42
-  constexpr double c13 = 13.0 / 3.0;
-  constexpr double k13 = 1.0 / 3.0, k16 = 1.0 / 6.0, k56 = 5.0 / 6.0, k23 = 2.0 / 3.0;
+  const double c13 = kW.c13, g0 = kW.g0, g1 = kW.g1, g2 = kW.g2;
 
   const double d1 = q1 - q0, d2 = q2 - q1, d3 = q3 - q2, d4 = q4 - q3;
   const double s23 = d2 + d3; // q3 - q1
@@ -104,37 +119,40 @@ PB2_HD void WENO5Z(const double q0, const double q1, const double q2, const doub
   const double t = tau5 * rcp_fast(b01 * b2);
   const double r0 = fma(t, b12, 1.0), r1 = fma(t, b02, 1.0), r2 = fma(t, b01, 1.0);
 
-  // candidate values minus q2 (rows of w5alpha applied to the differences)
-  const double e0 = fma(k56, d2, -k13 * d1), e1 = fma(k16, d2, k13 * d3),
-               e2 = fma(k23, d3, -k16 * d4);
-  const double f0 = fma(-k56, d3, k13 * d4), f1 = fma(-k16, d3, -k13 * d2),
-               f2 = fma(-k23, d2, k16 * d1);
+  // SIX times (candidate value - q2): the rows of w5alpha applied to the differences have
+  // small integer coefficients (short immediates, and a coefficient 1 costs no multiply)
+  const double e0 = fma(5.0, d2, -2.0 * d1), e1 = fma(2.0, d3, d2), e2 = fma(4.0, d3, -d4);
+  const double f0 = fma(-5.0, d3, 2.0 * d4), f1 = fma(-2.0, d2, -d3), f2 = fma(-4.0, d2, d1);
 
   const double w1 = fma(g1, r1, eps); // centre weight, both sides
-  // left: weights w_k = g_k r_k + eps;  (ql - q2) = sum(w e)/S;  alpha = 3 w0 w1 w2/(S D) + eps
+  // left: weights w_k = g_k r_k + eps, S = sum w, D = g2 w0 w1 + g1 w0 w2 + g0 w1 w2.
+  //   D is built with g/6, so 1/(S D/6) = 6/(S D):  2 alpha_l = 6 w0 w1 w2/(S D) + 2 eps needs
+  //   no extra factor, and (D/6) * 6/(S D) = 1/S scales the candidate sum: dl = 6 (ql_w - q2)
   double w0 = fma(g0, r0, eps), w2 = fma(g2, r2, eps);
   double w12 = w1 * w2;
   double S = w0 + w1 + w2;
-  double D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
+  double D = fma(w0, fma(kW.h2, w1, kW.h1 * w2), kW.h0 * w12);
   double iSD = rcp_fast(S * D);
-  const double alpha_l2 = fma(6.0 * w0 * w12, iSD, 2.0 * eps); // 2 alpha_l
+  const double al2 = fma(w0 * w12, iSD, 2.0 * eps);
   const double dl = fma(w0, e0, fma(w1, e1, w2 * e2)) * (D * iSD);
 
+  // right: mirrored weights; D unscaled, so  alpha_r / 3 = w0 w1 w2/(S D) + eps/3
   w0 = fma(g0, r2, eps);
   w2 = fma(g2, r0, eps);
   w12 = w1 * w2;
   S = w0 + w1 + w2;
   D = fma(w0, fma(g2, w1, g1 * w2), g0 * w12);
   iSD = rcp_fast(S * D);
-  const double alpha_r = fma(3.0 * w0 * w12, iSD, eps);
+  const double ar3 = fma(w0 * w12, iSD, kW.eps3);
   const double dr = fma(w0, f0, fma(w1, f1, w2 * f2)) * (D * iSD);
 
   const double dq = half_mc(d2, d3, s23);
-  // alpha_lin = 2 al ar / (al + ar)
-  const double alpha_lin = alpha_l2 * alpha_r * rcp_fast(fma(0.5, alpha_l2, alpha_r));
-  const double om = 1.0 - alpha_lin;
-  ql = fma(alpha_lin, dl, fma(om, dq, q2));
-  qr = fma(alpha_lin, dr, fma(-om, dq, q2));
+  // X = alpha_lin / 6 with alpha_lin = 2 al ar/(al + ar) = al2 (3 ar3) / (al2/2 + 3 ar3)
+  //   => X = al2 ar3 / (al2 + 6 ar3);  the 1/6 is the one the candidate sums still owe
+  const double X = al2 * ar3 * rcp_fast(fma(6.0, ar3, al2));
+  const double om = fma(-6.0, X, 1.0);
+  ql = fma(X, dl, fma(om, dq, q2));
+  qr = fma(X, dr, fma(-om, dq, q2));
 }
 
 } // namespace fastmath

@@ -10,6 +10,7 @@
 //   * local channels (sender and receiver on the same GPU) are ONE fused launch that moves
 //     sender box -> receiver ghost box with no intermediate buffer: half the HBM traffic of
 //     pack + unpack.  SendBoundBufs<local> only publishes "sent"; SetBounds<local> copies.
+//     On uniform meshes that launch does not even read a region table (see uniform_halo).
 //   * nonlocal channels are packed straight into one contiguous slab per peer GPU, shipped
 //     by one grouped ncclSend/ncclRecv per peer on a communication stream, and unpacked
 //     after a stream-side event wait (no host polling; the CommBuffer state machine of
@@ -71,6 +72,11 @@ struct BvarsCache {
   ExchangePlan plan;
   std::vector<Variable *> vars;
   pb2_bnd_table *copy_local = nullptr;
+  // uniform meshes, dense fields, one batch per device: local channels need no region table —
+  // one descriptor-free launch per field pulls every ghost cell from the owning neighbour
+  // (pb2_halo_copy_uniform); halo_nbr is [nblocks][27] on the device
+  bool uniform_halo = false;
+  DeviceBuffer halo_nbr;
   pb2_bnd_table *pack = nullptr, *unpack = nullptr;
   // [0]: regions whose neighbour is local, [1]: nonlocal
   pb2_bnd_table *restrict_send[2] = {nullptr, nullptr}, *restrict_set[2] = {nullptr, nullptr};

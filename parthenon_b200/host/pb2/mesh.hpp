@@ -208,6 +208,9 @@ class Mesh {
   // slab (nonlocal) path runs on one GPU (the reference tests its MPI path the same way
   // with one-rank runs of BuffCommType::both)
   int virtual_ranks = 1;
+  // test knob (pb2/table_halo): force the general region-table path for local channels even on
+  // uniform meshes, where the descriptor-free pb2_halo_copy_uniform would be used
+  bool table_halo = false;
   int VirtualRankOf(int gid) const;
 
   int GetNumMeshBlocksThisRank() const { return static_cast<int>(block_list.size()); }

@@ -298,6 +298,24 @@ void Rebuild(MeshData<Real> *md) {
   }
   PB2_CHECK(pb2_copy_table_create(&c.copy_local, copies.data(), static_cast<int64_t>(copies.size())));
 
+  // uniform fast path: all local channels are same-level boxes between blocks of this batch
+  c.uniform_halo = !pm->multilevel && pm->DefaultNumPartitions() == 1 && !c.plan.local.empty() &&
+                   !pm->table_halo;
+  for (Variable *v : c.vars) c.uniform_halo = c.uniform_halo && !v->metadata().IsSparse();
+  if (c.uniform_halo) {
+    std::vector<int32_t> nbr(static_cast<size_t>(md->NumBlocks()) * 27, -1);
+    for (const Channel &ch : c.plan.local) {
+      if (ch.var != 0) continue; // the topology is the same for every field
+      const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
+      const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
+      // offset_index is the sender's view of the receiver; the receiver sees the mirror image
+      nbr[static_cast<size_t>(rb->pack_index) * 27 + (26 - ch.offset_index)] = sb->pack_index;
+    }
+    c.halo_nbr.Allocate(sizeof(int32_t) * nbr.size(), md->stream());
+    PB2_CHECK(pb2_memcpy_h2d(c.halo_nbr.get(), nbr.data(), sizeof(int32_t) * nbr.size(), md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+  }
+
   // slab channels
   auto bnd = [&](const Channel &ch, bool send) {
     const int gid = send ? ch.sender_gid : ch.receiver_gid;
@@ -512,7 +530,14 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
   Mesh *pm = md->GetMeshPointer();
   pb2_stream_t st = md->stream();
   if (DoesLocal(bt)) {
-    PB2_CHECK(pb2_copy(c.copy_local, nullptr, st));
+    if (c.uniform_halo) {
+      for (Variable *v : c.vars) {
+        const pb2_pack_geom g = md->Geometry(*v);
+        PB2_CHECK(pb2_halo_copy_uniform(&g, v->data(), c.halo_nbr.get<int32_t>(), st));
+      }
+    } else {
+      PB2_CHECK(pb2_copy(c.copy_local, nullptr, st));
+    }
     c.elements_local = c.plan.local_elements;
     for (int p = 0; p < pm->DefaultNumPartitions(); ++p) {
       MeshData<Real> *smd =

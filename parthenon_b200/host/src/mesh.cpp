@@ -350,6 +350,7 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
   adaptive = refinement == "adaptive";
   pack_size_ = pin->GetOrAddInteger("parthenon/mesh", "pack_size", -1);
   virtual_ranks = pin->GetOrAddInteger("pb2", "virtual_ranks", 1);
+  table_halo = pin->GetOrAddBoolean("pb2", "table_halo", false);
 
   BuildTree(pin, leaves);
   if (refinement != "none") multilevel = true; // coarse buffers exist (mesh.cpp:118-140)

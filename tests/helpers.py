@@ -157,3 +157,13 @@ def leaves_from_bounds(bounds, nx_mesh, nx_block, xmin=-0.5, xmax=0.5):
               for d in range(3)]
         out.append((level, *lx))
     return np.array(out, dtype=np.int32), nrb
+
+
+def neighbor_table(mesh):
+    """[nblocks][27] int32: block owning the ghosts at receiver-side offset (ox1,ox2,ox3),
+    index (ox1+1) + 3 (ox2+1) + 9 (ox3+1); -1 where there is none (uniform meshes)"""
+    tab = np.full((mesh.nblocks, 27), -1, dtype=np.int32)
+    for b in range(mesh.nblocks):
+        for (gid, _lvl, o1, o2, o3) in mesh.neighbors(b):
+            tab[b, (o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)] = gid
+    return tab

@@ -65,6 +65,19 @@ def test_fast_cycles_within_tolerance_of_reference_dumps(recon, ng):
         assert abs(sim.time - g["times"][c]) <= TOL * g["times"][c]
 
 
+def test_table_halo_path_bit_exact_vs_reference_dumps():
+    """pb2/table_halo=true forces the general region-table copy for local channels (the path
+    multilevel meshes use) instead of the descriptor-free uniform kernel: same bits"""
+    g = np.load(os.path.join(GOLD, "burgers_u16_b8_s1_weno5.npz"))
+    sim = host.Simulation(overrides=burgers_overrides(8, 2, 4, 1, "weno5", "strict", True,
+                                                      {"pb2/table_halo": "true"}))
+    sim.pre_execute()
+    assert np.array_equal(sim.get_field("base", "U"), g["U_0"])
+    for c in (1, 2, 3):
+        sim.cycle()
+        assert np.array_equal(sim.get_field("base", "U"), g[f"U_{c}"]), f"cycle {c}"
+
+
 @pytest.mark.parametrize("math,rtol", [("strict", 2e-13), ("fast", 1e-12)])
 def test_history_vs_reference_hst(math, rtol):
     """benchmark shape (32^3 blocks, 8 scalars, weno5) for 10 cycles against the reference's

@@ -57,6 +57,41 @@ def test_pack_unpack_copy_uniform(ndim, nx, ng, nrb, ncomp):
     torch.cuda.synchronize()
     assert np.array_equal(Ud2.cpu().numpy(), Uref)
 
+    # descriptor-free uniform path: only a [nblocks][27] neighbour table
+    Ud3 = torch.from_numpy(U).to(DEV)
+    nbr = torch.from_numpy(H.neighbor_table(m)).to(DEV)
+    dx = torch.ones((m.nblocks, 3), dtype=torch.float64, device=DEV)
+    g = H.make_geom(m, ncomp, dx)
+    capi.check(capi.lib().pb2_halo_copy_uniform(C.byref(g), Ud3.data_ptr(), nbr.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(Ud3.cpu().numpy(), Uref)
+
+
+def test_halo_uniform_skips_missing_neighbours():
+    """ghosts whose owner is not on this device (table entry < 0) are left untouched — they
+    belong to pb2_unpack — while every other ghost is filled"""
+    m = oracle.Mesh(3, (8, 8, 8), 4, (2, 2, 2))
+    ncomp = 2
+    U = rand_field(m, ncomp, 5)
+    Uref = U.copy()
+    m.exchange(Uref)
+    tab = H.neighbor_table(m)
+    # pretend the +x neighbour (offset index 14) of every block lives elsewhere
+    tab[:, 14] = -1
+    Ud = torch.from_numpy(U).to(DEV)
+    nbr = torch.from_numpy(tab).to(DEV)
+    dx = torch.ones((m.nblocks, 3), dtype=torch.float64, device=DEV)
+    g = H.make_geom(m, ncomp, dx)
+    capi.check(capi.lib().pb2_halo_copy_uniform(C.byref(g), Ud.data_ptr(), nbr.data_ptr(), None))
+    torch.cuda.synchronize()
+    out = Ud.cpu().numpy()
+    ng, n = 4, 8
+    face = (slice(None), slice(None), slice(ng, ng + n), slice(ng, ng + n), slice(ng + n, None))
+    assert np.array_equal(out[face], U[face])          # untouched
+    mask = np.ones(out.shape, dtype=bool)
+    mask[face] = False
+    assert np.array_equal(out[mask], Uref[mask])       # everything else exchanged
+
 
 def test_exchange_idempotent_full_size():
     """size-independent property at benchmark block shape: a second exchange changes
@@ -69,6 +104,13 @@ def test_exchange_idempotent_full_size():
     torch.cuda.synchronize()
     once = Ud.clone()
     capi.check(capi.lib().pb2_copy(tc.h, None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(once, Ud)
+    # the descriptor-free kernel on the same field: nothing changes either
+    nbr = torch.from_numpy(H.neighbor_table(m)).to(DEV)
+    dx = torch.ones((m.nblocks, 3), dtype=torch.float64, device=DEV)
+    g = H.make_geom(m, ncomp, dx)
+    capi.check(capi.lib().pb2_halo_copy_uniform(C.byref(g), Ud.data_ptr(), nbr.data_ptr(), None))
     torch.cuda.synchronize()
     assert torch.equal(once, Ud)
     # block 0 (lx=0,0,0): its -x ghost slab equals the +x interior slab of block lx=(3,0,0)
