@@ -63,6 +63,7 @@ def algorithmic_bytes_per_zone(kernel, ghost_per_zone):
         "sweep_march_kernel<y>": 8 * (3 * c), "sweep_march_kernel<z>": 8 * (3 * c + 1),
         # every ghost value read once, written once
         "copy_kernel": 8 * 2 * c * ghost_per_zone,
+        "halo_uniform_kernel": 8 * 2 * c * ghost_per_zone,
         "pack_kernel": 8 * 2 * c * ghost_per_zone, "unpack_kernel": 8 * 2 * c * ghost_per_zone,
     }
     return table.get(kernel)

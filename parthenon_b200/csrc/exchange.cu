@@ -485,7 +485,7 @@ int pb2_halo_copy_uniform(const pb2_pack_geom *pg, double *field, const int32_t 
   g.parts = (g.total + g.per_part - 1) / g.per_part;
   const int64_t ctas = (int64_t)g.nblocks * g.ncomp * g.parts;
   PB2_REQUIRE(ctas < (1ll << 31), "grid too large");
-  ProfScope prof(K_COPY, as_stream(stream));
+  ProfScope prof(K_HALO_UNIFORM, as_stream(stream));
   if (v2)
     halo_uniform_kernel<2><<<static_cast<unsigned>(ctas), kThreads, 0, as_stream(stream)>>>(g, field, nbr);
   else
