@@ -218,7 +218,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, after=None):
         """CUDA events on the application's stream, barrier + sync on both sides, max over ranks"""
         ev0, ev1 = C.c_void_p(), C.c_void_p()
         capi.check(L.pb2_event_create(C.byref(ev0)))
@@ -227,6 +227,10 @@ def main():
         capi.check(L.pb2_event_record(ev0, sim.stream))
         for _ in range(steps):
             fn()
+        if after is not None:
+            # work still draining on the copy streams belongs to the timed region: wait for it
+            # on the host, then close the interval on the (now idle) application stream
+            after()
         capi.check(L.pb2_event_record(ev1, sim.stream))
         barrier()
         ms = C.c_float()
@@ -271,30 +275,60 @@ def main():
     # ---- end to end: state uploaded from pinned host memory and read back every step --------
     e2e = None
     if not args.no_e2e:
-        # the application's state lives in HOST memory (interior cells, pinned); every step
-        # uploads it, fills ghosts, advances one cycle and reads the new state back
+        # Every step takes one batch of state (interior cells of U) from PINNED HOST memory,
+        # uploads it, fills ghosts, advances one RK2 cycle and returns the new state to host
+        # memory.  Batches are independent (a stream of ensemble members), so the host API's two
+        # lanes overlap the H2D of batch n+1 and the D2H of batch n-1 with the cycle of batch n
+        # (full-duplex PCIe); the serial figure (one batch at a time, no overlap) is kept beside
+        # it.  Every step moves nreal*8 bytes each way inside the timed region either way.
         nreal = sim.interior_size("base", "U")
-        hbuf = torch.empty(nreal, dtype=torch.float64).pin_memory()
-        hp = hbuf.data_ptr()
-        sim.download_interior("base", "U", hp, nreal)
+        hin = [torch.empty(nreal, dtype=torch.float64).pin_memory() for _ in range(2)]
+        hout = [torch.empty(nreal, dtype=torch.float64).pin_memory() for _ in range(2)]
+        sim.download_interior("base", "U", hin[0].data_ptr(), nreal)
         sim.sync()
+        hin[1].copy_(hin[0])
 
-        def e2e_step():
-            sim.upload_interior("base", "U", hp, nreal)
+        def e2e_serial():
+            sim.upload_interior("base", "U", hin[0].data_ptr(), nreal)
             sim.cycle()
-            sim.download_interior("base", "U", hp, nreal)
+            sim.download_interior("base", "U", hout[0].data_ptr(), nreal)
 
-        e2e_step()
-        esec = timed(e2e_step, args.steps)
+        state = {"i": 0}
+
+        def e2e_piped():
+            i = state["i"]
+            # batch i+1 starts crossing PCIe now; batch i (prefetched one call earlier) joins
+            # the application stream, cycles, and drains on the D2H stream
+            sim.prefetch_interior("base", "U", hin[(i + 1) % 2].data_ptr(), nreal, (i + 1) % 2)
+            sim.commit_interior("base", "U", i % 2)
+            sim.cycle()
+            sim.writeback_interior("base", "U", hout[i % 2].data_ptr(), nreal, i % 2)
+            state["i"] = i + 1
+
+        def drain():
+            sim.lane_sync(0)
+            sim.lane_sync(1)
+
+        e2e_serial()
+        ssec = timed(e2e_serial, min(args.steps, 5)) / min(args.steps, 5)
+        sim.prefetch_interior("base", "U", hin[0].data_ptr(), nreal, 0)
+        for _ in range(2):
+            e2e_piped()
+        esec = timed(e2e_piped, args.steps, after=drain)
         tot = torch.tensor([float(nreal)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tot)
         e2e = {"value": args.steps * zones / esec, "unit": UNIT,
                "h2d_bytes_per_step": int(8 * tot.item()), "d2h_bytes_per_step": int(8 * tot.item()),
                "ms_per_step": 1e3 * esec / args.steps,
-               "what": "pinned host U (interior cells) -> H2D -> scatter + ghost exchange -> one RK2 "
-                       "cycle -> gather -> D2H, every step, through pb2h_sim_upload_interior / "
-                       "pb2h_sim_cycle / pb2h_sim_download_interior"}
+               "serial_value": zones / ssec, "serial_ms_per_step": 1e3 * ssec,
+               "what": "per step: pinned host U (interior cells) -> H2D -> scatter + ghost exchange "
+                       "-> one RK2 cycle -> gather -> D2H into pinned host memory, through "
+                       "pb2h_sim_prefetch_interior / _commit_interior / pb2h_sim_cycle / "
+                       "_writeback_interior; independent batches double-buffered over two lanes so "
+                       "the copies of neighbouring batches overlap the cycle (timed region ends "
+                       "when the last D2H has landed); serial_* = same path one batch at a time "
+                       "(pb2h_sim_upload_interior / _cycle / _download_interior)"}
 
     if rank != 0:
         if world > 1:

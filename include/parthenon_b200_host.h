@@ -83,6 +83,20 @@ int pb2h_sim_upload_interior(pb2h_sim *sim, const char *container, const char *f
                              const double *host, int64_t nreal);
 int pb2h_sim_download_interior(pb2h_sim *sim, const char *container, const char *field,
                                double *host, int64_t nreal);
+/* Pipelined variant for streams of INDEPENDENT batches of state (ensemble members, frames of a
+ * parameter scan): two lanes, each with its own device staging; the H2D copy runs on a copy
+ * stream as soon as the lane's staging is free (prefetch), the scatter + ghost exchange joins
+ * the application stream (commit), and the gather + D2H drains on a second copy stream
+ * (writeback), so the copies of neighbouring batches overlap the cycle of the current one.
+ *   prefetch(lane, batch n+1); commit(lane'); cycle; writeback(lane'); ... lane_sync(lane)
+ * `host` buffers must stay valid until pb2h_sim_lane_sync(lane) (writeback) or the matching
+ * commit has run (prefetch). */
+int pb2h_sim_prefetch_interior(pb2h_sim *sim, const char *container, const char *field,
+                               const double *host, int64_t nreal, int lane);
+int pb2h_sim_commit_interior(pb2h_sim *sim, const char *container, const char *field, int lane);
+int pb2h_sim_writeback_interior(pb2h_sim *sim, const char *container, const char *field,
+                                double *host, int64_t nreal, int lane);
+int pb2h_sim_lane_sync(pb2h_sim *sim, int lane);
 /* one full ghost exchange of a container (Send -> Receive -> Set [-> Prolongate]),
  * Mesh::CommunicateBoundaries mesh.cpp:640-706 */
 int pb2h_sim_exchange(pb2h_sim *sim, const char *container, int prolongate);

@@ -21,7 +21,8 @@ SYMBOLS = [
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_field_ptr",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
     "pb2h_sim_exchange_elements", "pb2h_sim_history", "pb2h_sim_upload_interior",
-    "pb2h_sim_download_interior",
+    "pb2h_sim_download_interior", "pb2h_sim_prefetch_interior", "pb2h_sim_commit_interior",
+    "pb2h_sim_writeback_interior", "pb2h_sim_lane_sync",
 ]
 
 BURGERS_DECK = """
@@ -103,6 +104,10 @@ def lib():
     L.pb2h_sim_set_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
     L.pb2h_sim_upload_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64]
     L.pb2h_sim_download_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64]
+    L.pb2h_sim_prefetch_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64, C.c_int]
+    L.pb2h_sim_commit_interior.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.pb2h_sim_writeback_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64, C.c_int]
+    L.pb2h_sim_lane_sync.argtypes = [vp, C.c_int]
     L.pb2h_sim_exchange.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_phase.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_elements.restype = i64
@@ -242,6 +247,9 @@ class Simulation(_Base):
     def dt(self):
         return lib().pb2h_sim_dt(self.h)
 
+    def set_dt(self, dt):
+        check(lib().pb2h_sim_set_dt(self.h, float(dt)))
+
     @property
     def ncycle(self):
         return lib().pb2h_sim_ncycle(self.h)
@@ -292,6 +300,21 @@ class Simulation(_Base):
     def download_interior(self, container, field, host_ptr, nreal):
         check(lib().pb2h_sim_download_interior(self.h, container.encode(), field.encode(),
                                                host_ptr, nreal))
+
+    # pipelined lanes (independent batches of state; see include/parthenon_b200_host.h)
+    def prefetch_interior(self, container, field, host_ptr, nreal, lane):
+        check(lib().pb2h_sim_prefetch_interior(self.h, container.encode(), field.encode(),
+                                               host_ptr, nreal, lane))
+
+    def commit_interior(self, container, field, lane):
+        check(lib().pb2h_sim_commit_interior(self.h, container.encode(), field.encode(), lane))
+
+    def writeback_interior(self, container, field, host_ptr, nreal, lane):
+        check(lib().pb2h_sim_writeback_interior(self.h, container.encode(), field.encode(),
+                                                host_ptr, nreal, lane))
+
+    def lane_sync(self, lane):
+        check(lib().pb2h_sim_lane_sync(self.h, lane))
 
     def exchange(self, container="base", prolongate=True):
         check(lib().pb2h_sim_exchange(self.h, container.encode(), int(prolongate)))

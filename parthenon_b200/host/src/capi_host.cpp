@@ -59,6 +59,22 @@ struct pb2h_sim {
   std::unique_ptr<MultiStageDriver> driver;
   bool topology_only = false;
   DeviceBuffer staging; // packed-interior staging for upload / download through host buffers
+  // double-buffered host <-> device lanes (pb2h_sim_prefetch_interior ...): copies run on their
+  // own streams so the H2D of batch n+1 and the D2H of batch n-1 overlap the cycle of batch n
+  struct Lane {
+    DeviceBuffer in, out;
+    pb2_event_t h2d_done = nullptr, in_free = nullptr, gathered = nullptr, d2h_done = nullptr;
+  };
+  static constexpr int kLanes = 2;
+  Lane lanes[kLanes];
+  pb2_stream_t s_h2d = nullptr, s_d2h = nullptr;
+  ~pb2h_sim() {
+    for (auto &l : lanes)
+      for (pb2_event_t e : {l.h2d_done, l.in_free, l.gathered, l.d2h_done})
+        if (e) pb2_event_destroy(e);
+    if (s_h2d) pb2_stream_destroy(s_h2d);
+    if (s_d2h) pb2_stream_destroy(s_d2h);
+  }
   // topology-only objects
   std::unique_ptr<ParameterInput> pin;
   std::unique_ptr<Mesh> mesh;
@@ -324,6 +340,89 @@ int pb2h_sim_download_interior(pb2h_sim *sim, const char *container, const char 
     DeviceBuffer &st = Staging(sim, sizeof(double) * n);
     PB2_CHECK(pb2_interior_gather(&g, v.data(), st.get<double>(), md->stream()));
     PB2_CHECK(pb2_memcpy_d2h(host, st.get(), sizeof(double) * n, md->stream()));
+  });
+}
+
+// ---- pipelined variant: independent batches of state streamed through two lanes ----------
+namespace {
+struct LaneCtx {
+  pb2h_sim::Lane *lane;
+  Variable *v;
+  std::shared_ptr<MeshData<Real>> md;
+  pb2_pack_geom g;
+  int64_t n;
+};
+LaneCtx GetLane(pb2h_sim *sim, const char *container, const char *field, int lane,
+                int64_t nreal) {
+  PARTHENON_REQUIRE(lane >= 0 && lane < pb2h_sim::kLanes, "lane out of range");
+  LaneCtx c;
+  c.v = &FindVar(sim, container, field);
+  c.md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+  c.g = c.md->Geometry(*c.v);
+  c.n = static_cast<int64_t>(c.g.nblocks) * c.g.ncomp * sim->pm()->GetNumberOfMeshBlockCells();
+  PARTHENON_REQUIRE(nreal < 0 || c.n == nreal, "interior size mismatch");
+  c.lane = &sim->lanes[lane];
+  if (!sim->s_h2d) {
+    PB2_CHECK(pb2_stream_create(&sim->s_h2d));
+    PB2_CHECK(pb2_stream_create(&sim->s_d2h));
+  }
+  pb2h_sim::Lane &l = *c.lane;
+  if (!l.h2d_done) {
+    PB2_CHECK(pb2_event_create(&l.h2d_done));
+    PB2_CHECK(pb2_event_create(&l.in_free));
+    PB2_CHECK(pb2_event_create(&l.gathered));
+    PB2_CHECK(pb2_event_create(&l.d2h_done));
+  }
+  const size_t bytes = sizeof(double) * c.n;
+  if (l.in.bytes() < bytes) {
+    l.in.Allocate(bytes, c.md->stream());
+    l.out.Allocate(bytes, c.md->stream());
+    PB2_CHECK(pb2_stream_sync(c.md->stream()));
+  }
+  return c;
+}
+} // namespace
+
+int pb2h_sim_prefetch_interior(pb2h_sim *sim, const char *container, const char *field,
+                               const double *host, int64_t nreal, int lane) {
+  return Guard([&] {
+    LaneCtx c = GetLane(sim, container, field, lane, nreal);
+    // the lane's input staging is free once the scatter that last read it has run
+    PB2_CHECK(pb2_stream_wait_event(sim->s_h2d, c.lane->in_free));
+    PB2_CHECK(pb2_memcpy_h2d(c.lane->in.get(), host, sizeof(double) * c.n, sim->s_h2d));
+    PB2_CHECK(pb2_event_record(c.lane->h2d_done, sim->s_h2d));
+  });
+}
+
+int pb2h_sim_commit_interior(pb2h_sim *sim, const char *container, const char *field,
+                             int lane) {
+  return Guard([&] {
+    LaneCtx c = GetLane(sim, container, field, lane, -1);
+    PB2_CHECK(pb2_stream_wait_event(c.md->stream(), c.lane->h2d_done));
+    PB2_CHECK(pb2_interior_scatter(&c.g, c.lane->in.get<double>(), c.v->data(), c.md->stream()));
+    PB2_CHECK(pb2_event_record(c.lane->in_free, c.md->stream()));
+    CommunicateBoundaries(c.md, true);
+  });
+}
+
+int pb2h_sim_writeback_interior(pb2h_sim *sim, const char *container, const char *field,
+                                double *host, int64_t nreal, int lane) {
+  return Guard([&] {
+    LaneCtx c = GetLane(sim, container, field, lane, nreal);
+    // the lane's output staging is free once its previous D2H has drained
+    PB2_CHECK(pb2_stream_wait_event(c.md->stream(), c.lane->d2h_done));
+    PB2_CHECK(pb2_interior_gather(&c.g, c.v->data(), c.lane->out.get<double>(), c.md->stream()));
+    PB2_CHECK(pb2_event_record(c.lane->gathered, c.md->stream()));
+    PB2_CHECK(pb2_stream_wait_event(sim->s_d2h, c.lane->gathered));
+    PB2_CHECK(pb2_memcpy_d2h(host, c.lane->out.get(), sizeof(double) * c.n, sim->s_d2h));
+    PB2_CHECK(pb2_event_record(c.lane->d2h_done, sim->s_d2h));
+  });
+}
+
+int pb2h_sim_lane_sync(pb2h_sim *sim, int lane) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(lane >= 0 && lane < pb2h_sim::kLanes, "lane out of range");
+    if (sim->lanes[lane].d2h_done) PB2_CHECK(pb2_event_sync(sim->lanes[lane].d2h_done));
   });
 }
 
