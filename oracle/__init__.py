@@ -54,6 +54,8 @@ def lib():
         L.orc_restrict_send.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_restrict_set.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_prolongate.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_flux_correct.restype = C.c_int64
+        L.orc_flux_correct.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int]
         L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
         L.orc_linear.argtypes = [C.c_double] * 3 + [dp, dp]
         L.orc_lr_to_flux.argtypes = [C.c_double] * 8 + [dp] * 5
@@ -170,6 +172,12 @@ class Mesh:
     def unpack(self, U, buf, off, Uc=None):
         lib().orc_unpack(self.h, _dp(U), _dp(Uc) if Uc is not None else None, U.shape[1],
                          _dp(buf), off.ctypes.data_as(C.POINTER(C.c_int64)))
+
+    def flux_correct(self, F):
+        """F: three face-flux arrays [nblocks][ncomp][nk][nj][ni], corrected in place"""
+        dp = C.POINTER(C.c_double)
+        arr = (dp * 3)(*[_dp(f) for f in F])
+        return lib().orc_flux_correct(self.h, arr, F[0].shape[1])
 
     def burgers_ic(self, U):
         lib().orc_burgers_ic(self.h, _dp(U), U.shape[1])

@@ -669,6 +669,134 @@ void orc_prolongate(const OrcMesh *m, double *U, const double *Uc, int ncomp) {
   }
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* flux correction at fine-coarse faces: SendBoundBufs<flxcor_send> / SetBounds<flxcor_recv>
+ * (boundary_communication.cpp:454-461) over the face flux of a cell-centred field.  Flux
+ * arrays have the cell array's extents; entry (k,j,i) of direction d is the LOWER d-face of
+ * cell (k,j,i), so face indices run is..ie+1 (IndexShape::GetBounds*(interior, F_d),
+ * mesh/domain.hpp:162-251). */
+
+static int face_dir(const int off[3]) { /* CellCentOffsets::IsFace: exactly one non-zero */
+  int nz = (off[0] != 0) + (off[1] != 0) + (off[2] != 0);
+  if (nz != 1) return -1;
+  return off[0] != 0 ? 0 : (off[1] != 0 ? 1 : 2);
+}
+
+/* CalcIndices (bnd_info.cpp:105-252) for a Metadata::Flux face field, element F_dir with
+ * dir the direction of the neighbour offset (GetFluxCorrectionElements :71-83).
+ * ir_type IR_SEND: the finer block, in its COARSE index space (nb coarser => c_cellbounds,
+ * :124-125); IR_RECV: the coarser block, in its fine index space. */
+static void calc_indices_flux(const OrcMesh *m, int b, int n, int ir_type, int s[3],
+                              int e[3]) {
+  const Block *blk = &m->blocks[b];
+  const Neighbor *nb = &blk->nb[n];
+  const Loc *loc = &blk->loc;
+  const int dir = face_dir(nb->off);
+  const int use_coarse = nb->loc.level < loc->level;
+  const int coarse_fac = nb->loc.level > loc->level ? 2 : 1;
+  for (int d = 0; d < 3; ++d) {
+    const int not_sym = d < m->ndim;
+    const int top = (d == dir && not_sym) ? 1 : 0; /* TopologicalOffset of F_dir */
+    const int bs = use_coarse ? m->cis[d] : m->is[d];
+    const int be = (use_coarse ? m->cie[d] : m->ie[d]) + top;
+    const int nbn = not_sym ? m->nx[d] / coarse_fac + top : 1;
+    if (nb->off[d] == 0) {
+      s[d] = bs;
+      e[d] = be;
+      if (loc->level < nb->origin_loc.level && not_sym) { /* :173-192, interior_offset = 0
+          for the receiving side; the sending side never has a finer neighbour here */
+        const int extra = (be - bs + 1) - nbn;
+        s[d] += (nb->origin_loc.lx[d] % 2 + 2) % 2 == 1 ? extra : 0;
+        e[d] -= (nb->origin_loc.lx[d] % 2 + 2) % 2 == 0 ? extra : 0;
+      }
+      /* :193-204 only moves the box by exterior_offset, which is 0 for a sender */
+    } else if (nb->off[d] > 0) { /* :207-208, flux: shared element only */
+      s[d] = be;
+      e[d] = be;
+    } else { /* :210-211 */
+      s[d] = bs;
+      e[d] = bs;
+    }
+  }
+  (void)ir_type;
+}
+
+/* RestrictAverage::Do pr_ops.hpp:105-165 with el = F_dir: average over the fine faces that
+ * tile one coarse face, weights coords.Volume<F_dir> = face area
+ * (uniform_cartesian.hpp:36-38, 248-258); fixed summation tree :155-162 */
+static double restrict_face(const OrcMesh *m, const double *F, int ncomp, int b, int c,
+                            int dir, int ck, int cj, int ci) {
+  const Block *blk = &m->blocks[b];
+  const int DIM = m->ndim;
+  const int inc[3] = {DIM > 0 && dir != 0, DIM > 1 && dir != 1, DIM > 2 && dir != 2};
+  const int i = (ci - m->cis[0]) * 2 + m->is[0];
+  const int j = DIM > 1 ? (cj - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int k = DIM > 2 ? (ck - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  const double area[3] = {blk->dx[1] * blk->dx[2], blk->dx[0] * blk->dx[2],
+                          blk->dx[0] * blk->dx[1]};
+  double vol[2][2][2], terms[2][2][2];
+  memset(vol, 0, sizeof(vol));
+  memset(terms, 0, sizeof(terms));
+  for (int ok = 0; ok < 1 + inc[2]; ++ok)
+    for (int oj = 0; oj < 1 + inc[1]; ++oj)
+      for (int oi = 0; oi < 1 + inc[0]; ++oi) {
+        vol[ok][oj][oi] = area[dir];
+        terms[ok][oj][oi] = vol[ok][oj][oi] * F[fidx(m, ncomp, b, c, k + ok, j + oj, i + oi)];
+      }
+  const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                      ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+  return (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+          ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+         tvol;
+}
+
+/* Every coarse block overwrites the part of a face flux shared with a finer neighbour by
+ * the area-weighted average of that neighbour's fine fluxes.  Region selection:
+ * ForEachBoundary<flxcor_recv> (loop_utils.hpp:145-160): face neighbours one level finer. */
+int64_t orc_flux_correct(const OrcMesh *m, double *const F[3], int ncomp) {
+  int64_t moved = 0;
+  if (!m->multilevel) return 0;
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      const int dir = face_dir(nb->off);
+      if (dir < 0 || dir >= m->ndim) continue;
+      if (nb->loc.level != blk->loc.level + 1) continue;
+      /* the sender's matching region */
+      const Block *sb = &m->blocks[nb->gid];
+      int sn = -1;
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          sn = q;
+          break;
+        }
+      if (sn < 0) {
+        fprintf(stderr, "oracle: no matching flux-correction sender for block %d nb %d\n", b, n);
+        abort();
+      }
+      int ss[3], se[3], rs[3], re[3];
+      calc_indices_flux(m, nb->gid, sn, IR_SEND, ss, se);
+      calc_indices_flux(m, b, n, IR_RECV, rs, re);
+      for (int d = 0; d < 3; ++d)
+        if (se[d] - ss[d] != re[d] - rs[d]) {
+          fprintf(stderr, "oracle: flux-correction extent mismatch block %d nb %d dir %d\n", b, n, d);
+          abort();
+        }
+      for (int c = 0; c < ncomp; ++c)
+        for (int k = 0; k <= re[2] - rs[2]; ++k)
+          for (int j = 0; j <= re[1] - rs[1]; ++j)
+            for (int i = 0; i <= re[0] - rs[0]; ++i) {
+              F[dir][fidx(m, ncomp, b, c, rs[2] + k, rs[1] + j, rs[0] + i)] =
+                  restrict_face(m, F[dir], ncomp, nb->gid, c, dir, ss[2] + k, ss[1] + j, ss[0] + i);
+              ++moved;
+            }
+    }
+  }
+  return moved;
+}
+
 int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int prolongate) {
   int64_t nreg = orc_count_regions(m);
   int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
@@ -790,6 +918,7 @@ struct OrcBurgers {
   double *rec[6]; /* Ulx Urx Uly Ury Ulz Urz */
   double *flux[3];
   double *derived;
+  double *Uc; /* coarse-buffer scratch of the container being exchanged (multilevel) */
   double dt, time, allowed_dt;
   int ncycle;
 };
@@ -840,6 +969,9 @@ OrcBurgers *orc_burgers_create(const OrcMesh *m, int num_scalars, int recon, dou
   for (int r = 0; r < 6; ++r) s->rec[r] = (double *)calloc(s->nfield, sizeof(double));
   for (int d = 0; d < 3; ++d) s->flux[d] = (double *)calloc(s->nfield, sizeof(double));
   s->derived = (double *)calloc((size_t)m->nblocks * ncell, sizeof(double));
+  if (m->multilevel)
+    s->Uc = (double *)calloc((size_t)m->nblocks * s->ncomp * m->cn[0] * m->cn[1] * m->cn[2],
+                             sizeof(double));
   s->dt = DBL_MAX;
   return s;
 }
@@ -851,6 +983,7 @@ void orc_burgers_destroy(OrcBurgers *s) {
   for (int r = 0; r < 6; ++r) free(s->rec[r]);
   for (int d = 0; d < 3; ++d) free(s->flux[d]);
   free(s->derived);
+  free(s->Uc);
   free(s);
 }
 double *orc_burgers_U(OrcBurgers *s) { return s->U; }
@@ -1020,10 +1153,17 @@ void orc_burgers_stage(OrcBurgers *st, int stage) {
   double *mc1 = stage == 1 ? st->U1 : st->U;
   double *base = st->U;
   orc_burgers_calculate_fluxes(st, mc0);
+  /* LoadAndSendFluxCorrections / SetFluxCorrections burgers_driver.cpp:94-96 */
+  if (st->m->multilevel) orc_flux_correct(st->m, st->flux, st->ncomp);
   flux_divergence(st);
   weighted_sum(st->nfield, mc0, base, beta, 1.0 - beta, mc0);        /* AverageIndependentData */
   weighted_sum(st->nfield, mc0, st->dUdt, 1.0, beta * st->dt, mc1); /* UpdateIndependentData */
-  orc_exchange(st->m, mc1, NULL, st->ncomp, 0);
+  /* Send/Receive/SetBounds<local|nonlocal>  burgers_driver.cpp:106-119.  The reference's
+   * stage list has NO ProlongateBounds task: on a multilevel mesh the coarse buffers are
+   * filled and restricted, but fine ghosts facing a coarser block keep the values they had
+   * (prolongated once by Mesh::Initialize, then carried through the full-extent
+   * WeightedSumData passes).  Reproduced as is. */
+  orc_exchange(st->m, mc1, st->Uc, st->ncomp, 0);
   calculate_derived(st, mc1);
   if (stage == 2) st->allowed_dt = estimate_timestep(st, mc1);
 }
@@ -1037,7 +1177,8 @@ static void set_global_timestep(OrcBurgers *st) {
 
 void orc_burgers_init(OrcBurgers *st) {
   orc_burgers_ic(st->m, st->U, st->ncomp);
-  orc_exchange(st->m, st->U, NULL, st->ncomp, 0);
+  /* Mesh::Initialize -> CommunicateBoundaries (mesh.cpp:640-706) does prolongate */
+  orc_exchange(st->m, st->U, st->Uc, st->ncomp, st->m->multilevel);
   calculate_derived(st, st->U);
   st->allowed_dt = estimate_timestep(st, st->U); /* InitializeBlockTimeSteps driver.cpp:194 */
   st->dt = DBL_MAX;
