@@ -175,6 +175,38 @@ int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream);
 int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * flux correction at fine-coarse faces
+ * replaces SendBoundBufs<flxcor_send> / SetBounds<flxcor_recv> (boundary_communication.cpp:
+ * 454-461) for the face fluxes of cell-centred fields: region selection loop_utils.hpp:145-160,
+ * index boxes bnd_info.cpp:105-252 with flux = true, RestrictAverage on faces pr_ops.hpp:105-165.
+ * The reference restricts the fine flux into the flux field's coarse buffer, packs it, and the
+ * coarser block unpacks it over its own face flux; here the restriction writes straight into
+ * the coarser block's flux array (same device) or into the peer slab (other device, unpacked
+ * there with pb2_unpack).
+ * ------------------------------------------------------------------------------------- */
+typedef struct pb2_flxcor_region {
+  const double *fine; /* component 0 of the FINER block's flux array of direction `dir` */
+  double *coarse;     /* component 0 of the COARSER block's flux array of the same direction,
+                         or NULL: write to the slab given at launch at buf_off */
+  int64_t buf_off;    /* slab offset in Reals; slab order is [comp][k][j][i] of the box */
+  int32_t dir;        /* 0..2: normal of the shared face (the neighbour offset direction) */
+  int32_t ndim;
+  int32_t fs[3];      /* fine-array index (i,j,k) of the first fine face of the box */
+  int32_t ds[3];      /* destination start (i,j,k) in the coarser block's array */
+  int32_t n[3];       /* extent in COARSE faces; n[dir] == 1 */
+  int32_t ncomp;
+  int32_t fine_stride_j, fine_stride_k, fine_stride_c;
+  int32_t coarse_stride_j, coarse_stride_k, coarse_stride_c;
+  uint32_t status;    /* PB2_REGION_ALLOCATED */
+  double area;        /* coords.Volume<F_dir>: face area of the finer block */
+} pb2_flxcor_region;
+
+int pb2_flxcor_table_create(pb2_bnd_table **table, const pb2_flxcor_region *regions, int64_t n);
+/* One launch restricts and delivers every region of the table.  `slab` may be NULL when no
+ * region has coarse == NULL. */
+int pb2_flux_correct(const pb2_bnd_table *table, double *slab, pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * dense per-stage updates: src/interface/update.hpp:43-91, update.cpp:63-86
  * ------------------------------------------------------------------------------------- */
 /* z = w1*x + w2*y over n Reals (WeightedSumData, update.hpp:71-91) */
@@ -189,6 +221,14 @@ typedef struct pb2_pack_geom {
   int64_t block_stride; /* Reals between blocks; component stride is ni*nj*nk */
   const double *dx;     /* device [nblocks][3] cell widths */
 } pb2_pack_geom;
+
+/* z = w1*x + w2*y over the GHOST cells of every block only: what the reference's full-extent
+ * WeightedSumData passes (AverageIndependentData / UpdateIndependentData, update.hpp:122-137)
+ * do outside the interior.  A fused interior update plus this call equals the reference on
+ * multilevel meshes, where fine ghosts facing a coarser block are not refreshed by the
+ * stage's exchange.  x, y, z may alias. */
+int pb2_weighted_sum_ghosts(const pb2_pack_geom *g, const double *x, const double *y, double w1,
+                            double w2, double *z, pb2_stream_t stream);
 
 /* interior cells of a field <-> a packed buffer [block][comp][nx3][nx2][nx1] without ghosts
  * (the layout of an application's host arrays): the device side of uploading / reading back a

@@ -54,6 +54,7 @@ def lib():
         L.orc_restrict_send.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_restrict_set.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_prolongate.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_calc_indices_flux.argtypes = [C.c_void_p, C.c_int, C.c_int, ip, ip]
         L.orc_flux_correct.restype = C.c_int64
         L.orc_flux_correct.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int]
         L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
@@ -172,6 +173,12 @@ class Mesh:
     def unpack(self, U, buf, off, Uc=None):
         lib().orc_unpack(self.h, _dp(U), _dp(Uc) if Uc is not None else None, U.shape[1],
                          _dp(buf), off.ctypes.data_as(C.POINTER(C.c_int64)))
+
+    def calc_indices_flux(self, b, n):
+        s = np.zeros(3, dtype=np.int32)
+        e = np.zeros(3, dtype=np.int32)
+        lib().orc_calc_indices_flux(self.h, b, n, _ip(s), _ip(e))
+        return tuple(int(x) for x in s), tuple(int(x) for x in e)
 
     def flux_correct(self, F):
         """F: three face-flux arrays [nblocks][ncomp][nk][nj][ni], corrected in place"""

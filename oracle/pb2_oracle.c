@@ -721,6 +721,11 @@ static void calc_indices_flux(const OrcMesh *m, int b, int n, int ir_type, int s
   (void)ir_type;
 }
 
+void orc_calc_indices_flux(const OrcMesh *m, int b, int n, int s[3], int e[3]) {
+  const Block *blk = &m->blocks[b];
+  calc_indices_flux(m, b, n, blk->nb[n].loc.level < blk->loc.level ? IR_SEND : IR_RECV, s, e);
+}
+
 /* RestrictAverage::Do pr_ops.hpp:105-165 with el = F_dir: average over the fine faces that
  * tile one coarse face, weights coords.Volume<F_dir> = face area
  * (uniform_cartesian.hpp:36-38, 248-258); fixed summation tree :155-162 */

@@ -47,6 +47,16 @@ class ProResRegion(C.Structure):
                 ("coarse_xmin", C.c_double * 3), ("coarse_dx", C.c_double * 3)]
 
 
+class FlxCorRegion(C.Structure):
+    _fields_ = [("fine", C.c_void_p), ("coarse", C.c_void_p), ("buf_off", C.c_int64),
+                ("dir", C.c_int32), ("ndim", C.c_int32), ("fs", C.c_int32 * 3),
+                ("ds", C.c_int32 * 3), ("n", C.c_int32 * 3), ("ncomp", C.c_int32),
+                ("fine_stride_j", C.c_int32), ("fine_stride_k", C.c_int32),
+                ("fine_stride_c", C.c_int32), ("coarse_stride_j", C.c_int32),
+                ("coarse_stride_k", C.c_int32), ("coarse_stride_c", C.c_int32),
+                ("status", C.c_uint32), ("area", C.c_double)]
+
+
 class PackGeom(C.Structure):
     _fields_ = [("nblocks", C.c_int32), ("ncomp", C.c_int32), ("ndim", C.c_int32),
                 ("nx", C.c_int32 * 3), ("ng", C.c_int32), ("block_stride", C.c_int64),
@@ -75,7 +85,8 @@ SYMBOLS = [
     "pb2_measure_fp64_peak",
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
-    "pb2_restrict", "pb2_prolongate", "pb2_weighted_sum", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
+    "pb2_restrict", "pb2_prolongate", "pb2_flxcor_table_create", "pb2_flux_correct",
+    "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
     "pb2_halo_copy_uniform",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
@@ -107,6 +118,8 @@ def lib():
     L.pb2_bnd_table_create.argtypes = [C.POINTER(vp), C.POINTER(BndRegion), i64]
     L.pb2_copy_table_create.argtypes = [C.POINTER(vp), C.POINTER(CopyRegion), i64]
     L.pb2_prores_table_create.argtypes = [C.POINTER(vp), C.POINTER(ProResRegion), i64]
+    L.pb2_flxcor_table_create.argtypes = [C.POINTER(vp), C.POINTER(FlxCorRegion), i64]
+    L.pb2_flux_correct.argtypes = [vp, vp, vp]
     L.pb2_bnd_table_destroy.argtypes = [vp]
     L.pb2_pack.argtypes = [vp, vp, vp, vp]
     L.pb2_unpack.argtypes = [vp, vp, vp, vp]
@@ -115,6 +128,8 @@ def lib():
     L.pb2_restrict.argtypes = [vp, vp]
     L.pb2_prolongate.argtypes = [vp, C.c_int, vp]
     L.pb2_weighted_sum.argtypes = [vp, vp, C.c_double, C.c_double, vp, i64, vp]
+    L.pb2_weighted_sum_ghosts.argtypes = [C.POINTER(PackGeom), vp, vp, C.c_double, C.c_double,
+                                          vp, vp]
     L.pb2_flux_divergence.argtypes = [C.POINTER(PackGeom), C.POINTER(vp), vp, vp]
     for f in ("pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage"):
         getattr(L, f).argtypes = [C.POINTER(BurgersArgs), vp]
@@ -177,6 +192,9 @@ class Table:
         elif kind == "prores":
             arr = (ProResRegion * max(n, 1))(*regions)
             check(lib().pb2_prores_table_create(C.byref(self.h), arr, n))
+        elif kind == "flxcor":
+            arr = (FlxCorRegion * max(n, 1))(*regions)
+            check(lib().pb2_flxcor_table_create(C.byref(self.h), arr, n))
         else:
             raise ValueError(kind)
         self.n = n

@@ -397,6 +397,7 @@ int pb2_bnd_table_destroy(pb2_bnd_table *table) {
   cudaFree(table->d_regions);
   cudaFree(table->d_chunks);
   cudaFree(table->d_prores);
+  cudaFree(table->d_flxcor);
   delete table;
   return PB2_OK;
 }

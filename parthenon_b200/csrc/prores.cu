@@ -150,6 +150,62 @@ __global__ void __launch_bounds__(kPrThreads)
   }
 }
 
+// Flux correction: RestrictAverage::Do pr_ops.hpp:105-165 with el = F_dir over the fine faces
+// tiling one coarse face, delivered straight to the coarser block's flux array (or a slab).
+// Weights are coords.Volume<F_dir> (the fine block's face area, uniform_cartesian.hpp:36-38);
+// the summation tree :155-162 is kept term for term (absent children contribute +0).
+__global__ void __launch_bounds__(kPrThreads)
+    flux_correct_kernel(const pb2_flxcor_region *__restrict__ regions,
+                        const Chunk *__restrict__ chunks, double *__restrict__ slab) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_flxcor_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+  const bool inc0 = r.dir != 0, inc1 = DIM > 1 && r.dir != 1, inc2 = DIM > 2 && r.dir != 2;
+  const uint32_t total = (uint32_t)r.ncomp * r.n[0] * r.n[1] * r.n[2];
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    const uint32_t e = ch.first_vec + u * kPrThreads + threadIdx.x;
+    if (e >= total) continue;
+    const int ci = e % r.n[0];
+    uint32_t t = e / r.n[0];
+    const int cj = t % r.n[1];
+    t /= r.n[1];
+    const int ck = t % r.n[2];
+    const int c = t / r.n[2];
+    // the box is one face thick along dir: tangential coarse steps are two fine faces
+    const int i = r.fs[0] + (inc0 ? 2 * ci : 0);
+    const int j = r.fs[1] + (inc1 ? 2 * cj : 0);
+    const int k = r.fs[2] + (inc2 ? 2 * ck : 0);
+    const double *f = r.fine + (int64_t)c * r.fine_stride_c;
+    double vol[2][2][2], terms[2][2][2];
+#pragma unroll
+    for (int ok = 0; ok < 2; ++ok)
+#pragma unroll
+      for (int oj = 0; oj < 2; ++oj)
+#pragma unroll
+        for (int oi = 0; oi < 2; ++oi) {
+          const bool on = (ok == 0 || inc2) && (oj == 0 || inc1) && (oi == 0 || inc0);
+          vol[ok][oj][oi] = on ? r.area : 0.0;
+          terms[ok][oj][oi] =
+              on ? vol[ok][oj][oi] * f[(int64_t)(k + ok) * r.fine_stride_k +
+                                       (int64_t)(j + oj) * r.fine_stride_j + (i + oi)]
+                 : 0.0;
+        }
+    const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                        ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+    const double val =
+        (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+         ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+        tvol;
+    if (r.coarse)
+      r.coarse[(int64_t)c * r.coarse_stride_c + (int64_t)(r.ds[2] + ck) * r.coarse_stride_k +
+               (int64_t)(r.ds[1] + cj) * r.coarse_stride_j + (r.ds[0] + ci)] = val;
+    else
+      slab[r.buf_off + e] = val;
+  }
+}
+
 } // namespace pb2
 
 using namespace pb2;
@@ -216,6 +272,62 @@ int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
   ProfScope prof(K_PROLONGATE, as_stream(stream));
   prolongate_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                       as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_flxcor_table_create(pb2_bnd_table **table, const pb2_flxcor_region *regions,
+                            int64_t n) {
+  PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
+  if (int rc = require_device()) return rc;
+  std::vector<Chunk> chunks;
+  int64_t elements = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    const pb2_flxcor_region &q = regions[r];
+    PB2_REQUIRE(q.dir >= 0 && q.dir < 3 && q.dir < q.ndim && q.n[q.dir] == 1,
+                "a flux-correction box is one face thick along its normal");
+    const int64_t total = (int64_t)q.ncomp * q.n[0] * q.n[1] * q.n[2];
+    PB2_REQUIRE(total >= 0 && total < (1ll << 31), "bad region extent");
+    elements += total;
+    for (int64_t v = 0; v < total; v += kPrThreads * kPrPerThread)
+      chunks.push_back(Chunk{static_cast<int32_t>(r), static_cast<uint32_t>(v)});
+  }
+  auto *t = new pb2_bnd_table();
+  t->kind = kFlxCor;
+  t->nregions = n;
+  t->nchunks = static_cast<int64_t>(chunks.size());
+  t->elements = elements;
+  t->d_regions = nullptr;
+  t->d_chunks = nullptr;
+  t->d_prores = nullptr;
+  t->d_flxcor = nullptr;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc(&t->d_flxcor, n * sizeof(pb2_flxcor_region));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(t->d_flxcor, regions, n * sizeof(pb2_flxcor_region),
+                     cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !chunks.empty())
+      e = cudaMemcpy(t->d_chunks, chunks.data(), chunks.size() * sizeof(Chunk),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error("flux-correction table upload failed: %s", cudaGetErrorString(e));
+      cudaFree(t->d_flxcor);
+      cudaFree(t->d_chunks);
+      delete t;
+      return PB2_ERR_CUDA;
+    }
+  }
+  *table = t;
+  return PB2_OK;
+}
+
+int pb2_flux_correct(const pb2_bnd_table *table, double *slab, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kFlxCor, "flux correction needs a flxcor table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_FLUX_CORRECT, as_stream(stream));
+  flux_correct_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                        as_stream(stream)>>>(table->d_flxcor, table->d_chunks, slab);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

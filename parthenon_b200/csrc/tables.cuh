@@ -7,7 +7,7 @@ namespace pb2 {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 
-enum TableKind { kBnd = 0, kCopy = 1, kProRes = 2 };
+enum TableKind { kBnd = 0, kCopy = 1, kProRes = 2, kFlxCor = 3 };
 
 struct DevRegion {
   double *var;       // array side (pack source / unpack destination / copy destination)
@@ -42,5 +42,6 @@ struct pb2_bnd_table {
   pb2::Chunk *d_chunks;
   // prores tables keep the API struct on device
   pb2_prores_region *d_prores;
+  pb2_flxcor_region *d_flxcor = nullptr;
 };
 

@@ -39,6 +39,31 @@ struct DivGeom {
   int64_t sj, sk, sc, sb;
 };
 
+// WeightedSumData (update.hpp:71-91) restricted to the GHOST cells of every block: the part of
+// the reference's full-extent passes that a fused interior update does not perform.  Needed on
+// multilevel meshes, where fine ghosts facing a coarser block are not refreshed by the stage's
+// exchange and so carry these values into the next stencil.
+__global__ void __launch_bounds__(256)
+    weighted_sum_ghost_kernel(const DivGeom g, const double *x, const double *y, double w1,
+                              double w2, double *z, int64_t total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t ncell = g.sc;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t bc = e / ncell; // (block, component)
+    int64_t t = e - bc * ncell;
+    const int i = (int)(t % g.n[0]);
+    t /= g.n[0];
+    const int j = (int)(t % g.n[1]);
+    const int k = (int)(t / g.n[1]);
+    const bool interior = i >= g.is[0] && i < g.is[0] + g.nx[0] && j >= g.is[1] &&
+                          j < g.is[1] + g.nx[1] && k >= g.is[2] && k < g.is[2] + g.nx[2];
+    if (interior) continue;
+    const int64_t b = bc / g.ncomp, c = bc - b * g.ncomp;
+    const int64_t p = b * g.sb + c * g.sc + (e - bc * ncell);
+    z[p] = w1 * x[p] + w2 * y[p];
+  }
+}
+
 // FluxDivergence<MeshData> update.cpp:63-86 + FluxDivHelper update.hpp:43-58
 __global__ void __launch_bounds__(256)
     flux_div_kernel(const DivGeom g, const double *__restrict__ fx,
@@ -109,6 +134,33 @@ int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, dou
   ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
   weighted_sum_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(x, y, w1, w2,
                                                                                  z, n);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_weighted_sum_ghosts(const pb2_pack_geom *pg, const double *x, const double *y, double w1,
+                            double w2, double *z, pb2_stream_t stream) {
+  PB2_REQUIRE(pg && x && y && z, "bad arguments");
+  if (int rc = require_device()) return rc;
+  DivGeom g;
+  g.nblocks = pg->nblocks;
+  g.ncomp = pg->ncomp;
+  g.ndim = pg->ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg->ndim;
+    g.nx[d] = sym ? 1 : pg->nx[d];
+    g.is[d] = sym ? 0 : pg->ng;
+    g.n[d] = sym ? 1 : pg->nx[d] + 2 * pg->ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg->block_stride;
+  const int64_t total = (int64_t)g.nblocks * g.ncomp * g.sc;
+  if (total == 0) return PB2_OK;
+  const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  weighted_sum_ghost_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, x, y, w1, w2, z, total);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -147,7 +147,10 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   a.out = mc1->Get("U").data();
   // only the bit-exact dataflow stores fluxes; the fast sweeps keep them in registers, so
   // the three flux arrays are never allocated (8.6 GB at 256^3, 69 GB at 512^3)
-  if (a.math == PB2_MATH_STRICT)
+  // ... and meshes with fine-coarse faces, whose face fluxes must exist to be corrected
+  Mesh *pm = mc0->GetMeshPointer();
+  const bool flxcor = pm->HasFineCoarseFaces();
+  if (a.math == PB2_MATH_STRICT || flxcor)
     for (int d = 0; d < a.geom.ndim; ++d) a.flux[d] = u.flux(d + 1);
   a.derived = mc1->Get("derived").data();
   a.beta = beta;
@@ -160,10 +163,19 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   // shipped on the communication stream while the interior blocks are advanced
   // (the local / nonlocal overlap of burgers_driver.cpp:106-119, without host polling).
   BvarsCache &bc = GetBvarsCache(mc1);
-  Mesh *pm = mc0->GetMeshPointer();
   const bool split = a.math == PB2_MATH_FAST && !pm->multilevel && bc.n_boundary > 0 &&
                      bc.n_interior > 0 && bc.plan.send_elements > 0;
-  if (split) {
+  if (flxcor) {
+    // CalculateFluxes -> flux correction -> FluxDivergence + update (burgers_driver.cpp:92-104)
+    PB2_CHECK(pb2_burgers_calculate_fluxes(&a, mc0->stream()));
+    FluxCorrection(mc0);
+    PB2_CHECK(pb2_burgers_update(&a, mc0->stream()));
+    // the reference's Average/UpdateIndependentData run over the full extents; ghosts that
+    // the exchange below does not refresh (fine ghosts facing a coarser block: the stage list
+    // has no ProlongateBounds) carry beta*mc0 + (1-beta)*base into the next stencil
+    PB2_CHECK(pb2_weighted_sum_ghosts(&a.geom, a.u, a.base, beta, 1.0 - beta, a.out,
+                                      mc0->stream()));
+  } else if (split) {
     a.block_ids = bc.ids_boundary.get<int32_t>();
     a.num_block_ids = bc.n_boundary;
     PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));

@@ -37,6 +37,10 @@ struct IndexBox {
 };
 IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeType ir_type,
                      bool prores);
+// the same for the face flux (Metadata::Flux, element F_dir with dir the direction of the face
+// offset; GetFluxCorrectionElements bnd_info.cpp:71-83): one face thick along dir.  A block
+// with a coarser neighbour gets the box in its coarse index space (bnd_info.cpp:124-125).
+IndexBox CalcIndicesFlux(const NeighborBlock &nb, const MeshBlock *pmb);
 
 // one boundary channel as the host sees it (pure topology: testable without a device)
 struct Channel {
@@ -98,6 +102,16 @@ struct BvarsCache {
   std::map<int, uint64_t> consumed_generation; // by sender partition
   // traffic accounting for bench.py: Reals moved by the last exchange
   int64_t elements_local = 0, elements_nonlocal = 0;
+
+  // flux correction at fine-coarse faces (flxcor_send / flxcor_recv), built on first use:
+  // fused restrict+deliver for same-device channels, restrict-into-slab + unpack for the rest
+  bool flxcor_built = false;
+  pb2_bnd_table *flxcor_local = nullptr, *flxcor_pack = nullptr, *flxcor_unpack = nullptr;
+  std::vector<int64_t> flxcor_send_off, flxcor_recv_off; // [npeers + 1]
+  int64_t flxcor_send_elements = 0, flxcor_recv_elements = 0, flxcor_local_elements = 0;
+  DeviceBuffer flxcor_send_slab, flxcor_recv_slab;
+  pb2_event_t flxcor_packed = nullptr, flxcor_received = nullptr;
+  bool flxcor_in_flight = false;
 };
 
 void BuildBoundaryBuffers(std::shared_ptr<MeshData<Real>> &md);
@@ -128,11 +142,13 @@ inline TaskStatus SetBoundaries(std::shared_ptr<MeshData<Real>> &md) {
   return SetBounds<BoundaryType::any>(md);
 }
 // flux corrections only exist at fine-coarse faces; on meshes without them these complete
-// immediately (boundary_communication.cpp:454-461)
+// immediately (boundary_communication.cpp:454-461).  FluxCorrection(md) is Send + Set in one
+// call for fused stages.
 TaskStatus StartReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
 TaskStatus LoadAndSendFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
 TaskStatus ReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
 TaskStatus SetFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
+void FluxCorrection(MeshData<Real> *md);
 
 // physical boundaries: all supported meshes are periodic, handled as neighbour exchange
 // (bvals/boundary_conditions.cpp:197 is a no-op for periodic)

@@ -202,6 +202,7 @@ class Mesh {
   void ReduceHistory(std::vector<Real> &vals);
   // true if some block of this rank has a neighbour on another level
   bool HasFineCoarseFaces() const;
+  mutable int fine_coarse_faces_ = -1; // cached answer (static meshes)
 
   pb2_comm *comm = nullptr; // NCCL communicator (nranks > 1), owned by the creator
   // test knob: split this rank's blocks over `virtual_ranks` pretend devices so the

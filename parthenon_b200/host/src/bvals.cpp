@@ -69,6 +69,37 @@ IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeTy
   return box;
 }
 
+// bnd_info.cpp:105-252 with flux = true and el = F_dir: the box is the shared face itself
+// (:207-211), tangentially the whole face of a finer sender (coarse index space) or the half
+// (quarter in 3-D) of a coarser receiver's face that the finer neighbour abuts (:173-192)
+IndexBox CalcIndicesFlux(const NeighborBlock &nb, const MeshBlock *pmb) {
+  const LogicalLocation &loc = pmb->loc;
+  const bool use_coarse = nb.loc.level < loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int coarse_fac = nb.loc.level > loc.level ? 2 : 1;
+  IndexBox box;
+  for (int d = 0; d < 3; ++d) {
+    const bool not_sym = !pmb->block_size.symmetry_[d];
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior);
+    int &s = box.s[d], &e = box.e[d];
+    if (nb.offsets[d] == 0) {
+      s = b.s;
+      e = b.e;
+      if (loc.level < nb.origin_loc.level && not_sym) {
+        const int extra = (b.e - b.s + 1) - pmb->block_size.nx_[d] / coarse_fac;
+        const bool upper_half = ((nb.origin_loc.lx[d] % 2) + 2) % 2 == 1;
+        s += upper_half ? extra : 0;
+        e -= upper_half ? 0 : extra;
+      }
+    } else if (nb.offsets[d] > 0) {
+      s = e = b.e + (not_sym ? 1 : 0); // upper face: index ie + 1 of the cell-aligned array
+    } else {
+      s = e = b.s;
+    }
+  }
+  return box;
+}
+
 // ---------------------------------------------------------------------------------------
 // channel plan (pure topology)
 // ---------------------------------------------------------------------------------------
@@ -202,6 +233,11 @@ void BvarsCache::Clear() {
   pb2_bnd_table_destroy(pack);
   pb2_bnd_table_destroy(unpack);
   copy_local = pack = unpack = nullptr;
+  pb2_bnd_table_destroy(flxcor_local);
+  pb2_bnd_table_destroy(flxcor_pack);
+  pb2_bnd_table_destroy(flxcor_unpack);
+  flxcor_local = flxcor_pack = flxcor_unpack = nullptr;
+  flxcor_built = false;
   built_generation = 0;
 }
 
@@ -581,18 +617,236 @@ PB2_INSTANTIATE(BoundaryType::local)
 PB2_INSTANTIATE(BoundaryType::nonlocal)
 #undef PB2_INSTANTIATE
 
+// ---------------------------------------------------------------------------------------
+// flux correction (flxcor_send / flxcor_recv of the reference, boundary_communication.cpp:
+// 454-461; region selection loop_utils.hpp:145-160)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+int FaceDir(const int off[3]) { // CellCentOffsets::IsFace
+  const int nz = (off[0] != 0) + (off[1] != 0) + (off[2] != 0);
+  if (nz != 1) return -1;
+  return off[0] != 0 ? 0 : (off[1] != 0 ? 1 : 2);
+}
+
+struct FlxChannel {
+  int seg;
+  int sender_gid, receiver_gid, var, offset_index;
+  pb2_flxcor_region send{}; // sender side (restrict into slab)
+  pb2_bnd_region recv{};    // receiver side (unpack from slab)
+  int64_t n = 0;
+};
+
+void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
+  Mesh *pm = md->GetMeshPointer();
+  const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
+  const int npeers = V > 1 ? V * V : pm->nranks;
+  std::vector<Variable *> vars = md->GetVariablesByFlag({Metadata::WithFluxes});
+  std::vector<pb2_flxcor_region> local;
+  std::vector<FlxChannel> send, recv;
+  c.flxcor_local_elements = 0;
+  for (auto &pmb : md->GetBlockList()) {
+    const int my_vr = pm->VirtualRankOf(pmb->gid);
+    for (auto &nb : pmb->neighbors) {
+      const int dir = FaceDir(nb.offsets);
+      if (dir < 0 || dir >= pm->ndim) continue;
+      const int nb_vr = nb.rank == pm->my_rank ? pm->VirtualRankOf(nb.gid) : 0;
+      const bool is_local = nb.rank == pm->my_rank && nb_vr == my_vr;
+      const IndexBox box = CalcIndicesFlux(nb, pmb.get());
+      for (size_t iv = 0; iv < vars.size(); ++iv) {
+        Variable &v = *vars[iv];
+        if (nb.loc.level == pmb->loc.level + 1) {
+          // this block is the coarser RECEIVER of nb's restricted fluxes
+          if (is_local) {
+            const MeshBlock *sb = pm->block_list[nb.lid].get();
+            const NeighborBlock *q = MatchingNeighbor(sb, pmb->gid, nb.offsets);
+            PARTHENON_REQUIRE(q != nullptr, "no matching flux-correction sender");
+            const IndexBox sbox = CalcIndicesFlux(*q, sb);
+            Variable &sv = ContainerOf(md, sb)->Get(v.label());
+            pb2_flxcor_region r{};
+            r.fine = sv.flux(dir + 1) + sb->pack_index * sv.block_stride;
+            r.coarse = v.flux(dir + 1) + pmb->pack_index * v.block_stride;
+            r.dir = dir;
+            r.ndim = pm->ndim;
+            for (int d = 0; d < 3; ++d) {
+              PARTHENON_REQUIRE(sbox.n(d) == box.n(d), "flux-correction extents differ");
+              // coarse index -> fine index of the first child face (pr_ops.hpp:129-131)
+              const int cis = sb->c_cellbounds.Bounds(d, IndexDomain::interior).s;
+              const int fis = sb->cellbounds.Bounds(d, IndexDomain::interior).s;
+              r.fs[d] = sb->block_size.symmetry_[d] ? fis : (sbox.s[d] - cis) * 2 + fis;
+              r.ds[d] = box.s[d];
+              r.n[d] = box.n(d);
+            }
+            r.ncomp = v.NumComponents();
+            r.fine_stride_j = sv.ni;
+            r.fine_stride_k = sv.ni * sv.nj;
+            r.fine_stride_c = static_cast<int32_t>(sv.comp_stride);
+            r.coarse_stride_j = v.ni;
+            r.coarse_stride_k = v.ni * v.nj;
+            r.coarse_stride_c = static_cast<int32_t>(v.comp_stride);
+            r.status = PB2_REGION_ALLOCATED;
+            const auto dx = sb->coords.Dx();
+            r.area = dir == 0 ? dx[1] * dx[2] : (dir == 1 ? dx[0] * dx[2] : dx[0] * dx[1]);
+            c.flxcor_local_elements += static_cast<int64_t>(r.ncomp) * r.n[0] * r.n[1] * r.n[2];
+            local.push_back(r);
+          } else {
+            FlxChannel ch;
+            ch.seg = V > 1 ? nb_vr * V + my_vr : nb.rank;
+            ch.sender_gid = nb.gid;
+            ch.receiver_gid = pmb->gid;
+            ch.var = static_cast<int>(iv);
+            ch.offset_index = OffsetIndexOf(-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]);
+            pb2_bnd_region &r = ch.recv;
+            r.var = v.flux(dir + 1) + pmb->pack_index * v.block_stride;
+            r.stride_j = v.ni;
+            r.stride_k = v.ni * v.nj;
+            r.stride_c = static_cast<int32_t>(v.comp_stride);
+            for (int d = 0; d < 3; ++d) {
+              r.s[d] = box.s[d];
+              r.n[d] = box.n(d);
+            }
+            r.ncomp = v.NumComponents();
+            r.flag_slot = -1;
+            r.status = PB2_REGION_ALLOCATED | PB2_REGION_BUF_ALLOCATED;
+            ch.n = box.size() * r.ncomp;
+            recv.push_back(ch);
+          }
+        } else if (nb.loc.level == pmb->loc.level - 1 && !is_local) {
+          // this block is the finer SENDER towards another device
+          FlxChannel ch;
+          ch.seg = V > 1 ? my_vr * V + nb_vr : nb.rank;
+          ch.sender_gid = pmb->gid;
+          ch.receiver_gid = nb.gid;
+          ch.var = static_cast<int>(iv);
+          ch.offset_index = nb.OffsetIndex();
+          pb2_flxcor_region &r = ch.send;
+          r.fine = v.flux(dir + 1) + pmb->pack_index * v.block_stride;
+          r.coarse = nullptr;
+          r.dir = dir;
+          r.ndim = pm->ndim;
+          for (int d = 0; d < 3; ++d) {
+            const int cis = pmb->c_cellbounds.Bounds(d, IndexDomain::interior).s;
+            const int fis = pmb->cellbounds.Bounds(d, IndexDomain::interior).s;
+            r.fs[d] = pmb->block_size.symmetry_[d] ? fis : (box.s[d] - cis) * 2 + fis;
+            r.ds[d] = 0;
+            r.n[d] = box.n(d);
+          }
+          r.ncomp = v.NumComponents();
+          r.fine_stride_j = v.ni;
+          r.fine_stride_k = v.ni * v.nj;
+          r.fine_stride_c = static_cast<int32_t>(v.comp_stride);
+          r.status = PB2_REGION_ALLOCATED;
+          const auto dx = pmb->coords.Dx();
+          r.area = dir == 0 ? dx[1] * dx[2] : (dir == 1 ? dx[0] * dx[2] : dx[0] * dx[1]);
+          ch.n = box.size() * r.ncomp;
+          send.push_back(ch);
+        }
+      }
+    }
+  }
+  // both sides order a peer segment by the same key => identical slab offsets, no handshake
+  auto layout = [&](std::vector<FlxChannel> &chs, std::vector<int64_t> &seg_off, int64_t &total,
+                    bool is_send) {
+    std::stable_sort(chs.begin(), chs.end(), [](const FlxChannel &a, const FlxChannel &b) {
+      return std::make_tuple(a.seg, a.sender_gid, a.receiver_gid, a.var, a.offset_index) <
+             std::make_tuple(b.seg, b.sender_gid, b.receiver_gid, b.var, b.offset_index);
+    });
+    std::vector<int64_t> seg_size(npeers, 0);
+    for (auto &ch : chs) {
+      (is_send ? ch.send.buf_off : ch.recv.buf_off) = seg_size[ch.seg];
+      seg_size[ch.seg] += ch.n + (ch.n & 1);
+    }
+    seg_off.assign(npeers + 1, 0);
+    for (int p = 0; p < npeers; ++p) seg_off[p + 1] = seg_off[p] + seg_size[p];
+    for (auto &ch : chs) (is_send ? ch.send.buf_off : ch.recv.buf_off) += seg_off[ch.seg];
+    total = seg_off[npeers];
+  };
+  layout(send, c.flxcor_send_off, c.flxcor_send_elements, true);
+  layout(recv, c.flxcor_recv_off, c.flxcor_recv_elements, false);
+  PARTHENON_REQUIRE(c.flxcor_send_elements + c.flxcor_recv_elements == 0 ||
+                        pm->DefaultNumPartitions() == 1,
+                    "inter-device flux correction needs one MeshData per rank");
+  std::vector<pb2_flxcor_region> packs;
+  std::vector<pb2_bnd_region> unpacks;
+  for (auto &ch : send) packs.push_back(ch.send);
+  for (auto &ch : recv) unpacks.push_back(ch.recv);
+  PB2_CHECK(pb2_flxcor_table_create(&c.flxcor_local, local.data(), static_cast<int64_t>(local.size())));
+  PB2_CHECK(pb2_flxcor_table_create(&c.flxcor_pack, packs.data(), static_cast<int64_t>(packs.size())));
+  PB2_CHECK(pb2_bnd_table_create(&c.flxcor_unpack, unpacks.data(), static_cast<int64_t>(unpacks.size())));
+  if (c.flxcor_send_elements > 0)
+    c.flxcor_send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.flxcor_send_elements), md->stream());
+  if (c.flxcor_recv_elements > 0)
+    c.flxcor_recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.flxcor_recv_elements), md->stream());
+  if (!c.flxcor_packed) {
+    PB2_CHECK(pb2_event_create(&c.flxcor_packed));
+    PB2_CHECK(pb2_event_create(&c.flxcor_received));
+  }
+  c.flxcor_built = true;
+}
+
+BvarsCache &FlxCache(MeshData<Real> *md) {
+  BvarsCache &c = GetBvarsCache(md);
+  if (!c.flxcor_built) RebuildFluxCorrection(md, c);
+  return c;
+}
+
+// SendBoundBufs<flxcor_send>: restrict the fine face fluxes that face another device into the
+// peer slabs and ship them
+void SendFluxCorrections(MeshData<Real> *md) {
+  Mesh *pm = md->GetMeshPointer();
+  if (!pm->multilevel) return;
+  BvarsCache &c = FlxCache(md);
+  if (c.flxcor_send_elements + c.flxcor_recv_elements == 0) return;
+  pb2_stream_t st = md->stream(), cs = pm->comm_stream;
+  PB2_CHECK(pb2_flux_correct(c.flxcor_pack, c.flxcor_send_slab.get<Real>(), st));
+  PB2_CHECK(pb2_event_record(c.flxcor_packed, st));
+  PB2_CHECK(pb2_stream_wait_event(cs, c.flxcor_packed));
+  if (pm->nranks > 1) {
+    PARTHENON_REQUIRE(pm->comm != nullptr, "multi-rank mesh without a communicator");
+    PB2_CHECK(pb2_comm_exchange(pm->comm, c.flxcor_send_slab.get<Real>(), c.flxcor_send_off.data(),
+                                c.flxcor_recv_slab.get<Real>(), c.flxcor_recv_off.data(), cs));
+  } else {
+    PB2_CHECK(pb2_memcpy_d2d(c.flxcor_recv_slab.get(), c.flxcor_send_slab.get(),
+                             sizeof(Real) * static_cast<size_t>(c.flxcor_send_elements), cs));
+  }
+  PB2_CHECK(pb2_event_record(c.flxcor_received, cs));
+  c.flxcor_in_flight = true;
+}
+
+// SetBounds<flxcor_recv>: the coarser block's face flux is overwritten by the restricted one
+void SetFluxCorrectionsImpl(MeshData<Real> *md) {
+  Mesh *pm = md->GetMeshPointer();
+  if (!pm->multilevel) return;
+  BvarsCache &c = FlxCache(md);
+  pb2_stream_t st = md->stream();
+  PB2_CHECK(pb2_flux_correct(c.flxcor_local, nullptr, st));
+  if (c.flxcor_in_flight) {
+    PB2_CHECK(pb2_stream_wait_event(st, c.flxcor_received));
+    PB2_CHECK(pb2_unpack(c.flxcor_unpack, c.flxcor_recv_slab.get<Real>(), nullptr, st));
+    c.flxcor_in_flight = false;
+  }
+}
+
+} // namespace
+
 TaskStatus StartReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &) {
-  return TaskStatus::complete;
+  return TaskStatus::complete; // receives are posted with the sends inside one NCCL group
 }
 TaskStatus LoadAndSendFluxCorrections(std::shared_ptr<MeshData<Real>> &md) {
-  PARTHENON_REQUIRE(!md->GetMeshPointer()->HasFineCoarseFaces(),
-                    "flux correction at fine-coarse faces is not implemented yet");
+  SendFluxCorrections(md.get());
   return TaskStatus::complete;
 }
 TaskStatus ReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &) {
+  return TaskStatus::complete; // completion is a stream-side event wait in SetFluxCorrections
+}
+TaskStatus SetFluxCorrections(std::shared_ptr<MeshData<Real>> &md) {
+  SetFluxCorrectionsImpl(md.get());
   return TaskStatus::complete;
 }
-TaskStatus SetFluxCorrections(std::shared_ptr<MeshData<Real>> &) { return TaskStatus::complete; }
+void FluxCorrection(MeshData<Real> *md) {
+  SendFluxCorrections(md);
+  SetFluxCorrectionsImpl(md);
+}
 
 TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &) {
   return TaskStatus::complete; // periodic: filled by the neighbour exchange

@@ -414,10 +414,14 @@ void Mesh::ReduceHistory(std::vector<Real> &vals) {
 }
 
 bool Mesh::HasFineCoarseFaces() const {
-  for (auto &pmb : block_list)
-    for (auto &nb : pmb->neighbors)
-      if (nb.loc.level != pmb->loc.level) return true;
-  return false;
+  if (!multilevel) return false;
+  if (fine_coarse_faces_ < 0) {
+    fine_coarse_faces_ = 0;
+    for (auto &pmb : block_list)
+      for (auto &nb : pmb->neighbors)
+        if (nb.loc.level != pmb->loc.level) fine_coarse_faces_ = 1;
+  }
+  return fine_coarse_faces_ == 1;
 }
 
 int Mesh::VirtualRankOf(int gid) const {

@@ -145,6 +145,51 @@ def test_multilevel_exchange_matches_oracle():
         assert np.array_equal(sim.get_field("base", "U"), Uref)
 
 
+MULTILEVEL = [("burgers_s16_b8_l2_weno5", (16, 16, 16), (8, 8, 8), 3),
+              ("burgers_s64_b8_l3_2d_weno5", (64, 64, 1), (8, 8, 1), 2)]
+
+
+def multilevel_sim(name, nx_mesh, nx_block, ndim, math, fused, extra=None):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    leaves, nrb = H.leaves_from_bounds(g["bounds"], nx_mesh, nx_block)
+    ov = deck_overrides(ndim, nx_block, 4, nrb, refinement="static")
+    ov.update({"burgers/num_scalars": 1, "burgers/recon": "weno5", "pb2/math": math,
+               "pb2/fused_stage": "true" if fused else "false"})
+    if extra:
+        ov.update(extra)
+    return g, host.Simulation(overrides=ov, leaves=leaves)
+
+
+@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 3}])
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name,nx_mesh,nx_block,ndim", MULTILEVEL)
+def test_multilevel_strict_cycles_bit_exact_vs_reference_dumps(name, nx_mesh, nx_block, ndim,
+                                                               fused, extra):
+    """static-refinement runs of the reference (3-D two levels, 2-D three levels): ghost fill
+    with restriction / prolongation at cycle 0, then two cycles with flux correction at the
+    fine-coarse faces — bit-exact, for the fused and the reference-shaped task list, through
+    the same-device path and (virtual ranks) the slab path"""
+    g, sim = multilevel_sim(name, nx_mesh, nx_block, ndim, "strict", fused, extra)
+    sim.pre_execute()
+    assert sim.dt == g["dts"][0]
+    assert np.array_equal(sim.get_field("base", "U"), g["U_0"])
+    for c in (1, 2):
+        sim.cycle()
+        assert sim.time == g["times"][c]
+        assert np.array_equal(sim.get_field("base", "U"), g[f"U_{c}"]), f"cycle {c}"
+
+
+@pytest.mark.parametrize("name,nx_mesh,nx_block,ndim", MULTILEVEL)
+def test_multilevel_fast_cycles_within_tolerance(name, nx_mesh, nx_block, ndim):
+    g, sim = multilevel_sim(name, nx_mesh, nx_block, ndim, "fast", True)
+    sim.pre_execute()
+    for c in (1, 2):
+        sim.cycle()
+        ref = g[f"U_{c}"]
+        err = np.abs(sim.get_field("base", "U") - ref).max() / np.abs(ref).max()
+        assert err <= TOL, (c, err)
+
+
 def test_full_block_shape_conservation_and_idempotence():
     """size-independent properties at the benchmark's block shape (128^3 mesh, 32^3 blocks,
     11 components): the flux-form update conserves every component's total to rounding, and a

@@ -294,6 +294,104 @@ def test_restrict_prolongate_multilevel():
     assert np.array_equal(Ud.cpu().numpy(), Uref)
 
 
+@pytest.mark.parametrize("ndim,nx,nrb,refine", [
+    (3, (8, 8, 8), 2, {(0, 0, 0)}),
+    (3, (8, 4, 6), 2, {(1, 0, 1)}),
+    (2, (8, 8, 1), 4, {(1, 1, 0), (2, 1, 0)}),
+])
+def test_flux_correct_multilevel(ndim, nx, nrb, refine):
+    """pb2_flux_correct (restrict the finer block's face fluxes straight into the coarser
+    block's flux array, or into a slab + pb2_unpack) against the oracle, bit-exact."""
+    ng, ncomp = 2, 3
+    if ndim == 3:
+        leaves = H.refined_leaves(nrb, refine)
+    else:
+        rl = int(np.log2(nrb))
+        leaves = []
+        for j in range(nrb):
+            for i in range(nrb):
+                if (i, j, 0) in refine:
+                    leaves += [(rl + 1, 2 * i + di, 2 * j + dj, 0) for dj in range(2) for di in range(2)]
+                else:
+                    leaves.append((rl, i, j, 0))
+        leaves = np.array(leaves, dtype=np.int32)
+    m = oracle.Mesh(ndim, nx[:ndim], ng, (nrb,) * ndim, leaves=leaves)
+    assert m.multilevel
+    F = [rand_field(m, ncomp, 11 + d) for d in range(3)]
+    Fref = [f.copy() for f in F]
+    moved = m.flux_correct(Fref)
+    assert moved > 0 and any(not np.array_equal(a, b) for a, b in zip(F, Fref))
+
+    lvl = [m.block_loc(b)[0] for b in range(m.nblocks)]
+    sj, sk, sc = H.strides(m.dims)
+    dx, _ = H.block_dx(m)
+    is_ = [ng if d < ndim else 0 for d in range(3)]
+
+    def regions(Fd, slab_mode):
+        regs, unpacks, off = [], [], 0
+        for b in range(m.nblocks):
+            for n, nb in enumerate(m.neighbors(b)):
+                gid, nlvl, o = nb[0], nb[1], nb[2:]
+                if sum(1 for x in o if x) != 1 or nlvl != lvl[b] + 1:
+                    continue
+                dir_ = [i for i, x in enumerate(o) if x][0]
+                rs, re = m.calc_indices_flux(b, n)  # receiver box (fine index space of b)
+                sn = [q for q, snb in enumerate(m.neighbors(gid))
+                      if snb[0] == b and snb[2:] == tuple(-x for x in o)][0]
+                ss, se = m.calc_indices_flux(gid, sn)  # sender box (coarse index space)
+                ext = [re[d] - rs[d] + 1 for d in range(3)]
+                assert ext == [se[d] - ss[d] + 1 for d in range(3)] and ext[dir_] == 1
+                r = capi.FlxCorRegion()
+                r.fine = Fd[dir_].data_ptr() + 8 * gid * ncomp * sc
+                r.coarse = None if slab_mode else Fd[dir_].data_ptr() + 8 * b * ncomp * sc
+                r.buf_off = off
+                r.dir, r.ndim = dir_, ndim
+                r.fs[:] = [(ss[d] - is_[d]) * 2 + is_[d] if d < ndim else 0 for d in range(3)]
+                r.ds[:] = rs
+                r.n[:] = ext
+                r.ncomp = ncomp
+                r.fine_stride_j, r.fine_stride_k, r.fine_stride_c = sj, sk, sc
+                r.coarse_stride_j, r.coarse_stride_k, r.coarse_stride_c = sj, sk, sc
+                r.status = capi.REGION_ALLOCATED
+                a = [dx[gid, 1] * dx[gid, 2], dx[gid, 0] * dx[gid, 2], dx[gid, 0] * dx[gid, 1]]
+                r.area = a[dir_]
+                regs.append(r)
+                u = capi.BndRegion()
+                u.var = Fd[dir_].data_ptr() + 8 * b * ncomp * sc
+                u.buf_off = off
+                u.s[:] = rs
+                u.n[:] = ext
+                u.ncomp = ncomp
+                u.stride_j, u.stride_k, u.stride_c = sj, sk, sc
+                u.flag_slot = -1
+                u.status = capi.REGION_ALLOCATED | capi.REGION_BUF_ALLOCATED
+                unpacks.append(u)
+                off += ncomp * ext[0] * ext[1] * ext[2]
+        return regs, unpacks, off
+
+    L = capi.lib()
+    # fused same-device delivery
+    Fd = [torch.from_numpy(f).to(DEV) for f in F]
+    regs, _, total = regions(Fd, False)
+    assert total == moved
+    t = capi.Table(regs, "flxcor")
+    assert t.elements == moved
+    capi.check(L.pb2_flux_correct(t.h, None, None))
+    torch.cuda.synchronize()
+    for d in range(3):
+        assert np.array_equal(Fd[d].cpu().numpy(), Fref[d]), d
+    # slab path: restrict into a buffer, unpack on the "other device"
+    Fd = [torch.from_numpy(f).to(DEV) for f in F]
+    regs, unpacks, total = regions(Fd, True)
+    slab = torch.full((total,), float("nan"), dtype=torch.float64, device=DEV)
+    t, tu = capi.Table(regs, "flxcor"), capi.Table(unpacks, "bnd")
+    capi.check(L.pb2_flux_correct(t.h, slab.data_ptr(), None))
+    capi.check(L.pb2_unpack(tu.h, slab.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    for d in range(3):
+        assert np.array_equal(Fd[d].cpu().numpy(), Fref[d]), d
+
+
 def test_weighted_sum_and_flux_div():
     n = 100003
     x = torch.randn(n, dtype=torch.float64, device=DEV)
