@@ -79,6 +79,22 @@ def lib():
         L.orc_burgers_stage.argtypes = [C.c_void_p, C.c_int]
         L.orc_burgers_history.argtypes = [C.c_void_p, dp]
         L.orc_burgers_cycle.argtypes = [C.c_void_p]
+        L.orc_advection_create.restype = C.c_void_p
+        L.orc_advection_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, dp,
+                                           C.c_double]
+        L.orc_advection_destroy.argtypes = [C.c_void_p]
+        L.orc_advection_U.restype = dp
+        L.orc_advection_U.argtypes = [C.c_void_p]
+        L.orc_advection_flux.restype = dp
+        L.orc_advection_flux.argtypes = [C.c_void_p, C.c_int]
+        L.orc_advection_init.argtypes = [C.c_void_p]
+        L.orc_advection_step.argtypes = [C.c_void_p]
+        L.orc_advection_stage.argtypes = [C.c_void_p, C.c_int]
+        L.orc_advection_calculate_fluxes.argtypes = [C.c_void_p, dp]
+        L.orc_advection_dt.restype = C.c_double
+        L.orc_advection_dt.argtypes = [C.c_void_p]
+        L.orc_advection_time.restype = C.c_double
+        L.orc_advection_time.argtypes = [C.c_void_p]
         L.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
 
@@ -240,6 +256,54 @@ class Burgers:
         o = np.zeros(8)
         lib().orc_burgers_history(self.h, _dp(o))
         return o
+
+
+class Advection:
+    """example/advection with a constant velocity; profile 'smooth_gaussian' | 'hard_sphere'"""
+
+    PROFILES = {"smooth_gaussian": 1, "hard_sphere": 2}
+
+    def __init__(self, mesh, vec_size=1, profile="hard_sphere", amp=1e-6, v=(1.0, 1.0, 1.0),
+                 cfl=0.45):
+        self.mesh = mesh
+        self.ncomp = vec_size
+        self._v = np.array(v, dtype=np.float64)
+        self.h = lib().orc_advection_create(mesh.h, vec_size, self.PROFILES[profile], amp,
+                                            _dp(self._v), cfl)
+
+    def __del__(self):
+        try:
+            lib().orc_advection_destroy(self.h)
+        except Exception:
+            pass
+
+    def _view(self, p):
+        shape = (self.mesh.nblocks, self.ncomp) + self.mesh.dims
+        return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape)
+
+    @property
+    def U(self):
+        return self._view(lib().orc_advection_U(self.h))
+
+    def flux(self, d):
+        return self._view(lib().orc_advection_flux(self.h, d))
+
+    def init(self):
+        lib().orc_advection_init(self.h)
+
+    def step(self):
+        lib().orc_advection_step(self.h)
+
+    def calculate_fluxes(self, U):
+        lib().orc_advection_calculate_fluxes(self.h, _dp(U))
+
+    @property
+    def dt(self):
+        return lib().orc_advection_dt(self.h)
+
+    @property
+    def time(self):
+        return lib().orc_advection_time(self.h)
 
 
 def weno5z(q):

@@ -1118,9 +1118,9 @@ static double estimate_timestep(const OrcBurgers *st, const double *U) {
 }
 
 /* FluxDivergence update.cpp:63-86 with FluxDivHelper update.hpp:43-58 */
-static void flux_divergence(OrcBurgers *st) {
-  const OrcMesh *m = st->m;
-  const int nc = st->ncomp, ndim = m->ndim;
+static void flux_divergence_generic(const OrcMesh *m, int nc, double *const flux[3],
+                                    double *dUdt) {
+  const int ndim = m->ndim;
   const size_t sj = (size_t)m->n[0], sk = (size_t)m->n[0] * m->n[1];
 #pragma omp parallel for collapse(2) schedule(static)
   for (int b = 0; b < m->nblocks; ++b)
@@ -1133,12 +1133,15 @@ static void flux_divergence(OrcBurgers *st) {
         for (int j = m->is[1]; j <= m->ie[1]; ++j)
           for (int i = m->is[0]; i <= m->ie[0]; ++i) {
             const size_t p = fidx(m, nc, b, l, k, j, i);
-            double du = (a1 * st->flux[0][p + 1] - a1 * st->flux[0][p]);
-            if (ndim >= 2) du += (a2 * st->flux[1][p + sj] - a2 * st->flux[1][p]);
-            if (ndim == 3) du += (a3 * st->flux[2][p + sk] - a3 * st->flux[2][p]);
-            st->dUdt[p] = -du / vol;
+            double du = (a1 * flux[0][p + 1] - a1 * flux[0][p]);
+            if (ndim >= 2) du += (a2 * flux[1][p + sj] - a2 * flux[1][p]);
+            if (ndim == 3) du += (a3 * flux[2][p + sk] - a3 * flux[2][p]);
+            dUdt[p] = -du / vol;
           }
     }
+}
+static void flux_divergence(OrcBurgers *st) {
+  flux_divergence_generic(st->m, st->ncomp, st->flux, st->dUdt);
 }
 
 /* WeightedSumData update.hpp:71-91: z = w1*x + w2*y over the ENTIRE extents */
@@ -1237,6 +1240,152 @@ void orc_burgers_history(const OrcBurgers *st, double out[8]) {
           }
         out[oct++] = result;
       }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* example/advection (constant velocity, v_const = true): advection_package.cpp,
+ * advection_driver.cpp, parthenon_app_inputs.cpp.  One field "advected" of vec_size
+ * components; fill_derived = false. */
+struct OrcAdvection {
+  const OrcMesh *m;
+  int ncomp, profile;
+  double amp, v[3], cfl;
+  size_t nfield;
+  double *U, *U1, *dUdt, *flux[3], *Uc;
+  double dt, time, allowed_dt;
+  int ncycle;
+};
+
+OrcAdvection *orc_advection_create(const OrcMesh *m, int vec_size, int profile, double amp,
+                                   const double v[3], double cfl) {
+  OrcAdvection *s = (OrcAdvection *)calloc(1, sizeof(OrcAdvection));
+  s->m = m;
+  s->ncomp = vec_size;
+  s->profile = profile;
+  s->amp = amp;
+  for (int d = 0; d < 3; ++d) s->v[d] = v[d];
+  s->cfl = cfl;
+  size_t ncell = (size_t)m->n[0] * m->n[1] * m->n[2];
+  s->nfield = (size_t)m->nblocks * s->ncomp * ncell;
+  s->U = (double *)calloc(s->nfield, sizeof(double));
+  s->U1 = (double *)calloc(s->nfield, sizeof(double));
+  s->dUdt = (double *)calloc(s->nfield, sizeof(double));
+  for (int d = 0; d < 3; ++d) s->flux[d] = (double *)calloc(s->nfield, sizeof(double));
+  if (m->multilevel)
+    s->Uc = (double *)calloc((size_t)m->nblocks * s->ncomp * m->cn[0] * m->cn[1] * m->cn[2],
+                             sizeof(double));
+  s->dt = DBL_MAX;
+  return s;
+}
+void orc_advection_destroy(OrcAdvection *s) {
+  if (!s) return;
+  free(s->U);
+  free(s->U1);
+  free(s->dUdt);
+  for (int d = 0; d < 3; ++d) free(s->flux[d]);
+  free(s->Uc);
+  free(s);
+}
+double *orc_advection_U(OrcAdvection *s) { return s->U; }
+double *orc_advection_flux(OrcAdvection *s, int dir) { return s->flux[dir]; }
+double orc_advection_dt(const OrcAdvection *s) { return s->dt; }
+double orc_advection_time(const OrcAdvection *s) { return s->time; }
+
+/* ProblemGenerator parthenon_app_inputs.cpp:40-100: profiles smooth_gaussian (1) and
+ * hard_sphere (2), interior cells */
+static void advection_ic(OrcAdvection *st) {
+  const OrcMesh *m = st->m;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < st->ncomp; ++n)
+      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+        for (int j = m->is[1]; j <= m->ie[1]; ++j)
+          for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+            const double x = xc(blk, 0, i), y = xc(blk, 1, j), z = xc(blk, 2, k);
+            const double rsq = x * x + y * y + z * z;
+            double q;
+            if (st->profile == 1)
+              q = 1. + st->amp * exp(-100.0 * rsq);
+            else
+              q = (rsq < 0.15 * 0.15 ? 1.0 : 0.0);
+            st->U[fidx(m, st->ncomp, b, n, k, j, i)] = q;
+          }
+  }
+}
+
+/* CalculateFluxes advection_package.cpp:540-646 with DonorCellX1/2/3
+ * (reconstruct/dc_inline.hpp:31-71): upwind cell value times the constant velocity */
+void orc_advection_calculate_fluxes(OrcAdvection *st, const double *U) {
+  const OrcMesh *m = st->m;
+  const int nc = st->ncomp, ndim = m->ndim;
+  const size_t str[3] = {1, (size_t)m->n[0], (size_t)m->n[0] * m->n[1]};
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int n = 0; n < nc; ++n)
+      for (int dir = 0; dir < ndim; ++dir) {
+        const int ke = m->ie[2] + (dir == 2), je = m->ie[1] + (dir == 1),
+                  ie = m->ie[0] + (dir == 0);
+        const double vel = st->v[dir];
+        for (int k = m->is[2]; k <= ke; ++k)
+          for (int j = m->is[1]; j <= je; ++j)
+            for (int i = m->is[0]; i <= ie; ++i) {
+              const size_t p = fidx(m, nc, b, n, k, j, i);
+              st->flux[dir][p] = vel > 0.0 ? U[p - str[dir]] * vel : U[p] * vel;
+            }
+      }
+}
+
+/* EstimateTimestepBlock advection_package.cpp:505-536, min over blocks
+ * (Update::EstimateTimestep update.hpp:268-278, driver.cpp:210-270) */
+static double advection_estimate_timestep(const OrcAdvection *st) {
+  const OrcMesh *m = st->m;
+  double min_dt = DBL_MAX;
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    double bdt = DBL_MAX;
+    for (int d = 0; d < 3; ++d)
+      if (st->v[d] != 0.0) bdt = fmin(bdt, blk->dx[d] / fabs(st->v[d]));
+    min_dt = fmin(min_dt, st->cfl * bdt);
+  }
+  return min_dt;
+}
+
+/* one stage of AdvectionDriver::MakeTaskCollection advection_driver.cpp:56-163 */
+void orc_advection_stage(OrcAdvection *st, int stage) {
+  const double beta = stage == 1 ? 1.0 : 0.5;
+  double *mc0 = stage == 1 ? st->U : st->U1;
+  double *mc1 = stage == 1 ? st->U1 : st->U;
+  orc_advection_calculate_fluxes(st, mc0);
+  if (st->m->multilevel) orc_flux_correct(st->m, st->flux, st->ncomp); /* :123 */
+  flux_divergence_generic(st->m, st->ncomp, st->flux, st->dUdt);
+  weighted_sum(st->nfield, mc0, st->U, beta, 1.0 - beta, mc0);
+  weighted_sum(st->nfield, mc0, st->dUdt, 1.0, beta * st->dt, mc1);
+  /* AddBoundaryExchangeTasks(update, tl, mc1, multilevel) :136: prolongates */
+  orc_exchange(st->m, mc1, st->Uc, st->ncomp, st->m->multilevel);
+  if (stage == 2) st->allowed_dt = advection_estimate_timestep(st);
+}
+
+void orc_advection_init(OrcAdvection *st) {
+  advection_ic(st);
+  orc_exchange(st->m, st->U, st->Uc, st->ncomp, st->m->multilevel);
+  st->allowed_dt = advection_estimate_timestep(st);
+  st->dt = DBL_MAX;
+  if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;
+  st->dt = fmin(st->dt, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+  st->time = 0;
+  st->ncycle = 0;
+}
+
+void orc_advection_step(OrcAdvection *st) {
+  orc_advection_stage(st, 1);
+  orc_advection_stage(st, 2);
+  st->ncycle++;
+  st->time += st->dt;
+  if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0; /* SetGlobalTimeStep driver.cpp:210-270 */
+  st->dt = fmin(st->dt, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
 }
 
 void orc_set_num_threads(int n) {

@@ -30,6 +30,12 @@ if [ ! -x "$WORK/burgers_dump" ] || [ "$HERE/burgers_dump_main.cpp" -nt "$WORK/b
      $B/burgers_package.cpp $B/parthenon_app_inputs.cpp $LIBS -o "$WORK/burgers_dump"
 fi
 
+if [ ! -x "$WORK/advection_dump" ] || [ "$HERE/advection_dump_main.cpp" -nt "$WORK/advection_dump" ]; then
+  A=$REF/example/advection
+  $CXX $FLAGS $INC -I$A "$HERE/advection_dump_main.cpp" $A/advection_driver.cpp \
+     $A/advection_package.cpp $A/parthenon_app_inputs.cpp $LIBS -o "$WORK/advection_dump"
+fi
+
 export OMP_NUM_THREADS=${OMP_NUM_THREADS:-8} OMP_PROC_BIND=false
 
 run_burgers () { # name nx nb nscal recon nlim extra...
@@ -79,6 +85,41 @@ run_burgers_static burgers_s16_b8_l2_weno5 16 8 1 weno5 2 2 "1:0.05:0.2:0.05:0.2
 run_burgers_static burgers_s64_b8_l3_2d_weno5 64 8 1 weno5 2 3 \
   "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0" \
   parthenon/mesh/nx3=1 parthenon/meshblock/nx3=1
+fi
+# example/advection (constant velocity, donor cell): the generic task list with
+# AddFluxCorrectionTasks + AddBoundaryExchangeTasks, i.e. prolongation INSIDE every cycle.
+run_advection () { # name ndim nx nb nlim refinement numlevel "regions" extra...
+  local name=$1 ndim=$2 nx=$3 nb=$4 nlim=$5 refinement=$6 numlevel=$7 regions=$8; shift 8
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  cp "$REF/example/advection/parthinput.advection" deck.pin
+  local n=0
+  for r in $regions; do
+    IFS=: read -r lev a b c e f g <<< "$r"
+    printf '\n<parthenon/static_refinement%d>\nlevel = %s\nx1min = %s\nx1max = %s\nx2min = %s\nx2max = %s\nx3min = %s\nx3max = %s\n' \
+      $n $lev $a $b $c $e $f $g >> deck.pin
+    n=$((n+1))
+  done
+  local nx3=1 nb3=1
+  if [ "$ndim" = 3 ]; then nx3=$nx; nb3=$nb; fi
+  PB2_DUMP_PREFIX="$d/U" PB2_DUMP_FIELD=advected "$WORK/advection_dump" -i deck.pin \
+    parthenon/mesh/nx1=$nx parthenon/mesh/nx2=$nx parthenon/mesh/nx3=$nx3 \
+    parthenon/meshblock/nx1=$nb parthenon/meshblock/nx2=$nb parthenon/meshblock/nx3=$nb3 \
+    parthenon/mesh/refinement=$refinement parthenon/mesh/numlevel=$numlevel \
+    parthenon/time/nlim=$nlim parthenon/time/tlim=1e9 parthenon/output0/dt=-1 \
+    parthenon/output1/dt=-1 parthenon/output3/dt=-1 parthenon/output4/dt=-1 \
+    Advection/fill_derived=false "$@" > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
+}
+if [ -z "${SKIP_ADVECTION:-}" ]; then
+# BASELINE.json configs[0]: 2-D 256^2 mesh, 32^2 blocks, uniform, hard sphere
+run_advection advection_u256_b32_2d_hard_sphere 2 256 32 3 none 1 ""
+# 3-D, three static levels (configs[2] without the remesh step), smooth data so that the
+# min-mod slopes of the in-cycle prolongation are non-trivial, and the hard sphere of the deck
+run_advection advection_s16_b8_l3_gaussian 3 16 8 3 static 3 \
+  "1:-0.3:0.2:-0.2:0.3:-0.3:0.1 2:-0.1:0.05:-0.05:0.12:-0.12:0.0" \
+  Advection/profile=smooth_gaussian Advection/amp=1.0 Advection/vy=-0.7 Advection/vz=0.4
+run_advection advection_s16_b8_l3_hard_sphere 3 16 8 2 static 3 \
+  "1:-0.3:0.2:-0.2:0.3:-0.3:0.1 2:-0.1:0.05:-0.05:0.12:-0.12:0.0"
 fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1
