@@ -253,6 +253,15 @@ int pb2_flux_divergence(const pb2_pack_geom *g, const double *const flux[3], dou
                         pb2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * example/advection stencil: CalculateFluxes with a constant velocity
+ * (example/advection/advection_package.cpp:540-646, DonorCellX1/2/3
+ * src/reconstruct/dc_inline.hpp:31-71): flux[d](k,j,i) = v[d] * (v[d] > 0 ? u(cell - e_d) : u(cell))
+ * on the d-faces of the interior, all blocks and components in one launch.  v is a HOST array.
+ * ------------------------------------------------------------------------------------- */
+int pb2_advection_fluxes(const pb2_pack_geom *g, const double *u, double *const flux[3],
+                         const double v[3], pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * benchmarks/burgers stencil: CalculateFluxes (burgers_package.cpp:202-404), fused with
  * FluxDivergence / AverageIndependentData / UpdateIndependentData / CalculateDerived /
  * EstimateTimestepMesh (burgers_driver.cpp:92-127)

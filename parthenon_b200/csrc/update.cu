@@ -90,6 +90,37 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// example/advection CalculateFluxes with a constant velocity (advection_package.cpp:540-646;
+// DonorCellX1/2/3 reconstruct/dc_inline.hpp:31-71): the flux through the lower d-face of a
+// cell is the upwind cell value times v_d.  One thread per (block, component, cell of the
+// interior extended by one layer on the upper side); it writes the d-faces it owns.
+__global__ void __launch_bounds__(256)
+    advection_flux_kernel(const DivGeom g, const double *__restrict__ u,
+                          double *__restrict__ fx, double *__restrict__ fy,
+                          double *__restrict__ fz, double vx, double vy, double vz,
+                          int64_t total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int e0 = g.nx[0] + 1, e1 = g.nx[1] + (g.ndim > 1), e2 = g.nx[2] + (g.ndim > 2);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int64_t t = e;
+    const int di = (int)(t % e0);
+    t /= e0;
+    const int dj = (int)(t % e1);
+    t /= e1;
+    const int dk = (int)(t % e2);
+    t /= e2;
+    const int c = (int)(t % g.ncomp);
+    const int64_t b = t / g.ncomp;
+    const int64_t p = b * g.sb + c * g.sc + (int64_t)(g.is[2] + dk) * g.sk +
+                      (int64_t)(g.is[1] + dj) * g.sj + (g.is[0] + di);
+    const double q = u[p];
+    const bool in0 = di < g.nx[0], in1 = dj < g.nx[1], in2 = dk < g.nx[2];
+    if (in1 && in2) fx[p] = vx > 0.0 ? u[p - 1] * vx : q * vx;
+    if (g.ndim > 1 && in0 && in2) fy[p] = vy > 0.0 ? u[p - g.sj] * vy : q * vy;
+    if (g.ndim > 2 && in0 && in1) fz[p] = vz > 0.0 ? u[p - g.sk] * vz : q * vz;
+  }
+}
+
 // interior cells <-> packed host-layout staging buffer [block][comp][nx3][nx2][nx1]
 // (what an application's host arrays hold: no ghosts).  16-byte vectors when nx1 is even.
 template <bool SCATTER>
@@ -202,6 +233,38 @@ int pb2_interior_scatter(const pb2_pack_geom *g, const double *packed, double *f
 int pb2_interior_gather(const pb2_pack_geom *g, const double *field, double *packed,
                         pb2_stream_t stream) {
   return interior_copy(g, const_cast<double *>(field), packed, false, stream);
+}
+
+int pb2_advection_fluxes(const pb2_pack_geom *pg, const double *u, double *const flux[3],
+                         const double v[3], pb2_stream_t stream) {
+  PB2_REQUIRE(pg && u && flux && v && flux[0], "bad arguments");
+  PB2_REQUIRE(pg->ndim < 2 || flux[1], "null x2 flux");
+  PB2_REQUIRE(pg->ndim < 3 || flux[2], "null x3 flux");
+  PB2_REQUIRE(pg->ng >= 1, "donor cell needs one ghost layer");
+  if (int rc = require_device()) return rc;
+  DivGeom g;
+  g.nblocks = pg->nblocks;
+  g.ncomp = pg->ncomp;
+  g.ndim = pg->ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg->ndim;
+    g.nx[d] = sym ? 1 : pg->nx[d];
+    g.is[d] = sym ? 0 : pg->ng;
+    g.n[d] = sym ? 1 : pg->nx[d] + 2 * pg->ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg->block_stride;
+  const int64_t total = (int64_t)g.nblocks * g.ncomp * (g.nx[0] + 1) *
+                        (g.nx[1] + (g.ndim > 1)) * (g.nx[2] + (g.ndim > 2));
+  if (total == 0) return PB2_OK;
+  const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
+  ProfScope prof(K_ADVECTION_FLUX, as_stream(stream));
+  advection_flux_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, u, flux[0], flux[1], flux[2],
+                                                            v[0], v[1], v[2], total);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
 }
 
 int pb2_flux_divergence(const pb2_pack_geom *pg, const double *const flux[3], double *dudt,

@@ -63,6 +63,53 @@ recon = weno5
 num_scalars = 8
 """
 
+# example/advection: the values of the reference's parthinput.advection that matter on this
+# path (outputs and the derived demo fields are off)
+ADVECTION_DECK = """
+<parthenon/job>
+problem_id = advection
+<parthenon/mesh>
+nghost = 2
+refinement = none
+numlevel = 1
+nx1 = 64
+x1min = -0.5
+x1max = 0.5
+ix1_bc = periodic
+ox1_bc = periodic
+nx2 = 64
+x2min = -0.5
+x2max = 0.5
+ix2_bc = periodic
+ox2_bc = periodic
+nx3 = 1
+x3min = -0.5
+x3max = 0.5
+ix3_bc = periodic
+ox3_bc = periodic
+<parthenon/meshblock>
+nx1 = 16
+nx2 = 16
+nx3 = 1
+<parthenon/time>
+nlim = -1
+tlim = 1e9
+integrator = rk2
+ncycle_out = 0
+perf_cycle_offset = 0
+<Advection>
+cfl = 0.45
+vx = 1.0
+vy = 1.0
+vz = 1.0
+profile = hard_sphere
+refine_tol = 0.3
+derefine_tol = 0.03
+num_vars = 1
+vec_size = 1
+fill_derived = false
+"""
+
 _lib = None
 
 
@@ -215,8 +262,10 @@ class Topology(_Base):
 class Simulation(_Base):
     """A running application on the GPU (ParthenonManager + BurgersDriver)."""
 
-    def __init__(self, app="burgers", deck=BURGERS_DECK, overrides=None, rank=0, nranks=1,
+    def __init__(self, app="burgers", deck=None, overrides=None, rank=0, nranks=1,
                  nccl_id=None, leaves=None):
+        if deck is None:
+            deck = ADVECTION_DECK if app == "advection" else BURGERS_DECK
         self.h = C.c_void_p()
         la, n = _leaves(leaves)
         check(lib().pb2h_sim_create(C.byref(self.h), app.encode(), deck.encode(),

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "../advection/advection_driver.hpp"
 #include "../burgers/burgers_driver.hpp"
 #include "../burgers/burgers_package.hpp"
 #include "parthenon_b200_host.h"
@@ -90,15 +91,27 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
                     int nleaves) {
   return Guard([&] {
     PARTHENON_REQUIRE(sim && app && deck, "null argument");
-    PARTHENON_REQUIRE(std::string(app) == "burgers", "unknown application (have: burgers)");
+    const std::string a(app);
+    PARTHENON_REQUIRE(a == "burgers" || a == "advection",
+                      "unknown application (have: burgers, advection)");
     auto s = std::make_unique<pb2h_sim>();
-    s->pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
-    s->pman.app_input->MeshProblemGenerator = burgers_benchmark::MeshProblemGenerator;
+    if (a == "burgers") {
+      s->pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
+      s->pman.app_input->MeshProblemGenerator = burgers_benchmark::MeshProblemGenerator;
+    } else {
+      s->pman.app_input->ProcessPackages = advection_example::ProcessPackages;
+      s->pman.app_input->MeshProblemGenerator = advection_example::MeshProblemGenerator;
+    }
     s->pman.ParthenonInitEnvFromString(deck, SplitLines(overrides));
     s->pman.SetRank(rank, nranks, nccl_id);
     s->pman.ParthenonInitPackagesAndMesh(Leaves(leaves, nleaves));
-    auto drv = std::make_unique<burgers_benchmark::BurgersDriver>(
-        s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
+    std::unique_ptr<MultiStageDriver> drv;
+    if (a == "burgers")
+      drv = std::make_unique<burgers_benchmark::BurgersDriver>(
+          s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
+    else
+      drv = std::make_unique<advection_example::AdvectionDriver>(
+          s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
     drv->quiet = true;
     s->driver = std::move(drv);
     *sim = s.release();
