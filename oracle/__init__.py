@@ -95,6 +95,20 @@ def lib():
         L.orc_advection_dt.argtypes = [C.c_void_p]
         L.orc_advection_time.restype = C.c_double
         L.orc_advection_time.argtypes = [C.c_void_p]
+        L.orc_sparse_create.restype = C.c_void_p
+        L.orc_sparse_create.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_int]
+        L.orc_sparse_destroy.argtypes = [C.c_void_p]
+        L.orc_sparse_U.restype = dp
+        L.orc_sparse_U.argtypes = [C.c_void_p, C.c_int]
+        L.orc_sparse_alloc.restype = C.POINTER(C.c_ubyte)
+        L.orc_sparse_alloc.argtypes = [C.c_void_p]
+        L.orc_sparse_init.argtypes = [C.c_void_p]
+        L.orc_sparse_step.argtypes = [C.c_void_p]
+        L.orc_sparse_dt.restype = C.c_double
+        L.orc_sparse_dt.argtypes = [C.c_void_p]
+        L.orc_sparse_time.restype = C.c_double
+        L.orc_sparse_time.argtypes = [C.c_void_p]
         L.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
 
@@ -304,6 +318,56 @@ class Advection:
     @property
     def time(self):
         return lib().orc_advection_time(self.h)
+
+
+class SparseAdvection:
+    """example/sparse_advection on a uniform mesh: four sparse fields"""
+
+    NF = 4
+
+    def __init__(self, mesh, speed=1.5, cfl=0.45, alloc_threshold=1e-5, dealloc_threshold=1e-6,
+                 dealloc_count=5):
+        self.mesh = mesh
+        self.h = lib().orc_sparse_create(mesh.h, speed, cfl, alloc_threshold, dealloc_threshold,
+                                         dealloc_count)
+
+    def __del__(self):
+        try:
+            lib().orc_sparse_destroy(self.h)
+        except Exception:
+            pass
+
+    def init(self):
+        lib().orc_sparse_init(self.h)
+
+    def step(self):
+        lib().orc_sparse_step(self.h)
+
+    @property
+    def allocated(self):
+        p = lib().orc_sparse_alloc(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.mesh.nblocks * 4,)).reshape(-1, 4).astype(bool)
+
+    @property
+    def U(self):
+        """[nblocks][4][nk][nj][ni]; NaN where the field is not allocated (the convention of
+        the reference dumps)"""
+        shape = (self.mesh.nblocks,) + self.mesh.dims
+        out = np.empty((self.mesh.nblocks, 4) + self.mesh.dims)
+        a = self.allocated
+        for f in range(4):
+            u = np.ctypeslib.as_array(lib().orc_sparse_U(self.h, f),
+                                      shape=(int(np.prod(shape)),)).reshape(shape)
+            out[:, f] = np.where(a[:, f][:, None, None, None], u, np.nan)
+        return out
+
+    @property
+    def dt(self):
+        return lib().orc_sparse_dt(self.h)
+
+    @property
+    def time(self):
+        return lib().orc_sparse_time(self.h)
 
 
 def weno5z(q):

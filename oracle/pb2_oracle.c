@@ -1388,6 +1388,294 @@ void orc_advection_step(OrcAdvection *st) {
   st->allowed_dt = DBL_MAX;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* example/sparse_advection on a uniform mesh (2-D in the reference):
+ * NF sparse fields "sparse_f" with one component each; a field exists on a block only
+ * where it is ALLOCATED.  Sparse semantics of the exchange:
+ *   send    boundary_communication.cpp:95-159  flag = allocated && any |x| >= alloc threshold
+ *           in the send box; flag false => SendNull
+ *   receive :201-235  a non-null message for an unallocated field allocates it on that block
+ *           in every stage (MeshBlock::AllocateSparse meshblock.cpp:277-325; arrays start
+ *           zeroed, variable.cpp:112-127)
+ *   set     :273-334  allocated receiver: data if the message was non-null, else the sparse
+ *           default value (0)
+ *   Update::SparseDealloc update.cpp:143-217 after the last stage. */
+#define ORC_NF 4
+struct OrcSparse {
+  const OrcMesh *m;
+  double cfl, alloc_thr, dealloc_thr, init_size;
+  int dealloc_count;
+  double vx[ORC_NF], vy[ORC_NF], x0[ORC_NF], y0[ORC_NF];
+  size_t ncell, nfield; /* per field: nblocks * ncell */
+  double *U[ORC_NF], *U1[ORC_NF], *dUdt[ORC_NF], *flux[ORC_NF][3];
+  unsigned char *alloc; /* [nblocks][NF] */
+  int *counter;         /* [nblocks][NF] dealloc_count of the control variable */
+  double dt, time, allowed_dt;
+  int ncycle;
+};
+
+OrcSparse *orc_sparse_create(const OrcMesh *m, double speed, double cfl, double alloc_thr,
+                             double dealloc_thr, int dealloc_count) {
+  OrcSparse *s = (OrcSparse *)calloc(1, sizeof(OrcSparse));
+  s->m = m;
+  s->cfl = cfl;
+  s->alloc_thr = alloc_thr;
+  s->dealloc_thr = dealloc_thr;
+  s->dealloc_count = dealloc_count;
+  s->init_size = 0.1;
+  /* sparse_advection_package.cpp:60-70 */
+  const double pos = 0.8, sp = speed / sqrt(2.0);
+  const double x0[4] = {pos, -pos, -pos, pos}, y0[4] = {pos, pos, -pos, -pos};
+  const double vx[4] = {-sp, sp, sp, -sp}, vy[4] = {-sp, -sp, sp, sp};
+  s->ncell = (size_t)m->n[0] * m->n[1] * m->n[2];
+  s->nfield = (size_t)m->nblocks * s->ncell;
+  for (int f = 0; f < ORC_NF; ++f) {
+    s->x0[f] = x0[f];
+    s->y0[f] = y0[f];
+    s->vx[f] = vx[f];
+    s->vy[f] = vy[f];
+    s->U[f] = (double *)calloc(s->nfield, sizeof(double));
+    s->U1[f] = (double *)calloc(s->nfield, sizeof(double));
+    s->dUdt[f] = (double *)calloc(s->nfield, sizeof(double));
+    for (int d = 0; d < 3; ++d) s->flux[f][d] = (double *)calloc(s->nfield, sizeof(double));
+  }
+  s->alloc = (unsigned char *)calloc((size_t)m->nblocks * ORC_NF, 1);
+  s->counter = (int *)calloc((size_t)m->nblocks * ORC_NF, sizeof(int));
+  s->dt = DBL_MAX;
+  return s;
+}
+void orc_sparse_destroy(OrcSparse *s) {
+  if (!s) return;
+  for (int f = 0; f < ORC_NF; ++f) {
+    free(s->U[f]);
+    free(s->U1[f]);
+    free(s->dUdt[f]);
+    for (int d = 0; d < 3; ++d) free(s->flux[f][d]);
+  }
+  free(s->alloc);
+  free(s->counter);
+  free(s);
+}
+double *orc_sparse_U(OrcSparse *s, int f) { return s->U[f]; }
+const unsigned char *orc_sparse_alloc(const OrcSparse *s) { return s->alloc; }
+double orc_sparse_dt(const OrcSparse *s) { return s->dt; }
+double orc_sparse_time(const OrcSparse *s) { return s->time; }
+
+/* MeshBlock::AllocateSparse: the field appears, zero-filled, in every stage */
+static void sparse_allocate(OrcSparse *st, int b, int f) {
+  st->alloc[b * ORC_NF + f] = 1;
+  const size_t o = (size_t)b * st->ncell, n = st->ncell * sizeof(double);
+  memset(st->U[f] + o, 0, n);
+  memset(st->U1[f] + o, 0, n);
+  memset(st->dUdt[f] + o, 0, n);
+  for (int d = 0; d < 3; ++d) memset(st->flux[f][d] + o, 0, n);
+}
+
+/* the exchange of ONE sparse field of one container (see the section comment) */
+static void sparse_exchange(OrcSparse *st, int f, double *U) {
+  const OrcMesh *m = st->m;
+  int64_t nreg = orc_count_regions(m);
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
+  int64_t total = orc_pack(m, U, NULL, 1, NULL, off);
+  double *buf = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
+  unsigned char *flag = (unsigned char *)calloc((size_t)nreg, 1);
+  int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
+  first[0] = 0;
+  for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+  orc_pack(m, U, NULL, 1, buf, off);
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int n = 0; n < m->blocks[b].nnb; ++n) {
+      const int64_t r = first[b] + n;
+      if (!st->alloc[b * ORC_NF + f]) continue;
+      for (int64_t q = off[r]; q < off[r + 1]; ++q)
+        if (fabs(buf[q]) >= st->alloc_thr) {
+          flag[r] = 1;
+          break;
+        }
+    }
+  /* receive: allocate on the first non-null message */
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      const Block *sb = &m->blocks[nb->gid];
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          if (flag[first[nb->gid] + q] && !st->alloc[b * ORC_NF + f]) sparse_allocate(st, b, f);
+          break;
+        }
+    }
+  }
+  /* set */
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    if (!st->alloc[b * ORC_NF + f]) continue;
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      const Block *sb = &m->blocks[nb->gid];
+      int sn = -1;
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          sn = q;
+          break;
+        }
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 0, s, e);
+      const int64_t r = first[nb->gid] + sn;
+      const double *p = buf + off[r];
+      for (int k = s[2]; k <= e[2]; ++k)
+        for (int j = s[1]; j <= e[1]; ++j)
+          for (int i = s[0]; i <= e[0]; ++i) {
+            const double val = *p++;
+            U[fidx(m, 1, b, 0, k, j, i)] = flag[r] ? val : 0.0; /* sparse_default_val */
+          }
+    }
+  }
+  free(first);
+  free(flag);
+  free(buf);
+  free(off);
+}
+
+/* ProblemGenerator example/sparse_advection/parthenon_app_inputs.cpp:42-105 */
+static void sparse_ic(OrcSparse *st) {
+  const OrcMesh *m = st->m;
+  const double size = st->init_size * st->init_size;
+  for (int f = 0; f < ORC_NF; ++f)
+    for (int b = 0; b < m->nblocks; ++b) {
+      const Block *blk = &m->blocks[b];
+      int any = 0;
+      for (int k = m->is[2]; k <= m->ie[2] && !any; ++k)
+        for (int j = m->is[1]; j <= m->ie[1] && !any; ++j)
+          for (int i = m->is[0]; i <= m->ie[0] && !any; ++i) {
+            const double x = xc(blk, 0, i) - st->x0[f], y = xc(blk, 1, j) - st->y0[f],
+                         z = xc(blk, 2, k);
+            if (x * x + y * y + z * z < size) any = 1;
+          }
+      if (!any) continue;
+      sparse_allocate(st, b, f);
+      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+        for (int j = m->is[1]; j <= m->ie[1]; ++j)
+          for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+            const double x = xc(blk, 0, i) - st->x0[f], y = xc(blk, 1, j) - st->y0[f],
+                         z = xc(blk, 2, k);
+            st->U[f][fidx(m, 1, b, 0, k, j, i)] = (x * x + y * y + z * z < size ? 1.0 : 0.0);
+          }
+    }
+}
+
+/* EstimateTimestepBlock sparse_advection_package.cpp:136-168: all fields vote, allocated
+ * or not */
+static double sparse_estimate_timestep(const OrcSparse *st) {
+  const OrcMesh *m = st->m;
+  double min_dt = DBL_MAX;
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    double bdt = DBL_MAX;
+    for (int f = 0; f < ORC_NF; ++f) {
+      if (st->vx[f] != 0.0) bdt = fmin(bdt, blk->dx[0] / fabs(st->vx[f]));
+      if (st->vy[f] != 0.0) bdt = fmin(bdt, blk->dx[1] / fabs(st->vy[f]));
+    }
+    min_dt = fmin(min_dt, st->cfl * bdt);
+  }
+  return min_dt;
+}
+
+/* Update::SparseDealloc update.cpp:143-217 on container `U` (the stage's mc1) */
+static void sparse_dealloc(OrcSparse *st, double *const U[ORC_NF]) {
+  const OrcMesh *m = st->m;
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int f = 0; f < ORC_NF; ++f) {
+      if (!st->alloc[b * ORC_NF + f]) continue;
+      int all_zero = 1;
+      const double *p = U[f] + (size_t)b * st->ncell;
+      for (size_t q = 0; q < st->ncell; ++q)
+        if (fabs(p[q]) > st->dealloc_thr) {
+          all_zero = 0;
+          break;
+        }
+      int *counter = &st->counter[b * ORC_NF + f];
+      if (all_zero)
+        (*counter)++;
+      else
+        *counter = 0;
+      if (*counter > st->dealloc_count) {
+        *counter = 0;
+        st->alloc[b * ORC_NF + f] = 0;
+      }
+    }
+}
+
+/* one stage of SparseAdvectionDriver::MakeTaskCollection sparse_advection_driver.cpp:56-149 */
+static void sparse_stage(OrcSparse *st, int stage) {
+  const OrcMesh *m = st->m;
+  const double beta = stage == 1 ? 1.0 : 0.5;
+  const size_t sj = (size_t)m->n[0];
+  for (int f = 0; f < ORC_NF; ++f) {
+    double *mc0 = stage == 1 ? st->U[f] : st->U1[f];
+    double *mc1 = stage == 1 ? st->U1[f] : st->U[f];
+    double *base = st->U[f];
+    const double v[2] = {st->vx[f], st->vy[f]};
+    for (int b = 0; b < m->nblocks; ++b) {
+      if (!st->alloc[b * ORC_NF + f]) continue; /* IsAllocated guards everywhere */
+      const Block *blk = &m->blocks[b];
+      /* CalculateFluxes sparse_advection_package.cpp:173-258 (donor cell) */
+      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+        for (int j = m->is[1]; j <= m->ie[1] + 1; ++j)
+          for (int i = m->is[0]; i <= m->ie[0] + 1; ++i) {
+            const size_t p = fidx(m, 1, b, 0, k, j, i);
+            if (j <= m->ie[1])
+              st->flux[f][0][p] = (v[0] > 0.0 ? mc0[p - 1] : mc0[p]) * v[0];
+            if (i <= m->ie[0])
+              st->flux[f][1][p] = (v[1] > 0.0 ? mc0[p - sj] : mc0[p]) * v[1];
+          }
+      /* FluxDivergence update.cpp:63-86 */
+      const double a1 = blk->dx[1] * blk->dx[2], a2 = blk->dx[0] * blk->dx[2];
+      const double vol = blk->dx[0] * blk->dx[1] * blk->dx[2];
+      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+        for (int j = m->is[1]; j <= m->ie[1]; ++j)
+          for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+            const size_t p = fidx(m, 1, b, 0, k, j, i);
+            double du = (a1 * st->flux[f][0][p + 1] - a1 * st->flux[f][0][p]);
+            du += (a2 * st->flux[f][1][p + sj] - a2 * st->flux[f][1][p]);
+            st->dUdt[f][p] = -du / vol;
+          }
+      /* Average / UpdateIndependentData update.hpp:71-91 over the entire extents */
+      const size_t o = (size_t)b * st->ncell;
+      for (size_t q = o; q < o + st->ncell; ++q) mc0[q] = beta * mc0[q] + (1.0 - beta) * base[q];
+      for (size_t q = o; q < o + st->ncell; ++q)
+        mc1[q] = 1.0 * mc0[q] + (beta * st->dt) * st->dUdt[f][q];
+    }
+  }
+  for (int f = 0; f < ORC_NF; ++f) sparse_exchange(st, f, stage == 1 ? st->U1[f] : st->U[f]);
+  if (stage == 2) {
+    sparse_dealloc(st, st->U);
+    st->allowed_dt = sparse_estimate_timestep(st);
+  }
+}
+
+void orc_sparse_init(OrcSparse *st) {
+  sparse_ic(st);
+  for (int f = 0; f < ORC_NF; ++f) sparse_exchange(st, f, st->U[f]);
+  st->allowed_dt = sparse_estimate_timestep(st);
+  st->dt = fmin(DBL_MAX, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+  st->time = 0;
+  st->ncycle = 0;
+}
+
+void orc_sparse_step(OrcSparse *st) {
+  sparse_stage(st, 1);
+  sparse_stage(st, 2);
+  st->ncycle++;
+  st->time += st->dt;
+  if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;
+  st->dt = fmin(st->dt, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+}
+
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP
   omp_set_num_threads(n);

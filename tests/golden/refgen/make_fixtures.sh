@@ -36,6 +36,12 @@ if [ ! -x "$WORK/advection_dump" ] || [ "$HERE/advection_dump_main.cpp" -nt "$WO
      $A/advection_package.cpp $A/parthenon_app_inputs.cpp $LIBS -o "$WORK/advection_dump"
 fi
 
+if [ ! -x "$WORK/sparse_dump" ] || [ "$HERE/sparse_dump_main.cpp" -nt "$WORK/sparse_dump" ]; then
+  S=$REF/example/sparse_advection
+  $CXX $FLAGS $INC -I$S "$HERE/sparse_dump_main.cpp" $S/sparse_advection_driver.cpp \
+     $S/sparse_advection_package.cpp $S/parthenon_app_inputs.cpp $LIBS -o "$WORK/sparse_dump"
+fi
+
 export OMP_NUM_THREADS=${OMP_NUM_THREADS:-8} OMP_PROC_BIND=false
 
 run_burgers () { # name nx nb nscal recon nlim extra...
@@ -120,6 +126,25 @@ run_advection advection_s16_b8_l3_gaussian 3 16 8 3 static 3 \
   Advection/profile=smooth_gaussian Advection/amp=1.0 Advection/vy=-0.7 Advection/vz=0.4
 run_advection advection_s16_b8_l3_hard_sphere 3 16 8 2 static 3 \
   "1:-0.3:0.2:-0.2:0.3:-0.3:0.1 2:-0.1:0.05:-0.05:0.12:-0.12:0.0"
+fi
+# example/sparse_advection (2-D only in the reference): four sparse fields allocated where
+# their data is, allocated on a neighbour when a non-null boundary buffer arrives, deallocated
+# after dealloc_count quiet cycles.  Uniform mesh; field not allocated on a block => NaN.
+run_sparse () { # name nx nb nlim extra...
+  local name=$1 nx=$2 nb=$3 nlim=$4; shift 4
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  PB2_DUMP_PREFIX="$d/U" "$WORK/sparse_dump" -i "$REF/example/sparse_advection/parthinput.sparse_advection" \
+    parthenon/mesh/nx1=$nx parthenon/mesh/nx2=$nx parthenon/meshblock/nx1=$nb parthenon/meshblock/nx2=$nb \
+    parthenon/mesh/refinement=none parthenon/mesh/numlevel=1 \
+    parthenon/time/nlim=$nlim parthenon/time/tlim=1e9 parthenon/output0/dt=-1 \
+    parthenon/output1/dt=-1 parthenon/output3/dt=-1 "$@" > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
+}
+if [ -z "${SKIP_SPARSE:-}" ]; then
+run_sparse sparse_u64_b8_2d 64 8 12
+# larger thresholds and a short quiet count so that blocks are DEallocated within the run
+PB2_DUMP_EVERY=4 run_sparse sparse_u64_b8_2d_dealloc 64 8 60 parthenon/sparse/alloc_threshold=1e-2 \
+  parthenon/sparse/dealloc_threshold=5e-3 parthenon/sparse/dealloc_count=2
 fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1
