@@ -84,6 +84,7 @@ int64_t pb2_launch_count(void);
 #define PB2_REGION_ALLOCATED 1u     /* BndInfo::allocated */
 #define PB2_REGION_BUF_ALLOCATED 2u /* BndInfo::buf_allocated (receive side) */
 #define PB2_REGION_SAME_TO_SAME 4u  /* BndInfo::same_to_same */
+#define PB2_REGION_DST_UNALLOCATED 8u /* copy regions: the RECEIVING field is not allocated */
 
 /* One side of a boundary channel: an index box of one block's array <-> a contiguous run
  * of the buffer slab.  Buffer order is [comp][k][j][i] (Indexer6D, src/utils/indexer.hpp). */
@@ -141,6 +142,15 @@ int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *dat
                pb2_stream_t stream);
 /* One launch moves every same-device channel straight from sender box to receiver box. */
 int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream);
+/* The same exchange in the two halves a SPARSE field needs, because the receiver must know
+ * whether a message is null before anything is written (and may have to allocate first):
+ *  pb2_copy_flags   sender half (boundary_communication.cpp:95-157): nonzero_flags[flag_slot]
+ *                   |= allocated source && any |x| >= threshold in the send box; writes no field
+ *  pb2_copy_select  receiver half (:273-334): regions with data_flags[flag_slot] != 0 (or
+ *                   flag_slot < 0) receive the data, all others default_value; regions marked
+ *                   PB2_REGION_DST_UNALLOCATED are skipped */
+int pb2_copy_flags(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream);
+int pb2_copy_select(const pb2_bnd_table *table, const int32_t *data_flags, pb2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * prolongation / restriction at fine-coarse boundaries
@@ -221,6 +231,24 @@ typedef struct pb2_pack_geom {
   int64_t block_stride; /* Reals between blocks; component stride is ni*nj*nk */
   const double *dx;     /* device [nblocks][3] cell widths */
 } pb2_pack_geom;
+
+/* Block-masked forms for SPARSE fields: block b of the batch is processed only if
+ * block_mask[b] != 0 (device int32 [nblocks]; NULL = every block), which is how the
+ * reference's kernels skip unallocated variables (IsAllocated guards in update.hpp:83-85,
+ * update.cpp:78, dc_inline.hpp:39).  x, y, z are whole slabs [nblocks][ncomp][nk][nj][ni]. */
+int pb2_weighted_sum_blocks(const pb2_pack_geom *g, const double *x, const double *y, double w1,
+                            double w2, double *z, const int32_t *block_mask,
+                            pb2_stream_t stream);
+int pb2_flux_divergence_blocks(const pb2_pack_geom *g, const double *const flux[3],
+                               double *dudt, const int32_t *block_mask, pb2_stream_t stream);
+int pb2_advection_fluxes_blocks(const pb2_pack_geom *g, const double *u, double *const flux[3],
+                                const double v[3], const int32_t *block_mask,
+                                pb2_stream_t stream);
+/* Update::SparseDealloc's device pass (update.cpp:161-186): quiet[b] = 1 if every |x| of
+ * block b (all components, ENTIRE extents) is <= threshold, else 0; blocks with
+ * block_mask[b] == 0 are left untouched.  quiet: device int32 [nblocks]. */
+int pb2_block_quiet_flags(const pb2_pack_geom *g, const double *u, double threshold,
+                          const int32_t *block_mask, int32_t *quiet, pb2_stream_t stream);
 
 /* z = w1*x + w2*y over the GHOST cells of every block only: what the reference's full-extent
  * WeightedSumData passes (AverageIndependentData / UpdateIndependentData, update.hpp:122-137)

@@ -74,6 +74,10 @@ int pb2h_sim_get_field(pb2h_sim *sim, const char *container, const char *field, 
                        double *host, int64_t nreal);
 int pb2h_sim_set_field(pb2h_sim *sim, const char *container, const char *field, int which,
                        const double *host, int64_t nreal);
+/* sparse fields: out[b] = 1 if `field` is allocated on this rank's block b (Variable::IsAllocated,
+ * reference src/interface/variable.hpp), else 0; dense fields report 1 everywhere */
+int pb2h_sim_allocation(pb2h_sim *sim, const char *container, const char *field, int *out,
+                        int nblocks);
 
 /* state through HOST buffers holding interior cells only, [block][comp][nx3][nx2][nx1] over
  * this rank's blocks (pinned memory recommended).  upload = H2D + scatter + ghost exchange;

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpb200.so")
 PB2_OK = 0
 PB2_ERR_NO_DEVICE = -3
 REGION_ALLOCATED, REGION_BUF_ALLOCATED, REGION_SAME_TO_SAME = 1, 2, 4
+REGION_DST_UNALLOCATED = 8
 RECON_WENO5, RECON_LINEAR = 0, 1
 MATH_STRICT, MATH_FAST = 0, 1
 PROLONG_MINMOD, PROLONG_LINEAR, PROLONG_PIECEWISE_CONSTANT = 0, 1, 2
@@ -87,7 +88,9 @@ SYMBOLS = [
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
     "pb2_restrict", "pb2_prolongate", "pb2_flxcor_table_create", "pb2_flux_correct",
     "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
-    "pb2_halo_copy_uniform", "pb2_advection_fluxes",
+    "pb2_halo_copy_uniform", "pb2_advection_fluxes", "pb2_copy_flags", "pb2_copy_select",
+    "pb2_weighted_sum_blocks", "pb2_flux_divergence_blocks", "pb2_advection_fluxes_blocks",
+    "pb2_block_quiet_flags",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
@@ -124,6 +127,14 @@ def lib():
     L.pb2_pack.argtypes = [vp, vp, vp, vp]
     L.pb2_unpack.argtypes = [vp, vp, vp, vp]
     L.pb2_copy.argtypes = [vp, vp, vp]
+    L.pb2_copy_flags.argtypes = [vp, vp, vp]
+    L.pb2_copy_select.argtypes = [vp, vp, vp]
+    L.pb2_weighted_sum_blocks.argtypes = [C.POINTER(PackGeom), vp, vp, C.c_double, C.c_double,
+                                          vp, vp, vp]
+    L.pb2_flux_divergence_blocks.argtypes = [C.POINTER(PackGeom), C.POINTER(vp), vp, vp, vp]
+    L.pb2_advection_fluxes_blocks.argtypes = [C.POINTER(PackGeom), vp, C.POINTER(vp),
+                                              c_double_p, vp, vp]
+    L.pb2_block_quiet_flags.argtypes = [C.POINTER(PackGeom), vp, C.c_double, vp, vp, vp]
     L.pb2_halo_copy_uniform.argtypes = [vp, vp, vp, vp]
     L.pb2_restrict.argtypes = [vp, vp]
     L.pb2_prolongate.argtypes = [vp, C.c_int, vp]

@@ -136,14 +136,25 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---- fused copy: receiver box <- sender box ------------------------------------------------
-template <int V>
+// MODE 0: copy, and report "any |x| >= threshold" per region (dense fields, legacy)
+// MODE 1: report only — the sender's half of a sparse exchange (SendBoundBufs decides between
+//         Send and SendNull, boundary_communication.cpp:95-157); nothing is written
+// MODE 2: deliver — the receiver's half (SetBounds :273-334): regions whose flag is set get
+//         the data, the others (null message, or unallocated sender) the sparse default;
+//         unallocated receivers are skipped
+template <int V, int MODE>
 __device__ __forceinline__ void copy_chunk(const DevRegion &r, uint32_t first,
                                            int32_t *flags) {
   using T = typename Vec<V>::type;
   T val[kUnroll];
   int64_t doff[kUnroll];
   bool ok[kUnroll];
-  const bool src_alloc = (r.status & PB2_REGION_ALLOCATED) != 0;
+  bool src_alloc = (r.status & PB2_REGION_ALLOCATED) != 0;
+  if (MODE == 1 && !src_alloc) return; // flag stays 0: SendNull
+  if (MODE == 2) {
+    if (r.status & PB2_REGION_DST_UNALLOCATED) return;
+    if (flags != nullptr && r.flag_slot >= 0) src_alloc = src_alloc && flags[r.flag_slot] != 0;
+  }
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
     const uint32_t v = first + u * kThreads + threadIdx.x;
@@ -165,25 +176,26 @@ __device__ __forceinline__ void copy_chunk(const DevRegion &r, uint32_t first,
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
     if (ok[u]) {
-      *reinterpret_cast<T *>(r.var + doff[u]) = val[u];
+      if (MODE != 1) *reinterpret_cast<T *>(r.var + doff[u]) = val[u];
       nz = nz || above(val[u], r.value);
     }
   }
-  if (flags != nullptr && r.flag_slot >= 0) {
+  if (MODE != 2 && flags != nullptr && r.flag_slot >= 0) {
     if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flags + r.flag_slot, 1);
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
     copy_kernel(const DevRegion *__restrict__ regions, const Chunk *__restrict__ chunks,
-                int32_t *__restrict__ flags) {
+                int32_t *flags) {
   const Chunk ch = chunks[blockIdx.x];
   const DevRegion &r = regions[ch.region];
   if (r.status & PB2_REGION_SAME_TO_SAME) return;
   if (r.vec == 2)
-    copy_chunk<2>(r, ch.first_vec, flags);
+    copy_chunk<2, MODE>(r, ch.first_vec, flags);
   else
-    copy_chunk<1>(r, ch.first_vec, flags);
+    copy_chunk<1, MODE>(r, ch.first_vec, flags);
 }
 
 
@@ -434,8 +446,28 @@ int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t st
   PB2_REQUIRE(table && table->kind == kCopy, "copy needs a copy table");
   if (table->nchunks == 0) return PB2_OK;
   ProfScope prof(K_COPY, as_stream(stream));
-  copy_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+  copy_kernel<0><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, nonzero_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_copy_flags(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kCopy && nonzero_flags, "copy_flags needs a copy table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_COPY, as_stream(stream));
+  copy_kernel<1><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+      table->d_regions, table->d_chunks, nonzero_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_copy_select(const pb2_bnd_table *table, const int32_t *data_flags, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kCopy, "copy_select needs a copy table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_COPY, as_stream(stream));
+  copy_kernel<2><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+      table->d_regions, table->d_chunks, const_cast<int32_t *>(data_flags));
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

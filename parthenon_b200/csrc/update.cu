@@ -68,10 +68,12 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     flux_div_kernel(const DivGeom g, const double *__restrict__ fx,
                     const double *__restrict__ fy, const double *__restrict__ fz,
-                    const double *__restrict__ dx, double *__restrict__ dudt) {
+                    const double *__restrict__ dx, double *__restrict__ dudt,
+                    const int32_t *__restrict__ mask) {
   const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
   const int ctas_per_block = (ncell + 255) / 256;
   const int b = blockIdx.x / ctas_per_block;
+  if (mask != nullptr && mask[b] == 0) return;
   const int t = (blockIdx.x % ctas_per_block) * 256 + threadIdx.x;
   if (t >= ncell) return;
   const int i = g.is[0] + t % g.nx[0];
@@ -90,6 +92,33 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// WeightedSumData for a sparse field: whole blocks, skipped where the field is unallocated
+__global__ void __launch_bounds__(256)
+    weighted_sum_blocks_kernel(const double *x, const double *y, double w1, double w2, double *z,
+                               int64_t block_stride, int64_t per_block,
+                               const int32_t *__restrict__ mask, int ctas_per_block) {
+  const int b = blockIdx.x / ctas_per_block;
+  if (mask != nullptr && mask[b] == 0) return;
+  const int64_t o = (int64_t)b * block_stride;
+  for (int64_t i = (int64_t)(blockIdx.x % ctas_per_block) * 256 + threadIdx.x; i < per_block;
+       i += (int64_t)ctas_per_block * 256)
+    z[o + i] = w1 * x[o + i] + w2 * y[o + i];
+}
+
+// SparseDealloc update.cpp:161-186: is every value of the block within the threshold?
+__global__ void __launch_bounds__(256)
+    block_quiet_kernel(const double *__restrict__ u, int64_t block_stride, int64_t per_block,
+                       double threshold, const int32_t *__restrict__ mask,
+                       int32_t *__restrict__ quiet) {
+  const int b = blockIdx.x;
+  if (mask != nullptr && mask[b] == 0) return;
+  const double *p = u + (int64_t)b * block_stride;
+  bool loud = false;
+  for (int64_t i = threadIdx.x; i < per_block; i += 256) loud = loud || (fabs(p[i]) > threshold);
+  const int any = __syncthreads_or(loud);
+  if (threadIdx.x == 0) quiet[b] = any ? 0 : 1;
+}
+
 // example/advection CalculateFluxes with a constant velocity (advection_package.cpp:540-646;
 // DonorCellX1/2/3 reconstruct/dc_inline.hpp:31-71): the flux through the lower d-face of a
 // cell is the upwind cell value times v_d.  One thread per (block, component, cell of the
@@ -98,7 +127,7 @@ __global__ void __launch_bounds__(256)
     advection_flux_kernel(const DivGeom g, const double *__restrict__ u,
                           double *__restrict__ fx, double *__restrict__ fy,
                           double *__restrict__ fz, double vx, double vy, double vz,
-                          int64_t total) {
+                          int64_t total, const int32_t *__restrict__ mask) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int e0 = g.nx[0] + 1, e1 = g.nx[1] + (g.ndim > 1), e2 = g.nx[2] + (g.ndim > 2);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -111,6 +140,7 @@ __global__ void __launch_bounds__(256)
     t /= e2;
     const int c = (int)(t % g.ncomp);
     const int64_t b = t / g.ncomp;
+    if (mask != nullptr && mask[b] == 0) continue;
     const int64_t p = b * g.sb + c * g.sc + (int64_t)(g.is[2] + dk) * g.sk +
                       (int64_t)(g.is[1] + dj) * g.sj + (g.is[0] + di);
     const double q = u[p];
@@ -237,6 +267,12 @@ int pb2_interior_gather(const pb2_pack_geom *g, const double *field, double *pac
 
 int pb2_advection_fluxes(const pb2_pack_geom *pg, const double *u, double *const flux[3],
                          const double v[3], pb2_stream_t stream) {
+  return pb2_advection_fluxes_blocks(pg, u, flux, v, nullptr, stream);
+}
+
+int pb2_advection_fluxes_blocks(const pb2_pack_geom *pg, const double *u, double *const flux[3],
+                                const double v[3], const int32_t *block_mask,
+                                pb2_stream_t stream) {
   PB2_REQUIRE(pg && u && flux && v && flux[0], "bad arguments");
   PB2_REQUIRE(pg->ndim < 2 || flux[1], "null x2 flux");
   PB2_REQUIRE(pg->ndim < 3 || flux[2], "null x3 flux");
@@ -262,13 +298,48 @@ int pb2_advection_fluxes(const pb2_pack_geom *pg, const double *u, double *const
   const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
   ProfScope prof(K_ADVECTION_FLUX, as_stream(stream));
   advection_flux_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, u, flux[0], flux[1], flux[2],
-                                                            v[0], v[1], v[2], total);
+                                                            v[0], v[1], v[2], total, block_mask);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }
 
 int pb2_flux_divergence(const pb2_pack_geom *pg, const double *const flux[3], double *dudt,
                         pb2_stream_t stream) {
+  return pb2_flux_divergence_blocks(pg, flux, dudt, nullptr, stream);
+}
+
+int pb2_weighted_sum_blocks(const pb2_pack_geom *pg, const double *x, const double *y, double w1,
+                            double w2, double *z, const int32_t *block_mask,
+                            pb2_stream_t stream) {
+  PB2_REQUIRE(pg && x && y && z, "bad arguments");
+  if (int rc = require_device()) return rc;
+  if (pg->nblocks == 0) return PB2_OK;
+  int64_t per_block = pg->ncomp;
+  for (int d = 0; d < 3; ++d) per_block *= d >= pg->ndim ? 1 : pg->nx[d] + 2 * pg->ng;
+  const int cpb = static_cast<int>(std::min<int64_t>((per_block + 255) / 256, 64));
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  weighted_sum_blocks_kernel<<<pg->nblocks * cpb, 256, 0, as_stream(stream)>>>(
+      x, y, w1, w2, z, pg->block_stride, per_block, block_mask, cpb);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_block_quiet_flags(const pb2_pack_geom *pg, const double *u, double threshold,
+                          const int32_t *block_mask, int32_t *quiet, pb2_stream_t stream) {
+  PB2_REQUIRE(pg && u && quiet, "bad arguments");
+  if (int rc = require_device()) return rc;
+  if (pg->nblocks == 0) return PB2_OK;
+  int64_t per_block = pg->ncomp;
+  for (int d = 0; d < 3; ++d) per_block *= d >= pg->ndim ? 1 : pg->nx[d] + 2 * pg->ng;
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  block_quiet_kernel<<<pg->nblocks, 256, 0, as_stream(stream)>>>(u, pg->block_stride, per_block,
+                                                                 threshold, block_mask, quiet);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_flux_divergence_blocks(const pb2_pack_geom *pg, const double *const flux[3],
+                               double *dudt, const int32_t *block_mask, pb2_stream_t stream) {
   PB2_REQUIRE(pg && flux && dudt && pg->dx, "bad arguments");
   if (int rc = require_device()) return rc;
   DivGeom g;
@@ -290,7 +361,7 @@ int pb2_flux_divergence(const pb2_pack_geom *pg, const double *const flux[3], do
   if (ctas == 0) return PB2_OK;
   ProfScope prof(K_FLUX_DIV, as_stream(stream));
   flux_div_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, flux[0], flux[1], flux[2], pg->dx,
-                                                      dudt);
+                                                      dudt, block_mask);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

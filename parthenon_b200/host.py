@@ -19,7 +19,7 @@ SYMBOLS = [
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_field_ptr",
-    "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
+    "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_allocation", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
     "pb2h_sim_exchange_elements", "pb2h_sim_history", "pb2h_sim_upload_interior",
     "pb2h_sim_download_interior", "pb2h_sim_prefetch_interior", "pb2h_sim_commit_interior",
     "pb2h_sim_writeback_interior", "pb2h_sim_lane_sync",
@@ -110,6 +110,52 @@ vec_size = 1
 fill_derived = false
 """
 
+# example/sparse_advection: the reference's parthinput.sparse_advection on a uniform mesh
+SPARSE_ADVECTION_DECK = """
+<parthenon/job>
+problem_id = sparse
+<parthenon/sparse>
+enable_sparse = true
+alloc_threshold = 1e-5
+dealloc_threshold = 1e-6
+dealloc_count = 5
+<parthenon/mesh>
+nghost = 2
+refinement = none
+numlevel = 1
+nx1 = 64
+x1min = -1.0
+x1max = 1.0
+ix1_bc = periodic
+ox1_bc = periodic
+nx2 = 64
+x2min = -1.0
+x2max = 1.0
+ix2_bc = periodic
+ox2_bc = periodic
+nx3 = 1
+x3min = -1.0
+x3max = 1.0
+ix3_bc = periodic
+ox3_bc = periodic
+<parthenon/meshblock>
+nx1 = 8
+nx2 = 8
+nx3 = 1
+<parthenon/time>
+nlim = -1
+tlim = 1e9
+integrator = rk2
+ncycle_out = 0
+perf_cycle_offset = 0
+<sparse_advection>
+restart_test = false
+cfl = 0.45
+speed = 1.5
+refine_tol = 0.3
+derefine_tol = 0.03
+"""
+
 _lib = None
 
 
@@ -149,6 +195,7 @@ def lib():
                                      C.POINTER(i64)]
     L.pb2h_sim_get_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
     L.pb2h_sim_set_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
+    L.pb2h_sim_allocation.argtypes = [vp, C.c_char_p, C.c_char_p, ip, C.c_int]
     L.pb2h_sim_upload_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64]
     L.pb2h_sim_download_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64]
     L.pb2h_sim_prefetch_interior.argtypes = [vp, C.c_char_p, C.c_char_p, vp, i64, C.c_int]
@@ -265,7 +312,8 @@ class Simulation(_Base):
     def __init__(self, app="burgers", deck=None, overrides=None, rank=0, nranks=1,
                  nccl_id=None, leaves=None):
         if deck is None:
-            deck = ADVECTION_DECK if app == "advection" else BURGERS_DECK
+            deck = {"advection": ADVECTION_DECK,
+                    "sparse_advection": SPARSE_ADVECTION_DECK}.get(app, BURGERS_DECK)
         self.h = C.c_void_p()
         la, n = _leaves(leaves)
         check(lib().pb2h_sim_create(C.byref(self.h), app.encode(), deck.encode(),
@@ -318,6 +366,14 @@ class Simulation(_Base):
         check(lib().pb2h_sim_field_ptr(self.h, container.encode(), field.encode(), which,
                                        C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def allocation(self, container, field):
+        """bool [nblocks]: where a (sparse) field is allocated on this rank"""
+        nb = self.info()["nblocks"]
+        out = np.zeros(nb, dtype=np.int32)
+        check(lib().pb2h_sim_allocation(self.h, container.encode(), field.encode(),
+                                        out.ctypes.data_as(C.POINTER(C.c_int)), nb))
+        return out.astype(bool)
 
     def get_field(self, container, field, which=FIELD_DATA, out=None):
         shape = self.field_shape(container, field, which)

@@ -103,6 +103,11 @@ struct BvarsCache {
   // traffic accounting for bench.py: Reals moved by the last exchange
   int64_t elements_local = 0, elements_nonlocal = 0;
 
+  // sparse fields (allocation-aware exchange): one "message is non-null" flag per local channel
+  bool sparse = false;
+  DeviceBuffer sparse_flags;
+  std::vector<int32_t> sparse_flags_h;
+
   // flux correction at fine-coarse faces (flxcor_send / flxcor_recv), built on first use:
   // fused restrict+deliver for same-device channels, restrict-into-slab + unpack for the rest
   bool flxcor_built = false;

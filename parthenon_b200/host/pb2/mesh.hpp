@@ -201,6 +201,17 @@ class Mesh {
   // in-place sum over ranks of a host vector (MPI_Reduce of outputs/history.cpp)
   void ReduceHistory(std::vector<Real> &vals);
   // true if some block of this rank has a neighbour on another level
+  // <parthenon/sparse> (globals.hpp:27-36, parthenon_manager.cpp:122-138)
+  struct SparseConfig {
+    bool enabled = true;
+    Real allocation_threshold = 1.0e-12;
+    Real deallocation_threshold = 1.0e-14;
+    int deallocation_count = 5;
+  } sparse_config;
+  // MeshBlock::AllocateSparse / DeallocateSparse (meshblock.cpp:277-349) for block `lid` of
+  // this rank: the field appears zero-filled in (or disappears from) EVERY container
+  void AllocateSparse(const std::string &label, int lid);
+  void DeallocateSparse(const std::string &label, int lid);
   bool HasFineCoarseFaces() const;
   mutable int fine_coarse_faces_ = -1; // cached answer (static meshes)
 

@@ -48,7 +48,14 @@ class Variable {
 
   // sparse allocation status per block (variable.hpp IsAllocated); dense fields: all true
   bool IsAllocated(int b) const { return allocated_[b] != 0; }
-  void SetAllocated(int b, bool a) { allocated_[b] = a ? 1 : 0; }
+  void SetAllocated(int b, bool a) {
+    allocated_[b] = a ? 1 : 0;
+    mask_dirty_ = true;
+  }
+  // Variable::AllocateData (variable.cpp:112-127): the block's arrays start zeroed
+  void AllocateBlock(int b);
+  // device int32 [nblocks] allocation mask for the block-masked kernels; NULL for dense fields
+  const int32_t *DeviceMask();
   const std::vector<uint8_t> &AllocationStatus() const { return allocated_; }
   int dealloc_count(int b) const { return dealloc_count_[b]; }
   int &dealloc_count(int b) { return dealloc_count_[b]; }
@@ -62,6 +69,8 @@ class Variable {
   DeviceBuffer data_, coarse_, flux_[3];
   std::vector<uint8_t> allocated_;
   std::vector<int> dealloc_count_;
+  DeviceBuffer mask_;
+  bool mask_dirty_ = true;
 };
 
 // what md->PackVariables(names) returns: the selected fields of every block, addressable

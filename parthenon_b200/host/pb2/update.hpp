@@ -66,5 +66,8 @@ TaskStatus PreCommFillDerived(MeshData<Real> *rc);
 template <>
 TaskStatus FillDerived(MeshData<Real> *rc);
 
+// update.cpp:143-217
+TaskStatus SparseDealloc(MeshData<Real> *md);
+
 } // namespace Update
 } // namespace parthenon

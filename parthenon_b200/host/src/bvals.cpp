@@ -288,6 +288,16 @@ void Rebuild(MeshData<Real> *md) {
   const bool slabs = c.plan.send_elements > 0 || c.plan.recv_elements > 0;
   PARTHENON_REQUIRE(!slabs || pm->DefaultNumPartitions() == 1,
                     "inter-device halos need one MeshData per rank (parthenon/mesh/pack_size=-1)");
+  // sparse fields: allocation-aware exchange (null messages, allocate-on-receive), built for
+  // same-device channels of a uniform mesh with one MeshData per device
+  c.sparse = false;
+  for (Variable *v : c.vars) c.sparse = c.sparse || (v->metadata().IsSparse() && pm->sparse_config.enabled);
+  if (c.sparse) {
+    PARTHENON_REQUIRE(!slabs, "sparse fields across devices are not supported by this build");
+    PARTHENON_REQUIRE(!pm->multilevel, "sparse fields on multilevel meshes are not supported by this build");
+    PARTHENON_REQUIRE(pm->DefaultNumPartitions() == 1,
+                      "sparse fields need one MeshData per rank (parthenon/mesh/pack_size=-1)");
+  }
 
   // fused local channels: receiver ghost box <- sender interior box
   std::vector<pb2_copy_region> copies;
@@ -330,7 +340,18 @@ void Rebuild(MeshData<Real> *md) {
     r.status = PB2_REGION_ALLOCATED;
     r.threshold = 0.0;
     r.default_value = rv.metadata().GetDefaultValue();
+    if (c.sparse && rv.metadata().IsSparse()) {
+      // BndInfo::allocated of the sender / the receiver (bnd_info.cpp:277, :290-292)
+      r.flag_slot = static_cast<int32_t>(copies.size());
+      r.status = (sv.IsAllocated(sb->pack_index) ? PB2_REGION_ALLOCATED : 0u) |
+                 (rv.IsAllocated(rb->pack_index) ? 0u : PB2_REGION_DST_UNALLOCATED);
+      r.threshold = rv.metadata().GetAllocationThreshold();
+    }
     copies.push_back(r);
+  }
+  if (c.sparse && !c.sparse_flags) {
+    c.sparse_flags.Allocate(sizeof(int32_t) * std::max<size_t>(copies.size(), 1), md->stream());
+    c.sparse_flags_h.assign(copies.size(), 0);
   }
   PB2_CHECK(pb2_copy_table_create(&c.copy_local, copies.data(), static_cast<int64_t>(copies.size())));
 
@@ -499,6 +520,11 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
   if (DoesLocal(bt)) {
     // boundary_communication.cpp:82-87: restrict before anything reads the coarse buffers
     if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_send[0], st));
+    if (c.sparse) {
+      // sender half of a sparse exchange: which messages are null (:95-157)
+      PB2_CHECK(pb2_memset(c.sparse_flags.get(), 0, sizeof(int32_t) * c.sparse_flags_h.size(), st));
+      PB2_CHECK(pb2_copy_flags(c.copy_local, c.sparse_flags.get<int32_t>(), st));
+    }
     c.send_generation++; // the copy itself happens in SetBounds<local> of the receiver
   }
   if (DoesNonlocal(bt) && c.plan.send_elements + c.plan.recv_elements > 0) {
@@ -555,6 +581,19 @@ TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     }
     if (c.send_generation <= c.consumed_generation[md->partition_id()])
       return TaskStatus::incomplete;
+    if (c.sparse) {
+      // :216-232: a field that receives actual data in any boundary is allocated there
+      PB2_CHECK(pb2_memcpy_d2h(c.sparse_flags_h.data(), c.sparse_flags.get(),
+                               sizeof(int32_t) * c.sparse_flags_h.size(), md->stream()));
+      PB2_CHECK(pb2_stream_sync(md->stream()));
+      for (size_t i = 0; i < c.plan.local.size(); ++i) {
+        const Channel &ch = c.plan.local[i];
+        Variable &rv = *c.vars[ch.var];
+        if (!rv.metadata().IsSparse() || !c.sparse_flags_h[i]) continue;
+        const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
+        if (!rv.IsAllocated(rb->pack_index)) pm->AllocateSparse(rv.label(), rb->lid);
+      }
+    }
   }
   // nonlocal: completion is a stream-side event wait in SetBounds — no host polling
   return TaskStatus::complete;
@@ -571,6 +610,10 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
         const pb2_pack_geom g = md->Geometry(*v);
         PB2_CHECK(pb2_halo_copy_uniform(&g, v->data(), c.halo_nbr.get<int32_t>(), st));
       }
+    } else if (c.sparse) {
+      // (Cache() above rebuilt the tables if ReceiveBoundBufs allocated anything; the flags
+      // are indexed by channel, which allocation does not change)
+      PB2_CHECK(pb2_copy_select(c.copy_local, c.sparse_flags.get<int32_t>(), st));
     } else {
       PB2_CHECK(pb2_copy(c.copy_local, nullptr, st));
     }

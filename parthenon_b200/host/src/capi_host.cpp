@@ -10,6 +10,7 @@
 
 #include "../advection/advection_driver.hpp"
 #include "../burgers/burgers_driver.hpp"
+#include "../sparse_advection/sparse_advection_driver.hpp"
 #include "../burgers/burgers_package.hpp"
 #include "parthenon_b200_host.h"
 #include "pb2/parthenon.hpp"
@@ -92,15 +93,18 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
   return Guard([&] {
     PARTHENON_REQUIRE(sim && app && deck, "null argument");
     const std::string a(app);
-    PARTHENON_REQUIRE(a == "burgers" || a == "advection",
-                      "unknown application (have: burgers, advection)");
+    PARTHENON_REQUIRE(a == "burgers" || a == "advection" || a == "sparse_advection",
+                      "unknown application (have: burgers, advection, sparse_advection)");
     auto s = std::make_unique<pb2h_sim>();
     if (a == "burgers") {
       s->pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = burgers_benchmark::MeshProblemGenerator;
-    } else {
+    } else if (a == "advection") {
       s->pman.app_input->ProcessPackages = advection_example::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = advection_example::MeshProblemGenerator;
+    } else {
+      s->pman.app_input->ProcessPackages = sparse_advection_example::ProcessPackages;
+      s->pman.app_input->MeshProblemGenerator = sparse_advection_example::MeshProblemGenerator;
     }
     s->pman.ParthenonInitEnvFromString(deck, SplitLines(overrides));
     s->pman.SetRank(rank, nranks, nccl_id);
@@ -109,8 +113,11 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
     if (a == "burgers")
       drv = std::make_unique<burgers_benchmark::BurgersDriver>(
           s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
-    else
+    else if (a == "advection")
       drv = std::make_unique<advection_example::AdvectionDriver>(
+          s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
+    else
+      drv = std::make_unique<sparse_advection_example::SparseAdvectionDriver>(
           s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
     drv->quiet = true;
     s->driver = std::move(drv);
@@ -304,6 +311,24 @@ int pb2h_sim_get_field(pb2h_sim *sim, const char *container, const char *field, 
     PARTHENON_REQUIRE(n == nreal, "field size mismatch");
     PB2_CHECK(pb2_memcpy_d2h(host, p, sizeof(double) * n, sim->pm()->stream));
     PB2_CHECK(pb2_stream_sync(sim->pm()->stream));
+  });
+}
+
+int pb2h_sim_allocation(pb2h_sim *sim, const char *container, const char *field, int *out,
+                        int nblocks) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && container && field && out, "null argument");
+    Mesh *pm = sim->pm();
+    int b = 0;
+    for (int p = 0; p < pm->DefaultNumPartitions(); ++p) {
+      auto &md = pm->mesh_data.GetOrAdd(container, p);
+      Variable &v = md->Get(field);
+      for (int i = 0; i < md->NumBlocks(); ++i, ++b) {
+        PARTHENON_REQUIRE(b < nblocks, "allocation buffer too small");
+        out[b] = v.IsAllocated(i) ? 1 : 0;
+      }
+    }
+    PARTHENON_REQUIRE(b == nblocks, "allocation buffer size mismatch");
   });
 }
 

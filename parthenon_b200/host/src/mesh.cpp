@@ -351,6 +351,11 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
   pack_size_ = pin->GetOrAddInteger("parthenon/mesh", "pack_size", -1);
   virtual_ranks = pin->GetOrAddInteger("pb2", "virtual_ranks", 1);
   table_halo = pin->GetOrAddBoolean("pb2", "table_halo", false);
+  sparse_config.enabled = pin->GetOrAddBoolean("parthenon/sparse", "enable_sparse", true);
+  sparse_config.allocation_threshold = pin->GetOrAddReal("parthenon/sparse", "alloc_threshold", 1e-12);
+  sparse_config.deallocation_threshold =
+      pin->GetOrAddReal("parthenon/sparse", "dealloc_threshold", 1e-14);
+  sparse_config.deallocation_count = pin->GetOrAddInteger("parthenon/sparse", "dealloc_count", 5);
 
   BuildTree(pin, leaves);
   if (refinement != "none") multilevel = true; // coarse buffers exist (mesh.cpp:118-140)
@@ -383,7 +388,38 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
     block_list.push_back(mb);
   }
   for (auto &name : packages.Order())
-    for (auto &f : packages.Get(name)->AllFields()) resolved_fields.push_back(f);
+    for (auto &f : packages.Get(name)->AllFields()) {
+      resolved_fields.push_back(f);
+      // metadata.cpp:160-171: sparse fields take the global thresholds, dense ones 0
+      FieldEntry &e = resolved_fields.back();
+      if (e.m.IsSparse())
+        e.m.SetSparseThresholds(sparse_config.allocation_threshold,
+                                sparse_config.deallocation_threshold, e.m.GetDefaultValue());
+    }
+}
+
+void Mesh::AllocateSparse(const std::string &label, int lid) {
+  MeshBlock *pmb = block_list[lid].get();
+  for (auto &kv : mesh_data.All()) {
+    MeshData<Real> *md = kv.second.get();
+    if (md->partition_id() != pmb->partition || !md->HasVariable(label)) continue;
+    Variable &v = md->Get(label);
+    if (v.IsAllocated(pmb->pack_index)) continue; // OneCopy fields are shared between stages
+    v.AllocateBlock(pmb->pack_index);
+    md->alloc_generation++;
+  }
+}
+
+void Mesh::DeallocateSparse(const std::string &label, int lid) {
+  MeshBlock *pmb = block_list[lid].get();
+  for (auto &kv : mesh_data.All()) {
+    MeshData<Real> *md = kv.second.get();
+    if (md->partition_id() != pmb->partition || !md->HasVariable(label)) continue;
+    Variable &v = md->Get(label);
+    if (!v.IsAllocated(pmb->pack_index)) continue;
+    v.SetAllocated(pmb->pack_index, false);
+    md->alloc_generation++;
+  }
 }
 
 Mesh::~Mesh() = default;

@@ -63,6 +63,30 @@ Real *Variable::flux(int dir) {
   return f.get<Real>();
 }
 
+void Variable::AllocateBlock(int b) {
+  SetAllocated(b, true);
+  auto zero = [&](DeviceBuffer &buf, int64_t stride) {
+    if (buf)
+      PB2_CHECK(pb2_memset(buf.get<Real>() + b * stride, 0, sizeof(Real) * static_cast<size_t>(stride),
+                           stream_));
+  };
+  zero(data_, block_stride);
+  zero(coarse_, cblock_stride);
+  for (auto &f : flux_) zero(f, block_stride);
+}
+
+const int32_t *Variable::DeviceMask() {
+  if (!m_.IsSparse()) return nullptr;
+  if (mask_dirty_) {
+    if (!mask_) mask_.Allocate(sizeof(int32_t) * std::max(nblocks_, 1), stream_);
+    std::vector<int32_t> h(allocated_.begin(), allocated_.end());
+    PB2_CHECK(pb2_memcpy_h2d(mask_.get(), h.data(), sizeof(int32_t) * h.size(), stream_));
+    PB2_CHECK(pb2_stream_sync(stream_)); // h goes out of scope
+    mask_dirty_ = false;
+  }
+  return mask_.get<int32_t>();
+}
+
 Real *const *VariablePack::DevicePtrs(pb2_stream_t stream) {
   if (!dev_ptrs && !ptrs.empty()) {
     dev_ptrs.Allocate(sizeof(Real *) * ptrs.size(), stream);

@@ -13,7 +13,8 @@ TaskStatus FluxDivergence(MeshData<Real> *in, MeshData<Real> *dudt_cont) {
     pb2_pack_geom g = in->Geometry(*v);
     const double *flux[3] = {v->flux(1), g.ndim > 1 ? v->flux(2) : nullptr,
                              g.ndim > 2 ? v->flux(3) : nullptr};
-    PB2_CHECK(pb2_flux_divergence(&g, flux, d.data(), in->stream()));
+    // update.cpp:78: only where both the field and dudt are allocated (sparse fields)
+    PB2_CHECK(pb2_flux_divergence_blocks(&g, flux, d.data(), v->DeviceMask(), in->stream()));
   }
   return TaskStatus::complete;
 }
@@ -25,6 +26,13 @@ TaskStatus WeightedSumData(const std::vector<MetadataFlag> &flags, MeshData<Real
   for (Variable *x : in1->GetVariablesByFlag(flags)) {
     Variable &y = in2->Get(x->label());
     Variable &z = out->Get(x->label());
+    if (x->metadata().IsSparse()) {
+      // update.hpp:83-85: skipped where x, y or z is unallocated (they are allocated together)
+      const pb2_pack_geom g = in1->Geometry(*x);
+      PB2_CHECK(pb2_weighted_sum_blocks(&g, x->data(), y.data(), w1, w2, z.data(),
+                                        x->DeviceMask(), in1->stream()));
+      continue;
+    }
     const int64_t n = x->block_stride * in1->NumBlocks();
     PB2_CHECK(pb2_weighted_sum(x->data(), y.data(), w1, w2, z.data(), n, in1->stream()));
   }
@@ -58,6 +66,35 @@ TaskStatus FillDerived(MeshData<Real> *rc) {
     if (pkg.second->FillDerivedMesh != nullptr) pkg.second->FillDerivedMesh(rc);
   for (const auto &pkg : pkgs)
     if (pkg.second->PostFillDerivedMesh != nullptr) pkg.second->PostFillDerivedMesh(rc);
+  return TaskStatus::complete;
+}
+
+// update.cpp:143-217: a sparse field whose every value on a block (entire extents) stayed
+// within the deallocation threshold for more than deallocation_count consecutive calls is
+// deallocated on that block, in every container
+TaskStatus SparseDealloc(MeshData<Real> *md) {
+  Mesh *pm = md->GetMeshPointer();
+  if (!pm->sparse_config.enabled || md->NumBlocks() == 0) return TaskStatus::complete;
+  const int nb = md->NumBlocks();
+  std::vector<int32_t> quiet(nb);
+  for (Variable *v : md->GetVariablesByFlag({Metadata::Sparse})) {
+    const pb2_pack_geom g = md->Geometry(*v);
+    DeviceBuffer flags;
+    flags.Allocate(sizeof(int32_t) * nb, md->stream());
+    PB2_CHECK(pb2_block_quiet_flags(&g, v->data(), v->metadata().GetDeallocationThreshold(),
+                                    v->DeviceMask(), flags.get<int32_t>(), md->stream()));
+    PB2_CHECK(pb2_memcpy_d2h(quiet.data(), flags.get(), sizeof(int32_t) * nb, md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+    for (int b = 0; b < nb; ++b) {
+      if (!v->IsAllocated(b)) continue;
+      int &counter = v->dealloc_count(b);
+      counter = quiet[b] ? counter + 1 : 0;
+      if (counter > pm->sparse_config.deallocation_count) {
+        counter = 0;
+        pm->DeallocateSparse(v->label(), md->GetBlock(b)->lid);
+      }
+    }
+  }
   return TaskStatus::complete;
 }
 
