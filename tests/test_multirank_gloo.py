@@ -1,0 +1,115 @@
+"""world_size-2 test of the N > 1 host logic on CPU (gloo): every process builds ITS OWN
+partition and exchange plan with the C++ host library (no device), packs the per-peer slabs the
+plan prescribes from a seeded field, ships them with torch.distributed send/recv over gloo,
+unpacks what it receives — and must end up with the ghosts the single-process CPU oracle
+computes for the whole mesh.  This is the path NCCL carries on the GPUs (pb2_comm_exchange):
+contiguous Morton gid ranges per rank, one slab segment per peer, offsets derived on both
+sides from topology alone (no handshake)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from parthenon_b200 import host
+from tests.test_host_topology import deck_overrides
+
+NX, NG, NRB, NCOMP, WORLD = (8, 6, 4), 2, (4, 4, 4), 2, 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _box(m, gid, other, off, ir):
+    """index box of the channel between `gid` and its neighbour `other` at offsets `off`"""
+    for n, nb in enumerate(m.neighbors(gid)):
+        if nb[0] == other and tuple(nb[2:]) == tuple(off):
+            s, e = m.calc_indices(gid, n, ir)
+            return tuple(slice(s[d], e[d] + 1) for d in (2, 1, 0))
+    raise AssertionError("channel without a neighbour entry")
+
+
+def _offsets(idx):
+    return (idx % 3 - 1, (idx // 3) % 3 - 1, idx // 9 - 1)
+
+
+def _worker(rank, port, result):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        m = oracle.Mesh(3, NX, NG, NRB)
+        rng = np.random.default_rng(3)
+        U = rng.standard_normal((m.nblocks, NCOMP) + m.dims)
+        Uref = U.copy()
+        m.exchange(Uref)
+
+        t = host.Topology(overrides=deck_overrides(3, NX, NG, NRB), rank=rank, nranks=WORLD)
+        info = t.info()
+        lo, hi = info["first_gid"], info["first_gid"] + info["nblocks"]
+        mine = U.copy()
+        mine[:lo] = np.nan  # this process only holds its own blocks
+        mine[hi:] = np.nan
+
+        send_rows, send_seg = t.plan(NCOMP, "send")
+        recv_rows, recv_seg = t.plan(NCOMP, "recv")
+        send = np.zeros(int(send_seg[WORLD]))
+        for sg, rg, _var, oi, off, n, _peer in send_rows:
+            assert lo <= sg < hi
+            # offset_index is the sender's view of the receiver
+            box = _box(m, int(sg), int(rg), _offsets(int(oi)), 0)
+            send[off:off + n] = mine[(int(sg), slice(None)) + box].ravel()
+        recv = np.zeros(int(recv_seg[WORLD]))
+        reqs = []
+        for p in range(WORLD):
+            if p == rank:
+                continue
+            a, b = int(send_seg[p]), int(send_seg[p + 1])
+            if b > a:
+                reqs.append(dist.isend(torch.from_numpy(send[a:b].copy()), p))
+        bufs = {}
+        for p in range(WORLD):
+            if p == rank:
+                continue
+            a, b = int(recv_seg[p]), int(recv_seg[p + 1])
+            if b > a:
+                bufs[p] = torch.empty(b - a, dtype=torch.float64)
+                dist.recv(bufs[p], p)
+                recv[a:b] = bufs[p].numpy()
+        for r in reqs:
+            r.wait()
+        for sg, rg, _var, oi, off, n, _peer in recv_rows:
+            assert lo <= rg < hi and not (lo <= sg < hi)
+            ro = tuple(-x for x in _offsets(int(oi)))  # the receiver sees the mirror offset
+            box = _box(m, int(rg), int(sg), ro, 1)
+            tgt = mine[(int(rg), slice(None)) + box]
+            tgt[...] = recv[off:off + n].reshape(tgt.shape)
+        for sg, rg, _var, oi, _off, n, _peer in t.plan(NCOMP, "local")[0]:
+            ro = tuple(-x for x in _offsets(int(oi)))
+            src = mine[(int(sg), slice(None)) + _box(m, int(sg), int(rg), _offsets(int(oi)), 0)]
+            tgt = mine[(int(rg), slice(None)) + _box(m, int(rg), int(sg), ro, 1)]
+            tgt[...] = src
+        ok = np.array_equal(mine[lo:hi], Uref[lo:hi])
+        moved = torch.tensor([float(send.size)], dtype=torch.float64)
+        dist.all_reduce(moved)
+        result[rank] = (bool(ok), hi - lo, float(moved.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slab_exchange_over_gloo():
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        result = mgr.dict()
+        mp.spawn(_worker, args=(_free_port(), result), nprocs=WORLD, join=True)
+        res = dict(result)
+    assert set(res) == {0, 1}
+    assert all(r[0] for r in res.values()), res
+    assert sum(r[1] for r in res.values()) == int(np.prod(NRB))
+    assert res[0][2] == res[1][2] > 0  # all-reduced count of Reals that crossed ranks
