@@ -36,6 +36,8 @@ def lib():
         L.orc_mesh_create_uniform.restype = C.c_void_p
         L.orc_mesh_create_uniform.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp]
         L.orc_mesh_destroy.argtypes = [C.c_void_p]
+        L.orc_mesh_set_next_bcs.argtypes = [ip]
+        L.orc_apply_bcs.argtypes = [C.c_void_p, dp, C.c_int]
         L.orc_mesh_nblocks.argtypes = [C.c_void_p]
         L.orc_mesh_multilevel.argtypes = [C.c_void_p]
         L.orc_mesh_dims.argtypes = [C.c_void_p, ip, ip]
@@ -124,8 +126,15 @@ def _ip(a):
 class Mesh:
     """Single-tree block-structured mesh; leaves=None => uniform root grid."""
 
-    def __init__(self, ndim, nx, ng, nrb, xmin=(-0.5,) * 3, xmax=(0.5,) * 3, leaves=None):
+    BCS = {"periodic": 0, "outflow": 1, "reflecting": 2}
+
+    def __init__(self, ndim, nx, ng, nrb, xmin=(-0.5,) * 3, xmax=(0.5,) * 3, leaves=None,
+                 bcs=None):
+        """bcs: six names (ix1, ox1, ix2, ox2, ix3, ox3) from BCS, default periodic"""
         L = lib()
+        self.bcs = tuple(bcs) if bcs else ("periodic",) * 6
+        bc = np.array([self.BCS[b] for b in self.bcs], dtype=np.int32)
+        L.orc_mesh_set_next_bcs(_ip(bc))
         self.ndim, self.ng = ndim, ng
         self._nx = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
         self._nrb = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
@@ -138,6 +147,7 @@ class Mesh:
             lv = np.ascontiguousarray(leaves, dtype=np.int32)
             self.h = L.orc_mesh_create(ndim, _ip(self._nx), ng, _ip(self._nrb),
                                        _dp(self._xmin), _dp(self._xmax), lv.shape[0], _ip(lv))
+        L.orc_mesh_set_next_bcs(None)
         if not self.h:
             raise ValueError("unsupported mesh")
         self.nblocks = L.orc_mesh_nblocks(self.h)
@@ -209,6 +219,9 @@ class Mesh:
         e = np.zeros(3, dtype=np.int32)
         lib().orc_calc_indices_flux(self.h, b, n, _ip(s), _ip(e))
         return tuple(int(x) for x in s), tuple(int(x) for x in e)
+
+    def apply_bcs(self, U):
+        lib().orc_apply_bcs(self.h, _dp(U), U.shape[1])
 
     def flux_correct(self, F):
         """F: three face-flux arrays [nblocks][ncomp][nk][nj][ni], corrected in place"""

@@ -43,6 +43,7 @@ typedef struct {
 struct OrcMesh {
   int ndim, nx[3], ng, nrb[3], root_level, nblocks, multilevel;
   int periodic[3];
+  int bc[6]; /* per mesh face (inner_x1, outer_x1, ...): 0 periodic, 1 outflow, 2 reflect */
   double xmin[3], xmax[3];
   int is[3], ie[3], n[3];    /* fine interior bounds and full extents (i,j,k order) */
   int cis[3], cie[3], cn[3]; /* coarse */
@@ -229,6 +230,12 @@ static void find_neighbors(OrcMesh *m, int b) {
       }
 }
 
+/* mesh boundary flags used by the NEXT orc_mesh_create* call (test convenience) */
+static int g_next_bc[6] = {0, 0, 0, 0, 0, 0};
+void orc_mesh_set_next_bcs(const int bc[6]) {
+  for (int f = 0; f < 6; ++f) g_next_bc[f] = bc ? bc[f] : 0;
+}
+
 OrcMesh *orc_mesh_create(int ndim, const int nx[3], int ng, const int nrb[3],
                          const double xmin[3], const double xmax[3], int nleaf,
                          const int *leaves) {
@@ -241,7 +248,9 @@ OrcMesh *orc_mesh_create(int ndim, const int nx[3], int ng, const int nrb[3],
     m->nrb[d] = d < ndim ? nrb[d] : 1;
     m->xmin[d] = xmin[d];
     m->xmax[d] = xmax[d];
-    m->periodic[d] = 1;
+    m->bc[2 * d] = g_next_bc[2 * d];
+    m->bc[2 * d + 1] = g_next_bc[2 * d + 1];
+    m->periodic[d] = m->bc[2 * d] == 0;
     if (m->nrb[d] > maxrb) maxrb = m->nrb[d];
   }
   /* single tree: all non-symmetry directions must hold the same power-of-two number of
@@ -818,6 +827,43 @@ int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int pro
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* physical boundary conditions: ApplyBoundaryConditionsOnCoarseOrFine
+ * (bvals/boundary_conditions.cpp:36-58) with the generic outflow / reflect functions
+ * (boundary_conditions_generic.hpp:174-268) on the fine arrays of cell-centred fields
+ * without a Metadata::Vector component (no sign flip).  Faces in BoundaryFace order; the
+ * ghost slab of a face spans the ENTIRE extents of the other directions
+ * (mesh/domain.hpp:183-251), so edges and corners outside the mesh come out right when the
+ * faces are applied in order. */
+void orc_apply_bcs(const OrcMesh *m, double *U, int ncomp) {
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int face = 0; face < 6; ++face) {
+      const int d = face / 2, inner = (face % 2) == 0;
+      if (d >= m->ndim || m->bc[face] == 0) continue;
+      /* MeshBlock::boundary_flag: the mesh flag where the block touches the mesh boundary */
+      const long nb_d = nblocks_at(m, blk->loc.level, d);
+      if (inner ? blk->loc.lx[d] != 0 : blk->loc.lx[d] != nb_d - 1) continue;
+      const int ref = inner ? m->is[d] : m->ie[d];
+      const int offset = 2 * ref + (inner ? -1 : 1);
+      int lo[3] = {0, 0, 0}, hi[3] = {m->n[0] - 1, m->n[1] - 1, m->n[2] - 1};
+      if (inner)
+        hi[d] = m->is[d] - 1;
+      else
+        lo[d] = m->ie[d] + 1;
+      for (int c = 0; c < ncomp; ++c)
+        for (int k = lo[2]; k <= hi[2]; ++k)
+          for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) {
+              int s[3] = {i, j, k};
+              s[d] = m->bc[face] == 2 ? offset - s[d] : ref;
+              U[fidx(m, ncomp, b, c, k, j, i)] = U[fidx(m, ncomp, b, c, s[2], s[1], s[0])];
+            }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* burgers: benchmarks/burgers/recon.hpp, burgers_package.{hpp,cpp} */
 
 #define ORC_EPS (10.0 * DBL_EPSILON) /* src/utils/robust.hpp:39-42 */
@@ -1172,6 +1218,7 @@ void orc_burgers_stage(OrcBurgers *st, int stage) {
    * (prolongated once by Mesh::Initialize, then carried through the full-extent
    * WeightedSumData passes).  Reproduced as is. */
   orc_exchange(st->m, mc1, st->Uc, st->ncomp, 0);
+  orc_apply_bcs(st->m, mc1, st->ncomp); /* ApplyBoundaryConditions burgers_driver.cpp:137 */
   calculate_derived(st, mc1);
   if (stage == 2) st->allowed_dt = estimate_timestep(st, mc1);
 }
@@ -1187,6 +1234,7 @@ void orc_burgers_init(OrcBurgers *st) {
   orc_burgers_ic(st->m, st->U, st->ncomp);
   /* Mesh::Initialize -> CommunicateBoundaries (mesh.cpp:640-706) does prolongate */
   orc_exchange(st->m, st->U, st->Uc, st->ncomp, st->m->multilevel);
+  orc_apply_bcs(st->m, st->U, st->ncomp); /* mesh.cpp:705 */
   calculate_derived(st, st->U);
   st->allowed_dt = estimate_timestep(st, st->U); /* InitializeBlockTimeSteps driver.cpp:194 */
   st->dt = DBL_MAX;

@@ -68,6 +68,9 @@ int main(int argc, char *argv[]) {
 
   pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
   pman.app_input->ProblemGenerator = burgers_benchmark::ProblemGenerator;
+  // "reflecting" mesh boundaries need their functions enrolled (application_input.hpp);
+  // periodic / outflow decks are unaffected
+  pman.app_input->RegisterDefaultReflectingBoundaryConditions();
   pman.app_input->UserWorkBeforeLoop = [](parthenon::Mesh *pm, parthenon::ParameterInput *,
                                           parthenon::SimTime &tm) {
     DumpU(pm, 0, tm.time, tm.dt);

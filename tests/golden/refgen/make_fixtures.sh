@@ -61,6 +61,11 @@ run_burgers () { # name nx nb nscal recon nlim extra...
 # small uniform cases: full fields (ghosts included) after cycles 0..nlim
 run_burgers burgers_u16_b8_s1_weno5   16  8 1 weno5  3
 run_burgers burgers_u16_b8_s1_linear  16  8 1 linear 3 parthenon/mesh/nghost=2
+# physical boundaries: outflow in x1, reflecting in x2, periodic in x3
+if [ -z "${SKIP_BC:-}" ]; then
+run_burgers burgers_u16_b8_s1_weno5_bc 16 8 1 weno5 3 parthenon/mesh/ix1_bc=outflow \
+  parthenon/mesh/ox1_bc=outflow parthenon/mesh/ix2_bc=reflecting parthenon/mesh/ox2_bc=reflecting
+fi
 # static-refinement (multilevel) cases: restrict / prolongate ghost fill (cycle 0) and, after
 # the first cycles, flux correction.  The deck is the reference deck plus
 # <parthenon/static_refinementN> blocks written into $WORK (never into $REF).
