@@ -185,6 +185,31 @@ int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream);
 int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * physical boundary conditions
+ * replaces ApplyBoundaryConditionsOnCoarseOrFine (src/bvals/boundary_conditions.cpp:36-58) with
+ * the generic outflow / reflect functions (boundary_conditions_generic.hpp:174-268) for
+ * cell-centred fields: one launch fills the ghost slabs of every listed (block, face) — the slab
+ * spans the ENTIRE extents of the other directions (mesh/domain.hpp:183-251).  Faces of
+ * different directions must be applied in order x1, x2, x3 (one table per direction), because
+ * the x2 slab reads x1 ghosts etc.
+ * ------------------------------------------------------------------------------------- */
+#define PB2_BC_OUTFLOW 0 /* ghost = value of the last interior cell along the normal */
+#define PB2_BC_REFLECT 1 /* ghost = mirror image; sign flipped for the normal vector component */
+typedef struct pb2_bc_region {
+  double *var;        /* component 0 of the block's array (fine data, or the coarse buffer) */
+  int32_t face;       /* BoundaryFace: 0 inner_x1, 1 outer_x1, 2 inner_x2, ... 5 outer_x3 */
+  int32_t type;       /* PB2_BC_* */
+  int32_t ncomp;
+  int32_t n[3];       /* entire extents (i,j,k) of the array */
+  int32_t is, ie;     /* interior bounds along the face normal */
+  int32_t stride_c;   /* component stride in Reals (row stride n[0], plane stride n[0]*n[1]) */
+  uint32_t flip_mask; /* reflect: bit c set => component c is the vector component along the
+                         normal (Metadata::Vector, vector_component == DIR) and changes sign */
+} pb2_bc_region;
+int pb2_bc_table_create(pb2_bnd_table **table, const pb2_bc_region *regions, int64_t n);
+int pb2_apply_bcs(const pb2_bnd_table *table, pb2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * flux correction at fine-coarse faces
  * replaces SendBoundBufs<flxcor_send> / SetBounds<flxcor_recv> (boundary_communication.cpp:
  * 454-461) for the face fluxes of cell-centred fields: region selection loop_utils.hpp:145-160,

@@ -58,6 +58,12 @@ class FlxCorRegion(C.Structure):
                 ("status", C.c_uint32), ("area", C.c_double)]
 
 
+class BcRegion(C.Structure):
+    _fields_ = [("var", C.c_void_p), ("face", C.c_int32), ("type", C.c_int32),
+                ("ncomp", C.c_int32), ("n", C.c_int32 * 3), ("is_", C.c_int32),
+                ("ie", C.c_int32), ("stride_c", C.c_int32), ("flip_mask", C.c_uint32)]
+
+
 class PackGeom(C.Structure):
     _fields_ = [("nblocks", C.c_int32), ("ncomp", C.c_int32), ("ndim", C.c_int32),
                 ("nx", C.c_int32 * 3), ("ng", C.c_int32), ("block_stride", C.c_int64),
@@ -90,7 +96,7 @@ SYMBOLS = [
     "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
     "pb2_halo_copy_uniform", "pb2_advection_fluxes", "pb2_copy_flags", "pb2_copy_select",
     "pb2_weighted_sum_blocks", "pb2_flux_divergence_blocks", "pb2_advection_fluxes_blocks",
-    "pb2_block_quiet_flags",
+    "pb2_block_quiet_flags", "pb2_bc_table_create", "pb2_apply_bcs",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
@@ -121,6 +127,8 @@ def lib():
     L.pb2_bnd_table_create.argtypes = [C.POINTER(vp), C.POINTER(BndRegion), i64]
     L.pb2_copy_table_create.argtypes = [C.POINTER(vp), C.POINTER(CopyRegion), i64]
     L.pb2_prores_table_create.argtypes = [C.POINTER(vp), C.POINTER(ProResRegion), i64]
+    L.pb2_bc_table_create.argtypes = [C.POINTER(vp), C.POINTER(BcRegion), i64]
+    L.pb2_apply_bcs.argtypes = [vp, vp]
     L.pb2_flxcor_table_create.argtypes = [C.POINTER(vp), C.POINTER(FlxCorRegion), i64]
     L.pb2_flux_correct.argtypes = [vp, vp, vp]
     L.pb2_bnd_table_destroy.argtypes = [vp]
@@ -204,6 +212,9 @@ class Table:
         elif kind == "prores":
             arr = (ProResRegion * max(n, 1))(*regions)
             check(lib().pb2_prores_table_create(C.byref(self.h), arr, n))
+        elif kind == "bc":
+            arr = (BcRegion * max(n, 1))(*regions)
+            check(lib().pb2_bc_table_create(C.byref(self.h), arr, n))
         elif kind == "flxcor":
             arr = (FlxCorRegion * max(n, 1))(*regions)
             check(lib().pb2_flxcor_table_create(C.byref(self.h), arr, n))

@@ -48,7 +48,7 @@ int require_device();
 // ---- optional per-kernel timing with CUDA events (pb2_profile_* of the C ABI) ----------
 enum KernelId {
   K_PACK = 0, K_UNPACK, K_COPY, K_RESTRICT, K_PROLONGATE, K_WEIGHTED_SUM, K_FLUX_DIV,
-  K_FLUX_X, K_FLUX_Y, K_FLUX_Z, K_UPDATE, K_DERIVED_DT, K_HISTORY, K_SWEEP_X, K_SWEEP_Y, K_SWEEP_Z, K_INTERIOR, K_HALO_UNIFORM, K_FLUX_CORRECT, K_ADVECTION_FLUX, K_COUNT
+  K_FLUX_X, K_FLUX_Y, K_FLUX_Z, K_UPDATE, K_DERIVED_DT, K_HISTORY, K_SWEEP_X, K_SWEEP_Y, K_SWEEP_Z, K_INTERIOR, K_HALO_UNIFORM, K_FLUX_CORRECT, K_ADVECTION_FLUX, K_APPLY_BC, K_COUNT
 };
 extern std::atomic<int> g_profile_on;
 void profile_begin(int id, cudaStream_t s, void **token);

@@ -410,6 +410,7 @@ int pb2_bnd_table_destroy(pb2_bnd_table *table) {
   cudaFree(table->d_chunks);
   cudaFree(table->d_prores);
   cudaFree(table->d_flxcor);
+  cudaFree(table->d_bc);
   delete table;
   return PB2_OK;
 }

@@ -206,6 +206,43 @@ __global__ void __launch_bounds__(kPrThreads)
   }
 }
 
+// GenericBC<DIR, SIDE, Outflow|Reflect> boundary_conditions_generic.hpp:174-268 for cell-centred
+// fields, every listed (block, face) in one launch.  The ghost slab of a face covers the whole
+// extents of the other two directions.
+__global__ void __launch_bounds__(kPrThreads)
+    apply_bc_kernel(const pb2_bc_region *__restrict__ regions, const Chunk *__restrict__ chunks) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_bc_region &r = regions[ch.region];
+  const int d = r.face >> 1;
+  const bool inner = (r.face & 1) == 0;
+  const int ref = inner ? r.is : r.ie;
+  const int offset = 2 * ref + (inner ? -1 : 1); // reflections
+  int ext[3] = {r.n[0], r.n[1], r.n[2]};
+  const int lo = inner ? 0 : r.ie + 1;
+  ext[d] = inner ? r.is : r.n[d] - (r.ie + 1);
+  const uint32_t total = (uint32_t)r.ncomp * ext[0] * ext[1] * ext[2];
+  const int64_t sj = r.n[0], sk = (int64_t)r.n[0] * r.n[1];
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    const uint32_t e = ch.first_vec + u * kPrThreads + threadIdx.x;
+    if (e >= total) continue;
+    int idx[3];
+    idx[0] = e % ext[0];
+    uint32_t t = e / ext[0];
+    idx[1] = t % ext[1];
+    t /= ext[1];
+    idx[2] = t % ext[2];
+    const int c = t / ext[2];
+    idx[d] += lo;
+    int src[3] = {idx[0], idx[1], idx[2]};
+    src[d] = r.type == PB2_BC_REFLECT ? offset - idx[d] : ref;
+    double *f = r.var + (int64_t)c * r.stride_c;
+    const double v = f[src[2] * sk + src[1] * sj + src[0]];
+    const bool flip = r.type == PB2_BC_REFLECT && ((r.flip_mask >> c) & 1u);
+    f[idx[2] * sk + idx[1] * sj + idx[0]] = flip ? -1.0 * v : 1.0 * v;
+  }
+}
+
 } // namespace pb2
 
 using namespace pb2;
@@ -328,6 +365,66 @@ int pb2_flux_correct(const pb2_bnd_table *table, double *slab, pb2_stream_t stre
   ProfScope prof(K_FLUX_CORRECT, as_stream(stream));
   flux_correct_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                         as_stream(stream)>>>(table->d_flxcor, table->d_chunks, slab);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_bc_table_create(pb2_bnd_table **table, const pb2_bc_region *regions, int64_t n) {
+  PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
+  if (int rc = require_device()) return rc;
+  std::vector<Chunk> chunks;
+  int64_t elements = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    const pb2_bc_region &q = regions[r];
+    PB2_REQUIRE(q.face >= 0 && q.face < 6, "face must be 0..5");
+    PB2_REQUIRE(q.type == PB2_BC_OUTFLOW || q.type == PB2_BC_REFLECT, "unknown boundary type");
+    PB2_REQUIRE(q.ncomp >= 0 && q.ncomp <= 32, "at most 32 components per boundary region");
+    const int d = q.face >> 1;
+    const int depth = (q.face & 1) == 0 ? q.is : q.n[d] - (q.ie + 1);
+    PB2_REQUIRE(depth >= 0 && (q.type != PB2_BC_REFLECT || depth <= q.ie - q.is + 1),
+                "ghost slab deeper than the interior it mirrors");
+    int64_t total = (int64_t)q.ncomp * depth;
+    for (int o = 0; o < 3; ++o)
+      if (o != d) total *= q.n[o];
+    PB2_REQUIRE(total >= 0 && total < (1ll << 31), "bad region extent");
+    elements += total;
+    for (int64_t v = 0; v < total; v += kPrThreads * kPrPerThread)
+      chunks.push_back(Chunk{static_cast<int32_t>(r), static_cast<uint32_t>(v)});
+  }
+  auto *t = new pb2_bnd_table();
+  t->kind = kBc;
+  t->nregions = n;
+  t->nchunks = static_cast<int64_t>(chunks.size());
+  t->elements = elements;
+  t->d_regions = nullptr;
+  t->d_chunks = nullptr;
+  t->d_prores = nullptr;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc(&t->d_bc, n * sizeof(pb2_bc_region));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(t->d_bc, regions, n * sizeof(pb2_bc_region), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !chunks.empty())
+      e = cudaMemcpy(t->d_chunks, chunks.data(), chunks.size() * sizeof(Chunk),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error("boundary-condition table upload failed: %s", cudaGetErrorString(e));
+      cudaFree(t->d_bc);
+      cudaFree(t->d_chunks);
+      delete t;
+      return PB2_ERR_CUDA;
+    }
+  }
+  *table = t;
+  return PB2_OK;
+}
+
+int pb2_apply_bcs(const pb2_bnd_table *table, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kBc, "apply_bcs needs a boundary-condition table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_APPLY_BC, as_stream(stream));
+  apply_bc_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0, as_stream(stream)>>>(
+      table->d_bc, table->d_chunks);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -31,7 +31,7 @@ const char *kKernelNames[K_COUNT] = {
     "weighted_sum_kernel", "flux_div_kernel", "flux_x_kernel", "flux_march_kernel<y>",
     "flux_march_kernel<z>", "update_kernel", "derived_dt_kernel", "history_kernel",
     "sweep_x_kernel", "sweep_march_kernel<y>", "sweep_march_kernel<z>",
-    "interior_kernel", "halo_uniform_kernel", "flux_correct_kernel", "advection_flux_kernel"};
+    "interior_kernel", "halo_uniform_kernel", "flux_correct_kernel", "advection_flux_kernel", "apply_bc_kernel"};
 } // namespace
 
 void profile_begin(int id, cudaStream_t s, void **token) {

@@ -7,7 +7,7 @@ namespace pb2 {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 
-enum TableKind { kBnd = 0, kCopy = 1, kProRes = 2, kFlxCor = 3 };
+enum TableKind { kBnd = 0, kCopy = 1, kProRes = 2, kFlxCor = 3, kBc = 4 };
 
 struct DevRegion {
   double *var;       // array side (pack source / unpack destination / copy destination)
@@ -43,5 +43,6 @@ struct pb2_bnd_table {
   // prores tables keep the API struct on device
   pb2_prores_region *d_prores;
   pb2_flxcor_region *d_flxcor = nullptr;
+  pb2_bc_region *d_bc = nullptr;
 };
 

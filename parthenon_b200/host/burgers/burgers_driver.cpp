@@ -75,6 +75,10 @@ TaskCollection BurgersDriver::MakeTaskCollection(BlockList_t &blocks, const int 
     auto recv = tl.AddTask(start_bnd | update | send, ReceiveBoundBufs<nonlocal>, mc1);
     auto set = tl.AddTask(recv | set_local, SetBounds<nonlocal>, mc1);
 
+    // set physical boundaries (the per-block second region of burgers_driver.cpp:129-147, here
+    // one launch per direction for the whole batch; nothing to do on periodic meshes)
+    tl.AddTask(set, ApplyBoundaryConditionsMD, mc1);
+
     if (fused) {
       if (last) tl.AddTask(set, burgers_package::CollectFusedTimestep, mc1.get());
     } else {

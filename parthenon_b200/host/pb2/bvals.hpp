@@ -103,6 +103,11 @@ struct BvarsCache {
   // traffic accounting for bench.py: Reals moved by the last exchange
   int64_t elements_local = 0, elements_nonlocal = 0;
 
+  // physical boundary conditions (outflow / reflect) of the blocks on a non-periodic mesh
+  // face, one table per direction: [0] fine arrays, [1] coarse buffers
+  pb2_bnd_table *bc[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  bool has_bcs = false;
+
   // sparse fields (allocation-aware exchange): one "message is non-null" flag per local channel
   bool sparse = false;
   DeviceBuffer sparse_flags;
@@ -155,9 +160,12 @@ TaskStatus ReceiveFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
 TaskStatus SetFluxCorrections(std::shared_ptr<MeshData<Real>> &md);
 void FluxCorrection(MeshData<Real> *md);
 
-// physical boundaries: all supported meshes are periodic, handled as neighbour exchange
-// (bvals/boundary_conditions.cpp:197 is a no-op for periodic)
+// physical boundaries (bvals/boundary_conditions.cpp:36-58, :85-95): generic outflow / reflect
+// on the blocks that touch a non-periodic mesh face, whole MeshData batch in <= 3 launches.
+// The per-block form of the reference is kept for source compatibility; batches should use
+// the MD forms.
 TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &rc);
+TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md);
 TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &md,
                                                    bool coarse);
 

@@ -119,6 +119,10 @@ class MeshBlock {
  public:
   int gid = 0, lid = 0; // global id (Morton order) and index on this rank
   LogicalLocation loc;
+  // meshblock.hpp boundary_flag: the mesh's flag on faces that lie on the mesh boundary,
+  // BoundaryFlag::block elsewhere (inner_x1, outer_x1, inner_x2, ...)
+  BoundaryFlag boundary_flag[6] = {BoundaryFlag::block, BoundaryFlag::block, BoundaryFlag::block,
+                                   BoundaryFlag::block, BoundaryFlag::block, BoundaryFlag::block};
   RegionSize block_size;
   IndexShape cellbounds, c_cellbounds;
   Coordinates_t coords;

@@ -233,6 +233,11 @@ void BvarsCache::Clear() {
   pb2_bnd_table_destroy(pack);
   pb2_bnd_table_destroy(unpack);
   copy_local = pack = unpack = nullptr;
+  for (int cf = 0; cf < 2; ++cf)
+    for (int d = 0; d < 3; ++d) {
+      pb2_bnd_table_destroy(bc[cf][d]);
+      bc[cf][d] = nullptr;
+    }
   pb2_bnd_table_destroy(flxcor_local);
   pb2_bnd_table_destroy(flxcor_pack);
   pb2_bnd_table_destroy(flxcor_unpack);
@@ -452,6 +457,44 @@ void Rebuild(MeshData<Real> *md) {
         PB2_CHECK(pb2_prores_table_create(&c.prolongate[cls][o], pro[cls][o].data(),
                                           static_cast<int64_t>(pro[cls][o].size())));
     }
+  }
+  // physical boundary conditions: blocks on a non-periodic mesh face
+  {
+    std::vector<pb2_bc_region> regs[2][3];
+    for (auto &pmb : md->GetBlockList())
+      for (int face = 0; face < 2 * pm->ndim; ++face) {
+        const BoundaryFlag flag = pmb->boundary_flag[face];
+        if (flag != BoundaryFlag::outflow && flag != BoundaryFlag::reflect) continue;
+        const int d = face / 2;
+        for (Variable *v : c.vars) {
+          if (!v->IsAllocated(pmb->pack_index)) continue;
+          for (int cf = 0; cf < (pm->multilevel ? 2 : 1); ++cf) {
+            const IndexShape &shape = cf ? pmb->c_cellbounds : pmb->cellbounds;
+            pb2_bc_region r{};
+            r.var = cf ? v->coarse() + pmb->pack_index * v->cblock_stride
+                       : v->data() + pmb->pack_index * v->block_stride;
+            r.face = face;
+            r.type = flag == BoundaryFlag::outflow ? PB2_BC_OUTFLOW : PB2_BC_REFLECT;
+            r.ncomp = v->NumComponents();
+            r.n[0] = cf ? v->cni : v->ni;
+            r.n[1] = cf ? v->cnj : v->nj;
+            r.n[2] = cf ? v->cnk : v->nk;
+            const IndexRange b = shape.Bounds(d, IndexDomain::interior);
+            r.is = b.s;
+            r.ie = b.e;
+            r.stride_c = static_cast<int32_t>(cf ? v->ccomp_stride : v->comp_stride);
+            // Metadata::Vector fields flip the component along the normal
+            // (boundary_conditions_generic.hpp:225-228)
+            r.flip_mask = v->IsSet(Metadata::Vector) && d < r.ncomp ? (1u << d) : 0u;
+            regs[cf][d].push_back(r);
+            c.has_bcs = true;
+          }
+        }
+      }
+    for (int cf = 0; cf < 2; ++cf)
+      for (int d = 0; d < 3; ++d)
+        PB2_CHECK(pb2_bc_table_create(&c.bc[cf][d], regs[cf][d].data(),
+                                      static_cast<int64_t>(regs[cf][d].size())));
   }
   // boundary / interior split of the batch for comm-compute overlap
   {
@@ -892,10 +935,22 @@ void FluxCorrection(MeshData<Real> *md) {
 }
 
 TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &) {
-  return TaskStatus::complete; // periodic: filled by the neighbour exchange
-}
-TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &, bool) {
+  // the batch form below does every block of the MeshData in one launch per direction;
+  // drivers written against this framework call it instead of looping over blocks
   return TaskStatus::complete;
+}
+TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &md,
+                                                   bool coarse) {
+  BvarsCache &c = Cache(md);
+  if (!c.has_bcs) return TaskStatus::complete; // periodic: filled by the neighbour exchange
+  // faces in BoundaryFace order; inner and outer slabs of one direction are disjoint, so a
+  // direction is one launch (boundary_conditions.cpp:47-55)
+  for (int d = 0; d < md->GetMeshPointer()->ndim; ++d)
+    PB2_CHECK(pb2_apply_bcs(c.bc[coarse ? 1 : 0][d], md->stream()));
+  return TaskStatus::complete;
+}
+TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md) {
+  return ApplyBoundaryConditionsOnCoarseOrFineMD(md, false);
 }
 
 TaskID AddBoundaryExchangeTasks(TaskID dependency, TaskList &tl,
@@ -924,8 +979,14 @@ void CommunicateBoundaries(std::shared_ptr<MeshData<Real>> &md, bool prolongate)
                       "local boundary buffers were not published");
     SetBounds<BoundaryType::any>(m);
   }
-  if (prolongate && pm->multilevel)
-    for (auto &m : parts) ProlongateBounds<BoundaryType::any>(m);
+  // mesh.cpp:698-706: coarse BCs + prolongation, then the fine BCs
+  for (auto &m : parts) {
+    if (prolongate && pm->multilevel) {
+      ApplyBoundaryConditionsOnCoarseOrFineMD(m, true);
+      ProlongateBounds<BoundaryType::any>(m);
+    }
+    ApplyBoundaryConditionsOnCoarseOrFineMD(m, false);
+  }
 }
 
 } // namespace parthenon

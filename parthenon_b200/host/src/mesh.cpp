@@ -333,10 +333,15 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
     mesh_bcs[2 * d] = ParseBoundary(pin->GetOrAddString("parthenon/mesh", bc_names[2 * d], "periodic"));
     mesh_bcs[2 * d + 1] =
         ParseBoundary(pin->GetOrAddString("parthenon/mesh", bc_names[2 * d + 1], "periodic"));
-    if (d < ndim)
-      PARTHENON_REQUIRE(mesh_bcs[2 * d] == BoundaryFlag::periodic &&
-                            mesh_bcs[2 * d + 1] == BoundaryFlag::periodic,
-                        "only periodic mesh boundaries are supported by this build");
+    if (d < ndim) {
+      for (int f = 2 * d; f < 2 * d + 2; ++f)
+        PARTHENON_REQUIRE(mesh_bcs[f] == BoundaryFlag::periodic || mesh_bcs[f] == BoundaryFlag::outflow ||
+                              mesh_bcs[f] == BoundaryFlag::reflect,
+                          "mesh boundaries must be periodic, outflow or reflecting in this build");
+      PARTHENON_REQUIRE((mesh_bcs[2 * d] == BoundaryFlag::periodic) ==
+                            (mesh_bcs[2 * d + 1] == BoundaryFlag::periodic),
+                        "a direction is periodic on both faces or on neither");
+    }
   }
   // Leaves are ordered by their Morton key in the smallest 2^n cube that holds the root
   // grid.  For a cubic 2^n root grid this is the reference's single-tree order
@@ -380,6 +385,11 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
     mb->c_cellbounds = IndexShape(ndim > 2 ? std::max(1, nx3 / 2) : 0,
                                   ndim > 1 ? std::max(1, nx2 / 2) : 0, std::max(1, nx1 / 2), ng);
     mb->coords = UniformCartesian(mb->block_size, ng);
+    for (int d = 0; d < ndim; ++d) {
+      if (mb->loc.lx[d] == 0) mb->boundary_flag[2 * d] = mesh_bcs[2 * d];
+      if (mb->loc.lx[d] == BlocksAtLevel(mb->loc.level, d) - 1)
+        mb->boundary_flag[2 * d + 1] = mesh_bcs[2 * d + 1];
+    }
     mb->pmy_mesh = this;
     const int ps = DefaultPackSizeFor(static_cast<int>(nblist[rank]));
     mb->partition = mb->lid / ps;

@@ -145,6 +145,34 @@ def test_multilevel_exchange_matches_oracle():
         assert np.array_equal(sim.get_field("base", "U"), Uref)
 
 
+BC_OVERRIDES = {"parthenon/mesh/ix1_bc": "outflow", "parthenon/mesh/ox1_bc": "outflow",
+                "parthenon/mesh/ix2_bc": "reflecting", "parthenon/mesh/ox2_bc": "reflecting"}
+
+
+@pytest.mark.parametrize("fused,math,extra", [(True, "strict", None), (False, "strict", None),
+                                              (True, "strict", {"pb2/virtual_ranks": 2}),
+                                              (True, "fast", None)])
+def test_physical_boundaries_vs_reference_dumps(fused, math, extra):
+    """outflow x1 / reflecting x2 / periodic x3 mesh boundaries: neighbour topology without
+    wrap-around + pb2_apply_bcs after the exchange, against a reference run"""
+    g = np.load(os.path.join(GOLD, "burgers_u16_b8_s1_weno5_bc.npz"))
+    ov = dict(BC_OVERRIDES)
+    if extra:
+        ov.update(extra)
+    sim = host.Simulation(overrides=burgers_overrides(8, 2, 4, 1, "weno5", math, fused, ov))
+    sim.pre_execute()
+    assert sim.dt == g["dts"][0]
+    assert np.array_equal(sim.get_field("base", "U"), g["U_0"])
+    for c in (1, 2, 3):
+        sim.cycle()
+        U, ref = sim.get_field("base", "U"), g[f"U_{c}"]
+        if math == "strict":
+            assert np.array_equal(U, ref), f"cycle {c}"
+            assert sim.time == g["times"][c]
+        else:
+            assert np.abs(U - ref).max() / np.abs(ref).max() <= TOL
+
+
 MULTILEVEL = [("burgers_s16_b8_l2_weno5", (16, 16, 16), (8, 8, 8), 3),
               ("burgers_s64_b8_l3_2d_weno5", (64, 64, 1), (8, 8, 1), 2)]
 

@@ -392,6 +392,60 @@ def test_flux_correct_multilevel(ndim, nx, nrb, refine):
         assert np.array_equal(Fd[d].cpu().numpy(), Fref[d]), d
 
 
+def test_apply_bcs_outflow_reflect():
+    """pb2_apply_bcs against the oracle (outflow / reflect, faces applied in order so edges and
+    corners outside the mesh are right), plus the sign flip of a vector's normal component"""
+    bcs = ("outflow", "reflecting", "reflecting", "outflow", "reflecting", "reflecting")
+    m = oracle.Mesh(3, (8, 6, 4), 3, (2, 2, 2), bcs=bcs)
+    ncomp, ng = 3, 3
+    U = rand_field(m, ncomp, 21)
+    Uref = U.copy()
+    m.apply_bcs(Uref)
+    assert not np.array_equal(U, Uref)
+    Ud = torch.from_numpy(U).to(DEV)
+    nk, nj, ni = m.dims
+    sj, sk, sc = H.strides(m.dims)
+    code = {"outflow": 0, "reflecting": 1}
+
+    def tables(flip):
+        per_dir = [[], [], []]
+        for b in range(m.nblocks):
+            loc = m.block_loc(b)
+            for face in range(6):
+                d, inner = face // 2, face % 2 == 0
+                if loc[1 + d] != (0 if inner else 1):
+                    continue
+                r = capi.BcRegion()
+                r.var = Ud.data_ptr() + 8 * b * ncomp * sc
+                r.face, r.type, r.ncomp = face, code[bcs[face]], ncomp
+                r.n[:] = [ni, nj, nk]
+                r.is_, r.ie = ng, ng + (8, 6, 4)[d] - 1
+                r.stride_c = sc
+                r.flip_mask = (1 << d) if flip else 0
+                per_dir[d].append(r)
+        return [capi.Table(x, "bc") for x in per_dir]
+
+    L = capi.lib()
+    for t in tables(False):
+        capi.check(L.pb2_apply_bcs(t.h, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(Ud.cpu().numpy(), Uref)
+    # vector field (components = x1, x2, x3): reflecting faces flip the normal component
+    V = rand_field(m, ncomp, 22)
+    Vd = torch.from_numpy(V).to(DEV)
+    Ud = Vd
+    for t in tables(True):
+        capi.check(L.pb2_apply_bcs(t.h, None))
+    torch.cuda.synchronize()
+    out = Vd.cpu().numpy()
+    b = 0  # block (0,0,0): inner faces; ix1 outflow (no flip), ix2 / ix3 reflecting
+    assert np.array_equal(out[b, :, ng:-ng, ng:-ng, :ng],
+                          np.repeat(V[b, :, ng:-ng, ng:-ng, ng:ng + 1], ng, axis=-1))
+    mirror = V[b, :, ng:-ng, ng:2 * ng, ng:-ng][:, :, ::-1, :]
+    sign = np.array([1.0, -1.0, 1.0])[:, None, None, None]
+    assert np.array_equal(out[b, :, ng:-ng, :ng, ng:-ng], sign * mirror)
+
+
 def test_weighted_sum_and_flux_div():
     n = 100003
     x = torch.randn(n, dtype=torch.float64, device=DEV)
