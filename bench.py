@@ -125,6 +125,9 @@ def cpu_oracle_rate(nx, block, steps, warmup):
     """the reference's algorithm restated on the CPU (oracle/, test infrastructure), all host
     threads: zone-cycles/s on a bounded sample of the workload"""
     import oracle
+    # all the host threads this process may use — torchrun exports OMP_NUM_THREADS=1, which
+    # would otherwise turn the reference arm into a single-thread run
+    oracle.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
     nrb = nx // block
     m = oracle.Mesh(3, (block,) * 3, 4, (nrb,) * 3)
     B = oracle.Burgers(m, num_scalars=NCOMP - 3, recon="weno5", cfl=0.8)
