@@ -1453,7 +1453,7 @@ struct OrcSparse {
   const OrcMesh *m;
   double cfl, alloc_thr, dealloc_thr, init_size;
   int dealloc_count;
-  double vx[ORC_NF], vy[ORC_NF], x0[ORC_NF], y0[ORC_NF];
+  double vx[ORC_NF], vy[ORC_NF], vz[ORC_NF], x0[ORC_NF], y0[ORC_NF];
   size_t ncell, nfield; /* per field: nblocks * ncell */
   double *U[ORC_NF], *U1[ORC_NF], *dUdt[ORC_NF], *flux[ORC_NF][3];
   unsigned char *alloc; /* [nblocks][NF] */
@@ -1482,6 +1482,7 @@ OrcSparse *orc_sparse_create(const OrcMesh *m, double speed, double cfl, double 
     s->y0[f] = y0[f];
     s->vx[f] = vx[f];
     s->vy[f] = vy[f];
+    s->vz[f] = 0.0; /* sparse_advection_package.cpp:70 */
     s->U[f] = (double *)calloc(s->nfield, sizeof(double));
     s->U1[f] = (double *)calloc(s->nfield, sizeof(double));
     s->dUdt[f] = (double *)calloc(s->nfield, sizeof(double));
@@ -1625,6 +1626,7 @@ static double sparse_estimate_timestep(const OrcSparse *st) {
     for (int f = 0; f < ORC_NF; ++f) {
       if (st->vx[f] != 0.0) bdt = fmin(bdt, blk->dx[0] / fabs(st->vx[f]));
       if (st->vy[f] != 0.0) bdt = fmin(bdt, blk->dx[1] / fabs(st->vy[f]));
+      if (st->vz[f] != 0.0) bdt = fmin(bdt, blk->dx[2] / fabs(st->vz[f]));
     }
     min_dt = fmin(min_dt, st->cfl * bdt);
   }
@@ -1660,27 +1662,33 @@ static void sparse_dealloc(OrcSparse *st, double *const U[ORC_NF]) {
 static void sparse_stage(OrcSparse *st, int stage) {
   const OrcMesh *m = st->m;
   const double beta = stage == 1 ? 1.0 : 0.5;
-  const size_t sj = (size_t)m->n[0];
+  const size_t sj = (size_t)m->n[0], sk = (size_t)m->n[0] * m->n[1];
+  const int dim3 = m->ndim > 2; /* the reference stops at 2-D (:256-257); the x3 terms below
+                                   are the same donor-cell / divergence formulas one
+                                   direction further (no reference parity in 3-D) */
   for (int f = 0; f < ORC_NF; ++f) {
     double *mc0 = stage == 1 ? st->U[f] : st->U1[f];
     double *mc1 = stage == 1 ? st->U1[f] : st->U[f];
     double *base = st->U[f];
-    const double v[2] = {st->vx[f], st->vy[f]};
+    const double v[3] = {st->vx[f], st->vy[f], st->vz[f]};
     for (int b = 0; b < m->nblocks; ++b) {
       if (!st->alloc[b * ORC_NF + f]) continue; /* IsAllocated guards everywhere */
       const Block *blk = &m->blocks[b];
       /* CalculateFluxes sparse_advection_package.cpp:173-258 (donor cell) */
-      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+      for (int k = m->is[2]; k <= m->ie[2] + dim3; ++k)
         for (int j = m->is[1]; j <= m->ie[1] + 1; ++j)
           for (int i = m->is[0]; i <= m->ie[0] + 1; ++i) {
             const size_t p = fidx(m, 1, b, 0, k, j, i);
-            if (j <= m->ie[1])
+            if (j <= m->ie[1] && k <= m->ie[2])
               st->flux[f][0][p] = (v[0] > 0.0 ? mc0[p - 1] : mc0[p]) * v[0];
-            if (i <= m->ie[0])
+            if (i <= m->ie[0] && k <= m->ie[2])
               st->flux[f][1][p] = (v[1] > 0.0 ? mc0[p - sj] : mc0[p]) * v[1];
+            if (dim3 && i <= m->ie[0] && j <= m->ie[1])
+              st->flux[f][2][p] = (v[2] > 0.0 ? mc0[p - sk] : mc0[p]) * v[2];
           }
       /* FluxDivergence update.cpp:63-86 */
-      const double a1 = blk->dx[1] * blk->dx[2], a2 = blk->dx[0] * blk->dx[2];
+      const double a1 = blk->dx[1] * blk->dx[2], a2 = blk->dx[0] * blk->dx[2],
+                   a3 = blk->dx[0] * blk->dx[1];
       const double vol = blk->dx[0] * blk->dx[1] * blk->dx[2];
       for (int k = m->is[2]; k <= m->ie[2]; ++k)
         for (int j = m->is[1]; j <= m->ie[1]; ++j)
@@ -1688,6 +1696,7 @@ static void sparse_stage(OrcSparse *st, int stage) {
             const size_t p = fidx(m, 1, b, 0, k, j, i);
             double du = (a1 * st->flux[f][0][p + 1] - a1 * st->flux[f][0][p]);
             du += (a2 * st->flux[f][1][p + sj] - a2 * st->flux[f][1][p]);
+            if (dim3) du += (a3 * st->flux[f][2][p + sk] - a3 * st->flux[f][2][p]);
             st->dUdt[f][p] = -du / vol;
           }
       /* Average / UpdateIndependentData update.hpp:71-91 over the entire extents */
