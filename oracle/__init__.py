@@ -111,6 +111,22 @@ def lib():
         L.orc_sparse_dt.argtypes = [C.c_void_p]
         L.orc_sparse_time.restype = C.c_double
         L.orc_sparse_time.argtypes = [C.c_void_p]
+        L.orc_amr_create.restype = C.c_void_p
+        L.orc_amr_create.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
+                                     C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, dp,
+                                     C.c_double]
+        L.orc_amr_destroy.argtypes = [C.c_void_p]
+        L.orc_amr_mesh.restype = C.c_void_p
+        L.orc_amr_mesh.argtypes = [C.c_void_p]
+        L.orc_amr_U.restype = dp
+        L.orc_amr_U.argtypes = [C.c_void_p]
+        L.orc_amr_init.argtypes = [C.c_void_p]
+        L.orc_amr_step.argtypes = [C.c_void_p]
+        L.orc_amr_regrid.argtypes = [C.c_void_p]
+        L.orc_amr_dt.restype = C.c_double
+        L.orc_amr_dt.argtypes = [C.c_void_p]
+        L.orc_amr_time.restype = C.c_double
+        L.orc_amr_time.argtypes = [C.c_void_p]
         L.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
 
@@ -331,6 +347,73 @@ class Advection:
     @property
     def time(self):
         return lib().orc_advection_time(self.h)
+
+
+class AmrAdvection:
+    """example/advection with refinement = adaptive: the mesh is owned by the C side and
+    changes as blocks are refined / derefined"""
+
+    def __init__(self, ndim, nx, ng, nrb, numlevel, derefine_count=10, refine_tol=0.3,
+                 derefine_tol=0.03, vec_size=1, profile="hard_sphere", amp=1e-6,
+                 v=(1.0, 1.0, 1.0), cfl=0.45, xmin=(-0.5,) * 3, xmax=(0.5,) * 3):
+        L = lib()
+        self.ndim, self.ncomp = ndim, vec_size
+        nx3 = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
+        nrb3 = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
+        vv = np.array(v, dtype=np.float64)
+        lo, hi = np.array(xmin, dtype=np.float64), np.array(xmax, dtype=np.float64)
+        self.h = L.orc_amr_create(ndim, _ip(nx3), ng, _ip(nrb3), _dp(lo), _dp(hi), numlevel,
+                                  derefine_count, refine_tol, derefine_tol, vec_size,
+                                  Advection.PROFILES[profile], amp, _dp(vv), cfl)
+
+    def __del__(self):
+        try:
+            lib().orc_amr_destroy(self.h)
+        except Exception:
+            pass
+
+    def init(self):
+        lib().orc_amr_init(self.h)
+
+    def step(self):
+        """Step + tagging; the mesh is adapted by regrid()"""
+        lib().orc_amr_step(self.h)
+
+    def regrid(self):
+        return bool(lib().orc_amr_regrid(self.h))
+
+    def _mesh(self):
+        return lib().orc_amr_mesh(self.h)
+
+    @property
+    def nblocks(self):
+        return lib().orc_mesh_nblocks(self._mesh())
+
+    @property
+    def block_locs(self):
+        L, mh = lib(), self._mesh()
+        out = np.zeros((self.nblocks, 4), dtype=np.int32)
+        o = np.zeros(4, dtype=np.int32)
+        for b in range(out.shape[0]):
+            L.orc_mesh_block_loc(mh, b, _ip(o))
+            out[b] = o
+        return out
+
+    @property
+    def U(self):
+        L, mh = lib(), self._mesh()
+        d, c = np.zeros(3, dtype=np.int32), np.zeros(3, dtype=np.int32)
+        L.orc_mesh_dims(mh, _ip(d), _ip(c))
+        shape = (self.nblocks, self.ncomp) + tuple(int(x) for x in d)
+        return np.ctypeslib.as_array(L.orc_amr_U(self.h), shape=(int(np.prod(shape)),)).reshape(shape).copy()
+
+    @property
+    def dt(self):
+        return lib().orc_amr_dt(self.h)
+
+    @property
+    def time(self):
+        return lib().orc_amr_time(self.h)
 
 
 class SparseAdvection:

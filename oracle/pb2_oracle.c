@@ -1319,9 +1319,8 @@ OrcAdvection *orc_advection_create(const OrcMesh *m, int vec_size, int profile, 
   s->U1 = (double *)calloc(s->nfield, sizeof(double));
   s->dUdt = (double *)calloc(s->nfield, sizeof(double));
   for (int d = 0; d < 3; ++d) s->flux[d] = (double *)calloc(s->nfield, sizeof(double));
-  if (m->multilevel)
-    s->Uc = (double *)calloc((size_t)m->nblocks * s->ncomp * m->cn[0] * m->cn[1] * m->cn[2],
-                             sizeof(double));
+  s->Uc = (double *)calloc((size_t)m->nblocks * s->ncomp * m->cn[0] * m->cn[1] * m->cn[2],
+                           sizeof(double));
   s->dt = DBL_MAX;
   return s;
 }
@@ -1434,6 +1433,441 @@ void orc_advection_step(OrcAdvection *st) {
   if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0; /* SetGlobalTimeStep driver.cpp:210-270 */
   st->dt = fmin(st->dt, st->allowed_dt);
   st->allowed_dt = DBL_MAX;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* adaptive mesh refinement for example/advection (refinement = adaptive):
+ *   tagging      Refinement::Tag -> advection_package::CheckRefinement
+ *                (advection_package.cpp:239-273) -> MeshRefinement::SetRefinement
+ *                (mesh/mesh_refinement.cpp:81-118)
+ *   tree update  Mesh::UpdateMeshBlockTree (mesh-amr_loadbalance.cpp:496-625) with
+ *                Tree::Refine / Tree::Derefine (mesh/forest/tree.cpp:93-143, 229-275:
+ *                proper nesting enforced)
+ *   data         Mesh::RedistributeAndRefineMeshBlocks (:663-1010): kept blocks keep their
+ *                arrays, derefined blocks are restricted (GetInteriorRestrict) and copied into
+ *                the new parent (TryRecvFineToCoarse :196-251), refined blocks get the
+ *                parent's data in their coarse buffer (TryRecvCoarseToFine :87-149) and are
+ *                prolongated over interior + ghosts (GetInteriorProlongate), then
+ *                CommunicateBoundaries
+ *   driver       EvolutionDriver::Execute (driver.cpp:99-150), Mesh::Initialize's refinement
+ *                loop (mesh.cpp:745-860)
+ * Single process (no load balancing across ranks). */
+typedef struct {
+  Loc *leaf;
+  int n, cap;
+} LeafSet;
+
+static int loc_eq(const Loc *a, const Loc *b) {
+  return a->level == b->level && a->lx[0] == b->lx[0] && a->lx[1] == b->lx[1] &&
+         a->lx[2] == b->lx[2];
+}
+static int ls_find(const LeafSet *t, const Loc *l) {
+  for (int i = 0; i < t->n; ++i)
+    if (loc_eq(&t->leaf[i], l)) return i;
+  return -1;
+}
+static int ls_internal(const LeafSet *t, const Loc *l) { /* some leaf lies strictly below l */
+  for (int i = 0; i < t->n; ++i) {
+    const Loc *q = &t->leaf[i];
+    if (q->level <= l->level) continue;
+    const int sh = q->level - l->level;
+    if ((q->lx[0] >> sh) == l->lx[0] && (q->lx[1] >> sh) == l->lx[1] &&
+        (q->lx[2] >> sh) == l->lx[2])
+      return 1;
+  }
+  return 0;
+}
+static void ls_add(LeafSet *t, const Loc *l) {
+  if (t->n == t->cap) {
+    t->cap = t->cap ? 2 * t->cap : 64;
+    t->leaf = (Loc *)realloc(t->leaf, sizeof(Loc) * (size_t)t->cap);
+  }
+  t->leaf[t->n++] = *l;
+}
+static void ls_remove(LeafSet *t, int i) { t->leaf[i] = t->leaf[--t->n]; }
+static int ndaughters(const OrcMesh *m) { return 1 << m->ndim; }
+static Loc daughter(const OrcMesh *m, const Loc *p, int q) { /* ox1 fastest */
+  Loc d;
+  d.level = p->level + 1;
+  for (int k = 0; k < 3; ++k) d.lx[k] = k < m->ndim ? (p->lx[k] << 1) + ((q >> k) & 1) : 0;
+  return d;
+}
+static Loc parent_of(const OrcMesh *m, const Loc *l) {
+  Loc p;
+  p.level = l->level - 1;
+  for (int k = 0; k < 3; ++k) p.lx[k] = k < m->ndim ? (l->lx[k] >> 1) : 0;
+  return p;
+}
+
+/* Tree::Refine tree.cpp:93-143 */
+static int tree_refine(const OrcMesh *m, LeafSet *t, const Loc *ref) {
+  const int i0 = ls_find(t, ref);
+  if (i0 < 0) return 0; /* can't refine a block that doesn't exist */
+  ls_remove(t, i0);
+  const int nd = ndaughters(m);
+  for (int q = 0; q < nd; ++q) {
+    Loc d = daughter(m, ref, q);
+    ls_add(t, &d);
+  }
+  int nadded = nd - 1;
+  if (ref->level <= m->root_level) return nadded; /* no leaves above the root grid */
+  /* proper nesting: the same-level neighbours of the PARENT on the side of this block */
+  const Loc par = parent_of(m, ref);
+  const int ox[3] = {(int)(ref->lx[0] - (par.lx[0] << 1)), (int)(ref->lx[1] - (par.lx[1] << 1)),
+                     (int)(ref->lx[2] - (par.lx[2] << 1))};
+  for (int k = 0; k < (m->ndim > 2 ? 2 : 1); ++k)
+    for (int j = 0; j < (m->ndim > 1 ? 2 : 1); ++j)
+      for (int i = 0; i < 2; ++i) {
+        Loc neigh = par, w;
+        neigh.lx[0] += i + ox[0] - 1;
+        neigh.lx[1] += j + ox[1] - (m->ndim > 1);
+        neigh.lx[2] += k + ox[2] - (m->ndim > 2);
+        if (!wrap_loc(m, &neigh, &w)) continue; /* no tree on that side */
+        nadded += tree_refine(m, t, &w);
+      }
+  return nadded;
+}
+
+/* Tree::Derefine tree.cpp:229-275 */
+static int tree_derefine(const OrcMesh *m, LeafSet *t, const Loc *ref) {
+  const int nd = ndaughters(m);
+  for (int q = 0; q < nd; ++q) {
+    const Loc d = daughter(m, ref, q);
+    if (ls_find(t, &d) < 0) return 0;
+    for (int k = (m->ndim > 2 ? -1 : 0); k <= (m->ndim > 2 ? 1 : 0); ++k)
+      for (int j = (m->ndim > 1 ? -1 : 0); j <= (m->ndim > 1 ? 1 : 0); ++j)
+        for (int i = -1; i <= 1; ++i) {
+          Loc neigh = d, w;
+          neigh.lx[0] += i;
+          neigh.lx[1] += j;
+          neigh.lx[2] += k;
+          if (!wrap_loc(m, &neigh, &w)) continue;
+          if (ls_internal(t, &w)) return 0; /* would abut a block two levels finer */
+        }
+  }
+  for (int q = 0; q < nd; ++q) {
+    const Loc d = daughter(m, ref, q);
+    ls_remove(t, ls_find(t, &d));
+  }
+  ls_add(t, ref);
+  return nd - 1;
+}
+
+struct OrcAmr {
+  /* mesh definition */
+  int ndim, nx[3], ng, nrb[3], bc[6];
+  double xmin[3], xmax[3];
+  int max_level, deref_threshold;
+  double refine_tol, derefine_tol;
+  OrcMesh *m;
+  OrcAdvection *adv;  /* state on the current mesh */
+  int *deref_count;   /* per block: MeshRefinement::deref_count_ */
+  int *refine_flag;   /* per block: MeshRefinement::refine_flag_ */
+  int profile;
+  double amp, v[3], cfl;
+  int ncomp;
+};
+
+static OrcMesh *amr_make_mesh(const struct OrcAmr *a, const LeafSet *t) {
+  int *lv = (int *)malloc(sizeof(int) * 4 * (size_t)t->n);
+  for (int i = 0; i < t->n; ++i) {
+    lv[4 * i] = t->leaf[i].level;
+    for (int d = 0; d < 3; ++d) lv[4 * i + 1 + d] = (int)t->leaf[i].lx[d];
+  }
+  orc_mesh_set_next_bcs(a->bc);
+  OrcMesh *m = orc_mesh_create(a->ndim, a->nx, a->ng, a->nrb, a->xmin, a->xmax, t->n, lv);
+  orc_mesh_set_next_bcs(NULL);
+  free(lv);
+  if (m) m->multilevel = 1; /* refinement != none (mesh.cpp:118-140) */
+  return m;
+}
+
+struct OrcAmr *orc_amr_create(int ndim, const int nx[3], int ng, const int nrb[3],
+                              const double xmin[3], const double xmax[3], int numlevel,
+                              int derefine_count, double refine_tol, double derefine_tol,
+                              int vec_size, int profile, double amp, const double v[3],
+                              double cfl) {
+  struct OrcAmr *a = (struct OrcAmr *)calloc(1, sizeof(struct OrcAmr));
+  a->ndim = ndim;
+  a->ng = ng;
+  for (int d = 0; d < 3; ++d) {
+    a->nx[d] = nx[d];
+    a->nrb[d] = nrb[d];
+    a->xmin[d] = xmin[d];
+    a->xmax[d] = xmax[d];
+    a->v[d] = v[d];
+  }
+  a->deref_threshold = derefine_count;
+  a->refine_tol = refine_tol;
+  a->derefine_tol = derefine_tol;
+  a->profile = profile;
+  a->amp = amp;
+  a->cfl = cfl;
+  a->ncomp = vec_size;
+  /* root grid */
+  LeafSet t = {0, 0, 0};
+  int rl = 0;
+  while ((1 << rl) < nrb[0]) ++rl;
+  for (int k = 0; k < (ndim > 2 ? nrb[2] : 1); ++k)
+    for (int j = 0; j < (ndim > 1 ? nrb[1] : 1); ++j)
+      for (int i = 0; i < nrb[0]; ++i) {
+        Loc l = {rl, {i, j, k}};
+        ls_add(&t, &l);
+      }
+  a->max_level = numlevel + rl - 1; /* mesh.cpp:125 */
+  a->m = amr_make_mesh(a, &t);
+  free(t.leaf);
+  a->adv = orc_advection_create(a->m, vec_size, profile, amp, v, cfl);
+  a->deref_count = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
+  a->refine_flag = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
+  return a;
+}
+void orc_amr_destroy(struct OrcAmr *a) {
+  if (!a) return;
+  orc_advection_destroy(a->adv);
+  orc_mesh_destroy(a->m);
+  free(a->deref_count);
+  free(a->refine_flag);
+  free(a);
+}
+const OrcMesh *orc_amr_mesh(const struct OrcAmr *a) { return a->m; }
+double *orc_amr_U(struct OrcAmr *a) { return a->adv->U; }
+double orc_amr_dt(const struct OrcAmr *a) { return a->adv->dt; }
+double orc_amr_time(const struct OrcAmr *a) { return a->adv->time; }
+
+/* CheckRefinement + SetRefinement for every block, on container U */
+static void amr_tag(struct OrcAmr *a, const double *U) {
+  const OrcMesh *m = a->m;
+  const size_t per_block = (size_t)a->ncomp * m->n[0] * m->n[1] * m->n[2];
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    double mn = DBL_MAX, mx = -DBL_MAX; /* Kokkos::MinMax identity */
+    const double *p = U + (size_t)b * per_block;
+    for (size_t q = 0; q < per_block; ++q) {
+      mn = p[q] < mn ? p[q] : mn;
+      mx = p[q] > mx ? p[q] : mx;
+    }
+    int aret = 0; /* AmrTag: derefine -1, same 0, refine 1 */
+    if (mx > a->refine_tol && mn < a->derefine_tol)
+      aret = 1;
+    else if (mx < a->derefine_tol)
+      aret = -1;
+    int *flag = &a->refine_flag[b], *cnt = &a->deref_count[b];
+    if (aret == 0) *flag = 0;
+    if (aret >= 0) *cnt = 0;
+    if (aret > 0) {
+      *flag = blk->loc.level == a->max_level ? 0 : 1;
+    } else if (aret < 0) {
+      if (blk->loc.level == m->root_level) {
+        *flag = 0;
+        *cnt = 0;
+      } else {
+        (*cnt)++;
+        int ec = 0;
+        for (int n = 0; n < blk->nnb; ++n)
+          if (blk->nb[n].loc.level > blk->loc.level) ec++;
+        if (ec > 0)
+          *flag = 0;
+        else
+          *flag = *cnt >= a->deref_threshold ? -1 : 0;
+      }
+    }
+  }
+}
+
+static int cmp_level_desc(const void *x, const void *y) {
+  return ((const Loc *)y)->level - ((const Loc *)x)->level;
+}
+
+/* LoadBalancingAndAdaptiveMeshRefinement: returns 1 if the mesh changed */
+static int amr_remesh(struct OrcAmr *a) {
+  const OrcMesh *m = a->m;
+  const int nleaf = ndaughters(m);
+  int tnref = 0, tnderef = 0;
+  for (int b = 0; b < m->nblocks; ++b) {
+    tnref += a->refine_flag[b] == 1;
+    tnderef += a->refine_flag[b] == -1;
+  }
+  if (tnref == 0 && tnderef < nleaf) return 0;
+  Loc *lref = (Loc *)malloc(sizeof(Loc) * (size_t)(tnref + 1));
+  Loc *lderef = (Loc *)malloc(sizeof(Loc) * (size_t)(tnderef + 1));
+  Loc *clderef = (Loc *)malloc(sizeof(Loc) * (size_t)(tnderef / nleaf + 1));
+  int ir = 0, id = 0;
+  for (int b = 0; b < m->nblocks; ++b) {
+    if (a->refine_flag[b] == 1) lref[ir++] = m->blocks[b].loc;
+    if (a->refine_flag[b] == -1 && tnderef >= nleaf) lderef[id++] = m->blocks[b].loc;
+  }
+  int ctnd = 0;
+  if (tnderef >= nleaf) {
+    const int lk = m->ndim > 2, lj = m->ndim > 1;
+    for (int n = 0; n < tnderef; ++n) {
+      if ((lderef[n].lx[0] & 1L) || (lderef[n].lx[1] & 1L) || (lderef[n].lx[2] & 1L)) continue;
+      int r = n, rr = 0;
+      for (long k = 0; k <= lk; ++k)
+        for (long j = 0; j <= lj; ++j)
+          for (long i = 0; i <= 1; ++i) {
+            if (r < tnderef) {
+              if (lderef[n].lx[0] + i == lderef[r].lx[0] && lderef[n].lx[1] + j == lderef[r].lx[1] &&
+                  lderef[n].lx[2] + k == lderef[r].lx[2] && lderef[n].level == lderef[r].level)
+                rr++;
+              r++;
+            }
+          }
+      if (rr == nleaf) clderef[ctnd++] = parent_of(m, &lderef[n]);
+    }
+  }
+  /* :597-602 sorts [first, last) with last = &clderef[ctnd - 1]: all but the final entry */
+  if (ctnd > 1) qsort(clderef, (size_t)(ctnd - 1), sizeof(Loc), cmp_level_desc);
+
+  LeafSet t = {0, 0, 0};
+  for (int b = 0; b < m->nblocks; ++b) ls_add(&t, &m->blocks[b].loc);
+  int nnew = 0, ndel = 0;
+  for (int n = 0; n < tnref; ++n) nnew += tree_refine(m, &t, &lref[n]);
+  for (int n = 0; n < ctnd; ++n) ndel += tree_derefine(m, &t, &clderef[n]);
+  free(lref);
+  free(lderef);
+  free(clderef);
+  if (nnew == 0 && ndel == 0) {
+    free(t.leaf);
+    return 0;
+  }
+
+  /* ---- RedistributeAndRefineMeshBlocks ---- */
+  OrcMesh *nm = amr_make_mesh(a, &t);
+  free(t.leaf);
+  OrcAdvection *oa = a->adv;
+  OrcAdvection *na = orc_advection_create(nm, a->ncomp, a->profile, a->amp, a->v, a->cfl);
+  na->dt = oa->dt;
+  na->time = oa->time;
+  na->ncycle = oa->ncycle;
+  na->allowed_dt = oa->allowed_dt;
+  int *ncount = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  int *nflag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  const int nc = a->ncomp;
+  const size_t per_block = (size_t)nc * m->n[0] * m->n[1] * m->n[2];
+  const size_t cper_block = (size_t)nc * m->cn[0] * m->cn[1] * m->cn[2];
+  double *ctmp = (double *)calloc((size_t)m->nblocks * cper_block, sizeof(double));
+  for (int nb = 0; nb < nm->nblocks; ++nb) {
+    const Loc *nl = &nm->blocks[nb].loc;
+    /* same location in the old mesh: the block object is kept (all data, counters) */
+    int ob = find_leaf(m, nl);
+    if (ob >= 0) {
+      memcpy(na->U + (size_t)nb * per_block, oa->U + (size_t)ob * per_block,
+             per_block * sizeof(double));
+      ncount[nb] = a->deref_count[ob];
+      nflag[nb] = a->refine_flag[ob];
+      continue;
+    }
+    /* refined: the old parent was a leaf */
+    if (nl->level > 0) {
+      const Loc par = parent_of(m, nl);
+      ob = find_leaf(m, &par);
+      if (ob >= 0) {
+        /* TryRecvCoarseToFine :87-149: coarse buffer (entire extents) <- parent fine data */
+        int sh[3];
+        for (int d = 0; d < 3; ++d)
+          sh[d] = (d < m->ndim && (nl->lx[d] & 1L)) ? (m->ie[d] - m->is[d] + 1) / 2 : 0;
+        for (int c = 0; c < nc; ++c)
+          for (int k = 0; k < m->cn[2]; ++k)
+            for (int j = 0; j < m->cn[1]; ++j)
+              for (int i = 0; i < m->cn[0]; ++i)
+                na->Uc[cidx(nm, nc, nb, c, k, j, i)] =
+                    oa->U[fidx(m, nc, ob, c, k + sh[2], j + sh[1], i + sh[0])];
+        /* ProlongateShared over GetInteriorProlongate: coarse interior +- ng/2
+         * (bnd_info.cpp:199-203) */
+        int s[3], e[3];
+        for (int d = 0; d < 3; ++d) {
+          const int g2 = d < m->ndim ? m->ng / 2 : 0;
+          s[d] = nm->cis[d] - g2;
+          e[d] = nm->cie[d] + g2;
+        }
+        for (int c = 0; c < nc; ++c)
+          for (int k = s[2]; k <= e[2]; ++k)
+            for (int j = s[1]; j <= e[1]; ++j)
+              for (int i = s[0]; i <= e[0]; ++i) prolongate_cell(nm, na->U, na->Uc, nc, nb, c, k, j, i);
+        continue;
+      }
+    }
+    /* derefined: the daughters were leaves */
+    for (int q = 0; q < nleaf; ++q) {
+      const Loc d = daughter(m, nl, q);
+      ob = find_leaf(m, &d);
+      if (ob < 0) {
+        fprintf(stderr, "oracle: remesh cannot find the origin of a new block\n");
+        abort();
+      }
+      /* Restrict over GetInteriorRestrict (coarse interior) into the child's coarse buffer */
+      int s[3] = {m->cis[0], m->cis[1], m->cis[2]}, e[3] = {m->cie[0], m->cie[1], m->cie[2]};
+      restrict_region(m, oa->U, ctmp, nc, ob, s, e);
+      /* TryRecvFineToCoarse :196-251: parent fine sub-box <- child's coarse interior */
+      int sh[3];
+      for (int dd = 0; dd < 3; ++dd)
+        sh[dd] = (dd < m->ndim && (d.lx[dd] & 1L)) ? (m->cie[dd] - m->cis[dd] + 1) : 0;
+      for (int c = 0; c < nc; ++c)
+        for (int k = m->cis[2]; k <= m->cie[2]; ++k)
+          for (int j = m->cis[1]; j <= m->cie[1]; ++j)
+            for (int i = m->cis[0]; i <= m->cie[0]; ++i)
+              na->U[fidx(nm, nc, nb, c, k + sh[2], j + sh[1], i + sh[0])] =
+                  ctmp[cidx(m, nc, ob, c, k, j, i)];
+    }
+  }
+  free(ctmp);
+  orc_advection_destroy(oa);
+  orc_mesh_destroy(a->m);
+  free(a->deref_count);
+  free(a->refine_flag);
+  a->m = nm;
+  a->adv = na;
+  a->deref_count = ncount;
+  a->refine_flag = nflag;
+  /* PreCommFillDerived; CommunicateBoundaries; FillDerived  (:1000-1003) */
+  orc_exchange(nm, na->U, na->Uc, nc, 1);
+  orc_apply_bcs(nm, na->U, nc);
+  return 1;
+}
+
+/* Mesh::Initialize mesh.cpp:745-860 + EvolutionDriver::InitializeBlockTimeStepsAndBoundaries */
+void orc_amr_init(struct OrcAmr *a) {
+  int done;
+  do {
+    OrcAdvection *st = a->adv;
+    advection_ic(st);
+    orc_exchange(a->m, st->U, st->Uc, st->ncomp, 1);
+    orc_apply_bcs(a->m, st->U, st->ncomp);
+    amr_tag(a, st->U);
+    done = !amr_remesh(a);
+  } while (!done);
+  OrcAdvection *st = a->adv;
+  st->allowed_dt = advection_estimate_timestep(st);
+  st->dt = fmin(DBL_MAX, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+  st->time = 0;
+  st->ncycle = 0;
+}
+
+/* one pass of the main loop, driver.cpp:99-150, in two halves so that a caller can look at
+ * the state where the reference's PostStepUserWorkInLoop hook sees it (after Step, before
+ * the mesh is adapted):
+ *   orc_amr_step    Step (both stages, tagging on the last stage's container,
+ *                   advection_driver.cpp:158), ncycle / time advance
+ *   orc_amr_regrid  LoadBalancingAndAdaptiveMeshRefinement, InitializeBlockTimeSteps if the
+ *                   mesh changed, SetGlobalTimeStep; returns 1 if the mesh changed */
+void orc_amr_step(struct OrcAmr *a) {
+  OrcAdvection *st = a->adv;
+  orc_advection_stage(st, 1);
+  orc_advection_stage(st, 2);
+  amr_tag(a, st->U);
+  st->ncycle++;
+  st->time += st->dt;
+}
+int orc_amr_regrid(struct OrcAmr *a) {
+  const int changed = amr_remesh(a);
+  OrcAdvection *st = a->adv;
+  if (changed) st->allowed_dt = advection_estimate_timestep(st);
+  if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;
+  st->dt = fmin(st->dt, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+  return changed;
 }
 
 /* ------------------------------------------------------------------------------------ */

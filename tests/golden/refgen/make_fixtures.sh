@@ -131,6 +131,13 @@ run_advection advection_s16_b8_l3_gaussian 3 16 8 3 static 3 \
   Advection/profile=smooth_gaussian Advection/amp=1.0 Advection/vy=-0.7 Advection/vz=0.4
 run_advection advection_s16_b8_l3_hard_sphere 3 16 8 2 static 3 \
   "1:-0.3:0.2:-0.2:0.3:-0.3:0.1 2:-0.1:0.05:-0.05:0.12:-0.12:0.0"
+# ADAPTIVE meshes (configs[2] in small): refinement tagging, tree update with proper nesting,
+# refine / derefine data movement, every cycle.  The block list changes => per-cycle metadata.
+# derefine_count is lowered so that blocks are also merged within the run.
+export PB2_PER_CYCLE_META=1
+run_advection advection_a32_b8_l3_2d 2 32 8 40 adaptive 3 "" parthenon/mesh/derefine_count=3
+run_advection advection_a32_b8_l2_3d 3 32 8 8 adaptive 2 "" parthenon/mesh/derefine_count=2
+unset PB2_PER_CYCLE_META
 fi
 # example/sparse_advection (2-D only in the reference): four sparse fields allocated where
 # their data is, allocated on a neighbour when a non-null boundary buffer arrives, deallocated

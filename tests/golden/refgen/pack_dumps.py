@@ -39,6 +39,9 @@ def main(src_dir, out):
         arrays[f"U_{cycle}"] = data
         arrays["meta"] = meta
         arrays["bounds"] = bounds
+        if os.environ.get("PB2_PER_CYCLE_META"):  # adaptive meshes: the block list changes
+            arrays[f"meta_{cycle}"] = meta
+            arrays[f"bounds_{cycle}"] = bounds
         cycles.append(cycle)
         times.append(time)
         dts.append(dt)
