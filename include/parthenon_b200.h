@@ -275,6 +275,12 @@ int pb2_advection_fluxes_blocks(const pb2_pack_geom *g, const double *u, double 
 int pb2_block_quiet_flags(const pb2_pack_geom *g, const double *u, double threshold,
                           const int32_t *block_mask, int32_t *quiet, pb2_stream_t stream);
 
+/* Refinement tagging reduction (example/advection CheckRefinement, advection_package.cpp:
+ * 239-273): minmax[2b] / minmax[2b+1] = minimum / maximum of block b over all components and
+ * the ENTIRE extents; blocks with block_mask[b] == 0 are left untouched.  minmax: device. */
+int pb2_block_minmax(const pb2_pack_geom *g, const double *u, const int32_t *block_mask,
+                     double *minmax, pb2_stream_t stream);
+
 /* z = w1*x + w2*y over the GHOST cells of every block only: what the reference's full-extent
  * WeightedSumData passes (AverageIndependentData / UpdateIndependentData, update.hpp:122-137)
  * do outside the interior.  A fused interior update plus this call equals the reference on

@@ -40,6 +40,10 @@ int pb2h_sim_destroy(pb2h_sim *sim);
  * of the loop body, or the whole thing */
 int pb2h_sim_pre_execute(pb2h_sim *sim);
 int pb2h_sim_cycle(pb2h_sim *sim, int ncycles);
+/* one cycle in the two halves either side of the reference's PostStepUserWorkInLoop hook
+ * (driver.cpp:112-129): phase 0 = Step + time advance, phase 1 =
+ * LoadBalancingAndAdaptiveMeshRefinement + SetGlobalTimeStep.  pb2h_sim_cycle does both. */
+int pb2h_sim_cycle_phase(pb2h_sim *sim, int phase);
 int pb2h_sim_execute(pb2h_sim *sim);
 int pb2h_sim_sync(pb2h_sim *sim);
 void *pb2h_sim_stream(pb2h_sim *sim); /* cudaStream_t the application enqueues on */

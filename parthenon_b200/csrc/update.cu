@@ -2,6 +2,7 @@
 // update.cpp:63-86).  Compiled with -fmad=false: these are memory-bound, so keeping the
 // reference's rounding costs nothing.
 #include <algorithm>
+#include <cfloat>
 
 #include "common.cuh"
 
@@ -117,6 +118,37 @@ __global__ void __launch_bounds__(256)
   for (int64_t i = threadIdx.x; i < per_block; i += 256) loud = loud || (fabs(p[i]) > threshold);
   const int any = __syncthreads_or(loud);
   if (threadIdx.x == 0) quiet[b] = any ? 0 : 1;
+}
+
+// per-block minimum / maximum over all components and the ENTIRE extents: the reduction of
+// example/advection's CheckRefinement (advection_package.cpp:252-263, Kokkos::MinMax)
+__global__ void __launch_bounds__(256)
+    block_minmax_kernel(const double *__restrict__ u, int64_t block_stride, int64_t per_block,
+                        const int32_t *__restrict__ mask, double *__restrict__ out) {
+  const int b = blockIdx.x;
+  if (mask != nullptr && mask[b] == 0) return;
+  const double *p = u + (int64_t)b * block_stride;
+  double mn = DBL_MAX, mx = -DBL_MAX;
+  for (int64_t i = threadIdx.x; i < per_block; i += 256) {
+    const double v = p[i];
+    mn = v < mn ? v : mn;
+    mx = v > mx ? v : mx;
+  }
+  __shared__ double smn[256], smx[256];
+  smn[threadIdx.x] = mn;
+  smx[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      smn[threadIdx.x] = smn[threadIdx.x + s] < smn[threadIdx.x] ? smn[threadIdx.x + s] : smn[threadIdx.x];
+      smx[threadIdx.x] = smx[threadIdx.x + s] > smx[threadIdx.x] ? smx[threadIdx.x + s] : smx[threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[2 * b] = smn[0];
+    out[2 * b + 1] = smx[0];
+  }
 }
 
 // example/advection CalculateFluxes with a constant velocity (advection_package.cpp:540-646;
@@ -320,6 +352,20 @@ int pb2_weighted_sum_blocks(const pb2_pack_geom *pg, const double *x, const doub
   ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
   weighted_sum_blocks_kernel<<<pg->nblocks * cpb, 256, 0, as_stream(stream)>>>(
       x, y, w1, w2, z, pg->block_stride, per_block, block_mask, cpb);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_block_minmax(const pb2_pack_geom *pg, const double *u, const int32_t *block_mask,
+                     double *minmax, pb2_stream_t stream) {
+  PB2_REQUIRE(pg && u && minmax, "bad arguments");
+  if (int rc = require_device()) return rc;
+  if (pg->nblocks == 0) return PB2_OK;
+  int64_t per_block = pg->ncomp;
+  for (int d = 0; d < 3; ++d) per_block *= d >= pg->ndim ? 1 : pg->nx[d] + 2 * pg->ng;
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  block_minmax_kernel<<<pg->nblocks, 256, 0, as_stream(stream)>>>(u, pg->block_stride, per_block,
+                                                                  block_mask, minmax);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpb200_host.so")
 
 SYMBOLS = [
     "pb2h_last_error", "pb2h_sim_create", "pb2h_topology_create", "pb2h_sim_destroy",
-    "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_execute", "pb2h_sim_sync",
+    "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_field_ptr",
@@ -177,6 +177,7 @@ def lib():
     for f in ("pb2h_sim_destroy", "pb2h_sim_pre_execute", "pb2h_sim_execute", "pb2h_sim_sync"):
         getattr(L, f).argtypes = [vp]
     L.pb2h_sim_cycle.argtypes = [vp, C.c_int]
+    L.pb2h_sim_cycle_phase.argtypes = [vp, C.c_int]
     L.pb2h_sim_stream.restype = vp
     L.pb2h_sim_stream.argtypes = [vp]
     for f in ("pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_zone_cycles_per_second"):
@@ -325,6 +326,14 @@ class Simulation(_Base):
 
     def cycle(self, n=1):
         check(lib().pb2h_sim_cycle(self.h, n))
+
+    def step(self):
+        """first half of a cycle: Step + time advance (adaptive meshes: before the remesh)"""
+        check(lib().pb2h_sim_cycle_phase(self.h, 0))
+
+    def regrid(self):
+        """second half: LoadBalancingAndAdaptiveMeshRefinement + SetGlobalTimeStep"""
+        check(lib().pb2h_sim_cycle_phase(self.h, 1))
 
     def execute(self):
         check(lib().pb2h_sim_execute(self.h))

@@ -68,8 +68,11 @@ TaskCollection AdvectionDriver::MakeTaskCollection(BlockList_t &blocks, const in
     auto bnd = AddBoundaryExchangeTasks(update | start_bnd, tl, mc1, pmesh->multilevel);
 
     auto fill_derived = tl.AddTask(bnd, FillDerived<MeshData<Real>>, mc1.get());
-    if (stage == integrator->nstages)
+    if (stage == integrator->nstages) {
       tl.AddTask(fill_derived, EstimateTimestep<MeshData<Real>>, mc1.get());
+      // Update refinement (advection_driver.cpp:156-159)
+      if (pmesh->adaptive) tl.AddTask(fill_derived, Refinement::Tag, mc1.get());
+    }
   }
   (void)blocks; // per-block region of the reference: periodic static meshes have no work there
   return tc;

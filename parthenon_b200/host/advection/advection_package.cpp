@@ -51,7 +51,43 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
     pkg->AddField(name, m);
   }
   pkg->EstimateTimestepMesh = EstimateTimestepMesh;
+  pkg->CheckRefinementMesh = CheckRefinement;
   return pkg;
+}
+
+// CheckRefinement advection_package.cpp:239-273: refine where the field spans the tolerances
+// inside a block (entire extents), derefine where it is small everywhere — one device
+// reduction for the whole batch instead of one par_reduce per block
+void CheckRefinement(MeshData<Real> *md, std::vector<AmrTag> &tags) {
+  auto pkg = md->GetMeshPointer()->packages.Get("advection_package");
+  const Real refine_tol = pkg->Param<Real>("refine_tol");
+  const Real derefine_tol = pkg->Param<Real>("derefine_tol");
+  const int nb = md->NumBlocks();
+  std::vector<Real> mn(nb, std::numeric_limits<Real>::max()),
+      mx(nb, -std::numeric_limits<Real>::max());
+  DeviceBuffer dev;
+  dev.Allocate(sizeof(Real) * 2 * nb, md->stream());
+  std::vector<Real> h(2 * nb);
+  const int num_vars = pkg->Param<int>("num_vars");
+  for (int var = 0; var < num_vars; ++var) {
+    Variable &u = md->Get(var == 0 ? "advected" : "advected_" + std::to_string(var));
+    const pb2_pack_geom g = md->Geometry(u);
+    PB2_CHECK(pb2_block_minmax(&g, u.data(), nullptr, dev.get<Real>(), md->stream()));
+    PB2_CHECK(pb2_memcpy_d2h(h.data(), dev.get(), sizeof(Real) * h.size(), md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+    for (int b = 0; b < nb; ++b) {
+      mn[b] = std::min(mn[b], h[2 * b]);
+      mx[b] = std::max(mx[b], h[2 * b + 1]);
+    }
+  }
+  for (int b = 0; b < nb; ++b) {
+    if (mx[b] > refine_tol && mn[b] < derefine_tol)
+      tags[b] = AmrTag::refine;
+    else if (mx[b] < derefine_tol)
+      tags[b] = AmrTag::derefine;
+    else
+      tags[b] = AmrTag::same;
+  }
 }
 
 TaskStatus CalculateFluxes(MeshData<Real> *md) {

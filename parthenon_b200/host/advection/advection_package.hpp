@@ -3,6 +3,7 @@
 // Initialize, CalculateFluxes, EstimateTimestep — batched over a whole MeshData.
 #pragma once
 #include <memory>
+#include <vector>
 
 #include "pb2/parthenon.hpp"
 
@@ -14,5 +15,7 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin);
 TaskStatus CalculateFluxes(MeshData<Real> *md);
 // cfl * min over blocks and directions of dx_d / |v_d| (advection_package.cpp:505-536)
 Real EstimateTimestepMesh(MeshData<Real> *md);
+// refinement tags of every block of the batch (advection_package.cpp:239-273)
+void CheckRefinement(MeshData<Real> *md, std::vector<AmrTag> &tags);
 
 } // namespace advection_package

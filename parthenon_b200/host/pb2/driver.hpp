@@ -55,6 +55,10 @@ class EvolutionDriver : public Driver {
   // one cycle of the main loop of Execute (Step + bookkeeping + dt), for callers that
   // drive the loop themselves (bench.py, tests)
   TaskListStatus DoCycle();
+  // the two halves of a cycle (driver.cpp:112-123 and :125-129): Step + time advance, then
+  // LoadBalancingAndAdaptiveMeshRefinement + SetGlobalTimeStep
+  TaskListStatus StepAndAdvanceTime();
+  void AdaptMeshAndSetTimeStep();
   // call once before the first DoCycle (what Execute does before its loop)
   void PreExecute();
   void OutputCycleDiagnostics();

@@ -130,6 +130,9 @@ class MeshBlock {
   Mesh *pmy_mesh = nullptr;
   int partition = 0; // MeshData batch holding this block
   int pack_index = 0; // position inside that batch
+  // MeshRefinement::refine_flag_ / deref_count_ (mesh/mesh_refinement.hpp): the tag of the last
+  // Refinement::Tag and the number of consecutive "derefine" tags
+  int refine_flag = 0, deref_count = 0;
 
   Real NewDt() const { return new_block_dt_; }
   void SetAllowedDt(Real dt) { new_block_dt_ = dt; }
@@ -159,6 +162,7 @@ class MeshDataCollection {
     return map_.count(label + "_part-" + std::to_string(partition_id)) > 0;
   }
   void PurgeNonBase();
+  void Clear() { map_.clear(); }
   std::map<std::string, std::shared_ptr<MeshData<Real>>> &All() { return map_; }
 
  private:
@@ -205,6 +209,18 @@ class Mesh {
   // in-place sum over ranks of a host vector (MPI_Reduce of outputs/history.cpp)
   void ReduceHistory(std::vector<Real> &vals);
   // true if some block of this rank has a neighbour on another level
+  // adaptive mesh refinement (refinement = adaptive; single device in this build)
+  int max_level = 63;          // numlevel + root_level - 1 (mesh.cpp:125)
+  int derefine_count = 10;     // <parthenon/mesh>/derefine_count (mesh_refinement.cpp:56)
+  bool modified = false;
+  int nbnew = 0, nbdel = 0;
+  // MeshRefinement::SetRefinement (mesh_refinement.cpp:81-118) for block `lid`
+  void SetRefinement(int lid, AmrTag flag);
+  // Mesh::LoadBalancingAndAdaptiveMeshRefinement (mesh-amr_loadbalance.cpp:324-351): update
+  // the tree from the blocks' refine flags and, if it changed, move the data onto the new
+  // block list (RedistributeAndRefineMeshBlocks :663-1010).  Sets `modified`.
+  void LoadBalancingAndAdaptiveMeshRefinement(ParameterInput *pin, ApplicationInput *app_in);
+
   // <parthenon/sparse> (globals.hpp:27-36, parthenon_manager.cpp:122-138)
   struct SparseConfig {
     bool enabled = true;
@@ -254,6 +270,11 @@ class Mesh {
   std::unordered_map<LogicalLocation, int, LogicalLocationHash> leaf_gid_;
   std::unordered_map<LogicalLocation, int, LogicalLocationHash> internal_;
   void BuildTree(ParameterInput *pin, const std::vector<LogicalLocation> &leaves);
+  // (re)create this rank's MeshBlocks from loclist / ranklist; blocks of `keep` that sit at an
+  // unchanged location are reused (they carry their refinement counters and time step)
+  void BuildBlockList(const BlockList_t *keep);
+  bool UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nnew, int &ndel);
+  void RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &new_leaves);
   void FindNeighbors(MeshBlock &mb) const;
   bool WrapLocation(const LogicalLocation &in, LogicalLocation &out) const;
   int64_t BlocksAtLevel(int level, int d) const;

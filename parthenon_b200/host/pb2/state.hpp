@@ -237,6 +237,8 @@ class StateDescriptor {
   std::function<Real(MeshData<Real> *)> EstimateTimestepMesh = nullptr;
   std::function<Real(MeshBlockData<Real> *)> EstimateTimestepBlock = nullptr;
   std::function<AmrTag(MeshBlockData<Real> *)> CheckRefinementBlock = nullptr;
+  // batch form: one tag per block of the MeshData (one device reduction for all blocks)
+  std::function<void(MeshData<Real> *, std::vector<AmrTag> &)> CheckRefinementMesh = nullptr;
   std::function<void(MeshData<Real> *)> InitNewlyAllocatedVarsMesh = nullptr;
   std::function<void(Mesh *, ParameterInput *, SimTime &)> UserWorkBeforeLoopMesh = nullptr;
   std::function<void(SimTime const &, MeshData<Real> *)> PreStepDiagnosticsMesh = nullptr;

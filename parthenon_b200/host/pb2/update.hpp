@@ -70,4 +70,9 @@ TaskStatus FillDerived(MeshData<Real> *rc);
 TaskStatus SparseDealloc(MeshData<Real> *md);
 
 } // namespace Update
+
+namespace Refinement {
+// amr_criteria/refinement_package.cpp:150-172 for a whole MeshData batch
+TaskStatus Tag(MeshData<Real> *rc);
+} // namespace Refinement
 } // namespace parthenon

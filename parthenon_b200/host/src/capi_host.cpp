@@ -161,6 +161,17 @@ int pb2h_sim_cycle(pb2h_sim *sim, int ncycles) {
   });
 }
 
+int pb2h_sim_cycle_phase(pb2h_sim *sim, int phase) {
+  return Guard([&] {
+    if (phase == 0) {
+      PARTHENON_REQUIRE(sim->driver->StepAndAdvanceTime() == TaskListStatus::complete,
+                        "Step failed to complete all tasks.");
+    } else {
+      sim->driver->AdaptMeshAndSetTimeStep();
+    }
+  });
+}
+
 int pb2h_sim_sync(pb2h_sim *sim) {
   return Guard([&] { PB2_CHECK(pb2_stream_sync(sim->pm()->stream)); });
 }

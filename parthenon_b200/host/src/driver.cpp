@@ -197,15 +197,27 @@ void EvolutionDriver::PreExecute() {
   timer_main_ = std::chrono::steady_clock::now();
 }
 
-TaskListStatus EvolutionDriver::DoCycle() {
+// driver.cpp:99-150 in the two halves either side of the PostStepUserWorkInLoop hook
+TaskListStatus EvolutionDriver::StepAndAdvanceTime() {
   OutputCycleDiagnostics();
   const TaskListStatus status = Step();
   if (status != TaskListStatus::complete) return status;
   tm.ncycle++;
   tm.time += tm.dt;
   pmesh->mbcnt += pmesh->nbtotal;
-  // LoadBalancingAndAdaptiveMeshRefinement: static meshes only in this build
+  return status;
+}
+
+void EvolutionDriver::AdaptMeshAndSetTimeStep() {
+  pmesh->LoadBalancingAndAdaptiveMeshRefinement(pinput, app_input);
+  if (pmesh->modified) InitializeBlockTimeSteps();
   SetGlobalTimeStep();
+}
+
+TaskListStatus EvolutionDriver::DoCycle() {
+  const TaskListStatus status = StepAndAdvanceTime();
+  if (status != TaskListStatus::complete) return status;
+  AdaptMeshAndSetTimeStep();
   if (tm.KeepGoing()) MakeHistoryOutput(false);
   if (tm.ncycle == perf_cycle_offset) {
     PB2_CHECK(pb2_stream_sync(pmesh->stream));

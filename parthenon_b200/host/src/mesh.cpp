@@ -312,7 +312,6 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
   Globals::my_rank = rank;
   Globals::nranks = nranks_in;
   Globals::nghost = pin->GetOrAddInteger("parthenon/mesh", "nghost", 2);
-  const int ng = Globals::nghost;
   const char *bc_names[6] = {"ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc"};
   for (int d = 0; d < 3; ++d) {
     const std::string n = std::to_string(d + 1);
@@ -372,31 +371,11 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
   nslist.assign(nranks, 0);
   for (int r = 1; r < nranks; ++r) nslist[r] = nslist[r - 1] + nblist[r - 1];
 
-  for (int gid = nslist[rank]; gid < nslist[rank] + nblist[rank]; ++gid) {
-    auto mb = std::make_shared<MeshBlock>();
-    mb->gid = gid;
-    mb->lid = gid - nslist[rank];
-    mb->loc = loclist[gid];
-    mb->block_size = GetBlockSize(mb->loc);
-    const int nx1 = base_block_size.nx_[0], nx2 = ndim > 1 ? base_block_size.nx_[1] : 0,
-              nx3 = ndim > 2 ? base_block_size.nx_[2] : 0;
-    mb->cellbounds = IndexShape(nx3, nx2, nx1, ng);
-    // meshblock.cpp:204-216
-    mb->c_cellbounds = IndexShape(ndim > 2 ? std::max(1, nx3 / 2) : 0,
-                                  ndim > 1 ? std::max(1, nx2 / 2) : 0, std::max(1, nx1 / 2), ng);
-    mb->coords = UniformCartesian(mb->block_size, ng);
-    for (int d = 0; d < ndim; ++d) {
-      if (mb->loc.lx[d] == 0) mb->boundary_flag[2 * d] = mesh_bcs[2 * d];
-      if (mb->loc.lx[d] == BlocksAtLevel(mb->loc.level, d) - 1)
-        mb->boundary_flag[2 * d + 1] = mesh_bcs[2 * d + 1];
-    }
-    mb->pmy_mesh = this;
-    const int ps = DefaultPackSizeFor(static_cast<int>(nblist[rank]));
-    mb->partition = mb->lid / ps;
-    mb->pack_index = mb->lid % ps;
-    FindNeighbors(*mb);
-    block_list.push_back(mb);
-  }
+  max_level = pin->GetOrAddInteger("parthenon/mesh", "numlevel", 1) + root_level - 1;
+  derefine_count = pin->GetOrAddInteger("parthenon/mesh", "derefine_count", 10);
+  PARTHENON_REQUIRE(!adaptive || nranks == 1,
+                    "refinement = adaptive runs on one device in this build");
+  BuildBlockList(nullptr);
   for (auto &name : packages.Order())
     for (auto &f : packages.Get(name)->AllFields()) {
       resolved_fields.push_back(f);
@@ -430,6 +409,44 @@ void Mesh::DeallocateSparse(const std::string &label, int lid) {
     v.SetAllocated(pmb->pack_index, false);
     md->alloc_generation++;
   }
+}
+
+void Mesh::BuildBlockList(const BlockList_t *keep) {
+  const int ng = Globals::nghost;
+  const int rank = my_rank;
+  std::unordered_map<LogicalLocation, std::shared_ptr<MeshBlock>, LogicalLocationHash> old;
+  if (keep)
+    for (auto &pmb : *keep) old[pmb->loc] = pmb;
+  BlockList_t blocks;
+  for (int gid = nslist[rank]; gid < nslist[rank] + nblist[rank]; ++gid) {
+    auto it = old.find(loclist[gid]);
+    auto mb = it != old.end() ? it->second : std::make_shared<MeshBlock>();
+    mb->gid = gid;
+    mb->lid = gid - nslist[rank];
+    mb->loc = loclist[gid];
+    mb->block_size = GetBlockSize(mb->loc);
+    const int nx1 = base_block_size.nx_[0], nx2 = ndim > 1 ? base_block_size.nx_[1] : 0,
+              nx3 = ndim > 2 ? base_block_size.nx_[2] : 0;
+    mb->cellbounds = IndexShape(nx3, nx2, nx1, ng);
+    // meshblock.cpp:204-216
+    mb->c_cellbounds = IndexShape(ndim > 2 ? std::max(1, nx3 / 2) : 0,
+                                  ndim > 1 ? std::max(1, nx2 / 2) : 0, std::max(1, nx1 / 2), ng);
+    mb->coords = UniformCartesian(mb->block_size, ng);
+    for (int f = 0; f < 6; ++f) mb->boundary_flag[f] = BoundaryFlag::block;
+    for (int d = 0; d < ndim; ++d) {
+      if (mb->loc.lx[d] == 0) mb->boundary_flag[2 * d] = mesh_bcs[2 * d];
+      if (mb->loc.lx[d] == BlocksAtLevel(mb->loc.level, d) - 1)
+        mb->boundary_flag[2 * d + 1] = mesh_bcs[2 * d + 1];
+    }
+    mb->pmy_mesh = this;
+    const int ps = DefaultPackSizeFor(static_cast<int>(nblist[rank]));
+    mb->partition = mb->lid / ps;
+    mb->pack_index = mb->lid % ps;
+    FindNeighbors(*mb);
+    blocks.push_back(mb);
+  }
+  block_list = std::move(blocks);
+  fine_coarse_faces_ = -1;
 }
 
 Mesh::~Mesh() = default;

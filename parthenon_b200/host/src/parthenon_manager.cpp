@@ -72,16 +72,26 @@ ParthenonManager::ParthenonStatus ParthenonManager::ParthenonFinalize() {
 }
 
 void Mesh::Initialize(bool init_problem, ParameterInput *pin, ApplicationInput *app_in) {
-  const int np = DefaultNumPartitions();
-  if (init_problem && app_in && app_in->MeshProblemGenerator)
-    for (int p = 0; p < np; ++p)
-      app_in->MeshProblemGenerator(mesh_data.GetOrAdd("base", p).get(), pin);
-  // mesh.cpp:640-706 CommunicateBoundaries (+ prolongation on multilevel meshes), then
-  // FillDerived on every batch
-  auto &base0 = mesh_data.GetOrAdd("base", 0);
-  CommunicateBoundaries(base0, true);
-  for (int p = 0; p < np; ++p) Update::FillDerived(mesh_data.GetOrAdd("base", p).get());
-  PB2_CHECK(pb2_stream_sync(stream));
+  bool init_done = true;
+  do { // mesh.cpp:745-860: on adaptive meshes, regenerate the problem until the mesh settles
+    const int np = DefaultNumPartitions();
+    if (init_problem && app_in && app_in->MeshProblemGenerator)
+      for (int p = 0; p < np; ++p)
+        app_in->MeshProblemGenerator(mesh_data.GetOrAdd("base", p).get(), pin);
+    // mesh.cpp:640-706 CommunicateBoundaries (+ prolongation on multilevel meshes), then
+    // FillDerived on every batch
+    auto &base0 = mesh_data.GetOrAdd("base", 0);
+    CommunicateBoundaries(base0, true);
+    for (int p = 0; p < np; ++p) Update::FillDerived(mesh_data.GetOrAdd("base", p).get());
+    PB2_CHECK(pb2_stream_sync(stream));
+    init_done = true;
+    if (init_problem && adaptive) {
+      for (int p = 0; p < np; ++p) Refinement::Tag(mesh_data.GetOrAdd("base", p).get());
+      const int nb_before = nbtotal;
+      LoadBalancingAndAdaptiveMeshRefinement(pin, app_in);
+      init_done = nbtotal == nb_before;
+    }
+  } while (!init_done);
 }
 
 } // namespace parthenon

@@ -63,3 +63,38 @@ def test_advection_conserves_total_on_multilevel_mesh():
     t0 = total()
     sim.cycle(5)
     assert abs(total() - t0) <= 1e-13 * abs(t0)
+
+
+from tests.test_oracle_golden import ADAPTIVE  # noqa: E402
+
+
+@pytest.mark.parametrize("name,ndim,nx_mesh,nx_block,numlevel,derefine_count,ncyc", ADAPTIVE)
+def test_adaptive_advection_bit_exact_vs_reference_dumps(name, ndim, nx_mesh, nx_block, numlevel,
+                                                         derefine_count, ncyc):
+    """refinement = adaptive through the host framework: the initial refinement loop, tagging on
+    the device (pb2_block_minmax), tree update, and the remesh as restrict / copy / prolongate
+    launches into a new slab — block list and field bit-exact against the reference's dumps,
+    which are taken after Step and before that cycle's remesh (sim.step() / sim.regrid())."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    nrb = [nx_mesh[d] // nx_block[d] if d < ndim else 1 for d in range(3)]
+    ov = deck_overrides(ndim, nx_block, 2, nrb, refinement="adaptive")
+    ov.update({"parthenon/mesh/numlevel": numlevel, "parthenon/mesh/derefine_count": derefine_count,
+               "Advection/profile": "hard_sphere"})
+    sim = host.Simulation(app="advection", overrides=ov)
+    sim.pre_execute()
+    counts = set()
+    for c in range(ncyc + 1):
+        if c:
+            sim.step()
+        ref = g[f"U_{c}"]
+        leaves, _ = H.leaves_from_bounds(g[f"bounds_{c}"], nx_mesh, nx_block)
+        info = sim.info()
+        assert info["nbtotal"] == ref.shape[0], f"cycle {c}"
+        locs = np.array([sim.block(b)["loc"] for b in range(info["nblocks"])])
+        assert np.array_equal(locs, leaves), f"cycle {c}"
+        assert np.array_equal(sim.get_field("base", "advected"), ref), f"cycle {c}"
+        assert sim.time == g["times"][c]
+        counts.add(info["nbtotal"])
+        if c:
+            sim.regrid()
+    assert len(counts) > 1
