@@ -371,6 +371,17 @@ def main():
     cycle_roof = {"algorithmic_bytes_per_zone_cycle": a_zc, "achieved_gbs": value / world * a_zc / 1e9,
                   "frac_of_hbm_peak": value / world * a_zc / 1e9 / peak}
 
+    # BASELINE.json's second metric: ghost-exchange GB/s vs the HBM peak.  A_exch = 2 G C 8 B per
+    # block: every ghost value read once from its owner and written once.
+    ghost = None
+    hk = [k for k in ("halo_uniform_kernel", "copy_kernel") if k in kernels and "gbs" in kernels[k]]
+    if hk:
+        k = hk[0]
+        ghost = {"kernel": k, "gbs": kernels[k]["gbs"], "frac_of_hbm_peak": kernels[k]["gbs"] / peak,
+                 "bytes_per_exchange_per_gpu": 8 * 2 * NCOMP * ghost_per_zone * zones_rank,
+                 "ms_per_exchange": prof[k][0] / prof[k][1],
+                 "note": "same-device channels, sender interior -> receiver ghosts in one launch; "
+                         "inter-GPU channels are pack_kernel / NCCL / unpack_kernel (see kernels)"}
     fp64_peak = capi.fp64_peak_tflops()
     cycle_roof["fp64_peak_tflops_measured"] = fp64_peak
     cpu = None
@@ -394,7 +405,8 @@ def main():
             "l2": "working set (>= 5.8 GB per GPU) exceeds the 126 MB L2; no flush needed",
             "partition": f"Morton-contiguous gid ranges, {world} rank(s)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cycle_roofline": cycle_roof, "kernels": kernels,
+        "roofline": roofline, "ghost_exchange": ghost, "cycle_roofline": cycle_roof,
+        "kernels": kernels,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
