@@ -49,18 +49,6 @@ void Mesh::SetRefinement(int lid, AmrTag flag) {
 namespace {
 using LeafSet = std::unordered_set<LogicalLocation, LogicalLocationHash>;
 
-bool IsInternal(const LeafSet &leaves, const LogicalLocation &l, int max_level) {
-  // some leaf lies strictly below l: walk down is expensive, so test the leaves' ancestors
-  for (const auto &q : leaves) {
-    if (q.level <= l.level) continue;
-    const int sh = q.level - l.level;
-    if ((q.lx[0] >> sh) == l.lx[0] && (q.lx[1] >> sh) == l.lx[1] && (q.lx[2] >> sh) == l.lx[2])
-      return true;
-  }
-  (void)max_level;
-  return false;
-}
-
 LogicalLocation Daughter(const LogicalLocation &p, int q, int ndim) {
   LogicalLocation d;
   d.level = p.level + 1;
@@ -109,10 +97,14 @@ bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nn
                      [](const LogicalLocation &a, const LogicalLocation &b) { return a.level > b.level; });
 
   LeafSet leaves(loclist.begin(), loclist.end());
+  // internal nodes of the tree (Tree::internal_nodes): kept in step with the leaf set
+  LeafSet internal;
+  for (const auto &kv : internal_) internal.insert(kv.first);
   // Tree::Refine with proper nesting (tree.cpp:93-143)
   std::function<int(const LogicalLocation &)> refine = [&](const LogicalLocation &ref) -> int {
     if (!leaves.count(ref)) return 0;
     leaves.erase(ref);
+    internal.insert(ref);
     for (int q = 0; q < nleaf; ++q) leaves.insert(Daughter(ref, q, ndim));
     int nadded = nleaf - 1;
     if (ref.level <= root_level) return nadded; // no leaves above the root grid
@@ -146,10 +138,11 @@ bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nn
             neigh.lx[1] += j;
             neigh.lx[2] += k;
             if (!WrapLocation(neigh, w)) continue;
-            if (IsInternal(leaves, w, max_level)) return 0; // would abut a block two levels finer
+            if (internal.count(w)) return 0; // would abut a block two levels finer
           }
     }
     for (int q = 0; q < nleaf; ++q) leaves.erase(Daughter(ref, q, ndim));
+    internal.erase(ref);
     leaves.insert(ref);
     return nleaf - 1;
   };

@@ -138,6 +138,17 @@ export PB2_PER_CYCLE_META=1
 run_advection advection_a32_b8_l3_2d 2 32 8 40 adaptive 3 "" parthenon/mesh/derefine_count=3
 run_advection advection_a32_b8_l2_3d 3 32 8 8 adaptive 2 "" parthenon/mesh/derefine_count=2
 unset PB2_PER_CYCLE_META
+# 3-D, three levels, 30 cycles (848 -> 764 -> 1198 blocks): too large to commit as raw fields
+# (380 MB), so the fixture holds the block list and per-block CRC-32 / interior sum of every cycle
+d="$WORK/advection_a32_b8_l3_3d"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+cp "$REF/example/advection/parthinput.advection" deck.pin
+PB2_DUMP_PREFIX="$d/U" PB2_DUMP_FIELD=advected "$WORK/advection_dump" -i deck.pin \
+  parthenon/mesh/nx1=32 parthenon/mesh/nx2=32 parthenon/mesh/nx3=32 \
+  parthenon/meshblock/nx1=8 parthenon/meshblock/nx2=8 parthenon/meshblock/nx3=8 \
+  parthenon/mesh/refinement=adaptive parthenon/mesh/numlevel=3 parthenon/mesh/derefine_count=3 \
+  parthenon/time/nlim=30 parthenon/time/tlim=1e9 parthenon/output0/dt=-1 parthenon/output1/dt=-1 \
+  parthenon/output3/dt=-1 parthenon/output4/dt=-1 Advection/fill_derived=false > run.log 2>&1
+python3 "$HERE/pack_checksums.py" "$d" "$OUT/advection_a32_b8_l3_3d_crc.npz" 2
 fi
 # example/sparse_advection (2-D only in the reference): four sparse fields allocated where
 # their data is, allocated on a neighbour when a non-null boundary buffer arrives, deallocated

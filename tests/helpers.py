@@ -167,3 +167,10 @@ def neighbor_table(mesh):
         for (gid, _lvl, o1, o2, o3) in mesh.neighbors(b):
             tab[b, (o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)] = gid
     return tab
+
+
+def block_crcs(data):
+    """CRC-32 of every block's bytes (the convention of tests/golden/refgen/pack_checksums.py)"""
+    import zlib
+    return np.array([zlib.crc32(np.ascontiguousarray(data[b]).tobytes())
+                     for b in range(data.shape[0])], dtype=np.uint32)

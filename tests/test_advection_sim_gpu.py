@@ -98,3 +98,23 @@ def test_adaptive_advection_bit_exact_vs_reference_dumps(name, ndim, nx_mesh, nx
         if c:
             sim.regrid()
     assert len(counts) > 1
+
+
+def test_adaptive_advection_3d_three_levels_crc():
+    """the same run 30 cycles long (848 -> 764 -> 1198 blocks) against the compact fixture of
+    the reference: block list and the CRC-32 of every block's bytes, every cycle"""
+    from tests.test_oracle_golden import check_against_crc_fixture
+    ov = deck_overrides(3, (8, 8, 8), 2, (4, 4, 4), refinement="adaptive")
+    ov.update({"parthenon/mesh/numlevel": 3, "parthenon/mesh/derefine_count": 3,
+               "Advection/profile": "hard_sphere"})
+    sim = host.Simulation(app="advection", overrides=ov)
+    sim.pre_execute()
+
+    def state():
+        n = sim.info()["nblocks"]
+        return (np.array([sim.block(b)["loc"] for b in range(n)]),
+                sim.get_field("base", "advected"), sim.time)
+
+    counts = check_against_crc_fixture("advection_a32_b8_l3_3d_crc", (32, 32, 32), (8, 8, 8), 30,
+                                       state, sim.step, sim.regrid)
+    assert len(counts) > 4
