@@ -208,8 +208,11 @@ class Mesh {
   Real *ScratchReal(); // 64 device doubles for tiny reductions
   // in-place sum over ranks of a host vector (MPI_Reduce of outputs/history.cpp)
   void ReduceHistory(std::vector<Real> &vals);
+  // in-place sum over ranks of a host vector of any length (AMR: the MPI_Allgatherv of
+  // refinement flags and counters, with every rank contributing its own gid range)
+  void AllReduceSum(std::vector<Real> &vals);
   // true if some block of this rank has a neighbour on another level
-  // adaptive mesh refinement (refinement = adaptive; single device in this build)
+  // adaptive mesh refinement (refinement = adaptive)
   int max_level = 63;          // numlevel + root_level - 1 (mesh.cpp:125)
   int derefine_count = 10;     // <parthenon/mesh>/derefine_count (mesh_refinement.cpp:56)
   bool modified = false;

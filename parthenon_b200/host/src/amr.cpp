@@ -60,11 +60,16 @@ LogicalLocation Daughter(const LogicalLocation &p, int q, int ndim) {
 bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nnew, int &ndel) {
   const int nleaf = 1 << ndim;
   std::vector<LogicalLocation> lref, lderef, clderef;
+  // the refinement flags of every block of the mesh, in gid order (MPI_Allgatherv of the
+  // flagged locations in the reference, :508-565)
+  std::vector<Real> flags(nbtotal, 0.0);
+  for (auto &pmb : block_list) flags[pmb->gid] = pmb->refine_flag;
+  AllReduceSum(flags);
   int tnderef = 0;
-  for (auto &pmb : block_list) tnderef += pmb->refine_flag == -1;
-  for (auto &pmb : block_list) {
-    if (pmb->refine_flag == 1) lref.push_back(pmb->loc);
-    if (pmb->refine_flag == -1 && tnderef >= nleaf) lderef.push_back(pmb->loc);
+  for (int g = 0; g < nbtotal; ++g) tnderef += flags[g] == -1.0;
+  for (int g = 0; g < nbtotal; ++g) {
+    if (flags[g] == 1.0) lref.push_back(loclist[g]);
+    if (flags[g] == -1.0 && tnderef >= nleaf) lderef.push_back(loclist[g]);
   }
   if (lref.empty() && tnderef < nleaf) return false; // nothing to do (:525-527)
 
@@ -154,16 +159,24 @@ bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nn
 }
 
 void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &new_leaves) {
-  PARTHENON_REQUIRE(nranks == 1 && DefaultNumPartitions() == 1,
-                    "remeshing needs one device and one MeshData per rank (pack_size = -1)");
+  PARTHENON_REQUIRE(DefaultNumPartitions() == 1,
+                    "remeshing needs one MeshData per rank (parthenon/mesh/pack_size = -1)");
   // only the base container survives a remesh (:667)
   mesh_data.PurgeNonBase();
   std::shared_ptr<MeshData<Real>> old_md = mesh_data.GetOrAdd("base", 0);
   const BlockList_t old_blocks = block_list;
-  std::unordered_map<LogicalLocation, int, LogicalLocationHash> old_index;
-  for (auto &pmb : old_blocks) old_index[pmb->loc] = pmb->pack_index;
+  const std::vector<LogicalLocation> old_loclist = loclist;
+  const std::vector<int> old_ranklist = ranklist, old_nslist = nslist;
+  std::unordered_map<LogicalLocation, int, LogicalLocationHash> old_gid;
+  for (int g = 0; g < static_cast<int>(old_loclist.size()); ++g) old_gid[old_loclist[g]] = g;
+  auto old_local = [&](int g) { return g - old_nslist[my_rank]; }; // index into the old slab
+  // derefinement counters travel with kept blocks (SendSameToSame packs them into the message,
+  // :253-283): every rank learns every old counter
+  std::vector<Real> old_count(old_loclist.size(), 0.0);
+  for (auto &pmb : old_blocks) old_count[pmb->gid] = pmb->deref_count;
+  AllReduceSum(old_count);
 
-  // new tree, block list and (empty) base container
+  // new tree, rank assignment (AssignBlocks with unit costs), block list, empty base container
   BuildTree(nullptr, new_leaves);
   multilevel = true;
   std::vector<double> cost(nbtotal, 1.0);
@@ -173,131 +186,127 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
   nslist.assign(nranks, 0);
   for (int r = 1; r < nranks; ++r) nslist[r] = nslist[r - 1] + nblist[r - 1];
   BuildBlockList(&old_blocks);
-  for (auto &pmb : block_list)
-    if (!old_index.count(pmb->loc)) { // MeshBlock::Make: fresh counters, no time step yet
-      pmb->refine_flag = 0;
-      pmb->deref_count = 0;
-      pmb->SetAllowedDt(std::numeric_limits<Real>::max());
-    }
+  for (auto &pmb : block_list) {
+    auto it = old_gid.find(pmb->loc);
+    pmb->refine_flag = 0;
+    pmb->deref_count = it != old_gid.end() ? static_cast<int>(old_count[it->second]) : 0;
+    if (it == old_gid.end() || old_ranklist[it->second] != my_rank)
+      pmb->SetAllowedDt(std::numeric_limits<Real>::max()); // MeshBlock::Make: no time step yet
+  }
   mesh_data.Clear();
   std::shared_ptr<MeshData<Real>> new_md = mesh_data.GetOrAdd("base", 0);
 
   const int nleaf = 1 << ndim;
   const int ng = Globals::nghost;
   pb2_stream_t st = stream;
+  auto daughter_of = [&](const LogicalLocation &p, int q) { return Daughter(p, q, ndim); };
+  auto parent_of = [&](const LogicalLocation &l) {
+    LogicalLocation par = l.GetParent();
+    for (int d = ndim; d < 3; ++d) par.lx[d] = 0;
+    return par;
+  };
+
   for (auto &nvp : new_md->GetVariableVector()) {
     Variable &nv = *nvp;
-    // the fields a remesh carries over: pmb->vars_cc_ (meshblock.cpp: Independent / FillGhost /
-    // ForceRemeshComm cell-centred variables)
+    // the fields a remesh carries over: pmb->vars_cc_ (Independent / FillGhost cell-centred)
     if (!(nv.IsSet(Metadata::Independent) || nv.IsSet(Metadata::FillGhost))) continue;
     PARTHENON_REQUIRE(!nv.metadata().IsSparse(), "sparse fields cannot be remeshed in this build");
     Variable &ov = old_md->Get(nv.label());
-    std::vector<pb2_copy_region> copies;
+    const int64_t fsz = nv.block_stride + (nv.block_stride & 1);   // slab entries, 16-B aligned
+    const int64_t csz = nv.cblock_stride + (nv.cblock_stride & 1);
+
+    // ---- what moves where.  Every rank walks the NEW block list of the whole mesh in gid order,
+    // so senders and receivers lay out the per-peer slabs identically without a handshake.
+    struct Piece { // one old block (or its coarse buffer) feeding one new block
+      int new_gid, old_gid, q; // q: daughter index for merged blocks, else -1
+      int kind;                // 0 kept, 1 split (parent -> child), 2 merged (child -> parent)
+    };
+    std::vector<Piece> pieces;
+    for (int n = 0; n < nbtotal; ++n) {
+      const LogicalLocation &nl = loclist[n];
+      auto same = old_gid.find(nl);
+      if (same != old_gid.end()) {
+        pieces.push_back({n, same->second, -1, 0});
+        continue;
+      }
+      auto up = nl.level > 0 ? old_gid.find(parent_of(nl)) : old_gid.end();
+      if (up != old_gid.end()) {
+        pieces.push_back({n, up->second, -1, 1});
+        continue;
+      }
+      for (int q = 0; q < nleaf; ++q) {
+        auto ch = old_gid.find(daughter_of(nl, q));
+        PARTHENON_REQUIRE(ch != old_gid.end(), "remesh cannot find the origin of a new block");
+        pieces.push_back({n, ch->second, q, 2});
+      }
+    }
+    std::vector<int64_t> send_off(nranks + 1, 0), recv_off(nranks + 1, 0);
+    std::vector<int64_t> piece_send(pieces.size(), -1), piece_recv(pieces.size(), -1);
+    {
+      std::vector<int64_t> ssz(nranks, 0), rsz(nranks, 0);
+      for (size_t i = 0; i < pieces.size(); ++i) {
+        const int src = old_ranklist[pieces[i].old_gid], dst = ranklist[pieces[i].new_gid];
+        if (src == dst) continue;
+        const int64_t sz = pieces[i].kind == 2 ? csz : fsz;
+        if (src == my_rank) {
+          piece_send[i] = ssz[dst];
+          ssz[dst] += sz;
+        }
+        if (dst == my_rank) {
+          piece_recv[i] = rsz[src];
+          rsz[src] += sz;
+        }
+      }
+      for (int r = 0; r < nranks; ++r) {
+        send_off[r + 1] = send_off[r] + ssz[r];
+        recv_off[r + 1] = recv_off[r] + rsz[r];
+      }
+      for (size_t i = 0; i < pieces.size(); ++i) {
+        if (piece_send[i] >= 0) piece_send[i] += send_off[ranklist[pieces[i].new_gid]];
+        if (piece_recv[i] >= 0) piece_recv[i] += recv_off[old_ranklist[pieces[i].old_gid]];
+      }
+    }
+    DeviceBuffer send_slab, recv_slab;
+    if (send_off[nranks] > 0) send_slab.Allocate(sizeof(Real) * send_off[nranks], st);
+    if (recv_off[nranks] > 0) recv_slab.Allocate(sizeof(Real) * recv_off[nranks], st);
+
+    std::vector<pb2_copy_region> copies, sends;
     std::vector<pb2_prores_region> restricts, prolongs;
-    auto whole = [&](pb2_copy_region &r) {
+    auto whole_block = [&](pb2_copy_region &r, const Real *src, Real *dst, bool coarse) {
+      r.src = src;
+      r.dst = dst;
       r.ncomp = nv.NumComponents();
       r.flag_slot = -1;
       r.status = PB2_REGION_ALLOCATED;
+      r.n[0] = coarse ? nv.cni : nv.ni;
+      r.n[1] = coarse ? nv.cnj : nv.nj;
+      r.n[2] = coarse ? nv.cnk : nv.nk;
+      r.src_stride_j = r.dst_stride_j = r.n[0];
+      r.src_stride_k = r.dst_stride_k = r.n[0] * r.n[1];
+      r.src_stride_c = r.dst_stride_c =
+          static_cast<int32_t>(coarse ? nv.ccomp_stride : nv.comp_stride);
     };
-    for (auto &pmb : block_list) {
-      const int nb = pmb->pack_index;
-      auto same = old_index.find(pmb->loc);
-      if (same != old_index.end()) {
-        // kept block: every cell, ghosts included
-        pb2_copy_region r{};
-        whole(r);
-        r.src = ov.data() + same->second * ov.block_stride;
-        r.dst = nv.data() + nb * nv.block_stride;
-        r.n[0] = nv.ni;
-        r.n[1] = nv.nj;
-        r.n[2] = nv.nk;
-        r.src_stride_j = r.dst_stride_j = nv.ni;
-        r.src_stride_k = r.dst_stride_k = nv.ni * nv.nj;
-        r.src_stride_c = r.dst_stride_c = static_cast<int32_t>(nv.comp_stride);
-        copies.push_back(r);
-        continue;
-      }
-      LogicalLocation par = pmb->loc.GetParent();
-      for (int d = ndim; d < 3; ++d) par.lx[d] = 0;
-      auto up = pmb->loc.level > 0 ? old_index.find(par) : old_index.end();
-      if (up != old_index.end()) {
-        // split: coarse buffer (entire extents) <- the parent's fine data, shifted into the
-        // quadrant / octant this child covers (TryRecvCoarseToFine :117-137)
-        pb2_copy_region r{};
-        whole(r);
-        r.src = ov.data() + up->second * ov.block_stride;
-        r.dst = nv.coarse() + nb * nv.cblock_stride;
-        for (int d = 0; d < 3; ++d) {
-          const bool upper = d < ndim && (pmb->loc.lx[d] & 1);
-          r.ss[d] = upper ? base_block_size.nx_[d] / 2 : 0;
-          r.ds[d] = 0;
-        }
-        r.n[0] = nv.cni;
-        r.n[1] = nv.cnj;
-        r.n[2] = nv.cnk;
-        r.src_stride_j = nv.ni;
-        r.src_stride_k = nv.ni * nv.nj;
-        r.src_stride_c = static_cast<int32_t>(nv.comp_stride);
-        r.dst_stride_j = nv.cni;
-        r.dst_stride_k = nv.cni * nv.cnj;
-        r.dst_stride_c = static_cast<int32_t>(nv.ccomp_stride);
-        copies.push_back(r);
-        // ProlongateShared over GetInteriorProlongate: coarse interior +- nghost / 2
-        // (bnd_info.cpp:199-203)
+    for (size_t i = 0; i < pieces.size(); ++i) {
+      const Piece &pc = pieces[i];
+      const int src_rank = old_ranklist[pc.old_gid], dst_rank = ranklist[pc.new_gid];
+      const bool mine_old = src_rank == my_rank, mine_new = dst_rank == my_rank;
+      if (!mine_old && !mine_new) continue;
+      // -- sender side: merged children are restricted first (GetInteriorRestrict), then the
+      //    data leaves in a slab if the new owner is another device
+      if (mine_old && pc.kind == 2) {
+        const int ol = old_local(pc.old_gid);
+        const MeshBlock *ob = old_blocks[ol].get();
         pb2_prores_region p{};
-        p.fine = nv.data() + nb * nv.block_stride;
-        p.coarse = nv.coarse() + nb * nv.cblock_stride;
-        for (int d = 0; d < 3; ++d) {
-          const IndexRange cb = pmb->c_cellbounds.Bounds(d, IndexDomain::interior);
-          const int g2 = d < ndim ? ng / 2 : 0;
-          p.s[d] = cb.s - g2;
-          p.n[d] = cb.e - cb.s + 1 + 2 * g2;
-          p.fine_is[d] = pmb->cellbounds.Bounds(d, IndexDomain::interior).s;
-          p.coarse_is[d] = cb.s;
-        }
-        p.ncomp = nv.NumComponents();
-        p.fine_stride_j = nv.ni;
-        p.fine_stride_k = nv.ni * nv.nj;
-        p.fine_stride_c = static_cast<int32_t>(nv.comp_stride);
-        p.coarse_stride_j = nv.cni;
-        p.coarse_stride_k = nv.cni * nv.cnj;
-        p.coarse_stride_c = static_cast<int32_t>(nv.ccomp_stride);
-        p.ndim = ndim;
-        p.status = PB2_REGION_ALLOCATED;
-        const UniformCartesian cc(pmb->coords, 2);
-        for (int d = 0; d < 3; ++d) {
-          p.fine_xmin[d] = pmb->coords.GetXmin()[d];
-          p.fine_dx[d] = pmb->coords.Dx()[d];
-          p.coarse_xmin[d] = cc.GetXmin()[d];
-          p.coarse_dx[d] = cc.Dx()[d];
-        }
-        prolongs.push_back(p);
-        continue;
-      }
-      // merged: every child restricts its interior into ITS coarse buffer (GetInteriorRestrict),
-      // which then lands in the parent's quadrant / octant (TryRecvFineToCoarse :225-246)
-      for (int q = 0; q < nleaf; ++q) {
-        const LogicalLocation dloc = Daughter(pmb->loc, q, ndim);
-        auto ch = old_index.find(dloc);
-        PARTHENON_REQUIRE(ch != old_index.end(), "remesh cannot find the origin of a new block");
-        const MeshBlock *ob = old_blocks[ch->second].get();
-        pb2_prores_region p{};
-        p.fine = ov.data() + ch->second * ov.block_stride;
-        p.coarse = ov.coarse() + ch->second * ov.cblock_stride;
-        pb2_copy_region r{};
-        whole(r);
-        r.src = p.coarse;
-        r.dst = nv.data() + nb * nv.block_stride;
+        p.fine = ov.data() + ol * ov.block_stride;
+        p.coarse = ov.coarse() + ol * ov.cblock_stride;
         for (int d = 0; d < 3; ++d) {
           const IndexRange cb = ob->c_cellbounds.Bounds(d, IndexDomain::interior);
           p.s[d] = cb.s;
           p.n[d] = cb.e - cb.s + 1;
           p.fine_is[d] = ob->cellbounds.Bounds(d, IndexDomain::interior).s;
           p.coarse_is[d] = cb.s;
-          const bool upper = d < ndim && (dloc.lx[d] & 1);
-          r.ss[d] = cb.s;
-          r.ds[d] = cb.s + (upper ? cb.e - cb.s + 1 : 0);
-          r.n[d] = cb.e - cb.s + 1;
+          p.fine_xmin[d] = ob->coords.GetXmin()[d];
+          p.fine_dx[d] = ob->coords.Dx()[d];
         }
         p.ncomp = ov.NumComponents();
         p.fine_stride_j = ov.ni;
@@ -308,29 +317,103 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
         p.coarse_stride_c = static_cast<int32_t>(ov.ccomp_stride);
         p.ndim = ndim;
         p.status = PB2_REGION_ALLOCATED;
-        for (int d = 0; d < 3; ++d) {
-          p.fine_xmin[d] = ob->coords.GetXmin()[d];
-          p.fine_dx[d] = ob->coords.Dx()[d];
-        }
         restricts.push_back(p);
-        r.src_stride_j = ov.cni;
-        r.src_stride_k = ov.cni * ov.cnj;
-        r.src_stride_c = static_cast<int32_t>(ov.ccomp_stride);
+      }
+      if (mine_old && !mine_new) {
+        const int ol = old_local(pc.old_gid);
+        pb2_copy_region r{};
+        if (pc.kind == 2)
+          whole_block(r, ov.coarse() + ol * ov.cblock_stride, send_slab.get<Real>() + piece_send[i], true);
+        else
+          whole_block(r, ov.data() + ol * ov.block_stride, send_slab.get<Real>() + piece_send[i], false);
+        sends.push_back(r);
+        continue;
+      }
+      // -- receiver side: the source is the old slab (same device) or the slab that arrived
+      MeshBlock *pmb = block_list[pc.new_gid - nslist[my_rank]].get();
+      const int nb = pmb->pack_index;
+      const Real *src_fine = mine_old ? ov.data() + old_local(pc.old_gid) * ov.block_stride
+                                      : recv_slab.get<Real>() + piece_recv[i];
+      const Real *src_coarse = mine_old && pc.kind == 2
+                                   ? ov.coarse() + old_local(pc.old_gid) * ov.cblock_stride
+                                   : src_fine;
+      if (pc.kind == 0) { // kept block: every cell, ghosts included
+        pb2_copy_region r{};
+        whole_block(r, src_fine, nv.data() + nb * nv.block_stride, false);
+        copies.push_back(r);
+      } else if (pc.kind == 1) {
+        // split: coarse buffer (entire extents) <- the parent's fine data, shifted into the
+        // quadrant / octant this child covers (TryRecvCoarseToFine :117-137)
+        pb2_copy_region r{};
+        whole_block(r, src_fine, nv.coarse() + nb * nv.cblock_stride, true);
+        for (int d = 0; d < 3; ++d)
+          r.ss[d] = (d < ndim && (pmb->loc.lx[d] & 1)) ? base_block_size.nx_[d] / 2 : 0;
+        r.src_stride_j = nv.ni;
+        r.src_stride_k = nv.ni * nv.nj;
+        r.src_stride_c = static_cast<int32_t>(nv.comp_stride);
+        copies.push_back(r);
+        // ProlongateShared over GetInteriorProlongate: coarse interior +- nghost / 2
+        // (bnd_info.cpp:199-203)
+        pb2_prores_region p{};
+        p.fine = nv.data() + nb * nv.block_stride;
+        p.coarse = nv.coarse() + nb * nv.cblock_stride;
+        const UniformCartesian cc(pmb->coords, 2);
+        for (int d = 0; d < 3; ++d) {
+          const IndexRange cb = pmb->c_cellbounds.Bounds(d, IndexDomain::interior);
+          const int g2 = d < ndim ? ng / 2 : 0;
+          p.s[d] = cb.s - g2;
+          p.n[d] = cb.e - cb.s + 1 + 2 * g2;
+          p.fine_is[d] = pmb->cellbounds.Bounds(d, IndexDomain::interior).s;
+          p.coarse_is[d] = cb.s;
+          p.fine_xmin[d] = pmb->coords.GetXmin()[d];
+          p.fine_dx[d] = pmb->coords.Dx()[d];
+          p.coarse_xmin[d] = cc.GetXmin()[d];
+          p.coarse_dx[d] = cc.Dx()[d];
+        }
+        p.ncomp = nv.NumComponents();
+        p.fine_stride_j = nv.ni;
+        p.fine_stride_k = nv.ni * nv.nj;
+        p.fine_stride_c = static_cast<int32_t>(nv.comp_stride);
+        p.coarse_stride_j = nv.cni;
+        p.coarse_stride_k = nv.cni * nv.cnj;
+        p.coarse_stride_c = static_cast<int32_t>(nv.ccomp_stride);
+        p.ndim = ndim;
+        p.status = PB2_REGION_ALLOCATED;
+        prolongs.push_back(p);
+      } else {
+        // merged: the child's restricted interior lands in the parent's quadrant / octant
+        // (TryRecvFineToCoarse :225-246)
+        const LogicalLocation dloc = daughter_of(pmb->loc, pc.q);
+        pb2_copy_region r{};
+        whole_block(r, src_coarse, nv.data() + nb * nv.block_stride, true);
+        for (int d = 0; d < 3; ++d) {
+          const IndexRange cb = pmb->c_cellbounds.Bounds(d, IndexDomain::interior);
+          const bool upper = d < ndim && (dloc.lx[d] & 1);
+          r.ss[d] = cb.s;
+          r.ds[d] = cb.s + (upper ? cb.e - cb.s + 1 : 0);
+          r.n[d] = cb.e - cb.s + 1;
+        }
         r.dst_stride_j = nv.ni;
         r.dst_stride_k = nv.ni * nv.nj;
         r.dst_stride_c = static_cast<int32_t>(nv.comp_stride);
         copies.push_back(r);
       }
     }
-    pb2_bnd_table *t_res = nullptr, *t_copy = nullptr, *t_pro = nullptr;
+    pb2_bnd_table *t_res = nullptr, *t_send = nullptr, *t_copy = nullptr, *t_pro = nullptr;
     PB2_CHECK(pb2_prores_table_create(&t_res, restricts.data(), static_cast<int64_t>(restricts.size())));
+    PB2_CHECK(pb2_copy_table_create(&t_send, sends.data(), static_cast<int64_t>(sends.size())));
     PB2_CHECK(pb2_copy_table_create(&t_copy, copies.data(), static_cast<int64_t>(copies.size())));
     PB2_CHECK(pb2_prores_table_create(&t_pro, prolongs.data(), static_cast<int64_t>(prolongs.size())));
     PB2_CHECK(pb2_restrict(t_res, st));
+    PB2_CHECK(pb2_copy(t_send, nullptr, st));
+    if (nranks > 1) // blocks that change device: one grouped NCCL send/recv per peer
+      PB2_CHECK(pb2_comm_exchange(comm, send_slab.get<Real>(), send_off.data(),
+                                  recv_slab.get<Real>(), recv_off.data(), st));
     PB2_CHECK(pb2_copy(t_copy, nullptr, st));
     PB2_CHECK(pb2_prolongate(t_pro, nv.metadata().ProlongationOp(), st));
     PB2_CHECK(pb2_stream_sync(st));
     pb2_bnd_table_destroy(t_res);
+    pb2_bnd_table_destroy(t_send);
     pb2_bnd_table_destroy(t_copy);
     pb2_bnd_table_destroy(t_pro);
   }

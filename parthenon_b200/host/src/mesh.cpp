@@ -373,8 +373,6 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
 
   max_level = pin->GetOrAddInteger("parthenon/mesh", "numlevel", 1) + root_level - 1;
   derefine_count = pin->GetOrAddInteger("parthenon/mesh", "derefine_count", 10);
-  PARTHENON_REQUIRE(!adaptive || nranks == 1,
-                    "refinement = adaptive runs on one device in this build");
   BuildBlockList(nullptr);
   for (auto &name : packages.Order())
     for (auto &f : packages.Get(name)->AllFields()) {
@@ -473,6 +471,17 @@ void Mesh::ReduceHistory(std::vector<Real> &vals) {
   PB2_CHECK(pb2_memcpy_h2d(d, vals.data(), sizeof(Real) * vals.size(), stream));
   PB2_CHECK(pb2_comm_allreduce_sum(comm, d, static_cast<int64_t>(vals.size()), stream));
   PB2_CHECK(pb2_memcpy_d2h(vals.data(), d, sizeof(Real) * vals.size(), stream));
+  PB2_CHECK(pb2_stream_sync(stream));
+}
+
+void Mesh::AllReduceSum(std::vector<Real> &vals) {
+  if (nranks == 1 || vals.empty()) return;
+  PARTHENON_REQUIRE(comm != nullptr, "multi-rank mesh without a communicator");
+  DeviceBuffer d;
+  d.Allocate(sizeof(Real) * vals.size(), stream);
+  PB2_CHECK(pb2_memcpy_h2d(d.get(), vals.data(), sizeof(Real) * vals.size(), stream));
+  PB2_CHECK(pb2_comm_allreduce_sum(comm, d.get<Real>(), static_cast<int64_t>(vals.size()), stream));
+  PB2_CHECK(pb2_memcpy_d2h(vals.data(), d.get(), sizeof(Real) * vals.size(), stream));
   PB2_CHECK(pb2_stream_sync(stream));
 }
 
