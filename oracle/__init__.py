@@ -115,6 +115,10 @@ def lib():
         L.orc_amr_create.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
                                      C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, dp,
                                      C.c_double]
+        L.orc_amr_create_burgers.restype = C.c_void_p
+        L.orc_amr_create_burgers.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
+                                             C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                             C.c_double]
         L.orc_amr_destroy.argtypes = [C.c_void_p]
         L.orc_amr_mesh.restype = C.c_void_p
         L.orc_amr_mesh.argtypes = [C.c_void_p]
@@ -355,9 +359,21 @@ class AmrAdvection:
 
     def __init__(self, ndim, nx, ng, nrb, numlevel, derefine_count=10, refine_tol=0.3,
                  derefine_tol=0.03, vec_size=1, profile="hard_sphere", amp=1e-6,
-                 v=(1.0, 1.0, 1.0), cfl=0.45, xmin=(-0.5,) * 3, xmax=(0.5,) * 3):
+                 v=(1.0, 1.0, 1.0), cfl=0.45, xmin=(-0.5,) * 3, xmax=(0.5,) * 3, burgers=None):
+        """burgers: None (example/advection) or dict(num_scalars=, recon=, vector_i=) for
+        benchmarks/burgers with the deck's derivative_order_1 criterion"""
         L = lib()
         self.ndim, self.ncomp = ndim, vec_size
+        if burgers is not None:
+            nx3 = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
+            nrb3 = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
+            lo, hi = np.array(xmin, dtype=np.float64), np.array(xmax, dtype=np.float64)
+            self.ncomp = 3 + burgers["num_scalars"]
+            self.h = L.orc_amr_create_burgers(
+                ndim, _ip(nx3), ng, _ip(nrb3), _dp(lo), _dp(hi), numlevel, derefine_count,
+                refine_tol, derefine_tol, burgers.get("vector_i", 3), burgers["num_scalars"],
+                0 if burgers.get("recon", "weno5") == "weno5" else 1, cfl)
+            return
         nx3 = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
         nrb3 = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
         vv = np.array(v, dtype=np.float64)

@@ -1566,6 +1566,12 @@ struct OrcAmr {
   int profile;
   double amp, v[3], cfl;
   int ncomp;
+  /* app = 1: benchmarks/burgers with the generic <parthenon/refinementN> criterion
+   * derivative_order_1 (amr_criteria.cpp:92-101) on one component of U */
+  int app;
+  OrcBurgers *bur;
+  int num_scalars, recon;
+  int crit_comp, crit_max_level; /* vector_i; max_level + root_level (parthenon_manager.cpp:216-220) */
 };
 
 static OrcMesh *amr_make_mesh(const struct OrcAmr *a, const LeafSet *t) {
@@ -1622,8 +1628,31 @@ struct OrcAmr *orc_amr_create(int ndim, const int nx[3], int ng, const int nrb[3
   a->refine_flag = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
   return a;
 }
+/* benchmarks/burgers, refinement = adaptive: criterion = derivative_order_1 on U(vector_i) */
+struct OrcAmr *orc_amr_create_burgers(int ndim, const int nx[3], int ng, const int nrb[3],
+                                      const double xmin[3], const double xmax[3], int numlevel,
+                                      int derefine_count, double refine_tol, double derefine_tol,
+                                      int vector_i, int num_scalars, int recon, double cfl) {
+  const double v0[3] = {0, 0, 0};
+  struct OrcAmr *a = orc_amr_create(ndim, nx, ng, nrb, xmin, xmax, numlevel, derefine_count,
+                                    refine_tol, derefine_tol, 3 + num_scalars, 2, 0.0, v0, cfl);
+  orc_advection_destroy(a->adv);
+  a->adv = NULL;
+  a->app = 1;
+  a->num_scalars = num_scalars;
+  a->recon = recon;
+  a->crit_comp = vector_i;
+  a->crit_max_level = numlevel + a->m->root_level;
+  a->bur = orc_burgers_create(a->m, num_scalars, recon, cfl);
+  if (!a->bur->Uc)
+    a->bur->Uc = (double *)calloc((size_t)a->m->nblocks * a->ncomp * a->m->cn[0] * a->m->cn[1] * a->m->cn[2],
+                                  sizeof(double));
+  return a;
+}
+
 void orc_amr_destroy(struct OrcAmr *a) {
   if (!a) return;
+  orc_burgers_destroy(a->bur);
   orc_advection_destroy(a->adv);
   orc_mesh_destroy(a->m);
   free(a->deref_count);
@@ -1631,9 +1660,9 @@ void orc_amr_destroy(struct OrcAmr *a) {
   free(a);
 }
 const OrcMesh *orc_amr_mesh(const struct OrcAmr *a) { return a->m; }
-double *orc_amr_U(struct OrcAmr *a) { return a->adv->U; }
-double orc_amr_dt(const struct OrcAmr *a) { return a->adv->dt; }
-double orc_amr_time(const struct OrcAmr *a) { return a->adv->time; }
+double *orc_amr_U(struct OrcAmr *a) { return a->app ? a->bur->U : a->adv->U; }
+double orc_amr_dt(const struct OrcAmr *a) { return a->app ? a->bur->dt : a->adv->dt; }
+double orc_amr_time(const struct OrcAmr *a) { return a->app ? a->bur->time : a->adv->time; }
 
 /* CheckRefinement + SetRefinement for every block, on container U */
 static void amr_tag(struct OrcAmr *a, const double *U) {
@@ -1648,7 +1677,25 @@ static void amr_tag(struct OrcAmr *a, const double *U) {
       mx = p[q] > mx ? p[q] : mx;
     }
     int aret = 0; /* AmrTag: derefine -1, same 0, refine 1 */
-    if (mx > a->refine_tol && mn < a->derefine_tol)
+    if (a->app == 1) {
+      /* Refinement::FirstDerivative refinement_package.cpp:92-122 over the interior of one
+       * component; CheckAllRefinement :55-90: a "refine" at or above the criterion's max level
+       * becomes "same" (:78-81); packages without a CheckRefinementBlock vote "derefine" */
+      const size_t str[3] = {1, (size_t)m->n[0], (size_t)m->n[0] * m->n[1]};
+      double maxd = 0.0;
+      for (int k = m->is[2]; k <= m->ie[2]; ++k)
+        for (int j = m->is[1]; j <= m->ie[1]; ++j)
+          for (int i = m->is[0]; i <= m->ie[0]; ++i) {
+            const double *q = U + fidx(m, a->ncomp, b, a->crit_comp, k, j, i);
+            const double scale = fabs(q[0]);
+            for (int d = 0; d < m->ndim; ++d) {
+              const double dd = 0.5 * fabs(q[str[d]] - q[-(long)str[d]]) / (scale + 1.0e-20);
+              maxd = dd > maxd ? dd : maxd;
+            }
+          }
+      aret = maxd > a->refine_tol ? 1 : (maxd < a->derefine_tol ? -1 : 0);
+      if (aret == 1 && blk->loc.level >= a->crit_max_level) aret = 0;
+    } else if (mx > a->refine_tol && mn < a->derefine_tol)
       aret = 1;
     else if (mx < a->derefine_tol)
       aret = -1;
@@ -1735,12 +1782,37 @@ static int amr_remesh(struct OrcAmr *a) {
   /* ---- RedistributeAndRefineMeshBlocks ---- */
   OrcMesh *nm = amr_make_mesh(a, &t);
   free(t.leaf);
-  OrcAdvection *oa = a->adv;
-  OrcAdvection *na = orc_advection_create(nm, a->ncomp, a->profile, a->amp, a->v, a->cfl);
-  na->dt = oa->dt;
-  na->time = oa->time;
-  na->ncycle = oa->ncycle;
-  na->allowed_dt = oa->allowed_dt;
+  /* the application state on the new mesh; only the base container is carried over (:667) */
+  typedef struct {
+    double *U, *Uc;
+  } BaseFields;
+  BaseFields oa_, na_, *oa = &oa_, *na = &na_;
+  OrcAdvection *nadv = NULL;
+  OrcBurgers *nbur = NULL;
+  if (a->app == 1) {
+    nbur = orc_burgers_create(nm, a->num_scalars, a->recon, a->cfl);
+    if (!nbur->Uc)
+      nbur->Uc = (double *)calloc((size_t)nm->nblocks * a->ncomp * nm->cn[0] * nm->cn[1] * nm->cn[2],
+                                  sizeof(double));
+    nbur->dt = a->bur->dt;
+    nbur->time = a->bur->time;
+    nbur->ncycle = a->bur->ncycle;
+    nbur->allowed_dt = a->bur->allowed_dt;
+    oa_.U = a->bur->U;
+    oa_.Uc = a->bur->Uc;
+    na_.U = nbur->U;
+    na_.Uc = nbur->Uc;
+  } else {
+    nadv = orc_advection_create(nm, a->ncomp, a->profile, a->amp, a->v, a->cfl);
+    nadv->dt = a->adv->dt;
+    nadv->time = a->adv->time;
+    nadv->ncycle = a->adv->ncycle;
+    nadv->allowed_dt = a->adv->allowed_dt;
+    oa_.U = a->adv->U;
+    oa_.Uc = a->adv->Uc;
+    na_.U = nadv->U;
+    na_.Uc = nadv->Uc;
+  }
   int *ncount = (int *)calloc((size_t)nm->nblocks, sizeof(int));
   int *nflag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
   const int nc = a->ncomp;
@@ -1812,22 +1884,51 @@ static int amr_remesh(struct OrcAmr *a) {
     }
   }
   free(ctmp);
-  orc_advection_destroy(oa);
+  if (a->app == 1) {
+    orc_burgers_destroy(a->bur);
+    a->bur = nbur;
+  } else {
+    orc_advection_destroy(a->adv);
+    a->adv = nadv;
+  }
   orc_mesh_destroy(a->m);
   free(a->deref_count);
   free(a->refine_flag);
   a->m = nm;
-  a->adv = na;
   a->deref_count = ncount;
   a->refine_flag = nflag;
   /* PreCommFillDerived; CommunicateBoundaries; FillDerived  (:1000-1003) */
   orc_exchange(nm, na->U, na->Uc, nc, 1);
   orc_apply_bcs(nm, na->U, nc);
+  if (a->app == 1) calculate_derived(a->bur, a->bur->U);
   return 1;
 }
 
 /* Mesh::Initialize mesh.cpp:745-860 + EvolutionDriver::InitializeBlockTimeStepsAndBoundaries */
+static void amr_init_burgers(struct OrcAmr *a) {
+  int done;
+  do {
+    OrcBurgers *st = a->bur;
+    orc_burgers_ic(a->m, st->U, st->ncomp);
+    orc_exchange(a->m, st->U, st->Uc, st->ncomp, 1);
+    orc_apply_bcs(a->m, st->U, st->ncomp);
+    calculate_derived(st, st->U);
+    amr_tag(a, st->U);
+    done = !amr_remesh(a);
+  } while (!done);
+  OrcBurgers *st = a->bur;
+  st->allowed_dt = estimate_timestep(st, st->U);
+  st->dt = DBL_MAX;
+  set_global_timestep(st);
+  st->time = 0;
+  st->ncycle = 0;
+}
+
 void orc_amr_init(struct OrcAmr *a) {
+  if (a->app == 1) {
+    amr_init_burgers(a);
+    return;
+  }
   int done;
   do {
     OrcAdvection *st = a->adv;
@@ -1853,6 +1954,15 @@ void orc_amr_init(struct OrcAmr *a) {
  *   orc_amr_regrid  LoadBalancingAndAdaptiveMeshRefinement, InitializeBlockTimeSteps if the
  *                   mesh changed, SetGlobalTimeStep; returns 1 if the mesh changed */
 void orc_amr_step(struct OrcAmr *a) {
+  if (a->app == 1) {
+    OrcBurgers *bs = a->bur;
+    orc_burgers_stage(bs, 1);
+    orc_burgers_stage(bs, 2);
+    amr_tag(a, bs->U); /* Refinement::Tag after ApplyBoundaryConditions, burgers_driver.cpp:137-144 */
+    bs->ncycle++;
+    bs->time += bs->dt;
+    return;
+  }
   OrcAdvection *st = a->adv;
   orc_advection_stage(st, 1);
   orc_advection_stage(st, 2);
@@ -1862,6 +1972,12 @@ void orc_amr_step(struct OrcAmr *a) {
 }
 int orc_amr_regrid(struct OrcAmr *a) {
   const int changed = amr_remesh(a);
+  if (a->app == 1) {
+    OrcBurgers *bs = a->bur;
+    if (changed) bs->allowed_dt = estimate_timestep(bs, bs->U); /* InitializeBlockTimeSteps */
+    set_global_timestep(bs);
+    return changed;
+  }
   OrcAdvection *st = a->adv;
   if (changed) st->allowed_dt = advection_estimate_timestep(st);
   if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;

@@ -149,6 +149,16 @@ PB2_DUMP_PREFIX="$d/U" PB2_DUMP_FIELD=advected "$WORK/advection_dump" -i deck.pi
   parthenon/time/nlim=30 parthenon/time/tlim=1e9 parthenon/output0/dt=-1 parthenon/output1/dt=-1 \
   parthenon/output3/dt=-1 parthenon/output4/dt=-1 Advection/fill_derived=false > run.log 2>&1
 python3 "$HERE/pack_checksums.py" "$d" "$OUT/advection_a32_b8_l3_3d_crc.npz" 2
+# benchmarks/burgers as shipped (adaptive, <parthenon/refinement0> derivative_order_1 on U(3)),
+# small: 32^3 base, 8^3 blocks, tolerances lowered so that the mesh changes within 24 cycles
+d="$WORK/burgers_a32_b8_l2"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+PB2_DUMP_PREFIX="$d/U" "$WORK/burgers_dump" -i "$REF/benchmarks/burgers/burgers.pin" \
+  parthenon/mesh/nx1=32 parthenon/mesh/nx2=32 parthenon/mesh/nx3=32 \
+  parthenon/meshblock/nx1=8 parthenon/meshblock/nx2=8 parthenon/meshblock/nx3=8 \
+  parthenon/time/nlim=24 parthenon/output0/dt=-1 parthenon/output1/dt=-1 burgers/num_scalars=1 \
+  parthenon/mesh/derefine_count=3 parthenon/refinement0/refine_tol=0.3 \
+  parthenon/refinement0/derefine_tol=0.1 > run.log 2>&1
+python3 "$HERE/pack_checksums.py" "$d" "$OUT/burgers_a32_b8_l2_crc.npz" 4
 fi
 # example/sparse_advection (2-D only in the reference): four sparse fields allocated where
 # their data is, allocated on a neighbour when a non-null boundary buffer arrives, deallocated
