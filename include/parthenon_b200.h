@@ -281,6 +281,13 @@ int pb2_block_quiet_flags(const pb2_pack_geom *g, const double *u, double thresh
 int pb2_block_minmax(const pb2_pack_geom *g, const double *u, const int32_t *block_mask,
                      double *minmax, pb2_stream_t stream);
 
+/* The stock refinement criteria <parthenon/refinementN> method = derivative_order_1 / _2
+ * (Refinement::FirstDerivative / SecondDerivative, amr_criteria/refinement_package.cpp:92-150):
+ * maxd[b] = largest normalised first (order 1) or second (order 2) difference of component
+ * `comp` over the interior cells of block b.  maxd: device [nblocks]. */
+int pb2_block_derivative(const pb2_pack_geom *g, const double *u, int comp, int order,
+                         double *maxd, pb2_stream_t stream);
+
 /* z = w1*x + w2*y over the GHOST cells of every block only: what the reference's full-extent
  * WeightedSumData passes (AverageIndependentData / UpdateIndependentData, update.hpp:122-137)
  * do outside the interior.  A fused interior update plus this call equals the reference on

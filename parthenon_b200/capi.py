@@ -96,7 +96,7 @@ SYMBOLS = [
     "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
     "pb2_halo_copy_uniform", "pb2_advection_fluxes", "pb2_copy_flags", "pb2_copy_select",
     "pb2_weighted_sum_blocks", "pb2_flux_divergence_blocks", "pb2_advection_fluxes_blocks",
-    "pb2_block_quiet_flags", "pb2_block_minmax", "pb2_bc_table_create", "pb2_apply_bcs",
+    "pb2_block_quiet_flags", "pb2_block_minmax", "pb2_block_derivative", "pb2_bc_table_create", "pb2_apply_bcs",
     "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
@@ -142,6 +142,7 @@ def lib():
     L.pb2_flux_divergence_blocks.argtypes = [C.POINTER(PackGeom), C.POINTER(vp), vp, vp, vp]
     L.pb2_advection_fluxes_blocks.argtypes = [C.POINTER(PackGeom), vp, C.POINTER(vp),
                                               c_double_p, vp, vp]
+    L.pb2_block_derivative.argtypes = [C.POINTER(PackGeom), vp, C.c_int, C.c_int, vp, vp]
     L.pb2_block_minmax.argtypes = [C.POINTER(PackGeom), vp, vp, vp, vp]
     L.pb2_block_quiet_flags.argtypes = [C.POINTER(PackGeom), vp, C.c_double, vp, vp, vp]
     L.pb2_halo_copy_uniform.argtypes = [vp, vp, vp, vp]

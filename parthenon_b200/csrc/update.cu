@@ -151,6 +151,48 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Refinement::FirstDerivative / SecondDerivative (amr_criteria/refinement_package.cpp:92-150):
+// the largest normalised first (ORDER 1) or second (ORDER 2) difference of one component over
+// the interior cells of every block.  max is exact in any order, so a plain tree reduction
+// reproduces the reference's Kokkos::Max bit for bit.
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+    block_derivative_kernel(const DivGeom g, const double *__restrict__ u, int comp,
+                            double *__restrict__ out) {
+  const int b = blockIdx.x;
+  const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
+  const double *q0 = u + (int64_t)b * g.sb + (int64_t)comp * g.sc;
+  const int64_t str[3] = {1, g.sj, g.sk};
+  double maxd = 0.0;
+  for (int t = threadIdx.x; t < ncell; t += 256) {
+    const int i = g.is[0] + t % g.nx[0];
+    const int tj = t / g.nx[0];
+    const int j = g.is[1] + tj % g.nx[1];
+    const int k = g.is[2] + tj / g.nx[1];
+    const double *q = q0 + (int64_t)k * g.sk + (int64_t)j * g.sj + i;
+    const double c = q[0];
+    for (int d = 0; d < g.ndim; ++d) {
+      double v;
+      if (ORDER == 1) {
+        v = 0.5 * fabs((q[str[d]] - q[-str[d]])) / (fabs(c) + 1.0e-20);
+      } else {
+        const double aqt = fabs(c) + 1.0e-20;
+        const double qavg = 0.5 * (q[str[d]] + q[-str[d]]);
+        v = fabs(qavg - c) / (fabs(qavg) + aqt);
+      }
+      maxd = v > maxd ? v : maxd;
+    }
+  }
+  __shared__ double sm[256];
+  sm[threadIdx.x] = maxd;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x + s] > sm[threadIdx.x] ? sm[threadIdx.x + s] : sm[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[b] = sm[0];
+}
+
 // example/advection CalculateFluxes with a constant velocity (advection_package.cpp:540-646;
 // DonorCellX1/2/3 reconstruct/dc_inline.hpp:31-71): the flux through the lower d-face of a
 // cell is the upwind cell value times v_d.  One thread per (block, component, cell of the
@@ -352,6 +394,37 @@ int pb2_weighted_sum_blocks(const pb2_pack_geom *pg, const double *x, const doub
   ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
   weighted_sum_blocks_kernel<<<pg->nblocks * cpb, 256, 0, as_stream(stream)>>>(
       x, y, w1, w2, z, pg->block_stride, per_block, block_mask, cpb);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_block_derivative(const pb2_pack_geom *pg, const double *u, int comp, int order,
+                         double *maxd, pb2_stream_t stream) {
+  PB2_REQUIRE(pg && u && maxd, "bad arguments");
+  PB2_REQUIRE(comp >= 0 && comp < pg->ncomp, "component out of range");
+  PB2_REQUIRE(order == 1 || order == 2, "order must be 1 or 2");
+  PB2_REQUIRE(pg->ng >= 1, "the criterion reads one ghost layer");
+  if (int rc = require_device()) return rc;
+  if (pg->nblocks == 0) return PB2_OK;
+  DivGeom g;
+  g.nblocks = pg->nblocks;
+  g.ncomp = pg->ncomp;
+  g.ndim = pg->ndim;
+  for (int d = 0; d < 3; ++d) {
+    const bool sym = d >= pg->ndim;
+    g.nx[d] = sym ? 1 : pg->nx[d];
+    g.is[d] = sym ? 0 : pg->ng;
+    g.n[d] = sym ? 1 : pg->nx[d] + 2 * pg->ng;
+  }
+  g.sj = g.n[0];
+  g.sk = (int64_t)g.n[0] * g.n[1];
+  g.sc = g.sk * g.n[2];
+  g.sb = pg->block_stride;
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  if (order == 1)
+    block_derivative_kernel<1><<<g.nblocks, 256, 0, as_stream(stream)>>>(g, u, comp, maxd);
+  else
+    block_derivative_kernel<2><<<g.nblocks, 256, 0, as_stream(stream)>>>(g, u, comp, maxd);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -57,6 +57,12 @@ tlim = 1e9
 integrator = rk2
 ncycle_out = 0
 perf_cycle_offset = 0
+<parthenon/refinement0>
+method = derivative_order_1
+field = U
+vector_i = 3
+refine_tol = 0.5
+derefine_tol = 0.2
 <burgers>
 cfl = 0.8
 recon = weno5

@@ -77,7 +77,9 @@ TaskCollection BurgersDriver::MakeTaskCollection(BlockList_t &blocks, const int 
 
     // set physical boundaries (the per-block second region of burgers_driver.cpp:129-147, here
     // one launch per direction for the whole batch; nothing to do on periodic meshes)
-    tl.AddTask(set, ApplyBoundaryConditionsMD, mc1);
+    auto set_bc = tl.AddTask(set, ApplyBoundaryConditionsMD, mc1);
+    // Update refinement (burgers_driver.cpp:139-145)
+    if (last && pmesh->adaptive) tl.AddTask(set_bc, Refinement::Tag, mc1.get());
 
     if (fused) {
       if (last) tl.AddTask(set, burgers_package::CollectFusedTimestep, mc1.get());

@@ -217,6 +217,16 @@ class Mesh {
   int derefine_count = 10;     // <parthenon/mesh>/derefine_count (mesh_refinement.cpp:56)
   bool modified = false;
   int nbnew = 0, nbdel = 0;
+  // <parthenon/refinementN> blocks (AMRCriteria, amr_criteria/amr_criteria.cpp:25-101): the
+  // stock derivative criteria on one component of a field
+  struct AMRCriterion {
+    int order = 1;     // method = derivative_order_1 | derivative_order_2
+    std::string field;
+    int comp = 0;      // vector_i (tensor indices are not supported)
+    Real refine_criteria = 0.5, derefine_criteria = 0.05;
+    int max_level = 1; // logical level: root level added (parthenon_manager.cpp:216-220)
+  };
+  std::vector<AMRCriterion> amr_criteria;
   // MeshRefinement::SetRefinement (mesh_refinement.cpp:81-118) for block `lid`
   void SetRefinement(int lid, AmrTag flag);
   // Mesh::LoadBalancingAndAdaptiveMeshRefinement (mesh-amr_loadbalance.cpp:324-351): update

@@ -451,7 +451,31 @@ TaskStatus Tag(MeshData<Real> *rc) {
     for (size_t b = 0; b < t.size(); ++b) tags[b] = any ? std::max(tags[b], t[b]) : t[b];
     any = true;
   }
-  if (!any) std::fill(tags.begin(), tags.end(), AmrTag::same);
+  // the stock criteria of <parthenon/refinementN> (:72-88): a "refine" at or above the
+  // criterion's max level counts as "same"
+  if (!pm->amr_criteria.empty()) {
+    const int nb = rc->NumBlocks();
+    DeviceBuffer dev;
+    dev.Allocate(sizeof(Real) * nb, rc->stream());
+    std::vector<Real> maxd(nb);
+    for (const auto &c : pm->amr_criteria) {
+      if (!rc->HasVariable(c.field)) continue; // AmrTag::same: no vote beyond the default
+      Variable &v = rc->Get(c.field);
+      const pb2_pack_geom g = rc->Geometry(v);
+      PB2_CHECK(pb2_block_derivative(&g, v.data(), c.comp, c.order, dev.get<Real>(), rc->stream()));
+      PB2_CHECK(pb2_memcpy_d2h(maxd.data(), dev.get(), sizeof(Real) * nb, rc->stream()));
+      PB2_CHECK(pb2_stream_sync(rc->stream()));
+      for (int b = 0; b < nb; ++b) {
+        AmrTag t = maxd[b] > c.refine_criteria
+                       ? AmrTag::refine
+                       : (maxd[b] < c.derefine_criteria ? AmrTag::derefine : AmrTag::same);
+        if (t == AmrTag::refine && rc->GetBlock(b)->loc.level >= c.max_level) t = AmrTag::same;
+        tags[b] = std::max(tags[b], t);
+      }
+    }
+    any = true;
+  }
+  if (!any) std::fill(tags.begin(), tags.end(), AmrTag::derefine);
   for (int b = 0; b < rc->NumBlocks(); ++b) pm->SetRefinement(rc->GetBlock(b)->lid, tags[b]);
   return TaskStatus::complete;
 }

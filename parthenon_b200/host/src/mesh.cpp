@@ -373,6 +373,28 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
 
   max_level = pin->GetOrAddInteger("parthenon/mesh", "numlevel", 1) + root_level - 1;
   derefine_count = pin->GetOrAddInteger("parthenon/mesh", "derefine_count", 10);
+  // Refinement::Initialize (refinement_package.cpp:36-50)
+  for (int n = 0;; ++n) {
+    const std::string block = "parthenon/refinement" + std::to_string(n);
+    if (!pin->DoesBlockExist(block)) break;
+    AMRCriterion c;
+    const std::string method = pin->GetOrAddString(block, "method", "PLEASE SPECIFY method");
+    PARTHENON_REQUIRE_THROWS(method == "derivative_order_1" || method == "derivative_order_2",
+                             "\n  Invalid selection for refinment method in " + block + ": " + method);
+    c.order = method == "derivative_order_1" ? 1 : 2;
+    c.field = pin->GetOrAddString(block, "field", "NO FIELD WAS SET");
+    PARTHENON_REQUIRE_THROWS(c.field != "NO FIELD WAS SET", "Error in " + block + ": no field set");
+    PARTHENON_REQUIRE_THROWS(!pin->DoesParameterExist(block, "tensor_ij") &&
+                                 !pin->DoesParameterExist(block, "tensor_ijk"),
+                             "tensor-valued refinement fields are not supported");
+    c.comp = pin->GetOrAddInteger(block, "vector_i", 0);
+    c.refine_criteria = pin->GetOrAddReal(block, "refine_tol", 0.5);
+    c.derefine_criteria = pin->GetOrAddReal(block, "derefine_tol", 0.05);
+    const int global_max_level = pin->GetOrAddInteger("parthenon/mesh", "numlevel", 1);
+    c.max_level = std::min(pin->GetOrAddInteger(block, "max_level", global_max_level), global_max_level);
+    c.max_level += root_level;
+    amr_criteria.push_back(c);
+  }
   BuildBlockList(nullptr);
   for (auto &name : packages.Order())
     for (auto &f : packages.Get(name)->AllFields()) {

@@ -316,3 +316,27 @@ def test_overlapped_halo_path_is_bit_identical():
     assert a.dt == b.dt and a.time == b.time
     assert np.array_equal(a.get_field("base", "U"), b.get_field("base", "U"))
     assert np.array_equal(a.get_field("base", "derived"), b.get_field("base", "derived"))
+
+
+@pytest.mark.parametrize("math,fused", [("strict", True), ("strict", False)])
+def test_adaptive_burgers_crc_vs_reference(math, fused):
+    """benchmarks/burgers with refinement = adaptive (the shipped deck's derivative_order_1
+    criterion): tagging on the device, remesh, flux correction, 120 -> 148 -> 176 blocks in 24
+    cycles — block list and CRC-32 of every block's bytes against the reference run"""
+    from tests.test_oracle_golden import check_against_crc_fixture
+    ov = burgers_overrides(8, 4, 4, 1, "weno5", math, fused,
+                           {"parthenon/mesh/refinement": "adaptive", "parthenon/mesh/numlevel": 2,
+                            "parthenon/mesh/derefine_count": 3,
+                            "parthenon/refinement0/refine_tol": 0.3,
+                            "parthenon/refinement0/derefine_tol": 0.1})
+    sim = host.Simulation(overrides=ov)
+    sim.pre_execute()
+
+    def state():
+        n = sim.info()["nblocks"]
+        return (np.array([sim.block(b)["loc"] for b in range(n)]),
+                sim.get_field("base", "U"), sim.time)
+
+    counts = check_against_crc_fixture("burgers_a32_b8_l2_crc", (32, 32, 32), (8, 8, 8), 24,
+                                       state, sim.step, sim.regrid)
+    assert counts == {120, 148, 176}
