@@ -1,6 +1,8 @@
 // runtime.cu — plumbing entry points of the C ABI (device, memory, streams, events).
 #include <cstdarg>
 #include <mutex>
+#include <unordered_map>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -188,14 +190,71 @@ int pb2_device_sm_count(int *count) {
   PB2_CUDA_CHECK(cudaDeviceGetAttribute(count, cudaDevAttrMultiProcessorCount, dev));
   return PB2_OK;
 }
+// Large device allocations are recycled through an exact-size cache: an adaptive run re-creates
+// its multi-GB field slabs on every remesh, and cudaFree of such slabs (unmapping) was measured
+// at up to half a second per remesh.  Callers round slab capacities (host: Variable), so sizes
+// repeat.  The synchronous semantics of cudaMalloc / cudaFree are kept: a pointer is usable by
+// any stream on return, and a free waits for the device before the memory can be handed out
+// again.  The cache is bounded; beyond the bound memory really is returned.
+namespace {
+constexpr size_t kCacheMinBytes = size_t(1) << 20;
+constexpr size_t kCacheMaxBytes = size_t(48) << 30;
+constexpr size_t kCacheMaxEntries = 96;
+std::mutex g_cache_mu;
+std::multimap<size_t, void *> g_cache;           // size -> free pointer
+std::unordered_map<void *, size_t> g_live_sizes; // every live pointer handed out by pb2_malloc
+size_t g_cache_bytes = 0;
+} // namespace
+
 int pb2_malloc(void **ptr, size_t bytes) {
   PB2_REQUIRE(ptr, "null argument");
   if (int rc = require_device()) return rc;
-  PB2_CUDA_CHECK(cudaMalloc(ptr, bytes ? bytes : 1));
+  if (bytes == 0) bytes = 1;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache.find(bytes);
+    if (it != g_cache.end()) {
+      *ptr = it->second;
+      g_cache_bytes -= bytes;
+      g_cache.erase(it);
+      g_live_sizes[*ptr] = bytes;
+      return PB2_OK;
+    }
+  }
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e == cudaErrorMemoryAllocation) { // give the cache back and try once more
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto &kv : g_cache) cudaFree(kv.second);
+    g_cache.clear();
+    g_cache_bytes = 0;
+    e = cudaMalloc(ptr, bytes);
+  }
+  PB2_CUDA_CHECK(e);
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  g_live_sizes[*ptr] = bytes;
   return PB2_OK;
 }
 int pb2_free(void *ptr) {
   if (!ptr) return PB2_OK;
+  size_t bytes = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_live_sizes.find(ptr);
+    if (it != g_live_sizes.end()) {
+      bytes = it->second;
+      g_live_sizes.erase(it);
+    }
+  }
+  if (bytes >= kCacheMinBytes) {
+    PB2_CUDA_CHECK(cudaDeviceSynchronize()); // what cudaFree would have waited for
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache_bytes + bytes <= kCacheMaxBytes && g_cache.size() < kCacheMaxEntries) {
+      g_cache.emplace(bytes, ptr);
+      g_cache_bytes += bytes;
+      return PB2_OK;
+    }
+  }
   PB2_CUDA_CHECK(cudaFree(ptr));
   return PB2_OK;
 }

@@ -245,6 +245,10 @@ class Mesh {
   // this rank: the field appears zero-filled in (or disappears from) EVERY container
   void AllocateSparse(const std::string &label, int lid);
   void DeallocateSparse(const std::string &label, int lid);
+  // number of blocks field slabs are sized for: the block count itself on static meshes; on
+  // adaptive meshes 25 % headroom that is only re-drawn when the block count leaves
+  // [capacity / 2, capacity], so that successive remeshes allocate identical slab sizes
+  int SlabCapacity(int nblocks);
   bool HasFineCoarseFaces() const;
   mutable int fine_coarse_faces_ = -1; // cached answer (static meshes)
 
@@ -279,6 +283,7 @@ class Mesh {
 
  private:
   int pack_size_ = -1;
+  int slab_capacity_ = 0;
   DeviceBuffer scratch_;
   std::unordered_map<LogicalLocation, int, LogicalLocationHash> leaf_gid_;
   std::unordered_map<LogicalLocation, int, LogicalLocationHash> internal_;

@@ -28,7 +28,8 @@ struct BvarsCache; // ghost-exchange tables of one MeshData (bvals.hpp)
 class Variable {
  public:
   Variable(const std::string &label, const Metadata &m, int sparse_id, int nblocks,
-           const IndexShape &cb, const IndexShape &ccb, bool multilevel, pb2_stream_t stream);
+           const IndexShape &cb, const IndexShape &ccb, bool multilevel, pb2_stream_t stream,
+           int capacity = 0);
   const std::string &label() const { return label_; }
   const Metadata &metadata() const { return m_; }
   bool IsSet(MetadataFlag f) const { return m_.IsSet(f); }
@@ -63,7 +64,7 @@ class Variable {
  private:
   std::string label_;
   Metadata m_;
-  int sparse_id_, ncomp_, nblocks_;
+  int sparse_id_, ncomp_, nblocks_, capacity_;
   bool multilevel_;
   pb2_stream_t stream_;
   DeviceBuffer data_, coarse_, flux_[3];

@@ -15,6 +15,9 @@
 //                     the parent, pb2_prolongate covers interior + ghosts
 // followed by one full ghost exchange on the new mesh.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <unordered_set>
 
 #include "pb2/bvals.hpp"
@@ -161,6 +164,10 @@ bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nn
 void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &new_leaves) {
   PARTHENON_REQUIRE(DefaultNumPartitions() == 1,
                     "remeshing needs one MeshData per rank (parthenon/mesh/pack_size = -1)");
+  static const bool timing = std::getenv("PB2_TIME_REMESH") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   // only the base container survives a remesh (:667)
   mesh_data.PurgeNonBase();
   std::shared_ptr<MeshData<Real>> old_md = mesh_data.GetOrAdd("base", 0);
@@ -193,8 +200,10 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     if (it == old_gid.end() || old_ranklist[it->second] != my_rank)
       pmb->SetAllowedDt(std::numeric_limits<Real>::max()); // MeshBlock::Make: no time step yet
   }
+  const auto t1 = now();
   mesh_data.Clear();
   std::shared_ptr<MeshData<Real>> new_md = mesh_data.GetOrAdd("base", 0);
+  const auto t2 = now();
 
   const int nleaf = 1 << ndim;
   const int ng = Globals::nghost;
@@ -417,12 +426,18 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     pb2_bnd_table_destroy(t_copy);
     pb2_bnd_table_destroy(t_pro);
   }
+  const auto t3 = now();
   old_md.reset(); // the old slabs go away here
+  const auto t4 = now();
   // PreCommFillDerived; CommunicateBoundaries; FillDerived (:1000-1003)
   Update::PreCommFillDerived(new_md.get());
   CommunicateBoundaries(new_md, true);
   Update::FillDerived(new_md.get());
   PB2_CHECK(pb2_stream_sync(st));
+  if (timing)
+    std::fprintf(stderr, "remesh: purge+tree+blocks %.2f ms, new container %.2f, move data %.2f, "
+                         "free old %.2f, exchange+derived %.2f (nblocks %d)\n",
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()), nbtotal);
 }
 
 void Mesh::LoadBalancingAndAdaptiveMeshRefinement(ParameterInput *, ApplicationInput *) {

@@ -507,6 +507,13 @@ void Mesh::AllReduceSum(std::vector<Real> &vals) {
   PB2_CHECK(pb2_stream_sync(stream));
 }
 
+int Mesh::SlabCapacity(int nblocks) {
+  if (!adaptive) return nblocks;
+  if (nblocks > slab_capacity_ || 2 * nblocks < slab_capacity_)
+    slab_capacity_ = (nblocks + nblocks / 4 + 63) / 64 * 64;
+  return slab_capacity_;
+}
+
 bool Mesh::HasFineCoarseFaces() const {
   if (!multilevel) return false;
   if (fine_coarse_faces_ < 0) {

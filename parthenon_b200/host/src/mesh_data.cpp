@@ -9,9 +9,10 @@ namespace parthenon {
 
 Variable::Variable(const std::string &label, const Metadata &m, int sparse_id, int nblocks,
                    const IndexShape &cb, const IndexShape &ccb, bool multilevel,
-                   pb2_stream_t stream)
+                   pb2_stream_t stream, int capacity)
     : label_(label), m_(m), sparse_id_(sparse_id), ncomp_(m.NumComponents()),
-      nblocks_(nblocks), multilevel_(multilevel), stream_(stream) {
+      nblocks_(nblocks), capacity_(std::max(capacity, nblocks)), multilevel_(multilevel),
+      stream_(stream) {
   PARTHENON_REQUIRE(m.IsSet(Metadata::Cell) || m.IsSet(Metadata::None),
                     "only cell-centred fields are supported by this build (" + label + ")");
   ni = cb.ncellsi(IndexDomain::entire);
@@ -39,17 +40,22 @@ int Variable::GetDim(int i) const {
   }
 }
 
+// slabs are allocated for `capacity_` blocks (>= the block count).  On adaptive meshes the mesh
+// hands out a capacity that changes rarely (Mesh::SlabCapacity), so the slabs of successive
+// remeshes have the same size and the allocator's exact-size cache (csrc/runtime.cu) recycles
+// them instead of unmapping and mapping GBs
+#define SlabBlocks(n) (static_cast<size_t>(std::max(capacity_, std::max((n), 1))))
+
 Real *Variable::data() {
   if (!data_)
-    data_.Allocate(sizeof(Real) * static_cast<size_t>(block_stride) * std::max(nblocks_, 1),
-                   stream_);
+    data_.Allocate(sizeof(Real) * static_cast<size_t>(block_stride) * SlabBlocks(nblocks_), stream_);
   return data_.get<Real>();
 }
 
 Real *Variable::coarse() {
   PARTHENON_REQUIRE(multilevel_, "coarse buffers only exist on multilevel meshes");
   if (!coarse_)
-    coarse_.Allocate(sizeof(Real) * static_cast<size_t>(cblock_stride) * std::max(nblocks_, 1),
+    coarse_.Allocate(sizeof(Real) * static_cast<size_t>(cblock_stride) * SlabBlocks(nblocks_),
                      stream_);
   return coarse_.get<Real>();
 }
@@ -59,7 +65,7 @@ Real *Variable::flux(int dir) {
   PARTHENON_REQUIRE(dir >= 1 && dir <= 3, "flux direction must be X1DIR..X3DIR");
   DeviceBuffer &f = flux_[dir - 1];
   if (!f)
-    f.Allocate(sizeof(Real) * static_cast<size_t>(block_stride) * std::max(nblocks_, 1), stream_);
+    f.Allocate(sizeof(Real) * static_cast<size_t>(block_stride) * SlabBlocks(nblocks_), stream_);
   return f.get<Real>();
 }
 
@@ -111,7 +117,8 @@ MeshData<T>::MeshData(Mesh *pmesh, int partition_id, const std::string &label,
       v = base->vars_.at(f.name);
     } else {
       v = std::make_shared<Variable>(f.name, f.m, f.sparse_id, NumBlocks(), cb, ccb,
-                                     pmesh->multilevel, pmesh->stream);
+                                     pmesh->multilevel, pmesh->stream,
+                                     pmesh->SlabCapacity(NumBlocks()));
       if (base != nullptr) // a stage container starts with base's allocation status
         for (int b = 0; b < NumBlocks(); ++b) v->SetAllocated(b, base->vars_.at(f.name)->IsAllocated(b));
     }

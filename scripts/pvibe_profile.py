@@ -22,3 +22,11 @@ for k, (ms, n) in sorted(p.items(), key=lambda kv: -kv[1][0]):
     print(f"  {k:28s} {ms / N:8.3f} ms/cycle  {n / N:6.1f} launches/cycle")
     tot += ms
 print("sum kernels ms/cycle", tot / N)
+# host-side split of a cycle: Step (both stages + tagging) vs LoadBalancing/AMR + new dt
+ts, tr, nre = 0.0, 0.0, 0
+n_before = sim.info()["nbtotal"]
+for _ in range(N):
+    a = time.time(); sim.step(); sim.sync(); b = time.time(); sim.regrid(); sim.sync(); c = time.time()
+    ts += b - a; tr += c - b
+    n_now = sim.info()["nbtotal"]; nre += n_now != n_before; n_before = n_now
+print(f"step {1e3 * ts / N:.3f} ms/cycle, regrid+dt {1e3 * tr / N:.3f} ms/cycle, {nre} remeshes in {N} cycles, blocks {n_before}")
