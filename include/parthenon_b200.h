@@ -295,6 +295,11 @@ int pb2_block_derivative(const pb2_pack_geom *g, const double *u, int comp, int 
  * stage's exchange.  x, y, z may alias. */
 int pb2_weighted_sum_ghosts(const pb2_pack_geom *g, const double *x, const double *y, double w1,
                             double w2, double *z, pb2_stream_t stream);
+/* the same for a subset of the batch: block_ids = device array of num_block_ids block indices
+ * (only blocks with a coarser neighbour own ghosts that the exchange does not refresh) */
+int pb2_weighted_sum_ghosts_blocks(const pb2_pack_geom *g, const double *x, const double *y,
+                                   double w1, double w2, double *z, const int32_t *block_ids,
+                                   int32_t num_block_ids, pb2_stream_t stream);
 
 /* interior cells of a field <-> a packed buffer [block][comp][nx3][nx2][nx1] without ghosts
  * (the layout of an application's host arrays): the device side of uploading / reading back a
@@ -352,9 +357,10 @@ typedef struct pb2_burgers_args {
                          Must be initialised to +huge by the caller. */
   double beta;        /* integrator->beta[stage-1] */
   double dt;
-  /* pb2_burgers_stage (FAST) only: restrict the launch to these blocks of the batch (device
-   * array of num_block_ids indices), or NULL for all geom.nblocks blocks.  Lets a caller run
-   * the blocks that feed inter-GPU halos first and overlap their exchange with the rest. */
+  /* restrict the launch to these blocks of the batch (device array of num_block_ids indices), or
+   * NULL for all geom.nblocks blocks.  Lets a caller run the blocks that feed inter-GPU halos
+   * first and overlap their exchange with the rest, and lets a multilevel mesh keep the
+   * stored-flux path for the blocks that take part in flux correction only. */
   const int32_t *block_ids;
   int32_t num_block_ids;
 } pb2_burgers_args;

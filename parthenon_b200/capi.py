@@ -93,7 +93,7 @@ SYMBOLS = [
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
     "pb2_restrict", "pb2_prolongate", "pb2_flxcor_table_create", "pb2_flux_correct",
-    "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
+    "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_weighted_sum_ghosts_blocks", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
     "pb2_halo_copy_uniform", "pb2_advection_fluxes", "pb2_copy_flags", "pb2_copy_select",
     "pb2_weighted_sum_blocks", "pb2_flux_divergence_blocks", "pb2_advection_fluxes_blocks",
     "pb2_block_quiet_flags", "pb2_block_minmax", "pb2_block_derivative", "pb2_bc_table_create", "pb2_apply_bcs",
@@ -152,6 +152,8 @@ def lib():
     L.pb2_weighted_sum_ghosts.argtypes = [C.POINTER(PackGeom), vp, vp, C.c_double, C.c_double,
                                           vp, vp]
     L.pb2_advection_fluxes.argtypes = [C.POINTER(PackGeom), vp, C.POINTER(vp), c_double_p, vp]
+    L.pb2_weighted_sum_ghosts_blocks.argtypes = [C.POINTER(PackGeom), vp, vp, C.c_double,
+                                                 C.c_double, vp, vp, C.c_int32, vp]
     L.pb2_flux_divergence.argtypes = [C.POINTER(PackGeom), C.POINTER(vp), vp, vp]
     for f in ("pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage"):
         getattr(L, f).argtypes = [C.POINTER(BurgersArgs), vp]

@@ -188,7 +188,6 @@ int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream) {
     PB2_REQUIRE(args->out != args->u, "the fused stage cannot write its stencil input");
     return burgers_stage_sweep(args, as_stream(stream));
   }
-  PB2_REQUIRE(args && args->block_ids == nullptr, "block_ids needs PB2_MATH_FAST");
   if (int rc = pb2_burgers_calculate_fluxes(args, stream)) return rc;
   return pb2_burgers_update(args, stream);
 }

@@ -155,11 +155,12 @@ constexpr int kMaxComp = 16;
 template <int RECON, int DIR>
 __global__ void __launch_bounds__(kFluxThreads)
     flux_march_kernel(const FluxGeom g, const double *__restrict__ u,
-                      double *__restrict__ flux) {
+                      double *__restrict__ flux, const int *__restrict__ block_ids) {
   const int ncol_other = (DIR == 1) ? g.nx[2] : g.nx[1]; // k for y sweep, j for z sweep
   const int ncol = ncol_other * g.nx[0];
   const int ctas_per_block = (ncol + kFluxThreads - 1) / kFluxThreads;
-  const int b = blockIdx.x / ctas_per_block;
+  const int bi = blockIdx.x / ctas_per_block;
+  const int b = block_ids ? block_ids[bi] : bi;
   const int col = (blockIdx.x % ctas_per_block) * kFluxThreads + threadIdx.x;
   if (col >= ncol) return;
   const int i = g.is[0] + col % g.nx[0];
@@ -221,14 +222,16 @@ constexpr int kRowsPerWarp = 16;
 
 template <int RECON>
 __global__ void __launch_bounds__(kFluxThreads)
-    flux_x_kernel(const FluxGeom g, const double *__restrict__ u, double *__restrict__ flux) {
+    flux_x_kernel(const FluxGeom g, const double *__restrict__ u, double *__restrict__ flux,
+                  const int *__restrict__ block_ids) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (kFluxThreads / 32) + (threadIdx.x >> 5);
   const int nrows = g.nx[1] * g.nx[2];
   const int warps_per_block = (nrows + kRowsPerWarp - 1) / kRowsPerWarp;
-  const int b = warp_global / warps_per_block;
-  if (b >= g.nblocks) return; // whole warp exits together
+  const int bi = warp_global / warps_per_block;
+  if (bi >= g.nblocks) return; // whole warp exits together
+  const int b = block_ids ? block_ids[bi] : bi;
   const int row0 = (warp_global % warps_per_block) * kRowsPerWarp;
   const int rows = min(kRowsPerWarp, nrows - row0);
   const int ncell = g.nx[0] + 2;
@@ -299,6 +302,7 @@ struct UpdateArgs {
   const double *u, *base;
   double *out;
   const double *fx, *fy, *fz;
+  const int *block_ids;     // launch block -> block of the batch, or null (identity)
   double *derived;          // [nblocks][nk][nj][ni] or null
   unsigned long long *dtmin; // bit pattern of a positive double, or null
   const double *dx;          // [nblocks][3]
@@ -311,7 +315,8 @@ __global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateArgs a)
   const FluxGeom &g = a.g;
   const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
   const int ctas_per_block = (ncell + kUpdThreads - 1) / kUpdThreads;
-  const int b = blockIdx.x / ctas_per_block;
+  const int bi = blockIdx.x / ctas_per_block;
+  const int b = a.block_ids ? a.block_ids[bi] : bi;
   const int t = (blockIdx.x % ctas_per_block) * kUpdThreads + threadIdx.x;
   double inv = DBL_MAX;
   if (t < ncell) {
@@ -374,27 +379,30 @@ template <int RECON>
 int launch_fluxes_t(const pb2_burgers_args *args, cudaStream_t st) {
   FluxGeom g;
   make_geom(args->geom, g);
+  const int *ids = args->block_ids;
+  if (ids) g.nblocks = args->num_block_ids; // the launch covers the listed blocks only
+  if (g.nblocks == 0) return PB2_OK;
   {
     const int nrows = g.nx[1] * g.nx[2];
     const int warps = g.nblocks * ((nrows + kRowsPerWarp - 1) / kRowsPerWarp);
     const int wpc = kFluxThreads / 32;
     ProfScope prof(K_FLUX_X, st);
     flux_x_kernel<RECON><<<(warps + wpc - 1) / wpc, kFluxThreads, 0, st>>>(g, args->u,
-                                                                          args->flux[0]);
+                                                                          args->flux[0], ids);
     PB2_LAUNCH_CHECK();
   }
   if (g.ndim > 1) {
     const int ncol = g.nx[2] * g.nx[0];
     const int ctas = g.nblocks * ((ncol + kFluxThreads - 1) / kFluxThreads);
     ProfScope prof(K_FLUX_Y, st);
-    flux_march_kernel<RECON, 1><<<ctas, kFluxThreads, 0, st>>>(g, args->u, args->flux[1]);
+    flux_march_kernel<RECON, 1><<<ctas, kFluxThreads, 0, st>>>(g, args->u, args->flux[1], ids);
     PB2_LAUNCH_CHECK();
   }
   if (g.ndim > 2) {
     const int ncol = g.nx[1] * g.nx[0];
     const int ctas = g.nblocks * ((ncol + kFluxThreads - 1) / kFluxThreads);
     ProfScope prof(K_FLUX_Z, st);
-    flux_march_kernel<RECON, 2><<<ctas, kFluxThreads, 0, st>>>(g, args->u, args->flux[2]);
+    flux_march_kernel<RECON, 2><<<ctas, kFluxThreads, 0, st>>>(g, args->u, args->flux[2], ids);
     PB2_LAUNCH_CHECK();
   }
   return PB2_OK;
@@ -414,6 +422,9 @@ inline int launch_update(const pb2_burgers_args *args, cudaStream_t st) {
   a.fx = args->flux[0];
   a.fy = args->flux[1];
   a.fz = args->flux[2];
+  a.block_ids = args->block_ids;
+  if (a.block_ids) a.g.nblocks = args->num_block_ids;
+  if (a.g.nblocks == 0) return PB2_OK;
   a.derived = args->derived;
   a.dtmin = reinterpret_cast<unsigned long long *>(args->dt_min);
   a.dx = args->geom.dx;

@@ -46,7 +46,8 @@ struct DivGeom {
 // exchange and so carry these values into the next stencil.
 __global__ void __launch_bounds__(256)
     weighted_sum_ghost_kernel(const DivGeom g, const double *x, const double *y, double w1,
-                              double w2, double *z, int64_t total) {
+                              double w2, double *z, int64_t total,
+                              const int *__restrict__ block_ids) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t ncell = g.sc;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(256)
     const bool interior = i >= g.is[0] && i < g.is[0] + g.nx[0] && j >= g.is[1] &&
                           j < g.is[1] + g.nx[1] && k >= g.is[2] && k < g.is[2] + g.nx[2];
     if (interior) continue;
-    const int64_t b = bc / g.ncomp, c = bc - b * g.ncomp;
+    const int64_t bi = bc / g.ncomp, c = bc - bi * g.ncomp;
+    const int64_t b = block_ids ? block_ids[bi] : bi;
     const int64_t p = b * g.sb + c * g.sc + (e - bc * ncell);
     z[p] = w1 * x[p] + w2 * y[p];
   }
@@ -275,10 +277,16 @@ int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, dou
 
 int pb2_weighted_sum_ghosts(const pb2_pack_geom *pg, const double *x, const double *y, double w1,
                             double w2, double *z, pb2_stream_t stream) {
+  return pb2_weighted_sum_ghosts_blocks(pg, x, y, w1, w2, z, nullptr, 0, stream);
+}
+
+int pb2_weighted_sum_ghosts_blocks(const pb2_pack_geom *pg, const double *x, const double *y,
+                                   double w1, double w2, double *z, const int32_t *block_ids,
+                                   int32_t num_block_ids, pb2_stream_t stream) {
   PB2_REQUIRE(pg && x && y && z, "bad arguments");
   if (int rc = require_device()) return rc;
   DivGeom g;
-  g.nblocks = pg->nblocks;
+  g.nblocks = block_ids ? num_block_ids : pg->nblocks;
   g.ncomp = pg->ncomp;
   g.ndim = pg->ndim;
   for (int d = 0; d < 3; ++d) {
@@ -295,7 +303,8 @@ int pb2_weighted_sum_ghosts(const pb2_pack_geom *pg, const double *x, const doub
   if (total == 0) return PB2_OK;
   const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
   ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
-  weighted_sum_ghost_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, x, y, w1, w2, z, total);
+  weighted_sum_ghost_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, x, y, w1, w2, z, total,
+                                                                 block_ids);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

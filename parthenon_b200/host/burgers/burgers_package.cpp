@@ -166,15 +166,32 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   const bool split = a.math == PB2_MATH_FAST && !pm->multilevel && bc.n_boundary > 0 &&
                      bc.n_interior > 0 && bc.plan.send_elements > 0;
   if (flxcor) {
-    // CalculateFluxes -> flux correction -> FluxDivergence + update (burgers_driver.cpp:92-104)
+    // CalculateFluxes -> flux correction -> FluxDivergence + update (burgers_driver.cpp:92-104).
+    // Only blocks with a face neighbour on another level exchange flux corrections; with
+    // pb2/math = fast the others take the flux-free sweeps (same equations, <= 1e-12), with
+    // strict every block keeps the reference's dataflow.
+    BvarsCache &fc = GetBvarsCache(mc0);
+    const bool mixed = a.math == PB2_MATH_FAST && fc.n_plain > 0;
+    if (mixed) {
+      a.block_ids = fc.ids_flxcor.get<int32_t>();
+      a.num_block_ids = fc.n_flxcor;
+    }
     PB2_CHECK(pb2_burgers_calculate_fluxes(&a, mc0->stream()));
     FluxCorrection(mc0);
     PB2_CHECK(pb2_burgers_update(&a, mc0->stream()));
+    if (mixed) {
+      a.block_ids = fc.ids_plain.get<int32_t>();
+      a.num_block_ids = fc.n_plain;
+      PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+      a.block_ids = nullptr;
+    }
     // the reference's Average/UpdateIndependentData run over the full extents; ghosts that
     // the exchange below does not refresh (fine ghosts facing a coarser block: the stage list
     // has no ProlongateBounds) carry beta*mc0 + (1-beta)*base into the next stencil
-    PB2_CHECK(pb2_weighted_sum_ghosts(&a.geom, a.u, a.base, beta, 1.0 - beta, a.out,
-                                      mc0->stream()));
+    if (fc.n_stale_ghosts > 0)
+      PB2_CHECK(pb2_weighted_sum_ghosts_blocks(&a.geom, a.u, a.base, beta, 1.0 - beta, a.out,
+                                               fc.ids_stale_ghosts.get<int32_t>(),
+                                               fc.n_stale_ghosts, mc0->stream()));
   } else if (split) {
     a.block_ids = bc.ids_boundary.get<int32_t>();
     a.num_block_ids = bc.n_boundary;

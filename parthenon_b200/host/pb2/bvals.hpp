@@ -95,6 +95,12 @@ struct BvarsCache {
   // are still being advanced on the compute stream.
   DeviceBuffer ids_boundary, ids_interior;
   int n_boundary = 0, n_interior = 0;
+  // multilevel meshes: blocks with a FACE neighbour on another level take part in flux
+  // correction and need their face fluxes stored (ids_flxcor); all others (ids_plain) can run
+  // the flux-free sweeps.  Blocks with a coarser neighbour own ghosts that a stage's exchange
+  // does not refresh (ids_stale_ghosts: the ghost part of the full-extent WeightedSumData).
+  DeviceBuffer ids_flxcor, ids_plain, ids_stale_ghosts;
+  int n_flxcor = 0, n_plain = 0, n_stale_ghosts = 0;
   pb2_event_t early_ready = nullptr, unpacked = nullptr;
   bool early_valid = false, unpacked_valid = false;
   // local channels: SendBoundBufs<local> publishes a generation; receivers consume it

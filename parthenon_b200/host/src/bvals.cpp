@@ -516,6 +516,24 @@ void Rebuild(MeshData<Real> *md) {
     };
     upload(c.ids_boundary, bnd);
     upload(c.ids_interior, inr);
+    // classes for the multilevel stage
+    std::vector<int32_t> flx, plain, stale;
+    for (auto &pmb : md->GetBlockList()) {
+      bool face_other_level = false, coarser = false;
+      for (auto &nb : pmb->neighbors) {
+        const int nz = (nb.offsets[0] != 0) + (nb.offsets[1] != 0) + (nb.offsets[2] != 0);
+        if (nz == 1 && nb.loc.level != pmb->loc.level) face_other_level = true;
+        if (nb.loc.level < pmb->loc.level) coarser = true;
+      }
+      (face_other_level ? flx : plain).push_back(pmb->pack_index);
+      if (coarser) stale.push_back(pmb->pack_index);
+    }
+    c.n_flxcor = static_cast<int>(flx.size());
+    c.n_plain = static_cast<int>(plain.size());
+    c.n_stale_ghosts = static_cast<int>(stale.size());
+    upload(c.ids_flxcor, flx);
+    upload(c.ids_plain, plain);
+    upload(c.ids_stale_ghosts, stale);
   }
   if (!c.packed) {
     PB2_CHECK(pb2_event_create(&c.early_ready));
