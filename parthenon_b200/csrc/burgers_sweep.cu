@@ -62,6 +62,7 @@ struct Args {
   const double *dx;          // [nblocks][3]
   const int *block_ids;      // launch block -> block of the batch, or null (identity)
   double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
+  FastDiv dncell, dnx1;      // x sweep: division by (nx1 + 2) and by nx2 as multiply-shift
 };
 
 using fastmath::Linear;
@@ -328,9 +329,10 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_x_kernel(const
       const int f = f0 + lane;
       const bool cell = f < items;
       const int fr = cell ? f : items - 1; // inactive lanes recompute a valid cell
-      const int r = fr / ncell, c = fr - r * ncell;
+      const int r = (int)a.dncell.div((uint32_t)fr), c = fr - r * ncell;
       const int row = row0 + r;
-      const int k = g.is[2] + row / g.nx[1], j = g.is[1] + row % g.nx[1];
+      const int rk = (int)a.dnx1.div((uint32_t)row);
+      const int k = g.is[2] + rk, j = g.is[1] + (row - rk * g.nx[1]);
       const int i = g.is[0] - 1 + c;
       const int64_t off = (int64_t)k * g.sk + (int64_t)j * g.sj + i;
       const bool upd = cell && c >= 2; // this lane completes cell i-1
@@ -340,9 +342,10 @@ __global__ void __launch_bounds__(kThreads, PB2_SWEEP_MINB) sweep_x_kernel(const
       if (f0 + 32 < items) {
         // lines of the NEXT pass (32 items further along the flattened rows)
         const int f2 = min(f + 32, items - 1);
-        const int r2 = f2 / ncell, c2 = f2 - r2 * ncell, row2 = row0 + r2;
-        const int64_t off2 = (int64_t)(g.is[2] + row2 / g.nx[1]) * g.sk +
-                             (int64_t)(g.is[1] + row2 % g.nx[1]) * g.sj + (g.is[0] - 1 + c2);
+        const int r2 = (int)a.dncell.div((uint32_t)f2), c2 = f2 - r2 * ncell, row2 = row0 + r2;
+        const int rk2 = (int)a.dnx1.div((uint32_t)row2);
+        const int64_t off2 = (int64_t)(g.is[2] + rk2) * g.sk +
+                             (int64_t)(g.is[1] + (row2 - rk2 * g.nx[1])) * g.sj + (g.is[0] - 1 + c2);
         for (int n = 0; n < nc; ++n) prefetch_l1(ub + n * g.sc + off2);
         if (use_base)
           for (int n = 0; n < nc; ++n) prefetch_l1(bb + n * g.sc + off2);
@@ -478,6 +481,8 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   a.block_ids = args->block_ids;
   if (args->block_ids) g.nblocks = args->num_block_ids;
   if (g.nblocks == 0) return PB2_OK;
+  a.dncell.init(static_cast<uint32_t>(g.nx[0] + 2));
+  a.dnx1.init(static_cast<uint32_t>(g.nx[1]));
   a.beta = args->beta;
   a.w2 = 1.0 - args->beta;
   a.bdt = args->beta * args->dt;
