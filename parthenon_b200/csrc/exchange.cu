@@ -205,7 +205,13 @@ __global__ void __launch_bounds__(kThreads)
 // in units of V doubles; a thread turns its flat index into (k, j, i) with multiply-shift
 // divisions, picks the owning neighbour from the 27-entry table of its block (shared memory)
 // and copies V doubles.  All kHaloUnroll loads of a thread are issued before its stores.
-constexpr int kHaloUnroll = 8;
+#ifndef PB2_HALO_UNROLL
+#define PB2_HALO_UNROLL 16
+#endif
+#ifndef PB2_HALO_MINB
+#define PB2_HALO_MINB 2
+#endif
+constexpr int kHaloUnroll = PB2_HALO_UNROLL;
 
 struct HaloGeom {
   int32_t nblocks, ncomp, parts;
@@ -224,7 +230,7 @@ struct HaloGeom {
 };
 
 template <int V>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, PB2_HALO_MINB)
     halo_uniform_kernel(const HaloGeom g, double *__restrict__ field,
                         const int32_t *__restrict__ nbr) {
   using T = typename Vec<V>::type;

@@ -3,7 +3,7 @@
 # usage: scripts/gpu_variants.sh "<flags A>" "<flags B>" ...   ("" = the default build)
 for v in "$@"; do
   echo "== variant [$v]"
-  rm -f parthenon_b200/csrc/burgers_sweep.o
+  rm -f parthenon_b200/csrc/burgers_sweep.o parthenon_b200/csrc/exchange.o
   make -C parthenon_b200/csrc -s -j8 EXTRA="$v" > /dev/null 2>&1 || { echo build failed; continue; }
   timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
