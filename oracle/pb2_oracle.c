@@ -811,6 +811,8 @@ int64_t orc_flux_correct(const OrcMesh *m, double *const F[3], int ncomp) {
   return moved;
 }
 
+void orc_apply_bcs_coarse(const OrcMesh *m, double *Uc, int ncomp);
+
 int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int prolongate) {
   int64_t nreg = orc_count_regions(m);
   int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
@@ -820,7 +822,10 @@ int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int pro
   orc_pack(m, U, Uc, ncomp, buf, off);
   orc_unpack(m, U, Uc, ncomp, buf, off);
   orc_restrict_set(m, U, Uc, ncomp);
-  if (prolongate) orc_prolongate(m, U, Uc, ncomp);
+  if (prolongate && m->multilevel && Uc) {
+    orc_apply_bcs_coarse(m, Uc, ncomp); /* ApplyBoundaryConditionsOnCoarseOrFineMD(md, true) */
+    orc_prolongate(m, U, Uc, ncomp);
+  }
   free(buf);
   free(off);
   return total;
@@ -834,7 +839,9 @@ int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int pro
  * ghost slab of a face spans the ENTIRE extents of the other directions
  * (mesh/domain.hpp:183-251), so edges and corners outside the mesh come out right when the
  * faces are applied in order. */
-void orc_apply_bcs(const OrcMesh *m, double *U, int ncomp) {
+static void apply_bcs_generic(const OrcMesh *m, double *A, int ncomp, int coarse) {
+  const int *is = coarse ? m->cis : m->is, *ie = coarse ? m->cie : m->ie,
+            *nn = coarse ? m->cn : m->n;
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < m->nblocks; ++b) {
     const Block *blk = &m->blocks[b];
@@ -844,23 +851,32 @@ void orc_apply_bcs(const OrcMesh *m, double *U, int ncomp) {
       /* MeshBlock::boundary_flag: the mesh flag where the block touches the mesh boundary */
       const long nb_d = nblocks_at(m, blk->loc.level, d);
       if (inner ? blk->loc.lx[d] != 0 : blk->loc.lx[d] != nb_d - 1) continue;
-      const int ref = inner ? m->is[d] : m->ie[d];
+      const int ref = inner ? is[d] : ie[d];
       const int offset = 2 * ref + (inner ? -1 : 1);
-      int lo[3] = {0, 0, 0}, hi[3] = {m->n[0] - 1, m->n[1] - 1, m->n[2] - 1};
+      int lo[3] = {0, 0, 0}, hi[3] = {nn[0] - 1, nn[1] - 1, nn[2] - 1};
       if (inner)
-        hi[d] = m->is[d] - 1;
+        hi[d] = is[d] - 1;
       else
-        lo[d] = m->ie[d] + 1;
+        lo[d] = ie[d] + 1;
       for (int c = 0; c < ncomp; ++c)
         for (int k = lo[2]; k <= hi[2]; ++k)
           for (int j = lo[1]; j <= hi[1]; ++j)
             for (int i = lo[0]; i <= hi[0]; ++i) {
               int s[3] = {i, j, k};
               s[d] = m->bc[face] == 2 ? offset - s[d] : ref;
-              U[fidx(m, ncomp, b, c, k, j, i)] = U[fidx(m, ncomp, b, c, s[2], s[1], s[0])];
+              if (coarse)
+                A[cidx(m, ncomp, b, c, k, j, i)] = A[cidx(m, ncomp, b, c, s[2], s[1], s[0])];
+              else
+                A[fidx(m, ncomp, b, c, k, j, i)] = A[fidx(m, ncomp, b, c, s[2], s[1], s[0])];
             }
     }
   }
+}
+void orc_apply_bcs(const OrcMesh *m, double *U, int ncomp) { apply_bcs_generic(m, U, ncomp, 0); }
+/* the same on the coarse buffers (coarse = true, c_cellbounds): done between SetBounds and
+ * ProlongateBounds on multilevel meshes (boundary_communication.cpp:445-449, mesh.cpp:701-703) */
+void orc_apply_bcs_coarse(const OrcMesh *m, double *Uc, int ncomp) {
+  apply_bcs_generic(m, Uc, ncomp, 1);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -1410,12 +1426,14 @@ void orc_advection_stage(OrcAdvection *st, int stage) {
   weighted_sum(st->nfield, mc0, st->dUdt, 1.0, beta * st->dt, mc1);
   /* AddBoundaryExchangeTasks(update, tl, mc1, multilevel) :136: prolongates */
   orc_exchange(st->m, mc1, st->Uc, st->ncomp, st->m->multilevel);
+  orc_apply_bcs(st->m, mc1, st->ncomp); /* fbound of AddBoundaryExchangeTasks, :449 */
   if (stage == 2) st->allowed_dt = advection_estimate_timestep(st);
 }
 
 void orc_advection_init(OrcAdvection *st) {
   advection_ic(st);
   orc_exchange(st->m, st->U, st->Uc, st->ncomp, st->m->multilevel);
+  orc_apply_bcs(st->m, st->U, st->ncomp); /* mesh.cpp:705 */
   st->allowed_dt = advection_estimate_timestep(st);
   st->dt = DBL_MAX;
   if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;

@@ -131,6 +131,13 @@ run_advection advection_s16_b8_l3_gaussian 3 16 8 3 static 3 \
   Advection/profile=smooth_gaussian Advection/amp=1.0 Advection/vy=-0.7 Advection/vz=0.4
 run_advection advection_s16_b8_l3_hard_sphere 3 16 8 2 static 3 \
   "1:-0.3:0.2:-0.2:0.3:-0.3:0.1 2:-0.1:0.05:-0.05:0.12:-0.12:0.0"
+# multilevel AND non-periodic: physical boundaries are applied to the coarse buffers before the
+# prolongation and to the fine arrays after it (mesh.cpp:698-706, boundary_communication.cpp:437-449)
+run_advection advection_s16_b8_l3_bc 3 16 8 3 static 3 \
+  "1:-0.5:0.2:-0.2:0.5:-0.3:0.1 2:-0.5:-0.3:0.3:0.5:-0.12:0.0" \
+  Advection/profile=smooth_gaussian Advection/amp=1.0 Advection/vy=-0.7 Advection/vz=0.4 \
+  parthenon/mesh/ix1_bc=outflow parthenon/mesh/ox1_bc=outflow \
+  parthenon/mesh/ix2_bc=reflecting parthenon/mesh/ox2_bc=reflecting
 # ADAPTIVE meshes (configs[2] in small): refinement tagging, tree update with proper nesting,
 # refine / derefine data movement, every cycle.  The block list changes => per-cycle metadata.
 # derefine_count is lowered so that blocks are also merged within the run.

@@ -27,6 +27,9 @@ def advection_sim(name, ndim, nx_mesh, nx_block, profile, kw, extra=None):
         ov["Advection/amp"] = kw["amp"]
     for k, v in zip(("vx", "vy", "vz"), kw.get("v", (1.0, 1.0, 1.0))):
         ov[f"Advection/{k}"] = v
+    if kw.get("bcs"):
+        ov.update({"parthenon/mesh/ix1_bc": "outflow", "parthenon/mesh/ox1_bc": "outflow",
+                   "parthenon/mesh/ix2_bc": "reflecting", "parthenon/mesh/ox2_bc": "reflecting"})
     if extra:
         ov.update(extra)
     return g, host.Simulation(app="advection", overrides=ov, leaves=None if uniform else leaves)
