@@ -34,6 +34,14 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
  * neighbour lists, index boxes and slab layouts. */
 int pb2h_topology_create(pb2h_sim **sim, const char *deck, const char *overrides, int rank,
                          int nranks, const int *leaves, int nleaves);
+/* device-free AMR host logic on a topology object: apply one AmrTag per block (-1 derefine,
+ * 0 same, 1 refine) through MeshRefinement::SetRefinement's rules, update the tree
+ * (Mesh::UpdateMeshBlockTree: proper nesting, sibling-complete derefinement) and rebuild the
+ * block list.  *changed = 1 if the mesh changed. */
+int pb2h_topology_regrid(pb2h_sim *sim, const int *tags, int nblocks, int *changed);
+/* the per-block derefinement counters (MeshRefinement::deref_count_) of a topology object:
+ * set != 0 stores counts[] into the blocks, set == 0 reads them out */
+int pb2h_topology_derefine_counts(pb2h_sim *sim, int *counts, int nblocks, int set);
 int pb2h_sim_destroy(pb2h_sim *sim);
 
 /* EvolutionDriver pieces (driver.cpp:67-193): what Execute does before its loop, N cycles

@@ -119,6 +119,8 @@ def lib():
         L.orc_amr_create_burgers.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
                                              C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                              C.c_double]
+        L.orc_amr_tags.argtypes = [C.c_void_p, ip]
+        L.orc_amr_deref_counts.argtypes = [C.c_void_p, ip]
         L.orc_amr_destroy.argtypes = [C.c_void_p]
         L.orc_amr_mesh.restype = C.c_void_p
         L.orc_amr_mesh.argtypes = [C.c_void_p]
@@ -397,6 +399,18 @@ class AmrAdvection:
 
     def regrid(self):
         return bool(lib().orc_amr_regrid(self.h))
+
+    @property
+    def tags(self):
+        out = np.zeros(self.nblocks, dtype=np.int32)
+        lib().orc_amr_tags(self.h, _ip(out))
+        return out
+
+    @property
+    def deref_counts(self):
+        out = np.zeros(self.nblocks, dtype=np.int32)
+        lib().orc_amr_deref_counts(self.h, _ip(out))
+        return out
 
     def _mesh(self):
         return lib().orc_amr_mesh(self.h)

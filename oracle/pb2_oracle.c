@@ -1581,6 +1581,7 @@ struct OrcAmr {
   OrcAdvection *adv;  /* state on the current mesh */
   int *deref_count;   /* per block: MeshRefinement::deref_count_ */
   int *refine_flag;   /* per block: MeshRefinement::refine_flag_ */
+  int *last_tag;      /* per block: the raw AmrTag of the last tagging pass (for tests) */
   int profile;
   double amp, v[3], cfl;
   int ncomp;
@@ -1644,6 +1645,7 @@ struct OrcAmr *orc_amr_create(int ndim, const int nx[3], int ng, const int nrb[3
   a->adv = orc_advection_create(a->m, vec_size, profile, amp, v, cfl);
   a->deref_count = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
   a->refine_flag = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
+  a->last_tag = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
   return a;
 }
 /* benchmarks/burgers, refinement = adaptive: criterion = derivative_order_1 on U(vector_i) */
@@ -1675,9 +1677,16 @@ void orc_amr_destroy(struct OrcAmr *a) {
   orc_mesh_destroy(a->m);
   free(a->deref_count);
   free(a->refine_flag);
+  free(a->last_tag);
   free(a);
 }
 const OrcMesh *orc_amr_mesh(const struct OrcAmr *a) { return a->m; }
+void orc_amr_deref_counts(const struct OrcAmr *a, int *out) {
+  for (int b = 0; b < a->m->nblocks; ++b) out[b] = a->deref_count[b];
+}
+void orc_amr_tags(const struct OrcAmr *a, int *out) {
+  for (int b = 0; b < a->m->nblocks; ++b) out[b] = a->last_tag[b];
+}
 double *orc_amr_U(struct OrcAmr *a) { return a->app ? a->bur->U : a->adv->U; }
 double orc_amr_dt(const struct OrcAmr *a) { return a->app ? a->bur->dt : a->adv->dt; }
 double orc_amr_time(const struct OrcAmr *a) { return a->app ? a->bur->time : a->adv->time; }
@@ -1718,6 +1727,7 @@ static void amr_tag(struct OrcAmr *a, const double *U) {
     else if (mx < a->derefine_tol)
       aret = -1;
     int *flag = &a->refine_flag[b], *cnt = &a->deref_count[b];
+    a->last_tag[b] = aret;
     if (aret == 0) *flag = 0;
     if (aret >= 0) *cnt = 0;
     if (aret > 0) {
@@ -1912,9 +1922,11 @@ static int amr_remesh(struct OrcAmr *a) {
   orc_mesh_destroy(a->m);
   free(a->deref_count);
   free(a->refine_flag);
+  free(a->last_tag);
   a->m = nm;
   a->deref_count = ncount;
   a->refine_flag = nflag;
+  a->last_tag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
   /* PreCommFillDerived; CommunicateBoundaries; FillDerived  (:1000-1003) */
   orc_exchange(nm, na->U, na->Uc, nc, 1);
   orc_apply_bcs(nm, na->U, nc);

@@ -14,7 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpb200_host.so")
 
 SYMBOLS = [
-    "pb2h_last_error", "pb2h_sim_create", "pb2h_topology_create", "pb2h_sim_destroy",
+    "pb2h_last_error", "pb2h_sim_create", "pb2h_topology_create", "pb2h_topology_regrid",
+    "pb2h_topology_derefine_counts",
+    "pb2h_sim_destroy",
     "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
@@ -182,6 +184,8 @@ def lib():
                                        ip, C.c_int]
     for f in ("pb2h_sim_destroy", "pb2h_sim_pre_execute", "pb2h_sim_execute", "pb2h_sim_sync"):
         getattr(L, f).argtypes = [vp]
+    L.pb2h_topology_regrid.argtypes = [vp, ip, C.c_int, ip]
+    L.pb2h_topology_derefine_counts.argtypes = [vp, ip, C.c_int, C.c_int]
     L.pb2h_sim_cycle.argtypes = [vp, C.c_int]
     L.pb2h_sim_cycle_phase.argtypes = [vp, C.c_int]
     L.pb2h_sim_stream.restype = vp
@@ -311,6 +315,28 @@ class Topology(_Base):
         check(lib().pb2h_topology_create(C.byref(self.h), deck.encode(), _overrides(overrides),
                                          rank, nranks,
                                          la.ctypes.data_as(C.POINTER(C.c_int)) if n else None, n))
+
+    def regrid(self, tags):
+        """apply one AmrTag per block (SetRefinement rules), update the tree, rebuild the block
+        list; returns True if the mesh changed"""
+        t = np.ascontiguousarray(tags, dtype=np.int32)
+        changed = C.c_int(0)
+        check(lib().pb2h_topology_regrid(self.h, t.ctypes.data_as(C.POINTER(C.c_int)), len(t),
+                                         C.byref(changed)))
+        return bool(changed.value)
+
+    @property
+    def derefine_counts(self):
+        out = np.zeros(self.info()["nblocks"], dtype=np.int32)
+        check(lib().pb2h_topology_derefine_counts(self.h, out.ctypes.data_as(C.POINTER(C.c_int)),
+                                                  len(out), 0))
+        return out
+
+    @derefine_counts.setter
+    def derefine_counts(self, counts):
+        c = np.ascontiguousarray(counts, dtype=np.int32)
+        check(lib().pb2h_topology_derefine_counts(self.h, c.ctypes.data_as(C.POINTER(C.c_int)),
+                                                  len(c), 1))
 
 
 class Simulation(_Base):

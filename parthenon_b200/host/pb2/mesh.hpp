@@ -233,6 +233,8 @@ class Mesh {
   // the tree from the blocks' refine flags and, if it changed, move the data onto the new
   // block list (RedistributeAndRefineMeshBlocks :663-1010).  Sets `modified`.
   void LoadBalancingAndAdaptiveMeshRefinement(ParameterInput *pin, ApplicationInput *app_in);
+  // tree update + new block list from the blocks' refine flags, no field data (tests)
+  bool RegridTopologyOnly();
 
   // <parthenon/sparse> (globals.hpp:27-36, parthenon_manager.cpp:122-138)
   struct SparseConfig {
@@ -293,6 +295,8 @@ class Mesh {
   void BuildBlockList(const BlockList_t *keep);
   bool UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nnew, int &ndel);
   void RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &new_leaves);
+  void RebuildFromLeaves(const std::vector<LogicalLocation> &new_leaves,
+                         const BlockList_t &old_blocks);
   void FindNeighbors(MeshBlock &mb) const;
   bool WrapLocation(const LogicalLocation &in, LogicalLocation &out) const;
   int64_t BlocksAtLevel(int level, int d) const;

@@ -161,6 +161,36 @@ bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nn
   return true;
 }
 
+void Mesh::RebuildFromLeaves(const std::vector<LogicalLocation> &new_leaves,
+                             const BlockList_t &old_blocks) {
+  BuildTree(nullptr, new_leaves);
+  multilevel = true;
+  std::vector<double> cost(nbtotal, 1.0);
+  AssignBlocks(cost, nranks, ranklist);
+  nblist.assign(nranks, 0);
+  for (int r : ranklist) nblist[r]++;
+  nslist.assign(nranks, 0);
+  for (int r = 1; r < nranks; ++r) nslist[r] = nslist[r - 1] + nblist[r - 1];
+  BuildBlockList(&old_blocks);
+}
+
+// the host half of a remesh alone (tree update, re-partition, new block list): what
+// pb2h_topology_regrid drives in device-free tests
+bool Mesh::RegridTopologyOnly() {
+  PARTHENON_REQUIRE(nranks == 1, "topology-only regrid is a single-rank test facility");
+  int nnew = 0, ndel = 0;
+  std::vector<LogicalLocation> new_leaves;
+  if (!UpdateMeshBlockTree(new_leaves, nnew, ndel)) return false;
+  const BlockList_t old_blocks = block_list;
+  std::unordered_set<LogicalLocation, LogicalLocationHash> old(loclist.begin(), loclist.end());
+  RebuildFromLeaves(new_leaves, old_blocks);
+  for (auto &pmb : block_list) {
+    pmb->refine_flag = 0;
+    if (!old.count(pmb->loc)) pmb->deref_count = 0;
+  }
+  return true;
+}
+
 void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &new_leaves) {
   PARTHENON_REQUIRE(DefaultNumPartitions() == 1,
                     "remeshing needs one MeshData per rank (parthenon/mesh/pack_size = -1)");
@@ -184,15 +214,7 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
   AllReduceSum(old_count);
 
   // new tree, rank assignment (AssignBlocks with unit costs), block list, empty base container
-  BuildTree(nullptr, new_leaves);
-  multilevel = true;
-  std::vector<double> cost(nbtotal, 1.0);
-  AssignBlocks(cost, nranks, ranklist);
-  nblist.assign(nranks, 0);
-  for (int r : ranklist) nblist[r]++;
-  nslist.assign(nranks, 0);
-  for (int r = 1; r < nranks; ++r) nslist[r] = nslist[r - 1] + nblist[r - 1];
-  BuildBlockList(&old_blocks);
+  RebuildFromLeaves(new_leaves, old_blocks);
   for (auto &pmb : block_list) {
     auto it = old_gid.find(pmb->loc);
     pmb->refine_flag = 0;

@@ -141,6 +141,33 @@ int pb2h_topology_create(pb2h_sim **sim, const char *deck, const char *overrides
   });
 }
 
+int pb2h_topology_regrid(pb2h_sim *sim, const int *tags, int nblocks, int *changed) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && tags && changed, "null argument");
+    Mesh *pm = sim->pm();
+    PARTHENON_REQUIRE(sim->topology_only, "pb2h_topology_regrid works on topology objects");
+    PARTHENON_REQUIRE(nblocks == pm->GetNumMeshBlocksThisRank(), "one tag per block");
+    // Refinement::Tag's bookkeeping (SetRefinement: level limits, derefinement counters), then
+    // the tree update and the new block list
+    for (int b = 0; b < nblocks; ++b) pm->SetRefinement(b, static_cast<AmrTag>(tags[b]));
+    *changed = pm->RegridTopologyOnly() ? 1 : 0;
+  });
+}
+
+int pb2h_topology_derefine_counts(pb2h_sim *sim, int *counts, int nblocks, int set) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && counts, "null argument");
+    Mesh *pm = sim->pm();
+    PARTHENON_REQUIRE(nblocks == pm->GetNumMeshBlocksThisRank(), "one counter per block");
+    for (int b = 0; b < nblocks; ++b) {
+      if (set)
+        pm->block_list[b]->deref_count = counts[b];
+      else
+        counts[b] = pm->block_list[b]->deref_count;
+    }
+  });
+}
+
 int pb2h_sim_destroy(pb2h_sim *sim) {
   return Guard([&] {
     if (!sim) return;

@@ -176,3 +176,37 @@ def test_elongated_mesh_partitions_into_cubes():
     xs = sorted({(t.block(b)["xmin"][0], t.block(b)["xmax"][0]) for b in range(16)})
     assert xs[0][0] == -0.5 and xs[-1][1] == 0.5
     assert all(xs[i][1] == xs[i + 1][0] for i in range(3))
+
+
+@pytest.mark.parametrize("ndim,nb,nrb,numlevel,dc,ncyc", [(2, 8, 4, 3, 3, 40), (3, 8, 4, 3, 3, 14)])
+def test_adaptive_tree_update_follows_oracle(ndim, nb, nrb, numlevel, dc, ncyc):
+    """the host half of a remesh without a device: the raw refinement tags of the CPU oracle's
+    adaptive advection run (pinned to the reference) are fed, cycle by cycle, to the host
+    library's SetRefinement / UpdateMeshBlockTree / block-list rebuild; block lists must agree
+    after every regrid (level limits, derefinement counters that survive on kept blocks,
+    sibling-complete derefinement, proper nesting)"""
+    A = oracle.AmrAdvection(ndim, (nb,) * ndim, 2, (nrb,) * ndim, numlevel, derefine_count=dc)
+    ov = deck_overrides(ndim, (nb,) * 3, 2, (nrb,) * 3, refinement="adaptive")
+    ov.update({"parthenon/mesh/numlevel": numlevel, "parthenon/mesh/derefine_count": dc})
+
+    def same():
+        n = t.info()["nblocks"]
+        return n == A.nblocks and np.array_equal(
+            np.array([t.block(b)["loc"] for b in range(n)]), A.block_locs)
+
+    # both start from the oracle's mesh and counters after its initial refinement loop
+    A.init()
+    t = host.Topology(overrides=ov, leaves=A.block_locs)
+    t.derefine_counts = A.deref_counts
+    assert same()
+    changes = 0
+    for c in range(ncyc):
+        A.step()
+        tags = A.tags
+        ch_o = A.regrid()
+        ch_h = t.regrid(tags)
+        assert ch_o == ch_h, c
+        assert same(), c
+        assert np.array_equal(t.derefine_counts, A.deref_counts), c
+        changes += ch_o
+    assert changes > 2
