@@ -57,6 +57,12 @@ def lib():
         L.orc_restrict_set.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_prolongate.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_calc_indices_flux.argtypes = [C.c_void_p, C.c_int, C.c_int, ip, ip]
+        L.orc_te_extents.argtypes = [C.c_void_p, C.c_int, ip]
+        L.orc_calc_indices_te.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          ip, ip]
+        L.orc_te_recv_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip]
+        L.orc_exchange_te.argtypes = [C.c_void_p, dp, C.c_int, C.c_int]
+        L.orc_exchange_te.restype = C.c_int64
         L.orc_flux_correct.restype = C.c_int64
         L.orc_flux_correct.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int]
         L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
@@ -244,6 +250,29 @@ class Mesh:
 
     def apply_bcs(self, U):
         lib().orc_apply_bcs(self.h, _dp(U), U.shape[1])
+
+    # non-cell-centred fields (uniform meshes): kind 0 cell, 1 face, 2 edge, 3 node
+    def te_extents(self, kind):
+        pn = np.zeros(3, dtype=np.int32)
+        lib().orc_te_extents(self.h, kind, _ip(pn))
+        return tuple(int(x) for x in pn[::-1])  # (nk, nj, ni)
+
+    def calc_indices_te(self, b, n, kind, el, ir_type):
+        s = np.zeros(3, dtype=np.int32)
+        e = np.zeros(3, dtype=np.int32)
+        lib().orc_calc_indices_te(self.h, b, n, kind, el, ir_type, _ip(s), _ip(e))
+        return tuple(int(x) for x in s), tuple(int(x) for x in e)
+
+    def te_recv_mask(self, b, n, kind, el):
+        """[k][j][i] over (-1, 0, 1): which entries of the receive box are written"""
+        mk = np.zeros(27, dtype=np.int32)
+        lib().orc_te_recv_mask(self.h, b, n, kind, el, _ip(mk))
+        return mk.reshape(3, 3, 3)
+
+    def exchange_te(self, U, kind):
+        """U: [nblocks][elements][ncomp][nk'][nj'][ni'] (te_extents), exchanged in place"""
+        assert U.flags.c_contiguous and U.shape[3:] == self.te_extents(kind)
+        return lib().orc_exchange_te(self.h, _dp(U), U.shape[2], kind)
 
     def flux_correct(self, F):
         """F: three face-flux arrays [nblocks][ncomp][nk][nj][ni], corrected in place"""

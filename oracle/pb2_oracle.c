@@ -832,6 +832,216 @@ int64_t orc_exchange(const OrcMesh *m, double *U, double *Uc, int ncomp, int pro
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* ghost exchange of NON-CELL-CENTRED fields (face / edge / node) between blocks of the SAME
+ * level: element-aware index boxes (bnd_info.cpp:105-252 with TopologicalOffset{I,J,K},
+ * basic_types.hpp:195-203, and the element bounds of mesh/domain.hpp:183-251), one buffer
+ * section per topological element (boundary_communication.cpp:108-137), and the ownership
+ * mask of the unpack (:296-300; mesh/forest/block_ownership.cpp:42-140; utils/indexer.hpp:
+ * 163-175): an element shared by several blocks takes the value of the block that owns it —
+ * highest level first, then highest (tree, Morton) number, i.e. highest gid on one level.
+ *
+ * Array layout: [block][element][comp][k][j][i] with every non-symmetry extent one longer than
+ * the cell-centred one (metadata.cpp:383-387). */
+enum { ORC_TE_CELL = 0, ORC_TE_FACE = 1, ORC_TE_EDGE = 2, ORC_TE_NODE = 3 };
+
+int orc_te_num_elements(int kind) { return kind == ORC_TE_FACE || kind == ORC_TE_EDGE ? 3 : 1; }
+/* TopologicalOffsetI/J/K of element `el` of a field of `kind` */
+static void te_top_offset(int kind, int el, int top[3]) {
+  for (int d = 0; d < 3; ++d) {
+    if (kind == ORC_TE_CELL)
+      top[d] = 0;
+    else if (kind == ORC_TE_FACE)
+      top[d] = d == el; /* F1: I, F2: J, F3: K */
+    else if (kind == ORC_TE_EDGE)
+      top[d] = d != el; /* E1: J and K, E2: I and K, E3: I and J */
+    else
+      top[d] = 1;
+  }
+}
+void orc_te_extents(const OrcMesh *m, int kind, int pn[3]) {
+  for (int d = 0; d < 3; ++d) pn[d] = m->n[d] + (kind != ORC_TE_CELL && m->n[d] > 1 ? 1 : 0);
+}
+
+/* LogicalLocation::IsNeighborOfTE (mesh/forest/logical_location.cpp:131-158) */
+static int is_neighbor_of_te(const Loc *self, const Loc *in, const int te[3]) {
+  const int maxl = in->level > self->level ? in->level : self->level;
+  const long bs_in = 1L << (maxl - in->level), bs_this = 1L << (maxl - self->level);
+  for (int d = 0; d < 3; ++d) {
+    long low = self->lx[d] * bs_this, hi = low + bs_this - 1;
+    if (te[d] == -1) {
+      low -= 1;
+      hi = low + 1;
+    } else if (te[d] == 1) {
+      hi += 1;
+      low = hi - 1;
+    }
+    const long low_in = in->lx[d] * bs_in, hi_in = low_in + bs_in - 1;
+    if (hi < low_in || low > hi_in) return 0;
+  }
+  return 1;
+}
+
+/* DetermineOwnership (block_ownership.cpp:42-83) of leaf block g, no newly refined blocks:
+ * owns[(o1+1) + 3 (o2+1) + 9 (o3+1)].  On one tree (level, Morton number) orders leaves like
+ * (level, gid). */
+static void determine_ownership(const OrcMesh *m, int g, int owns[27]) {
+  const Block *blk = &m->blocks[g];
+  for (int o1 = -1; o1 <= 1; ++o1)
+    for (int o2 = -1; o2 <= 1; ++o2)
+      for (int o3 = -1; o3 <= 1; ++o3) {
+        int own = 1;
+        const int te[3] = {o1, o2, o3};
+        for (int n = 0; n < blk->nnb && own; ++n) {
+          const Neighbor *nb = &blk->nb[n];
+          const int less = blk->loc.level != nb->loc.level ? blk->loc.level < nb->loc.level
+                                                           : g < nb->gid;
+          if (less && is_neighbor_of_te(&blk->loc, &nb->origin_loc, te)) own = 0;
+        }
+        owns[(o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)] = own;
+      }
+}
+
+/* GetIndexRangeMaskFromOwnership (block_ownership.cpp:85-140) */
+static void index_range_mask(const int top[3], const int sender[27], const int sox[3],
+                             int mask[27]) {
+#define OWN(a, i, j, k) (a)[((i) + 1) + 3 * ((j) + 1) + 9 * ((k) + 1)]
+  for (int i = -1; i <= 1; ++i)
+    for (int j = -1; j <= 1; ++j)
+      for (int k = -1; k <= 1; ++k)
+        OWN(mask, i, j, k) = OWN(sender, top[0] ? i : 0, top[1] ? j : 0, top[2] ? k : 0);
+  if (sox[0] != 0)
+    for (int j = -1; j <= 1; ++j)
+      for (int k = -1; k <= 1; ++k) OWN(mask, -sox[0], j, k) = OWN(mask, 0, j, k);
+  if (sox[1] != 0)
+    for (int i = -1; i <= 1; ++i)
+      for (int k = -1; k <= 1; ++k) OWN(mask, i, -sox[1], k) = OWN(mask, i, 0, k);
+  if (sox[2] != 0)
+    for (int i = -1; i <= 1; ++i)
+      for (int j = -1; j <= 1; ++j) OWN(mask, i, j, -sox[2]) = OWN(mask, i, j, 0);
+}
+
+/* CalcIndices for element (kind, el), same-level neighbour, non-flux (bnd_info.cpp:205-218) */
+void orc_calc_indices_te(const OrcMesh *m, int b, int n, int kind, int el, int ir_type,
+                         int s[3], int e[3]) {
+  const Neighbor *nb = &m->blocks[b].nb[n];
+  int top[3];
+  te_top_offset(kind, el, top);
+  const int interior_offset = ir_type == IR_SEND ? m->ng : 0;
+  const int exterior_offset = ir_type == IR_RECV ? m->ng : 0;
+  for (int d = 0; d < 3; ++d) {
+    /* IndexShape::GetBounds(interior, el): domain.hpp:183-251 */
+    const int bs = m->is[d], be = m->n[d] == 1 ? 0 : m->ie[d] + top[d];
+    if (nb->off[d] == 0) {
+      s[d] = bs;
+      e[d] = be;
+    } else if (nb->off[d] > 0) {
+      s[d] = be + (-interior_offset + 1 - top[d]);
+      e[d] = be + exterior_offset;
+    } else {
+      s[d] = bs - exterior_offset;
+      e[d] = bs + (interior_offset - 1 + top[d]);
+    }
+  }
+}
+
+/* the ownership mask the receiving region (b, n) applies to element (kind, el):
+ * bnd_info.cpp:232-248 */
+void orc_te_recv_mask(const OrcMesh *m, int b, int n, int kind, int el, int mask[27]) {
+  const Neighbor *nb = &m->blocks[b].nb[n];
+  int top[3], sender[27];
+  te_top_offset(kind, el, top);
+  determine_ownership(m, nb->gid, sender);
+  const int sox[3] = {-nb->off[0], -nb->off[1], -nb->off[2]};
+  index_range_mask(top, sender, sox, mask);
+}
+
+int64_t orc_exchange_te(const OrcMesh *m, double *U, int ncomp, int kind) {
+  if (m->multilevel) {
+    fprintf(stderr, "oracle: non-cell-centred exchange is restated for uniform meshes only\n");
+    abort();
+  }
+  const int nel = orc_te_num_elements(kind);
+  int pn[3];
+  orc_te_extents(m, kind, pn);
+  const size_t blk_sz = (size_t)nel * ncomp * pn[2] * pn[1] * pn[0];
+#define TEIDX(b, el, c, k, j, i) \
+  ((size_t)(b) * blk_sz + ((((size_t)(el) * ncomp + (c)) * pn[2] + (k)) * pn[1] + (j)) * pn[0] + (i))
+  int64_t nreg = orc_count_regions(m);
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
+  int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
+  first[0] = 0;
+  for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+  int64_t total = 0, r = 0;
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int n = 0; n < m->blocks[b].nnb; ++n) {
+      off[r++] = total;
+      for (int el = 0; el < nel; ++el) {
+        int s[3], e[3];
+        orc_calc_indices_te(m, b, n, kind, el, IR_SEND, s, e);
+        total += (int64_t)ncomp * (e[2] - s[2] + 1) * (e[1] - s[1] + 1) * (e[0] - s[0] + 1);
+      }
+    }
+  off[r] = total;
+  double *buf = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
+  /* pack: every element of the send box, no mask (boundary_communication.cpp:108-137) */
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int n = 0; n < m->blocks[b].nnb; ++n) {
+      double *p = buf + off[first[b] + n];
+      for (int el = 0; el < nel; ++el) {
+        int s[3], e[3];
+        orc_calc_indices_te(m, b, n, kind, el, IR_SEND, s, e);
+        for (int c = 0; c < ncomp; ++c)
+          for (int k = s[2]; k <= e[2]; ++k)
+            for (int j = s[1]; j <= e[1]; ++j)
+              for (int i = s[0]; i <= e[0]; ++i) *p++ = U[TEIDX(b, el, c, k, j, i)];
+      }
+    }
+  /* unpack under the ownership mask (:296-300) */
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      const Block *sb = &m->blocks[nb->gid];
+      int sn = -1;
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          sn = q;
+          break;
+        }
+      if (sn < 0) abort();
+      const double *p = buf + off[first[nb->gid] + sn];
+      for (int el = 0; el < nel; ++el) {
+        int s[3], e[3], ss[3], se[3], mask[27];
+        orc_calc_indices_te(m, b, n, kind, el, IR_RECV, s, e);
+        orc_calc_indices_te(m, nb->gid, sn, kind, el, IR_SEND, ss, se);
+        for (int d = 0; d < 3; ++d)
+          if (e[d] - s[d] != se[d] - ss[d]) {
+            fprintf(stderr, "oracle: send/recv box mismatch (block %d nb %d el %d)\n", b, n, el);
+            abort();
+          }
+        orc_te_recv_mask(m, b, n, kind, el, mask);
+        for (int c = 0; c < ncomp; ++c)
+          for (int k = s[2]; k <= e[2]; ++k)
+            for (int j = s[1]; j <= e[1]; ++j)
+              for (int i = s[0]; i <= e[0]; ++i, ++p) {
+                /* SpatiallyMaskedIndexer::IsActive, indexer.hpp:163-175 */
+                const int ii = (i == e[0]) - (i == s[0]), jj = (j == e[1]) - (j == s[1]),
+                          kk = (k == e[2]) - (k == s[2]);
+                if (OWN(mask, ii, jj, kk)) U[TEIDX(b, el, c, k, j, i)] = *p;
+              }
+      }
+    }
+  }
+#undef TEIDX
+#undef OWN
+  free(buf);
+  free(off);
+  free(first);
+  return total;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* physical boundary conditions: ApplyBoundaryConditionsOnCoarseOrFine
  * (bvals/boundary_conditions.cpp:36-58) with the generic outflow / reflect functions
  * (boundary_conditions_generic.hpp:174-268) on the fine arrays of cell-centred fields

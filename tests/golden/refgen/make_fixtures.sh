@@ -42,6 +42,10 @@ if [ ! -x "$WORK/sparse_dump" ] || [ "$HERE/sparse_dump_main.cpp" -nt "$WORK/spa
      $S/sparse_advection_package.cpp $S/parthenon_app_inputs.cpp $LIBS -o "$WORK/sparse_dump"
 fi
 
+if [ ! -x "$WORK/tecomm_dump" ] || [ "$HERE/tecomm_dump_main.cpp" -nt "$WORK/tecomm_dump" ]; then
+  $CXX $FLAGS $INC "$HERE/tecomm_dump_main.cpp" $LIBS -o "$WORK/tecomm_dump"
+fi
+
 export OMP_NUM_THREADS=${OMP_NUM_THREADS:-8} OMP_PROC_BIND=false
 
 run_burgers () { # name nx nb nscal recon nlim extra...
@@ -185,6 +189,26 @@ run_sparse sparse_u64_b8_2d 64 8 12
 # larger thresholds and a short quiet count so that blocks are DEallocated within the run
 PB2_DUMP_EVERY=4 run_sparse sparse_u64_b8_2d_dealloc 64 8 60 parthenon/sparse/alloc_threshold=1e-2 \
   parthenon/sparse/dealloc_threshold=5e-3 parthenon/sparse/dealloc_count=2
+fi
+# non-cell-centred fields (face / edge / node) after the boundary exchange of Mesh::Initialize:
+# keys U_0 (face, 3 elements x 2 components), U_1 (edge, 3 x 1), U_2 (node)
+run_tecomm () { # name ndim nx nb ng
+  local name=$1 ndim=$2 nx=$3 nb=$4 ng=$5; shift 5
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  local nx3=$nx nb3=$nb; if [ "$ndim" = 2 ]; then nx3=1; nb3=1; fi
+  printf '<parthenon/job>\nproblem_id = tecomm\n<parthenon/mesh>\nrefinement = none\nnumlevel = 1\nnghost = %d\n' $ng > deck.pin
+  printf 'nx1 = %d\nx1min = -0.5\nx1max = 0.5\nix1_bc = periodic\nox1_bc = periodic\n' $nx >> deck.pin
+  printf 'nx2 = %d\nx2min = -0.5\nx2max = 0.5\nix2_bc = periodic\nox2_bc = periodic\n' $nx >> deck.pin
+  printf 'nx3 = %d\nx3min = -0.5\nx3max = 0.5\nix3_bc = periodic\nox3_bc = periodic\n' $nx3 >> deck.pin
+  printf '<parthenon/meshblock>\nnx1 = %d\nnx2 = %d\nnx3 = %d\n<parthenon/time>\ntlim = 1.0\nnlim = 0\n' $nb $nb $nb3 >> deck.pin
+  PB2_DUMP_PREFIX="$d/U" "$WORK/tecomm_dump" -i deck.pin "$@" > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
+}
+if [ -z "${SKIP_TECOMM:-}" ]; then
+run_tecomm tecomm_u16_b8_g2_3d 3 16 8 2
+run_tecomm tecomm_u16_b8_g4_3d 3 16 8 4
+run_tecomm tecomm_u16_b4_g2_3d 3 16 4 2
+run_tecomm tecomm_u32_b8_g2_2d 2 32 8 2
 fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1

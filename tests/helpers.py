@@ -174,3 +174,22 @@ def block_crcs(data):
     import zlib
     return np.array([zlib.crc32(np.ascontiguousarray(data[b]).tobytes())
                      for b in range(data.shape[0])], dtype=np.uint32)
+
+
+# non-cell-centred exchange fixtures (tests/golden/refgen/tecomm_dump_main.cpp):
+# (name, ndim, mesh cells per direction, block cells per direction, nghost)
+TECOMM = [("tecomm_u16_b8_g2_3d", 3, 16, 8, 2), ("tecomm_u16_b8_g4_3d", 3, 16, 8, 4),
+          ("tecomm_u16_b4_g2_3d", 3, 16, 4, 2), ("tecomm_u32_b8_g2_2d", 2, 32, 8, 2)]
+# (kind, fixture key, components): kind 1 face, 2 edge, 3 node
+TECOMM_FIELDS = [(1, "U_0", 2), (2, "U_1", 1), (3, "U_2", 1)]
+
+
+def tecomm_initial(nblocks, nel, ncomp, nk, nj, ni, first_gid=0):
+    """the block-dependent integer code the reference-side problem generator writes into every
+    entry (ghosts and shared elements included) before the exchange"""
+    import numpy as np
+    gid = np.arange(first_gid, first_gid + nblocks).reshape(-1, 1, 1, 1, 1, 1)
+    e = np.arange(nel).reshape(1, -1, 1, 1, 1, 1)
+    c = np.arange(ncomp).reshape(1, 1, -1, 1, 1, 1)
+    flat = np.arange(nk * nj * ni).reshape(1, 1, 1, nk, nj, ni)
+    return np.ascontiguousarray((gid + 1) * 1.0e6 + e * 1.0e5 + c * 5.0e4 + flat)
