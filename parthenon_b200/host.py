@@ -20,7 +20,8 @@ SYMBOLS = [
     "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
-    "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_field_ptr",
+    "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_plan_boxes",
+    "pb2h_sim_field_ptr",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_allocation", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
     "pb2h_sim_exchange_elements", "pb2h_sim_history", "pb2h_sim_upload_interior",
     "pb2h_sim_download_interior", "pb2h_sim_prefetch_interior", "pb2h_sim_commit_interior",
@@ -202,6 +203,8 @@ def lib():
     L.pb2h_sim_ranklist.argtypes = [vp, ip, C.c_int]
     L.pb2h_sim_plan.restype = i64
     L.pb2h_sim_plan.argtypes = [vp, C.c_int, C.c_int, C.POINTER(i64), i64, C.POINTER(i64)]
+    L.pb2h_sim_plan_boxes.restype = i64
+    L.pb2h_sim_plan_boxes.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(i64), i64]
     L.pb2h_sim_field_ptr.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp),
                                      C.POINTER(i64)]
     L.pb2h_sim_get_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
@@ -293,6 +296,18 @@ class _Base:
         p64 = C.POINTER(C.c_int64)
         lib().pb2h_sim_plan(self.h, ncomp, k, rows.ctypes.data_as(p64), n, seg.ctypes.data_as(p64))
         return rows[:n], seg
+
+    def plan_boxes(self, ncomp, tt, kind):
+        """channels (pieces) of one field of topological type tt (0 cell, 1 face, 2 edge, 3 node)
+        with their index boxes: rows[n, 18] = [sender_gid, receiver_gid, offset_index, piece,
+        comp0, ncomp, send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, 0]"""
+        k = {"local": 0, "send": 1, "recv": 2}[kind]
+        n = lib().pb2h_sim_plan_boxes(self.h, ncomp, tt, k, None, 0)
+        if n < 0:
+            check(-1)
+        rows = np.zeros((max(n, 1), 18), dtype=np.int64)
+        lib().pb2h_sim_plan_boxes(self.h, ncomp, tt, k, rows.ctypes.data_as(C.POINTER(C.c_int64)), n)
+        return rows[:n]
 
     def close(self):
         if self.h:

@@ -42,11 +42,31 @@ IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeTy
 // with a coarser neighbour gets the box in its coarse index space (bnd_info.cpp:124-125).
 IndexBox CalcIndicesFlux(const NeighborBlock &nb, const MeshBlock *pmb);
 
-// one boundary channel as the host sees it (pure topology: testable without a device)
+// CalcIndices for one topological element of a face / edge / node field, same-level neighbour
+// (bnd_info.cpp:205-218 with TopologicalOffset and the element bounds of mesh/domain.hpp)
+IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
+                       IndexRangeType ir_type);
+// GetIndexRangeMaskFromOwnership (block_ownership.cpp:85-140): which entries of a receive box
+// — first / inner / last index per direction, index (i+1) + 3 (j+1) + 9 (k+1) — the receiver
+// takes from a sender with the given block ownership; sox = offsets of the receiver seen from
+// the sender
+std::array<bool, 27> IndexRangeMask(TE el, const std::array<bool, 27> &sender_ownership,
+                                    const int sox[3]);
+// the boxes (relative to the start of a box of extents n) that a mask lets through.  The unpack
+// predicate of the reference (SpatiallyMaskedIndexer6D::IsActive, utils/indexer.hpp:163-175) is
+// resolved on the host: masked-out entries are neither read nor sent, kernels stay predicate-free.
+std::vector<IndexBox> ActivePieces(const int n[3], const std::array<bool, 27> &mask);
+
+// one boundary channel as the host sees it (pure topology: testable without a device).  A
+// channel of a face / edge / node field is split into pieces: one per topological element and
+// active sub-box of the ownership mask.
 struct Channel {
   int sender_gid, receiver_gid;
   int var;          // index into the MeshData's FillGhost variable list
   int offset_index; // sender-perspective offset index (0..26): the channel key
+  int piece = 0;    // element * 32 + sub-box number (0 for cell-centred fields)
+  int comp0 = 0;    // first slab component of the piece
+  int ncomp = 0;    // slab components it moves
   IndexBox send_box, recv_box;
   bool send_coarse; // sender reads its coarse buffer (receiver is coarser)
   bool recv_coarse; // receiver writes its coarse buffer (sender is coarser)
@@ -65,9 +85,14 @@ struct ExchangePlan {
   int npeers = 1;                 // real ranks, or virtual ranks in the test mode
   int64_t local_elements = 0, send_elements = 0, recv_elements = 0;
 };
-// vars_ncomp: components of each FillGhost variable (sizes the slabs)
+// what the plan needs to know about each FillGhost variable: tensor components per element and
+// where the values live
+struct PlanVar {
+  int ncomp = 1;
+  TopologicalType tt = TopologicalType::Cell;
+};
 ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
-                               const std::vector<int> &vars_ncomp);
+                               const std::vector<PlanVar> &vars);
 
 struct BvarsCache {
   ~BvarsCache();

@@ -50,6 +50,9 @@ struct LogicalLocation {
   std::array<int, 3> GetSameLevelOffsets(const LogicalLocation &neighbor) const;
   // logical_location.cpp:110-129
   bool IsNeighbor(const LogicalLocation &in) const;
+  // logical_location.cpp:131-158: does block `in` touch the topological element of this block
+  // at te_offset (a face, edge or node of the block; {0,0,0} is its volume)
+  bool IsNeighborOfTE(const LogicalLocation &in, const std::array<int, 3> &te_offset) const;
 };
 
 struct LogicalLocationHash {
@@ -279,6 +282,12 @@ class Mesh {
   // ProblemGenerator + first ghost exchange + FillDerived (mesh.cpp:745)
   void Initialize(bool init_problem, ParameterInput *pin, ApplicationInput *app_in);
 
+  // which of its 27 topological elements (index (o1+1) + 3 (o2+1) + 9 (o3+1)) leaf block `gid`
+  // owns: DetermineOwnership, mesh/forest/block_ownership.cpp:42-83.  Any rank can ask about any
+  // block (every rank holds the whole tree), so both sides of an inter-device channel derive the
+  // same ownership mask without a message.
+  const std::array<bool, 27> &Ownership(int gid) const;
+
   // pure topology helpers (also used by the CPU-only tests)
   static void AssignBlocks(const std::vector<double> &costlist, int nranks,
                            std::vector<int> &ranklist);
@@ -298,6 +307,8 @@ class Mesh {
   void RebuildFromLeaves(const std::vector<LogicalLocation> &new_leaves,
                          const BlockList_t &old_blocks);
   void FindNeighbors(MeshBlock &mb) const;
+  std::vector<NeighborBlock> FindNeighbors(const LogicalLocation &loc) const;
+  mutable std::unordered_map<int, std::array<bool, 27>> ownership_;
   bool WrapLocation(const LogicalLocation &in, LogicalLocation &out) const;
   int64_t BlocksAtLevel(int level, int d) const;
 };

@@ -33,7 +33,14 @@ class Variable {
   const std::string &label() const { return label_; }
   const Metadata &metadata() const { return m_; }
   bool IsSet(MetadataFlag f) const { return m_.IsSet(f); }
+  // slab components per block: topological elements x tensor components (element slowest, like
+  // the reference's 7-D arrays (el, t, u, v, k, j, i))
   int NumComponents() const { return ncomp_; }
+  // where the values live (Metadata::Cell / Face / Edge / Node) and how many topological
+  // elements each cell carries: F1..F3 / E1..E3 = 3, cell and node = 1 (metadata.cpp:376-382)
+  TopologicalType topological_type() const { return tt_; }
+  int NumElements() const { return nel_; }
+  int TensorComponents() const { return ncomp_ / nel_; }
   int GetDim(int i) const; // 1: ni, 2: nj, 3: nk, 4: ncomp (variable.hpp GetDim)
   int sparse_id() const { return sparse_id_; }
 
@@ -65,6 +72,8 @@ class Variable {
   std::string label_;
   Metadata m_;
   int sparse_id_, ncomp_, nblocks_, capacity_;
+  TopologicalType tt_ = TopologicalType::Cell;
+  int nel_ = 1;
   bool multilevel_;
   pb2_stream_t stream_;
   DeviceBuffer data_, coarse_, flux_[3];

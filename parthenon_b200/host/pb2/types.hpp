@@ -26,6 +26,31 @@ enum class DriverStatus { complete, timeout, failed };
 
 enum CoordinateDirection { NODIR = -1, X0DIR = 0, X1DIR = 1, X2DIR = 2, X3DIR = 3 };
 enum class BoundaryFlag { block = -1, undef, reflect, outflow, periodic, user };
+// where on the cell a value lives (basic_types.hpp:156-166); element % 3 is the index of the
+// element inside a face / edge field
+enum class TopologicalElement : std::size_t { CC = 0, F1 = 3, F2 = 4, F3 = 5, E1 = 6, E2 = 7, E3 = 8, NN = 9 };
+enum class TopologicalType { Cell, Face, Edge, Node };
+using TE = TopologicalElement;
+// is the element displaced by half a cell from the cell centre along I / J / K
+// (basic_types.hpp:195-203)
+constexpr int TopologicalOffset(TE el, int dir) {
+  return dir == 0   ? (el == TE::F1 || el == TE::E2 || el == TE::E3 || el == TE::NN)
+         : dir == 1 ? (el == TE::F2 || el == TE::E3 || el == TE::E1 || el == TE::NN)
+                    : (el == TE::F3 || el == TE::E2 || el == TE::E1 || el == TE::NN);
+}
+constexpr int TopologicalOffsetI(TE el) { return TopologicalOffset(el, 0); }
+constexpr int TopologicalOffsetJ(TE el) { return TopologicalOffset(el, 1); }
+constexpr int TopologicalOffsetK(TE el) { return TopologicalOffset(el, 2); }
+// the elements a field of a topological type holds, in storage order
+inline std::vector<TE> GetTopologicalElements(TopologicalType tt) {
+  switch (tt) {
+  case TopologicalType::Face: return {TE::F1, TE::F2, TE::F3};
+  case TopologicalType::Edge: return {TE::E1, TE::E2, TE::E3};
+  case TopologicalType::Node: return {TE::NN};
+  default: return {TE::CC};
+  }
+}
+
 enum class IndexDomain {
   entire,
   interior,
@@ -81,6 +106,13 @@ class IndexShape {
   IndexRange Bounds(int dir, IndexDomain d) const {
     if (d == IndexDomain::interior) return x_[dir];
     return IndexRange{0, n_[dir] - 1};
+  }
+  // bounds of the entries of topological element `el` (mesh/domain.hpp:162-251): one more
+  // entry at the upper end of every direction the element is displaced in
+  IndexRange Bounds(int dir, IndexDomain d, TE el) const {
+    IndexRange r = Bounds(dir, d);
+    if (n_[dir] > 1) r.e += TopologicalOffset(el, dir);
+    return r;
   }
   int is(IndexDomain d) const { return Bounds(0, d).s; }
   int ie(IndexDomain d) const { return Bounds(0, d).e; }

@@ -69,6 +69,106 @@ IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeTy
   return box;
 }
 
+IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
+                       IndexRangeType ir_type) {
+  PARTHENON_REQUIRE(nb.loc.level == pmb->loc.level,
+                    "non-cell-centred fields are exchanged between blocks of one level only");
+  const int ng = Globals::nghost;
+  const int interior_offset = ir_type == IndexRangeType::BoundaryInteriorSend ? ng : 0;
+  const int exterior_offset = ir_type == IndexRangeType::BoundaryExteriorRecv ? ng : 0;
+  IndexBox box;
+  for (int d = 0; d < 3; ++d) {
+    const IndexRange b = pmb->cellbounds.Bounds(d, IndexDomain::interior, el);
+    const int top = pmb->block_size.symmetry_[d] ? 0 : TopologicalOffset(el, d);
+    int &s = box.s[d], &e = box.e[d];
+    if (nb.offsets[d] == 0) {
+      s = b.s;
+      e = b.e;
+    } else if (nb.offsets[d] > 0) {
+      // a neighbour duplicates the shared elements: its boundary lies one deeper (:150-155)
+      s = b.e + (-interior_offset + 1 - top);
+      e = b.e + exterior_offset;
+    } else {
+      s = b.s - exterior_offset;
+      e = b.s + (interior_offset - 1 + top);
+    }
+  }
+  return box;
+}
+
+std::array<bool, 27> IndexRangeMask(TE el, const std::array<bool, 27> &sender,
+                                    const int sox[3]) {
+  auto at = [](int i, int j, int k) { return (i + 1) + 3 * (j + 1) + 9 * (k + 1); };
+  std::array<bool, 27> m;
+  // block ownership -> ownership of the element's entries: directions the element is not
+  // displaced in have no shared entries and follow the block's interior
+  for (int i = -1; i <= 1; ++i)
+    for (int j = -1; j <= 1; ++j)
+      for (int k = -1; k <= 1; ++k)
+        m[at(i, j, k)] = sender[at(TopologicalOffsetI(el) ? i : 0, TopologicalOffsetJ(el) ? j : 0,
+                                   TopologicalOffsetK(el) ? k : 0)];
+  // the box is a slice of the sender next to its (sox) boundary: the side of it that faces the
+  // sender's interior holds interior entries
+  if (sox[0] != 0)
+    for (int j = -1; j <= 1; ++j)
+      for (int k = -1; k <= 1; ++k) m[at(-sox[0], j, k)] = m[at(0, j, k)];
+  if (sox[1] != 0)
+    for (int i = -1; i <= 1; ++i)
+      for (int k = -1; k <= 1; ++k) m[at(i, -sox[1], k)] = m[at(i, 0, k)];
+  if (sox[2] != 0)
+    for (int i = -1; i <= 1; ++i)
+      for (int j = -1; j <= 1; ++j) m[at(i, j, -sox[2])] = m[at(i, j, 0)];
+  return m;
+}
+
+std::vector<IndexBox> ActivePieces(const int n[3], const std::array<bool, 27> &mask) {
+  // per direction: first entry (-1), inner run (0), last entry (+1); a single entry counts as
+  // inner (indexer.hpp:171-173: (i == end) - (i == start))
+  struct Seg {
+    int s, e, idx;
+  };
+  std::vector<Seg> segs[3];
+  for (int d = 0; d < 3; ++d) {
+    if (n[d] == 1) {
+      segs[d] = {{0, 0, 0}};
+    } else {
+      segs[d].push_back({0, 0, -1});
+      if (n[d] > 2) segs[d].push_back({1, n[d] - 2, 0});
+      segs[d].push_back({n[d] - 1, n[d] - 1, 1});
+    }
+  }
+  std::vector<IndexBox> out;
+  for (const Seg &k : segs[2])
+    for (const Seg &j : segs[1])
+      for (const Seg &i : segs[0]) {
+        if (!mask[(i.idx + 1) + 3 * (j.idx + 1) + 9 * (k.idx + 1)]) continue;
+        IndexBox b;
+        b.s[0] = i.s, b.e[0] = i.e, b.s[1] = j.s, b.e[1] = j.e, b.s[2] = k.s, b.e[2] = k.e;
+        out.push_back(b);
+      }
+  // glue boxes that share a whole side (fewer, longer regions); deterministic, so the sending
+  // and the receiving device arrive at the same list
+  bool merged = true;
+  while (merged) {
+    merged = false;
+    for (size_t a = 0; a < out.size() && !merged; ++a)
+      for (size_t b = 0; b < out.size() && !merged; ++b) {
+        if (a == b) continue;
+        for (int d = 0; d < 3 && !merged; ++d) {
+          const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+          if (out[a].e[d] + 1 == out[b].s[d] && out[a].s[d1] == out[b].s[d1] &&
+              out[a].e[d1] == out[b].e[d1] && out[a].s[d2] == out[b].s[d2] &&
+              out[a].e[d2] == out[b].e[d2]) {
+            out[a].e[d] = out[b].e[d];
+            out.erase(out.begin() + static_cast<std::ptrdiff_t>(b));
+            merged = true;
+          }
+        }
+      }
+  }
+  return out;
+}
+
 // bnd_info.cpp:105-252 with flux = true and el = F_dir: the box is the shared face itself
 // (:207-211), tangentially the whole face of a finer sender (coarse index space) or the half
 // (quarter in 3-D) of a coarser receiver's face that the finer neighbour abuts (:173-192)
@@ -118,18 +218,60 @@ const NeighborBlock *MatchingNeighbor(const MeshBlock *sender, int receiver_gid,
   return nullptr;
 }
 auto ChannelKey(const Channel &c) {
-  return std::make_tuple(c.sender_gid, c.receiver_gid, c.var, c.offset_index);
+  return std::make_tuple(c.sender_gid, c.receiver_gid, c.var, c.offset_index, c.piece);
+}
+IndexBox SubBox(const IndexBox &box, const IndexBox &rel) {
+  IndexBox b;
+  for (int d = 0; d < 3; ++d) {
+    b.s[d] = box.s[d] + rel.s[d];
+    b.e[d] = box.s[d] + rel.e[d];
+  }
+  return b;
 }
 } // namespace
 
 ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
-                               const std::vector<int> &vars_ncomp) {
+                               const std::vector<PlanVar> &vars) {
   ExchangePlan plan;
   const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
   PARTHENON_REQUIRE(!(V > 1 && pm->nranks > 1), "pb2/virtual_ranks needs a single real rank");
   plan.npeers = V > 1 ? V * V : pm->nranks;
-  const int nvar = static_cast<int>(vars_ncomp.size());
+  const int nvar = static_cast<int>(vars.size());
   std::vector<std::pair<int, Channel>> send, recv; // (segment, channel)
+  // a face / edge / node channel: one piece per element and active sub-box of the ownership
+  // mask of its sender; `emit` receives each piece with boxes, component range and piece id set
+  auto pieces = [&](Channel base, const NeighborBlock &nb, const MeshBlock *pmb, bool pmb_sends,
+                    const MeshBlock *local_sender, const NeighborBlock *q, auto &&emit) {
+    const PlanVar &pv = vars[base.var];
+    const std::vector<TE> els = GetTopologicalElements(pv.tt);
+    const int sender_gid = pmb_sends ? pmb->gid : nb.gid;
+    int sox[3];
+    for (int d = 0; d < 3; ++d) sox[d] = pmb_sends ? nb.offsets[d] : -nb.offsets[d];
+    for (size_t e = 0; e < els.size(); ++e) {
+      const IndexBox mine = CalcIndicesTE(nb, pmb, els[e],
+                                          pmb_sends ? IndexRangeType::BoundaryInteriorSend
+                                                    : IndexRangeType::BoundaryExteriorRecv);
+      IndexBox other = mine;
+      if (local_sender)
+        other = CalcIndicesTE(*q, local_sender, els[e], IndexRangeType::BoundaryInteriorSend);
+      int n[3];
+      for (int d = 0; d < 3; ++d) {
+        n[d] = mine.n(d);
+        PARTHENON_REQUIRE(other.n(d) == n[d], "send/receive extents of a channel differ");
+      }
+      const auto mask = IndexRangeMask(els[e], pm->Ownership(sender_gid), sox);
+      int sub = 0;
+      for (const IndexBox &rel : ActivePieces(n, mask)) {
+        Channel c = base;
+        c.piece = static_cast<int>(e) * 32 + sub++;
+        c.comp0 = static_cast<int>(e) * pv.ncomp;
+        c.ncomp = pv.ncomp;
+        c.send_box = SubBox(pmb_sends ? mine : other, rel);
+        c.recv_box = SubBox(pmb_sends ? other : mine, rel);
+        emit(c);
+      }
+    }
+  };
   for (auto &pmb : blocks) {
     const int my_vr = pm->VirtualRankOf(pmb->gid);
     for (auto &nb : pmb->neighbors) {
@@ -150,19 +292,32 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
         rc.sender_vrank = nb_vr;
         rc.receiver_vrank = my_vr;
         rc.send_box = rc.recv_box;
+        rc.ncomp = vars[v].ncomp;
+        const bool cell = vars[v].tt == TopologicalType::Cell;
         if (local) {
           const MeshBlock *sender = pm->block_list[nb.lid].get();
           const NeighborBlock *q = MatchingNeighbor(sender, pmb->gid, nb.offsets);
           PARTHENON_REQUIRE(q != nullptr, "no matching send region for a local channel");
-          rc.send_box = CalcIndices(*q, sender, IndexRangeType::BoundaryInteriorSend, false);
-          for (int d = 0; d < 3; ++d)
-            PARTHENON_REQUIRE(rc.send_box.n(d) == rc.recv_box.n(d),
-                              "send/receive extents of a channel differ");
-          plan.local_elements += rc.recv_box.size() * vars_ncomp[v];
-          plan.local.push_back(rc);
+          auto emit = [&](const Channel &c) {
+            plan.local_elements += c.recv_box.size() * c.ncomp;
+            plan.local.push_back(c);
+          };
+          if (cell) {
+            rc.send_box = CalcIndices(*q, sender, IndexRangeType::BoundaryInteriorSend, false);
+            for (int d = 0; d < 3; ++d)
+              PARTHENON_REQUIRE(rc.send_box.n(d) == rc.recv_box.n(d),
+                                "send/receive extents of a channel differ");
+            emit(rc);
+          } else {
+            pieces(rc, nb, pmb.get(), false, sender, q, emit);
+          }
         } else {
           const int seg = V > 1 ? nb_vr * V + my_vr : nb.rank;
-          recv.emplace_back(seg, rc);
+          auto emit = [&](const Channel &c) { recv.emplace_back(seg, c); };
+          if (cell)
+            emit(rc);
+          else
+            pieces(rc, nb, pmb.get(), false, nullptr, nullptr, emit);
         }
         // this block as SENDER of the channel pmb -> nb
         if (!local) {
@@ -179,8 +334,13 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
           sc.receiver_rank = nb.rank;
           sc.sender_vrank = my_vr;
           sc.receiver_vrank = nb_vr;
+          sc.ncomp = vars[v].ncomp;
           const int seg = V > 1 ? my_vr * V + nb_vr : nb.rank;
-          send.emplace_back(seg, sc);
+          auto emit = [&](const Channel &c) { send.emplace_back(seg, c); };
+          if (vars[v].tt == TopologicalType::Cell)
+            emit(sc);
+          else
+            pieces(sc, nb, pmb.get(), true, nullptr, nullptr, emit);
         }
       }
     }
@@ -198,7 +358,7 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
     for (auto &sc : chs) {
       Channel c = sc.second;
       c.slab_off = seg_size[sc.first];
-      int64_t n = c.send_box.size() * vars_ncomp[c.var];
+      int64_t n = c.send_box.size() * c.ncomp;
       n += n & 1; // keep every channel 16-byte aligned for vector access
       seg_size[sc.first] += n;
       out.push_back(c);
@@ -287,9 +447,13 @@ void Rebuild(MeshData<Real> *md) {
   c.Clear();
   Mesh *pm = md->GetMeshPointer();
   c.vars = md->GetVariablesByFlag({Metadata::FillGhost});
-  std::vector<int> ncomp;
-  for (Variable *v : c.vars) ncomp.push_back(v->NumComponents());
-  c.plan = BuildExchangePlan(pm, md->GetBlockList(), ncomp);
+  std::vector<PlanVar> pvars;
+  bool all_cell = true;
+  for (Variable *v : c.vars) {
+    pvars.push_back(PlanVar{v->TensorComponents(), v->topological_type()});
+    all_cell = all_cell && v->topological_type() == TopologicalType::Cell;
+  }
+  c.plan = BuildExchangePlan(pm, md->GetBlockList(), pvars);
   const bool slabs = c.plan.send_elements > 0 || c.plan.recv_elements > 0;
   PARTHENON_REQUIRE(!slabs || pm->DefaultNumPartitions() == 1,
                     "inter-device halos need one MeshData per rank (parthenon/mesh/pack_size=-1)");
@@ -314,23 +478,23 @@ void Rebuild(MeshData<Real> *md) {
     Variable &sv = ContainerOf(md, sb)->Get(rv.label());
     pb2_copy_region r{};
     if (ch.send_coarse) {
-      r.src = sv.coarse() + sb->pack_index * sv.cblock_stride;
+      r.src = sv.coarse() + sb->pack_index * sv.cblock_stride + ch.comp0 * sv.ccomp_stride;
       r.src_stride_j = sv.cni;
       r.src_stride_k = sv.cni * sv.cnj;
       r.src_stride_c = static_cast<int32_t>(sv.ccomp_stride);
     } else {
-      r.src = sv.data() + sb->pack_index * sv.block_stride;
+      r.src = sv.data() + sb->pack_index * sv.block_stride + ch.comp0 * sv.comp_stride;
       r.src_stride_j = sv.ni;
       r.src_stride_k = sv.ni * sv.nj;
       r.src_stride_c = static_cast<int32_t>(sv.comp_stride);
     }
     if (ch.recv_coarse) {
-      r.dst = rv.coarse() + rb->pack_index * rv.cblock_stride;
+      r.dst = rv.coarse() + rb->pack_index * rv.cblock_stride + ch.comp0 * rv.ccomp_stride;
       r.dst_stride_j = rv.cni;
       r.dst_stride_k = rv.cni * rv.cnj;
       r.dst_stride_c = static_cast<int32_t>(rv.ccomp_stride);
     } else {
-      r.dst = rv.data() + rb->pack_index * rv.block_stride;
+      r.dst = rv.data() + rb->pack_index * rv.block_stride + ch.comp0 * rv.comp_stride;
       r.dst_stride_j = rv.ni;
       r.dst_stride_k = rv.ni * rv.nj;
       r.dst_stride_c = static_cast<int32_t>(rv.comp_stride);
@@ -340,7 +504,7 @@ void Rebuild(MeshData<Real> *md) {
       r.ds[d] = ch.recv_box.s[d];
       r.n[d] = ch.recv_box.n(d);
     }
-    r.ncomp = rv.NumComponents();
+    r.ncomp = ch.ncomp;
     r.flag_slot = -1;
     r.status = PB2_REGION_ALLOCATED;
     r.threshold = 0.0;
@@ -362,7 +526,7 @@ void Rebuild(MeshData<Real> *md) {
 
   // uniform fast path: all local channels are same-level boxes between blocks of this batch
   c.uniform_halo = !pm->multilevel && pm->DefaultNumPartitions() == 1 && !c.plan.local.empty() &&
-                   !pm->table_halo;
+                   !pm->table_halo && all_cell;
   for (Variable *v : c.vars) c.uniform_halo = c.uniform_halo && !v->metadata().IsSparse();
   if (c.uniform_halo) {
     std::vector<int32_t> nbr(static_cast<size_t>(md->NumBlocks()) * 27, -1);
@@ -387,12 +551,12 @@ void Rebuild(MeshData<Real> *md) {
     const IndexBox &box = send ? ch.send_box : ch.recv_box;
     pb2_bnd_region r{};
     if (coarse) {
-      r.var = v.coarse() + pmb->pack_index * v.cblock_stride;
+      r.var = v.coarse() + pmb->pack_index * v.cblock_stride + ch.comp0 * v.ccomp_stride;
       r.stride_j = v.cni;
       r.stride_k = v.cni * v.cnj;
       r.stride_c = static_cast<int32_t>(v.ccomp_stride);
     } else {
-      r.var = v.data() + pmb->pack_index * v.block_stride;
+      r.var = v.data() + pmb->pack_index * v.block_stride + ch.comp0 * v.comp_stride;
       r.stride_j = v.ni;
       r.stride_k = v.ni * v.nj;
       r.stride_c = static_cast<int32_t>(v.comp_stride);
@@ -402,7 +566,7 @@ void Rebuild(MeshData<Real> *md) {
       r.s[d] = box.s[d];
       r.n[d] = box.n(d);
     }
-    r.ncomp = v.NumComponents();
+    r.ncomp = ch.ncomp;
     r.flag_slot = -1;
     r.status = PB2_REGION_ALLOCATED | (send ? 0u : PB2_REGION_BUF_ALLOCATED);
     r.value = send ? v.metadata().GetAllocationThreshold() : v.metadata().GetDefaultValue();
@@ -468,6 +632,9 @@ void Rebuild(MeshData<Real> *md) {
         const int d = face / 2;
         for (Variable *v : c.vars) {
           if (!v->IsAllocated(pmb->pack_index)) continue;
+          PARTHENON_REQUIRE(v->topological_type() == TopologicalType::Cell,
+                            "outflow / reflecting boundaries of non-cell-centred fields are not "
+                            "supported by this build (" + v->label() + ")");
           for (int cf = 0; cf < (pm->multilevel ? 2 : 1); ++cf) {
             const IndexShape &shape = cf ? pmb->c_cellbounds : pmb->cellbounds;
             pb2_bc_region r{};

@@ -292,7 +292,7 @@ int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t
   int64_t count = -1;
   Guard([&] {
     Mesh *pm = sim->pm();
-    const ExchangePlan plan = BuildExchangePlan(pm, pm->block_list, {ncomp});
+    const ExchangePlan plan = BuildExchangePlan(pm, pm->block_list, {PlanVar{ncomp}});
     const std::vector<Channel> &chs = kind == 0 ? plan.local : (kind == 1 ? plan.send : plan.recv);
     count = static_cast<int64_t>(chs.size());
     if (rows) {
@@ -311,6 +311,42 @@ int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t
     if (seg_off && kind != 0) {
       const auto &off = kind == 1 ? plan.send_off : plan.recv_off;
       for (size_t p = 0; p < off.size(); ++p) seg_off[p] = off[p];
+    }
+  });
+  return count;
+}
+
+// the same for a field of topological type tt (0 cell, 1 face, 2 edge, 3 node), with the index
+// boxes: rows of 18 int64 [sender_gid, receiver_gid, offset_index, piece, comp0, ncomp,
+// send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, 0]
+int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t *rows,
+                            int64_t max_rows) {
+  int64_t count = -1;
+  Guard([&] {
+    PARTHENON_REQUIRE(tt >= 0 && tt <= 3, "topological type: 0 cell, 1 face, 2 edge, 3 node");
+    Mesh *pm = sim->pm();
+    const ExchangePlan plan = BuildExchangePlan(
+        pm, pm->block_list, {PlanVar{ncomp, static_cast<TopologicalType>(tt)}});
+    const std::vector<Channel> &chs = kind == 0 ? plan.local : (kind == 1 ? plan.send : plan.recv);
+    count = static_cast<int64_t>(chs.size());
+    if (!rows) return;
+    for (int64_t i = 0; i < std::min<int64_t>(count, max_rows); ++i) {
+      const Channel &c = chs[i];
+      int64_t *r = rows + 18 * i;
+      r[0] = c.sender_gid;
+      r[1] = c.receiver_gid;
+      r[2] = c.offset_index;
+      r[3] = c.piece;
+      r[4] = c.comp0;
+      r[5] = c.ncomp;
+      for (int d = 0; d < 3; ++d) {
+        r[6 + d] = c.send_box.s[d];
+        r[9 + d] = c.recv_box.s[d];
+        r[12 + d] = c.recv_box.n(d);
+      }
+      r[15] = c.slab_off;
+      r[16] = kind == 1 ? c.receiver_rank : c.sender_rank;
+      r[17] = 0;
     }
   });
   return count;

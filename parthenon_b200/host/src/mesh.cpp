@@ -44,6 +44,26 @@ bool LogicalLocation::IsNeighbor(const LogicalLocation &in) const {
   return true;
 }
 
+bool LogicalLocation::IsNeighborOfTE(const LogicalLocation &in,
+                                     const std::array<int, 3> &te_offset) const {
+  const int max_level = std::max(in.level, level);
+  const int64_t bs_in = int64_t{1} << (max_level - in.level);
+  const int64_t bs_this = int64_t{1} << (max_level - level);
+  for (int d = 0; d < 3; ++d) {
+    int64_t low = lx[d] * bs_this, hi = low + bs_this - 1;
+    if (te_offset[d] == -1) {
+      low -= 1;
+      hi = low + 1;
+    } else if (te_offset[d] == 1) {
+      hi += 1;
+      low = hi - 1;
+    }
+    const int64_t low_in = in.lx[d] * bs_in, hi_in = low_in + bs_in - 1;
+    if (hi < low_in || low > hi_in) return false;
+  }
+  return true;
+}
+
 namespace {
 // logical_location.cpp:61-74: position in [-0.5, 0.5] built from integers so that the
 // mesh is bitwise symmetric about its centre
@@ -227,6 +247,7 @@ void Mesh::BuildTree(ParameterInput *pin, const std::vector<LogicalLocation> &le
   });
   loclist.clear();
   leaf_gid_.clear();
+  ownership_.clear();
   internal_.clear();
   current_level = maxlevel;
   multilevel = false;
@@ -245,9 +266,37 @@ void Mesh::BuildTree(ParameterInput *pin, const std::vector<LogicalLocation> &le
 
 // neighbour search on the leaf grid, tree.cpp:139-226; offsets iterate ox1 slowest like the
 // reference's 3-D indexer (indexer.hpp:117-144)
-void Mesh::FindNeighbors(MeshBlock &mb) const {
-  mb.neighbors.clear();
-  const LogicalLocation &loc = mb.loc;
+void Mesh::FindNeighbors(MeshBlock &mb) const { mb.neighbors = FindNeighbors(mb.loc); }
+
+// ownership of shared faces / edges / nodes: the block of the highest level, then of the
+// highest (tree, Morton) number — on leaves that is the highest gid of the level — owns an
+// element (block_ownership.cpp:42-83, without newly refined blocks)
+const std::array<bool, 27> &Mesh::Ownership(int gid) const {
+  auto it = ownership_.find(gid);
+  if (it != ownership_.end()) return it->second;
+  const LogicalLocation &loc = loclist[gid];
+  const std::vector<NeighborBlock> nbs = FindNeighbors(loc);
+  std::array<bool, 27> owns;
+  for (int o1 = -1; o1 <= 1; ++o1)
+    for (int o2 = -1; o2 <= 1; ++o2)
+      for (int o3 = -1; o3 <= 1; ++o3) {
+        bool own = true;
+        for (const NeighborBlock &n : nbs) {
+          const bool less = loc.level != n.loc.level ? loc.level < n.loc.level : gid < n.gid;
+          if (less && loc.IsNeighborOfTE(n.origin_loc, {o1, o2, o3})) {
+            own = false;
+            break;
+          }
+        }
+        owns[(o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)] = own;
+      }
+  return ownership_.emplace(gid, owns).first->second;
+}
+
+std::vector<NeighborBlock> Mesh::FindNeighbors(const LogicalLocation &loc) const {
+  struct {
+    std::vector<NeighborBlock> neighbors;
+  } mb;
   auto add = [&](int gid, const LogicalLocation &wrapped, const LogicalLocation &origin) {
     NeighborBlock nb;
     nb.gid = gid;
@@ -304,6 +353,7 @@ void Mesh::FindNeighbors(MeshBlock &mb) const {
           if (so[0] == o1 && so[1] == o2 && so[2] == o3) add(pl->second, pw, par);
         }
       }
+  return mb.neighbors;
 }
 
 Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, int nranks_in,

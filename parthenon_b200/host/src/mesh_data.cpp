@@ -13,11 +13,27 @@ Variable::Variable(const std::string &label, const Metadata &m, int sparse_id, i
     : label_(label), m_(m), sparse_id_(sparse_id), ncomp_(m.NumComponents()),
       nblocks_(nblocks), capacity_(std::max(capacity, nblocks)), multilevel_(multilevel),
       stream_(stream) {
-  PARTHENON_REQUIRE(m.IsSet(Metadata::Cell) || m.IsSet(Metadata::None),
-                    "only cell-centred fields are supported by this build (" + label + ")");
+  if (m.IsSet(Metadata::Face)) tt_ = TopologicalType::Face;
+  if (m.IsSet(Metadata::Edge)) tt_ = TopologicalType::Edge;
+  if (m.IsSet(Metadata::Node)) tt_ = TopologicalType::Node;
+  nel_ = (tt_ == TopologicalType::Face || tt_ == TopologicalType::Edge) ? 3 : 1;
+  ncomp_ *= nel_;
   ni = cb.ncellsi(IndexDomain::entire);
   nj = cb.ncellsj(IndexDomain::entire);
   nk = cb.ncellsk(IndexDomain::entire);
+  if (tt_ != TopologicalType::Cell) {
+    // face, edge and node arrays are one longer in every non-symmetry direction
+    // (metadata.cpp:383-387)
+    PARTHENON_REQUIRE(!(multilevel && m.IsSet(Metadata::FillGhost)),
+                      "non-cell-centred FillGhost fields need a uniform mesh in this build (" +
+                          label + ")");
+    PARTHENON_REQUIRE(!m.IsSparse() && !m.IsSet(Metadata::WithFluxes),
+                      "non-cell-centred fields cannot be sparse or carry fluxes in this build (" +
+                          label + ")");
+    ni++;
+    if (nj > 1) nj++;
+    if (nk > 1) nk++;
+  }
   cni = ccb.ncellsi(IndexDomain::entire);
   cnj = ccb.ncellsj(IndexDomain::entire);
   cnk = ccb.ncellsk(IndexDomain::entire);
