@@ -89,6 +89,10 @@ int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t 
  * [block][component][k][j][i] over this rank's blocks. */
 int pb2h_sim_field_ptr(pb2h_sim *sim, const char *container, const char *field, int which,
                        void **dev_ptr, int64_t *nreal);
+/* extents of a field's fine array: out = [blocks on this rank, slab components (topological
+ * elements x tensor components), nk, nj, ni, topological elements].  Face / edge / node fields
+ * are one entry longer than cell-centred ones in every non-symmetry direction. */
+int pb2h_sim_field_dims(pb2h_sim *sim, const char *container, const char *field, int out[6]);
 int pb2h_sim_get_field(pb2h_sim *sim, const char *container, const char *field, int which,
                        double *host, int64_t nreal);
 int pb2h_sim_set_field(pb2h_sim *sim, const char *container, const char *field, int which,

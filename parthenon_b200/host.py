@@ -21,7 +21,7 @@ SYMBOLS = [
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_plan_boxes",
-    "pb2h_sim_field_ptr",
+    "pb2h_sim_field_ptr", "pb2h_sim_field_dims",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_allocation", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
     "pb2h_sim_exchange_elements", "pb2h_sim_history", "pb2h_sim_upload_interior",
     "pb2h_sim_download_interior", "pb2h_sim_prefetch_interior", "pb2h_sim_commit_interior",
@@ -205,6 +205,7 @@ def lib():
     L.pb2h_sim_plan.argtypes = [vp, C.c_int, C.c_int, C.POINTER(i64), i64, C.POINTER(i64)]
     L.pb2h_sim_plan_boxes.restype = i64
     L.pb2h_sim_plan_boxes.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(i64), i64]
+    L.pb2h_sim_field_dims.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
     L.pb2h_sim_field_ptr.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp),
                                      C.POINTER(i64)]
     L.pb2h_sim_get_field.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i64]
@@ -413,7 +414,9 @@ class Simulation(_Base):
         if which == FIELD_COARSE:
             cell = (i["cnk"], i["cnj"], i["cni"])
         else:
-            cell = (i["nk"], i["nj"], i["ni"])
+            d = (C.c_int * 6)()
+            check(lib().pb2h_sim_field_dims(self.h, container.encode(), field.encode(), d))
+            cell = (d[2], d[3], d[4])
         ncomp = n // (i["nblocks"] * cell[0] * cell[1] * cell[2])
         return (i["nblocks"], ncomp) + cell
 

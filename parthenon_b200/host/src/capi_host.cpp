@@ -12,6 +12,7 @@
 #include "../burgers/burgers_driver.hpp"
 #include "../sparse_advection/sparse_advection_driver.hpp"
 #include "../burgers/burgers_package.hpp"
+#include "../tecomm/tecomm_app.hpp"
 #include "parthenon_b200_host.h"
 #include "pb2/parthenon.hpp"
 
@@ -93,8 +94,9 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
   return Guard([&] {
     PARTHENON_REQUIRE(sim && app && deck, "null argument");
     const std::string a(app);
-    PARTHENON_REQUIRE(a == "burgers" || a == "advection" || a == "sparse_advection",
-                      "unknown application (have: burgers, advection, sparse_advection)");
+    PARTHENON_REQUIRE(a == "burgers" || a == "advection" || a == "sparse_advection" ||
+                          a == "tecomm",
+                      "unknown application (have: burgers, advection, sparse_advection, tecomm)");
     auto s = std::make_unique<pb2h_sim>();
     if (a == "burgers") {
       s->pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
@@ -102,6 +104,9 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
     } else if (a == "advection") {
       s->pman.app_input->ProcessPackages = advection_example::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = advection_example::MeshProblemGenerator;
+    } else if (a == "tecomm") {
+      s->pman.app_input->ProcessPackages = tecomm_example::ProcessPackages;
+      s->pman.app_input->MeshProblemGenerator = tecomm_example::MeshProblemGenerator;
     } else {
       s->pman.app_input->ProcessPackages = sparse_advection_example::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = sparse_advection_example::MeshProblemGenerator;
@@ -116,10 +121,11 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
     else if (a == "advection")
       drv = std::make_unique<advection_example::AdvectionDriver>(
           s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
-    else
+    else if (a == "sparse_advection")
       drv = std::make_unique<sparse_advection_example::SparseAdvectionDriver>(
           s->pman.pinput.get(), s->pman.app_input.get(), s->pman.pmesh.get());
-    drv->quiet = true;
+    // tecomm has no time loop: fields, the exchange and the field accessors only
+    if (drv) drv->quiet = true;
     s->driver = std::move(drv);
     *sim = s.release();
   });
@@ -177,11 +183,15 @@ int pb2h_sim_destroy(pb2h_sim *sim) {
 }
 
 int pb2h_sim_pre_execute(pb2h_sim *sim) {
-  return Guard([&] { sim->driver->PreExecute(); });
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim->driver != nullptr, "this application has no time loop");
+    sim->driver->PreExecute();
+  });
 }
 
 int pb2h_sim_cycle(pb2h_sim *sim, int ncycles) {
   return Guard([&] {
+    PARTHENON_REQUIRE(sim->driver != nullptr, "this application has no time loop");
     for (int c = 0; c < ncycles; ++c)
       PARTHENON_REQUIRE(sim->driver->DoCycle() == TaskListStatus::complete,
                         "Step failed to complete all tasks.");
@@ -190,6 +200,7 @@ int pb2h_sim_cycle(pb2h_sim *sim, int ncycles) {
 
 int pb2h_sim_cycle_phase(pb2h_sim *sim, int phase) {
   return Guard([&] {
+    PARTHENON_REQUIRE(sim->driver != nullptr, "this application has no time loop");
     if (phase == 0) {
       PARTHENON_REQUIRE(sim->driver->StepAndAdvanceTime() == TaskListStatus::complete,
                         "Step failed to complete all tasks.");
@@ -204,9 +215,9 @@ int pb2h_sim_sync(pb2h_sim *sim) {
 }
 
 void *pb2h_sim_stream(pb2h_sim *sim) { return sim->pm()->stream; }
-double pb2h_sim_time(pb2h_sim *sim) { return sim->driver->tm.time; }
-double pb2h_sim_dt(pb2h_sim *sim) { return sim->driver->tm.dt; }
-int pb2h_sim_ncycle(pb2h_sim *sim) { return sim->driver->tm.ncycle; }
+double pb2h_sim_time(pb2h_sim *sim) { return sim->driver ? sim->driver->tm.time : 0.0; }
+double pb2h_sim_dt(pb2h_sim *sim) { return sim->driver ? sim->driver->tm.dt : 0.0; }
+int pb2h_sim_ncycle(pb2h_sim *sim) { return sim->driver ? sim->driver->tm.ncycle : 0; }
 int pb2h_sim_set_dt(pb2h_sim *sim, double dt) {
   sim->driver->tm.dt = dt;
   return 0;
@@ -373,6 +384,18 @@ int pb2h_sim_field_ptr(pb2h_sim *sim, const char *container, const char *field, 
       *ptr = v.flux(which);
       *nreal = v.block_stride * nb;
     }
+  });
+}
+
+int pb2h_sim_field_dims(pb2h_sim *sim, const char *container, const char *field, int out[6]) {
+  return Guard([&] {
+    Variable &v = FindVar(sim, container, field);
+    out[0] = sim->pm()->GetNumMeshBlocksThisRank();
+    out[1] = v.NumComponents();
+    out[2] = v.nk;
+    out[3] = v.nj;
+    out[4] = v.ni;
+    out[5] = v.NumElements();
   });
 }
 
@@ -584,6 +607,7 @@ double pb2h_sim_zone_cycles_per_second(pb2h_sim *sim) { return sim->driver->Zone
 
 int pb2h_sim_execute(pb2h_sim *sim) {
   return Guard([&] {
+    PARTHENON_REQUIRE(sim->driver != nullptr, "this application has no time loop");
     PARTHENON_REQUIRE(sim->driver->Execute() != DriverStatus::failed, "driver failed");
   });
 }

@@ -1,0 +1,42 @@
+// tecomm_app.cpp — see tecomm_app.hpp
+#include "tecomm_app.hpp"
+
+#include <vector>
+
+namespace tecomm_example {
+using namespace parthenon;
+
+Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &) {
+  Packages_t packages;
+  auto pkg = std::make_shared<StateDescriptor>("tecomm");
+  pkg->AddField("face", Metadata({Metadata::Face, Metadata::Independent, Metadata::FillGhost},
+                                 std::vector<int>{2}));
+  pkg->AddField("edge", Metadata({Metadata::Edge, Metadata::Independent, Metadata::FillGhost}));
+  pkg->AddField("node", Metadata({Metadata::Node, Metadata::Independent, Metadata::FillGhost}));
+  packages.Add(pkg);
+  return packages;
+}
+
+// value = (gid + 1) * 1e6 + element * 1e5 + component * 5e4 + flat (k, j, i) index, in every
+// entry of every array (ghosts and shared elements included)
+void MeshProblemGenerator(MeshData<Real> *md, ParameterInput *) {
+  const int nb = md->NumBlocks();
+  for (const char *name : {"face", "edge", "node"}) {
+    Variable &v = md->Get(name);
+    const int nc = v.TensorComponents();
+    std::vector<Real> h(static_cast<size_t>(nb) * v.block_stride);
+    for (int b = 0; b < nb; ++b) {
+      const int gid = md->GetBlock(b)->gid;
+      Real *vb = h.data() + static_cast<size_t>(b) * v.block_stride;
+      for (int e = 0; e < v.NumElements(); ++e)
+        for (int c = 0; c < nc; ++c)
+          for (int64_t n = 0; n < v.comp_stride; ++n)
+            vb[(e * nc + c) * v.comp_stride + n] =
+                (gid + 1) * 1.0e6 + e * 1.0e5 + c * 5.0e4 + static_cast<Real>(n);
+    }
+    PB2_CHECK(pb2_memcpy_h2d(v.data(), h.data(), sizeof(Real) * h.size(), md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+  }
+}
+
+} // namespace tecomm_example
