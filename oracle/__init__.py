@@ -63,6 +63,8 @@ def lib():
         L.orc_te_recv_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip]
         L.orc_exchange_te.argtypes = [C.c_void_p, dp, C.c_int, C.c_int]
         L.orc_exchange_te.restype = C.c_int64
+        L.orc_exchange_te_ml.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
+        L.orc_exchange_te_ml.restype = C.c_int64
         L.orc_flux_correct.restype = C.c_int64
         L.orc_flux_correct.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int]
         L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
@@ -270,9 +272,14 @@ class Mesh:
         return mk.reshape(3, 3, 3)
 
     def exchange_te(self, U, kind):
-        """U: [nblocks][elements][ncomp][nk'][nj'][ni'] (te_extents), exchanged in place"""
+        """U: [nblocks][elements][ncomp][nk'][nj'][ni'] (te_extents), exchanged in place;
+        multilevel meshes get scratch coarse buffers (restriction / prolongation included)"""
         assert U.flags.c_contiguous and U.shape[3:] == self.te_extents(kind)
-        return lib().orc_exchange_te(self.h, _dp(U), U.shape[2], kind)
+        if not self.multilevel:
+            return lib().orc_exchange_te(self.h, _dp(U), U.shape[2], kind)
+        cd = tuple(n + (1 if (kind != 0 and n > 1) else 0) for n in self.cdims)
+        Uc = np.zeros(U.shape[:3] + cd)
+        return lib().orc_exchange_te_ml(self.h, _dp(U), _dp(Uc), U.shape[2], kind)
 
     def flux_correct(self, F):
         """F: three face-flux arrays [nblocks][ncomp][nk][nj][ni], corrected in place"""

@@ -902,9 +902,9 @@ static void determine_ownership(const OrcMesh *m, int g, int owns[27]) {
 }
 
 /* GetIndexRangeMaskFromOwnership (block_ownership.cpp:85-140) */
+#define OWN(a, i, j, k) (a)[((i) + 1) + 3 * ((j) + 1) + 9 * ((k) + 1)]
 static void index_range_mask(const int top[3], const int sender[27], const int sox[3],
                              int mask[27]) {
-#define OWN(a, i, j, k) (a)[((i) + 1) + 3 * ((j) + 1) + 9 * ((k) + 1)]
   for (int i = -1; i <= 1; ++i)
     for (int j = -1; j <= 1; ++j)
       for (int k = -1; k <= 1; ++k)
@@ -955,48 +955,298 @@ void orc_te_recv_mask(const OrcMesh *m, int b, int n, int kind, int el, int mask
   index_range_mask(top, sender, sox, mask);
 }
 
-int64_t orc_exchange_te(const OrcMesh *m, double *U, int ncomp, int kind) {
-  if (m->multilevel) {
-    fprintf(stderr, "oracle: non-cell-centred exchange is restated for uniform meshes only\n");
+/* ---- multilevel: the general CalcIndices for one element (bnd_info.cpp:105-252), the
+ * element forms of RestrictAverage (pr_ops.hpp:105-165), ProlongateSharedMinMod (:167-280)
+ * and ProlongateInternalAverage (:291-382), applied in the order of SendBoundBufs (restrict
+ * send regions, pack), SetBounds (masked unpack, restrict set regions) and ProlongateBounds
+ * (shared, then internal; boundary_communication.cpp:361-393) ---- */
+typedef struct {
+  int s[3], e[3];
+  int mask[27];
+} TeBox;
+static inline int te_active(const TeBox *bx, int k, int j, int i) {
+  const int ii = (i == bx->e[0]) - (i == bx->s[0]), jj = (j == bx->e[1]) - (j == bx->s[1]),
+            kk = (k == bx->e[2]) - (k == bx->s[2]);
+  return OWN(bx->mask, ii, jj, kk);
+}
+
+/* el is a TopologicalElement in its own right here (kind, el): the box of a cell / face /
+ * edge / node element whatever the field holds (ProResInfo carries all ten, bnd_info.cpp:
+ * 440-446) */
+static void calc_indices_te_general(const OrcMesh *m, int b, int n, int kind, int el,
+                                    int ir_type, int prores, TeBox *out) {
+  const Block *blk = &m->blocks[b];
+  const Neighbor *nb = &blk->nb[n];
+  const Loc *loc = &blk->loc;
+  const int ng = m->ng;
+  int top[3];
+  te_top_offset(kind, el, top);
+  const int use_coarse = prores || nb->loc.level < loc->level;
+  const int coarse_fac = nb->loc.level > loc->level ? 2 : 1;
+  const int interior_offset = ir_type == IR_SEND ? ng : 0;
+  int exterior_offset = ir_type == IR_RECV ? ng : 0;
+  if (prores) exterior_offset /= 2;
+  for (int d = 0; d < 3; ++d) {
+    const int sym = d >= m->ndim;
+    const int bs = use_coarse ? m->cis[d] : m->is[d];
+    const int be = sym ? 0 : (use_coarse ? m->cie[d] : m->ie[d]) + top[d];
+    const int nbs = sym ? 0 : ng, nbe = sym ? 0 : ng + m->nx[d] / coarse_fac - 1 + top[d];
+    int *s = &out->s[d], *e = &out->e[d];
+    if (nb->off[d] == 0) {
+      *s = bs;
+      *e = be;
+      if (loc->level < nb->origin_loc.level && !sym) {
+        const int extra = (be - bs + 1) - (nbe - nbs + 1);
+        const int odd = (int)((nb->origin_loc.lx[d] % 2 + 2) % 2);
+        *s += odd == 1 ? extra - interior_offset : 0;
+        *e -= odd == 0 ? extra - interior_offset : 0;
+      }
+      if (loc->level > nb->origin_loc.level && !sym) {
+        *s -= loc->lx[d] % 2 == 1 ? exterior_offset : 0;
+        *e += loc->lx[d] % 2 == 0 ? exterior_offset : 0;
+      }
+    } else if (nb->off[d] > 0) {
+      *s = be + (-interior_offset + 1 - top[d]);
+      *e = be + exterior_offset;
+    } else {
+      *s = bs - exterior_offset;
+      *e = bs + (interior_offset - 1 + top[d]);
+    }
+  }
+  for (int q = 0; q < 27; ++q) out->mask[q] = 1;
+  if (ir_type == IR_RECV) { /* :232-248 */
+    int sox[3] = {-nb->off[0], -nb->off[1], -nb->off[2]}, sender[27];
+    if (nb->origin_loc.level < loc->level)
+      for (int d = 0; d < 3; ++d)
+        if (sox[d] == 0) sox[d] = loc->lx[d] % 2 == 1 ? 1 : -1;
+    determine_ownership(m, nb->gid, sender);
+    index_range_mask(top, sender, sox, out->mask);
+  }
+}
+
+typedef struct {
+  const OrcMesh *m;
+  double *U, *Uc;
+  int ncomp, nel, pn[3], cpn[3];
+  size_t blk_sz, cblk_sz;
+} TeField;
+static inline double *te_f(const TeField *f, int b, int el, int c, int k, int j, int i) {
+  return f->U + (size_t)b * f->blk_sz +
+         ((((size_t)el * f->ncomp + c) * f->pn[2] + k) * f->pn[1] + j) * f->pn[0] + i;
+}
+static inline double *te_c(const TeField *f, int b, int el, int c, int k, int j, int i) {
+  return f->Uc + (size_t)b * f->cblk_sz +
+         ((((size_t)el * f->ncomp + c) * f->cpn[2] + k) * f->cpn[1] + j) * f->cpn[0] + i;
+}
+
+/* RestrictAverage::Do for element (kind, el): averages over the directions the element is
+ * centred in (INCLUDE_Xd), weights = Volume<el> of uniform_cartesian.hpp:247-270 */
+static void te_restrict(const TeField *f, int kind, int b, int el, int c, int ck, int cj,
+                        int ci) {
+  const OrcMesh *m = f->m;
+  const Block *blk = &m->blocks[b];
+  const int DIM = m->ndim;
+  int top[3];
+  te_top_offset(kind, el, top);
+  const int inc[3] = {DIM > 0 && !top[0], DIM > 1 && !top[1], DIM > 2 && !top[2]};
+  const int i = (ci - m->cis[0]) * 2 + m->is[0];
+  const int j = DIM > 1 ? (cj - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int k = DIM > 2 ? (ck - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  const double *dx = blk->dx;
+  double v;
+  if (kind == ORC_TE_CELL)
+    v = dx[0] * dx[1] * dx[2];
+  else if (kind == ORC_TE_FACE)
+    v = el == 0 ? dx[1] * dx[2] : (el == 1 ? dx[0] * dx[2] : dx[0] * dx[1]);
+  else if (kind == ORC_TE_EDGE)
+    v = dx[el];
+  else
+    v = 1.0;
+  double vol[2][2][2], terms[2][2][2];
+  memset(vol, 0, sizeof(vol));
+  memset(terms, 0, sizeof(terms));
+  for (int ok = 0; ok < 1 + inc[2]; ++ok)
+    for (int oj = 0; oj < 1 + inc[1]; ++oj)
+      for (int oi = 0; oi < 1 + inc[0]; ++oi) {
+        vol[ok][oj][oi] = v;
+        terms[ok][oj][oi] = vol[ok][oj][oi] * *te_f(f, b, el, c, k + ok, j + oj, i + oi);
+      }
+  const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                      ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+  *te_c(f, b, el, c, ck, cj, ci) =
+      (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+       ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+      tvol;
+}
+
+/* ProlongateSharedGeneral<true,false>::Do for element (kind, el): the fine elements that
+ * coincide with coarse element (k, j, i); slopes only in the directions the element is
+ * centred in (where GetGridSpacings uses cell-centre positions) */
+static void te_prolongate_shared(const TeField *f, int kind, int b, int el, int c, int k, int j,
+                                 int i) {
+  const OrcMesh *m = f->m;
+  const Block *blk = &m->blocks[b];
+  const int DIM = m->ndim;
+  int top[3];
+  te_top_offset(kind, el, top);
+  const int inc[3] = {DIM > 0 && !top[0], DIM > 1 && !top[1], DIM > 2 && !top[2]};
+  const int fi = (i - m->cis[0]) * 2 + m->is[0];
+  const int fj = DIM > 1 ? (j - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int fk = DIM > 2 ? (k - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  const double fc = *te_c(f, b, el, c, k, j, i);
+  double g[3] = {0, 0, 0}, dxfm[3] = {0, 0, 0}, dxfp[3] = {0, 0, 0};
+  const int cc[3] = {i, j, k}, ff[3] = {fi, fj, fk};
+  for (int d = 0; d < 3; ++d) {
+    if (!inc[d]) continue;
+    const double xm = blk->ccxmin[d] + ((cc[d] - 1) + 0.5) * blk->cdx[d];
+    const double xc = blk->ccxmin[d] + (cc[d] + 0.5) * blk->cdx[d];
+    const double xp = blk->ccxmin[d] + ((cc[d] + 1) + 0.5) * blk->cdx[d];
+    const double dxm = xc - xm, dxp = xp - xc;
+    const double fxm = blk->cxmin[d] + (ff[d] + 0.5) * blk->dx[d];
+    const double fxp = blk->cxmin[d] + ((ff[d] + 1) + 0.5) * blk->dx[d];
+    dxfm[d] = xc - fxm;
+    dxfp[d] = fxp - xc;
+    int o[3] = {0, 0, 0};
+    o[d] = 1;
+    const double fm = *te_c(f, b, el, c, k - o[2], j - o[1], i - o[0]);
+    const double fp = *te_c(f, b, el, c, k + o[2], j + o[1], i + o[0]);
+    g[d] = grad_minmod(fc, fm, fp, dxm, dxp);
+  }
+  const double gx1m = g[0], gx1p = g[0], gx2m = g[1], gx2p = g[1], gx3m = g[2], gx3p = g[2];
+  const double dx1fm = dxfm[0], dx1fp = dxfp[0], dx2fm = dxfm[1], dx2fp = dxfp[1],
+               dx3fm = dxfm[2], dx3fp = dxfp[2];
+  *te_f(f, b, el, c, fk, fj, fi) = fc - (gx1m * dx1fm + gx2m * dx2fm + gx3m * dx3fm);
+  if (inc[0])
+    *te_f(f, b, el, c, fk, fj, fi + 1) = fc + (gx1p * dx1fp - gx2m * dx2fm - gx3m * dx3fm);
+  if (inc[1])
+    *te_f(f, b, el, c, fk, fj + 1, fi) = fc - (gx1m * dx1fm - gx2p * dx2fp + gx3m * dx3fm);
+  if (inc[1] && inc[0])
+    *te_f(f, b, el, c, fk, fj + 1, fi + 1) = fc + (gx1p * dx1fp + gx2p * dx2fp - gx3m * dx3fm);
+  if (inc[2])
+    *te_f(f, b, el, c, fk + 1, fj, fi) = fc - (gx1m * dx1fm + gx2m * dx2fm - gx3p * dx3fp);
+  if (inc[2] && inc[0])
+    *te_f(f, b, el, c, fk + 1, fj, fi + 1) = fc + (gx1p * dx1fp - gx2m * dx2fm + gx3p * dx3fp);
+  if (inc[2] && inc[1])
+    *te_f(f, b, el, c, fk + 1, fj + 1, fi) = fc - (gx1m * dx1fm - gx2p * dx2fp - gx3p * dx3fp);
+  if (inc[2] && inc[1] && inc[0])
+    *te_f(f, b, el, c, fk + 1, fj + 1, fi + 1) =
+        fc + (gx1p * dx1fp + gx2p * dx2fp + gx3p * dx3fp);
+}
+
+/* IsSubmanifold(containee, container), basic_types.hpp:207-232, on (kind, el) pairs: an
+ * element is a boundary of another iff it is displaced in every direction the container is
+ * and in at least one more */
+static int te_is_submanifold(const int ftop[3], const int ctop[3]) {
+  int more = 0;
+  for (int d = 0; d < 3; ++d) {
+    if (ctop[d] && !ftop[d]) return 0;
+    more += ftop[d] && !ctop[d];
+  }
+  return more > 0;
+}
+
+/* ProlongateInternalAverage::Do<DIM, fel, cel>: fine elements of the field (ftop) strictly
+ * inside coarse element cel (ctop) at coarse position (k, j, i) = the average of the fine
+ * shared elements around them */
+static void te_prolongate_internal(const TeField *f, const int ftop[3], const int ctop[3], int b,
+                                   int el, int c, int k, int j, int i) {
+  const OrcMesh *m = f->m;
+  const int DIM = m->ndim;
+  const int fi = (i - m->cis[0]) * 2 + m->is[0];
+  const int fj = DIM > 1 ? (j - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int fk = DIM > 2 ? (k - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  int center[3], stencil[3];
+  for (int d = 0; d < 3; ++d) {
+    center[d] = d < DIM && !ftop[d];
+    stencil[d] = d < DIM && !center[d] && !ctop[d];
+  }
+  const double w = 1.0 / ((1.0 + stencil[2]) * (1.0 + stencil[1]) * (1.0 + stencil[0]));
+  for (int ok = 0; ok < 1 + center[2]; ++ok)
+    for (int oj = 0; oj < 1 + center[1]; ++oj)
+      for (int oi = 0; oi < 1 + center[0]; ++oi) {
+        const int tk = fk + ok + stencil[2], tj = fj + oj + stencil[1],
+                  ti = fi + oi + stencil[0];
+        double v = 0.0;
+        for (int stk = -stencil[2]; stk <= stencil[2]; stk += 2)
+          for (int stj = -stencil[1]; stj <= stencil[1]; stj += 2)
+            for (int sti = -stencil[0]; sti <= stencil[0]; sti += 2)
+              v += w * *te_f(f, b, el, c, tk + stk, tj + stj, ti + sti);
+        *te_f(f, b, el, c, tk, tj, ti) = v;
+      }
+}
+
+/* kinds and in-kind element numbers of the ten TopologicalElements in the order the internal
+ * prolongation visits the containers: NN, E3, E2, E1, F1, F2, F3, CC (pr_loops.hpp:82-108) */
+static const int kCelKind[8] = {ORC_TE_NODE, ORC_TE_EDGE, ORC_TE_EDGE, ORC_TE_EDGE,
+                                ORC_TE_FACE, ORC_TE_FACE, ORC_TE_FACE, ORC_TE_CELL};
+static const int kCelEl[8] = {0, 2, 1, 0, 0, 1, 2, 0};
+
+int64_t orc_exchange_te_ml(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind) {
+  TeField F;
+  F.m = m;
+  F.U = U;
+  F.Uc = Uc;
+  F.ncomp = ncomp;
+  F.nel = orc_te_num_elements(kind);
+  orc_te_extents(m, kind, F.pn);
+  for (int d = 0; d < 3; ++d) F.cpn[d] = m->cn[d] + (kind != ORC_TE_CELL && m->cn[d] > 1 ? 1 : 0);
+  F.blk_sz = (size_t)F.nel * ncomp * F.pn[2] * F.pn[1] * F.pn[0];
+  F.cblk_sz = (size_t)F.nel * ncomp * F.cpn[2] * F.cpn[1] * F.cpn[0];
+  const int nel = F.nel;
+  if (m->multilevel && !Uc) {
+    fprintf(stderr, "oracle: multilevel exchange needs coarse buffers\n");
     abort();
   }
-  const int nel = orc_te_num_elements(kind);
-  int pn[3];
-  orc_te_extents(m, kind, pn);
-  const size_t blk_sz = (size_t)nel * ncomp * pn[2] * pn[1] * pn[0];
-#define TEIDX(b, el, c, k, j, i) \
-  ((size_t)(b) * blk_sz + ((((size_t)(el) * ncomp + (c)) * pn[2] + (k)) * pn[1] + (j)) * pn[0] + (i))
   int64_t nreg = orc_count_regions(m);
   int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
   int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
   first[0] = 0;
   for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+  TeBox bx;
+  /* SendBoundBufs: restriction of the send regions that face a coarser block (:82-87) */
+  if (m->multilevel)
+    for (int b = 0; b < m->nblocks; ++b) {
+      const Block *blk = &m->blocks[b];
+      for (int n = 0; n < blk->nnb; ++n) {
+        if (!(blk->nb[n].origin_loc.level < blk->loc.level)) continue;
+        for (int el = 0; el < nel; ++el) {
+          calc_indices_te_general(m, b, n, kind, el, IR_SEND, 1, &bx);
+          for (int c = 0; c < ncomp; ++c)
+            for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+              for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+                for (int i = bx.s[0]; i <= bx.e[0]; ++i) te_restrict(&F, kind, b, el, c, k, j, i);
+        }
+      }
+    }
+  /* pack */
   int64_t total = 0, r = 0;
   for (int b = 0; b < m->nblocks; ++b)
     for (int n = 0; n < m->blocks[b].nnb; ++n) {
       off[r++] = total;
       for (int el = 0; el < nel; ++el) {
-        int s[3], e[3];
-        orc_calc_indices_te(m, b, n, kind, el, IR_SEND, s, e);
-        total += (int64_t)ncomp * (e[2] - s[2] + 1) * (e[1] - s[1] + 1) * (e[0] - s[0] + 1);
+        calc_indices_te_general(m, b, n, kind, el, IR_SEND, 0, &bx);
+        total += (int64_t)ncomp * (bx.e[2] - bx.s[2] + 1) * (bx.e[1] - bx.s[1] + 1) *
+                 (bx.e[0] - bx.s[0] + 1);
       }
     }
   off[r] = total;
   double *buf = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
-  /* pack: every element of the send box, no mask (boundary_communication.cpp:108-137) */
-  for (int b = 0; b < m->nblocks; ++b)
-    for (int n = 0; n < m->blocks[b].nnb; ++n) {
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
       double *p = buf + off[first[b] + n];
+      const int coarse = blk->nb[n].origin_loc.level < blk->loc.level;
       for (int el = 0; el < nel; ++el) {
-        int s[3], e[3];
-        orc_calc_indices_te(m, b, n, kind, el, IR_SEND, s, e);
+        calc_indices_te_general(m, b, n, kind, el, IR_SEND, 0, &bx);
         for (int c = 0; c < ncomp; ++c)
-          for (int k = s[2]; k <= e[2]; ++k)
-            for (int j = s[1]; j <= e[1]; ++j)
-              for (int i = s[0]; i <= e[0]; ++i) *p++ = U[TEIDX(b, el, c, k, j, i)];
+          for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+            for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+              for (int i = bx.s[0]; i <= bx.e[0]; ++i)
+                *p++ = coarse ? *te_c(&F, b, el, c, k, j, i) : *te_f(&F, b, el, c, k, j, i);
       }
     }
-  /* unpack under the ownership mask (:296-300) */
+  }
+  /* SetBounds: unpack under the ownership mask (:296-300) */
   for (int b = 0; b < m->nblocks; ++b) {
     const Block *blk = &m->blocks[b];
     for (int n = 0; n < blk->nnb; ++n) {
@@ -1011,34 +1261,104 @@ int64_t orc_exchange_te(const OrcMesh *m, double *U, int ncomp, int kind) {
         }
       if (sn < 0) abort();
       const double *p = buf + off[first[nb->gid] + sn];
+      const int coarse = nb->origin_loc.level < blk->loc.level;
       for (int el = 0; el < nel; ++el) {
-        int s[3], e[3], ss[3], se[3], mask[27];
-        orc_calc_indices_te(m, b, n, kind, el, IR_RECV, s, e);
-        orc_calc_indices_te(m, nb->gid, sn, kind, el, IR_SEND, ss, se);
+        TeBox sx;
+        calc_indices_te_general(m, b, n, kind, el, IR_RECV, 0, &bx);
+        calc_indices_te_general(m, nb->gid, sn, kind, el, IR_SEND, 0, &sx);
         for (int d = 0; d < 3; ++d)
-          if (e[d] - s[d] != se[d] - ss[d]) {
-            fprintf(stderr, "oracle: send/recv box mismatch (block %d nb %d el %d)\n", b, n, el);
+          if (bx.e[d] - bx.s[d] != sx.e[d] - sx.s[d]) {
+            fprintf(stderr, "oracle: send/recv box mismatch (block %d nb %d el %d dir %d)\n", b,
+                    n, el, d);
             abort();
           }
-        orc_te_recv_mask(m, b, n, kind, el, mask);
         for (int c = 0; c < ncomp; ++c)
-          for (int k = s[2]; k <= e[2]; ++k)
-            for (int j = s[1]; j <= e[1]; ++j)
-              for (int i = s[0]; i <= e[0]; ++i, ++p) {
-                /* SpatiallyMaskedIndexer::IsActive, indexer.hpp:163-175 */
-                const int ii = (i == e[0]) - (i == s[0]), jj = (j == e[1]) - (j == s[1]),
-                          kk = (k == e[2]) - (k == s[2]);
-                if (OWN(mask, ii, jj, kk)) U[TEIDX(b, el, c, k, j, i)] = *p;
-              }
+          for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+            for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+              for (int i = bx.s[0]; i <= bx.e[0]; ++i, ++p)
+                if (te_active(&bx, k, j, i)) {
+                  if (coarse)
+                    *te_c(&F, b, el, c, k, j, i) = *p;
+                  else
+                    *te_f(&F, b, el, c, k, j, i) = *p;
+                }
       }
     }
   }
-#undef TEIDX
-#undef OWN
+  if (m->multilevel) {
+    /* restriction of the received regions of blocks that have a coarser neighbour
+     * (ProResInfo::GetSet, bnd_info.cpp:405-431; SetBounds :338-346) */
+    for (int b = 0; b < m->nblocks; ++b) {
+      const Block *blk = &m->blocks[b];
+      int restricted = 0;
+      if (blk->loc.level > 0)
+        for (int n = 0; n < blk->nnb; ++n)
+          restricted = restricted || (blk->nb[n].origin_loc.level == blk->loc.level - 1);
+      if (!restricted) continue;
+      for (int n = 0; n < blk->nnb; ++n) {
+        if (blk->nb[n].origin_loc.level < blk->loc.level) continue;
+        for (int el = 0; el < nel; ++el) {
+          calc_indices_te_general(m, b, n, kind, el, IR_RECV, 1, &bx);
+          for (int c = 0; c < ncomp; ++c)
+            for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+              for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+                for (int i = bx.s[0]; i <= bx.e[0]; ++i)
+                  if (te_active(&bx, k, j, i)) te_restrict(&F, kind, b, el, c, k, j, i);
+        }
+      }
+    }
+    /* ProlongateBounds: shared elements first ... */
+    for (int b = 0; b < m->nblocks; ++b) {
+      const Block *blk = &m->blocks[b];
+      for (int n = 0; n < blk->nnb; ++n) {
+        if (!(blk->nb[n].origin_loc.level < blk->loc.level)) continue;
+        for (int el = 0; el < nel; ++el) {
+          calc_indices_te_general(m, b, n, kind, el, IR_RECV, 1, &bx);
+          for (int c = 0; c < ncomp; ++c)
+            for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+              for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+                for (int i = bx.s[0]; i <= bx.e[0]; ++i)
+                  if (te_active(&bx, k, j, i)) te_prolongate_shared(&F, kind, b, el, c, k, j, i);
+        }
+      }
+    }
+    /* ... then the fine elements inside coarse edges, faces and cells */
+    for (int b = 0; b < m->nblocks; ++b) {
+      const Block *blk = &m->blocks[b];
+      for (int n = 0; n < blk->nnb; ++n) {
+        if (!(blk->nb[n].origin_loc.level < blk->loc.level)) continue;
+        for (int el = 0; el < nel; ++el) {
+          int ftop[3];
+          te_top_offset(kind, el, ftop);
+          for (int q = 0; q < 8; ++q) {
+            int ctop[3];
+            te_top_offset(kCelKind[q], kCelEl[q], ctop);
+            if (!te_is_submanifold(ftop, ctop)) continue;
+            calc_indices_te_general(m, b, n, kCelKind[q], kCelEl[q], IR_RECV, 1, &bx);
+            for (int c = 0; c < ncomp; ++c)
+              for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+                for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+                  for (int i = bx.s[0]; i <= bx.e[0]; ++i)
+                    if (te_active(&bx, k, j, i))
+                      te_prolongate_internal(&F, ftop, ctop, b, el, c, k, j, i);
+          }
+        }
+      }
+    }
+  }
   free(buf);
   free(off);
   free(first);
   return total;
+}
+#undef OWN
+
+int64_t orc_exchange_te(const OrcMesh *m, double *U, int ncomp, int kind) {
+  if (m->multilevel) {
+    fprintf(stderr, "oracle: orc_exchange_te is the uniform-mesh form; use orc_exchange_te_ml\n");
+    abort();
+  }
+  return orc_exchange_te_ml(m, U, NULL, ncomp, kind);
 }
 
 /* ------------------------------------------------------------------------------------ */

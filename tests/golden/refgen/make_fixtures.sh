@@ -192,16 +192,24 @@ PB2_DUMP_EVERY=4 run_sparse sparse_u64_b8_2d_dealloc 64 8 60 parthenon/sparse/al
 fi
 # non-cell-centred fields (face / edge / node) after the boundary exchange of Mesh::Initialize:
 # keys U_0 (face, 3 elements x 2 components), U_1 (edge, 3 x 1), U_2 (node)
-run_tecomm () { # name ndim nx nb ng
-  local name=$1 ndim=$2 nx=$3 nb=$4 ng=$5; shift 5
+run_tecomm () { # name ndim nx nb ng [numlevel "regions"]
+  local name=$1 ndim=$2 nx=$3 nb=$4 ng=$5 numlevel=${6:-1} regions=${7:-}
   local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
   local nx3=$nx nb3=$nb; if [ "$ndim" = 2 ]; then nx3=1; nb3=1; fi
-  printf '<parthenon/job>\nproblem_id = tecomm\n<parthenon/mesh>\nrefinement = none\nnumlevel = 1\nnghost = %d\n' $ng > deck.pin
+  local refinement=none; if [ "$numlevel" -gt 1 ]; then refinement=static; fi
+  printf '<parthenon/job>\nproblem_id = tecomm\n<parthenon/mesh>\nrefinement = %s\nnumlevel = %d\nnghost = %d\n' $refinement $numlevel $ng > deck.pin
   printf 'nx1 = %d\nx1min = -0.5\nx1max = 0.5\nix1_bc = periodic\nox1_bc = periodic\n' $nx >> deck.pin
   printf 'nx2 = %d\nx2min = -0.5\nx2max = 0.5\nix2_bc = periodic\nox2_bc = periodic\n' $nx >> deck.pin
   printf 'nx3 = %d\nx3min = -0.5\nx3max = 0.5\nix3_bc = periodic\nox3_bc = periodic\n' $nx3 >> deck.pin
   printf '<parthenon/meshblock>\nnx1 = %d\nnx2 = %d\nnx3 = %d\n<parthenon/time>\ntlim = 1.0\nnlim = 0\n' $nb $nb $nb3 >> deck.pin
-  PB2_DUMP_PREFIX="$d/U" "$WORK/tecomm_dump" -i deck.pin "$@" > run.log 2>&1
+  local n=0
+  for r in $regions; do # level:x1min:x1max:x2min:x2max:x3min:x3max
+    IFS=: read -r lev a b c e f g <<< "$r"
+    printf '\n<parthenon/static_refinement%d>\nlevel = %s\nx1min = %s\nx1max = %s\nx2min = %s\nx2max = %s\nx3min = %s\nx3max = %s\n' \
+      $n $lev $a $b $c $e $f $g >> deck.pin
+    n=$((n+1))
+  done
+  PB2_DUMP_PREFIX="$d/U" "$WORK/tecomm_dump" -i deck.pin > run.log 2>&1
   python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
 }
 if [ -z "${SKIP_TECOMM:-}" ]; then
@@ -209,6 +217,10 @@ run_tecomm tecomm_u16_b8_g2_3d 3 16 8 2
 run_tecomm tecomm_u16_b8_g4_3d 3 16 8 4
 run_tecomm tecomm_u16_b4_g2_3d 3 16 4 2
 run_tecomm tecomm_u32_b8_g2_2d 2 32 8 2
+# statically refined meshes: restriction, shared and internal prolongation of face / edge /
+# node fields (pins the oracle; the GPU path for these is not built yet)
+run_tecomm tecomm_s16_b8_l2_3d 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
+run_tecomm tecomm_s32_b8_l3_2d 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
 fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1

@@ -180,6 +180,9 @@ def block_crcs(data):
 # (name, ndim, mesh cells per direction, block cells per direction, nghost)
 TECOMM = [("tecomm_u16_b8_g2_3d", 3, 16, 8, 2), ("tecomm_u16_b8_g4_3d", 3, 16, 8, 4),
           ("tecomm_u16_b4_g2_3d", 3, 16, 4, 2), ("tecomm_u32_b8_g2_2d", 2, 32, 8, 2)]
+# statically refined meshes (restriction, shared + internal prolongation): two levels in 3-D,
+# three levels in 2-D
+TECOMM_MULTILEVEL = [("tecomm_s16_b8_l2_3d", 3, 16, 8, 2), ("tecomm_s32_b8_l3_2d", 2, 32, 8, 2)]
 # (kind, fixture key, components): kind 1 face, 2 edge, 3 node
 TECOMM_FIELDS = [(1, "U_0", 2), (2, "U_1", 1), (3, "U_2", 1)]
 
