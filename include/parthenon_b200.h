@@ -171,6 +171,13 @@ typedef struct pb2_prores_region {
   uint32_t status;
   double fine_xmin[3], fine_dx[3];     /* UniformCartesian xmin_, dx_ of the block */
   double coarse_xmin[3], coarse_dx[3]; /* and of its coarse coordinates */
+  /* face / edge / node elements (the *_te entry points; zero for cell-centred regions): in
+   * which directions (i, j, k) the region's element is displaced by half a cell
+   * (TopologicalOffsetI/J/K, basic_types.hpp:195-203), and the same for the coarse CONTAINER
+   * element of an internal prolongation.  `fine` / `coarse` point at the element's first slab
+   * component; the box counts entries of the (container) element. */
+  int32_t ftop[3];
+  int32_t ctop[3];
 } pb2_prores_region;
 
 #define PB2_PROLONG_MINMOD 0             /* ProlongateSharedMinMod (default, metadata.hpp:337) */
@@ -183,6 +190,15 @@ int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regi
 int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream);
 /* ProlongateSharedGeneral over every region of the table (pr_ops.hpp:167-280) */
 int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream);
+/* The element forms for face / edge / node fields (regions carry ftop): RestrictAverage::Do<el>
+ * and ProlongateSharedGeneral::Do<el> average / interpolate only along the directions the
+ * element is centred in; pb2_prolongate_internal is ProlongateInternalAverage::Do<fel, cel>
+ * (pr_ops.hpp:291-382) over boxes of coarse container elements (ctop) and must follow the
+ * pb2_prolongate_te of the same exchange on the same stream.  The ownership mask of the
+ * reference's loops (pr_loops.hpp:69-77 IsActive) is resolved by the caller into boxes. */
+int pb2_restrict_te(const pb2_bnd_table *table, pb2_stream_t stream);
+int pb2_prolongate_te(const pb2_bnd_table *table, int op, pb2_stream_t stream);
+int pb2_prolongate_internal(const pb2_bnd_table *table, pb2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * physical boundary conditions

@@ -150,6 +150,169 @@ __global__ void __launch_bounds__(kPrThreads)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// face / edge / node elements (pb2_prores_region::ftop / ctop): the element forms of the same
+// operators.  A region addresses ONE topological element of a field (its `fine` / `coarse`
+// pointers start at the element's first slab component); ftop says in which directions the
+// element is displaced by half a cell (TopologicalOffsetI/J/K, basic_types.hpp:195-203).
+// ---------------------------------------------------------------------------------------
+
+// RestrictAverage::Do<DIM, el> pr_ops.hpp:105-165: average over the directions the element is
+// centred in (INCLUDE_Xd), weights Volume<el> (uniform_cartesian.hpp:247-270): cell volume,
+// face area, edge length or 1 — the product of dx over the centred directions
+__global__ void __launch_bounds__(kPrThreads)
+    restrict_te_kernel(const pb2_prores_region *__restrict__ regions,
+                       const Chunk *__restrict__ chunks) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_prores_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+  const bool inc0 = DIM > 0 && !r.ftop[0], inc1 = DIM > 1 && !r.ftop[1],
+             inc2 = DIM > 2 && !r.ftop[2];
+  double elvol = 1.0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if (!r.ftop[d]) elvol = elvol * r.fine_dx[d];
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    int c, ck, cj, ci;
+    if (!cell_of(r, ch.first_vec + u * kPrThreads + threadIdx.x, c, ck, cj, ci)) continue;
+    const int i = (ci - r.coarse_is[0]) * 2 + r.fine_is[0];
+    const int j = DIM > 1 ? (cj - r.coarse_is[1]) * 2 + r.fine_is[1] : r.fine_is[1];
+    const int k = DIM > 2 ? (ck - r.coarse_is[2]) * 2 + r.fine_is[2] : r.fine_is[2];
+    const double *f = r.fine + (int64_t)c * r.fine_stride_c;
+    double vol[2][2][2], terms[2][2][2];
+#pragma unroll
+    for (int ok = 0; ok < 2; ++ok)
+#pragma unroll
+      for (int oj = 0; oj < 2; ++oj)
+#pragma unroll
+        for (int oi = 0; oi < 2; ++oi) {
+          const bool on = (ok == 0 || inc2) && (oj == 0 || inc1) && (oi == 0 || inc0);
+          vol[ok][oj][oi] = on ? elvol : 0.0;
+          terms[ok][oj][oi] =
+              on ? vol[ok][oj][oi] * f[(int64_t)(k + ok) * r.fine_stride_k +
+                                       (int64_t)(j + oj) * r.fine_stride_j + (i + oi)]
+                 : 0.0;
+        }
+    const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                        ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+    r.coarse[(int64_t)c * r.coarse_stride_c + (int64_t)ck * r.coarse_stride_k +
+             (int64_t)cj * r.coarse_stride_j + ci] =
+        (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+         ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+        tvol;
+  }
+}
+
+// ProlongateSharedGeneral::Do<DIM, el> pr_ops.hpp:167-280: the fine elements that coincide
+// with coarse element (k, j, i); slopes exist only in the directions the element is centred in
+// (there GetGridSpacings :76-93 uses cell-centre positions)
+__global__ void __launch_bounds__(kPrThreads)
+    prolongate_te_kernel(const pb2_prores_region *__restrict__ regions,
+                         const Chunk *__restrict__ chunks, int op) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_prores_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+  const bool inc[3] = {DIM > 0 && !r.ftop[0], DIM > 1 && !r.ftop[1], DIM > 2 && !r.ftop[2]};
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    int c, k, j, i;
+    if (!cell_of(r, ch.first_vec + u * kPrThreads + threadIdx.x, c, k, j, i)) continue;
+    const int fi = (i - r.coarse_is[0]) * 2 + r.fine_is[0];
+    const int fj = DIM > 1 ? (j - r.coarse_is[1]) * 2 + r.fine_is[1] : r.fine_is[1];
+    const int fk = DIM > 2 ? (k - r.coarse_is[2]) * 2 + r.fine_is[2] : r.fine_is[2];
+    const double *cs = r.coarse + (int64_t)c * r.coarse_stride_c +
+                       (int64_t)k * r.coarse_stride_k + (int64_t)j * r.coarse_stride_j + i;
+    const double fc = cs[0];
+    double gm[3] = {0, 0, 0}, gp[3] = {0, 0, 0}, dxfm[3] = {0, 0, 0}, dxfp[3] = {0, 0, 0};
+    const int cc[3] = {i, j, k}, ff[3] = {fi, fj, fk};
+    const int64_t cstr[3] = {1, r.coarse_stride_j, r.coarse_stride_k};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (inc[d]) {
+        const double xm = r.coarse_xmin[d] + ((cc[d] - 1) + 0.5) * r.coarse_dx[d];
+        const double xc = r.coarse_xmin[d] + (cc[d] + 0.5) * r.coarse_dx[d];
+        const double xp = r.coarse_xmin[d] + ((cc[d] + 1) + 0.5) * r.coarse_dx[d];
+        const double dxm = xc - xm, dxp = xp - xc;
+        const double fxm = r.fine_xmin[d] + (ff[d] + 0.5) * r.fine_dx[d];
+        const double fxp = r.fine_xmin[d] + ((ff[d] + 1) + 0.5) * r.fine_dx[d];
+        dxfm[d] = xc - fxm;
+        dxfp[d] = fxp - xc;
+        double gxm, gxp;
+        const double gc = grad_minmod(fc, cs[-cstr[d]], cs[cstr[d]], dxm, dxp, gxm, gxp);
+        if (op == PB2_PROLONG_MINMOD) {
+          gm[d] = gc;
+          gp[d] = gc;
+        } else if (op == PB2_PROLONG_LINEAR) {
+          gm[d] = gxm;
+          gp[d] = gxp;
+        }
+      }
+    }
+    const double gx1m = gm[0], gx1p = gp[0], gx2m = gm[1], gx2p = gp[1], gx3m = gm[2],
+                 gx3p = gp[2];
+    const double dx1fm = dxfm[0], dx1fp = dxfp[0], dx2fm = dxfm[1], dx2fp = dxfp[1],
+                 dx3fm = dxfm[2], dx3fp = dxfp[2];
+    double *f = r.fine + (int64_t)c * r.fine_stride_c + (int64_t)fk * r.fine_stride_k +
+                (int64_t)fj * r.fine_stride_j + fi;
+    const int64_t sj = r.fine_stride_j, sk = r.fine_stride_k;
+    f[0] = fc - (gx1m * dx1fm + gx2m * dx2fm + gx3m * dx3fm);
+    if (inc[0]) f[1] = fc + (gx1p * dx1fp - gx2m * dx2fm - gx3m * dx3fm);
+    if (inc[1]) f[sj] = fc - (gx1m * dx1fm - gx2p * dx2fp + gx3m * dx3fm);
+    if (inc[1] && inc[0]) f[sj + 1] = fc + (gx1p * dx1fp + gx2p * dx2fp - gx3m * dx3fm);
+    if (inc[2]) f[sk] = fc - (gx1m * dx1fm + gx2m * dx2fm - gx3p * dx3fp);
+    if (inc[2] && inc[0]) f[sk + 1] = fc + (gx1p * dx1fp - gx2m * dx2fm + gx3p * dx3fp);
+    if (inc[2] && inc[1]) f[sk + sj] = fc - (gx1m * dx1fm - gx2p * dx2fp - gx3p * dx3fp);
+    if (inc[2] && inc[1] && inc[0])
+      f[sk + sj + 1] = fc + (gx1p * dx1fp + gx2p * dx2fp + gx3p * dx3fp);
+  }
+}
+
+// ProlongateInternalAverage::Do<DIM, fel, cel> pr_ops.hpp:291-382: the fine elements of the
+// field (ftop) strictly inside coarse container element cel (ctop) at (k, j, i) become the
+// average of the fine shared elements around them.  Runs after prolongate_te_kernel of the
+// same exchange has completed; reads only shared elements, writes only internal ones.
+__global__ void __launch_bounds__(kPrThreads)
+    prolongate_internal_kernel(const pb2_prores_region *__restrict__ regions,
+                               const Chunk *__restrict__ chunks) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_prores_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+  int center[3], stencil[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    center[d] = d < DIM && !r.ftop[d];
+    stencil[d] = d < DIM && !center[d] && !r.ctop[d];
+  }
+  const double w = 1.0 / ((1.0 + stencil[2]) * (1.0 + stencil[1]) * (1.0 + stencil[0]));
+  const int64_t sj = r.fine_stride_j, sk = r.fine_stride_k;
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    int c, k, j, i;
+    if (!cell_of(r, ch.first_vec + u * kPrThreads + threadIdx.x, c, k, j, i)) continue;
+    const int fi = (i - r.coarse_is[0]) * 2 + r.fine_is[0];
+    const int fj = DIM > 1 ? (j - r.coarse_is[1]) * 2 + r.fine_is[1] : r.fine_is[1];
+    const int fk = DIM > 2 ? (k - r.coarse_is[2]) * 2 + r.fine_is[2] : r.fine_is[2];
+    double *f = r.fine + (int64_t)c * r.fine_stride_c;
+    for (int ok = 0; ok < 1 + center[2]; ++ok)
+      for (int oj = 0; oj < 1 + center[1]; ++oj)
+        for (int oi = 0; oi < 1 + center[0]; ++oi) {
+          const int tk = fk + ok + stencil[2], tj = fj + oj + stencil[1],
+                    ti = fi + oi + stencil[0];
+          double v = 0.0;
+          for (int stk = -stencil[2]; stk <= stencil[2]; stk += 2)
+            for (int stj = -stencil[1]; stj <= stencil[1]; stj += 2)
+              for (int sti = -stencil[0]; sti <= stencil[0]; sti += 2)
+                v += w * f[(int64_t)(tk + stk) * sk + (int64_t)(tj + stj) * sj + (ti + sti)];
+          f[(int64_t)tk * sk + (int64_t)tj * sj + ti] = v;
+        }
+  }
+}
+
 // Flux correction: RestrictAverage::Do pr_ops.hpp:105-165 with el = F_dir over the fine faces
 // tiling one coarse face, delivered straight to the coarser block's flux array (or a slab).
 // Weights are coords.Volume<F_dir> (the fine block's face area, uniform_cartesian.hpp:36-38);
@@ -309,6 +472,37 @@ int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
   ProfScope prof(K_PROLONGATE, as_stream(stream));
   prolongate_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                       as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_restrict_te(const pb2_bnd_table *table, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kProRes, "restrict needs a prores table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_RESTRICT, as_stream(stream));
+  restrict_te_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                       as_stream(stream)>>>(table->d_prores, table->d_chunks);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_prolongate_te(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
+  PB2_REQUIRE(op >= 0 && op <= 2, "unknown prolongation operator");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  prolongate_te_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                         as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_prolongate_internal(const pb2_bnd_table *table, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  prolongate_internal_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                               as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -42,10 +42,14 @@ IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeTy
 // with a coarser neighbour gets the box in its coarse index space (bnd_info.cpp:124-125).
 IndexBox CalcIndicesFlux(const NeighborBlock &nb, const MeshBlock *pmb);
 
-// CalcIndices for one topological element of a face / edge / node field, same-level neighbour
-// (bnd_info.cpp:205-218 with TopologicalOffset and the element bounds of mesh/domain.hpp)
+// CalcIndices for one topological element (bnd_info.cpp:105-252 with TopologicalOffset and the
+// element bounds of mesh/domain.hpp:162-251); el may be any of the ten elements whatever the
+// field holds (the internal prolongation runs over boxes of container elements)
 IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
-                       IndexRangeType ir_type);
+                       IndexRangeType ir_type, bool prores = false);
+// the ownership mask a RECEIVING region applies to element el (bnd_info.cpp:232-248)
+std::array<bool, 27> RecvMask(const Mesh *pm, const NeighborBlock &nb, const MeshBlock *pmb,
+                              TE el);
 // GetIndexRangeMaskFromOwnership (block_ownership.cpp:85-140): which entries of a receive box
 // — first / inner / last index per direction, index (i+1) + 3 (j+1) + 9 (k+1) — the receiver
 // takes from a sender with the given block ownership; sox = offsets of the receiver seen from
@@ -111,6 +115,11 @@ struct BvarsCache {
   pb2_bnd_table *restrict_send[2] = {nullptr, nullptr}, *restrict_set[2] = {nullptr, nullptr};
   pb2_bnd_table *prolongate[2][3] = {{nullptr, nullptr, nullptr},
                                      {nullptr, nullptr, nullptr}}; // per prolongation op
+  // the same for face / edge / node fields: one region per element and active sub-box of the
+  // ownership mask; te_internal: ProlongateInternalAverage over container-element boxes
+  pb2_bnd_table *te_restrict_send[2] = {nullptr, nullptr}, *te_restrict_set[2] = {nullptr, nullptr};
+  pb2_bnd_table *te_prolongate[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  pb2_bnd_table *te_internal[2] = {nullptr, nullptr};
   DeviceBuffer send_slab, recv_slab;
   pb2_event_t packed = nullptr, received = nullptr, sent = nullptr;
   bool nonlocal_in_flight = false;

@@ -70,20 +70,36 @@ IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeTy
 }
 
 IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
-                       IndexRangeType ir_type) {
-  PARTHENON_REQUIRE(nb.loc.level == pmb->loc.level,
-                    "non-cell-centred fields are exchanged between blocks of one level only");
+                       IndexRangeType ir_type, bool prores) {
+  const LogicalLocation &loc = pmb->loc;
   const int ng = Globals::nghost;
+  const bool use_coarse = prores || nb.loc.level < loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int coarse_fac = nb.loc.level > loc.level ? 2 : 1;
   const int interior_offset = ir_type == IndexRangeType::BoundaryInteriorSend ? ng : 0;
-  const int exterior_offset = ir_type == IndexRangeType::BoundaryExteriorRecv ? ng : 0;
+  int exterior_offset = ir_type == IndexRangeType::BoundaryExteriorRecv ? ng : 0;
+  if (prores) exterior_offset /= 2;
   IndexBox box;
   for (int d = 0; d < 3; ++d) {
-    const IndexRange b = pmb->cellbounds.Bounds(d, IndexDomain::interior, el);
-    const int top = pmb->block_size.symmetry_[d] ? 0 : TopologicalOffset(el, d);
+    const bool not_sym = !pmb->block_size.symmetry_[d];
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior, el);
+    const int top = not_sym ? TopologicalOffset(el, d) : 0;
+    // entries of the element the neighbour holds along d in the index space of the exchange
+    const int nb_n = not_sym ? pmb->block_size.nx_[d] / coarse_fac + top : 1;
     int &s = box.s[d], &e = box.e[d];
     if (nb.offsets[d] == 0) {
       s = b.s;
       e = b.e;
+      if (loc.level < nb.origin_loc.level && not_sym) { // :173-192
+        const int extra = (b.e - b.s + 1) - nb_n;
+        const bool upper_half = ((nb.origin_loc.lx[d] % 2) + 2) % 2 == 1;
+        s += upper_half ? extra - interior_offset : 0;
+        e -= upper_half ? 0 : extra - interior_offset;
+      }
+      if (loc.level > nb.origin_loc.level && not_sym) { // :193-204
+        s -= loc.lx[d] % 2 == 1 ? exterior_offset : 0;
+        e += loc.lx[d] % 2 == 0 ? exterior_offset : 0;
+      }
     } else if (nb.offsets[d] > 0) {
       // a neighbour duplicates the shared elements: its boundary lies one deeper (:150-155)
       s = b.e + (-interior_offset + 1 - top);
@@ -94,6 +110,16 @@ IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
     }
   }
   return box;
+}
+
+std::array<bool, 27> RecvMask(const Mesh *pm, const NeighborBlock &nb, const MeshBlock *pmb,
+                              TE el) {
+  int sox[3] = {-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]};
+  if (nb.origin_loc.level < pmb->loc.level)
+    // a coarser sender passes zones from an interior corner only, never a whole face or edge
+    for (int d = 0; d < 3; ++d)
+      if (sox[d] == 0) sox[d] = pmb->loc.lx[d] % 2 == 1 ? 1 : -1;
+  return IndexRangeMask(el, pm->Ownership(nb.gid), sox);
 }
 
 std::array<bool, 27> IndexRangeMask(TE el, const std::array<bool, 27> &sender,
@@ -244,9 +270,18 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
                     const MeshBlock *local_sender, const NeighborBlock *q, auto &&emit) {
     const PlanVar &pv = vars[base.var];
     const std::vector<TE> els = GetTopologicalElements(pv.tt);
+    // the mask is the RECEIVER's (bnd_info.cpp:232-248): offsets of the receiver seen from the
+    // sender, replaced by the receiver's position inside its parent where a coarser sender
+    // faces it with offset 0
+    const LogicalLocation &recv_loc = pmb_sends ? nb.origin_loc : pmb->loc;
     const int sender_gid = pmb_sends ? pmb->gid : nb.gid;
+    const int sender_level = pmb_sends ? pmb->loc.level : nb.loc.level;
     int sox[3];
-    for (int d = 0; d < 3; ++d) sox[d] = pmb_sends ? nb.offsets[d] : -nb.offsets[d];
+    for (int d = 0; d < 3; ++d) {
+      sox[d] = pmb_sends ? nb.offsets[d] : -nb.offsets[d];
+      if (sender_level < recv_loc.level && sox[d] == 0)
+        sox[d] = ((recv_loc.lx[d] % 2) + 2) % 2 == 1 ? 1 : -1;
+    }
     for (size_t e = 0; e < els.size(); ++e) {
       const IndexBox mine = CalcIndicesTE(nb, pmb, els[e],
                                           pmb_sends ? IndexRangeType::BoundaryInteriorSend
@@ -384,6 +419,14 @@ void BvarsCache::Clear() {
     pb2_bnd_table_destroy(restrict_send[c]);
     pb2_bnd_table_destroy(restrict_set[c]);
     restrict_send[c] = restrict_set[c] = nullptr;
+    pb2_bnd_table_destroy(te_restrict_send[c]);
+    pb2_bnd_table_destroy(te_restrict_set[c]);
+    pb2_bnd_table_destroy(te_internal[c]);
+    te_restrict_send[c] = te_restrict_set[c] = te_internal[c] = nullptr;
+    for (int o = 0; o < 3; ++o) {
+      pb2_bnd_table_destroy(te_prolongate[c][o]);
+      te_prolongate[c][o] = nullptr;
+    }
     for (int o = 0; o < 3; ++o) {
       pb2_bnd_table_destroy(prolongate[c][o]);
       prolongate[c][o] = nullptr;
@@ -440,6 +483,32 @@ pb2_prores_region MakeProRes(Variable &v, const MeshBlock *pmb, const IndexBox &
     r.coarse_dx[d] = cc.Dx()[d];
   }
   return r;
+}
+
+// one region per active sub-box of `mask` over `box`, for element number e (storage order) of
+// a face / edge / node field; ctop != nullptr: boxes of a container element (internal
+// prolongation)
+void AddTeRegions(std::vector<pb2_prores_region> &out, Variable &v, const MeshBlock *pmb, int e,
+                  TE fel, const TE *cel, const IndexBox &box, const std::array<bool, 27> &mask,
+                  int ndim) {
+  int n[3] = {box.n(0), box.n(1), box.n(2)};
+  for (const IndexBox &rel : ActivePieces(n, mask)) {
+    IndexBox sub;
+    for (int d = 0; d < 3; ++d) {
+      sub.s[d] = box.s[d] + rel.s[d];
+      sub.e[d] = box.s[d] + rel.e[d];
+    }
+    pb2_prores_region r = MakeProRes(v, pmb, sub, ndim);
+    const int nc = v.TensorComponents();
+    r.fine += static_cast<int64_t>(e) * nc * v.comp_stride;
+    r.coarse += static_cast<int64_t>(e) * nc * v.ccomp_stride;
+    r.ncomp = nc;
+    for (int d = 0; d < 3; ++d) {
+      r.ftop[d] = TopologicalOffset(fel, d);
+      r.ctop[d] = cel ? TopologicalOffset(*cel, d) : 0;
+    }
+    out.push_back(r);
+  }
 }
 
 void Rebuild(MeshData<Real> *md) {
@@ -586,6 +655,23 @@ void Rebuild(MeshData<Real> *md) {
   // split by whether the neighbour is local so the local / nonlocal task split still works
   if (pm->multilevel) {
     std::vector<pb2_prores_region> rsend[2], rset[2], pro[2][3];
+    std::vector<pb2_prores_region> te_rsend[2], te_rset[2], te_pro[2][3], te_int[2];
+    PARTHENON_REQUIRE(all_cell || !pm->adaptive,
+                      "non-cell-centred FillGhost fields on adaptive meshes are not supported "
+                      "by this build");
+    std::array<bool, 27> all_true;
+    all_true.fill(true);
+    // containers of the internal prolongation in the order the reference visits them
+    // (pr_loops.hpp:82-108)
+    const TE containers[8] = {TE::NN, TE::E3, TE::E2, TE::E1, TE::F1, TE::F2, TE::F3, TE::CC};
+    auto is_submanifold = [](TE f, TE cnt) { // basic_types.hpp:207-232
+      int more = 0;
+      for (int d = 0; d < 3; ++d) {
+        if (TopologicalOffset(cnt, d) && !TopologicalOffset(f, d)) return false;
+        more += TopologicalOffset(f, d) && !TopologicalOffset(cnt, d);
+      }
+      return more > 0;
+    };
     for (auto &pmb : md->GetBlockList()) {
       const int my_vr = pm->VirtualRankOf(pmb->gid);
       bool restricted = false;
@@ -597,6 +683,35 @@ void Rebuild(MeshData<Real> *md) {
             nb.rank == pm->my_rank && pm->VirtualRankOf(nb.gid) == my_vr;
         const int cls = local ? 0 : 1;
         for (Variable *v : c.vars) {
+          if (v->topological_type() != TopologicalType::Cell) {
+            const std::vector<TE> els = GetTopologicalElements(v->topological_type());
+            const int op = v->metadata().ProlongationOp();
+            for (size_t e = 0; e < els.size(); ++e) {
+              const int ei = static_cast<int>(e);
+              if (nb.origin_loc.level < pmb->loc.level) {
+                AddTeRegions(te_rsend[cls], *v, pmb.get(), ei, els[e], nullptr,
+                             CalcIndicesTE(nb, pmb.get(), els[e],
+                                           IndexRangeType::BoundaryInteriorSend, true),
+                             all_true, pm->ndim);
+                AddTeRegions(te_pro[cls][op], *v, pmb.get(), ei, els[e], nullptr,
+                             CalcIndicesTE(nb, pmb.get(), els[e],
+                                           IndexRangeType::BoundaryExteriorRecv, true),
+                             RecvMask(pm, nb, pmb.get(), els[e]), pm->ndim);
+                for (const TE &cel : containers)
+                  if (is_submanifold(els[e], cel))
+                    AddTeRegions(te_int[cls], *v, pmb.get(), ei, els[e], &cel,
+                                 CalcIndicesTE(nb, pmb.get(), cel,
+                                               IndexRangeType::BoundaryExteriorRecv, true),
+                                 RecvMask(pm, nb, pmb.get(), cel), pm->ndim);
+              } else if (restricted) {
+                AddTeRegions(te_rset[cls], *v, pmb.get(), ei, els[e], nullptr,
+                             CalcIndicesTE(nb, pmb.get(), els[e],
+                                           IndexRangeType::BoundaryExteriorRecv, true),
+                             RecvMask(pm, nb, pmb.get(), els[e]), pm->ndim);
+              }
+            }
+            continue;
+          }
           if (nb.origin_loc.level < pmb->loc.level) {
             rsend[cls].push_back(MakeProRes(
                 *v, pmb.get(),
@@ -620,6 +735,15 @@ void Rebuild(MeshData<Real> *md) {
       for (int o = 0; o < 3; ++o)
         PB2_CHECK(pb2_prores_table_create(&c.prolongate[cls][o], pro[cls][o].data(),
                                           static_cast<int64_t>(pro[cls][o].size())));
+      PB2_CHECK(pb2_prores_table_create(&c.te_restrict_send[cls], te_rsend[cls].data(),
+                                        static_cast<int64_t>(te_rsend[cls].size())));
+      PB2_CHECK(pb2_prores_table_create(&c.te_restrict_set[cls], te_rset[cls].data(),
+                                        static_cast<int64_t>(te_rset[cls].size())));
+      PB2_CHECK(pb2_prores_table_create(&c.te_internal[cls], te_int[cls].data(),
+                                        static_cast<int64_t>(te_int[cls].size())));
+      for (int o = 0; o < 3; ++o)
+        PB2_CHECK(pb2_prores_table_create(&c.te_prolongate[cls][o], te_pro[cls][o].data(),
+                                          static_cast<int64_t>(te_pro[cls][o].size())));
     }
   }
   // physical boundary conditions: blocks on a non-periodic mesh face
@@ -747,7 +871,10 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
   pb2_stream_t st = md->stream();
   if (DoesLocal(bt)) {
     // boundary_communication.cpp:82-87: restrict before anything reads the coarse buffers
-    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_send[0], st));
+    if (pm->multilevel) {
+      PB2_CHECK(pb2_restrict(c.restrict_send[0], st));
+      PB2_CHECK(pb2_restrict_te(c.te_restrict_send[0], st));
+    }
     if (c.sparse) {
       // sender half of a sparse exchange: which messages are null (:95-157)
       PB2_CHECK(pb2_memset(c.sparse_flags.get(), 0, sizeof(int32_t) * c.sparse_flags_h.size(), st));
@@ -756,7 +883,10 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     c.send_generation++; // the copy itself happens in SetBounds<local> of the receiver
   }
   if (DoesNonlocal(bt) && c.plan.send_elements + c.plan.recv_elements > 0) {
-    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_send[1], st));
+    if (pm->multilevel) {
+      PB2_CHECK(pb2_restrict(c.restrict_send[1], st));
+      PB2_CHECK(pb2_restrict_te(c.te_restrict_send[1], st));
+    }
     pb2_stream_t cs = pm->comm_stream;
     // Where the pack runs: normally on the compute stream, after everything enqueued so far.
     // If the producer signalled `early_ready` (all blocks that feed nonlocal channels are
@@ -851,7 +981,10 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
           p == md->partition_id() ? md.get() : pm->mesh_data.GetOrAdd(md->label(), p).get();
       c.consumed_generation[p] = smd->bvars().send_generation;
     }
-    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_set[0], st)); // :338-346
+    if (pm->multilevel) { // :338-346
+      PB2_CHECK(pb2_restrict(c.restrict_set[0], st));
+      PB2_CHECK(pb2_restrict_te(c.te_restrict_set[0], st));
+    }
   }
   if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
     PB2_CHECK(pb2_stream_wait_event(st, c.received));
@@ -859,7 +992,10 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
     PB2_CHECK(pb2_event_record(c.unpacked, st));
     c.unpacked_valid = true;
     c.elements_nonlocal = c.plan.recv_elements;
-    if (pm->multilevel) PB2_CHECK(pb2_restrict(c.restrict_set[1], st));
+    if (pm->multilevel) {
+      PB2_CHECK(pb2_restrict(c.restrict_set[1], st));
+      PB2_CHECK(pb2_restrict_te(c.te_restrict_set[1], st));
+    }
   }
   return TaskStatus::complete;
 }
@@ -873,6 +1009,17 @@ TaskStatus ProlongateBounds(std::shared_ptr<MeshData<Real>> &md) {
     if (cls == 0 && !DoesLocal(bt)) continue;
     if (cls == 1 && !DoesNonlocal(bt)) continue;
     for (int o = 0; o < 3; ++o) PB2_CHECK(pb2_prolongate(c.prolongate[cls][o], o, md->stream()));
+    for (int o = 0; o < 3; ++o)
+      PB2_CHECK(pb2_prolongate_te(c.te_prolongate[cls][o], o, md->stream()));
+  }
+  // face / edge / node fields: the fine elements inside coarse edges, faces and cells come
+  // after ALL elements that fine and coarse grids share (boundary_communication.cpp:384-389) —
+  // an internal element of a local region may average shared elements that a nonlocal region
+  // prolongates
+  for (int cls = 0; cls < 2; ++cls) {
+    if (cls == 0 && !DoesLocal(bt)) continue;
+    if (cls == 1 && !DoesNonlocal(bt)) continue;
+    PB2_CHECK(pb2_prolongate_internal(c.te_internal[cls], md->stream()));
   }
   return TaskStatus::complete;
 }

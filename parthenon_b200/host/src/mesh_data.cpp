@@ -24,9 +24,6 @@ Variable::Variable(const std::string &label, const Metadata &m, int sparse_id, i
   if (tt_ != TopologicalType::Cell) {
     // face, edge and node arrays are one longer in every non-symmetry direction
     // (metadata.cpp:383-387)
-    PARTHENON_REQUIRE(!(multilevel && m.IsSet(Metadata::FillGhost)),
-                      "non-cell-centred FillGhost fields need a uniform mesh in this build (" +
-                          label + ")");
     PARTHENON_REQUIRE(!m.IsSparse() && !m.IsSet(Metadata::WithFluxes),
                       "non-cell-centred fields cannot be sparse or carry fluxes in this build (" +
                           label + ")");
@@ -37,6 +34,11 @@ Variable::Variable(const std::string &label, const Metadata &m, int sparse_id, i
   cni = ccb.ncellsi(IndexDomain::entire);
   cnj = ccb.ncellsj(IndexDomain::entire);
   cnk = ccb.ncellsk(IndexDomain::entire);
+  if (tt_ != TopologicalType::Cell) { // coarse buffers are padded like the fine arrays
+    cni++;
+    if (cnj > 1) cnj++;
+    if (cnk > 1) cnk++;
+  }
   comp_stride = static_cast<int64_t>(ni) * nj * nk;
   block_stride = comp_stride * ncomp_;
   ccomp_stride = static_cast<int64_t>(cni) * cnj * cnk;
