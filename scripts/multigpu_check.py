@@ -123,6 +123,26 @@ def main():
               f"gid ranges on this rank: {'bit-exact' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
         sim.close()
+    # face / edge / node fields across devices: channel pieces from ownership masks that sender
+    # and receiver derive independently, element forms of restriction / prolongation on regions
+    # whose neighbour lives on another GPU, against the reference's dumps
+    for name, ndim, nx, nb, ng in H.TECOMM + H.TECOMM_MULTILEVEL:
+        nccl_id = new_id()
+        g = np.load(os.path.join(gold, name + ".npz"))
+        full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+        leaves, nrb = H.leaves_from_bounds(g["bounds"], full(nx), full(nb))
+        static = len(set(g["meta"][:, 1])) > 1
+        ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static" if static else "none")
+        sim = host.Simulation(app="tecomm", overrides=ov, leaves=leaves if static else None,
+                              rank=rank, nranks=world, nccl_id=nccl_id)
+        info = sim.info()
+        lo, hi = info["first_gid"], info["first_gid"] + info["nblocks"]
+        good = all(np.array_equal(sim.get_field("base", f), g[k][lo:hi])
+                   for f, k in (("face", "U_0"), ("edge", "U_1"), ("node", "U_2")))
+        print(f"rank {rank}/{world}: {name}, face / edge / node fields, blocks {lo}..{hi - 1} of "
+              f"{g['U_0'].shape[0]}: {'bit-exact' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
+        sim.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
