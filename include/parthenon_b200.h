@@ -199,6 +199,11 @@ int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream);
 int pb2_restrict_te(const pb2_bnd_table *table, pb2_stream_t stream);
 int pb2_prolongate_te(const pb2_bnd_table *table, int op, pb2_stream_t stream);
 int pb2_prolongate_internal(const pb2_bnd_table *table, pb2_stream_t stream);
+/* ProlongateInternalTothAndRoe::Do<fel, CC> (pr_ops.hpp:384-470) for face fields: regions are
+ * boxes of coarse CELLS, `fine` points at element F1 of the field (all three are read), ncomp =
+ * tensor components per element, ftop names the element whose internal faces are written.
+ * Same ordering rule as pb2_prolongate_internal. */
+int pb2_prolongate_toth_roe(const pb2_bnd_table *table, pb2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * physical boundary conditions

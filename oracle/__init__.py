@@ -65,6 +65,8 @@ def lib():
         L.orc_exchange_te.restype = C.c_int64
         L.orc_exchange_te_ml.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.orc_exchange_te_ml.restype = C.c_int64
+        L.orc_exchange_te_ml_toth_roe.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_exchange_te_ml_toth_roe.restype = C.c_int64
         L.orc_flux_correct.restype = C.c_int64
         L.orc_flux_correct.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int]
         L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
@@ -271,7 +273,7 @@ class Mesh:
         lib().orc_te_recv_mask(self.h, b, n, kind, el, _ip(mk))
         return mk.reshape(3, 3, 3)
 
-    def exchange_te(self, U, kind):
+    def exchange_te(self, U, kind, toth_roe=False):
         """U: [nblocks][elements][ncomp][nk'][nj'][ni'] (te_extents), exchanged in place;
         multilevel meshes get scratch coarse buffers (restriction / prolongation included)"""
         assert U.flags.c_contiguous and U.shape[3:] == self.te_extents(kind)
@@ -279,6 +281,9 @@ class Mesh:
             return lib().orc_exchange_te(self.h, _dp(U), U.shape[2], kind)
         cd = tuple(n + (1 if (kind != 0 and n > 1) else 0) for n in self.cdims)
         Uc = np.zeros(U.shape[:3] + cd)
+        if toth_roe:
+            assert kind == 1, "Toth & Roe prolongation is defined for face fields"
+            return lib().orc_exchange_te_ml_toth_roe(self.h, _dp(U), _dp(Uc), U.shape[2])
         return lib().orc_exchange_te_ml(self.h, _dp(U), _dp(Uc), U.shape[2], kind)
 
     def flux_correct(self, F):

@@ -1175,13 +1175,63 @@ static void te_prolongate_internal(const TeField *f, const int ftop[3], const in
       }
 }
 
+/* ProlongateInternalTothAndRoe::Do<DIM, fel, CC> pr_ops.hpp:384-470: the fine faces of
+ * element el (0..2 = F1..F3) inside coarse cell (k, j, i) from the fine faces on the cell's
+ * surface so that the fine divergence equals the coarse one (Toth & Roe 2002); written for the
+ * x-component, the others by cyclic permutation */
+static void te_toth_roe(const TeField *f, int b, int el, int c, int k, int j, int i) {
+  const OrcMesh *m = f->m;
+  const Block *blk = &m->blocks[b];
+  const int DIM = m->ndim;
+  const int fi = (i - m->cis[0]) * 2 + m->is[0];
+  const int fj = DIM > 1 ? (j - m->cis[1]) * 2 + m->is[1] : m->is[1];
+  const int fk = DIM > 2 ? (k - m->cis[2]) * 2 + m->is[2] : m->is[2];
+  const int g3 = DIM > 2, g2 = DIM > 1;
+#define FP(eidx, ok, oj, oi)                                                                  \
+  (el == 0   ? te_f(f, b, (el + (eidx)) % 3, c, fk + (ok)*g3, fj + (oj)*g2, fi + (oi))         \
+   : el == 1 ? te_f(f, b, (el + (eidx)) % 3, c, fk + (oj)*g3, fj + (oi)*g2, fi + (ok))         \
+             : te_f(f, b, (el + (eidx)) % 3, c, fk + (oi)*g3, fj + (ok)*g2, fi + (oj)))
+#define SG(o) ((o) == 0 ? -1.0 : 1.0)
+  double Uxx = 0.0, Vxyz = 0.0, Wxyz = 0.0;
+  for (int v = 0; v <= 1; ++v)
+    for (int u = 0; u <= 2; u += 2)
+      for (int t = 0; t <= 1; ++t) {
+        const double fine2 = *FP(1, v, u, t);
+        const double fine3 = *FP(2, u, v, t);
+        Uxx += SG(t) * SG(u) * (fine2 + fine3);
+        Vxyz += SG(t) * SG(u) * SG(v) * fine2;
+        Wxyz += SG(t) * SG(u) * SG(v) * fine3;
+      }
+  Uxx *= 0.125;
+  const double d1 = blk->cdx[el], d2 = blk->cdx[(el + 1) % 3], d3 = blk->cdx[(el + 2) % 3];
+  const double dx2 = d1 * d1, dy2 = d2 * d2, dz2 = d3 * d3; /* std::pow(x, 2) */
+  Vxyz *= 0.125 * dz2 / (dx2 + dz2);
+  Wxyz *= 0.125 * dy2 / (dx2 + dy2);
+  for (int ok = 0; ok <= 1; ++ok)
+    for (int oj = 0; oj <= 1; ++oj)
+      *FP(0, ok, oj, 1) =
+          0.5 * (*FP(0, ok, oj, 0) + *FP(0, ok, oj, 2)) + Uxx + SG(ok) * Vxyz + SG(oj) * Wxyz;
+#undef FP
+#undef SG
+}
+
 /* kinds and in-kind element numbers of the ten TopologicalElements in the order the internal
  * prolongation visits the containers: NN, E3, E2, E1, F1, F2, F3, CC (pr_loops.hpp:82-108) */
 static const int kCelKind[8] = {ORC_TE_NODE, ORC_TE_EDGE, ORC_TE_EDGE, ORC_TE_EDGE,
                                 ORC_TE_FACE, ORC_TE_FACE, ORC_TE_FACE, ORC_TE_CELL};
 static const int kCelEl[8] = {0, 2, 1, 0, 0, 1, 2, 0};
 
+static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind,
+                                int toth_roe);
 int64_t orc_exchange_te_ml(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind) {
+  return exchange_te_impl(m, U, Uc, ncomp, kind, 0);
+}
+/* a face field that registered ProlongateInternalTothAndRoe as its internal prolongation */
+int64_t orc_exchange_te_ml_toth_roe(const OrcMesh *m, double *U, double *Uc, int ncomp) {
+  return exchange_te_impl(m, U, Uc, ncomp, ORC_TE_FACE, 1);
+}
+static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind,
+                                int toth_roe) {
   TeField F;
   F.m = m;
   F.U = U;
@@ -1333,14 +1383,19 @@ int64_t orc_exchange_te_ml(const OrcMesh *m, double *U, double *Uc, int ncomp, i
           for (int q = 0; q < 8; ++q) {
             int ctop[3];
             te_top_offset(kCelKind[q], kCelEl[q], ctop);
-            if (!te_is_submanifold(ftop, ctop)) continue;
+            /* OperationRequired: Toth & Roe fills coarse CELLS only (pr_ops.hpp:390-393) */
+            if (toth_roe ? kCelKind[q] != ORC_TE_CELL : !te_is_submanifold(ftop, ctop)) continue;
             calc_indices_te_general(m, b, n, kCelKind[q], kCelEl[q], IR_RECV, 1, &bx);
             for (int c = 0; c < ncomp; ++c)
               for (int k = bx.s[2]; k <= bx.e[2]; ++k)
                 for (int j = bx.s[1]; j <= bx.e[1]; ++j)
                   for (int i = bx.s[0]; i <= bx.e[0]; ++i)
-                    if (te_active(&bx, k, j, i))
-                      te_prolongate_internal(&F, ftop, ctop, b, el, c, k, j, i);
+                    if (te_active(&bx, k, j, i)) {
+                      if (toth_roe)
+                        te_toth_roe(&F, b, el, c, k, j, i);
+                      else
+                        te_prolongate_internal(&F, ftop, ctop, b, el, c, k, j, i);
+                    }
           }
         }
       }

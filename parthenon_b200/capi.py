@@ -94,7 +94,7 @@ SYMBOLS = [
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
     "pb2_restrict", "pb2_prolongate", "pb2_restrict_te", "pb2_prolongate_te",
-    "pb2_prolongate_internal", "pb2_flxcor_table_create", "pb2_flux_correct",
+    "pb2_prolongate_internal", "pb2_prolongate_toth_roe", "pb2_flxcor_table_create", "pb2_flux_correct",
     "pb2_weighted_sum", "pb2_weighted_sum_ghosts", "pb2_weighted_sum_ghosts_blocks", "pb2_flux_divergence", "pb2_interior_scatter", "pb2_interior_gather",
     "pb2_halo_copy_uniform", "pb2_advection_fluxes", "pb2_copy_flags", "pb2_copy_select",
     "pb2_weighted_sum_blocks", "pb2_flux_divergence_blocks", "pb2_advection_fluxes_blocks",
@@ -153,6 +153,7 @@ def lib():
     L.pb2_restrict_te.argtypes = [vp, vp]
     L.pb2_prolongate_te.argtypes = [vp, C.c_int, vp]
     L.pb2_prolongate_internal.argtypes = [vp, vp]
+    L.pb2_prolongate_toth_roe.argtypes = [vp, vp]
     L.pb2_weighted_sum.argtypes = [vp, vp, C.c_double, C.c_double, vp, i64, vp]
     L.pb2_weighted_sum_ghosts.argtypes = [C.POINTER(PackGeom), vp, vp, C.c_double, C.c_double,
                                           vp, vp]

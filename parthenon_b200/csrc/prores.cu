@@ -313,6 +313,59 @@ __global__ void __launch_bounds__(kPrThreads)
   }
 }
 
+// ProlongateInternalTothAndRoe::Do<DIM, fel, CC> pr_ops.hpp:384-470: the fine faces of element
+// fel inside coarse cell (k, j, i) from the fine faces on the cell's surface, so that the fine
+// divergence equals the coarse one (Toth & Roe 2002).  The region's `fine` points at element F1
+// of the face field (the operator reads all three), ncomp = tensor components per element;
+// ftop names fel.  Written for the x-component, the others by cyclic permutation.
+__global__ void __launch_bounds__(kPrThreads)
+    prolongate_toth_roe_kernel(const pb2_prores_region *__restrict__ regions,
+                               const Chunk *__restrict__ chunks) {
+  const Chunk ch = chunks[blockIdx.x];
+  const pb2_prores_region &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_ALLOCATED)) return;
+  const int DIM = r.ndim;
+  const int el = r.ftop[0] ? 0 : (r.ftop[1] ? 1 : 2);
+  const int g3 = DIM > 2, g2 = DIM > 1;
+  const int64_t sj = r.fine_stride_j, sk = r.fine_stride_k;
+  const double d1 = r.coarse_dx[el], d2 = r.coarse_dx[(el + 1) % 3],
+               d3 = r.coarse_dx[(el + 2) % 3];
+  const double dx2 = d1 * d1, dy2 = d2 * d2, dz2 = d3 * d3;
+  const double vfac = 0.125 * dz2 / (dx2 + dz2), wfac = 0.125 * dy2 / (dx2 + dy2);
+#pragma unroll
+  for (int u = 0; u < kPrPerThread; ++u) {
+    int c, k, j, i;
+    if (!cell_of(r, ch.first_vec + u * kPrThreads + threadIdx.x, c, k, j, i)) continue;
+    const int fi = (i - r.coarse_is[0]) * 2 + r.fine_is[0];
+    const int fj = DIM > 1 ? (j - r.coarse_is[1]) * 2 + r.fine_is[1] : r.fine_is[1];
+    const int fk = DIM > 2 ? (k - r.coarse_is[2]) * 2 + r.fine_is[2] : r.fine_is[2];
+    auto fp = [&](int eidx, int ok, int oj, int oi) -> double * {
+      double *f = r.fine + ((int64_t)((el + eidx) % 3) * r.ncomp + c) * r.fine_stride_c;
+      if (el == 0) return f + (int64_t)(fk + ok * g3) * sk + (int64_t)(fj + oj * g2) * sj + (fi + oi);
+      if (el == 1) return f + (int64_t)(fk + oj * g3) * sk + (int64_t)(fj + oi * g2) * sj + (fi + ok);
+      return f + (int64_t)(fk + oi * g3) * sk + (int64_t)(fj + ok * g2) * sj + (fi + oj);
+    };
+    auto sg = [](int o) { return o == 0 ? -1.0 : 1.0; };
+    double Uxx = 0.0, Vxyz = 0.0, Wxyz = 0.0;
+    for (int v = 0; v <= 1; ++v)
+      for (int w = 0; w <= 2; w += 2)
+        for (int t = 0; t <= 1; ++t) {
+          const double fine2 = *fp(1, v, w, t);
+          const double fine3 = *fp(2, w, v, t);
+          Uxx += sg(t) * sg(w) * (fine2 + fine3);
+          Vxyz += sg(t) * sg(w) * sg(v) * fine2;
+          Wxyz += sg(t) * sg(w) * sg(v) * fine3;
+        }
+    Uxx *= 0.125;
+    Vxyz *= vfac;
+    Wxyz *= wfac;
+    for (int ok = 0; ok <= 1; ++ok)
+      for (int oj = 0; oj <= 1; ++oj)
+        *fp(0, ok, oj, 1) =
+            0.5 * (*fp(0, ok, oj, 0) + *fp(0, ok, oj, 2)) + Uxx + sg(ok) * Vxyz + sg(oj) * Wxyz;
+  }
+}
+
 // Flux correction: RestrictAverage::Do pr_ops.hpp:105-165 with el = F_dir over the fine faces
 // tiling one coarse face, delivered straight to the coarser block's flux array (or a slab).
 // Weights are coords.Volume<F_dir> (the fine block's face area, uniform_cartesian.hpp:36-38);
@@ -502,6 +555,16 @@ int pb2_prolongate_internal(const pb2_bnd_table *table, pb2_stream_t stream) {
   if (table->nchunks == 0) return PB2_OK;
   ProfScope prof(K_PROLONGATE, as_stream(stream));
   prolongate_internal_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
+                               as_stream(stream)>>>(table->d_prores, table->d_chunks);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_prolongate_toth_roe(const pb2_bnd_table *table, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  prolongate_toth_roe_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                                as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
   return PB2_OK;

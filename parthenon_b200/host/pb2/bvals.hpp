@@ -120,6 +120,7 @@ struct BvarsCache {
   pb2_bnd_table *te_restrict_send[2] = {nullptr, nullptr}, *te_restrict_set[2] = {nullptr, nullptr};
   pb2_bnd_table *te_prolongate[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   pb2_bnd_table *te_internal[2] = {nullptr, nullptr};
+  pb2_bnd_table *te_toth_roe[2] = {nullptr, nullptr}; // ProlongateInternalTothAndRoe (faces)
   DeviceBuffer send_slab, recv_slab;
   pb2_event_t packed = nullptr, received = nullptr, sent = nullptr;
   bool nonlocal_in_flight = false;

@@ -38,6 +38,7 @@ struct ProlongateSharedLinear { static constexpr int id = 1; };
 struct ProlongatePiecewiseConstant { static constexpr int id = 2; };
 struct RestrictAverage { static constexpr int id = 0; };
 struct ProlongateInternalAverage { static constexpr int id = 0; };
+struct ProlongateInternalTothAndRoe { static constexpr int id = 1; }; // face fields only
 } // namespace refinement_ops
 
 struct MetadataFlag {
@@ -107,11 +108,13 @@ class Metadata {
   void RegisterRefinementOps() {
     prolongation_op_ = ProlongationOp::id;
     restriction_op_ = RestrictionOp::id;
+    internal_op_ = InternalOp::id;
     refinement_registered_ = true;
   }
   bool IsRefined() const { return refinement_registered_; }
   int ProlongationOp() const { return prolongation_op_; }
   int RestrictionOp() const { return restriction_op_; }
+  int InternalProlongationOp() const { return internal_op_; }
 
  private:
   uint64_t bits_ = 0;
@@ -120,6 +123,7 @@ class Metadata {
   parthenon::Real allocation_threshold_ = 0.0, deallocation_threshold_ = 0.0,
                   default_value_ = 0.0;
   int prolongation_op_ = 0, restriction_op_ = 0; // MinMod / Average (metadata.hpp:337)
+  int internal_op_ = 0;                          // ProlongateInternalAverage
   bool refinement_registered_ = false;
 };
 

@@ -422,7 +422,8 @@ void BvarsCache::Clear() {
     pb2_bnd_table_destroy(te_restrict_send[c]);
     pb2_bnd_table_destroy(te_restrict_set[c]);
     pb2_bnd_table_destroy(te_internal[c]);
-    te_restrict_send[c] = te_restrict_set[c] = te_internal[c] = nullptr;
+    pb2_bnd_table_destroy(te_toth_roe[c]);
+    te_restrict_send[c] = te_restrict_set[c] = te_internal[c] = te_toth_roe[c] = nullptr;
     for (int o = 0; o < 3; ++o) {
       pb2_bnd_table_destroy(te_prolongate[c][o]);
       te_prolongate[c][o] = nullptr;
@@ -655,7 +656,7 @@ void Rebuild(MeshData<Real> *md) {
   // split by whether the neighbour is local so the local / nonlocal task split still works
   if (pm->multilevel) {
     std::vector<pb2_prores_region> rsend[2], rset[2], pro[2][3];
-    std::vector<pb2_prores_region> te_rsend[2], te_rset[2], te_pro[2][3], te_int[2];
+    std::vector<pb2_prores_region> te_rsend[2], te_rset[2], te_pro[2][3], te_int[2], te_tr[2];
     PARTHENON_REQUIRE(all_cell || !pm->adaptive,
                       "non-cell-centred FillGhost fields on adaptive meshes are not supported "
                       "by this build");
@@ -697,12 +698,28 @@ void Rebuild(MeshData<Real> *md) {
                              CalcIndicesTE(nb, pmb.get(), els[e],
                                            IndexRangeType::BoundaryExteriorRecv, true),
                              RecvMask(pm, nb, pmb.get(), els[e]), pm->ndim);
-                for (const TE &cel : containers)
-                  if (is_submanifold(els[e], cel))
-                    AddTeRegions(te_int[cls], *v, pmb.get(), ei, els[e], &cel,
-                                 CalcIndicesTE(nb, pmb.get(), cel,
-                                               IndexRangeType::BoundaryExteriorRecv, true),
-                                 RecvMask(pm, nb, pmb.get(), cel), pm->ndim);
+                if (v->metadata().InternalProlongationOp() == 1) {
+                  // Toth & Roe: coarse cells only, all three face elements are read — the
+                  // regions point at element F1 (pr_ops.hpp:390-393)
+                  PARTHENON_REQUIRE(v->topological_type() == TopologicalType::Face,
+                                    "ProlongateInternalTothAndRoe is defined for face fields");
+                  const TE cc = TE::CC;
+                  const size_t first = te_tr[cls].size();
+                  AddTeRegions(te_tr[cls], *v, pmb.get(), ei, els[e], &cc,
+                               CalcIndicesTE(nb, pmb.get(), cc,
+                                             IndexRangeType::BoundaryExteriorRecv, true),
+                               RecvMask(pm, nb, pmb.get(), cc), pm->ndim);
+                  for (size_t q = first; q < te_tr[cls].size(); ++q)
+                    te_tr[cls][q].fine -=
+                        static_cast<int64_t>(ei) * v->TensorComponents() * v->comp_stride;
+                } else {
+                  for (const TE &cel : containers)
+                    if (is_submanifold(els[e], cel))
+                      AddTeRegions(te_int[cls], *v, pmb.get(), ei, els[e], &cel,
+                                   CalcIndicesTE(nb, pmb.get(), cel,
+                                                 IndexRangeType::BoundaryExteriorRecv, true),
+                                   RecvMask(pm, nb, pmb.get(), cel), pm->ndim);
+                }
               } else if (restricted) {
                 AddTeRegions(te_rset[cls], *v, pmb.get(), ei, els[e], nullptr,
                              CalcIndicesTE(nb, pmb.get(), els[e],
@@ -741,6 +758,8 @@ void Rebuild(MeshData<Real> *md) {
                                         static_cast<int64_t>(te_rset[cls].size())));
       PB2_CHECK(pb2_prores_table_create(&c.te_internal[cls], te_int[cls].data(),
                                         static_cast<int64_t>(te_int[cls].size())));
+      PB2_CHECK(pb2_prores_table_create(&c.te_toth_roe[cls], te_tr[cls].data(),
+                                        static_cast<int64_t>(te_tr[cls].size())));
       for (int o = 0; o < 3; ++o)
         PB2_CHECK(pb2_prores_table_create(&c.te_prolongate[cls][o], te_pro[cls][o].data(),
                                           static_cast<int64_t>(te_pro[cls][o].size())));
@@ -1020,6 +1039,7 @@ TaskStatus ProlongateBounds(std::shared_ptr<MeshData<Real>> &md) {
     if (cls == 0 && !DoesLocal(bt)) continue;
     if (cls == 1 && !DoesNonlocal(bt)) continue;
     PB2_CHECK(pb2_prolongate_internal(c.te_internal[cls], md->stream()));
+    PB2_CHECK(pb2_prolongate_toth_roe(c.te_toth_roe[cls], md->stream()));
   }
   return TaskStatus::complete;
 }

@@ -6,11 +6,17 @@
 namespace tecomm_example {
 using namespace parthenon;
 
-Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &) {
+Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
   Packages_t packages;
   auto pkg = std::make_shared<StateDescriptor>("tecomm");
-  pkg->AddField("face", Metadata({Metadata::Face, Metadata::Independent, Metadata::FillGhost},
-                                 std::vector<int>{2}));
+  Metadata mface({Metadata::Face, Metadata::Independent, Metadata::FillGhost},
+                 std::vector<int>{2});
+  // tecomm/toth_roe = true: the divergence-preserving internal prolongation for the face field
+  if (pin->GetOrAddBoolean("tecomm", "toth_roe", false))
+    mface.RegisterRefinementOps<refinement_ops::ProlongateSharedMinMod,
+                                refinement_ops::RestrictAverage,
+                                refinement_ops::ProlongateInternalTothAndRoe>();
+  pkg->AddField("face", mface);
   pkg->AddField("edge", Metadata({Metadata::Edge, Metadata::Independent, Metadata::FillGhost}));
   pkg->AddField("node", Metadata({Metadata::Node, Metadata::Independent, Metadata::FillGhost}));
   packages.Add(pkg);

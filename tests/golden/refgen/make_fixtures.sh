@@ -221,6 +221,13 @@ run_tecomm tecomm_u32_b8_g2_2d 2 32 8 2
 # node fields (pins the oracle; the GPU path for these is not built yet)
 run_tecomm tecomm_s16_b8_l2_3d 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
 run_tecomm tecomm_s32_b8_l3_2d 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+# the face field with ProlongateInternalTothAndRoe (divergence-preserving internal faces)
+PB2_TOTH_ROE=1 run_tecomm tecomm_s16_b8_l2_3d_tothroe 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
+PB2_TOTH_ROE=1 run_tecomm tecomm_s32_b8_l3_2d_tothroe 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+# only the face field differs from the fixtures above: drop the edge and node arrays
+for n in tecomm_s16_b8_l2_3d_tothroe tecomm_s32_b8_l3_2d_tothroe; do
+  python3 -c "import numpy as np,sys; g=np.load(sys.argv[1]); np.savez_compressed(sys.argv[1], **{k: g[k] for k in ('U_0','meta','bounds')})" "$OUT/$n.npz"
+done
 fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1

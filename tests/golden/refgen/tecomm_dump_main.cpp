@@ -10,6 +10,10 @@
 // (and which entry of it) it came from — in particular which block OWNS each shared face, edge
 // and node (mesh/forest/block_ownership.cpp).  Only this file is ours.
 //
+// With $PB2_TOTH_ROE set the face field registers ProlongateInternalTothAndRoe (the
+// divergence-preserving internal prolongation, pr_ops.hpp:384-470) instead of the default
+// ProlongateInternalAverage.
+//
 // Dump layout: the one of burgers_dump_main.cpp; the "cycle" slot of the file name and header
 // enumerates the fields: 0 = face [3 elements x 2 components], 1 = edge [3 x 1], 2 = node
 // [1 x 1]; ncomp in the header is elements x components, extents are the padded array extents.
@@ -21,6 +25,7 @@
 
 #include "parthenon_manager.hpp"
 #include <parthenon/package.hpp>
+#include <prolong_restrict/pr_ops.hpp>
 
 namespace {
 using namespace parthenon;
@@ -31,8 +36,13 @@ const char *kFields[3] = {"face", "edge", "node"};
 Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
   Packages_t packages;
   auto pkg = std::make_shared<StateDescriptor>("tecomm");
-  pkg->AddField("face", Metadata({Metadata::Face, Metadata::Independent, Metadata::FillGhost},
-                                 std::vector<int>{2}));
+  Metadata mface({Metadata::Face, Metadata::Independent, Metadata::FillGhost},
+                 std::vector<int>{2});
+  if (std::getenv("PB2_TOTH_ROE"))
+    mface.RegisterRefinementOps<parthenon::refinement_ops::ProlongateSharedMinMod,
+                                parthenon::refinement_ops::RestrictAverage,
+                                parthenon::refinement_ops::ProlongateInternalTothAndRoe>();
+  pkg->AddField("face", mface);
   pkg->AddField("edge", Metadata({Metadata::Edge, Metadata::Independent, Metadata::FillGhost}));
   pkg->AddField("node", Metadata({Metadata::Node, Metadata::Independent, Metadata::FillGhost}));
   packages.Add(pkg);

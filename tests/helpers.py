@@ -183,6 +183,9 @@ TECOMM = [("tecomm_u16_b8_g2_3d", 3, 16, 8, 2), ("tecomm_u16_b8_g4_3d", 3, 16, 8
 # statically refined meshes (restriction, shared + internal prolongation): two levels in 3-D,
 # three levels in 2-D
 TECOMM_MULTILEVEL = [("tecomm_s16_b8_l2_3d", 3, 16, 8, 2), ("tecomm_s32_b8_l3_2d", 2, 32, 8, 2)]
+# the same meshes with ProlongateInternalTothAndRoe registered for the face field (U_0 only)
+TECOMM_TOTH_ROE = [("tecomm_s16_b8_l2_3d_tothroe", 3, 16, 8, 2),
+                   ("tecomm_s32_b8_l3_2d_tothroe", 2, 32, 8, 2)]
 # (kind, fixture key, components): kind 1 face, 2 edge, 3 node
 TECOMM_FIELDS = [(1, "U_0", 2), (2, "U_1", 1), (3, "U_2", 1)]
 

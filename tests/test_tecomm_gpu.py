@@ -79,6 +79,24 @@ def test_non_cell_centred_multilevel_exchange_bit_exact(name, ndim, nx, nb, ng, 
         sim.close()
 
 
+@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 2}])
+@pytest.mark.parametrize("name,ndim,nx,nb,ng", H.TECOMM_TOTH_ROE)
+def test_toth_roe_internal_prolongation_bit_exact(name, ndim, nx, nb, ng, extra):
+    """the face field registered with ProlongateInternalTothAndRoe (tecomm/toth_roe = true):
+    pb2_prolongate_toth_roe against the reference's dumps"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+    leaves, nrb = H.leaves_from_bounds(g["bounds"], full(nx), full(nb))
+    ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static")
+    ov["tecomm/toth_roe"] = "true"
+    ov.update(extra or {})
+    sim = host.Simulation(app="tecomm", overrides=ov, leaves=leaves)
+    try:
+        assert np.array_equal(sim.get_field("base", "face"), g["U_0"]), name
+    finally:
+        sim.close()
+
+
 def test_unsupported_combinations_fail_loudly():
     """non-periodic boundaries are not built for non-cell-centred fields:
     the framework must say so instead of exchanging something else"""
