@@ -1215,6 +1215,52 @@ static void te_toth_roe(const TeField *f, int b, int el, int c, int k, int j, in
 #undef SG
 }
 
+/* GenericBC<DIR, SIDE, Outflow | Reflect> for the elements of a face / edge / node field
+ * (boundary_conditions_generic.hpp:174-268; no Metadata::Vector components, so reflections
+ * keep the sign): for element el the reference index along the boundary direction is the
+ * first / last INTERIOR entry of the element (the boundary face itself for an element
+ * displaced in that direction) and the ghost slab covers the element's whole index range in
+ * the other directions (mesh/domain.hpp:183-251) */
+static void te_apply_bcs(const TeField *f, int kind, int coarse) {
+  const OrcMesh *m = f->m;
+  const int *is = coarse ? m->cis : m->is, *ie = coarse ? m->cie : m->ie,
+            *nn = coarse ? m->cn : m->n;
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int face = 0; face < 6; ++face) {
+      const int d = face / 2, inner = (face % 2) == 0;
+      if (d >= m->ndim || m->bc[face] == 0) continue;
+      const long nb_d = nblocks_at(m, blk->loc.level, d);
+      if (inner ? blk->loc.lx[d] != 0 : blk->loc.lx[d] != nb_d - 1) continue;
+      for (int el = 0; el < f->nel; ++el) {
+        int top[3], lo[3], hi[3];
+        te_top_offset(kind, el, top);
+        for (int q = 0; q < 3; ++q) {
+          lo[q] = 0;
+          hi[q] = nn[q] == 1 ? 0 : nn[q] - 1 + top[q];
+        }
+        const int ref = inner ? is[d] : ie[d] + top[d];
+        const int offset = 2 * ref + (inner ? -1 : 1);
+        if (inner)
+          hi[d] = is[d] - 1;
+        else
+          lo[d] = ie[d] + 1 + top[d];
+        for (int c = 0; c < f->ncomp; ++c)
+          for (int k = lo[2]; k <= hi[2]; ++k)
+            for (int j = lo[1]; j <= hi[1]; ++j)
+              for (int i = lo[0]; i <= hi[0]; ++i) {
+                int sidx[3] = {i, j, k};
+                sidx[d] = m->bc[face] == 2 ? offset - sidx[d] : ref;
+                if (coarse)
+                  *te_c(f, b, el, c, k, j, i) = *te_c(f, b, el, c, sidx[2], sidx[1], sidx[0]);
+                else
+                  *te_f(f, b, el, c, k, j, i) = *te_f(f, b, el, c, sidx[2], sidx[1], sidx[0]);
+              }
+      }
+    }
+  }
+}
+
 /* kinds and in-kind element numbers of the ten TopologicalElements in the order the internal
  * prolongation visits the containers: NN, E3, E2, E1, F1, F2, F3, CC (pr_loops.hpp:82-108) */
 static const int kCelKind[8] = {ORC_TE_NODE, ORC_TE_EDGE, ORC_TE_EDGE, ORC_TE_EDGE,
@@ -1357,6 +1403,8 @@ static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int nco
         }
       }
     }
+    /* physical boundaries of the coarse buffers (boundary_communication.cpp:445-449) */
+    te_apply_bcs(&F, kind, 1);
     /* ProlongateBounds: shared elements first ... */
     for (int b = 0; b < m->nblocks; ++b) {
       const Block *blk = &m->blocks[b];
@@ -1401,6 +1449,7 @@ static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int nco
       }
     }
   }
+  te_apply_bcs(&F, kind, 0); /* and of the fine arrays, after the prolongation */
   free(buf);
   free(off);
   free(first);

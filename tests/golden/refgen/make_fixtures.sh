@@ -209,7 +209,7 @@ run_tecomm () { # name ndim nx nb ng [numlevel "regions"]
       $n $lev $a $b $c $e $f $g >> deck.pin
     n=$((n+1))
   done
-  PB2_DUMP_PREFIX="$d/U" "$WORK/tecomm_dump" -i deck.pin > run.log 2>&1
+  PB2_DUMP_PREFIX="$d/U" "$WORK/tecomm_dump" -i deck.pin ${TECOMM_ARGS:-} > run.log 2>&1
   python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
 }
 if [ -z "${SKIP_TECOMM:-}" ]; then
@@ -224,6 +224,13 @@ run_tecomm tecomm_s32_b8_l3_2d 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05
 # the face field with ProlongateInternalTothAndRoe (divergence-preserving internal faces)
 PB2_TOTH_ROE=1 run_tecomm tecomm_s16_b8_l2_3d_tothroe 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
 PB2_TOTH_ROE=1 run_tecomm tecomm_s32_b8_l3_2d_tothroe 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+# physical boundaries of face / edge / node fields: outflow in x1, reflecting in x2, periodic in
+# x3, on a uniform and on the statically refined mesh (coarse-buffer boundaries before the
+# prolongation)
+BCARGS="parthenon/mesh/ix1_bc=outflow parthenon/mesh/ox1_bc=outflow parthenon/mesh/ix2_bc=reflecting parthenon/mesh/ox2_bc=reflecting"
+TECOMM_ARGS="$BCARGS" run_tecomm tecomm_u16_b8_g2_3d_bc 3 16 8 2
+TECOMM_ARGS="$BCARGS" run_tecomm tecomm_s16_b8_l2_3d_bc 3 16 8 2 2 "1:0.05:0.5:0.05:0.5:0.05:0.2"
+TECOMM_ARGS="$BCARGS" run_tecomm tecomm_s32_b8_l3_2d_bc 2 32 8 2 3 "1:-0.5:0.1:-0.2:0.5:0:0 2:-0.5:-0.3:0.3:0.5:0:0"
 # only the face field differs from the fixtures above: drop the edge and node arrays
 for n in tecomm_s16_b8_l2_3d_tothroe tecomm_s32_b8_l3_2d_tothroe; do
   python3 -c "import numpy as np,sys; g=np.load(sys.argv[1]); np.savez_compressed(sys.argv[1], **{k: g[k] for k in ('U_0','meta','bounds')})" "$OUT/$n.npz"

@@ -108,6 +108,7 @@ int main(int argc, char *argv[]) {
   if (const char *p = std::getenv("PB2_DUMP_PREFIX")) g_prefix = p;
   pman.app_input->ProcessPackages = ProcessPackages;
   pman.app_input->ProblemGenerator = ProblemGenerator;
+  pman.app_input->RegisterDefaultReflectingBoundaryConditions(); // "reflecting" in a deck
   auto manager_status = pman.ParthenonInitEnv(argc, argv);
   if (manager_status == ParthenonStatus::complete) {
     pman.ParthenonFinalize();

@@ -186,6 +186,11 @@ TECOMM_MULTILEVEL = [("tecomm_s16_b8_l2_3d", 3, 16, 8, 2), ("tecomm_s32_b8_l3_2d
 # the same meshes with ProlongateInternalTothAndRoe registered for the face field (U_0 only)
 TECOMM_TOTH_ROE = [("tecomm_s16_b8_l2_3d_tothroe", 3, 16, 8, 2),
                    ("tecomm_s32_b8_l3_2d_tothroe", 2, 32, 8, 2)]
+# outflow in x1, reflecting in x2, periodic in x3 (uniform, and refined regions touching the
+# boundaries)
+TECOMM_BC = [("tecomm_u16_b8_g2_3d_bc", 3, 16, 8, 2), ("tecomm_s16_b8_l2_3d_bc", 3, 16, 8, 2),
+             ("tecomm_s32_b8_l3_2d_bc", 2, 32, 8, 2)]
+TECOMM_BC_NAMES = ("outflow", "outflow", "reflecting", "reflecting", "periodic", "periodic")
 # (kind, fixture key, components): kind 1 face, 2 edge, 3 node
 TECOMM_FIELDS = [(1, "U_0", 2), (2, "U_1", 1), (3, "U_2", 1)]
 
