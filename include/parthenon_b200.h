@@ -208,8 +208,7 @@ int pb2_prolongate_toth_roe(const pb2_bnd_table *table, pb2_stream_t stream);
 /* ---------------------------------------------------------------------------------------
  * physical boundary conditions
  * replaces ApplyBoundaryConditionsOnCoarseOrFine (src/bvals/boundary_conditions.cpp:36-58) with
- * the generic outflow / reflect functions (boundary_conditions_generic.hpp:174-268) for
- * cell-centred fields: one launch fills the ghost slabs of every listed (block, face) — the slab
+ * the generic outflow / reflect functions (boundary_conditions_generic.hpp:174-268): one launch fills the ghost slabs of every listed (block, face) — the slab
  * spans the ENTIRE extents of the other directions (mesh/domain.hpp:183-251).  Faces of
  * different directions must be applied in order x1, x2, x3 (one table per direction), because
  * the x2 slab reads x1 ghosts etc.
@@ -226,6 +225,11 @@ typedef struct pb2_bc_region {
   int32_t stride_c;   /* component stride in Reals (row stride n[0], plane stride n[0]*n[1]) */
   uint32_t flip_mask; /* reflect: bit c set => component c is the vector component along the
                          normal (Metadata::Vector, vector_component == DIR) and changes sign */
+  /* face / edge / node elements: one region per topological element, `var` at the element's
+   * first slab component, n = the index range the element USES (cells + 1 where it is
+   * displaced), is / ie = its first / last interior entry along the normal (the boundary face
+   * itself for a displaced element), and the strides of the (padded) array: */
+  int32_t stride_j, stride_k; /* 0: n[0] and n[0] * n[1] */
 } pb2_bc_region;
 int pb2_bc_table_create(pb2_bnd_table **table, const pb2_bc_region *regions, int64_t n);
 int pb2_apply_bcs(const pb2_bnd_table *table, pb2_stream_t stream);

@@ -62,7 +62,8 @@ class FlxCorRegion(C.Structure):
 class BcRegion(C.Structure):
     _fields_ = [("var", C.c_void_p), ("face", C.c_int32), ("type", C.c_int32),
                 ("ncomp", C.c_int32), ("n", C.c_int32 * 3), ("is_", C.c_int32),
-                ("ie", C.c_int32), ("stride_c", C.c_int32), ("flip_mask", C.c_uint32)]
+                ("ie", C.c_int32), ("stride_c", C.c_int32), ("flip_mask", C.c_uint32),
+                ("stride_j", C.c_int32), ("stride_k", C.c_int32)]
 
 
 class PackGeom(C.Structure):

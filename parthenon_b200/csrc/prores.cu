@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(kPrThreads)
   const int lo = inner ? 0 : r.ie + 1;
   ext[d] = inner ? r.is : r.n[d] - (r.ie + 1);
   const uint32_t total = (uint32_t)r.ncomp * ext[0] * ext[1] * ext[2];
-  const int64_t sj = r.n[0], sk = (int64_t)r.n[0] * r.n[1];
+  const int64_t sj = r.stride_j ? r.stride_j : r.n[0],
+                sk = r.stride_k ? r.stride_k : (int64_t)r.n[0] * r.n[1];
 #pragma unroll
   for (int u = 0; u < kPrPerThread; ++u) {
     const uint32_t e = ch.first_vec + u * kPrThreads + threadIdx.x;

@@ -775,9 +775,36 @@ void Rebuild(MeshData<Real> *md) {
         const int d = face / 2;
         for (Variable *v : c.vars) {
           if (!v->IsAllocated(pmb->pack_index)) continue;
-          PARTHENON_REQUIRE(v->topological_type() == TopologicalType::Cell,
-                            "outflow / reflecting boundaries of non-cell-centred fields are not "
-                            "supported by this build (" + v->label() + ")");
+          if (v->topological_type() != TopologicalType::Cell) {
+            // GenericBC per topological element (boundary_conditions_generic.hpp:268-273)
+            PARTHENON_REQUIRE(!v->IsSet(Metadata::Vector),
+                              "Metadata::Vector on non-cell-centred fields is not supported");
+            const std::vector<TE> els = GetTopologicalElements(v->topological_type());
+            const int nc = v->TensorComponents();
+            for (int cf = 0; cf < (pm->multilevel ? 2 : 1); ++cf) {
+              const IndexShape &shape = cf ? pmb->c_cellbounds : pmb->cellbounds;
+              for (size_t e = 0; e < els.size(); ++e) {
+                pb2_bc_region r{};
+                const int64_t cs = cf ? v->ccomp_stride : v->comp_stride;
+                r.var = (cf ? v->coarse() + pmb->pack_index * v->cblock_stride
+                            : v->data() + pmb->pack_index * v->block_stride) +
+                        static_cast<int64_t>(e) * nc * cs;
+                r.face = face;
+                r.type = flag == BoundaryFlag::outflow ? PB2_BC_OUTFLOW : PB2_BC_REFLECT;
+                r.ncomp = nc;
+                for (int q = 0; q < 3; ++q) r.n[q] = shape.Bounds(q, IndexDomain::entire, els[e]).e + 1;
+                const IndexRange b = shape.Bounds(d, IndexDomain::interior, els[e]);
+                r.is = b.s;
+                r.ie = b.e;
+                r.stride_c = static_cast<int32_t>(cs);
+                r.stride_j = cf ? v->cni : v->ni;
+                r.stride_k = cf ? v->cni * v->cnj : v->ni * v->nj;
+                regs[cf][d].push_back(r);
+                c.has_bcs = true;
+              }
+            }
+            continue;
+          }
           for (int cf = 0; cf < (pm->multilevel ? 2 : 1); ++cf) {
             const IndexShape &shape = cf ? pmb->c_cellbounds : pmb->cellbounds;
             pb2_bc_region r{};
