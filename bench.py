@@ -393,7 +393,8 @@ def main():
                          f"({csec:.2f} s per cycle); oracle/pb2_oracle.c with OpenMP"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if not args.nx else METRIC.replace("256^3", f"{args.nx}^3"),
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (analytic burgers initial condition of the reference deck)",
