@@ -61,6 +61,11 @@ std::array<bool, 27> IndexRangeMask(TE el, const std::array<bool, 27> &sender_ow
 // resolved on the host: masked-out entries are neither read nor sent, kernels stay predicate-free.
 std::vector<IndexBox> ActivePieces(const int n[3], const std::array<bool, 27> &mask);
 
+// the C-ABI region that fills the ghost slab of mesh face `face` of one block of a CELL-CENTRED
+// field with a stock condition (type = PB2_BC_OUTFLOW / PB2_BC_REFLECT); user boundary
+// conditions can build their own tables from these
+pb2_bc_region MakeBcRegion(Variable &v, const MeshBlock *pmb, int face, int type, bool coarse);
+
 // one boundary channel as the host sees it (pure topology: testable without a device).  A
 // channel of a face / edge / node field is split into pieces: one per topological element and
 // active sub-box of the ownership mask.

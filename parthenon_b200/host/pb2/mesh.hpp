@@ -10,6 +10,7 @@
 // boundaries, uniform or statically refined leaves with 2:1 nesting.
 #pragma once
 #include <functional>
+#include <map>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -174,7 +175,21 @@ class MeshDataCollection {
 };
 
 // application hooks (application_input.hpp)
+// a user boundary condition (bvals/boundary_conditions.hpp:35 BValFunc) in the batched shape of
+// this framework: it fills the ghost slabs of mesh face `face` for the blocks of the batch that
+// lie on it (MeshBlock::boundary_flag[face] == BoundaryFlag::user), on the fine arrays or, if
+// coarse, on the coarse buffers, by enqueueing its own kernels on md->stream()
+using BValFuncMD = std::function<void(std::shared_ptr<MeshData<Real>> &, bool coarse)>;
+
 struct ApplicationInput {
+  // application_input.hpp:79-83: a deck selects it with <parthenon/mesh> ix1_bc = name
+  void RegisterBoundaryCondition(int face, const std::string &name, BValFuncMD condition) {
+    boundary_conditions_[face][name] = std::move(condition);
+  }
+  void RegisterBoundaryCondition(int face, BValFuncMD condition) {
+    RegisterBoundaryCondition(face, "user", std::move(condition));
+  }
+  std::map<std::string, BValFuncMD> boundary_conditions_[6];
   std::function<Packages_t(std::unique_ptr<ParameterInput> &)> ProcessPackages = nullptr;
   // fills the interior of every block of a MeshData batch on the device
   std::function<void(MeshData<Real> *, ParameterInput *)> MeshProblemGenerator = nullptr;
@@ -193,6 +208,7 @@ class Mesh {
   int ndim = 3;
   RegionSize mesh_size, base_block_size;
   BoundaryFlag mesh_bcs[6];
+  BValFuncMD user_bcs[6]; // set where mesh_bcs[f] == BoundaryFlag::user
   int root_level = 0, current_level = 0;
   int nrbx[3] = {1, 1, 1};
   bool multilevel = false, adaptive = false;

@@ -512,6 +512,33 @@ void AddTeRegions(std::vector<pb2_prores_region> &out, Variable &v, const MeshBl
   }
 }
 
+} // namespace
+
+pb2_bc_region MakeBcRegion(Variable &v, const MeshBlock *pmb, int face, int type, bool coarse) {
+  PARTHENON_REQUIRE(v.topological_type() == TopologicalType::Cell,
+                    "MakeBcRegion describes cell-centred fields");
+  const IndexShape &shape = coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int d = face / 2;
+  pb2_bc_region r{};
+  r.var = coarse ? v.coarse() + pmb->pack_index * v.cblock_stride
+                 : v.data() + pmb->pack_index * v.block_stride;
+  r.face = face;
+  r.type = type;
+  r.ncomp = v.NumComponents();
+  r.n[0] = coarse ? v.cni : v.ni;
+  r.n[1] = coarse ? v.cnj : v.nj;
+  r.n[2] = coarse ? v.cnk : v.nk;
+  const IndexRange b = shape.Bounds(d, IndexDomain::interior);
+  r.is = b.s;
+  r.ie = b.e;
+  r.stride_c = static_cast<int32_t>(coarse ? v.ccomp_stride : v.comp_stride);
+  // Metadata::Vector fields flip the component along the normal
+  // (boundary_conditions_generic.hpp:225-228)
+  r.flip_mask = v.IsSet(Metadata::Vector) && d < r.ncomp ? (1u << d) : 0u;
+  return r;
+}
+
+namespace {
 void Rebuild(MeshData<Real> *md) {
   BvarsCache &c = md->bvars();
   c.Clear();
@@ -806,23 +833,9 @@ void Rebuild(MeshData<Real> *md) {
             continue;
           }
           for (int cf = 0; cf < (pm->multilevel ? 2 : 1); ++cf) {
-            const IndexShape &shape = cf ? pmb->c_cellbounds : pmb->cellbounds;
-            pb2_bc_region r{};
-            r.var = cf ? v->coarse() + pmb->pack_index * v->cblock_stride
-                       : v->data() + pmb->pack_index * v->block_stride;
-            r.face = face;
-            r.type = flag == BoundaryFlag::outflow ? PB2_BC_OUTFLOW : PB2_BC_REFLECT;
-            r.ncomp = v->NumComponents();
-            r.n[0] = cf ? v->cni : v->ni;
-            r.n[1] = cf ? v->cnj : v->nj;
-            r.n[2] = cf ? v->cnk : v->nk;
-            const IndexRange b = shape.Bounds(d, IndexDomain::interior);
-            r.is = b.s;
-            r.ie = b.e;
-            r.stride_c = static_cast<int32_t>(cf ? v->ccomp_stride : v->comp_stride);
-            // Metadata::Vector fields flip the component along the normal
-            // (boundary_conditions_generic.hpp:225-228)
-            r.flip_mask = v->IsSet(Metadata::Vector) && d < r.ncomp ? (1u << d) : 0u;
+            const pb2_bc_region r = MakeBcRegion(
+                *v, pmb.get(), face,
+                flag == BoundaryFlag::outflow ? PB2_BC_OUTFLOW : PB2_BC_REFLECT, cf != 0);
             regs[cf][d].push_back(r);
             c.has_bcs = true;
           }
@@ -1321,11 +1334,15 @@ TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &) {
 TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &md,
                                                    bool coarse) {
   BvarsCache &c = Cache(md);
-  if (!c.has_bcs) return TaskStatus::complete; // periodic: filled by the neighbour exchange
-  // faces in BoundaryFace order; inner and outer slabs of one direction are disjoint, so a
-  // direction is one launch (boundary_conditions.cpp:47-55)
-  for (int d = 0; d < md->GetMeshPointer()->ndim; ++d)
-    PB2_CHECK(pb2_apply_bcs(c.bc[coarse ? 1 : 0][d], md->stream()));
+  Mesh *pm = md->GetMeshPointer();
+  // faces in BoundaryFace order; inner and outer slabs of one direction are disjoint, so the
+  // stock conditions of a direction are one launch (boundary_conditions.cpp:47-55); user
+  // conditions of that direction follow before the next direction reads their ghosts
+  for (int d = 0; d < pm->ndim; ++d) {
+    if (c.has_bcs) PB2_CHECK(pb2_apply_bcs(c.bc[coarse ? 1 : 0][d], md->stream()));
+    for (int f = 2 * d; f < 2 * d + 2; ++f)
+      if (pm->user_bcs[f]) pm->user_bcs[f](md, coarse);
+  }
   return TaskStatus::complete;
 }
 TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md) {

@@ -45,6 +45,35 @@ std::vector<std::string> SplitLines(const char *s) {
   return out;
 }
 
+// Two USER boundary conditions every application created through this interface can select in
+// its deck ("pb2_user_outflow", "pb2_user_reflect"): written the way a downstream code would
+// write its own — a function on a MeshData batch that builds C-ABI regions for the blocks on
+// the face and launches them on the batch's stream.  They do what the stock outflow /
+// reflecting conditions do, which is how the tests check the ApplicationInput::
+// RegisterBoundaryCondition plumbing (call order relative to the stock directions, coarse
+// buffers before prolongation, fine arrays after it).
+void RegisterExampleUserBoundaries(ApplicationInput *app) {
+  for (int face = 0; face < 6; ++face)
+    for (int type : {PB2_BC_OUTFLOW, PB2_BC_REFLECT})
+      app->RegisterBoundaryCondition(
+          face, type == PB2_BC_OUTFLOW ? "pb2_user_outflow" : "pb2_user_reflect",
+          [face, type](std::shared_ptr<MeshData<Real>> &md, bool coarse) {
+            std::vector<pb2_bc_region> regs;
+            for (auto &pmb : md->GetBlockList()) {
+              if (pmb->boundary_flag[face] != BoundaryFlag::user) continue;
+              for (Variable *v : md->GetVariablesByFlag({Metadata::FillGhost}))
+                if (v->IsAllocated(pmb->pack_index))
+                  regs.push_back(MakeBcRegion(*v, pmb.get(), face, type, coarse));
+            }
+            if (regs.empty()) return;
+            pb2_bnd_table *table = nullptr;
+            PB2_CHECK(pb2_bc_table_create(&table, regs.data(), static_cast<int64_t>(regs.size())));
+            PB2_CHECK(pb2_apply_bcs(table, md->stream()));
+            PB2_CHECK(pb2_stream_sync(md->stream())); // the table goes away
+            PB2_CHECK(pb2_bnd_table_destroy(table));
+          });
+}
+
 std::vector<LogicalLocation> Leaves(const int *leaves, int n) {
   std::vector<LogicalLocation> out;
   for (int i = 0; i < n; ++i) {
@@ -111,6 +140,7 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
       s->pman.app_input->ProcessPackages = sparse_advection_example::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = sparse_advection_example::MeshProblemGenerator;
     }
+    RegisterExampleUserBoundaries(s->pman.app_input.get());
     s->pman.ParthenonInitEnvFromString(deck, SplitLines(overrides));
     s->pman.SetRank(rank, nranks, nccl_id);
     s->pman.ParthenonInitPackagesAndMesh(Leaves(leaves, nleaves));

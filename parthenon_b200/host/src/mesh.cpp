@@ -77,12 +77,13 @@ Real SymmetrizedCoordinate(int64_t index, int bloc, int64_t nrange) {
 Real LogicalToActual(Real u, Real xmin, Real xmax) {
   return static_cast<Real>(0.5) * (xmin + xmax) + (u * xmax - u * xmin);
 }
+// anything that is not a stock condition names a user-registered one
+// (ApplicationInput::RegisterBoundaryCondition)
 BoundaryFlag ParseBoundary(const std::string &s) {
   if (s == "periodic") return BoundaryFlag::periodic;
   if (s == "outflow") return BoundaryFlag::outflow;
   if (s == "reflecting" || s == "reflect") return BoundaryFlag::reflect;
-  if (s == "user") return BoundaryFlag::user;
-  PARTHENON_FAIL("unknown boundary condition '" + s + "'");
+  return BoundaryFlag::user;
 }
 } // namespace
 
@@ -356,7 +357,7 @@ std::vector<NeighborBlock> Mesh::FindNeighbors(const LogicalLocation &loc) const
   return mb.neighbors;
 }
 
-Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, int nranks_in,
+Mesh::Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &pkgs, int rank, int nranks_in,
            const std::vector<LogicalLocation> &leaves)
     : my_rank(rank), nranks(nranks_in), packages(pkgs) {
   Globals::my_rank = rank;
@@ -383,10 +384,15 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *, Packages_t &pkgs, int rank, 
     mesh_bcs[2 * d + 1] =
         ParseBoundary(pin->GetOrAddString("parthenon/mesh", bc_names[2 * d + 1], "periodic"));
     if (d < ndim) {
-      for (int f = 2 * d; f < 2 * d + 2; ++f)
-        PARTHENON_REQUIRE(mesh_bcs[f] == BoundaryFlag::periodic || mesh_bcs[f] == BoundaryFlag::outflow ||
-                              mesh_bcs[f] == BoundaryFlag::reflect,
-                          "mesh boundaries must be periodic, outflow or reflecting in this build");
+      for (int f = 2 * d; f < 2 * d + 2; ++f) {
+        if (mesh_bcs[f] != BoundaryFlag::user) continue;
+        const std::string name = pin->GetString("parthenon/mesh", bc_names[f]);
+        const bool have = app_in != nullptr && app_in->boundary_conditions_[f].count(name) > 0;
+        PARTHENON_REQUIRE(have, "boundary condition '" + name + "' of " + bc_names[f] +
+                                    " is neither periodic / outflow / reflecting nor registered "
+                                    "with ApplicationInput::RegisterBoundaryCondition");
+        user_bcs[f] = app_in->boundary_conditions_[f].at(name);
+      }
       PARTHENON_REQUIRE((mesh_bcs[2 * d] == BoundaryFlag::periodic) ==
                             (mesh_bcs[2 * d + 1] == BoundaryFlag::periodic),
                         "a direction is periodic on both faces or on neither");

@@ -51,6 +51,22 @@ def test_advection_cycles_bit_exact_vs_reference_dumps(name, ndim, nx_mesh, nx_b
         assert np.array_equal(sim.get_field("base", "advected"), g[f"U_{c}"]), f"cycle {c}"
 
 
+def test_user_boundary_conditions_on_multilevel_mesh():
+    """user-registered boundary conditions on a three-level mesh whose refined regions touch the
+    boundaries: called on the coarse buffers before the prolongation and on the fine arrays
+    after it, like the stock ones (same reference dump)"""
+    name, ndim, nx_mesh, nx_block, profile, kw, ncyc = [a for a in ADVECTION if a[5].get("bcs")][0]
+    extra = {"parthenon/mesh/ix1_bc": "pb2_user_outflow", "parthenon/mesh/ox1_bc": "pb2_user_outflow",
+             "parthenon/mesh/ix2_bc": "pb2_user_reflect", "parthenon/mesh/ox2_bc": "pb2_user_reflect"}
+    g, sim = advection_sim(name, ndim, nx_mesh, nx_block, profile, kw, extra)
+    sim.pre_execute()
+    assert np.array_equal(sim.get_field("base", "advected"), g["U_0"])
+    for c in range(1, ncyc + 1):
+        sim.cycle()
+        assert np.array_equal(sim.get_field("base", "advected"), g[f"U_{c}"]), f"cycle {c}"
+    sim.close()
+
+
 def test_advection_conserves_total_on_multilevel_mesh():
     """flux correction makes the update conservative across fine-coarse faces: the
     volume-weighted total of the advected field is constant to rounding"""

@@ -173,6 +173,29 @@ def test_physical_boundaries_vs_reference_dumps(fused, math, extra):
             assert np.abs(U - ref).max() / np.abs(ref).max() <= TOL
 
 
+def test_user_boundary_conditions_hook():
+    """ApplicationInput::RegisterBoundaryCondition: the deck names user-registered conditions
+    (written against the C ABI like a downstream code's own, here doing what outflow /
+    reflecting do) instead of the stock ones — same reference dump, bit for bit; mixing user
+    and stock faces keeps the x1 -> x2 -> x3 order"""
+    g = np.load(os.path.join(GOLD, "burgers_u16_b8_s1_weno5_bc.npz"))
+    for ov in ({"parthenon/mesh/ix1_bc": "pb2_user_outflow", "parthenon/mesh/ox1_bc": "pb2_user_outflow",
+                "parthenon/mesh/ix2_bc": "pb2_user_reflect", "parthenon/mesh/ox2_bc": "pb2_user_reflect"},
+               {"parthenon/mesh/ix1_bc": "pb2_user_outflow", "parthenon/mesh/ox1_bc": "outflow",
+                "parthenon/mesh/ix2_bc": "reflecting", "parthenon/mesh/ox2_bc": "pb2_user_reflect"}):
+        sim = host.Simulation(overrides=burgers_overrides(8, 2, 4, 1, "weno5", "strict", True, ov))
+        sim.pre_execute()
+        assert np.array_equal(sim.get_field("base", "U"), g["U_0"])
+        for c in (1, 2, 3):
+            sim.cycle()
+            assert np.array_equal(sim.get_field("base", "U"), g[f"U_{c}"]), f"cycle {c}"
+        sim.close()
+    with pytest.raises(RuntimeError, match="RegisterBoundaryCondition"):
+        host.Simulation(overrides=burgers_overrides(8, 2, 4, 1, "weno5", "strict", True,
+                                                    {"parthenon/mesh/ix1_bc": "no_such_condition",
+                                                     "parthenon/mesh/ox1_bc": "outflow"}))
+
+
 MULTILEVEL = [("burgers_s16_b8_l2_weno5", (16, 16, 16), (8, 8, 8), 3),
               ("burgers_s64_b8_l3_2d_weno5", (64, 64, 1), (8, 8, 1), 2)]
 
