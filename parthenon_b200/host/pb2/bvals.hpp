@@ -158,6 +158,14 @@ struct BvarsCache {
   bool sparse = false;
   DeviceBuffer sparse_flags;
   std::vector<int32_t> sparse_flags_h;
+  // ... and per inter-device channel: the pack kernel raises int32 flags, they travel as one
+  // Real per channel in their own small slab (same per-peer order as the data slab, so the
+  // offsets need no handshake either) and come back as the int32 data flags of the unpack
+  DeviceBuffer send_flags, recv_flags;           // int32 per send / recv channel
+  DeviceBuffer send_flag_slab, recv_flag_slab;   // Real per send / recv channel
+  std::vector<int32_t> send_flags_h, recv_flags_h;
+  std::vector<Real> flag_slab_h;
+  std::vector<int64_t> send_flag_off, recv_flag_off; // [npeers + 1] channel counts per peer
 
   // flux correction at fine-coarse faces (flxcor_send / flxcor_recv), built on first use:
   // fused restrict+deliver for same-device channels, restrict-into-slab + unpack for the rest

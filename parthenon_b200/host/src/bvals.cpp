@@ -559,7 +559,6 @@ void Rebuild(MeshData<Real> *md) {
   c.sparse = false;
   for (Variable *v : c.vars) c.sparse = c.sparse || (v->metadata().IsSparse() && pm->sparse_config.enabled);
   if (c.sparse) {
-    PARTHENON_REQUIRE(!slabs, "sparse fields across devices are not supported by this build");
     PARTHENON_REQUIRE(!pm->multilevel, "sparse fields on multilevel meshes are not supported by this build");
     PARTHENON_REQUIRE(pm->DefaultNumPartitions() == 1,
                       "sparse fields need one MeshData per rank (parthenon/mesh/pack_size=-1)");
@@ -672,11 +671,53 @@ void Rebuild(MeshData<Real> *md) {
   std::vector<pb2_bnd_region> packs, unpacks;
   for (const Channel &ch : c.plan.send) packs.push_back(bnd(ch, true));
   for (const Channel &ch : c.plan.recv) unpacks.push_back(bnd(ch, false));
+  if (c.sparse) {
+    // every inter-device channel gets a flag slot; BndInfo::allocated is this side's own field
+    // (bnd_info.cpp:277): an unallocated sender packs nothing and its flag stays 0 (a null
+    // message), an unallocated receiver is skipped by the unpack
+    for (size_t i = 0; i < packs.size(); ++i) {
+      const Channel &ch = c.plan.send[i];
+      const MeshBlock *pmb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
+      packs[i].flag_slot = static_cast<int32_t>(i);
+      packs[i].status = c.vars[ch.var]->IsAllocated(pmb->pack_index) ? PB2_REGION_ALLOCATED : 0u;
+    }
+    for (size_t i = 0; i < unpacks.size(); ++i) {
+      const Channel &ch = c.plan.recv[i];
+      const MeshBlock *pmb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
+      unpacks[i].flag_slot = static_cast<int32_t>(i);
+      unpacks[i].status = c.vars[ch.var]->IsAllocated(pmb->pack_index) ? PB2_REGION_ALLOCATED : 0u;
+    }
+    auto counts = [&](const std::vector<Channel> &chs, bool send, std::vector<int64_t> &off) {
+      const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
+      off.assign(c.plan.npeers + 1, 0);
+      for (const Channel &ch : chs) {
+        const int seg = V > 1 ? ch.sender_vrank * V + ch.receiver_vrank
+                              : (send ? ch.receiver_rank : ch.sender_rank);
+        off[seg + 1]++;
+      }
+      for (int p = 0; p < c.plan.npeers; ++p) off[p + 1] += off[p];
+    };
+    counts(c.plan.send, true, c.send_flag_off);
+    counts(c.plan.recv, false, c.recv_flag_off);
+    auto ensure = [&](DeviceBuffer &b, size_t bytes) {
+      if (b.bytes() != std::max<size_t>(bytes, 8)) b.Allocate(std::max<size_t>(bytes, 8), md->stream());
+    };
+    ensure(c.send_flags, sizeof(int32_t) * packs.size());
+    ensure(c.recv_flags, sizeof(int32_t) * unpacks.size());
+    ensure(c.send_flag_slab, sizeof(Real) * packs.size());
+    ensure(c.recv_flag_slab, sizeof(Real) * unpacks.size());
+    c.send_flags_h.assign(packs.size(), 0);
+    c.recv_flags_h.assign(unpacks.size(), 0);
+  }
   PB2_CHECK(pb2_bnd_table_create(&c.pack, packs.data(), static_cast<int64_t>(packs.size())));
   PB2_CHECK(pb2_bnd_table_create(&c.unpack, unpacks.data(), static_cast<int64_t>(unpacks.size())));
-  if (c.plan.send_elements > 0)
+  // slabs of an unchanged size survive a rebuild: allocate-on-receive rebuilds the tables
+  // between the arrival of a slab and its unpack
+  if (c.plan.send_elements > 0 &&
+      c.send_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.send_elements))
     c.send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.send_elements), md->stream());
-  if (c.plan.recv_elements > 0)
+  if (c.plan.recv_elements > 0 &&
+      c.recv_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.recv_elements))
     c.recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.recv_elements), md->stream());
 
   // restriction / prolongation regions (ProResInfo::GetSend / GetSet, bnd_info.cpp:387-448),
@@ -960,7 +1001,20 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     // the previous exchange must have left the slabs: its sends (same stream order on cs, or
     // the `sent` event) and its unpack (`unpacked`, recorded on the compute stream)
     if (c.nonlocal_in_flight && ps == st) PB2_CHECK(pb2_stream_wait_event(st, c.sent));
-    PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), nullptr, ps));
+    if (c.sparse) {
+      // which messages are null (:95-157): flags out of the pack, as Reals into the flag slab
+      PB2_CHECK(pb2_memset(c.send_flags.get(), 0, sizeof(int32_t) * c.send_flags_h.size(), ps));
+      PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), c.send_flags.get<int32_t>(), ps));
+      PB2_CHECK(pb2_memcpy_d2h(c.send_flags_h.data(), c.send_flags.get(),
+                               sizeof(int32_t) * c.send_flags_h.size(), ps));
+      PB2_CHECK(pb2_stream_sync(ps));
+      c.flag_slab_h.assign(c.send_flags_h.begin(), c.send_flags_h.end());
+      PB2_CHECK(pb2_memcpy_h2d(c.send_flag_slab.get(), c.flag_slab_h.data(),
+                               sizeof(Real) * c.flag_slab_h.size(), ps));
+      PB2_CHECK(pb2_stream_sync(ps)); // flag_slab_h is reused by the receive side
+    } else {
+      PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), nullptr, ps));
+    }
     if (ps == st) {
       PB2_CHECK(pb2_event_record(c.packed, st));
       PB2_CHECK(pb2_stream_wait_event(cs, c.packed));
@@ -970,10 +1024,17 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
       PARTHENON_REQUIRE(pm->comm != nullptr, "multi-rank mesh without a communicator");
       PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_slab.get<Real>(), c.plan.send_off.data(),
                                   c.recv_slab.get<Real>(), c.plan.recv_off.data(), cs));
+      if (c.sparse)
+        PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_flag_slab.get<Real>(),
+                                    c.send_flag_off.data(), c.recv_flag_slab.get<Real>(),
+                                    c.recv_flag_off.data(), cs));
     } else {
       // virtual ranks on one device: the "wire" is a device-to-device copy of the slab
       PB2_CHECK(pb2_memcpy_d2d(c.recv_slab.get(), c.send_slab.get(),
                                sizeof(Real) * static_cast<size_t>(c.plan.send_elements), cs));
+      if (c.sparse)
+        PB2_CHECK(pb2_memcpy_d2d(c.recv_flag_slab.get(), c.send_flag_slab.get(),
+                                 sizeof(Real) * c.send_flags_h.size(), cs));
     }
     PB2_CHECK(pb2_event_record(c.received, cs));
     PB2_CHECK(pb2_event_record(c.sent, cs));
@@ -1012,7 +1073,28 @@ TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
       }
     }
   }
-  // nonlocal: completion is a stream-side event wait in SetBounds — no host polling
+  // nonlocal: completion is a stream-side event wait in SetBounds — no host polling; only
+  // sparse fields need the host: which messages were null decides what gets allocated
+  if (DoesNonlocal(bt) && c.sparse && !c.recv_flags_h.empty()) {
+    PB2_CHECK(pb2_event_sync(c.received));
+    c.flag_slab_h.resize(c.recv_flags_h.size());
+    PB2_CHECK(pb2_memcpy_d2h(c.flag_slab_h.data(), c.recv_flag_slab.get(),
+                             sizeof(Real) * c.flag_slab_h.size(), md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+    for (size_t i = 0; i < c.plan.recv.size(); ++i) {
+      const Channel &ch = c.plan.recv[i];
+      Variable &rv = *c.vars[ch.var];
+      c.recv_flags_h[i] = c.flag_slab_h[i] != 0.0 ? 1 : 0;
+      if (!rv.metadata().IsSparse() || !c.recv_flags_h[i]) continue;
+      const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
+      if (!rv.IsAllocated(rb->pack_index)) pm->AllocateSparse(rv.label(), rb->lid);
+    }
+    // (an allocation bumps alloc_generation: the next Cache() rebuilds the tables; the flag
+    // buffers and slabs keep their size and survive)
+    PB2_CHECK(pb2_memcpy_h2d(c.recv_flags.get(), c.recv_flags_h.data(),
+                             sizeof(int32_t) * c.recv_flags_h.size(), md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+  }
   return TaskStatus::complete;
 }
 
@@ -1047,7 +1129,8 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
   }
   if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
     PB2_CHECK(pb2_stream_wait_event(st, c.received));
-    PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(), nullptr, st));
+    PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(),
+                         c.sparse ? c.recv_flags.get<int32_t>() : nullptr, st));
     PB2_CHECK(pb2_event_record(c.unpacked, st));
     c.unpacked_valid = true;
     c.elements_nonlocal = c.plan.recv_elements;

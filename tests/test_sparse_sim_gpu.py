@@ -24,10 +24,14 @@ def sparse_state(sim):
     return np.stack(out, axis=1)
 
 
+@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 2}, {"pb2/virtual_ranks": 3}])
 @pytest.mark.parametrize("name,kw,ncyc", SPARSE)
-def test_sparse_advection_bit_exact_vs_reference_dumps(name, kw, ncyc):
+def test_sparse_advection_bit_exact_vs_reference_dumps(name, kw, ncyc, extra):
+    """extra = pb2/virtual_ranks: the blocks of the one GPU are split into groups whose channels
+    take the inter-device path — pack with null-message flags, flags shipped in their own slab,
+    allocate-on-receive from the received flags, unpack with data flags"""
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    ov = {}
+    ov = dict(extra or {})
     for k, key in (("alloc_threshold", "alloc_threshold"), ("dealloc_threshold", "dealloc_threshold"),
                    ("dealloc_count", "dealloc_count")):
         if k in kw:
@@ -63,6 +67,7 @@ def test_sparse_advection_3d_matches_oracle():
     ov = {"parthenon/mesh/nx1": 32, "parthenon/mesh/nx2": 32, "parthenon/mesh/nx3": 32,
           "parthenon/meshblock/nx3": 8, "parthenon/sparse/alloc_threshold": 1e-2,
           "parthenon/sparse/dealloc_threshold": 5e-3, "parthenon/sparse/dealloc_count": 2}
+    ov["pb2/virtual_ranks"] = 2  # half of the channels through the slab path
     sim = host.Simulation(app="sparse_advection", overrides=ov)
     sim.pre_execute()
     assert sim.dt == S.dt
