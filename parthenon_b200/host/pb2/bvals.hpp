@@ -108,6 +108,7 @@ struct BvarsCache {
   void Clear();
   uint64_t built_generation = 0;
   ExchangePlan plan;
+  bool plan_built = false;
   std::vector<Variable *> vars;
   pb2_bnd_table *copy_local = nullptr;
   // uniform meshes, dense fields, one batch per device: local channels need no region table —

@@ -550,7 +550,13 @@ void Rebuild(MeshData<Real> *md) {
     pvars.push_back(PlanVar{v->TensorComponents(), v->topological_type()});
     all_cell = all_cell && v->topological_type() == TopologicalType::Cell;
   }
-  c.plan = BuildExchangePlan(pm, md->GetBlockList(), pvars);
+  // the plan is pure topology: the block list and the FillGhost fields of a MeshData never
+  // change during its life (a remesh builds new MeshData), so a rebuild after a sparse
+  // (de)allocation reuses it — only region statuses and tables change
+  if (!c.plan_built) {
+    c.plan = BuildExchangePlan(pm, md->GetBlockList(), pvars);
+    c.plan_built = true;
+  }
   const bool slabs = c.plan.send_elements > 0 || c.plan.recv_elements > 0;
   PARTHENON_REQUIRE(!slabs || pm->DefaultNumPartitions() == 1,
                     "inter-device halos need one MeshData per rank (parthenon/mesh/pack_size=-1)");
@@ -606,17 +612,22 @@ void Rebuild(MeshData<Real> *md) {
     r.threshold = 0.0;
     r.default_value = rv.metadata().GetDefaultValue();
     if (c.sparse && rv.metadata().IsSparse()) {
-      // BndInfo::allocated of the sender / the receiver (bnd_info.cpp:277, :290-292)
-      r.flag_slot = static_cast<int32_t>(copies.size());
-      r.status = (sv.IsAllocated(sb->pack_index) ? PB2_REGION_ALLOCATED : 0u) |
-                 (rv.IsAllocated(rb->pack_index) ? 0u : PB2_REGION_DST_UNALLOCATED);
+      // BndInfo::allocated of the sender / the receiver (bnd_info.cpp:277, :290-292).  Flags are
+      // indexed by CHANNEL; a channel with neither side allocated can neither carry data nor
+      // need a default fill, so it gets no region at all (its flag stays 0): with a few percent
+      // of the fields allocated the launches shrink by the same factor
+      const bool src_alloc = sv.IsAllocated(sb->pack_index), dst_alloc = rv.IsAllocated(rb->pack_index);
+      if (!src_alloc && !dst_alloc) continue;
+      r.flag_slot = static_cast<int32_t>(&ch - c.plan.local.data());
+      r.status = (src_alloc ? PB2_REGION_ALLOCATED : 0u) |
+                 (dst_alloc ? 0u : PB2_REGION_DST_UNALLOCATED);
       r.threshold = rv.metadata().GetAllocationThreshold();
     }
     copies.push_back(r);
   }
   if (c.sparse && !c.sparse_flags) {
-    c.sparse_flags.Allocate(sizeof(int32_t) * std::max<size_t>(copies.size(), 1), md->stream());
-    c.sparse_flags_h.assign(copies.size(), 0);
+    c.sparse_flags.Allocate(sizeof(int32_t) * std::max<size_t>(c.plan.local.size(), 1), md->stream());
+    c.sparse_flags_h.assign(c.plan.local.size(), 0);
   }
   PB2_CHECK(pb2_copy_table_create(&c.copy_local, copies.data(), static_cast<int64_t>(copies.size())));
 
