@@ -280,6 +280,12 @@ typedef struct pb2_pack_geom {
   int32_t ng;      /* ghost width (0 in symmetry directions) */
   int64_t block_stride; /* Reals between blocks; component stride is ni*nj*nk */
   const double *dx;     /* device [nblocks][3] cell widths */
+  /* optional compact list for the block-masked (`_blocks`) entry points: if block_list != NULL
+   * they launch over its nlist entries (device int32 block indices, e.g. the blocks on which a
+   * sparse field is allocated) instead of over all nblocks blocks; a mask, if given as well, is
+   * still honoured.  Zero / NULL elsewhere. */
+  const int32_t *block_list;
+  int32_t nlist;
 } pb2_pack_geom;
 
 /* Block-masked forms for SPARSE fields: block b of the batch is processed only if

@@ -69,7 +69,7 @@ class BcRegion(C.Structure):
 class PackGeom(C.Structure):
     _fields_ = [("nblocks", C.c_int32), ("ncomp", C.c_int32), ("ndim", C.c_int32),
                 ("nx", C.c_int32 * 3), ("ng", C.c_int32), ("block_stride", C.c_int64),
-                ("dx", C.c_void_p)]
+                ("dx", C.c_void_p), ("block_list", C.c_void_p), ("nlist", C.c_int32)]
 
 
 class BurgersArgs(C.Structure):

@@ -72,10 +72,11 @@ __global__ void __launch_bounds__(256)
     flux_div_kernel(const DivGeom g, const double *__restrict__ fx,
                     const double *__restrict__ fy, const double *__restrict__ fz,
                     const double *__restrict__ dx, double *__restrict__ dudt,
-                    const int32_t *__restrict__ mask) {
+                    const int32_t *__restrict__ mask, const int32_t *__restrict__ list) {
   const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
   const int ctas_per_block = (ncell + 255) / 256;
-  const int b = blockIdx.x / ctas_per_block;
+  const int slot = blockIdx.x / ctas_per_block;
+  const int b = list != nullptr ? list[slot] : slot;
   if (mask != nullptr && mask[b] == 0) return;
   const int t = (blockIdx.x % ctas_per_block) * 256 + threadIdx.x;
   if (t >= ncell) return;
@@ -99,8 +100,10 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     weighted_sum_blocks_kernel(const double *x, const double *y, double w1, double w2, double *z,
                                int64_t block_stride, int64_t per_block,
-                               const int32_t *__restrict__ mask, int ctas_per_block) {
-  const int b = blockIdx.x / ctas_per_block;
+                               const int32_t *__restrict__ mask, int ctas_per_block,
+                               const int32_t *__restrict__ list) {
+  const int slot = blockIdx.x / ctas_per_block;
+  const int b = list != nullptr ? list[slot] : slot;
   if (mask != nullptr && mask[b] == 0) return;
   const int64_t o = (int64_t)b * block_stride;
   for (int64_t i = (int64_t)(blockIdx.x % ctas_per_block) * 256 + threadIdx.x; i < per_block;
@@ -203,7 +206,8 @@ __global__ void __launch_bounds__(256)
     advection_flux_kernel(const DivGeom g, const double *__restrict__ u,
                           double *__restrict__ fx, double *__restrict__ fy,
                           double *__restrict__ fz, double vx, double vy, double vz,
-                          int64_t total, const int32_t *__restrict__ mask) {
+                          int64_t total, const int32_t *__restrict__ mask,
+                          const int32_t *__restrict__ list) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int e0 = g.nx[0] + 1, e1 = g.nx[1] + (g.ndim > 1), e2 = g.nx[2] + (g.ndim > 2);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -215,7 +219,8 @@ __global__ void __launch_bounds__(256)
     const int dk = (int)(t % e2);
     t /= e2;
     const int c = (int)(t % g.ncomp);
-    const int64_t b = t / g.ncomp;
+    const int64_t slot = t / g.ncomp;
+    const int64_t b = list != nullptr ? list[slot] : slot;
     if (mask != nullptr && mask[b] == 0) continue;
     const int64_t p = b * g.sb + c * g.sc + (int64_t)(g.is[2] + dk) * g.sk +
                       (int64_t)(g.is[1] + dj) * g.sj + (g.is[0] + di);
@@ -375,13 +380,14 @@ int pb2_advection_fluxes_blocks(const pb2_pack_geom *pg, const double *u, double
   g.sk = (int64_t)g.n[0] * g.n[1];
   g.sc = g.sk * g.n[2];
   g.sb = pg->block_stride;
-  const int64_t total = (int64_t)g.nblocks * g.ncomp * (g.nx[0] + 1) *
-                        (g.nx[1] + (g.ndim > 1)) * (g.nx[2] + (g.ndim > 2));
+  const int64_t total = (int64_t)(pg->block_list ? pg->nlist : g.nblocks) * g.ncomp *
+                        (g.nx[0] + 1) * (g.nx[1] + (g.ndim > 1)) * (g.nx[2] + (g.ndim > 2));
   if (total == 0) return PB2_OK;
   const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
   ProfScope prof(K_ADVECTION_FLUX, as_stream(stream));
   advection_flux_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, u, flux[0], flux[1], flux[2],
-                                                            v[0], v[1], v[2], total, block_mask);
+                                                            v[0], v[1], v[2], total, block_mask,
+                                                            pg->block_list);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }
@@ -401,8 +407,10 @@ int pb2_weighted_sum_blocks(const pb2_pack_geom *pg, const double *x, const doub
   for (int d = 0; d < 3; ++d) per_block *= d >= pg->ndim ? 1 : pg->nx[d] + 2 * pg->ng;
   const int cpb = static_cast<int>(std::min<int64_t>((per_block + 255) / 256, 64));
   ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
-  weighted_sum_blocks_kernel<<<pg->nblocks * cpb, 256, 0, as_stream(stream)>>>(
-      x, y, w1, w2, z, pg->block_stride, per_block, block_mask, cpb);
+  const int nslots = pg->block_list ? pg->nlist : pg->nblocks;
+  if (nslots == 0) return PB2_OK;
+  weighted_sum_blocks_kernel<<<nslots * cpb, 256, 0, as_stream(stream)>>>(
+      x, y, w1, w2, z, pg->block_stride, per_block, block_mask, cpb, pg->block_list);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }
@@ -485,11 +493,11 @@ int pb2_flux_divergence_blocks(const pb2_pack_geom *pg, const double *const flux
   g.sc = g.sk * g.n[2];
   g.sb = pg->block_stride;
   const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
-  const int ctas = g.nblocks * ((ncell + 255) / 256);
+  const int ctas = (pg->block_list ? pg->nlist : g.nblocks) * ((ncell + 255) / 256);
   if (ctas == 0) return PB2_OK;
   ProfScope prof(K_FLUX_DIV, as_stream(stream));
   flux_div_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, flux[0], flux[1], flux[2], pg->dx,
-                                                      dudt, block_mask);
+                                                      dudt, block_mask, pg->block_list);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

@@ -64,6 +64,9 @@ class Variable {
   void AllocateBlock(int b);
   // device int32 [nblocks] allocation mask for the block-masked kernels; NULL for dense fields
   const int32_t *DeviceMask();
+  // device int32 list of the allocated blocks (and its length) for the same kernels: they
+  // launch over the list instead of over every block; NULL / 0 for dense fields
+  const int32_t *DeviceList(int32_t *n);
   const std::vector<uint8_t> &AllocationStatus() const { return allocated_; }
   int dealloc_count(int b) const { return dealloc_count_[b]; }
   int &dealloc_count(int b) { return dealloc_count_[b]; }
@@ -81,6 +84,8 @@ class Variable {
   std::vector<int> dealloc_count_;
   DeviceBuffer mask_;
   bool mask_dirty_ = true;
+  int32_t nlist_ = 0;
+  void UploadAllocation();
 };
 
 // what md->PackVariables(names) returns: the selected fields of every block, addressable

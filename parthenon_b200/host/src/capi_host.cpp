@@ -514,7 +514,7 @@ struct LaneCtx {
   pb2h_sim::Lane *lane;
   Variable *v;
   std::shared_ptr<MeshData<Real>> md;
-  pb2_pack_geom g;
+  pb2_pack_geom g{};
   int64_t n;
 };
 LaneCtx GetLane(pb2h_sim *sim, const char *container, const char *field, int lane,

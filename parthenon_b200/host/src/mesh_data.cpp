@@ -99,16 +99,33 @@ void Variable::AllocateBlock(int b) {
   for (auto &f : flux_) zero(f, block_stride);
 }
 
+void Variable::UploadAllocation() {
+  if (!mask_dirty_) return;
+  if (!mask_) mask_.Allocate(sizeof(int32_t) * 2 * std::max(nblocks_, 1), stream_);
+  // [0, nblocks): the mask; [nblocks, 2 nblocks): the indices of the allocated blocks
+  std::vector<int32_t> h(2 * static_cast<size_t>(std::max(nblocks_, 1)), 0);
+  nlist_ = 0;
+  for (int b = 0; b < nblocks_; ++b) {
+    h[b] = allocated_[b];
+    if (allocated_[b]) h[nblocks_ + nlist_++] = b;
+  }
+  PB2_CHECK(pb2_memcpy_h2d(mask_.get(), h.data(), sizeof(int32_t) * h.size(), stream_));
+  PB2_CHECK(pb2_stream_sync(stream_)); // h goes out of scope
+  mask_dirty_ = false;
+}
+
 const int32_t *Variable::DeviceMask() {
   if (!m_.IsSparse()) return nullptr;
-  if (mask_dirty_) {
-    if (!mask_) mask_.Allocate(sizeof(int32_t) * std::max(nblocks_, 1), stream_);
-    std::vector<int32_t> h(allocated_.begin(), allocated_.end());
-    PB2_CHECK(pb2_memcpy_h2d(mask_.get(), h.data(), sizeof(int32_t) * h.size(), stream_));
-    PB2_CHECK(pb2_stream_sync(stream_)); // h goes out of scope
-    mask_dirty_ = false;
-  }
+  UploadAllocation();
   return mask_.get<int32_t>();
+}
+
+const int32_t *Variable::DeviceList(int32_t *n) {
+  *n = 0;
+  if (!m_.IsSparse()) return nullptr;
+  UploadAllocation();
+  *n = nlist_;
+  return mask_.get<int32_t>() + nblocks_;
 }
 
 Real *const *VariablePack::DevicePtrs(pb2_stream_t stream) {
@@ -256,7 +273,7 @@ const Real *MeshData<T>::DeviceXmin() {
 
 template <typename T>
 pb2_pack_geom MeshData<T>::Geometry(Variable &v) {
-  pb2_pack_geom g;
+  pb2_pack_geom g{};
   g.nblocks = NumBlocks();
   g.ncomp = v.NumComponents();
   g.ndim = pmesh_->ndim;
@@ -264,6 +281,8 @@ pb2_pack_geom MeshData<T>::Geometry(Variable &v) {
   g.ng = Globals::nghost;
   g.block_stride = v.block_stride;
   g.dx = DeviceDx();
+  // sparse fields: the block-masked kernels launch over the allocated blocks only
+  g.block_list = v.DeviceList(&g.nlist);
   return g;
 }
 

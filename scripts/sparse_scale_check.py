@@ -71,6 +71,25 @@ def main():
           f"{pairs * zones / wall:.3e} allocated-field zone-cycles/s, "
           f"{ncyc * nblocks * zones / wall:.3e} mesh zone-cycles/s "
           f"({1e3 * wall / ncyc:.2f} ms per cycle)", flush=True)
+    # where the time goes: device time per kernel class over a few more cycles
+    from parthenon_b200 import capi
+    capi.profile(reset=True)
+    capi.profile(enable=True)
+    t0 = time.time()
+    nprof = 20
+    for c in range(nprof):
+        sim.cycle()
+    sim.sync()
+    wallp = time.time() - t0
+    capi.profile(enable=False)
+    prof = capi.profile()
+    prof = {k: {"ms": v[0], "launches": v[1]} for k, v in prof.items()}
+    tot = sum(v["ms"] for v in prof.values())
+    print(f"profile of {nprof} cycles ({1e3 * wallp / nprof:.2f} ms per cycle with event brackets): "
+          f"device time {tot / nprof:.3f} ms per cycle: " +
+          ", ".join(f"{k} {v['ms'] / nprof:.3f} ms / {v['launches'] // nprof} launches"
+                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if v["launches"]),
+          flush=True)
     sim.close()
     if not ok:
         raise SystemExit("sparse scale check FAILED")
