@@ -79,7 +79,8 @@ int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t
                       int64_t *seg_off);
 /* the same for one field of topological type tt (0 cell, 1 face, 2 edge, 3 node) with `ncomp`
  * tensor components, index boxes included: rows of 18 int64 [sender_gid, receiver_gid,
- * offset_index, piece, comp0, ncomp, send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, 0].
+ * offset_index, piece, comp0, ncomp, send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer,
+ * coarse flags (bit 0: the sender reads its coarse buffer, bit 1: the receiver writes its)].
  * Channels of non-cell-centred fields come in pieces: one per topological element and active
  * sub-box of the sender's ownership mask (block_ownership.cpp:85-140). */
 int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t *rows,

@@ -65,6 +65,8 @@ def lib():
         L.orc_exchange_te.restype = C.c_int64
         L.orc_exchange_te_ml.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.orc_exchange_te_ml.restype = C.c_int64
+        L.orc_calc_indices_te_general.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.c_int, C.c_int, ip, ip, ip]
         L.orc_exchange_te_ml_toth_roe.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_exchange_te_ml_toth_roe.restype = C.c_int64
         L.orc_flux_correct.restype = C.c_int64
@@ -266,6 +268,15 @@ class Mesh:
         e = np.zeros(3, dtype=np.int32)
         lib().orc_calc_indices_te(self.h, b, n, kind, el, ir_type, _ip(s), _ip(e))
         return tuple(int(x) for x in s), tuple(int(x) for x in e)
+
+    def calc_indices_te_general(self, b, n, kind, el, ir_type, prores=False):
+        """(s, e, mask[k][j][i]) of region (b, n), element (kind, el), on any mesh"""
+        s = np.zeros(3, dtype=np.int32)
+        e = np.zeros(3, dtype=np.int32)
+        mk = np.zeros(27, dtype=np.int32)
+        lib().orc_calc_indices_te_general(self.h, b, n, kind, el, ir_type, int(prores), _ip(s),
+                                          _ip(e), _ip(mk))
+        return tuple(int(x) for x in s), tuple(int(x) for x in e), mk.reshape(3, 3, 3)
 
     def te_recv_mask(self, b, n, kind, el):
         """[k][j][i] over (-1, 0, 1): which entries of the receive box are written"""

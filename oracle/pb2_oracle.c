@@ -1272,6 +1272,17 @@ static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int nco
 int64_t orc_exchange_te_ml(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind) {
   return exchange_te_impl(m, U, Uc, ncomp, kind, 0);
 }
+/* the general index box and receive mask of region (b, n), element (kind, el), for tests */
+void orc_calc_indices_te_general(const OrcMesh *m, int b, int n, int kind, int el, int ir_type,
+                                 int prores, int s[3], int e[3], int mask[27]) {
+  TeBox bx;
+  calc_indices_te_general(m, b, n, kind, el, ir_type, prores, &bx);
+  for (int d = 0; d < 3; ++d) {
+    s[d] = bx.s[d];
+    e[d] = bx.e[d];
+  }
+  for (int q = 0; q < 27; ++q) mask[q] = bx.mask[q];
+}
 /* a face field that registered ProlongateInternalTothAndRoe as its internal prolongation */
 int64_t orc_exchange_te_ml_toth_roe(const OrcMesh *m, double *U, double *Uc, int ncomp) {
   return exchange_te_impl(m, U, Uc, ncomp, ORC_TE_FACE, 1);

@@ -301,7 +301,7 @@ class _Base:
     def plan_boxes(self, ncomp, tt, kind):
         """channels (pieces) of one field of topological type tt (0 cell, 1 face, 2 edge, 3 node)
         with their index boxes: rows[n, 18] = [sender_gid, receiver_gid, offset_index, piece,
-        comp0, ncomp, send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, 0]"""
+        comp0, ncomp, send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, coarse flags]"""
         k = {"local": 0, "send": 1, "recv": 2}[kind]
         n = lib().pb2h_sim_plan_boxes(self.h, ncomp, tt, k, None, 0)
         if n < 0:

@@ -359,7 +359,8 @@ int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t
 
 // the same for a field of topological type tt (0 cell, 1 face, 2 edge, 3 node), with the index
 // boxes: rows of 18 int64 [sender_gid, receiver_gid, offset_index, piece, comp0, ncomp,
-// send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, 0]
+// send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer, coarse flags (1: the sender reads its
+// coarse buffer, 2: the receiver writes its coarse buffer)]
 int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t *rows,
                             int64_t max_rows) {
   int64_t count = -1;
@@ -387,7 +388,7 @@ int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t 
       }
       r[15] = c.slab_off;
       r[16] = kind == 1 ? c.receiver_rank : c.sender_rank;
-      r[17] = 0;
+      r[17] = (c.send_coarse ? 1 : 0) | (c.recv_coarse ? 2 : 0);
     }
   });
   return count;

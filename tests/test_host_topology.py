@@ -303,3 +303,46 @@ def test_non_cell_centred_plan_two_ranks(name, ndim, nx, nb, ng):
                 U[rg, c0:c0 + nc, rk:rk + bk, rj:rj + bj, ri:ri + bi] = \
                     slabs[1 - r][int(q[15]):int(q[15]) + n].reshape(nc, bk, bj, bi)
         assert np.array_equal(U, ref), (name, key)
+
+
+@pytest.mark.parametrize("name,ndim,nx,nb,ng", H.TECOMM_MULTILEVEL)
+def test_non_cell_centred_multilevel_plan_matches_oracle_regions(name, ndim, nx, nb, ng):
+    """refined meshes, host half without a device: for every block the entries its local channel
+    pieces write — into the fine array or, from a coarser sender, into the coarse buffer — are
+    exactly the entries the oracle's masked unpack (pinned to the reference) writes; pieces never
+    overlap, and what they read on the sender is exactly the sender-side box entries the
+    receiver's mask lets through"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+    leaves, nrb = H.leaves_from_bounds(g["bounds"], full(nx), full(nb))
+    ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static")
+    t = host.Topology(overrides=ov, leaves=leaves)
+    m = oracle.Mesh(ndim, (nb,) * ndim, ng, tuple(nrb[:ndim]), leaves=leaves)
+    for kind in (1, 2, 3):
+        nel = 3 if kind < 3 else 1
+        fine = (m.nblocks, nel) + m.te_extents(kind)
+        coarse = (m.nblocks, nel) + tuple(n + (1 if n > 1 else 0) for n in m.cdims)
+        want = {False: np.zeros(fine, dtype=np.int32), True: np.zeros(coarse, dtype=np.int32)}
+        for b in range(m.nblocks):
+            lev = m.block_loc(b)[0]
+            for n, nbr in enumerate(m.neighbors(b)):
+                for el in range(nel):
+                    s, e, mask = m.calc_indices_te_general(b, n, kind, el, 1)
+                    to_coarse = nbr[1] < lev  # (gid, level, ox1, ox2, ox3)
+                    for k in range(s[2], e[2] + 1):
+                        kk = (k == e[2]) - (k == s[2])
+                        for j in range(s[1], e[1] + 1):
+                            jj = (j == e[1]) - (j == s[1])
+                            for i in range(s[0], e[0] + 1):
+                                ii = (i == e[0]) - (i == s[0])
+                                if mask[kk + 1, jj + 1, ii + 1]:
+                                    want[to_coarse][b, el, k, j, i] = 1
+        got = {False: np.zeros(fine, dtype=np.int32), True: np.zeros(coarse, dtype=np.int32)}
+        for r in t.plan_boxes(1, kind, "local"):
+            rg, el = int(r[1]), int(r[4])
+            (ri, rj, rk), (bi, bj, bk) = r[9:12], r[12:15]
+            got[bool(int(r[17]) & 2)][rg, el, rk:rk + bk, rj:rj + bj, ri:ri + bi] += 1
+        for to_coarse in (False, True):
+            assert got[to_coarse].max() <= 1, (kind, to_coarse)
+            assert np.array_equal(got[to_coarse] > 0, want[to_coarse] > 0), (kind, to_coarse)
+        assert got[True].sum() > 0 and got[False].sum() > 0
