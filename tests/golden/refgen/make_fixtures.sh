@@ -221,6 +221,23 @@ run_tecomm tecomm_u32_b8_g2_2d 2 32 8 2
 # node fields (pins the oracle; the GPU path for these is not built yet)
 run_tecomm tecomm_s16_b8_l2_3d 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
 run_tecomm tecomm_s32_b8_l3_2d 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+# nghost = 4 on three levels in 2-D; three levels in 3-D (197 blocks of 4^3: kept as one CRC-32
+# per block and field, the convention of pack_checksums.py)
+run_tecomm tecomm_s32_b8_g4_l3_2d 2 32 8 4 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+run_tecomm tecomm_s16_b4_l3_3d 3 16 4 2 3 "1:-0.3:0.1:-0.2:0.2:-0.1:0.3 2:-0.12:-0.05:0.02:0.12:0.05:0.12"
+python3 - "$OUT/tecomm_s16_b4_l3_3d.npz" "$OUT/tecomm_s16_b4_l3_3d_crc.npz" <<'PYEOF'
+import sys, zlib
+import numpy as np
+g = np.load(sys.argv[1])
+out = {"meta": g["meta"], "bounds": g["bounds"]}
+for k in ("0", "1", "2"):
+    a = g["U_" + k]
+    out["crc_" + k] = np.array([zlib.crc32(np.ascontiguousarray(a[b]).tobytes())
+                                for b in range(a.shape[0])], dtype=np.uint32)
+    out["shape_" + k] = np.array(a.shape)
+np.savez_compressed(sys.argv[2], **out)
+PYEOF
+rm -f "$OUT/tecomm_s16_b4_l3_3d.npz"
 # the face field with ProlongateInternalTothAndRoe (divergence-preserving internal faces)
 PB2_TOTH_ROE=1 run_tecomm tecomm_s16_b8_l2_3d_tothroe 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
 PB2_TOTH_ROE=1 run_tecomm tecomm_s32_b8_l3_2d_tothroe 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"

@@ -182,7 +182,10 @@ TECOMM = [("tecomm_u16_b8_g2_3d", 3, 16, 8, 2), ("tecomm_u16_b8_g4_3d", 3, 16, 8
           ("tecomm_u16_b4_g2_3d", 3, 16, 4, 2), ("tecomm_u32_b8_g2_2d", 2, 32, 8, 2)]
 # statically refined meshes (restriction, shared + internal prolongation): two levels in 3-D,
 # three levels in 2-D
-TECOMM_MULTILEVEL = [("tecomm_s16_b8_l2_3d", 3, 16, 8, 2), ("tecomm_s32_b8_l3_2d", 2, 32, 8, 2)]
+TECOMM_MULTILEVEL = [("tecomm_s16_b8_l2_3d", 3, 16, 8, 2), ("tecomm_s32_b8_l3_2d", 2, 32, 8, 2),
+                     ("tecomm_s32_b8_g4_l3_2d", 2, 32, 8, 4)]
+# three levels in 3-D, 197 blocks of 4^3: one CRC-32 per block and field (crc_0 / crc_1 / crc_2)
+TECOMM_MULTILEVEL_CRC = [("tecomm_s16_b4_l3_3d_crc", 3, 16, 4, 2)]
 # the same meshes with ProlongateInternalTothAndRoe registered for the face field (U_0 only)
 TECOMM_TOTH_ROE = [("tecomm_s16_b8_l2_3d_tothroe", 3, 16, 8, 2),
                    ("tecomm_s32_b8_l3_2d_tothroe", 2, 32, 8, 2)]

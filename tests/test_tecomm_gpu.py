@@ -79,6 +79,26 @@ def test_non_cell_centred_multilevel_exchange_bit_exact(name, ndim, nx, nb, ng, 
         sim.close()
 
 
+@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 3}])
+@pytest.mark.parametrize("name,ndim,nx,nb,ng", H.TECOMM_MULTILEVEL_CRC)
+def test_non_cell_centred_three_levels_3d_crc(name, ndim, nx, nb, ng, extra):
+    """three levels in 3-D (197 blocks of 4^3) against the CRC-32 per block and field of the
+    reference's dump"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+    leaves, nrb = H.leaves_from_bounds(g["bounds"], full(nx), full(nb))
+    ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static")
+    ov.update(extra or {})
+    sim = host.Simulation(app="tecomm", overrides=ov, leaves=leaves)
+    try:
+        for field, (key, nel, ncomp) in FIELDS.items():
+            got = sim.get_field("base", field)
+            assert got.shape == tuple(g["shape_" + key[2:]])
+            assert np.array_equal(H.block_crcs(got), g["crc_" + key[2:]]), (name, field)
+    finally:
+        sim.close()
+
+
 @pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 2}])
 @pytest.mark.parametrize("name,ndim,nx,nb,ng", H.TECOMM_TOTH_ROE)
 def test_toth_roe_internal_prolongation_bit_exact(name, ndim, nx, nb, ng, extra):
