@@ -65,6 +65,8 @@ def lib():
         L.orc_exchange_te.restype = C.c_int64
         L.orc_exchange_te_ml.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         L.orc_exchange_te_ml.restype = C.c_int64
+        L.orc_exchange_te_ml_op.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int]
+        L.orc_exchange_te_ml_op.restype = C.c_int64
         L.orc_calc_indices_te_general.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                   C.c_int, C.c_int, ip, ip, ip]
         L.orc_exchange_te_ml_toth_roe.argtypes = [C.c_void_p, dp, dp, C.c_int]
@@ -284,7 +286,7 @@ class Mesh:
         lib().orc_te_recv_mask(self.h, b, n, kind, el, _ip(mk))
         return mk.reshape(3, 3, 3)
 
-    def exchange_te(self, U, kind, toth_roe=False):
+    def exchange_te(self, U, kind, toth_roe=False, shared_op=0):
         """U: [nblocks][elements][ncomp][nk'][nj'][ni'] (te_extents), exchanged in place;
         multilevel meshes get scratch coarse buffers (restriction / prolongation included)"""
         assert U.flags.c_contiguous and U.shape[3:] == self.te_extents(kind)
@@ -295,6 +297,8 @@ class Mesh:
         if toth_roe:
             assert kind == 1, "Toth & Roe prolongation is defined for face fields"
             return lib().orc_exchange_te_ml_toth_roe(self.h, _dp(U), _dp(Uc), U.shape[2])
+        if shared_op:
+            return lib().orc_exchange_te_ml_op(self.h, _dp(U), _dp(Uc), U.shape[2], kind, shared_op)
         return lib().orc_exchange_te_ml(self.h, _dp(U), _dp(Uc), U.shape[2], kind)
 
     def flux_correct(self, F):

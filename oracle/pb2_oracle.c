@@ -1083,7 +1083,7 @@ static void te_restrict(const TeField *f, int kind, int b, int el, int c, int ck
  * coincide with coarse element (k, j, i); slopes only in the directions the element is
  * centred in (where GetGridSpacings uses cell-centre positions) */
 static void te_prolongate_shared(const TeField *f, int kind, int b, int el, int c, int k, int j,
-                                 int i) {
+                                 int i, int op) {
   const OrcMesh *m = f->m;
   const Block *blk = &m->blocks[b];
   const int DIM = m->ndim;
@@ -1094,7 +1094,8 @@ static void te_prolongate_shared(const TeField *f, int kind, int b, int el, int 
   const int fj = DIM > 1 ? (j - m->cis[1]) * 2 + m->is[1] : m->is[1];
   const int fk = DIM > 2 ? (k - m->cis[2]) * 2 + m->is[2] : m->is[2];
   const double fc = *te_c(f, b, el, c, k, j, i);
-  double g[3] = {0, 0, 0}, dxfm[3] = {0, 0, 0}, dxfp[3] = {0, 0, 0};
+  double g[3] = {0, 0, 0}, gm[3] = {0, 0, 0}, gp[3] = {0, 0, 0}, dxfm[3] = {0, 0, 0},
+         dxfp[3] = {0, 0, 0};
   const int cc[3] = {i, j, k}, ff[3] = {fi, fj, fk};
   for (int d = 0; d < 3; ++d) {
     if (!inc[d]) continue;
@@ -1111,8 +1112,14 @@ static void te_prolongate_shared(const TeField *f, int kind, int b, int el, int 
     const double fm = *te_c(f, b, el, c, k - o[2], j - o[1], i - o[0]);
     const double fp = *te_c(f, b, el, c, k + o[2], j + o[1], i + o[0]);
     g[d] = grad_minmod(fc, fm, fp, dxm, dxp);
+    /* ProlongateSharedGeneral<use_minmod_slope, piecewise_constant> pr_ops.hpp:206-262:
+     * 0 MinMod (both one-sided slopes replaced by the limited one), 1 Linear (the one-sided
+     * slopes themselves), 2 PiecewiseConstant (zero slopes) */
+    gm[d] = op == 0 ? g[d] : (op == 1 ? (fc - fm) / dxm : 0.0);
+    gp[d] = op == 0 ? g[d] : (op == 1 ? (fp - fc) / dxp : 0.0);
   }
-  const double gx1m = g[0], gx1p = g[0], gx2m = g[1], gx2p = g[1], gx3m = g[2], gx3p = g[2];
+  const double gx1m = gm[0], gx1p = gp[0], gx2m = gm[1], gx2p = gp[1], gx3m = gm[2],
+               gx3p = gp[2];
   const double dx1fm = dxfm[0], dx1fp = dxfp[0], dx2fm = dxfm[1], dx2fp = dxfp[1],
                dx3fm = dxfm[2], dx3fp = dxfp[2];
   *te_f(f, b, el, c, fk, fj, fi) = fc - (gx1m * dx1fm + gx2m * dx2fm + gx3m * dx3fm);
@@ -1268,9 +1275,14 @@ static const int kCelKind[8] = {ORC_TE_NODE, ORC_TE_EDGE, ORC_TE_EDGE, ORC_TE_ED
 static const int kCelEl[8] = {0, 2, 1, 0, 0, 1, 2, 0};
 
 static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind,
-                                int toth_roe);
+                                int toth_roe, int shared_op);
 int64_t orc_exchange_te_ml(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind) {
-  return exchange_te_impl(m, U, Uc, ncomp, kind, 0);
+  return exchange_te_impl(m, U, Uc, ncomp, kind, 0, 0);
+}
+/* shared_op: 0 ProlongateSharedMinMod, 1 ProlongateSharedLinear, 2 ProlongatePiecewiseConstant */
+int64_t orc_exchange_te_ml_op(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind,
+                              int shared_op) {
+  return exchange_te_impl(m, U, Uc, ncomp, kind, 0, shared_op);
 }
 /* the general index box and receive mask of region (b, n), element (kind, el), for tests */
 void orc_calc_indices_te_general(const OrcMesh *m, int b, int n, int kind, int el, int ir_type,
@@ -1285,10 +1297,10 @@ void orc_calc_indices_te_general(const OrcMesh *m, int b, int n, int kind, int e
 }
 /* a face field that registered ProlongateInternalTothAndRoe as its internal prolongation */
 int64_t orc_exchange_te_ml_toth_roe(const OrcMesh *m, double *U, double *Uc, int ncomp) {
-  return exchange_te_impl(m, U, Uc, ncomp, ORC_TE_FACE, 1);
+  return exchange_te_impl(m, U, Uc, ncomp, ORC_TE_FACE, 1, 0);
 }
 static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int ncomp, int kind,
-                                int toth_roe) {
+                                int toth_roe, int shared_op) {
   TeField F;
   F.m = m;
   F.U = U;
@@ -1427,7 +1439,8 @@ static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int nco
             for (int k = bx.s[2]; k <= bx.e[2]; ++k)
               for (int j = bx.s[1]; j <= bx.e[1]; ++j)
                 for (int i = bx.s[0]; i <= bx.e[0]; ++i)
-                  if (te_active(&bx, k, j, i)) te_prolongate_shared(&F, kind, b, el, c, k, j, i);
+                  if (te_active(&bx, k, j, i))
+                    te_prolongate_shared(&F, kind, b, el, c, k, j, i, shared_op);
         }
       }
     }

@@ -16,9 +16,24 @@ Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
     mface.RegisterRefinementOps<refinement_ops::ProlongateSharedMinMod,
                                 refinement_ops::RestrictAverage,
                                 refinement_ops::ProlongateInternalTothAndRoe>();
+  Metadata medge({Metadata::Edge, Metadata::Independent, Metadata::FillGhost});
+  Metadata mnode({Metadata::Node, Metadata::Independent, Metadata::FillGhost});
+  // tecomm/shared_op = linear | constant: the other stock shared prolongations for all fields
+  const std::string op = pin->GetOrAddString("tecomm", "shared_op", "minmod");
+  PARTHENON_REQUIRE(op == "minmod" || op == "linear" || op == "constant",
+                    "tecomm/shared_op must be minmod, linear or constant");
+  if (op != "minmod")
+    for (Metadata *m : {&mface, &medge, &mnode}) {
+      if (op == "linear")
+        m->RegisterRefinementOps<refinement_ops::ProlongateSharedLinear,
+                                 refinement_ops::RestrictAverage>();
+      else
+        m->RegisterRefinementOps<refinement_ops::ProlongatePiecewiseConstant,
+                                 refinement_ops::RestrictAverage>();
+    }
   pkg->AddField("face", mface);
-  pkg->AddField("edge", Metadata({Metadata::Edge, Metadata::Independent, Metadata::FillGhost}));
-  pkg->AddField("node", Metadata({Metadata::Node, Metadata::Independent, Metadata::FillGhost}));
+  pkg->AddField("edge", medge);
+  pkg->AddField("node", mnode);
   packages.Add(pkg);
   return packages;
 }

@@ -238,6 +238,9 @@ for k in ("0", "1", "2"):
 np.savez_compressed(sys.argv[2], **out)
 PYEOF
 rm -f "$OUT/tecomm_s16_b4_l3_3d.npz"
+# the other stock shared prolongations
+PB2_SHARED_OP=linear run_tecomm tecomm_s32_b8_l3_2d_linear 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+PB2_SHARED_OP=constant run_tecomm tecomm_s32_b8_l3_2d_constant 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
 # the face field with ProlongateInternalTothAndRoe (divergence-preserving internal faces)
 PB2_TOTH_ROE=1 run_tecomm tecomm_s16_b8_l2_3d_tothroe 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
 PB2_TOTH_ROE=1 run_tecomm tecomm_s32_b8_l3_2d_tothroe 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"

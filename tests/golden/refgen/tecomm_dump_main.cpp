@@ -42,9 +42,24 @@ Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
     mface.RegisterRefinementOps<parthenon::refinement_ops::ProlongateSharedMinMod,
                                 parthenon::refinement_ops::RestrictAverage,
                                 parthenon::refinement_ops::ProlongateInternalTothAndRoe>();
+  Metadata medge({Metadata::Edge, Metadata::Independent, Metadata::FillGhost});
+  Metadata mnode({Metadata::Node, Metadata::Independent, Metadata::FillGhost});
+  // $PB2_SHARED_OP = linear | constant: ProlongateSharedLinear / ProlongatePiecewiseConstant
+  // instead of the default ProlongateSharedMinMod, for all three fields
+  if (const char *op = std::getenv("PB2_SHARED_OP")) {
+    using namespace parthenon::refinement_ops;
+    for (Metadata *m : {&mface, &medge, &mnode}) {
+      if (std::string(op) == "linear")
+        m->RegisterRefinementOps<ProlongateSharedLinear, RestrictAverage,
+                                 ProlongateInternalAverage>();
+      else
+        m->RegisterRefinementOps<ProlongatePiecewiseConstant, RestrictAverage,
+                                 ProlongateInternalAverage>();
+    }
+  }
   pkg->AddField("face", mface);
-  pkg->AddField("edge", Metadata({Metadata::Edge, Metadata::Independent, Metadata::FillGhost}));
-  pkg->AddField("node", Metadata({Metadata::Node, Metadata::Independent, Metadata::FillGhost}));
+  pkg->AddField("edge", medge);
+  pkg->AddField("node", mnode);
   packages.Add(pkg);
   return packages;
 }

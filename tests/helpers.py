@@ -186,6 +186,9 @@ TECOMM_MULTILEVEL = [("tecomm_s16_b8_l2_3d", 3, 16, 8, 2), ("tecomm_s32_b8_l3_2d
                      ("tecomm_s32_b8_g4_l3_2d", 2, 32, 8, 4)]
 # three levels in 3-D, 197 blocks of 4^3: one CRC-32 per block and field (crc_0 / crc_1 / crc_2)
 TECOMM_MULTILEVEL_CRC = [("tecomm_s16_b4_l3_3d_crc", 3, 16, 4, 2)]
+# the 2-D three-level mesh with the other stock shared prolongations: (name, ..., operator id)
+TECOMM_SHARED_OPS = [("tecomm_s32_b8_l3_2d_linear", 2, 32, 8, 2, 1, "linear"),
+                     ("tecomm_s32_b8_l3_2d_constant", 2, 32, 8, 2, 2, "constant")]
 # the same meshes with ProlongateInternalTothAndRoe registered for the face field (U_0 only)
 TECOMM_TOTH_ROE = [("tecomm_s16_b8_l2_3d_tothroe", 3, 16, 8, 2),
                    ("tecomm_s32_b8_l3_2d_tothroe", 2, 32, 8, 2)]

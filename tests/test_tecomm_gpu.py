@@ -79,6 +79,23 @@ def test_non_cell_centred_multilevel_exchange_bit_exact(name, ndim, nx, nb, ng, 
         sim.close()
 
 
+@pytest.mark.parametrize("name,ndim,nx,nb,ng,op,opname", H.TECOMM_SHARED_OPS)
+def test_non_cell_centred_other_shared_prolongations(name, ndim, nx, nb, ng, op, opname):
+    """tecomm/shared_op = linear | constant: ProlongateSharedLinear / ProlongatePiecewiseConstant
+    on faces, edges and nodes (pb2_prolongate_te with the operator id) vs the reference"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+    leaves, nrb = H.leaves_from_bounds(g["bounds"], full(nx), full(nb))
+    ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static")
+    ov["tecomm/shared_op"] = opname
+    sim = host.Simulation(app="tecomm", overrides=ov, leaves=leaves)
+    try:
+        for field, (key, nel, ncomp) in FIELDS.items():
+            assert np.array_equal(sim.get_field("base", field), g[key]), (name, field)
+    finally:
+        sim.close()
+
+
 @pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 3}])
 @pytest.mark.parametrize("name,ndim,nx,nb,ng", H.TECOMM_MULTILEVEL_CRC)
 def test_non_cell_centred_three_levels_3d_crc(name, ndim, nx, nb, ng, extra):
