@@ -66,6 +66,13 @@ std::vector<IndexBox> ActivePieces(const int n[3], const std::array<bool, 27> &m
 // conditions can build their own tables from these
 pb2_bc_region MakeBcRegion(Variable &v, const MeshBlock *pmb, int face, int type, bool coarse);
 
+// (o1, o2, o3) -> 0..26, and the entry of `sender`'s neighbour list that describes the channel
+// towards `receiver_gid` seen from the receiver at offsets `roff` (channels are keyed by sender
+// gid, receiver gid and the location index: bvals_utils.hpp:43-67)
+int OffsetIndexOf(int o1, int o2, int o3);
+const NeighborBlock *MatchingNeighbor(const MeshBlock *sender, int receiver_gid,
+                                      const int roff[3]);
+
 // one boundary channel as the host sees it (pure topology: testable without a device).  A
 // channel of a face / edge / node field is split into pieces: one per topological element and
 // active sub-box of the ownership mask.

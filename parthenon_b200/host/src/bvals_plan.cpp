@@ -1,0 +1,415 @@
+// bvals_plan.cpp — the pure-topology half of the ghost-zone exchange: index boxes
+// (CalcIndices and its flux / topological-element forms), ownership masks resolved into boxes,
+// and the channel plan with its per-peer slab layout.  Nothing here touches a device, which is
+// what the CPU-only tests exercise through pb2h_topology_create / pb2h_sim_plan_boxes.
+// See pb2/bvals.hpp for the design and the reference files each piece replaces.
+#include "pb2/bvals.hpp"
+
+#include <algorithm>
+#include <tuple>
+
+namespace parthenon {
+
+// ---------------------------------------------------------------------------------------
+// CalcIndices for cell-centred, non-flux fields with the identity logical-coordinate
+// transform and full ownership (what a single-tree mesh produces): bnd_info.cpp:105-252
+// ---------------------------------------------------------------------------------------
+IndexBox CalcIndices(const NeighborBlock &nb, const MeshBlock *pmb, IndexRangeType ir_type,
+                     bool prores) {
+  const LogicalLocation &loc = pmb->loc;
+  const int ng = Globals::nghost;
+  // prolongation/restriction work in the coarse index space; so does any exchange with a
+  // coarser neighbour (:121-125)
+  const bool use_coarse = prores || nb.loc.level < loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int coarse_fac = nb.loc.level > loc.level ? 2 : 1; // :130
+  const int interior_offset = ir_type == IndexRangeType::BoundaryInteriorSend ? ng : 0;
+  int exterior_offset = ir_type == IndexRangeType::BoundaryExteriorRecv ? ng : 0;
+  if (prores) exterior_offset /= 2; // only coarse ghosts that have fine ghosts (:161-166)
+  IndexBox box;
+  for (int d = 0; d < 3; ++d) {
+    const bool not_sym = !pmb->block_size.symmetry_[d];
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior);
+    // the neighbour's interior extent in the index space we exchange in (:131-135)
+    const int nb_n = not_sym ? pmb->block_size.nx_[d] / coarse_fac : 1;
+    int &s = box.s[d], &e = box.e[d];
+    if (nb.offsets[d] == 0) {
+      s = b.s;
+      e = b.e;
+      if (loc.level < nb.origin_loc.level && not_sym) {
+        // finer neighbour abuts half of this face; send ng extra interior zones so the
+        // receiver can prolongate (:173-192)
+        const int extra = (b.e - b.s + 1) - nb_n;
+        const bool upper_half = ((nb.origin_loc.lx[d] % 2) + 2) % 2 == 1;
+        s += upper_half ? extra - interior_offset : 0;
+        e -= upper_half ? 0 : extra - interior_offset;
+        if (ir_type == IndexRangeType::InteriorSend && !prores) {
+          s -= ng;
+          e += ng;
+        }
+      }
+      if (loc.level > nb.origin_loc.level && not_sym) {
+        // coarser neighbour: it sent extra zones on the side away from our corner (:193-204)
+        s -= loc.lx[d] % 2 == 1 ? exterior_offset : 0;
+        e += loc.lx[d] % 2 == 0 ? exterior_offset : 0;
+        if (ir_type == IndexRangeType::InteriorRecv && !prores) {
+          s -= ng;
+          e += ng;
+        }
+      }
+      if (prores && not_sym && ir_type == IndexRangeType::InteriorRecv) {
+        s -= ng / 2;
+        e += ng / 2;
+      }
+    } else if (nb.offsets[d] > 0) {
+      s = b.e + (-interior_offset + 1);
+      e = b.e + exterior_offset;
+    } else {
+      s = b.s - exterior_offset;
+      e = b.s + (interior_offset - 1);
+    }
+  }
+  return box;
+}
+
+IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
+                       IndexRangeType ir_type, bool prores) {
+  const LogicalLocation &loc = pmb->loc;
+  const int ng = Globals::nghost;
+  const bool use_coarse = prores || nb.loc.level < loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int coarse_fac = nb.loc.level > loc.level ? 2 : 1;
+  const int interior_offset = ir_type == IndexRangeType::BoundaryInteriorSend ? ng : 0;
+  int exterior_offset = ir_type == IndexRangeType::BoundaryExteriorRecv ? ng : 0;
+  if (prores) exterior_offset /= 2;
+  IndexBox box;
+  for (int d = 0; d < 3; ++d) {
+    const bool not_sym = !pmb->block_size.symmetry_[d];
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior, el);
+    const int top = not_sym ? TopologicalOffset(el, d) : 0;
+    // entries of the element the neighbour holds along d in the index space of the exchange
+    const int nb_n = not_sym ? pmb->block_size.nx_[d] / coarse_fac + top : 1;
+    int &s = box.s[d], &e = box.e[d];
+    if (nb.offsets[d] == 0) {
+      s = b.s;
+      e = b.e;
+      if (loc.level < nb.origin_loc.level && not_sym) { // :173-192
+        const int extra = (b.e - b.s + 1) - nb_n;
+        const bool upper_half = ((nb.origin_loc.lx[d] % 2) + 2) % 2 == 1;
+        s += upper_half ? extra - interior_offset : 0;
+        e -= upper_half ? 0 : extra - interior_offset;
+      }
+      if (loc.level > nb.origin_loc.level && not_sym) { // :193-204
+        s -= loc.lx[d] % 2 == 1 ? exterior_offset : 0;
+        e += loc.lx[d] % 2 == 0 ? exterior_offset : 0;
+      }
+    } else if (nb.offsets[d] > 0) {
+      // a neighbour duplicates the shared elements: its boundary lies one deeper (:150-155)
+      s = b.e + (-interior_offset + 1 - top);
+      e = b.e + exterior_offset;
+    } else {
+      s = b.s - exterior_offset;
+      e = b.s + (interior_offset - 1 + top);
+    }
+  }
+  return box;
+}
+
+std::array<bool, 27> RecvMask(const Mesh *pm, const NeighborBlock &nb, const MeshBlock *pmb,
+                              TE el) {
+  int sox[3] = {-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]};
+  if (nb.origin_loc.level < pmb->loc.level)
+    // a coarser sender passes zones from an interior corner only, never a whole face or edge
+    for (int d = 0; d < 3; ++d)
+      if (sox[d] == 0) sox[d] = pmb->loc.lx[d] % 2 == 1 ? 1 : -1;
+  return IndexRangeMask(el, pm->Ownership(nb.gid), sox);
+}
+
+std::array<bool, 27> IndexRangeMask(TE el, const std::array<bool, 27> &sender,
+                                    const int sox[3]) {
+  auto at = [](int i, int j, int k) { return (i + 1) + 3 * (j + 1) + 9 * (k + 1); };
+  std::array<bool, 27> m;
+  // block ownership -> ownership of the element's entries: directions the element is not
+  // displaced in have no shared entries and follow the block's interior
+  for (int i = -1; i <= 1; ++i)
+    for (int j = -1; j <= 1; ++j)
+      for (int k = -1; k <= 1; ++k)
+        m[at(i, j, k)] = sender[at(TopologicalOffsetI(el) ? i : 0, TopologicalOffsetJ(el) ? j : 0,
+                                   TopologicalOffsetK(el) ? k : 0)];
+  // the box is a slice of the sender next to its (sox) boundary: the side of it that faces the
+  // sender's interior holds interior entries
+  if (sox[0] != 0)
+    for (int j = -1; j <= 1; ++j)
+      for (int k = -1; k <= 1; ++k) m[at(-sox[0], j, k)] = m[at(0, j, k)];
+  if (sox[1] != 0)
+    for (int i = -1; i <= 1; ++i)
+      for (int k = -1; k <= 1; ++k) m[at(i, -sox[1], k)] = m[at(i, 0, k)];
+  if (sox[2] != 0)
+    for (int i = -1; i <= 1; ++i)
+      for (int j = -1; j <= 1; ++j) m[at(i, j, -sox[2])] = m[at(i, j, 0)];
+  return m;
+}
+
+std::vector<IndexBox> ActivePieces(const int n[3], const std::array<bool, 27> &mask) {
+  // per direction: first entry (-1), inner run (0), last entry (+1); a single entry counts as
+  // inner (indexer.hpp:171-173: (i == end) - (i == start))
+  struct Seg {
+    int s, e, idx;
+  };
+  std::vector<Seg> segs[3];
+  for (int d = 0; d < 3; ++d) {
+    if (n[d] == 1) {
+      segs[d] = {{0, 0, 0}};
+    } else {
+      segs[d].push_back({0, 0, -1});
+      if (n[d] > 2) segs[d].push_back({1, n[d] - 2, 0});
+      segs[d].push_back({n[d] - 1, n[d] - 1, 1});
+    }
+  }
+  std::vector<IndexBox> out;
+  for (const Seg &k : segs[2])
+    for (const Seg &j : segs[1])
+      for (const Seg &i : segs[0]) {
+        if (!mask[(i.idx + 1) + 3 * (j.idx + 1) + 9 * (k.idx + 1)]) continue;
+        IndexBox b;
+        b.s[0] = i.s, b.e[0] = i.e, b.s[1] = j.s, b.e[1] = j.e, b.s[2] = k.s, b.e[2] = k.e;
+        out.push_back(b);
+      }
+  // glue boxes that share a whole side (fewer, longer regions); deterministic, so the sending
+  // and the receiving device arrive at the same list
+  bool merged = true;
+  while (merged) {
+    merged = false;
+    for (size_t a = 0; a < out.size() && !merged; ++a)
+      for (size_t b = 0; b < out.size() && !merged; ++b) {
+        if (a == b) continue;
+        for (int d = 0; d < 3 && !merged; ++d) {
+          const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+          if (out[a].e[d] + 1 == out[b].s[d] && out[a].s[d1] == out[b].s[d1] &&
+              out[a].e[d1] == out[b].e[d1] && out[a].s[d2] == out[b].s[d2] &&
+              out[a].e[d2] == out[b].e[d2]) {
+            out[a].e[d] = out[b].e[d];
+            out.erase(out.begin() + static_cast<std::ptrdiff_t>(b));
+            merged = true;
+          }
+        }
+      }
+  }
+  return out;
+}
+
+// bnd_info.cpp:105-252 with flux = true and el = F_dir: the box is the shared face itself
+// (:207-211), tangentially the whole face of a finer sender (coarse index space) or the half
+// (quarter in 3-D) of a coarser receiver's face that the finer neighbour abuts (:173-192)
+IndexBox CalcIndicesFlux(const NeighborBlock &nb, const MeshBlock *pmb) {
+  const LogicalLocation &loc = pmb->loc;
+  const bool use_coarse = nb.loc.level < loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  const int coarse_fac = nb.loc.level > loc.level ? 2 : 1;
+  IndexBox box;
+  for (int d = 0; d < 3; ++d) {
+    const bool not_sym = !pmb->block_size.symmetry_[d];
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior);
+    int &s = box.s[d], &e = box.e[d];
+    if (nb.offsets[d] == 0) {
+      s = b.s;
+      e = b.e;
+      if (loc.level < nb.origin_loc.level && not_sym) {
+        const int extra = (b.e - b.s + 1) - pmb->block_size.nx_[d] / coarse_fac;
+        const bool upper_half = ((nb.origin_loc.lx[d] % 2) + 2) % 2 == 1;
+        s += upper_half ? extra : 0;
+        e -= upper_half ? 0 : extra;
+      }
+    } else if (nb.offsets[d] > 0) {
+      s = e = b.e + (not_sym ? 1 : 0); // upper face: index ie + 1 of the cell-aligned array
+    } else {
+      s = e = b.s;
+    }
+  }
+  return box;
+}
+
+// ---------------------------------------------------------------------------------------
+// channel plan (pure topology)
+// ---------------------------------------------------------------------------------------
+int OffsetIndexOf(int o1, int o2, int o3) { return (o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1); }
+
+// the entry of `sender`'s neighbour list that describes the channel towards `receiver_gid`
+// seen from the receiver at offsets `roff` (bvals_utils.hpp:43-67: channels are keyed by
+// sender gid, receiver gid and the location index)
+const NeighborBlock *MatchingNeighbor(const MeshBlock *sender, int receiver_gid,
+                                      const int roff[3]) {
+  for (auto &q : sender->neighbors)
+    if (q.gid == receiver_gid && q.offsets[0] == -roff[0] && q.offsets[1] == -roff[1] &&
+        q.offsets[2] == -roff[2])
+      return &q;
+  return nullptr;
+}
+namespace {
+auto ChannelKey(const Channel &c) {
+  return std::make_tuple(c.sender_gid, c.receiver_gid, c.var, c.offset_index, c.piece);
+}
+IndexBox SubBox(const IndexBox &box, const IndexBox &rel) {
+  IndexBox b;
+  for (int d = 0; d < 3; ++d) {
+    b.s[d] = box.s[d] + rel.s[d];
+    b.e[d] = box.s[d] + rel.e[d];
+  }
+  return b;
+}
+} // namespace
+
+ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
+                               const std::vector<PlanVar> &vars) {
+  ExchangePlan plan;
+  const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
+  PARTHENON_REQUIRE(!(V > 1 && pm->nranks > 1), "pb2/virtual_ranks needs a single real rank");
+  plan.npeers = V > 1 ? V * V : pm->nranks;
+  const int nvar = static_cast<int>(vars.size());
+  std::vector<std::pair<int, Channel>> send, recv; // (segment, channel)
+  // a face / edge / node channel: one piece per element and active sub-box of the ownership
+  // mask of its sender; `emit` receives each piece with boxes, component range and piece id set
+  auto pieces = [&](Channel base, const NeighborBlock &nb, const MeshBlock *pmb, bool pmb_sends,
+                    const MeshBlock *local_sender, const NeighborBlock *q, auto &&emit) {
+    const PlanVar &pv = vars[base.var];
+    const std::vector<TE> els = GetTopologicalElements(pv.tt);
+    // the mask is the RECEIVER's (bnd_info.cpp:232-248): offsets of the receiver seen from the
+    // sender, replaced by the receiver's position inside its parent where a coarser sender
+    // faces it with offset 0
+    const LogicalLocation &recv_loc = pmb_sends ? nb.origin_loc : pmb->loc;
+    const int sender_gid = pmb_sends ? pmb->gid : nb.gid;
+    const int sender_level = pmb_sends ? pmb->loc.level : nb.loc.level;
+    int sox[3];
+    for (int d = 0; d < 3; ++d) {
+      sox[d] = pmb_sends ? nb.offsets[d] : -nb.offsets[d];
+      if (sender_level < recv_loc.level && sox[d] == 0)
+        sox[d] = ((recv_loc.lx[d] % 2) + 2) % 2 == 1 ? 1 : -1;
+    }
+    for (size_t e = 0; e < els.size(); ++e) {
+      const IndexBox mine = CalcIndicesTE(nb, pmb, els[e],
+                                          pmb_sends ? IndexRangeType::BoundaryInteriorSend
+                                                    : IndexRangeType::BoundaryExteriorRecv);
+      IndexBox other = mine;
+      if (local_sender)
+        other = CalcIndicesTE(*q, local_sender, els[e], IndexRangeType::BoundaryInteriorSend);
+      int n[3];
+      for (int d = 0; d < 3; ++d) {
+        n[d] = mine.n(d);
+        PARTHENON_REQUIRE(other.n(d) == n[d], "send/receive extents of a channel differ");
+      }
+      const auto mask = IndexRangeMask(els[e], pm->Ownership(sender_gid), sox);
+      int sub = 0;
+      for (const IndexBox &rel : ActivePieces(n, mask)) {
+        Channel c = base;
+        c.piece = static_cast<int>(e) * 32 + sub++;
+        c.comp0 = static_cast<int>(e) * pv.ncomp;
+        c.ncomp = pv.ncomp;
+        c.send_box = SubBox(pmb_sends ? mine : other, rel);
+        c.recv_box = SubBox(pmb_sends ? other : mine, rel);
+        emit(c);
+      }
+    }
+  };
+  for (auto &pmb : blocks) {
+    const int my_vr = pm->VirtualRankOf(pmb->gid);
+    for (auto &nb : pmb->neighbors) {
+      const int nb_vr = nb.rank == pm->my_rank ? pm->VirtualRankOf(nb.gid) : 0;
+      const bool local = nb.rank == pm->my_rank && nb_vr == my_vr;
+      for (int v = 0; v < nvar; ++v) {
+        // this block as RECEIVER of the channel nb -> pmb
+        Channel rc;
+        rc.sender_gid = nb.gid;
+        rc.receiver_gid = pmb->gid;
+        rc.var = v;
+        rc.offset_index = OffsetIndexOf(-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]);
+        rc.recv_box = CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, false);
+        rc.recv_coarse = nb.loc.level < pmb->loc.level; // bnd_info.cpp:285-289
+        rc.send_coarse = pmb->loc.level < nb.loc.level;
+        rc.sender_rank = nb.rank;
+        rc.receiver_rank = pm->my_rank;
+        rc.sender_vrank = nb_vr;
+        rc.receiver_vrank = my_vr;
+        rc.send_box = rc.recv_box;
+        rc.ncomp = vars[v].ncomp;
+        const bool cell = vars[v].tt == TopologicalType::Cell;
+        if (local) {
+          const MeshBlock *sender = pm->block_list[nb.lid].get();
+          const NeighborBlock *q = MatchingNeighbor(sender, pmb->gid, nb.offsets);
+          PARTHENON_REQUIRE(q != nullptr, "no matching send region for a local channel");
+          auto emit = [&](const Channel &c) {
+            plan.local_elements += c.recv_box.size() * c.ncomp;
+            plan.local.push_back(c);
+          };
+          if (cell) {
+            rc.send_box = CalcIndices(*q, sender, IndexRangeType::BoundaryInteriorSend, false);
+            for (int d = 0; d < 3; ++d)
+              PARTHENON_REQUIRE(rc.send_box.n(d) == rc.recv_box.n(d),
+                                "send/receive extents of a channel differ");
+            emit(rc);
+          } else {
+            pieces(rc, nb, pmb.get(), false, sender, q, emit);
+          }
+        } else {
+          const int seg = V > 1 ? nb_vr * V + my_vr : nb.rank;
+          auto emit = [&](const Channel &c) { recv.emplace_back(seg, c); };
+          if (cell)
+            emit(rc);
+          else
+            pieces(rc, nb, pmb.get(), false, nullptr, nullptr, emit);
+        }
+        // this block as SENDER of the channel pmb -> nb
+        if (!local) {
+          Channel sc;
+          sc.sender_gid = pmb->gid;
+          sc.receiver_gid = nb.gid;
+          sc.var = v;
+          sc.offset_index = nb.OffsetIndex();
+          sc.send_box = CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryInteriorSend, false);
+          sc.recv_box = sc.send_box;
+          sc.send_coarse = nb.loc.level < pmb->loc.level;
+          sc.recv_coarse = pmb->loc.level < nb.loc.level;
+          sc.sender_rank = pm->my_rank;
+          sc.receiver_rank = nb.rank;
+          sc.sender_vrank = my_vr;
+          sc.receiver_vrank = nb_vr;
+          sc.ncomp = vars[v].ncomp;
+          const int seg = V > 1 ? my_vr * V + nb_vr : nb.rank;
+          auto emit = [&](const Channel &c) { send.emplace_back(seg, c); };
+          if (vars[v].tt == TopologicalType::Cell)
+            emit(sc);
+          else
+            pieces(sc, nb, pmb.get(), true, nullptr, nullptr, emit);
+        }
+      }
+    }
+  }
+  // both sides of a peer segment order its channels by the same key, so slab offsets agree
+  // without any handshake
+  auto layout = [&](std::vector<std::pair<int, Channel>> &chs, std::vector<Channel> &out,
+                    std::vector<int64_t> &seg_off, int64_t &total) {
+    std::stable_sort(chs.begin(), chs.end(), [](const auto &a, const auto &b) {
+      if (a.first != b.first) return a.first < b.first;
+      return ChannelKey(a.second) < ChannelKey(b.second);
+    });
+    seg_off.assign(plan.npeers + 1, 0);
+    std::vector<int64_t> seg_size(plan.npeers, 0);
+    for (auto &sc : chs) {
+      Channel c = sc.second;
+      c.slab_off = seg_size[sc.first];
+      int64_t n = c.send_box.size() * c.ncomp;
+      n += n & 1; // keep every channel 16-byte aligned for vector access
+      seg_size[sc.first] += n;
+      out.push_back(c);
+    }
+    for (int p = 0; p < plan.npeers; ++p) seg_off[p + 1] = seg_off[p] + seg_size[p];
+    total = seg_off[plan.npeers];
+    // make slab_off absolute
+    size_t i = 0;
+    for (auto &sc : chs) out[i++].slab_off += seg_off[sc.first];
+  };
+  layout(send, plan.send, plan.send_off, plan.send_elements);
+  layout(recv, plan.recv, plan.recv_off, plan.recv_elements);
+  return plan;
+}
+
+} // namespace parthenon
