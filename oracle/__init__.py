@@ -133,6 +133,11 @@ def lib():
         L.orc_amr_create_burgers.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
                                              C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                              C.c_double]
+        L.orc_amr_create_te.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int]
+        L.orc_amr_create_te.restype = C.c_void_p
+        L.orc_amr_te_cycle.argtypes = [C.c_void_p, C.c_int]
+        L.orc_amr_te_field.argtypes = [C.c_void_p, C.c_int]
+        L.orc_amr_te_field.restype = dp
         L.orc_amr_tags.argtypes = [C.c_void_p, ip]
         L.orc_amr_deref_counts.argtypes = [C.c_void_p, ip]
         L.orc_amr_destroy.argtypes = [C.c_void_p]
@@ -500,6 +505,56 @@ class AmrAdvection:
     @property
     def time(self):
         return lib().orc_amr_time(self.h)
+
+
+class AmrNonCellCentred:
+    """the adaptive face / edge / node field application of
+    tests/golden/refgen/teamr_dump_main.cpp (fields never evolve, the mesh follows a moving
+    geometric criterion): pins the remesh data movement of non-cell-centred fields"""
+
+    def __init__(self, ndim, nx, ng, nrb, numlevel, derefine_count=2, xmin=(-0.5,) * 3,
+                 xmax=(0.5,) * 3):
+        nx3 = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
+        nrb3 = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
+        lo, hi = np.array(xmin, dtype=np.float64), np.array(xmax, dtype=np.float64)
+        self.ndim = ndim
+        self.h = lib().orc_amr_create_te(ndim, _ip(nx3), ng, _ip(nrb3), _dp(lo), _dp(hi), numlevel,
+                                         derefine_count)
+
+    def __del__(self):
+        try:
+            lib().orc_amr_destroy(self.h)
+        except Exception:
+            pass
+
+    def init(self):
+        lib().orc_amr_init(self.h)
+
+    def cycle(self, c):
+        """tag with the criterion of cycle c and remesh; True if the mesh changed"""
+        return bool(lib().orc_amr_te_cycle(self.h, c))
+
+    @property
+    def nblocks(self):
+        return lib().orc_mesh_nblocks(lib().orc_amr_mesh(self.h))
+
+    @property
+    def block_locs(self):
+        m = lib().orc_amr_mesh(self.h)
+        out = np.zeros((self.nblocks, 4), dtype=np.int32)
+        for b in range(self.nblocks):
+            lib().orc_mesh_block_loc(m, b, _ip(out[b]))
+        return out
+
+    def field(self, f):
+        """f = 0 face [nb][3*2], 1 edge [nb][3], 2 node [nb][1], each with padded extents"""
+        m = lib().orc_amr_mesh(self.h)
+        pn = np.zeros(3, dtype=np.int32)
+        lib().orc_te_extents(m, f + 1, _ip(pn))
+        ncs = (6, 3, 1)[f]
+        shape = (self.nblocks, ncs, int(pn[2]), int(pn[1]), int(pn[0]))
+        p = lib().orc_amr_te_field(self.h, f)
+        return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape).copy()
 
 
 class SparseAdvection:

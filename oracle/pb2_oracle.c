@@ -884,6 +884,12 @@ static int is_neighbor_of_te(const Loc *self, const Loc *in, const int te[3]) {
 /* DetermineOwnership (block_ownership.cpp:42-83) of leaf block g, no newly refined blocks:
  * owns[(o1+1) + 3 (o2+1) + 9 (o3+1)].  On one tree (level, Morton number) orders leaves like
  * (level, gid). */
+/* blocks created by refinement in the remesh in progress (NULL otherwise): they rank below
+ * older blocks of their level, above their parents' level (block_ownership.cpp:48-54) */
+static const int *g_newly_refined = NULL;
+static int ownership_level(const Loc *l, int gid) {
+  return g_newly_refined != NULL && g_newly_refined[gid] ? 2 * l->level - 1 : 2 * l->level;
+}
 static void determine_ownership(const OrcMesh *m, int g, int owns[27]) {
   const Block *blk = &m->blocks[g];
   for (int o1 = -1; o1 <= 1; ++o1)
@@ -893,8 +899,8 @@ static void determine_ownership(const OrcMesh *m, int g, int owns[27]) {
         const int te[3] = {o1, o2, o3};
         for (int n = 0; n < blk->nnb && own; ++n) {
           const Neighbor *nb = &blk->nb[n];
-          const int less = blk->loc.level != nb->loc.level ? blk->loc.level < nb->loc.level
-                                                           : g < nb->gid;
+          const int la = ownership_level(&blk->loc, g), lb = ownership_level(&nb->loc, nb->gid);
+          const int less = la != lb ? la < lb : g < nb->gid;
           if (less && is_neighbor_of_te(&blk->loc, &nb->origin_loc, te)) own = 0;
         }
         owns[(o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)] = own;
@@ -2249,7 +2255,18 @@ struct OrcAmr {
   OrcBurgers *bur;
   int num_scalars, recon;
   int crit_comp, crit_max_level; /* vector_i; max_level + root_level (parthenon_manager.cpp:216-220) */
+  /* app = 2: the non-cell-centred field application of tests/golden/refgen/teamr_dump_main.cpp:
+   * a face (2 components), an edge and a node field that never evolve; the mesh follows a
+   * geometric criterion that moves with te_cycle */
+  double *te_U[3], *te_Uc[3];
+  int te_cycle;
 };
+static const int kTeNcomp[3] = {2, 1, 1};
+static void te_alloc(const OrcMesh *m, int f, double **U, double **Uc);
+static void te_ic(struct OrcAmr *a);
+static void te_remesh(struct OrcAmr *a, OrcMesh *nm);
+static void amr_tag(struct OrcAmr *a, const double *U);
+static int amr_remesh(struct OrcAmr *a);
 
 static OrcMesh *amr_make_mesh(const struct OrcAmr *a, const LeafSet *t) {
   int *lv = (int *)malloc(sizeof(int) * 4 * (size_t)t->n);
@@ -2306,6 +2323,39 @@ struct OrcAmr *orc_amr_create(int ndim, const int nx[3], int ng, const int nrb[3
   a->last_tag = (int *)calloc((size_t)a->m->nblocks, sizeof(int));
   return a;
 }
+/* the non-cell-centred field application (app = 2) */
+struct OrcAmr *orc_amr_create_te(int ndim, const int nx[3], int ng, const int nrb[3],
+                                 const double xmin[3], const double xmax[3], int numlevel,
+                                 int derefine_count) {
+  const double v0[3] = {0, 0, 0};
+  struct OrcAmr *a = orc_amr_create(ndim, nx, ng, nrb, xmin, xmax, numlevel, derefine_count, 0.0,
+                                    0.0, 1, 2, 0.0, v0, 0.0);
+  orc_advection_destroy(a->adv);
+  a->adv = NULL;
+  a->app = 2;
+  for (int f = 0; f < 3; ++f) te_alloc(a->m, f, &a->te_U[f], &a->te_Uc[f]);
+  return a;
+}
+/* Mesh::Initialize: problem generator, exchange, tag, remesh until the mesh stops changing */
+static void amr_init_te(struct OrcAmr *a) {
+  int done;
+  a->te_cycle = 0;
+  do {
+    te_ic(a);
+    for (int f = 0; f < 3; ++f)
+      exchange_te_impl(a->m, a->te_U[f], a->te_Uc[f], kTeNcomp[f], f + 1, 0, 0);
+    amr_tag(a, NULL);
+    done = !amr_remesh(a);
+  } while (!done);
+}
+/* one "cycle" of the fixture generator: tag with the criterion of `cycle`, remesh */
+int orc_amr_te_cycle(struct OrcAmr *a, int cycle) {
+  a->te_cycle = cycle;
+  amr_tag(a, NULL);
+  return amr_remesh(a);
+}
+const double *orc_amr_te_field(const struct OrcAmr *a, int f) { return a->te_U[f]; }
+
 /* benchmarks/burgers, refinement = adaptive: criterion = derivative_order_1 on U(vector_i) */
 struct OrcAmr *orc_amr_create_burgers(int ndim, const int nx[3], int ng, const int nrb[3],
                                       const double xmin[3], const double xmax[3], int numlevel,
@@ -2330,6 +2380,10 @@ struct OrcAmr *orc_amr_create_burgers(int ndim, const int nx[3], int ng, const i
 
 void orc_amr_destroy(struct OrcAmr *a) {
   if (!a) return;
+  for (int f = 0; f < 3; ++f) {
+    free(a->te_U[f]);
+    free(a->te_Uc[f]);
+  }
   orc_burgers_destroy(a->bur);
   orc_advection_destroy(a->adv);
   orc_mesh_destroy(a->m);
@@ -2357,12 +2411,20 @@ static void amr_tag(struct OrcAmr *a, const double *U) {
     const Block *blk = &m->blocks[b];
     double mn = DBL_MAX, mx = -DBL_MAX; /* Kokkos::MinMax identity */
     const double *p = U + (size_t)b * per_block;
-    for (size_t q = 0; q < per_block; ++q) {
+    for (size_t q = 0; U != NULL && q < per_block; ++q) {
       mn = p[q] < mn ? p[q] : mn;
       mx = p[q] > mx ? p[q] : mx;
     }
     int aret = 0; /* AmrTag: derefine -1, same 0, refine 1 */
-    if (a->app == 1) {
+    if (a->app == 2) {
+      /* TagByPosition of the fixture generator */
+      const double xc = 0.5 * (blk->xmin[0] + blk->xmax[0]), yc = 0.5 * (blk->xmin[1] + blk->xmax[1]);
+      const double zc = m->ndim > 2 ? 0.5 * (blk->xmin[2] + blk->xmax[2]) : 0.0;
+      const double px = -0.25 + 0.125 * a->te_cycle, py = -0.125 + 0.0625 * a->te_cycle,
+                   pz = m->ndim > 2 ? 0.125 : 0.0;
+      const double r2 = (xc - px) * (xc - px) + (yc - py) * (yc - py) + (zc - pz) * (zc - pz);
+      aret = r2 < 0.2 * 0.2 ? 1 : -1;
+    } else if (a->app == 1) {
       /* Refinement::FirstDerivative refinement_package.cpp:92-122 over the interior of one
        * component; CheckAllRefinement :55-90: a "refine" at or above the criterion's max level
        * becomes "same" (:78-81); packages without a CheckRefinementBlock vote "derefine" */
@@ -2406,6 +2468,194 @@ static void amr_tag(struct OrcAmr *a, const double *U) {
       }
     }
   }
+}
+
+
+/* ---- remesh of face / edge / node fields (mesh-amr_loadbalance.cpp:663-1010) ---- */
+static void te_field_init(TeField *F, const OrcMesh *m, double *U, double *Uc, int ncomp, int kind) {
+  F->m = m;
+  F->U = U;
+  F->Uc = Uc;
+  F->ncomp = ncomp;
+  F->nel = orc_te_num_elements(kind);
+  orc_te_extents(m, kind, F->pn);
+  for (int d = 0; d < 3; ++d) F->cpn[d] = m->cn[d] + (kind != ORC_TE_CELL && m->cn[d] > 1 ? 1 : 0);
+  F->blk_sz = (size_t)F->nel * ncomp * F->pn[2] * F->pn[1] * F->pn[0];
+  F->cblk_sz = (size_t)F->nel * ncomp * F->cpn[2] * F->cpn[1] * F->cpn[0];
+}
+static void te_alloc(const OrcMesh *m, int f, double **U, double **Uc) {
+  TeField F;
+  te_field_init(&F, m, NULL, NULL, kTeNcomp[f], f + 1);
+  *U = (double *)calloc((size_t)m->nblocks * F.blk_sz, sizeof(double));
+  *Uc = (double *)calloc((size_t)m->nblocks * F.cblk_sz, sizeof(double));
+}
+/* the fixture generator's problem generator: a code in every entry of every array */
+static void te_ic(struct OrcAmr *a) {
+  for (int f = 0; f < 3; ++f) {
+    TeField F;
+    te_field_init(&F, a->m, a->te_U[f], a->te_Uc[f], kTeNcomp[f], f + 1);
+    const size_t per = (size_t)F.pn[2] * F.pn[1] * F.pn[0];
+    for (int b = 0; b < a->m->nblocks; ++b)
+      for (int el = 0; el < F.nel; ++el)
+        for (int c = 0; c < F.ncomp; ++c)
+          for (size_t q = 0; q < per; ++q)
+            F.U[(size_t)b * F.blk_sz + ((size_t)el * F.ncomp + c) * per + q] =
+                (b + 1) * 1.0e6 + el * 1.0e5 + c * 5.0e4 + (double)q;
+  }
+}
+
+static void te_remesh(struct OrcAmr *a, OrcMesh *nm) {
+  const OrcMesh *m = a->m;
+  const int nleaf = ndaughters(m);
+  int *ncount = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  int *nflag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  int *newly = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  double *nU[3], *nUc[3];
+  for (int f = 0; f < 3; ++f) {
+    const int kind = f + 1;
+    te_alloc(nm, f, &nU[f], &nUc[f]);
+    TeField O, N;
+    te_field_init(&O, m, a->te_U[f], a->te_Uc[f], kTeNcomp[f], kind);
+    te_field_init(&N, nm, nU[f], nUc[f], kTeNcomp[f], kind);
+    const int nc = O.ncomp;
+    for (int nb = 0; nb < nm->nblocks; ++nb) {
+      const Loc *nl = &nm->blocks[nb].loc;
+      int ob = find_leaf(m, nl);
+      if (ob >= 0) { /* kept: the block object with all its data and counters */
+        memcpy(N.U + (size_t)nb * N.blk_sz, O.U + (size_t)ob * O.blk_sz, O.blk_sz * sizeof(double));
+        memcpy(N.Uc + (size_t)nb * N.cblk_sz, O.Uc + (size_t)ob * O.cblk_sz,
+               O.cblk_sz * sizeof(double));
+        ncount[nb] = a->deref_count[ob];
+        nflag[nb] = a->refine_flag[ob];
+        continue;
+      }
+      if (nl->level > 0) {
+        const Loc par = parent_of(m, nl);
+        ob = find_leaf(m, &par);
+        if (ob >= 0) { /* refined */
+          newly[nb] = 1;
+          for (int el = 0; el < O.nel; ++el) {
+            int top[3], sh[3], hi[3];
+            te_top_offset(kind, el, top);
+            for (int d = 0; d < 3; ++d) {
+              /* TryRecvCoarseToFine :118-141 */
+              const int nint = m->n[d] == 1 ? 1 : m->ie[d] - m->is[d] + 1 + top[d];
+              sh[d] = (d < m->ndim && (nl->lx[d] & 1L)) ? nint / 2 : 0;
+              hi[d] = m->cn[d] == 1 ? 0 : m->cn[d] - 1 + top[d];
+            }
+            for (int c = 0; c < nc; ++c)
+              for (int k = 0; k <= hi[2]; ++k)
+                for (int j = 0; j <= hi[1]; ++j)
+                  for (int i = 0; i <= hi[0]; ++i)
+                    *te_c(&N, nb, el, c, k, j, i) =
+                        *te_f(&O, ob, el, c, k + sh[2], j + sh[1], i + sh[0]);
+          }
+          continue;
+        }
+      }
+      /* derefined: the daughters were leaves */
+      for (int q = 0; q < nleaf; ++q) {
+        const Loc dl = daughter(m, nl, q);
+        ob = find_leaf(m, &dl);
+        if (ob < 0) {
+          fprintf(stderr, "oracle: remesh cannot find the origin of a new block\n");
+          abort();
+        }
+        for (int el = 0; el < O.nel; ++el) {
+          int top[3], s[3], e[3], sh[3];
+          te_top_offset(kind, el, top);
+          /* Restrict over GetInteriorRestrict: the coarse interior of the element */
+          for (int d = 0; d < 3; ++d) {
+            s[d] = m->cis[d];
+            e[d] = m->cn[d] == 1 ? 0 : m->cie[d] + top[d];
+          }
+          for (int c = 0; c < nc; ++c)
+            for (int k = s[2]; k <= e[2]; ++k)
+              for (int j = s[1]; j <= e[1]; ++j)
+                for (int i = s[0]; i <= e[0]; ++i) te_restrict(&O, kind, ob, el, c, k, j, i);
+          /* TryRecvFineToCoarse :210-232: shared elements come from the upper daughter */
+          for (int d = 0; d < 3; ++d) {
+            const int ox = (int)(dl.lx[d] & 1L);
+            if (d < m->ndim && ox == 0) e[d] -= top[d];
+            sh[d] = (ox == 0 || d >= m->ndim) ? 0 : (e[d] - s[d] + 1 - top[d]);
+          }
+          for (int c = 0; c < nc; ++c)
+            for (int k = s[2]; k <= e[2]; ++k)
+              for (int j = s[1]; j <= e[1]; ++j)
+                for (int i = s[0]; i <= e[0]; ++i)
+                  *te_f(&N, nb, el, c, k + sh[2], j + sh[1], i + sh[0]) =
+                      *te_c(&O, ob, el, c, k, j, i);
+        }
+      }
+    }
+    /* ProlongateShared over GetInteriorProlongate of the new fine blocks (:925-937):
+     * CalcIndices(InteriorRecv, prores) = the coarse interior of the element +- ng / 2 */
+    for (int nb = 0; nb < nm->nblocks; ++nb) {
+      if (!newly[nb]) continue;
+      for (int el = 0; el < N.nel; ++el) {
+        int top[3], s[3], e[3];
+        te_top_offset(kind, el, top);
+        for (int d = 0; d < 3; ++d) {
+          const int g2 = d < nm->ndim ? nm->ng / 2 : 0;
+          s[d] = nm->cis[d] - g2;
+          e[d] = (nm->cn[d] == 1 ? 0 : nm->cie[d] + top[d]) + g2;
+        }
+        for (int c = 0; c < nc; ++c)
+          for (int k = s[2]; k <= e[2]; ++k)
+            for (int j = s[1]; j <= e[1]; ++j)
+              for (int i = s[0]; i <= e[0]; ++i) te_prolongate_shared(&N, kind, nb, el, c, k, j, i, 0);
+      }
+    }
+  }
+  /* :958-990: shared elements of new fine blocks from neighbours that were fine already
+   * (ownership favours old blocks), then the internal elements of the new fine blocks */
+  g_newly_refined = newly;
+  for (int f = 0; f < 3; ++f) exchange_te_impl(nm, nU[f], nUc[f], kTeNcomp[f], f + 1, 0, 0);
+  g_newly_refined = NULL;
+  for (int f = 0; f < 3; ++f) {
+    const int kind = f + 1;
+    TeField N;
+    te_field_init(&N, nm, nU[f], nUc[f], kTeNcomp[f], kind);
+    for (int nb = 0; nb < nm->nblocks; ++nb) {
+      if (!newly[nb]) continue;
+      for (int el = 0; el < N.nel; ++el) {
+        int ftop[3];
+        te_top_offset(kind, el, ftop);
+        for (int q = 0; q < 8; ++q) {
+          int ctop[3], s[3], e[3];
+          te_top_offset(kCelKind[q], kCelEl[q], ctop);
+          if (!te_is_submanifold(ftop, ctop)) continue;
+          for (int d = 0; d < 3; ++d) {
+            const int g2 = d < nm->ndim ? nm->ng / 2 : 0;
+            s[d] = nm->cis[d] - g2;
+            e[d] = (nm->cn[d] == 1 ? 0 : nm->cie[d] + ctop[d]) + g2;
+          }
+          for (int c = 0; c < N.ncomp; ++c)
+            for (int k = s[2]; k <= e[2]; ++k)
+              for (int j = s[1]; j <= e[1]; ++j)
+                for (int i = s[0]; i <= e[0]; ++i)
+                  te_prolongate_internal(&N, ftop, ctop, nb, el, c, k, j, i);
+        }
+      }
+    }
+  }
+  /* :992-1003: the regular ownership again, then the exchange of everything */
+  for (int f = 0; f < 3; ++f) exchange_te_impl(nm, nU[f], nUc[f], kTeNcomp[f], f + 1, 0, 0);
+  for (int f = 0; f < 3; ++f) {
+    free(a->te_U[f]);
+    free(a->te_Uc[f]);
+    a->te_U[f] = nU[f];
+    a->te_Uc[f] = nUc[f];
+  }
+  orc_mesh_destroy(a->m);
+  free(a->deref_count);
+  free(a->refine_flag);
+  free(a->last_tag);
+  free(newly);
+  a->m = nm;
+  a->deref_count = ncount;
+  a->refine_flag = nflag;
+  a->last_tag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
 }
 
 static int cmp_level_desc(const void *x, const void *y) {
@@ -2468,6 +2718,10 @@ static int amr_remesh(struct OrcAmr *a) {
   /* ---- RedistributeAndRefineMeshBlocks ---- */
   OrcMesh *nm = amr_make_mesh(a, &t);
   free(t.leaf);
+  if (a->app == 2) {
+    te_remesh(a, nm);
+    return 1;
+  }
   /* the application state on the new mesh; only the base container is carried over (:667) */
   typedef struct {
     double *U, *Uc;
@@ -2615,6 +2869,10 @@ static void amr_init_burgers(struct OrcAmr *a) {
 void orc_amr_init(struct OrcAmr *a) {
   if (a->app == 1) {
     amr_init_burgers(a);
+    return;
+  }
+  if (a->app == 2) {
+    amr_init_te(a);
     return;
   }
   int done;

@@ -256,6 +256,28 @@ for n in tecomm_s16_b8_l2_3d_tothroe tecomm_s32_b8_l3_2d_tothroe; do
   python3 -c "import numpy as np,sys; g=np.load(sys.argv[1]); np.savez_compressed(sys.argv[1], **{k: g[k] for k in ('U_0','meta','bounds')})" "$OUT/$n.npz"
 done
 fi
+# adaptive meshes with face / edge / node fields (teamr_dump_main.cpp: the fields never evolve, a
+# moving geometric criterion refines and derefines every cycle): remesh data movement of
+# non-cell-centred fields, kept as CRC-32 per block, field and cycle
+if [ -z "${SKIP_TEAMR:-}" ]; then
+if [ ! -x "$WORK/teamr_dump" ] || [ "$HERE/teamr_dump_main.cpp" -nt "$WORK/teamr_dump" ]; then
+  $CXX $FLAGS $INC "$HERE/teamr_dump_main.cpp" $LIBS -o "$WORK/teamr_dump"
+fi
+run_teamr () { # name ndim nx nb numlevel ncycles
+  local name=$1 ndim=$2 nx=$3 nb=$4 numlevel=$5 ncyc=$6
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  local nx3=$nx nb3=$nb; if [ "$ndim" = 2 ]; then nx3=1; nb3=1; fi
+  printf '<parthenon/job>\nproblem_id = teamr\n<parthenon/mesh>\nrefinement = adaptive\nnumlevel = %d\nnghost = 2\nderefine_count = 2\n' $numlevel > deck.pin
+  printf 'nx1 = %d\nx1min = -0.5\nx1max = 0.5\nix1_bc = periodic\nox1_bc = periodic\n' $nx >> deck.pin
+  printf 'nx2 = %d\nx2min = -0.5\nx2max = 0.5\nix2_bc = periodic\nox2_bc = periodic\n' $nx >> deck.pin
+  printf 'nx3 = %d\nx3min = -0.5\nx3max = 0.5\nix3_bc = periodic\nox3_bc = periodic\n' $nx3 >> deck.pin
+  printf '<parthenon/meshblock>\nnx1 = %d\nnx2 = %d\nnx3 = %d\n<parthenon/time>\ntlim = 1.0\nnlim = 0\n' $nb $nb $nb3 >> deck.pin
+  PB2_CYCLES=$ncyc PB2_DUMP_PREFIX="$d/U" "$WORK/teamr_dump" -i deck.pin > run.log 2>&1
+  (cd "$HERE" && python3 pack_teamr.py "$d" "$OUT/$name.npz")
+}
+run_teamr teamr_a32_b8_l3_2d_crc 2 32 8 3 6
+run_teamr teamr_a16_b4_l2_3d_crc 3 16 4 2 4
+fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1
 run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4

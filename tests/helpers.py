@@ -210,3 +210,8 @@ def tecomm_initial(nblocks, nel, ncomp, nk, nj, ni, first_gid=0):
     c = np.arange(ncomp).reshape(1, 1, -1, 1, 1, 1)
     flat = np.arange(nk * nj * ni).reshape(1, 1, 1, nk, nj, ni)
     return np.ascontiguousarray((gid + 1) * 1.0e6 + e * 1.0e5 + c * 5.0e4 + flat)
+
+
+# adaptive meshes with face / edge / node fields (tests/golden/refgen/teamr_dump_main.cpp):
+# (name, ndim, mesh cells, block cells, numlevel)
+TEAMR = [("teamr_a32_b8_l3_2d_crc", 2, 32, 8, 3), ("teamr_a16_b4_l2_3d_crc", 3, 16, 4, 2)]
