@@ -42,6 +42,10 @@ int pb2h_topology_regrid(pb2h_sim *sim, const int *tags, int nblocks, int *chang
 /* the per-block derefinement counters (MeshRefinement::deref_count_) of a topology object:
  * set != 0 stores counts[] into the blocks, set == 0 reads them out */
 int pb2h_topology_derefine_counts(pb2h_sim *sim, int *counts, int nblocks, int set);
+/* application "tecomm" on an adaptive mesh: tag every block with the geometric criterion of
+ * `cycle` (tests/golden/refgen/teamr_dump_main.cpp), then adapt the mesh
+ * (Mesh::LoadBalancingAndAdaptiveMeshRefinement); *changed = 1 if blocks were (de)refined */
+int pb2h_sim_tag_and_remesh(pb2h_sim *sim, int cycle, int *changed);
 int pb2h_sim_destroy(pb2h_sim *sim);
 
 /* EvolutionDriver pieces (driver.cpp:67-193): what Execute does before its loop, N cycles

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpb200_host.so")
 SYMBOLS = [
     "pb2h_last_error", "pb2h_sim_create", "pb2h_topology_create", "pb2h_topology_regrid",
     "pb2h_topology_derefine_counts",
-    "pb2h_sim_destroy",
+    "pb2h_sim_destroy", "pb2h_sim_tag_and_remesh",
     "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
@@ -186,6 +186,7 @@ def lib():
     for f in ("pb2h_sim_destroy", "pb2h_sim_pre_execute", "pb2h_sim_execute", "pb2h_sim_sync"):
         getattr(L, f).argtypes = [vp]
     L.pb2h_topology_regrid.argtypes = [vp, ip, C.c_int, ip]
+    L.pb2h_sim_tag_and_remesh.argtypes = [vp, C.c_int, ip]
     L.pb2h_topology_derefine_counts.argtypes = [vp, ip, C.c_int, C.c_int]
     L.pb2h_sim_cycle.argtypes = [vp, C.c_int]
     L.pb2h_sim_cycle_phase.argtypes = [vp, C.c_int]
@@ -382,6 +383,12 @@ class Simulation(_Base):
     def regrid(self):
         """second half: LoadBalancingAndAdaptiveMeshRefinement + SetGlobalTimeStep"""
         check(lib().pb2h_sim_cycle_phase(self.h, 1))
+
+    def tag_and_remesh(self, cycle):
+        """application tecomm, adaptive mesh: tag with the criterion of `cycle` and remesh"""
+        changed = C.c_int(0)
+        check(lib().pb2h_sim_tag_and_remesh(self.h, cycle, C.byref(changed)))
+        return bool(changed.value)
 
     def execute(self):
         check(lib().pb2h_sim_execute(self.h))

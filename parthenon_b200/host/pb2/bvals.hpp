@@ -116,6 +116,11 @@ struct BvarsCache {
   uint64_t built_generation = 0;
   ExchangePlan plan;
   bool plan_built = false;
+  // the ownership of shared elements changed (end of a remesh): plan and tables are rebuilt
+  void Invalidate() {
+    plan_built = false;
+    built_generation = 0;
+  }
   std::vector<Variable *> vars;
   pb2_bnd_table *copy_local = nullptr;
   // uniform meshes, dense fields, one batch per device: local channels need no region table —

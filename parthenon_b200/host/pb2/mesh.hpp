@@ -14,6 +14,7 @@
 #include <memory>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "device.hpp"
@@ -325,6 +326,9 @@ class Mesh {
   void FindNeighbors(MeshBlock &mb) const;
   std::vector<NeighborBlock> FindNeighbors(const LogicalLocation &loc) const;
   mutable std::unordered_map<int, std::array<bool, 27>> ownership_;
+  // blocks created by refinement in the remesh in progress: they rank below older blocks of
+  // their level when shared elements are owned (block_ownership.cpp:48-54); empty otherwise
+  std::unordered_set<LogicalLocation, LogicalLocationHash> newly_refined_;
   bool WrapLocation(const LogicalLocation &in, LogicalLocation &out) const;
   int64_t BlocksAtLevel(int level, int d) const;
 };

@@ -237,6 +237,21 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     return par;
   };
 
+  // face / edge / node fields: the fine elements inside coarse edges, faces and cells of NEW
+  // children are prolongated only after an exchange in which older fine blocks own the shared
+  // elements (mesh-amr_loadbalance.cpp:958-990); the regions are collected here
+  bool has_te = false;
+  std::vector<pb2_prores_region> te_internal, te_toth_roe;
+  const TE te_containers[8] = {TE::NN, TE::E3, TE::E2, TE::E1, TE::F1, TE::F2, TE::F3, TE::CC};
+  auto is_submanifold = [](TE f, TE cnt) { // basic_types.hpp:207-232
+    int more = 0;
+    for (int d = 0; d < 3; ++d) {
+      if (TopologicalOffset(cnt, d) && !TopologicalOffset(f, d)) return false;
+      more += TopologicalOffset(f, d) && !TopologicalOffset(cnt, d);
+    }
+    return more > 0;
+  };
+
   for (auto &nvp : new_md->GetVariableVector()) {
     Variable &nv = *nvp;
     // the fields a remesh carries over: pmb->vars_cc_ (Independent / FillGhost cell-centred)
@@ -302,7 +317,43 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     if (recv_off[nranks] > 0) recv_slab.Allocate(sizeof(Real) * recv_off[nranks], st);
 
     std::vector<pb2_copy_region> copies, sends;
-    std::vector<pb2_prores_region> restricts, prolongs;
+    std::vector<pb2_prores_region> restricts, prolongs, te_restricts, te_prolongs;
+    const bool te = nv.topological_type() != TopologicalType::Cell;
+    has_te = has_te || te;
+    const std::vector<TE> els = GetTopologicalElements(nv.topological_type());
+    const int tnc = nv.TensorComponents();
+    // one region of element number e (storage order) of block `lidx` of variable v, box given
+    // in the coarse index space
+    auto prores_te = [&](Variable &v, const MeshBlock *pmb, int lidx, int e, TE fel, const TE *cel,
+                         const int bs[3], const int bn[3]) {
+      pb2_prores_region p{};
+      p.fine = v.data() + lidx * v.block_stride + static_cast<int64_t>(e) * tnc * v.comp_stride;
+      p.coarse =
+          v.coarse() + lidx * v.cblock_stride + static_cast<int64_t>(e) * tnc * v.ccomp_stride;
+      const UniformCartesian cc(pmb->coords, 2);
+      for (int d = 0; d < 3; ++d) {
+        p.s[d] = bs[d];
+        p.n[d] = bn[d];
+        p.fine_is[d] = pmb->cellbounds.Bounds(d, IndexDomain::interior).s;
+        p.coarse_is[d] = pmb->c_cellbounds.Bounds(d, IndexDomain::interior).s;
+        p.fine_xmin[d] = pmb->coords.GetXmin()[d];
+        p.fine_dx[d] = pmb->coords.Dx()[d];
+        p.coarse_xmin[d] = cc.GetXmin()[d];
+        p.coarse_dx[d] = cc.Dx()[d];
+        p.ftop[d] = TopologicalOffset(fel, d);
+        p.ctop[d] = cel ? TopologicalOffset(*cel, d) : 0;
+      }
+      p.ncomp = tnc;
+      p.fine_stride_j = v.ni;
+      p.fine_stride_k = v.ni * v.nj;
+      p.fine_stride_c = static_cast<int32_t>(v.comp_stride);
+      p.coarse_stride_j = v.cni;
+      p.coarse_stride_k = v.cni * v.cnj;
+      p.coarse_stride_c = static_cast<int32_t>(v.ccomp_stride);
+      p.ndim = ndim;
+      p.status = PB2_REGION_ALLOCATED;
+      return p;
+    };
     auto whole_block = [&](pb2_copy_region &r, const Real *src, Real *dst, bool coarse) {
       r.src = src;
       r.dst = dst;
@@ -324,7 +375,21 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
       if (!mine_old && !mine_new) continue;
       // -- sender side: merged children are restricted first (GetInteriorRestrict), then the
       //    data leaves in a slab if the new owner is another device
-      if (mine_old && pc.kind == 2) {
+      if (mine_old && pc.kind == 2 && te) {
+        // RestrictAverage per element over its coarse interior (GetInteriorRestrict)
+        const int ol = old_local(pc.old_gid);
+        const MeshBlock *ob = old_blocks[ol].get();
+        for (size_t e = 0; e < els.size(); ++e) {
+          int bs[3], bn[3];
+          for (int d = 0; d < 3; ++d) {
+            const IndexRange cb = ob->c_cellbounds.Bounds(d, IndexDomain::interior, els[e]);
+            bs[d] = cb.s;
+            bn[d] = cb.e - cb.s + 1;
+          }
+          te_restricts.push_back(
+              prores_te(ov, ob, ol, static_cast<int>(e), els[e], nullptr, bs, bn));
+        }
+      } else if (mine_old && pc.kind == 2) {
         const int ol = old_local(pc.old_gid);
         const MeshBlock *ob = old_blocks[ol].get();
         pb2_prores_region p{};
@@ -383,6 +448,38 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
         r.src_stride_k = nv.ni * nv.nj;
         r.src_stride_c = static_cast<int32_t>(nv.comp_stride);
         copies.push_back(r);
+        if (te) {
+          // ProlongateShared per element over its coarse interior +- nghost / 2; the internal
+          // elements follow after the first exchange (see below)
+          for (size_t e = 0; e < els.size(); ++e) {
+            auto box_of = [&](TE el, int bs[3], int bn[3]) {
+              for (int d = 0; d < 3; ++d) {
+                const IndexRange cb = pmb->c_cellbounds.Bounds(d, IndexDomain::interior, el);
+                const int g2 = d < ndim ? ng / 2 : 0;
+                bs[d] = cb.s - g2;
+                bn[d] = cb.e - cb.s + 1 + 2 * g2;
+              }
+            };
+            int bs[3], bn[3];
+            box_of(els[e], bs, bn);
+            const int ei = static_cast<int>(e);
+            te_prolongs.push_back(prores_te(nv, pmb, nb, ei, els[e], nullptr, bs, bn));
+            if (nv.metadata().InternalProlongationOp() == 1) {
+              const TE ccel = TE::CC;
+              box_of(ccel, bs, bn);
+              pb2_prores_region q = prores_te(nv, pmb, nb, ei, els[e], &ccel, bs, bn);
+              q.fine -= static_cast<int64_t>(ei) * tnc * nv.comp_stride; // points at element F1
+              te_toth_roe.push_back(q);
+            } else {
+              for (const TE &cel : te_containers)
+                if (is_submanifold(els[e], cel)) {
+                  box_of(cel, bs, bn);
+                  te_internal.push_back(prores_te(nv, pmb, nb, ei, els[e], &cel, bs, bn));
+                }
+            }
+          }
+          continue;
+        }
         // ProlongateShared over GetInteriorProlongate: coarse interior +- nghost / 2
         // (bnd_info.cpp:199-203)
         pb2_prores_region p{};
@@ -415,6 +512,35 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
         // merged: the child's restricted interior lands in the parent's quadrant / octant
         // (TryRecvFineToCoarse :225-246)
         const LogicalLocation dloc = daughter_of(pmb->loc, pc.q);
+        if (te) {
+          // per element; shared elements come from the upper daughter: the lower one leaves out
+          // its last entry along every direction the element is displaced in (:216-228)
+          for (size_t e = 0; e < els.size(); ++e) {
+            pb2_copy_region r{};
+            r.src = src_coarse + static_cast<int64_t>(e) * tnc * nv.ccomp_stride;
+            r.dst = nv.data() + nb * nv.block_stride + static_cast<int64_t>(e) * tnc * nv.comp_stride;
+            r.ncomp = tnc;
+            r.flag_slot = -1;
+            r.status = PB2_REGION_ALLOCATED;
+            for (int d = 0; d < 3; ++d) {
+              const IndexRange cb = pmb->c_cellbounds.Bounds(d, IndexDomain::interior, els[e]);
+              const int top = d < ndim ? TopologicalOffset(els[e], d) : 0;
+              const bool upper = d < ndim && (dloc.lx[d] & 1);
+              const int last = cb.e - (d < ndim && !upper ? top : 0);
+              r.ss[d] = cb.s;
+              r.n[d] = last - cb.s + 1;
+              r.ds[d] = cb.s + (upper ? r.n[d] - top : 0);
+            }
+            r.src_stride_j = nv.cni;
+            r.src_stride_k = nv.cni * nv.cnj;
+            r.src_stride_c = static_cast<int32_t>(nv.ccomp_stride);
+            r.dst_stride_j = nv.ni;
+            r.dst_stride_k = nv.ni * nv.nj;
+            r.dst_stride_c = static_cast<int32_t>(nv.comp_stride);
+            copies.push_back(r);
+          }
+          continue;
+        }
         pb2_copy_region r{};
         whole_block(r, src_coarse, nv.data() + nb * nv.block_stride, true);
         for (int d = 0; d < 3; ++d) {
@@ -431,18 +557,27 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
       }
     }
     pb2_bnd_table *t_res = nullptr, *t_send = nullptr, *t_copy = nullptr, *t_pro = nullptr;
+    pb2_bnd_table *t_res_te = nullptr, *t_pro_te = nullptr;
+    PB2_CHECK(pb2_prores_table_create(&t_res_te, te_restricts.data(),
+                                      static_cast<int64_t>(te_restricts.size())));
+    PB2_CHECK(pb2_prores_table_create(&t_pro_te, te_prolongs.data(),
+                                      static_cast<int64_t>(te_prolongs.size())));
     PB2_CHECK(pb2_prores_table_create(&t_res, restricts.data(), static_cast<int64_t>(restricts.size())));
     PB2_CHECK(pb2_copy_table_create(&t_send, sends.data(), static_cast<int64_t>(sends.size())));
     PB2_CHECK(pb2_copy_table_create(&t_copy, copies.data(), static_cast<int64_t>(copies.size())));
     PB2_CHECK(pb2_prores_table_create(&t_pro, prolongs.data(), static_cast<int64_t>(prolongs.size())));
     PB2_CHECK(pb2_restrict(t_res, st));
+    PB2_CHECK(pb2_restrict_te(t_res_te, st));
     PB2_CHECK(pb2_copy(t_send, nullptr, st));
     if (nranks > 1) // blocks that change device: one grouped NCCL send/recv per peer
       PB2_CHECK(pb2_comm_exchange(comm, send_slab.get<Real>(), send_off.data(),
                                   recv_slab.get<Real>(), recv_off.data(), st));
     PB2_CHECK(pb2_copy(t_copy, nullptr, st));
     PB2_CHECK(pb2_prolongate(t_pro, nv.metadata().ProlongationOp(), st));
+    PB2_CHECK(pb2_prolongate_te(t_pro_te, nv.metadata().ProlongationOp(), st));
     PB2_CHECK(pb2_stream_sync(st));
+    pb2_bnd_table_destroy(t_res_te);
+    pb2_bnd_table_destroy(t_pro_te);
     pb2_bnd_table_destroy(t_res);
     pb2_bnd_table_destroy(t_send);
     pb2_bnd_table_destroy(t_copy);
@@ -451,6 +586,32 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
   const auto t3 = now();
   old_md.reset(); // the old slabs go away here
   const auto t4 = now();
+  if (has_te) {
+    // A newly refined block may have neighbours that were fine already: its prolongated shared
+    // elements must give way to theirs.  One exchange with an ownership that ranks new fine
+    // blocks below old ones (:958-984), then the internal elements of the new blocks (:986-990)
+    for (int n = 0; n < nbtotal; ++n) {
+      const LogicalLocation &nl = loclist[n];
+      if (old_gid.count(nl) == 0 && nl.level > 0 && old_gid.count(parent_of(nl)) > 0)
+        newly_refined_.insert(nl);
+    }
+    ownership_.clear();
+    CommunicateBoundaries(new_md, true);
+    pb2_bnd_table *t_int = nullptr, *t_tr = nullptr;
+    PB2_CHECK(pb2_prores_table_create(&t_int, te_internal.data(),
+                                      static_cast<int64_t>(te_internal.size())));
+    PB2_CHECK(pb2_prores_table_create(&t_tr, te_toth_roe.data(),
+                                      static_cast<int64_t>(te_toth_roe.size())));
+    PB2_CHECK(pb2_prolongate_internal(t_int, st));
+    PB2_CHECK(pb2_prolongate_toth_roe(t_tr, st));
+    PB2_CHECK(pb2_stream_sync(st));
+    pb2_bnd_table_destroy(t_int);
+    pb2_bnd_table_destroy(t_tr);
+    // the regular ownership again (:992-996): plan and tables of the exchange are rebuilt
+    newly_refined_.clear();
+    ownership_.clear();
+    new_md->bvars().Invalidate();
+  }
   // PreCommFillDerived; CommunicateBoundaries; FillDerived (:1000-1003)
   Update::PreCommFillDerived(new_md.get());
   CommunicateBoundaries(new_md, true);

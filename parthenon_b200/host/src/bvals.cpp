@@ -334,9 +334,6 @@ void Rebuild(MeshData<Real> *md) {
   if (pm->multilevel) {
     std::vector<pb2_prores_region> rsend[2], rset[2], pro[2][3];
     std::vector<pb2_prores_region> te_rsend[2], te_rset[2], te_pro[2][3], te_int[2], te_tr[2];
-    PARTHENON_REQUIRE(all_cell || !pm->adaptive,
-                      "non-cell-centred FillGhost fields on adaptive meshes are not supported "
-                      "by this build");
     std::array<bool, 27> all_true;
     all_true.fill(true);
     // containers of the internal prolongation in the order the reference visits them

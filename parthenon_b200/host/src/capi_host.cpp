@@ -141,6 +141,7 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
       s->pman.app_input->MeshProblemGenerator = sparse_advection_example::MeshProblemGenerator;
     }
     RegisterExampleUserBoundaries(s->pman.app_input.get());
+    tecomm_example::SetCriterionCycle(0);
     s->pman.ParthenonInitEnvFromString(deck, SplitLines(overrides));
     s->pman.SetRank(rank, nranks, nccl_id);
     s->pman.ParthenonInitPackagesAndMesh(Leaves(leaves, nleaves));
@@ -201,6 +202,20 @@ int pb2h_topology_derefine_counts(pb2h_sim *sim, int *counts, int nblocks, int s
       else
         counts[b] = pm->block_list[b]->deref_count;
     }
+  });
+}
+
+// tecomm on an adaptive mesh: one "cycle" of the fixture generator — tag every block with the
+// criterion of `cycle`, then LoadBalancingAndAdaptiveMeshRefinement
+int pb2h_sim_tag_and_remesh(pb2h_sim *sim, int cycle, int *changed) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    PARTHENON_REQUIRE(!sim->topology_only && pm->DefaultNumPartitions() == 1,
+                      "tag_and_remesh needs a simulation with one MeshData per rank");
+    tecomm_example::SetCriterionCycle(cycle);
+    Refinement::Tag(pm->mesh_data.GetOrAdd("base", 0).get());
+    pm->LoadBalancingAndAdaptiveMeshRefinement(sim->pman.pinput.get(), sim->pman.app_input.get());
+    if (changed) *changed = pm->modified ? 1 : 0;
   });
 }
 

@@ -283,7 +283,9 @@ const std::array<bool, 27> &Mesh::Ownership(int gid) const {
       for (int o3 = -1; o3 <= 1; ++o3) {
         bool own = true;
         for (const NeighborBlock &n : nbs) {
-          const bool less = loc.level != n.loc.level ? loc.level < n.loc.level : gid < n.gid;
+          const int la = 2 * loc.level - (newly_refined_.count(loc) ? 1 : 0);
+          const int lb = 2 * n.loc.level - (newly_refined_.count(n.loc) ? 1 : 0);
+          const bool less = la != lb ? la < lb : gid < n.gid;
           if (less && loc.IsNeighborOfTE(n.origin_loc, {o1, o2, o3})) {
             own = false;
             break;

@@ -6,6 +6,24 @@
 namespace tecomm_example {
 using namespace parthenon;
 
+namespace {
+int g_cycle = 0;
+void TagByPosition(MeshData<Real> *md, std::vector<AmrTag> &tags) {
+  const int ndim = md->GetMeshPointer()->ndim;
+  for (int b = 0; b < md->NumBlocks(); ++b) {
+    const RegionSize &bs = md->GetBlock(b)->block_size;
+    const Real xc = 0.5 * (bs.xmin_[0] + bs.xmax_[0]), yc = 0.5 * (bs.xmin_[1] + bs.xmax_[1]);
+    const Real zc = ndim > 2 ? 0.5 * (bs.xmin_[2] + bs.xmax_[2]) : 0.0;
+    const Real px = -0.25 + 0.125 * g_cycle, py = -0.125 + 0.0625 * g_cycle,
+               pz = ndim > 2 ? 0.125 : 0.0;
+    const Real r2 = (xc - px) * (xc - px) + (yc - py) * (yc - py) + (zc - pz) * (zc - pz);
+    tags[b] = r2 < 0.2 * 0.2 ? AmrTag::refine : AmrTag::derefine;
+  }
+}
+} // namespace
+
+void SetCriterionCycle(int cycle) { g_cycle = cycle; }
+
 Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
   Packages_t packages;
   auto pkg = std::make_shared<StateDescriptor>("tecomm");
@@ -34,6 +52,7 @@ Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
   pkg->AddField("face", mface);
   pkg->AddField("edge", medge);
   pkg->AddField("node", mnode);
+  pkg->CheckRefinementMesh = TagByPosition;
   packages.Add(pkg);
   return packages;
 }

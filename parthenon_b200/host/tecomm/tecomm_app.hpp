@@ -10,6 +10,10 @@
 #include "pb2/parthenon.hpp"
 
 namespace tecomm_example {
+// adaptive runs (refinement = adaptive): the criterion of the reference-side fixture generator
+// tests/golden/refgen/teamr_dump_main.cpp — refine the blocks whose centre lies within 0.2 of a
+// point that moves with the cycle number, derefine all others.  The fields never evolve.
+void SetCriterionCycle(int cycle);
 parthenon::Packages_t ProcessPackages(std::unique_ptr<parthenon::ParameterInput> &pin);
 void MeshProblemGenerator(parthenon::MeshData<parthenon::Real> *md, parthenon::ParameterInput *pin);
 } // namespace tecomm_example

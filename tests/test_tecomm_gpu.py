@@ -156,10 +156,34 @@ def test_non_cell_centred_physical_boundaries_bit_exact(name, ndim, nx, nb, ng, 
         sim.close()
 
 
-def test_unsupported_combinations_fail_loudly():
-    """adaptive remeshing of non-cell-centred fields is not built: the framework must say so
-    instead of moving something else"""
-    ov = deck_overrides(3, (8,) * 3, 2, (2,) * 3, refinement="adaptive")
-    ov["parthenon/mesh/numlevel"] = 2
-    with pytest.raises(RuntimeError, match="adaptive"):
-        host.Simulation(app="tecomm", overrides=ov)
+@pytest.mark.parametrize("name,ndim,nx,nb,numlevel", H.TEAMR)
+def test_adaptive_remesh_of_non_cell_centred_fields_crc(name, ndim, nx, nb, numlevel):
+    """adaptive meshes: every cycle a moving geometric criterion refines some blocks and derefines
+    others while the fields never evolve, so the state after each remesh pins the data movement
+    of face / edge / node fields (element-wise restriction into new parents with shared elements
+    from the upper daughter, shared prolongation into new children, an exchange in which older
+    fine blocks own shared elements over newly refined ones, internal prolongation, the regular
+    exchange) — block lists and one CRC-32 per block and field against the reference"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+    ov = deck_overrides(ndim, (nb,) * 3, 2, (nx // nb,) * 3, refinement="adaptive")
+    ov.update({"parthenon/mesh/numlevel": numlevel, "parthenon/mesh/derefine_count": 2})
+    sim = host.Simulation(app="tecomm", overrides=ov)
+    try:
+        counts = set()
+        for c in range(int(g["ncycles"]) + 1):
+            if c:
+                sim.tag_and_remesh(c)
+            leaves, _ = H.leaves_from_bounds(g[f"bounds_{c}"], full(nx), full(nb))
+            n = sim.info()["nblocks"]
+            assert n == len(leaves), c
+            assert np.array_equal(np.array([sim.block(b)["loc"] for b in range(n)]), leaves), c
+            for f, field in enumerate(("face", "edge", "node")):
+                got = sim.get_field("base", field)
+                assert got.shape == tuple(g[f"shape_{c}_{f}"])
+                bad = np.nonzero(H.block_crcs(got) != g[f"crc_{c}_{f}"])[0]
+                assert len(bad) == 0, (c, field, len(bad), bad[:8])
+            counts.add(n)
+        assert len(counts) > 2
+    finally:
+        sim.close()
