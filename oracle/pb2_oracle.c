@@ -767,16 +767,22 @@ static double restrict_face(const OrcMesh *m, const double *F, int ncomp, int b,
 /* Every coarse block overwrites the part of a face flux shared with a finer neighbour by
  * the area-weighted average of that neighbour's fine fluxes.  Region selection:
  * ForEachBoundary<flxcor_recv> (loop_utils.hpp:145-160): face neighbours one level finer. */
-int64_t orc_flux_correct(const OrcMesh *m, double *const F[3], int ncomp) {
+/* alloc (optional, stride astride, entry alloc[b * astride]): sparse fields — an unallocated
+ * sender sends a null message, which leaves the receiver's flux alone (no default fill for
+ * flxcor_recv, boundary_communication.cpp:311); an unallocated receiver sets nothing */
+static int64_t flux_correct_masked(const OrcMesh *m, double *const F[3], int ncomp,
+                                   const unsigned char *alloc, int astride) {
   int64_t moved = 0;
   if (!m->multilevel) return 0;
   for (int b = 0; b < m->nblocks; ++b) {
     const Block *blk = &m->blocks[b];
+    if (alloc != NULL && !alloc[b * astride]) continue;
     for (int n = 0; n < blk->nnb; ++n) {
       const Neighbor *nb = &blk->nb[n];
       const int dir = face_dir(nb->off);
       if (dir < 0 || dir >= m->ndim) continue;
       if (nb->loc.level != blk->loc.level + 1) continue;
+      if (alloc != NULL && !alloc[nb->gid * astride]) continue;
       /* the sender's matching region */
       const Block *sb = &m->blocks[nb->gid];
       int sn = -1;
@@ -809,6 +815,9 @@ int64_t orc_flux_correct(const OrcMesh *m, double *const F[3], int ncomp) {
     }
   }
   return moved;
+}
+int64_t orc_flux_correct(const OrcMesh *m, double *const F[3], int ncomp) {
+  return flux_correct_masked(m, F, ncomp, NULL, 0);
 }
 
 void orc_apply_bcs_coarse(const OrcMesh *m, double *Uc, int ncomp);
@@ -2952,6 +2961,7 @@ struct OrcSparse {
   double vx[ORC_NF], vy[ORC_NF], vz[ORC_NF], x0[ORC_NF], y0[ORC_NF];
   size_t ncell, nfield; /* per field: nblocks * ncell */
   double *U[ORC_NF], *U1[ORC_NF], *dUdt[ORC_NF], *flux[ORC_NF][3];
+  double *Uc[ORC_NF];   /* coarse buffers (multilevel meshes) */
   unsigned char *alloc; /* [nblocks][NF] */
   int *counter;         /* [nblocks][NF] dealloc_count of the control variable */
   double dt, time, allowed_dt;
@@ -2983,6 +2993,9 @@ OrcSparse *orc_sparse_create(const OrcMesh *m, double speed, double cfl, double 
     s->U1[f] = (double *)calloc(s->nfield, sizeof(double));
     s->dUdt[f] = (double *)calloc(s->nfield, sizeof(double));
     for (int d = 0; d < 3; ++d) s->flux[f][d] = (double *)calloc(s->nfield, sizeof(double));
+    s->Uc[f] = m->multilevel ? (double *)calloc((size_t)m->nblocks * m->cn[0] * m->cn[1] * m->cn[2],
+                                                sizeof(double))
+                             : NULL;
   }
   s->alloc = (unsigned char *)calloc((size_t)m->nblocks * ORC_NF, 1);
   s->counter = (int *)calloc((size_t)m->nblocks * ORC_NF, sizeof(int));
@@ -2995,6 +3008,7 @@ void orc_sparse_destroy(OrcSparse *s) {
     free(s->U[f]);
     free(s->U1[f]);
     free(s->dUdt[f]);
+    free(s->Uc[f]);
     for (int d = 0; d < 3; ++d) free(s->flux[f][d]);
   }
   free(s->alloc);
@@ -3014,11 +3028,135 @@ static void sparse_allocate(OrcSparse *st, int b, int f) {
   memset(st->U1[f] + o, 0, n);
   memset(st->dUdt[f] + o, 0, n);
   for (int d = 0; d < 3; ++d) memset(st->flux[f][d] + o, 0, n);
+  if (st->Uc[f]) {
+    const size_t cn = (size_t)st->m->cn[0] * st->m->cn[1] * st->m->cn[2];
+    memset(st->Uc[f] + (size_t)b * cn, 0, cn * sizeof(double));
+  }
+}
+
+/* the same exchange on a MULTILEVEL mesh: the allocation-aware forms of restriction (send and
+ * set), pack / unpack through the coarse buffers, and prolongation (ProResInfo::allocated,
+ * pr_loops.hpp:43-46 DoRefinementOp) */
+static void sparse_exchange_ml(OrcSparse *st, int f, double *U) {
+  const OrcMesh *m = st->m;
+  double *Uc = st->Uc[f];
+  const unsigned char *al = st->alloc;
+#define ALLOC(b) (al[(b)*ORC_NF + f])
+  int64_t nreg = orc_count_regions(m);
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
+  int64_t total = orc_pack(m, U, Uc, 1, NULL, off);
+  double *buf = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
+  unsigned char *flag = (unsigned char *)calloc((size_t)nreg, 1);
+  int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
+  first[0] = 0;
+  for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+  /* restriction of the send regions that face a coarser block */
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    if (!ALLOC(b)) continue;
+    for (int n = 0; n < blk->nnb; ++n)
+      if (blk->nb[n].origin_loc.level < blk->loc.level) {
+        int s[3], e[3];
+        orc_calc_indices(m, b, n, IR_SEND, 1, s, e);
+        restrict_region(m, U, Uc, 1, b, s, e);
+      }
+  }
+  orc_pack(m, U, Uc, 1, buf, off);
+  for (int b = 0; b < m->nblocks; ++b)
+    for (int n = 0; n < m->blocks[b].nnb; ++n) {
+      const int64_t r = first[b] + n;
+      if (!ALLOC(b)) continue;
+      for (int64_t q = off[r]; q < off[r + 1]; ++q)
+        if (fabs(buf[q]) >= st->alloc_thr) {
+          flag[r] = 1;
+          break;
+        }
+    }
+  /* receive: allocate on the first non-null message; set */
+  int *sender_region = (int *)malloc(sizeof(int) * (size_t)nreg);
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      const Block *sb = &m->blocks[nb->gid];
+      int sn = -1;
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          sn = q;
+          break;
+        }
+      if (sn < 0) abort();
+      sender_region[first[b] + n] = (int)(first[nb->gid] + sn);
+      if (flag[first[nb->gid] + sn] && !ALLOC(b)) sparse_allocate(st, b, f);
+    }
+  }
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    if (!ALLOC(b)) continue;
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 0, s, e);
+      const int64_t r = sender_region[first[b] + n];
+      const int coarse = nb->origin_loc.level < blk->loc.level;
+      const double *p = buf + off[r];
+      for (int k = s[2]; k <= e[2]; ++k)
+        for (int j = s[1]; j <= e[1]; ++j)
+          for (int i = s[0]; i <= e[0]; ++i) {
+            const double val = flag[r] ? *p : 0.0; /* sparse_default_val */
+            ++p;
+            if (coarse)
+              Uc[cidx(m, 1, b, 0, k, j, i)] = val;
+            else
+              U[fidx(m, 1, b, 0, k, j, i)] = val;
+          }
+    }
+  }
+  /* restriction of the received regions of blocks with a coarser neighbour */
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    if (!ALLOC(b)) continue;
+    int restricted = 0;
+    if (blk->loc.level > 0)
+      for (int n = 0; n < blk->nnb; ++n)
+        restricted = restricted || (blk->nb[n].origin_loc.level == blk->loc.level - 1);
+    if (!restricted) continue;
+    for (int n = 0; n < blk->nnb; ++n) {
+      if (blk->nb[n].origin_loc.level < blk->loc.level) continue;
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 1, s, e);
+      restrict_region(m, U, Uc, 1, b, s, e);
+    }
+  }
+  /* prolongation into the ghosts that face a coarser block */
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    if (!ALLOC(b)) continue;
+    for (int n = 0; n < blk->nnb; ++n) {
+      if (!(blk->nb[n].origin_loc.level < blk->loc.level)) continue;
+      int s[3], e[3];
+      orc_calc_indices(m, b, n, IR_RECV, 1, s, e);
+      for (int k = s[2]; k <= e[2]; ++k)
+        for (int j = s[1]; j <= e[1]; ++j)
+          for (int i = s[0]; i <= e[0]; ++i) prolongate_cell(m, U, Uc, 1, b, 0, k, j, i);
+    }
+  }
+#undef ALLOC
+  free(sender_region);
+  free(first);
+  free(flag);
+  free(buf);
+  free(off);
 }
 
 /* the exchange of ONE sparse field of one container (see the section comment) */
 static void sparse_exchange(OrcSparse *st, int f, double *U) {
   const OrcMesh *m = st->m;
+  if (m->multilevel) {
+    sparse_exchange_ml(st, f, U);
+    return;
+  }
   int64_t nreg = orc_count_regions(m);
   int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nreg + 1));
   int64_t total = orc_pack(m, U, NULL, 1, NULL, off);
@@ -3182,6 +3320,12 @@ static void sparse_stage(OrcSparse *st, int stage) {
             if (dim3 && i <= m->ie[0] && j <= m->ie[1])
               st->flux[f][2][p] = (v[2] > 0.0 ? mc0[p - sk] : mc0[p]) * v[2];
           }
+    }
+    /* AddFluxCorrectionTasks sparse_advection_driver.cpp:99-104 (multilevel meshes) */
+    if (m->multilevel) flux_correct_masked(m, st->flux[f], 1, st->alloc + f, ORC_NF);
+    for (int b = 0; b < m->nblocks; ++b) {
+      if (!st->alloc[b * ORC_NF + f]) continue;
+      const Block *blk = &m->blocks[b];
       /* FluxDivergence update.cpp:63-86 */
       const double a1 = blk->dx[1] * blk->dx[2], a2 = blk->dx[0] * blk->dx[2],
                    a3 = blk->dx[0] * blk->dx[1];

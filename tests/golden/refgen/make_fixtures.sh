@@ -278,6 +278,18 @@ run_teamr () { # name ndim nx nb numlevel ncycles
 run_teamr teamr_a32_b8_l3_2d_crc 2 32 8 3 6
 run_teamr teamr_a16_b4_l2_3d_crc 3 16 4 2 4
 fi
+# sparse fields on a statically refined mesh (three levels; refined regions on the blobs' paths):
+# allocation-aware restriction / prolongation and flux correction
+if [ -z "${SKIP_SPARSE:-}" ]; then
+  d="$WORK/sparse_s64_b8_l3_2d"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  cp "$REF/example/sparse_advection/parthinput.sparse_advection" deck.pin
+  printf '\n<parthenon/static_refinement0>\nlevel = 1\nx1min = 0.3\nx1max = 0.7\nx2min = 0.3\nx2max = 0.7\n<parthenon/static_refinement1>\nlevel = 2\nx1min = -0.6\nx1max = -0.45\nx2min = 0.45\nx2max = 0.6\n' >> deck.pin
+  PB2_DUMP_EVERY=6 PB2_DUMP_PREFIX="$d/U" "$WORK/sparse_dump" -i deck.pin parthenon/mesh/nx1=64 parthenon/mesh/nx2=64 \
+    parthenon/meshblock/nx1=8 parthenon/meshblock/nx2=8 parthenon/mesh/refinement=static parthenon/mesh/numlevel=3 \
+    parthenon/time/nlim=48 parthenon/time/tlim=1e9 parthenon/output0/dt=-1 parthenon/output1/dt=-1 parthenon/output3/dt=-1 \
+    parthenon/sparse/alloc_threshold=1e-2 parthenon/sparse/dealloc_threshold=5e-3 parthenon/sparse/dealloc_count=2 > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/sparse_s64_b8_l3_2d.npz"
+fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1
 run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4
