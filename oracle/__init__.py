@@ -138,6 +138,15 @@ def lib():
         L.orc_amr_te_cycle.argtypes = [C.c_void_p, C.c_int]
         L.orc_amr_te_field.argtypes = [C.c_void_p, C.c_int]
         L.orc_amr_te_field.restype = dp
+        L.orc_amr_create_sparse.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
+                                            C.c_double, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_double, C.c_int]
+        L.orc_amr_create_sparse.restype = C.c_void_p
+        for fn in ("orc_amr_sparse_init", "orc_amr_sparse_step"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.orc_amr_sparse_regrid.argtypes = [C.c_void_p]
+        L.orc_amr_sparse_state.argtypes = [C.c_void_p]
+        L.orc_amr_sparse_state.restype = C.c_void_p
         L.orc_amr_tags.argtypes = [C.c_void_p, ip]
         L.orc_amr_deref_counts.argtypes = [C.c_void_p, ip]
         L.orc_amr_destroy.argtypes = [C.c_void_p]
@@ -555,6 +564,72 @@ class AmrNonCellCentred:
         shape = (self.nblocks, ncs, int(pn[2]), int(pn[1]), int(pn[0]))
         p = lib().orc_amr_te_field(self.h, f)
         return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape).copy()
+
+
+class AmrSparseAdvection:
+    """example/sparse_advection with refinement = adaptive (2-D in the reference)"""
+
+    def __init__(self, ndim, nx, ng, nrb, numlevel, derefine_count=10, refine_tol=0.3,
+                 derefine_tol=0.03, speed=1.5, cfl=0.45, alloc_threshold=1e-5,
+                 dealloc_threshold=1e-6, dealloc_count=5, xmin=(-1.0,) * 3, xmax=(1.0,) * 3):
+        nx3 = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
+        nrb3 = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
+        lo, hi = np.array(xmin, dtype=np.float64), np.array(xmax, dtype=np.float64)
+        self.h = lib().orc_amr_create_sparse(ndim, _ip(nx3), ng, _ip(nrb3), _dp(lo), _dp(hi),
+                                             numlevel, derefine_count, refine_tol, derefine_tol,
+                                             speed, cfl, alloc_threshold, dealloc_threshold,
+                                             dealloc_count)
+
+    def __del__(self):
+        try:
+            lib().orc_amr_destroy(self.h)
+        except Exception:
+            pass
+
+    def init(self):
+        lib().orc_amr_sparse_init(self.h)
+
+    def step(self):
+        lib().orc_amr_sparse_step(self.h)
+
+    def regrid(self):
+        return bool(lib().orc_amr_sparse_regrid(self.h))
+
+    @property
+    def nblocks(self):
+        return lib().orc_mesh_nblocks(lib().orc_amr_mesh(self.h))
+
+    @property
+    def block_locs(self):
+        m = lib().orc_amr_mesh(self.h)
+        out = np.zeros((self.nblocks, 4), dtype=np.int32)
+        for b in range(self.nblocks):
+            lib().orc_mesh_block_loc(m, b, _ip(out[b]))
+        return out
+
+    @property
+    def time(self):
+        return lib().orc_sparse_time(lib().orc_amr_sparse_state(self.h))
+
+    @property
+    def dt(self):
+        return lib().orc_sparse_dt(lib().orc_amr_sparse_state(self.h))
+
+    @property
+    def U(self):
+        """[nblocks][4][nk][nj][ni]; NaN where a field is not allocated"""
+        L = lib()
+        st, m = L.orc_amr_sparse_state(self.h), L.orc_amr_mesh(self.h)
+        nb = self.nblocks
+        dims = np.zeros(3, dtype=np.int32)
+        L.orc_te_extents(m, 0, _ip(dims))
+        shape = (nb, int(dims[2]), int(dims[1]), int(dims[0]))
+        al = np.ctypeslib.as_array(L.orc_sparse_alloc(st), shape=(nb * 4,)).reshape(nb, 4).astype(bool)
+        out = np.full((nb, 4) + shape[1:], np.nan)
+        for f in range(4):
+            u = np.ctypeslib.as_array(L.orc_sparse_U(st, f), shape=(int(np.prod(shape)),)).reshape(shape)
+            out[:, f] = np.where(al[:, f, None, None, None], u, np.nan)
+        return out
 
 
 class SparseAdvection:

@@ -2269,11 +2269,17 @@ struct OrcAmr {
    * geometric criterion that moves with te_cycle */
   double *te_U[3], *te_Uc[3];
   int te_cycle;
+  /* app = 3: example/sparse_advection with refinement = adaptive */
+  struct OrcSparse *sp;
+  double sp_speed, sp_alloc_thr, sp_dealloc_thr;
+  int sp_dealloc_count;
 };
 static const int kTeNcomp[3] = {2, 1, 1};
 static void te_alloc(const OrcMesh *m, int f, double **U, double **Uc);
 static void te_ic(struct OrcAmr *a);
 static void te_remesh(struct OrcAmr *a, OrcMesh *nm);
+static void sparse_remesh(struct OrcAmr *a, OrcMesh *nm);
+static void sparse_minmax(const struct OrcSparse *st, int b, double *mn, double *mx);
 static void amr_tag(struct OrcAmr *a, const double *U);
 static int amr_remesh(struct OrcAmr *a);
 
@@ -2389,6 +2395,7 @@ struct OrcAmr *orc_amr_create_burgers(int ndim, const int nx[3], int ng, const i
 
 void orc_amr_destroy(struct OrcAmr *a) {
   if (!a) return;
+  orc_sparse_destroy(a->sp);
   for (int f = 0; f < 3; ++f) {
     free(a->te_U[f]);
     free(a->te_Uc[f]);
@@ -2424,6 +2431,7 @@ static void amr_tag(struct OrcAmr *a, const double *U) {
       mn = p[q] < mn ? p[q] : mn;
       mx = p[q] > mx ? p[q] : mx;
     }
+    if (a->app == 3) sparse_minmax(a->sp, b, &mn, &mx); /* sparse_advection_package.cpp:110-143 */
     int aret = 0; /* AmrTag: derefine -1, same 0, refine 1 */
     if (a->app == 2) {
       /* TagByPosition of the fixture generator */
@@ -2729,6 +2737,10 @@ static int amr_remesh(struct OrcAmr *a) {
   free(t.leaf);
   if (a->app == 2) {
     te_remesh(a, nm);
+    return 1;
+  }
+  if (a->app == 3) {
+    sparse_remesh(a, nm);
     return 1;
   }
   /* the application state on the new mesh; only the base container is carried over (:667) */
@@ -3238,7 +3250,7 @@ static void sparse_ic(OrcSparse *st) {
             if (x * x + y * y + z * z < size) any = 1;
           }
       if (!any) continue;
-      sparse_allocate(st, b, f);
+      if (!st->alloc[b * ORC_NF + f]) sparse_allocate(st, b, f);
       for (int k = m->is[2]; k <= m->ie[2]; ++k)
         for (int j = m->is[1]; j <= m->ie[1]; ++j)
           for (int i = m->is[0]; i <= m->ie[0]; ++i) {
@@ -3307,7 +3319,6 @@ static void sparse_stage(OrcSparse *st, int stage) {
     const double v[3] = {st->vx[f], st->vy[f], st->vz[f]};
     for (int b = 0; b < m->nblocks; ++b) {
       if (!st->alloc[b * ORC_NF + f]) continue; /* IsAllocated guards everywhere */
-      const Block *blk = &m->blocks[b];
       /* CalculateFluxes sparse_advection_package.cpp:173-258 (donor cell) */
       for (int k = m->is[2]; k <= m->ie[2] + dim3; ++k)
         for (int j = m->is[1]; j <= m->ie[1] + 1; ++j)
@@ -3372,6 +3383,174 @@ void orc_sparse_step(OrcSparse *st) {
   st->dt = fmin(st->dt, st->allowed_dt);
   st->allowed_dt = DBL_MAX;
 }
+
+
+/* ---- example/sparse_advection with refinement = adaptive ---- */
+static void sparse_minmax(const struct OrcSparse *st, int b, double *mn, double *mx) {
+  *mn = DBL_MAX;
+  *mx = -DBL_MAX;
+  for (int f = 0; f < ORC_NF; ++f) {
+    if (!st->alloc[b * ORC_NF + f]) continue;
+    const double *p = st->U[f] + (size_t)b * st->ncell;
+    for (size_t q = 0; q < st->ncell; ++q) {
+      *mn = p[q] < *mn ? p[q] : *mn;
+      *mx = p[q] > *mx ? p[q] : *mx;
+    }
+  }
+}
+
+/* RedistributeAndRefineMeshBlocks for the sparse fields: a new child exists where its parent
+ * did (TryRecvCoarseToFine :100-103, :137-141), a new parent where any daughter did
+ * (TryRecvFineToCoarse :193-195); counters of Update::SparseDealloc live on the block object */
+static void sparse_remesh(struct OrcAmr *a, OrcMesh *nm) {
+  const OrcMesh *m = a->m;
+  OrcSparse *os = a->sp;
+  OrcSparse *ns = orc_sparse_create(nm, a->sp_speed, os->cfl, a->sp_alloc_thr, a->sp_dealloc_thr,
+                                    a->sp_dealloc_count);
+  ns->dt = os->dt;
+  ns->time = os->time;
+  ns->ncycle = os->ncycle;
+  ns->allowed_dt = os->allowed_dt;
+  const int nleaf = ndaughters(m);
+  int *ncount = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  int *nflag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  const size_t cper = (size_t)m->cn[0] * m->cn[1] * m->cn[2];
+  double *ctmp = (double *)calloc((size_t)m->nblocks * cper, sizeof(double));
+  for (int nb = 0; nb < nm->nblocks; ++nb) {
+    const Loc *nl = &nm->blocks[nb].loc;
+    int ob = find_leaf(m, nl);
+    if (ob >= 0) {
+      ncount[nb] = a->deref_count[ob];
+      nflag[nb] = a->refine_flag[ob];
+    }
+    for (int f = 0; f < ORC_NF; ++f) {
+      double *nU = ns->U[f], *nUc = ns->Uc[f];
+      const double *oU = os->U[f];
+      if (ob >= 0) { /* kept */
+        if (!os->alloc[ob * ORC_NF + f]) continue;
+        ns->alloc[nb * ORC_NF + f] = 1;
+        ns->counter[nb * ORC_NF + f] = os->counter[ob * ORC_NF + f];
+        memcpy(nU + (size_t)nb * ns->ncell, oU + (size_t)ob * os->ncell, os->ncell * sizeof(double));
+        continue;
+      }
+      int pb = -1;
+      if (nl->level > 0) {
+        const Loc par = parent_of(m, nl);
+        pb = find_leaf(m, &par);
+      }
+      if (pb >= 0) { /* refined */
+        if (!os->alloc[pb * ORC_NF + f]) continue;
+        sparse_allocate(ns, nb, f);
+        int sh[3];
+        for (int d = 0; d < 3; ++d)
+          sh[d] = (d < m->ndim && (nl->lx[d] & 1L)) ? (m->ie[d] - m->is[d] + 1) / 2 : 0;
+        for (int k = 0; k < m->cn[2]; ++k)
+          for (int j = 0; j < m->cn[1]; ++j)
+            for (int i = 0; i < m->cn[0]; ++i)
+              nUc[cidx(nm, 1, nb, 0, k, j, i)] =
+                  oU[fidx(m, 1, pb, 0, k + sh[2], j + sh[1], i + sh[0])];
+        int s[3], e[3];
+        for (int d = 0; d < 3; ++d) {
+          const int g2 = d < m->ndim ? m->ng / 2 : 0;
+          s[d] = nm->cis[d] - g2;
+          e[d] = nm->cie[d] + g2;
+        }
+        for (int k = s[2]; k <= e[2]; ++k)
+          for (int j = s[1]; j <= e[1]; ++j)
+            for (int i = s[0]; i <= e[0]; ++i) prolongate_cell(nm, nU, nUc, 1, nb, 0, k, j, i);
+        continue;
+      }
+      /* derefined */
+      for (int q = 0; q < nleaf; ++q) {
+        const Loc dl = daughter(m, nl, q);
+        const int db = find_leaf(m, &dl);
+        if (db < 0) {
+          fprintf(stderr, "oracle: remesh cannot find the origin of a new block\n");
+          abort();
+        }
+        if (!os->alloc[db * ORC_NF + f]) continue;
+        if (!ns->alloc[nb * ORC_NF + f]) sparse_allocate(ns, nb, f);
+        int s[3] = {m->cis[0], m->cis[1], m->cis[2]}, e[3] = {m->cie[0], m->cie[1], m->cie[2]};
+        restrict_region(m, oU, ctmp, 1, db, s, e);
+        int sh[3];
+        for (int dd = 0; dd < 3; ++dd)
+          sh[dd] = (dd < m->ndim && (dl.lx[dd] & 1L)) ? (m->cie[dd] - m->cis[dd] + 1) : 0;
+        for (int k = m->cis[2]; k <= m->cie[2]; ++k)
+          for (int j = m->cis[1]; j <= m->cie[1]; ++j)
+            for (int i = m->cis[0]; i <= m->cie[0]; ++i)
+              nU[fidx(nm, 1, nb, 0, k + sh[2], j + sh[1], i + sh[0])] =
+                  ctmp[cidx(m, 1, db, 0, k, j, i)];
+      }
+    }
+  }
+  free(ctmp);
+  orc_sparse_destroy(os);
+  orc_mesh_destroy(a->m);
+  free(a->deref_count);
+  free(a->refine_flag);
+  free(a->last_tag);
+  a->m = nm;
+  a->sp = ns;
+  a->deref_count = ncount;
+  a->refine_flag = nflag;
+  a->last_tag = (int *)calloc((size_t)nm->nblocks, sizeof(int));
+  /* CommunicateBoundaries on the new mesh (:1000-1003) */
+  for (int f = 0; f < ORC_NF; ++f) sparse_exchange(ns, f, ns->U[f]);
+}
+
+struct OrcAmr *orc_amr_create_sparse(int ndim, const int nx[3], int ng, const int nrb[3],
+                                     const double xmin[3], const double xmax[3], int numlevel,
+                                     int derefine_count, double refine_tol, double derefine_tol,
+                                     double speed, double cfl, double alloc_thr,
+                                     double dealloc_thr, int dealloc_count) {
+  const double v0[3] = {0, 0, 0};
+  struct OrcAmr *a = orc_amr_create(ndim, nx, ng, nrb, xmin, xmax, numlevel, derefine_count,
+                                    refine_tol, derefine_tol, 1, 2, 0.0, v0, cfl);
+  orc_advection_destroy(a->adv);
+  a->adv = NULL;
+  a->app = 3;
+  a->sp_speed = speed;
+  a->sp_alloc_thr = alloc_thr;
+  a->sp_dealloc_thr = dealloc_thr;
+  a->sp_dealloc_count = dealloc_count;
+  a->sp = orc_sparse_create(a->m, speed, cfl, alloc_thr, dealloc_thr, dealloc_count);
+  return a;
+}
+/* Mesh::Initialize: problem generator, exchange, tag, remesh until the mesh stops changing */
+void orc_amr_sparse_init(struct OrcAmr *a) {
+  int done;
+  do {
+    sparse_ic(a->sp);
+    for (int f = 0; f < ORC_NF; ++f) sparse_exchange(a->sp, f, a->sp->U[f]);
+    amr_tag(a, NULL);
+    done = !amr_remesh(a);
+  } while (!done);
+  OrcSparse *st = a->sp;
+  st->allowed_dt = sparse_estimate_timestep(st);
+  st->dt = fmin(DBL_MAX, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+  st->time = 0;
+  st->ncycle = 0;
+}
+/* Step + tagging, then LoadBalancingAndAdaptiveMeshRefinement + SetGlobalTimeStep */
+void orc_amr_sparse_step(struct OrcAmr *a) {
+  OrcSparse *st = a->sp;
+  sparse_stage(st, 1);
+  sparse_stage(st, 2);
+  amr_tag(a, NULL);
+  st->ncycle++;
+  st->time += st->dt;
+}
+int orc_amr_sparse_regrid(struct OrcAmr *a) {
+  const int changed = amr_remesh(a);
+  OrcSparse *st = a->sp;
+  if (changed) st->allowed_dt = sparse_estimate_timestep(st);
+  if (st->dt < 0.1 * DBL_MAX) st->dt *= 2.0;
+  st->dt = fmin(st->dt, st->allowed_dt);
+  st->allowed_dt = DBL_MAX;
+  return changed;
+}
+struct OrcSparse *orc_amr_sparse_state(struct OrcAmr *a) { return a->sp; }
 
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP

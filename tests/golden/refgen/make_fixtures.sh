@@ -290,6 +290,17 @@ if [ -z "${SKIP_SPARSE:-}" ]; then
     parthenon/sparse/alloc_threshold=1e-2 parthenon/sparse/dealloc_threshold=5e-3 parthenon/sparse/dealloc_count=2 > run.log 2>&1
   python3 "$HERE/pack_dumps.py" "$d" "$OUT/sparse_s64_b8_l3_2d.npz"
 fi
+# the sparse_advection deck as shipped: refinement = adaptive (three levels), dumps every 5 cycles
+# with the block list of every dump
+if [ -z "${SKIP_SPARSE:-}" ]; then
+  d="$WORK/sparse_a64_b8_l3_2d"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  PB2_DUMP_EVERY=5 PB2_DUMP_PREFIX="$d/U" "$WORK/sparse_dump" -i "$REF/example/sparse_advection/parthinput.sparse_advection" \
+    parthenon/mesh/nx1=64 parthenon/mesh/nx2=64 parthenon/meshblock/nx1=8 parthenon/meshblock/nx2=8 \
+    parthenon/mesh/refinement=adaptive parthenon/mesh/numlevel=3 parthenon/time/nlim=40 parthenon/time/tlim=1e9 \
+    parthenon/output0/dt=-1 parthenon/output1/dt=-1 parthenon/output3/dt=-1 parthenon/sparse/alloc_threshold=1e-2 \
+    parthenon/sparse/dealloc_threshold=5e-3 parthenon/sparse/dealloc_count=2 > run.log 2>&1
+  PB2_PER_CYCLE_META=1 python3 "$HERE/pack_dumps.py" "$d" "$OUT/sparse_a64_b8_l3_2d.npz"
+fi
 # history-only cases (MS Mass 0..7 per cycle, %.14e) at benchmark component count
 HST_ONLY=1
 run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4
