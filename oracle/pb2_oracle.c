@@ -2,7 +2,10 @@
  *
  * Plain-C restatement of the reference's ghost-zone hot path: mesh topology for a
  * single-tree forest, boundary index boxes, pack/unpack, restriction/prolongation at
- * fine-coarse boundaries, and the benchmarks/burgers RK2 cycle.  Cell-centred fields only.
+ * fine-coarse boundaries, flux correction, physical boundaries, the benchmarks/burgers RK2
+ * cycle, example/advection and example/sparse_advection (uniform, statically and adaptively
+ * refined meshes), and the exchange / remesh of face, edge and node fields with block
+ * ownership.  Every section is pinned against dumps of the reference (tests/golden/).
  * Must be compiled with -ffp-contract=off (the reference CPU build emits no FMAs).
  */
 #include "pb2_oracle.h"
