@@ -138,6 +138,7 @@ def lib():
         L.orc_amr_te_cycle.argtypes = [C.c_void_p, C.c_int]
         L.orc_amr_te_field.argtypes = [C.c_void_p, C.c_int]
         L.orc_amr_te_field.restype = dp
+        L.orc_amr_te_set_toth_roe.argtypes = [C.c_void_p, C.c_int]
         L.orc_amr_create_sparse.argtypes = [C.c_int, ip, C.c_int, ip, dp, dp, C.c_int, C.c_int,
                                             C.c_double, C.c_double, C.c_double, C.c_double,
                                             C.c_double, C.c_double, C.c_int]
@@ -522,13 +523,14 @@ class AmrNonCellCentred:
     geometric criterion): pins the remesh data movement of non-cell-centred fields"""
 
     def __init__(self, ndim, nx, ng, nrb, numlevel, derefine_count=2, xmin=(-0.5,) * 3,
-                 xmax=(0.5,) * 3):
+                 xmax=(0.5,) * 3, toth_roe=False):
         nx3 = np.array(list(nx) + [1] * (3 - len(nx)), dtype=np.int32)
         nrb3 = np.array(list(nrb) + [1] * (3 - len(nrb)), dtype=np.int32)
         lo, hi = np.array(xmin, dtype=np.float64), np.array(xmax, dtype=np.float64)
         self.ndim = ndim
         self.h = lib().orc_amr_create_te(ndim, _ip(nx3), ng, _ip(nrb3), _dp(lo), _dp(hi), numlevel,
                                          derefine_count)
+        lib().orc_amr_te_set_toth_roe(self.h, int(toth_roe))
 
     def __del__(self):
         try:

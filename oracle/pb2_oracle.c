@@ -2272,6 +2272,7 @@ struct OrcAmr {
    * geometric criterion that moves with te_cycle */
   double *te_U[3], *te_Uc[3];
   int te_cycle;
+  int te_toth_roe; /* the face field registered ProlongateInternalTothAndRoe */
   /* app = 3: example/sparse_advection with refinement = adaptive */
   struct OrcSparse *sp;
   double sp_speed, sp_alloc_thr, sp_dealloc_thr;
@@ -2361,7 +2362,8 @@ static void amr_init_te(struct OrcAmr *a) {
   do {
     te_ic(a);
     for (int f = 0; f < 3; ++f)
-      exchange_te_impl(a->m, a->te_U[f], a->te_Uc[f], kTeNcomp[f], f + 1, 0, 0);
+      exchange_te_impl(a->m, a->te_U[f], a->te_Uc[f], kTeNcomp[f], f + 1,
+                       f == 0 && a->te_toth_roe, 0);
     amr_tag(a, NULL);
     done = !amr_remesh(a);
   } while (!done);
@@ -2373,6 +2375,7 @@ int orc_amr_te_cycle(struct OrcAmr *a, int cycle) {
   return amr_remesh(a);
 }
 const double *orc_amr_te_field(const struct OrcAmr *a, int f) { return a->te_U[f]; }
+void orc_amr_te_set_toth_roe(struct OrcAmr *a, int on) { a->te_toth_roe = on; }
 
 /* benchmarks/burgers, refinement = adaptive: criterion = derivative_order_1 on U(vector_i) */
 struct OrcAmr *orc_amr_create_burgers(int ndim, const int nx[3], int ng, const int nrb[3],
@@ -2630,7 +2633,8 @@ static void te_remesh(struct OrcAmr *a, OrcMesh *nm) {
   /* :958-990: shared elements of new fine blocks from neighbours that were fine already
    * (ownership favours old blocks), then the internal elements of the new fine blocks */
   g_newly_refined = newly;
-  for (int f = 0; f < 3; ++f) exchange_te_impl(nm, nU[f], nUc[f], kTeNcomp[f], f + 1, 0, 0);
+  for (int f = 0; f < 3; ++f)
+    exchange_te_impl(nm, nU[f], nUc[f], kTeNcomp[f], f + 1, f == 0 && a->te_toth_roe, 0);
   g_newly_refined = NULL;
   for (int f = 0; f < 3; ++f) {
     const int kind = f + 1;
@@ -2644,7 +2648,8 @@ static void te_remesh(struct OrcAmr *a, OrcMesh *nm) {
         for (int q = 0; q < 8; ++q) {
           int ctop[3], s[3], e[3];
           te_top_offset(kCelKind[q], kCelEl[q], ctop);
-          if (!te_is_submanifold(ftop, ctop)) continue;
+          const int tr = f == 0 && a->te_toth_roe;
+          if (tr ? kCelKind[q] != ORC_TE_CELL : !te_is_submanifold(ftop, ctop)) continue;
           for (int d = 0; d < 3; ++d) {
             const int g2 = d < nm->ndim ? nm->ng / 2 : 0;
             s[d] = nm->cis[d] - g2;
@@ -2653,14 +2658,19 @@ static void te_remesh(struct OrcAmr *a, OrcMesh *nm) {
           for (int c = 0; c < N.ncomp; ++c)
             for (int k = s[2]; k <= e[2]; ++k)
               for (int j = s[1]; j <= e[1]; ++j)
-                for (int i = s[0]; i <= e[0]; ++i)
-                  te_prolongate_internal(&N, ftop, ctop, nb, el, c, k, j, i);
+                for (int i = s[0]; i <= e[0]; ++i) {
+                  if (tr)
+                    te_toth_roe(&N, nb, el, c, k, j, i);
+                  else
+                    te_prolongate_internal(&N, ftop, ctop, nb, el, c, k, j, i);
+                }
         }
       }
     }
   }
   /* :992-1003: the regular ownership again, then the exchange of everything */
-  for (int f = 0; f < 3; ++f) exchange_te_impl(nm, nU[f], nUc[f], kTeNcomp[f], f + 1, 0, 0);
+  for (int f = 0; f < 3; ++f)
+    exchange_te_impl(nm, nU[f], nUc[f], kTeNcomp[f], f + 1, f == 0 && a->te_toth_roe, 0);
   for (int f = 0; f < 3; ++f) {
     free(a->te_U[f]);
     free(a->te_Uc[f]);

@@ -277,6 +277,9 @@ run_teamr () { # name ndim nx nb numlevel ncycles
 }
 run_teamr teamr_a32_b8_l3_2d_crc 2 32 8 3 6
 run_teamr teamr_a16_b4_l2_3d_crc 3 16 4 2 4
+# the same with ProlongateInternalTothAndRoe registered for the face field
+PB2_TOTH_ROE=1 run_teamr teamr_a32_b8_l3_2d_tothroe_crc 2 32 8 3 6
+PB2_TOTH_ROE=1 run_teamr teamr_a16_b4_l2_3d_tothroe_crc 3 16 4 2 4
 fi
 # sparse fields on a statically refined mesh (three levels; refined regions on the blobs' paths):
 # allocation-aware restriction / prolongation and flux correction

@@ -215,3 +215,6 @@ def tecomm_initial(nblocks, nel, ncomp, nk, nj, ni, first_gid=0):
 # adaptive meshes with face / edge / node fields (tests/golden/refgen/teamr_dump_main.cpp):
 # (name, ndim, mesh cells, block cells, numlevel)
 TEAMR = [("teamr_a32_b8_l3_2d_crc", 2, 32, 8, 3), ("teamr_a16_b4_l2_3d_crc", 3, 16, 4, 2)]
+# the same runs with ProlongateInternalTothAndRoe registered for the face field
+TEAMR_TOTH_ROE = [("teamr_a32_b8_l3_2d_tothroe_crc", 2, 32, 8, 3),
+                  ("teamr_a16_b4_l2_3d_tothroe_crc", 3, 16, 4, 2)]
