@@ -50,6 +50,7 @@ def compare_topology(t, m):
     (3, (16, 8, 4), 2, (4, 4, 4)),
     (2, (16, 16), 2, (8, 8)),
     (3, (32, 32, 32), 4, (4, 4, 4)),
+    (1, (8,), 2, (4,)),
 ])
 def test_uniform_topology_matches_oracle(ndim, nx, ng, nrb):
     m = oracle.Mesh(ndim, nx, ng, nrb)
