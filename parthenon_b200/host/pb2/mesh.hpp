@@ -282,6 +282,11 @@ class Mesh {
   // test knob (pb2/table_halo): force the general region-table path for local channels even on
   // uniform meshes, where the descriptor-free pb2_halo_copy_uniform would be used
   bool table_halo = false;
+  // pb2/unverified_sparse_multilevel = true lifts the refusal of sparse fields on refined
+  // (static) meshes: allocation-aware restriction / prolongation / flux correction on
+  // same-device channels.  The oracle for this case is pinned to the reference, the device
+  // path has not been run yet (written when no GPU time was left in round 1).
+  bool unverified_sparse_multilevel = false;
   int VirtualRankOf(int gid) const;
 
   int GetNumMeshBlocksThisRank() const { return static_cast<int>(block_list.size()); }

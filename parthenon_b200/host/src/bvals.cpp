@@ -73,7 +73,9 @@ pb2_prores_region MakeProRes(Variable &v, const MeshBlock *pmb, const IndexBox &
   r.coarse_stride_k = v.cni * v.cnj;
   r.coarse_stride_c = static_cast<int32_t>(v.ccomp_stride);
   r.ndim = ndim;
-  r.status = PB2_REGION_ALLOCATED;
+  // ProResInfo::allocated (bnd_info.cpp:344): a sparse field that is not allocated on the
+  // block is neither restricted nor prolongated (pr_loops.hpp:43-46)
+  r.status = v.IsAllocated(pmb->pack_index) ? PB2_REGION_ALLOCATED : 0u;
   const UniformCartesian cc(pmb->coords, 2); // MeshRefinement::GetCoarseCoords
   for (int d = 0; d < 3; ++d) {
     r.fine_xmin[d] = pmb->coords.GetXmin()[d];
@@ -163,7 +165,8 @@ void Rebuild(MeshData<Real> *md) {
   c.sparse = false;
   for (Variable *v : c.vars) c.sparse = c.sparse || (v->metadata().IsSparse() && pm->sparse_config.enabled);
   if (c.sparse) {
-    PARTHENON_REQUIRE(!pm->multilevel, "sparse fields on multilevel meshes are not supported by this build");
+    PARTHENON_REQUIRE(!pm->multilevel || (pm->unverified_sparse_multilevel && !pm->adaptive && !slabs),
+                      "sparse fields on multilevel meshes are not supported by this build");
     PARTHENON_REQUIRE(pm->DefaultNumPartitions() == 1,
                       "sparse fields need one MeshData per rank (parthenon/mesh/pack_size=-1)");
   }
@@ -851,7 +854,12 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
             r.coarse_stride_j = v.ni;
             r.coarse_stride_k = v.ni * v.nj;
             r.coarse_stride_c = static_cast<int32_t>(v.comp_stride);
-            r.status = PB2_REGION_ALLOCATED;
+            // sparse fields: an unallocated sender sends a null message, which leaves the
+            // receiver's flux alone (no default fill for flxcor_recv); an unallocated receiver
+            // sets nothing
+            r.status = sv.IsAllocated(sb->pack_index) && v.IsAllocated(pmb->pack_index)
+                           ? PB2_REGION_ALLOCATED
+                           : 0u;
             const auto dx = sb->coords.Dx();
             r.area = dir == 0 ? dx[1] * dx[2] : (dir == 1 ? dx[0] * dx[2] : dx[0] * dx[1]);
             c.flxcor_local_elements += static_cast<int64_t>(r.ncomp) * r.n[0] * r.n[1] * r.n[2];

@@ -1,0 +1,75 @@
+"""GPU tests of device paths that were WRITTEN AFTER THE GPU BUDGET OF ROUND 1 WAS SPENT.  Their
+oracles are pinned to the reference (tests/test_oracle_golden.py), the device code has not been
+run once, so every test here is a non-strict expected failure: a pass shows up as XPASS, a
+mismatch as xfail, neither breaks the suite.  The file sorts last so that nothing runs after it
+in the same process.  Remove the marks once a run has confirmed them."""
+import os
+
+import numpy as np
+import pytest
+
+from parthenon_b200 import host
+from tests import helpers as H
+from tests.test_host_topology import deck_overrides
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: the oracle "
+                   "is pinned to the reference for this case, the device path (te_toth_roe "
+                   "regions in host/src/amr.cpp) has not been run yet")
+@pytest.mark.parametrize("name,ndim,nx,nb,numlevel", H.TEAMR_TOTH_ROE)
+def test_adaptive_remesh_with_toth_roe_crc(name, ndim, nx, nb, numlevel):
+    """the adaptive runs with ProlongateInternalTothAndRoe registered for the face field
+    (tecomm/toth_roe = true): new children get their internal faces from the divergence-
+    preserving operator after the newly-refined-ownership exchange"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
+    ov = deck_overrides(ndim, (nb,) * 3, 2, (nx // nb,) * 3, refinement="adaptive")
+    ov.update({"parthenon/mesh/numlevel": numlevel, "parthenon/mesh/derefine_count": 2,
+               "tecomm/toth_roe": "true"})
+    sim = host.Simulation(app="tecomm", overrides=ov)
+    try:
+        for c in range(int(g["ncycles"]) + 1):
+            if c:
+                sim.tag_and_remesh(c)
+            leaves, _ = H.leaves_from_bounds(g[f"bounds_{c}"], full(nx), full(nb))
+            n = sim.info()["nblocks"]
+            assert n == len(leaves), c
+            assert np.array_equal(np.array([sim.block(b)["loc"] for b in range(n)]), leaves), c
+            for f, field in enumerate(("face", "edge", "node")):
+                got = sim.get_field("base", field)
+                bad = np.nonzero(H.block_crcs(got) != g[f"crc_{c}_{f}"])[0]
+                assert len(bad) == 0, (c, field, len(bad), bad[:8])
+    finally:
+        sim.close()
+
+
+@pytest.mark.xfail(strict=False, reason="sparse fields on refined meshes: opt-in device path "
+                   "(pb2/unverified_sparse_multilevel) that has not been run yet")
+def test_sparse_advection_on_refined_mesh():
+    """sparse fields on a three-level statically refined mesh (same-device channels):
+    allocation-aware restriction / prolongation / flux correction vs the reference's dumps"""
+    g = np.load(os.path.join(GOLD, "sparse_s64_b8_l3_2d.npz"))
+    leaves, nrb = H.leaves_from_bounds(g["bounds"], (64, 64, 1), (8, 8, 1), xmin=-1.0, xmax=1.0)
+    ov = {"parthenon/mesh/refinement": "static", "parthenon/mesh/numlevel": 3,
+          "parthenon/sparse/alloc_threshold": 1e-2, "parthenon/sparse/dealloc_threshold": 5e-3,
+          "parthenon/sparse/dealloc_count": 2, "pb2/unverified_sparse_multilevel": "true"}
+    sim = host.Simulation(app="sparse_advection", overrides=ov, leaves=leaves)
+    try:
+        sim.pre_execute()
+
+        def state():
+            return np.stack([np.where(sim.allocation("base", f"sparse_{f}")[:, None, None, None],
+                                      sim.get_field("base", f"sparse_{f}")[:, 0], np.nan)
+                             for f in range(4)], axis=1)
+
+        dumped = {int(c): i for i, c in enumerate(g["cycles"])}
+        assert np.array_equal(state(), g["U_0"], equal_nan=True)
+        for c in range(1, 49):
+            sim.cycle()
+            if c in dumped:
+                assert np.array_equal(state(), g[f"U_{c}"], equal_nan=True), f"cycle {c}"
+    finally:
+        sim.close()
