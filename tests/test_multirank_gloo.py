@@ -113,3 +113,74 @@ def test_two_rank_slab_exchange_over_gloo():
     assert all(r[0] for r in res.values()), res
     assert sum(r[1] for r in res.values()) == int(np.prod(NRB))
     assert res[0][2] == res[1][2] > 0  # all-reduced count of Reals that crossed ranks
+
+
+
+# ---- face / edge / node fields: channel pieces (ownership masks resolved into boxes) ----
+def _te_worker(rank, port, result):
+    """each process holds only its own blocks of the reference problem generator's state,
+    derives its send / receive / local pieces with the host library (the receiver computes the
+    SENDER's ownership from the tree), ships one slab to its peer over gloo and must end up
+    with the reference's dump on its blocks"""
+    from tests import helpers as H
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        name, ndim, nx, nb, ng = H.TECOMM[2]  # 4 x 4 x 4 blocks of 4^3
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+        nrb = nx // nb
+        t = host.Topology(overrides=deck_overrides(ndim, (nb,) * 3, ng, (nrb,) * 3), rank=rank,
+                          nranks=WORLD)
+        info = t.info()
+        lo, hi = info["first_gid"], info["first_gid"] + info["nblocks"]
+        peer = 1 - rank
+        ok, moved = True, 0
+        size = lambda r: int(r[5] * r[12] * r[13] * r[14])
+        for kind, key, ncomp in H.TECOMM_FIELDS:
+            ref = g[key]
+            nblocks, _, nk, nj, ni = ref.shape
+            nel = 3 if kind < 3 else 1
+            U = H.tecomm_initial(nblocks, nel, ncomp, nk, nj, ni).reshape(ref.shape)
+            U[:lo] = np.nan  # the other rank's blocks are not here
+            U[hi:] = np.nan
+            U0 = U.copy()
+            send_rows = t.plan_boxes(ncomp, kind, "send")
+            recv_rows = t.plan_boxes(ncomp, kind, "recv")
+            send = np.full(max(int(r[15]) + size(r) for r in send_rows), np.nan)
+            for r in send_rows:
+                sg, c0, nc = int(r[0]), int(r[4]), int(r[5])
+                (si, sj, sk), (bi, bj, bk) = r[6:9], r[12:15]
+                send[int(r[15]):int(r[15]) + size(r)] = \
+                    U0[sg, c0:c0 + nc, sk:sk + bk, sj:sj + bj, si:si + bi].ravel()
+            recv = torch.empty(max(int(r[15]) + size(r) for r in recv_rows), dtype=torch.float64)
+            req = dist.isend(torch.from_numpy(send.copy()), peer)
+            dist.recv(recv, peer)
+            req.wait()
+            recv = recv.numpy()
+            for r in recv_rows:
+                rg, c0, nc = int(r[1]), int(r[4]), int(r[5])
+                (ri, rj, rk), (bi, bj, bk) = r[9:12], r[12:15]
+                U[rg, c0:c0 + nc, rk:rk + bk, rj:rj + bj, ri:ri + bi] = \
+                    recv[int(r[15]):int(r[15]) + size(r)].reshape(nc, bk, bj, bi)
+            for r in t.plan_boxes(ncomp, kind, "local"):
+                sg, rg, c0, nc = int(r[0]), int(r[1]), int(r[4]), int(r[5])
+                (si, sj, sk), (ri, rj, rk), (bi, bj, bk) = r[6:9], r[9:12], r[12:15]
+                U[rg, c0:c0 + nc, rk:rk + bk, rj:rj + bj, ri:ri + bi] = \
+                    U0[sg, c0:c0 + nc, sk:sk + bk, sj:sj + bj, si:si + bi]
+            ok = ok and np.array_equal(U[lo:hi], ref[lo:hi])
+            moved += send.size
+        result[rank] = (bool(ok), hi - lo, moved)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_face_edge_node_exchange_over_gloo():
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        result = mgr.dict()
+        mp.spawn(_te_worker, args=(_free_port(), result), nprocs=WORLD, join=True)
+        res = dict(result)
+    assert set(res) == {0, 1}
+    assert all(r[0] for r in res.values()), res
+    assert sum(r[1] for r in res.values()) == 64
+    assert res[0][2] > 0 and res[1][2] > 0
