@@ -70,6 +70,11 @@ int pb2_profile_enable(int on);
 int pb2_profile_reset(void);
 int pb2_profile_kernels(void);
 int pb2_profile_get(int id, const char **name, double *total_ms, int64_t *launches);
+/* work the recorded launches of kernel `id` processed, in the kernel's own unit: zones (cells of
+ * the blocks actually launched) for the stencil kernels, values moved for the copy / pack /
+ * unpack / ghost-fill kernels, 0 where a kernel does not report it.  Bytes per launch in
+ * bench.py's roofline = work / launches x the kernel's algorithmic bytes per unit. */
+int pb2_profile_get_work(int id, double *work);
 /* FP64 FMA throughput of the current device in TFLOP/s (2 flops per FMA), measured with a
  * register-resident microbenchmark: the FP64-pipe roofline of the burgers stencil */
 int pb2_measure_fp64_peak(double *tflops);
@@ -394,6 +399,14 @@ typedef struct pb2_burgers_args {
    * stored-flux path for the blocks that take part in flux correction only. */
   const int32_t *block_ids;
   int32_t num_block_ids;
+  /* PB2_MATH_FAST, pb2_burgers_stage only.  Device table [geom.nblocks][27] of same-device
+   * neighbour blocks (index (ox+1) + 3(oy+1) + 9(oz+1), -1 = none: physical boundary, another
+   * device, another level) as pb2_halo_copy_uniform takes it, or NULL.  If given, the last
+   * direction sweep also stores every finished cell within nghost of a block face into the ghost
+   * cells of those neighbours of `out`: SendBoundBufs<local> + SetBounds<local> of a uniform
+   * mesh (boundary_communication.cpp:95-140, :273-334) without a pass of their own — the caller
+   * then skips its same-device exchange of `out`.  Needs ndim >= 2. */
+  const int32_t *push_nbr;
 } pb2_burgers_args;
 
 /* fluxes only: writes args->flux[0..ndim-1] from args->u */

@@ -77,7 +77,8 @@ class BurgersArgs(C.Structure):
                 ("u", C.c_void_p), ("base", C.c_void_p), ("out", C.c_void_p),
                 ("flux", C.c_void_p * 3), ("derived", C.c_void_p), ("dt_min", C.c_void_p),
                 ("beta", C.c_double), ("dt", C.c_double),
-                ("block_ids", C.c_void_p), ("num_block_ids", C.c_int32)]
+                ("block_ids", C.c_void_p), ("num_block_ids", C.c_int32),
+                ("push_nbr", C.c_void_p)]
 
 
 _lib = None
@@ -90,7 +91,7 @@ SYMBOLS = [
     "pb2_stream_destroy", "pb2_stream_sync", "pb2_device_sync", "pb2_event_create",
     "pb2_event_destroy", "pb2_event_record", "pb2_event_sync", "pb2_event_query",
     "pb2_stream_wait_event", "pb2_event_elapsed_ms", "pb2_launch_count",
-    "pb2_profile_enable", "pb2_profile_reset", "pb2_profile_kernels", "pb2_profile_get",
+    "pb2_profile_enable", "pb2_profile_reset", "pb2_profile_kernels", "pb2_profile_get", "pb2_profile_get_work",
     "pb2_measure_fp64_peak",
     "pb2_bnd_table_create", "pb2_copy_table_create", "pb2_bnd_table_destroy",
     "pb2_bnd_table_elements", "pb2_pack", "pb2_unpack", "pb2_copy", "pb2_prores_table_create",
@@ -195,6 +196,20 @@ def profile(enable=None, reset=False):
         check(L.pb2_profile_get(i, C.byref(name), C.byref(ms), C.byref(n)))
         if n.value:
             out[name.value.decode()] = (ms.value, n.value)
+    return out
+
+
+def profile_work():
+    """{name: work}: what the recorded launches processed (zones / values), see
+    pb2_profile_get_work"""
+    L = lib()
+    out = {}
+    for i in range(L.pb2_profile_kernels()):
+        name, ms, n, w = C.c_char_p(), C.c_double(), C.c_int64(), C.c_double()
+        check(L.pb2_profile_get(i, C.byref(name), C.byref(ms), C.byref(n)))
+        check(L.pb2_profile_get_work(i, C.byref(w)))
+        if n.value:
+            out[name.value.decode()] = w.value
     return out
 
 

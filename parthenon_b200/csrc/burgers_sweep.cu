@@ -21,6 +21,7 @@
 // arithmetic lives in burgers_strict.cu.  Valid for |q| < ~1e40 (products of three
 // smoothness indicators must not overflow).
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "weno_fast.cuh"
@@ -61,8 +62,11 @@ struct Args {
   unsigned long long *dtmin; // LAST sweep only, or null
   const double *dx;          // [nblocks][3]
   const int *block_ids;      // launch block -> block of the batch, or null (identity)
+  const int *nbr;            // LAST sweep: [nblocks][27] same-device neighbour blocks (-1: none)
+                             // whose ghost cells take the finished cells, or null (no push)
   double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
   FastDiv dncell, dnx1;      // x sweep: division by (nx1 + 2) and by nx2 as multiply-shift
+  FastDiv dnpair;            // paired x sweep: division by nx1 / 2 + 1
 };
 
 using fastmath::Linear;
@@ -285,6 +289,13 @@ __global__ void __launch_bounds__(kThreads, 3) sweep_march_kernel(const Args a) 
   if (LAST) reduce_dt(a, rate);
 }
 
+} // namespace PB2_SWEEP_NS
+} // namespace pb2
+#include "burgers_march.cuh"
+#include "burgers_xsweep.cuh"
+namespace pb2 {
+namespace PB2_SWEEP_NS {
+
 // ---- x sweep: (row, cell) items flattened over the lanes of a warp --------------------------
 constexpr int kRowsPerWarp = 16;
 
@@ -483,6 +494,7 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   if (g.nblocks == 0) return PB2_OK;
   a.dncell.init(static_cast<uint32_t>(g.nx[0] + 2));
   a.dnx1.init(static_cast<uint32_t>(g.nx[1]));
+  a.dnpair.init(static_cast<uint32_t>(g.nx[0] / 2 + 1));
   a.beta = args->beta;
   a.w2 = 1.0 - args->beta;
   a.bdt = args->beta * args->dt;
@@ -502,12 +514,35 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
     x.derived = args->derived;
     x.dtmin = reinterpret_cast<unsigned long long *>(args->dt_min);
   };
+  const double zones = (double)g.nblocks * g.nx[0] * g.nx[1] * g.nx[2]; // of the launched blocks
+  // PB2_SWEEP_V1=1 selects the kernels of round 1 (one cell per lane in x, shared-memory-ring
+  // march in y / z) for A/B runs
+  static const bool v1 = std::getenv("PB2_SWEEP_V1") != nullptr;
+  const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool g32 = geo32(g) && al16(a.u) && al16(a.base) && al16(a.out) && g.sb % 2 == 0;
+  a.nbr = nullptr;
+  if (!v1 && g.nx[0] % 2 == 0) {
+    const int nrows = g.nx[1] * g.nx[2];
+    const int warps = g.nblocks * ((nrows + kXRows - 1) / kXRows);
+    const int wpc = kThreads / 32;
+    const int ctas = (warps + wpc - 1) / wpc;
+    ProfScope prof(K_SWEEP_XPAIR, st, zones);
+    if (g.ndim == 1) {
+      last(a);
+      sweep_xpair_kernel<RECON, true, 0><<<ctas, kThreads, 0, st>>>(a);
+    } else if (g32) {
+      sweep_xpair_kernel<RECON, false, 32><<<ctas, kThreads, 0, st>>>(a);
+    } else {
+      sweep_xpair_kernel<RECON, false, 0><<<ctas, kThreads, 0, st>>>(a);
+    }
+    PB2_LAUNCH_CHECK();
+  } else
   {
     const int nrows = g.nx[1] * g.nx[2];
     const int warps = g.nblocks * ((nrows + kRowsPerWarp - 1) / kRowsPerWarp);
     const int wpc = kThreads / 32;
     const int ctas = (warps + wpc - 1) / wpc;
-    ProfScope prof(K_SWEEP_X, st);
+    ProfScope prof(K_SWEEP_X, st, zones);
     if (g.ndim == 1) {
       last(a);
       sweep_x_kernel<RECON, true, NC><<<ctas, kThreads, 0, st>>>(a);
@@ -516,10 +551,43 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
     }
     PB2_LAUNCH_CHECK();
   }
+  // y / z sweeps: chunked register march (burgers_march.cuh)
+  if (!v1) {
+    const size_t csm = chunk_smem_bytes(g.ncomp);
+    auto march = [&](auto kern, int dir, bool is_last) -> int {
+      const int ncol = g.nx[dir == 1 ? 2 : 1] * g.nx[0];
+      const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
+      if (is_last) {
+        last(a);
+        a.nbr = args->push_nbr;
+      }
+      PB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(csm)));
+      ProfScope prof(dir == 1 ? K_SWEEP_CHUNK_Y : K_SWEEP_CHUNK_Z, st, zones);
+      kern<<<ctas, kThreads, csm, st>>>(a);
+      PB2_LAUNCH_CHECK();
+      return PB2_OK;
+    };
+    const bool push = args->push_nbr != nullptr;
+    if (g.ndim == 2) {
+      return push ? march(sweep_chunk_kernel<RECON, 1, true, true, 0>, 1, true)
+                  : march(sweep_chunk_kernel<RECON, 1, true, false, 0>, 1, true);
+    } else if (g.ndim == 3) {
+      if (g32) {
+        if (int rc = march(sweep_chunk_kernel<RECON, 1, false, false, 32>, 1, false)) return rc;
+        return push ? march(sweep_chunk_kernel<RECON, 2, true, true, 32>, 2, true)
+                    : march(sweep_chunk_kernel<RECON, 2, true, false, 32>, 2, true);
+      }
+      if (int rc = march(sweep_chunk_kernel<RECON, 1, false, false, 0>, 1, false)) return rc;
+      return push ? march(sweep_chunk_kernel<RECON, 2, true, true, 0>, 2, true)
+                  : march(sweep_chunk_kernel<RECON, 2, true, false, 0>, 2, true);
+    }
+    return PB2_OK;
+  }
   if (g.ndim > 1) {
     const int ncol = g.nx[2] * g.nx[0];
     const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
-    ProfScope prof(K_SWEEP_Y, st);
+    ProfScope prof(K_SWEEP_Y, st, zones);
     if (g.ndim == 2) {
       last(a);
       sweep_march_kernel<RECON, 1, true, NC><<<ctas, kThreads, smem, st>>>(a);
@@ -532,7 +600,7 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
     const int ncol = g.nx[1] * g.nx[0];
     const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
     last(a);
-    ProfScope prof(K_SWEEP_Z, st);
+    ProfScope prof(K_SWEEP_Z, st, zones);
     sweep_march_kernel<RECON, 2, true, NC><<<ctas, kThreads, smem, st>>>(a);
     PB2_LAUNCH_CHECK();
   }

@@ -48,16 +48,20 @@ int require_device();
 // ---- optional per-kernel timing with CUDA events (pb2_profile_* of the C ABI) ----------
 enum KernelId {
   K_PACK = 0, K_UNPACK, K_COPY, K_RESTRICT, K_PROLONGATE, K_WEIGHTED_SUM, K_FLUX_DIV,
-  K_FLUX_X, K_FLUX_Y, K_FLUX_Z, K_UPDATE, K_DERIVED_DT, K_HISTORY, K_SWEEP_X, K_SWEEP_Y, K_SWEEP_Z, K_INTERIOR, K_HALO_UNIFORM, K_FLUX_CORRECT, K_ADVECTION_FLUX, K_APPLY_BC, K_COUNT
+  K_FLUX_X, K_FLUX_Y, K_FLUX_Z, K_UPDATE, K_DERIVED_DT, K_HISTORY, K_SWEEP_X, K_SWEEP_Y, K_SWEEP_Z, K_INTERIOR, K_HALO_UNIFORM, K_FLUX_CORRECT, K_ADVECTION_FLUX, K_APPLY_BC, K_SWEEP_XPAIR,
+  K_SWEEP_CHUNK_Y, K_SWEEP_CHUNK_Z, K_COUNT
 };
 extern std::atomic<int> g_profile_on;
-void profile_begin(int id, cudaStream_t s, void **token);
+void profile_begin(int id, cudaStream_t s, void **token, double work);
 void profile_end(void *token, cudaStream_t s);
+// `work`: what the launch processes in the kernel's own unit (zones for the stencil kernels,
+// values for the copy / pack / unpack / restrict / prolongate kernels), summed per kernel so
+// that bytes per launch follow from what was actually launched (pb2_profile_get_work)
 struct ProfScope {
   void *token = nullptr;
   cudaStream_t s;
-  ProfScope(int id, cudaStream_t st) : s(st) {
-    if (g_profile_on.load(std::memory_order_relaxed)) profile_begin(id, st, &token);
+  ProfScope(int id, cudaStream_t st, double work = 0.0) : s(st) {
+    if (g_profile_on.load(std::memory_order_relaxed)) profile_begin(id, st, &token, work);
   }
   ~ProfScope() {
     if (token) profile_end(token, s);

@@ -430,7 +430,7 @@ int pb2_pack(const pb2_bnd_table *table, double *buf, int32_t *nonzero_flags,
   PB2_REQUIRE(table && table->kind == kBnd, "pack needs a boundary table");
   if (table->nchunks == 0) return PB2_OK;
   PB2_REQUIRE(buf, "null buffer");
-  ProfScope prof(K_PACK, as_stream(stream));
+  ProfScope prof(K_PACK, as_stream(stream), static_cast<double>(table->elements));
   pack_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, buf, nonzero_flags);
   PB2_LAUNCH_CHECK();
@@ -442,7 +442,7 @@ int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *dat
   PB2_REQUIRE(table && table->kind == kBnd, "unpack needs a boundary table");
   if (table->nchunks == 0) return PB2_OK;
   PB2_REQUIRE(buf, "null buffer");
-  ProfScope prof(K_UNPACK, as_stream(stream));
+  ProfScope prof(K_UNPACK, as_stream(stream), static_cast<double>(table->elements));
   unpack_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, buf, data_flags);
   PB2_LAUNCH_CHECK();
@@ -452,7 +452,7 @@ int pb2_unpack(const pb2_bnd_table *table, const double *buf, const int32_t *dat
 int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kCopy, "copy needs a copy table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_COPY, as_stream(stream));
+  ProfScope prof(K_COPY, as_stream(stream), static_cast<double>(table->elements));
   copy_kernel<0><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, nonzero_flags);
   PB2_LAUNCH_CHECK();
@@ -462,7 +462,7 @@ int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t st
 int pb2_copy_flags(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kCopy && nonzero_flags, "copy_flags needs a copy table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_COPY, as_stream(stream));
+  ProfScope prof(K_COPY, as_stream(stream), static_cast<double>(table->elements));
   copy_kernel<1><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, nonzero_flags);
   PB2_LAUNCH_CHECK();
@@ -472,7 +472,7 @@ int pb2_copy_flags(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_strea
 int pb2_copy_select(const pb2_bnd_table *table, const int32_t *data_flags, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kCopy, "copy_select needs a copy table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_COPY, as_stream(stream));
+  ProfScope prof(K_COPY, as_stream(stream), static_cast<double>(table->elements));
   copy_kernel<2><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, const_cast<int32_t *>(data_flags));
   PB2_LAUNCH_CHECK();
@@ -525,7 +525,8 @@ int pb2_halo_copy_uniform(const pb2_pack_geom *pg, double *field, const int32_t 
   g.parts = (g.total + g.per_part - 1) / g.per_part;
   const int64_t ctas = (int64_t)g.nblocks * g.ncomp * g.parts;
   PB2_REQUIRE(ctas < (1ll << 31), "grid too large");
-  ProfScope prof(K_HALO_UNIFORM, as_stream(stream));
+  ProfScope prof(K_HALO_UNIFORM, as_stream(stream),
+                 static_cast<double>(g.total) * (v2 ? 2 : 1) * g.nblocks * g.ncomp);
   if (v2)
     halo_uniform_kernel<2><<<static_cast<unsigned>(ctas), kThreads, 0, as_stream(stream)>>>(g, field, nbr);
   else

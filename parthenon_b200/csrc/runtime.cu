@@ -22,21 +22,24 @@ std::atomic<int> g_profile_on{0};
 namespace {
 struct ProfPair {
   int id;
+  double work;
   cudaEvent_t a, b;
 };
 std::mutex g_prof_mu;
 std::vector<ProfPair *> g_prof_pending, g_prof_free;
 double g_prof_ms[K_COUNT];
 int64_t g_prof_n[K_COUNT];
+double g_prof_work[K_COUNT];
 const char *kKernelNames[K_COUNT] = {
     "pack_kernel", "unpack_kernel", "copy_kernel", "restrict_kernel", "prolongate_kernel",
     "weighted_sum_kernel", "flux_div_kernel", "flux_x_kernel", "flux_march_kernel<y>",
     "flux_march_kernel<z>", "update_kernel", "derived_dt_kernel", "history_kernel",
     "sweep_x_kernel", "sweep_march_kernel<y>", "sweep_march_kernel<z>",
-    "interior_kernel", "halo_uniform_kernel", "flux_correct_kernel", "advection_flux_kernel", "apply_bc_kernel"};
+    "interior_kernel", "halo_uniform_kernel", "flux_correct_kernel", "advection_flux_kernel", "apply_bc_kernel",
+    "sweep_xpair_kernel", "sweep_chunk_kernel<y>", "sweep_chunk_kernel<z>"};
 } // namespace
 
-void profile_begin(int id, cudaStream_t s, void **token) {
+void profile_begin(int id, cudaStream_t s, void **token, double work) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfPair *p = nullptr;
   if (!g_prof_free.empty()) {
@@ -51,6 +54,7 @@ void profile_begin(int id, cudaStream_t s, void **token) {
     }
   }
   p->id = id;
+  p->work = work;
   cudaEventRecord(p->a, s);
   *token = p;
 }
@@ -68,6 +72,7 @@ static void profile_collect() {
     if (cudaEventElapsedTime(&ms, p->a, p->b) == cudaSuccess) {
       g_prof_ms[p->id] += ms;
       g_prof_n[p->id] += 1;
+      g_prof_work[p->id] += p->work;
     } else {
       cudaGetLastError();
     }
@@ -153,6 +158,7 @@ int pb2_profile_reset(void) {
   for (int i = 0; i < K_COUNT; ++i) {
     g_prof_ms[i] = 0;
     g_prof_n[i] = 0;
+    g_prof_work[i] = 0;
   }
   return PB2_OK;
 }
@@ -163,6 +169,13 @@ int pb2_profile_get(int id, const char **name, double *total_ms, int64_t *launch
   if (name) *name = kKernelNames[id];
   if (total_ms) *total_ms = g_prof_ms[id];
   if (launches) *launches = g_prof_n[id];
+  return PB2_OK;
+}
+
+int pb2_profile_get_work(int id, double *work) {
+  PB2_REQUIRE(id >= 0 && id < K_COUNT && work, "bad kernel id");
+  profile_collect();
+  *work = g_prof_work[id];
   return PB2_OK;
 }
 

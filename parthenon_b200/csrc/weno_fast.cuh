@@ -96,22 +96,31 @@ static const WenoConst kW = {13.0 / 3.0, 0.1, 0.6, 0.3, 0.1 / 6.0, 0.6 / 6.0, 0.
                              10.0 * DBL_EPSILON / 3.0};
 #endif
 
-PB2_HD void WENO5Z(const double q0, const double q1, const double q2, const double q3,
-                   const double q4, double &ql, double &qr) {
+// c13 a^2 + eps of the second difference a = dhi - dlo: the part of a smoothness indicator that
+// THREE neighbouring cells share (beta0 of cell c+1, beta1 of cell c, beta2 of cell c-1 all hold
+// the second difference centred at c) — a marching thread computes it once per row
+PB2_HD double weno_curv(const double dlo, const double dhi) {
   constexpr double eps = 10.0 * DBL_EPSILON; // robust.hpp:39-42
-  const double c13 = kW.c13, g0 = kW.g0, g1 = kW.g1, g2 = kW.g2;
+  const double a = dhi - dlo;
+  return fma(kW.c13 * a, a, eps);
+}
 
-  const double d1 = q1 - q0, d2 = q2 - q1, d3 = q3 - q2, d4 = q4 - q3;
+// WENO5-Z of cell c from its four first differences d_k = q_k - q_{k-1} (d1 = q1 - q0 ... d4 =
+// q4 - q3 in the numbering of recon.hpp:43), the curvature terms A0, A1, A2 = weno_curv centred
+// at c-1, c, c+1 and the cell value q2
+PB2_HD void WENO5Z_diff(const double d1, const double d2, const double d3, const double d4,
+                        const double A0, const double A1, const double A2, const double q2,
+                        double &ql, double &qr) {
+  constexpr double eps = 10.0 * DBL_EPSILON;
+  const double g0 = kW.g0, g1 = kW.g1, g2 = kW.g2;
   const double s23 = d2 + d3; // q3 - q1
 
-  // smoothness indicators (recon.hpp:52-60): second difference a, one-sided slope b
-  double a = d2 - d1, b = fma(3.0, d2, -d1);
-  const double b0 = fma(c13 * a, a, fma(b, b, eps));
-  a = d3 - d2;
-  const double b1 = fma(c13 * a, a, fma(s23, s23, eps));
-  a = d4 - d3;
+  // smoothness indicators (recon.hpp:52-60): curvature term + one-sided slope squared
+  double b = fma(3.0, d2, -d1);
+  const double b0 = fma(b, b, A0);
+  const double b1 = fma(s23, s23, A1);
   b = fma(-3.0, d3, d4);
-  const double b2 = fma(c13 * a, a, fma(b, b, eps));
+  const double b2 = fma(b, b, A2);
   const double tau5 = fabs(b2 - b0);
 
   // r_k = (b_k + tau5) / b_k = 1 + tau5 * (product of the other two) / (b0 b1 b2)
@@ -153,6 +162,21 @@ PB2_HD void WENO5Z(const double q0, const double q1, const double q2, const doub
   const double om = fma(-6.0, X, 1.0);
   ql = fma(X, dl, fma(om, dq, q2));
   qr = fma(X, dr, fma(-om, dq, q2));
+}
+
+PB2_HD void WENO5Z(const double q0, const double q1, const double q2, const double q3,
+                   const double q4, double &ql, double &qr) {
+  const double d1 = q1 - q0, d2 = q2 - q1, d3 = q3 - q2, d4 = q4 - q3;
+  WENO5Z_diff(d1, d2, d3, d4, weno_curv(d1, d2), weno_curv(d2, d3), weno_curv(d3, d4), q2, ql,
+              qr);
+}
+
+// 0.5 * mc-limited linear reconstruction from the two first differences around the cell
+PB2_HD void Linear_diff(const double dm, const double dp, const double q0, double &ql,
+                        double &qr) {
+  const double dq = half_mc(dm, dp, dm + dp);
+  ql = q0 + dq;
+  qr = q0 - dq;
 }
 
 } // namespace fastmath

@@ -2,6 +2,7 @@
 // a whole MeshData batch to the sm_100a kernels (see burgers_package.hpp).
 #include "burgers_package.hpp"
 
+#include <algorithm>
 #include <cfloat>
 #include <string>
 
@@ -25,7 +26,7 @@ pb2_burgers_args MakeArgs(MeshData<Real> *md, Variable &u) {
 }
 
 // one device scalar per MeshData batch that the update kernel min-reduces into
-Real *DtScratch(MeshData<Real> *md) { return md->GetMeshPointer()->ScratchReal() + 8 + md->partition_id() % 32; }
+Real *DtScratch(MeshData<Real> *md) { return md->DtCell(); }
 
 void ResetDt(MeshData<Real> *md) {
   static const Real huge = DBL_MAX;
@@ -67,6 +68,9 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
   cfg.math = math == "strict" ? PB2_MATH_STRICT : PB2_MATH_FAST;
   pkg->AddParam("kernel_config", cfg);
   pkg->AddParam("fused_stage", pin->GetOrAddBoolean("pb2", "fused_stage", true));
+  // fast fused stage on a uniform mesh: the last direction sweep stores the same-device ghost
+  // cells itself (pb2_burgers_args::push_nbr) instead of a ghost-exchange pass after the stage
+  pkg->AddParam("ghost_push", pin->GetOrAddBoolean("pb2", "ghost_push", true));
 
   const int num_scalars = pin->GetOrAddInteger("burgers", "num_scalars", 1);
   pkg->AddParam("num_scalars", num_scalars);
@@ -165,6 +169,13 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   BvarsCache &bc = GetBvarsCache(mc1);
   const bool split = a.math == PB2_MATH_FAST && !pm->multilevel && bc.n_boundary > 0 &&
                      bc.n_interior > 0 && bc.plan.send_elements > 0;
+  if (a.math == PB2_MATH_FAST && !flxcor && bc.uniform_halo && bc.vars.size() == 1 &&
+      bc.vars[0] == &mc1->Get("U") && a.geom.ndim >= 2 && pkg->Param<bool>("ghost_push") &&
+      std::min({a.geom.nx[0], a.geom.nx[1], a.geom.ndim > 2 ? a.geom.nx[2] : a.geom.nx[1]}) >=
+          2 * a.geom.ng) {
+    a.push_nbr = bc.halo_nbr.get<int32_t>();
+    bc.ghosts_pushed = true;
+  }
   if (flxcor) {
     // CalculateFluxes -> flux correction -> FluxDivergence + update (burgers_driver.cpp:92-104).
     // Only blocks with a face neighbour on another level exchange flux corrections; with

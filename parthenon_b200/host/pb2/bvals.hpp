@@ -127,6 +127,9 @@ struct BvarsCache {
   // one descriptor-free launch per field pulls every ghost cell from the owning neighbour
   // (pb2_halo_copy_uniform); halo_nbr is [nblocks][27] on the device
   bool uniform_halo = false;
+  // the producer of this container's data already stored the same-device ghosts (the last sweep
+  // of the fused burgers stage, pb2_burgers_args::push_nbr): SetBounds<local> has nothing to copy
+  bool ghosts_pushed = false;
   DeviceBuffer halo_nbr;
   pb2_bnd_table *pack = nullptr, *unpack = nullptr;
   // [0]: regions whose neighbour is local, [1]: nonlocal

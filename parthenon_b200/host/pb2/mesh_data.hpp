@@ -143,6 +143,13 @@ class MeshData {
   // C-ABI geometry descriptor of a field of this batch
   pb2_pack_geom Geometry(Variable &v);
 
+  // one device Real owned by this batch: the min-dt cell its stage kernels reduce into (every
+  // batch needs its own — task lists of different partitions interleave on the stream)
+  Real *DtCell() {
+    if (!dt_cell_) dt_cell_.Allocate(sizeof(Real), stream());
+    return dt_cell_.get<Real>();
+  }
+
   BvarsCache &bvars() { return *bvars_; }
   // bumped whenever an allocation status changes; the exchange tables are rebuilt when
   // their generation differs (replaces the per-call host walk of
@@ -157,7 +164,7 @@ class MeshData {
   std::map<std::string, std::shared_ptr<Variable>> vars_;
   std::vector<std::shared_ptr<Variable>> order_;
   std::map<std::string, std::unique_ptr<VariablePack>> pack_cache_;
-  DeviceBuffer dx_, xmin_;
+  DeviceBuffer dx_, xmin_, dt_cell_;
   std::unique_ptr<BvarsCache> bvars_;
 };
 

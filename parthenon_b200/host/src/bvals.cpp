@@ -713,7 +713,9 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
   Mesh *pm = md->GetMeshPointer();
   pb2_stream_t st = md->stream();
   if (DoesLocal(bt)) {
-    if (c.uniform_halo) {
+    if (c.uniform_halo && c.ghosts_pushed) {
+      c.ghosts_pushed = false; // this exchange's copies were the producer's own stores
+    } else if (c.uniform_halo) {
       for (Variable *v : c.vars) {
         const pb2_pack_geom g = md->Geometry(*v);
         PB2_CHECK(pb2_halo_copy_uniform(&g, v->data(), c.halo_nbr.get<int32_t>(), st));

@@ -1,8 +1,6 @@
-"""GPU tests of device paths that were WRITTEN AFTER THE GPU BUDGET OF ROUND 1 WAS SPENT.  Their
-oracles are pinned to the reference (tests/test_oracle_golden.py), the device code has not been
-run once, so every test here is a non-strict expected failure: a pass shows up as XPASS, a
-mismatch as xfail, neither breaks the suite.  The file sorts last so that nothing runs after it
-in the same process.  Remove the marks once a run has confirmed them."""
+"""GPU tests of device paths written after the GPU budget of round 1 was spent.  They first ran
+on the driver's box at the end of that round (GPUTEST_r01.json: all passed) and are ordinary
+tests since: a mismatch fails the suite."""
 import os
 
 import numpy as np
@@ -16,9 +14,6 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: the oracle "
-                   "is pinned to the reference for this case, the device path (te_toth_roe "
-                   "regions in host/src/amr.cpp) has not been run yet")
 @pytest.mark.parametrize("name,ndim,nx,nb,numlevel", H.TEAMR_TOTH_ROE)
 def test_adaptive_remesh_with_toth_roe_crc(name, ndim, nx, nb, numlevel):
     """the adaptive runs with ProlongateInternalTothAndRoe registered for the face field
@@ -46,8 +41,6 @@ def test_adaptive_remesh_with_toth_roe_crc(name, ndim, nx, nb, numlevel):
         sim.close()
 
 
-@pytest.mark.xfail(strict=False, reason="sparse fields on refined meshes: opt-in device path "
-                   "(pb2/unverified_sparse_multilevel) that has not been run yet")
 def test_sparse_advection_on_refined_mesh():
     """sparse fields on a three-level statically refined mesh (same-device channels):
     allocation-aware restriction / prolongation / flux correction vs the reference's dumps"""
