@@ -401,12 +401,14 @@ typedef struct pb2_burgers_args {
   int32_t num_block_ids;
   /* PB2_MATH_FAST, pb2_burgers_stage only.  Device table [geom.nblocks][27] of same-device
    * neighbour blocks (index (ox+1) + 3(oy+1) + 9(oz+1), -1 = none: physical boundary, another
-   * device, another level) as pb2_halo_copy_uniform takes it, or NULL.  If given, the last
-   * direction sweep also stores every finished cell within nghost of a block face into the ghost
-   * cells of those neighbours of `out`: SendBoundBufs<local> + SetBounds<local> of a uniform
-   * mesh (boundary_communication.cpp:95-140, :273-334) without a pass of their own — the caller
-   * then skips its same-device exchange of `out`.  Needs ndim >= 2. */
-  const int32_t *push_nbr;
+   * device, another level) as pb2_halo_copy_uniform takes it, or NULL.  If given, stencil values
+   * beyond a block face that has such a neighbour are read from the neighbour's INTERIOR cells
+   * instead of the block's own ghost cells — the values SendBoundBufs<local> + SetBounds<local>
+   * (boundary_communication.cpp:95-140, :273-334) would have copied there — so the ghost cells
+   * of `u` across those faces need not be current: the caller may leave the same-device ghost
+   * exchange out of the cycle and run it only when something else reads ghost cells.  Only the
+   * six face entries are used (a direction sweep never reads edge or corner ghosts). */
+  const int32_t *nbr_direct;
 } pb2_burgers_args;
 
 /* fluxes only: writes args->flux[0..ndim-1] from args->u */

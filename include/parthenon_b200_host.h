@@ -139,6 +139,25 @@ int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t
 /* the history columns "MS Mass 0..7" of the burgers benchmark, reduced over ranks */
 int pb2h_sim_history(pb2h_sim *sim, double out[8]);
 
+/* A SparsePack over one container of the running application (parthenon::MakePackDescriptor +
+ * Descriptor::GetPack, host/pb2/sparse_pack.hpp), handed out as the POD a user kernel takes by
+ * value (include/parthenon_b200_pack.h).  names: '\n'-separated variable (or sparse pool) names,
+ * each optionally prefixed "re:" for a regular expression; flags: '\n'-separated Metadata flag
+ * names every selected field must carry ("WithFluxes", "FillGhost", "Independent", "Sparse" ...);
+ * options: bit 0 WithFluxes, bit 1 Coarse, bit 2 Flatten.  The tables stay valid until the
+ * container's allocation status changes (ask again then: the pack is cached otherwise).
+ * host_bounds (optional): the bounds table [2][nblocks][nvar+1] copied to the host. */
+#include "parthenon_b200_pack.h"
+int pb2h_sim_sparse_pack(pb2h_sim *sim, const char *container, const char *names,
+                         const char *flags, int options, pb2_sparse_pack *pack,
+                         int32_t *host_bounds, int64_t host_bounds_len);
+/* label of pack entry (b, idx), as SparsePack::LabelHost */
+const char *pb2h_sim_sparse_pack_label(pb2h_sim *sim, const char *container, const char *names,
+                                       const char *flags, int options, int b, int idx);
+/* (de)allocate a sparse field on one block of every container (MeshBlock::AllocateSparse /
+ * DeallocateSparse) — lets a test reproduce tst/unit/test_sparse_pack.cpp */
+int pb2h_sim_set_sparse_allocation(pb2h_sim *sim, const char *field, int lid, int allocated);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,7 +78,7 @@ class BurgersArgs(C.Structure):
                 ("flux", C.c_void_p * 3), ("derived", C.c_void_p), ("dt_min", C.c_void_p),
                 ("beta", C.c_double), ("dt", C.c_double),
                 ("block_ids", C.c_void_p), ("num_block_ids", C.c_int32),
-                ("push_nbr", C.c_void_p)]
+                ("nbr_direct", C.c_void_p)]
 
 
 _lib = None

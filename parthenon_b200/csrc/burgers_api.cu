@@ -186,12 +186,6 @@ int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream) {
     if (int rc = require_device()) return rc;
     if (args->geom.nblocks == 0) return PB2_OK;
     PB2_REQUIRE(args->out != args->u, "the fused stage cannot write its stencil input");
-    if (args->push_nbr) {
-      PB2_REQUIRE(args->geom.ndim >= 2, "the ghost push needs a 2-D or 3-D mesh");
-      for (int d = 0; d < args->geom.ndim; ++d)
-        PB2_REQUIRE(args->geom.nx[d] >= 2 * args->geom.ng,
-                    "the ghost push needs blocks at least two ghost widths wide");
-    }
     return burgers_stage_sweep(args, as_stream(stream));
   }
   if (int rc = pb2_burgers_calculate_fluxes(args, stream)) return rc;

@@ -13,14 +13,19 @@
 //      (weno_fast.cuh: WENO5Z_diff), so a reconstruction costs ~85 FP64 instructions instead
 //      of the ~165 of the reference's expression tree (recon.hpp:43-99);
 //   3. in the LAST sweep of a stage finishes the chunk's cells: derived field, min dt
-//      (burgers_package.cpp:143-200), and — when the caller passes the mesh's neighbour table —
-//      stores every finished cell that lies within nghost of a block face straight into the
-//      ghost cells of the blocks that own that face's other side.  That replaces the whole
-//      same-device ghost exchange of the stage (SendBoundBufs + SetBounds,
-//      boundary_communication.cpp:95-140, :273-334) by stores: no second pass over the field.
-// What a component carries from chunk to chunk (left state and flux of the last face) sits
-// in a per-thread shared-memory column; the five stencil rows are re-read at a chunk start
-// (L1 / L2 hits).
+//      (burgers_package.cpp:143-200).
+// The rows of a component are staged asynchronously (cp.async) into a per-thread shared-memory
+// column one component ahead of the arithmetic.  What a component carries from chunk to chunk
+// (left state and flux of the last face) sits in a per-thread shared-memory column as well; the
+// four overlapping stencil rows are re-read at a chunk start (L2 hits).
+//
+// Ghost rows: with Args::nbr (the mesh's same-device neighbour table) the stencil rows beyond a
+// block face are read from the INTERIOR rows of the block on the other side of that face instead
+// of from the block's own ghost rows — the values SendBoundBufs + SetBounds
+// (boundary_communication.cpp:95-140, :273-334) would have copied there.  The caller can then
+// leave the same-device ghost exchange out of the cycle and refresh ghost cells only when
+// something else wants to read them.  Faces without a same-device neighbour (physical
+// boundary, another GPU) keep reading the block's ghost rows.
 //
 // GEO = 32 fixes the geometry at compile time (32^3 cells, 4 ghosts, 3-D: the benchmark's
 // block): every component / row offset becomes an immediate of the load or store.
@@ -30,10 +35,10 @@ namespace pb2 {
 namespace PB2_SWEEP_NS {
 
 #ifndef PB2_CHUNK
-#define PB2_CHUNK 8
+#define PB2_CHUNK 4
 #endif
 #ifndef PB2_CHUNK_MINB
-#define PB2_CHUNK_MINB 3
+#define PB2_CHUNK_MINB 4
 #endif
 constexpr int kChunk = PB2_CHUNK;
 
@@ -107,13 +112,24 @@ constexpr int kURows = kChunk + 4; // rows of u per stage buffer (weno5)
 constexpr int kStageDoubles = kURows + kChunk; // + the old `out` values of the chunk's cells
 
 // rows of u (stencil) and old values of out for CH cells starting at march cell s0; pu / po
-// point at the component's row of cell s0
-template <int RECON, int CH>
+// point at the component's row of cell s0.  EDGE: some rows lie beyond the block's ends; they
+// come from the neighbour block (element offsets dlo / dhi from the own-row address, 0 = own
+// ghost row).
+template <int RECON, int CH, bool EDGE>
 __device__ __forceinline__ void stage_issue(const uint32_t st, const double *__restrict__ pu,
-                                            const double *po, const int64_t sd, const int s0) {
+                                            const double *po, const int64_t sd, const int s0,
+                                            const int nd, const long long dlo,
+                                            const long long dhi) {
   constexpr int lo = StencilRows<RECON>::kLo, nrow = CH + StencilRows<RECON>::kExtra;
 #pragma unroll
-  for (int r = 0; r < nrow; ++r) cp_async8(st + r * kThreads * 8, pu + (lo + r) * sd);
+  for (int r = 0; r < nrow; ++r) {
+    const double *src = pu + (lo + r) * sd;
+    if (EDGE) {
+      const int rr = s0 + lo + r;
+      src += rr < 0 ? dlo : (rr >= nd ? dhi : 0);
+    }
+    cp_async8(st + r * kThreads * 8, src);
+  }
 #pragma unroll
   for (int t = 0; t < CH; ++t)
     if (s0 + t >= 1) cp_async8(st + (kURows + t) * kThreads * 8, po + (t - 1) * sd);
@@ -184,67 +200,24 @@ struct MarchStencil<PB2_RECON_LINEAR> {
   }
 };
 
-// Ghost push of the LAST sweep: where a finished cell of this thread's column also goes.
-// Element offsets from the cell to its images in the ghost zones of neighbour blocks:
-//   d[0..2]: the neighbours at (ox,0), (0,oo), (ox,oo) in the plane across the march — every
-//            cell of the column; bit i of `col` set if the thread has that target;
-//   d[3..6]: the neighbours at (0,0), (ox,0), (0,oo), (ox,oo) one block DOWN the march
-//            direction — only cells within nghost of the block's low end (the steps of the
-//            chunk in `steps[0]`); bit i of `band[0]` set if the thread has that target;
-//   d[7..10], steps[1], band[1]: the same one block UP, for cells within nghost of the high end.
-// The offsets sit in a per-thread shared-memory column (+ i * kThreads).
-constexpr int kPushSlots = 11;
-struct PushCtx {
-  const long long *d;
-  unsigned col, band[2], steps[2];
-};
-
 // CH cells of one component out of the stage column `st` (rows of u, then old values of out).
 // Cell s gives face s its right state and cell s-1 its last flux; the previous cell's left
 // state L and the previous face's flux F come in and go out.  po points at the component's
 // row of cell s0 in `out`.
-template <int RECON, bool COEF, bool PUSH, int CH>
+template <int RECON, bool COEF, int CH>
 __device__ __forceinline__ void comp_chunk(const double *st, double *po, const int64_t sd,
                                            const int s0, const double cd, double &L, double &F,
-                                           double (&P)[CH], double (&Q)[CH],
-                                           const PushCtx &px) {
+                                           double (&P)[CH], double (&Q)[CH]) {
   MarchStencil<RECON> ms;
   ms.init(st);
-  long long dx = 0, dy = 0, dxy = 0;
-  const bool wy = PUSH && (px.col & 6u) != 0;
-  if (PUSH) {
-    dx = px.d[0];
-    if (wy) {
-      dy = px.d[kThreads];
-      dxy = px.d[2 * kThreads];
-    }
-  }
 #pragma unroll
   for (int t = 0; t < CH; ++t) {
     double ql, qr;
     ms.recon(ql, qr);
     if (COEF) face_pq(L, qr, P[t], Q[t]);
     const double f = fma(P[t], L, Q[t] * qr);
-    if (s0 + t >= 1) { // face s and face s-1 are known: cell s-1 is complete
-      double *p = po + (t - 1) * sd;
-      const double v = fma(cd, f - F, st[(kURows + t) * kThreads]);
-      *p = v;
-      if (PUSH) {
-        if (px.col & 1u) p[dx] = v;
-        if (wy) {
-          if (px.col & 2u) p[dy] = v;
-          if (px.col & 4u) p[dxy] = v;
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if ((px.steps[e] >> t) & 1u) { // uniform: the cell lies within nghost of that end
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if ((px.band[e] >> i) & 1u) p[px.d[(3 + 4 * e + i) * kThreads]] = v;
-          }
-        }
-      }
-    }
+    if (s0 + t >= 1) // face s and face s-1 are known: cell s-1 is complete
+      po[(t - 1) * sd] = fma(cd, f - F, st[(kURows + t) * kThreads]);
     F = f;
     L = ql;
     if (t + 1 < CH) ms.advance(st, t);
@@ -289,11 +262,9 @@ struct ColumnCtx {
   double *ob;       // out, same place
   double *sL, *sF;  // per-thread carry columns in shared memory (+ n * kThreads)
   double *stage;    // per-thread stage columns: [2][kStageDoubles] (+ i * kThreads)
-  long long *pd;    // per-thread push offsets [kPushSlots] (+ i * kThreads), LAST sweep
-  const int *s_nbr; // neighbour table of block b in shared memory, or null (no ghost push)
-  int64_t sb, col0;
-  int b, nc, ci, co, nd;
-  unsigned pcol;    // PushCtx::col
+  long long dlo, dhi; // ghost rows below / above the block: offset to the neighbour's rows
+  int64_t col0;
+  int b, nc, nd;
   double cdir, idx0, idx1, idx2;
 };
 
@@ -313,62 +284,24 @@ __device__ __forceinline__ void issue_item(const GeoT<GEO> &G, const ColumnCtx &
   const int64_t off = n * G.sc() + (int64_t)(G.is(DIR) + s0n) * sd;
   const uint32_t st = static_cast<uint32_t>(__cvta_generic_to_shared(
       c.stage + (size_t)buf * kStageDoubles * kThreads));
-  if (c.nd + 1 - s0n >= kChunk)
-    stage_issue<RECON, kChunk>(st, c.ub + off, c.ob + off, sd, s0n);
-  else
-    stage_issue<RECON, 1>(st, c.ub + off, c.ob + off, sd, s0n);
+  constexpr int lo = StencilRows<RECON>::kLo, extra = StencilRows<RECON>::kExtra;
+  if (c.nd + 1 - s0n >= kChunk) {
+    if (s0n + lo < 0 || s0n + lo + kChunk + extra > c.nd)
+      stage_issue<RECON, kChunk, true>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, c.dlo, c.dhi);
+    else
+      stage_issue<RECON, kChunk, false>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, 0, 0);
+  } else {
+    stage_issue<RECON, 1, true>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, c.dlo, c.dhi);
+  }
   cp_async_commit();
 }
 
-// targets of the ghost push down / up the march direction for the chunk that starts at march
-// cell s0: fills offsets 3..10 of the thread's table and PushCtx::band / ::steps
-template <int DIR, int GEO, int CH>
-__device__ __forceinline__ void push_bands(const GeoT<GEO> &G, const ColumnCtx &c, const int s0,
-                                           PushCtx &px) {
-  const int OD = (DIR == 1) ? 2 : 1;
-  const int64_t sd = (DIR == 1) ? G.sj() : G.sk();
-  const int64_t so = (DIR == 1) ? G.sk() : G.sj();
-  const int nx0 = G.nx(0), nxo = G.nx(OD), nxm = G.nx(DIR), gm = G.is(DIR);
-  const int ox = (c.pcol & 8u) ? (c.ci < G.is(0) ? -1 : 1) : 0;
-  const int oo = (c.pcol & 16u) ? (c.co < G.is(OD) ? -1 : 1) : 0;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    px.band[e] = 0;
-    px.steps[e] = 0;
-#pragma unroll
-    for (int t = 0; t < CH; ++t) {
-      const int kk = s0 + t - 1; // the cell step t completes
-      if (kk >= 0 && (e == 0 ? kk < gm : kk >= nxm - gm)) px.steps[e] |= 1u << t;
-    }
-    if (px.steps[e] == 0) continue;
-    const int om = e == 0 ? -1 : 1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int tx = (i & 1) ? ox : 0, to = (i & 2) ? oo : 0;
-      if (((i & 1) && ox == 0) || ((i & 2) && oo == 0)) continue;
-      const int oy = (DIR == 1) ? om : to, oz = (DIR == 1) ? to : om;
-      const int nb = c.s_nbr[(tx + 1) + 3 * (oy + 1) + 9 * (oz + 1)];
-      if (nb < 0) continue;
-      c.pd[(3 + 4 * e + i) * kThreads] =
-          (long long)(nb - c.b) * c.sb -
-          ((long long)om * nxm * sd + (long long)to * nxo * so + tx * nx0);
-      px.band[e] |= 1u << i;
-    }
-  }
-}
-
-template <int RECON, int DIR, bool LAST, bool PUSH, int GEO, int CH>
+template <int RECON, int DIR, bool LAST, int GEO, int CH>
 __device__ __forceinline__ void run_chunk(const Args &a, const GeoT<GEO> &G, const ColumnCtx &c,
                                           const int s0, int &buf, double &rate) {
   const int64_t sd = (DIR == 1) ? G.sj() : G.sk();
   double P[CH], Q[CH];
   const int64_t row0 = (int64_t)(G.is(DIR) + s0) * sd;
-  PushCtx px;
-  px.d = c.pd;
-  px.col = c.pcol;
-  px.band[0] = px.band[1] = 0;
-  px.steps[0] = px.steps[1] = 0;
-  if (PUSH) push_bands<DIR, GEO, CH>(G, c, s0, px);
 #pragma unroll 1
   for (int m = 0; m < c.nc; ++m) {
     // next item in flight: component m+1 of this chunk, or the first of the next one
@@ -388,9 +321,9 @@ __device__ __forceinline__ void run_chunk(const Args &a, const GeoT<GEO> &G, con
     const double cd = n < 3 ? 0.5 * c.cdir : c.cdir;
     double *po = c.ob + n * G.sc() + row0;
     if (m == 0)
-      comp_chunk<RECON, true, PUSH, CH>(st, po, sd, s0, cd, L, F, P, Q, px);
+      comp_chunk<RECON, true, CH>(st, po, sd, s0, cd, L, F, P, Q);
     else
-      comp_chunk<RECON, false, PUSH, CH>(st, po, sd, s0, cd, L, F, P, Q, px);
+      comp_chunk<RECON, false, CH>(st, po, sd, s0, cd, L, F, P, Q);
     c.sL[n * kThreads] = L;
     c.sF[n * kThreads] = F;
     buf ^= 1;
@@ -402,8 +335,12 @@ __device__ __forceinline__ void run_chunk(const Args &a, const GeoT<GEO> &G, con
   }
 }
 
-// PUSH (LAST sweep only): a.nbr is the neighbour table, finished cells also go to its ghosts
-template <int RECON, int DIR, bool LAST, bool PUSH, int GEO>
+// index of a face neighbour in the 27-entry table: (ox+1) + 3 (oy+1) + 9 (oz+1)
+__device__ __forceinline__ constexpr int face_slot(const int dir, const int side) {
+  return 13 + (dir == 0 ? 1 : (dir == 1 ? 3 : 9)) * (side ? 1 : -1);
+}
+
+template <int RECON, int DIR, bool LAST, int GEO>
 __global__ void __launch_bounds__(kThreads, PB2_CHUNK_MINB) sweep_chunk_kernel(const Args a) {
   const GeoT<GEO> G(a.g);
   const int OD = (DIR == 1) ? 2 : 1;
@@ -413,25 +350,19 @@ __global__ void __launch_bounds__(kThreads, PB2_CHUNK_MINB) sweep_chunk_kernel(c
   const int b = a.block_ids ? a.block_ids[bi] : bi;
   const int col = (blockIdx.x % ctas_per_block) * kThreads + threadIdx.x;
   extern __shared__ double smem[];
-  __shared__ int s_nbr[27];
-  constexpr bool push = PUSH;
-  if (push) {
-    if (threadIdx.x < 27) s_nbr[threadIdx.x] = a.nbr[b * 27 + threadIdx.x];
-    __syncthreads();
-  }
   double rate = 0.0;
   if (col < ncol) {
     ColumnCtx c;
     c.b = b;
     c.nc = a.g.ncomp;
-    c.ci = col % G.nx(0);
-    c.co = col / G.nx(0);
+    const int ci = col % G.nx(0), co = col / G.nx(0);
     const int64_t so = (DIR == 1) ? G.sk() : G.sj();
+    const int64_t sd = (DIR == 1) ? G.sj() : G.sk();
     c.nd = G.nx(DIR);
-    c.col0 = (int64_t)(G.is(OD) + c.co) * so + (G.is(0) + c.ci); // inside a component
-    c.sb = a.g.sb;
-    c.ub = a.u + (int64_t)b * c.sb + c.col0;
-    c.ob = a.out + (int64_t)b * c.sb + c.col0;
+    c.col0 = (int64_t)(G.is(OD) + co) * so + (G.is(0) + ci); // inside a component
+    const int64_t sb = a.g.sb;
+    c.ub = a.u + (int64_t)b * sb + c.col0;
+    c.ob = a.out + (int64_t)b * sb + c.col0;
     c.idx0 = 1.0 / a.dx[3 * b];
     c.idx1 = 1.0 / a.dx[3 * b + 1];
     c.idx2 = 1.0 / a.dx[3 * b + 2];
@@ -439,50 +370,32 @@ __global__ void __launch_bounds__(kThreads, PB2_CHUNK_MINB) sweep_chunk_kernel(c
     c.sL = smem + threadIdx.x;
     c.sF = c.sL + (size_t)c.nc * kThreads;
     c.stage = c.sF + (size_t)c.nc * kThreads;
-    c.pd = reinterpret_cast<long long *>(c.stage + (size_t)2 * kStageDoubles * kThreads);
-    c.s_nbr = push ? s_nbr : nullptr;
-    c.pcol = 0;
+    c.dlo = 0;
+    c.dhi = 0;
+    if (a.nbr) {
+      // rows beyond the block's ends: the same columns of the face neighbour's interior
+      const int nlo = a.nbr[b * 27 + face_slot(DIR, 0)], nhi = a.nbr[b * 27 + face_slot(DIR, 1)];
+      if (nlo >= 0) c.dlo = (long long)(nlo - b) * sb + (long long)c.nd * sd;
+      if (nhi >= 0) c.dhi = (long long)(nhi - b) * sb - (long long)c.nd * sd;
+    }
     for (int n = 0; n < c.nc; ++n) {
       c.sL[n * kThreads] = 0.0;
       c.sF[n * kThreads] = 0.0;
-    }
-    if (push) {
-      // neighbours across the march direction: every finished cell of the column goes there
-      const int nx0 = G.nx(0), nxo = G.nx(OD), g0 = G.is(0), go = G.is(OD);
-      // (blocks are at least two ghost widths wide here — checked at launch — so a column feeds
-      // at most one neighbour per direction)
-      const int ox = c.ci < g0 ? -1 : (c.ci >= nx0 - g0 ? 1 : 0);
-      const int oo = c.co < go ? -1 : (c.co >= nxo - go ? 1 : 0);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int tx = (i != 1) ? ox : 0, to = (i != 0) ? oo : 0;
-        if ((i != 1 && ox == 0) || (i != 0 && oo == 0)) continue;
-        const int oy = (DIR == 1) ? 0 : to, oz = (DIR == 1) ? to : 0;
-        const int nb = s_nbr[(tx + 1) + 3 * (oy + 1) + 9 * (oz + 1)];
-        if (nb < 0) continue;
-        c.pd[i * kThreads] =
-            (long long)(nb - b) * c.sb - ((long long)to * nxo * so + tx * nx0);
-        c.pcol |= 1u << i;
-      }
-      // bits 0 / 1 of pcol double as "has an x / other offset" for the band targets
-      // (push_bands); a missing in-plane neighbour (physical boundary) clears the bit, which
-      // would also drop the diagonal band targets — so keep the offsets' existence apart:
-      c.pcol |= (ox != 0 ? 8u : 0u) | (oo != 0 ? 16u : 0u);
     }
     // cells s = -1 .. nd: whole chunks, then single cells; the first item's rows start now
     int s0 = -1, buf = 0;
     issue_item<RECON, DIR, GEO>(G, c, 0, s0, 0);
 #pragma unroll 1
     for (; c.nd + 1 - s0 >= kChunk; s0 += kChunk)
-      run_chunk<RECON, DIR, LAST, PUSH, GEO, kChunk>(a, G, c, s0, buf, rate);
+      run_chunk<RECON, DIR, LAST, GEO, kChunk>(a, G, c, s0, buf, rate);
 #pragma unroll 1
-    for (; s0 <= c.nd; ++s0) run_chunk<RECON, DIR, LAST, PUSH, GEO, 1>(a, G, c, s0, buf, rate);
+    for (; s0 <= c.nd; ++s0) run_chunk<RECON, DIR, LAST, GEO, 1>(a, G, c, s0, buf, rate);
   }
   if (LAST) reduce_dt(a, rate);
 }
 
 inline size_t chunk_smem_bytes(int ncomp) {
-  return sizeof(double) * kThreads * (2 * ncomp + 2 * kStageDoubles + kPushSlots);
+  return sizeof(double) * kThreads * (2 * ncomp + 2 * kStageDoubles);
 }
 
 } // namespace PB2_SWEEP_NS

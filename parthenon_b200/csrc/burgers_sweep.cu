@@ -62,8 +62,8 @@ struct Args {
   unsigned long long *dtmin; // LAST sweep only, or null
   const double *dx;          // [nblocks][3]
   const int *block_ids;      // launch block -> block of the batch, or null (identity)
-  const int *nbr;            // LAST sweep: [nblocks][27] same-device neighbour blocks (-1: none)
-                             // whose ghost cells take the finished cells, or null (no push)
+  const int *nbr;            // [nblocks][27] same-device neighbour blocks (-1: none) whose
+                             // interiors stand in for this block's ghost rows, or null
   double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
   FastDiv dncell, dnx1;      // x sweep: division by (nx1 + 2) and by nx2 as multiply-shift
   FastDiv dnpair;            // paired x sweep: division by nx1 / 2 + 1
@@ -520,7 +520,7 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   static const bool v1 = std::getenv("PB2_SWEEP_V1") != nullptr;
   const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool g32 = geo32(g) && al16(a.u) && al16(a.base) && al16(a.out) && g.sb % 2 == 0;
-  a.nbr = nullptr;
+  a.nbr = v1 ? nullptr : args->nbr_direct;
   if (!v1 && g.nx[0] % 2 == 0) {
     const int nrows = g.nx[1] * g.nx[2];
     const int warps = g.nblocks * ((nrows + kXRows - 1) / kXRows);
@@ -553,14 +553,11 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   }
   // y / z sweeps: chunked register march (burgers_march.cuh)
   if (!v1) {
-    const size_t csm = chunk_smem_bytes(g.ncomp);
     auto march = [&](auto kern, int dir, bool is_last) -> int {
       const int ncol = g.nx[dir == 1 ? 2 : 1] * g.nx[0];
       const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
-      if (is_last) {
-        last(a);
-        a.nbr = args->push_nbr;
-      }
+      if (is_last) last(a);
+      const size_t csm = chunk_smem_bytes(g.ncomp);
       PB2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(csm)));
       ProfScope prof(dir == 1 ? K_SWEEP_CHUNK_Y : K_SWEEP_CHUNK_Z, st, zones);
@@ -568,19 +565,15 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
       PB2_LAUNCH_CHECK();
       return PB2_OK;
     };
-    const bool push = args->push_nbr != nullptr;
     if (g.ndim == 2) {
-      return push ? march(sweep_chunk_kernel<RECON, 1, true, true, 0>, 1, true)
-                  : march(sweep_chunk_kernel<RECON, 1, true, false, 0>, 1, true);
+      return march(sweep_chunk_kernel<RECON, 1, true, 0>, 1, true);
     } else if (g.ndim == 3) {
       if (g32) {
-        if (int rc = march(sweep_chunk_kernel<RECON, 1, false, false, 32>, 1, false)) return rc;
-        return push ? march(sweep_chunk_kernel<RECON, 2, true, true, 32>, 2, true)
-                    : march(sweep_chunk_kernel<RECON, 2, true, false, 32>, 2, true);
+        if (int rc = march(sweep_chunk_kernel<RECON, 1, false, 32>, 1, false)) return rc;
+        return march(sweep_chunk_kernel<RECON, 2, true, 32>, 2, true);
       }
-      if (int rc = march(sweep_chunk_kernel<RECON, 1, false, false, 0>, 1, false)) return rc;
-      return push ? march(sweep_chunk_kernel<RECON, 2, true, true, 0>, 2, true)
-                  : march(sweep_chunk_kernel<RECON, 2, true, false, 0>, 2, true);
+      if (int rc = march(sweep_chunk_kernel<RECON, 1, false, 0>, 1, false)) return rc;
+      return march(sweep_chunk_kernel<RECON, 2, true, 0>, 2, true);
     }
     return PB2_OK;
   }

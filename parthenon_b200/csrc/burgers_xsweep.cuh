@@ -13,6 +13,8 @@
 // face_pq); the components then run one after the other with the next component's stencil
 // loads in flight.  Cells 2p-2 and 2p-1 are complete once faces 2p-1 and 2p are known:
 //   out = beta u + (1 - beta) base - (beta dt / dx1) (F(i+1) - F(i))      (update.hpp:43-137)
+// With Args::nbr the stencil values beyond the row's ends come from the interior cells of the
+// x neighbours instead of the block's own ghost cells (see burgers_march.cuh, "Ghost rows").
 #pragma once
 
 namespace pb2 {
@@ -55,22 +57,53 @@ struct PairStencil<PB2_RECON_LINEAR> {
   __device__ __forceinline__ double u1() const { return q[1]; }
 };
 
+// Element offsets that move a load from the block's own cells to the x neighbour's when the
+// cells it fetches lie beyond the row's ends: four load groups of a pair whose first cell is c0
+// (cells c0-2 | c0-1, c0 | c0+1, c0+2 | c0+3; c0 is odd, so a group never straddles an end).
+struct PairShift {
+  long long o[4];
+};
+template <int RECON>
+__device__ __forceinline__ PairShift pair_shift(const int c0, const int nx, const long long dlo,
+                                                const long long dhi) {
+  PairShift s;
+  if (RECON == PB2_RECON_WENO5) {
+    s.o[0] = c0 - 2 < 0 ? dlo : 0;
+    s.o[1] = c0 < 0 ? dlo : 0;      // cells c0-1, c0 (c0 = -1: both below the row)
+    s.o[2] = c0 + 1 >= nx ? dhi : 0; // cells c0+1, c0+2
+    s.o[3] = c0 + 3 >= nx ? dhi : 0;
+  } else { // cells c0-1 | c0 | c0+1 | c0+2
+    s.o[0] = c0 - 1 < 0 ? dlo : 0;
+    s.o[1] = c0 < 0 ? dlo : 0;
+    s.o[2] = c0 + 1 >= nx ? dhi : 0;
+    s.o[3] = c0 + 2 >= nx ? dhi : 0;
+  }
+  return s;
+}
+
 template <int RECON, int GEO>
-__device__ __forceinline__ void load_pair(PairStencil<RECON> &s, const double *__restrict__ p) {
+__device__ __forceinline__ void load_pair(PairStencil<RECON> &s, const double *__restrict__ p,
+                                          const PairShift &sh) {
   // p -> cell c0 of the pair (odd element index when the ghost width is even)
-  if (GEO == 32 && RECON == PB2_RECON_WENO5) {
-    // c0 - 1 is 16-byte aligned: (c0-1, c0) and (c0+1, c0+2) as vectors
-    s.q[0] = __ldg(p - 2);
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(p - 1));
-    const double2 b = __ldg(reinterpret_cast<const double2 *>(p + 1));
-    s.q[1] = a.x;
-    s.q[2] = a.y;
-    s.q[3] = b.x;
-    s.q[4] = b.y;
-    s.q[5] = __ldg(p + 3);
+  if (RECON == PB2_RECON_WENO5) {
+    s.q[0] = __ldg(p + sh.o[0] - 2);
+    if (GEO == 32) { // c0 - 1 is 16-byte aligned: (c0-1, c0) and (c0+1, c0+2) as vectors
+      const double2 a = __ldg(reinterpret_cast<const double2 *>(p + sh.o[1] - 1));
+      const double2 b = __ldg(reinterpret_cast<const double2 *>(p + sh.o[2] + 1));
+      s.q[1] = a.x;
+      s.q[2] = a.y;
+      s.q[3] = b.x;
+      s.q[4] = b.y;
+    } else {
+      s.q[1] = __ldg(p + sh.o[1] - 1);
+      s.q[2] = __ldg(p + sh.o[1]);
+      s.q[3] = __ldg(p + sh.o[2] + 1);
+      s.q[4] = __ldg(p + sh.o[2] + 2);
+    }
+    s.q[5] = __ldg(p + sh.o[3] + 3);
   } else {
 #pragma unroll
-    for (int t = 0; t < PairStencil<RECON>::kN; ++t) s.q[t] = __ldg(p + PairStencil<RECON>::kLo + t);
+    for (int t = 0; t < 4; ++t) s.q[t] = __ldg(p + sh.o[t] - 1 + t);
   }
 }
 
@@ -102,6 +135,12 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
     const double cdir = -a.bdt * idx0;
     const bool use_base = a.w2 != 0.0;
     const int src = (lane + 31) & 31;
+    long long dlo = 0, dhi = 0; // to the x neighbours' interiors, or 0: own ghost cells
+    if (a.nbr) {
+      const int nlo = a.nbr[b * 27 + face_slot(0, 0)], nhi = a.nbr[b * 27 + face_slot(0, 1)];
+      if (nlo >= 0) dlo = (long long)(nlo - b) * a.g.sb + G.nx(0);
+      if (nhi >= 0) dhi = (long long)(nhi - b) * a.g.sb - G.nx(0);
+    }
     if (lane < kMaxComp) {
       sL[wid][lane] = 0.0;
       sF[wid][lane] = 0.0;
@@ -164,10 +203,11 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
       PairStencil<RECON> cur, nxt;
       double P0, Q0, P1, Q1;
       double sq0 = 0.0, sq1 = 0.0; // LAST (1-D meshes): sum of squared velocities, cells 2p-2 / 2p-1
-      load_pair<RECON, GEO>(cur, ub + off);
+      const PairShift sh = pair_shift<RECON>(2 * p - 1, G.nx(0), dlo, dhi);
+      load_pair<RECON, GEO>(cur, ub + off, sh);
 #pragma unroll 2
       for (int n = 0; n < nc; ++n) {
-        if (n + 1 < nc) load_pair<RECON, GEO>(nxt, ub + (n + 1) * sc + off);
+        if (n + 1 < nc) load_pair<RECON, GEO>(nxt, ub + (n + 1) * sc + off, sh);
         double b0 = 0.0, b1 = 0.0;
         if (ldb) {
           if (GEO == 32) {

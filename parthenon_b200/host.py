@@ -26,6 +26,7 @@ SYMBOLS = [
     "pb2h_sim_exchange_elements", "pb2h_sim_history", "pb2h_sim_upload_interior",
     "pb2h_sim_download_interior", "pb2h_sim_prefetch_interior", "pb2h_sim_commit_interior",
     "pb2h_sim_writeback_interior", "pb2h_sim_lane_sync",
+    "pb2h_sim_sparse_pack", "pb2h_sim_sparse_pack_label", "pb2h_sim_set_sparse_allocation",
 ]
 
 BURGERS_DECK = """
@@ -223,6 +224,12 @@ def lib():
     L.pb2h_sim_exchange_elements.restype = i64
     L.pb2h_sim_exchange_elements.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
     L.pb2h_sim_history.argtypes = [vp, dp]
+    L.pb2h_sim_sparse_pack.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, vp,
+                                       C.POINTER(C.c_int32), i64]
+    L.pb2h_sim_sparse_pack_label.restype = C.c_char_p
+    L.pb2h_sim_sparse_pack_label.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
+                                             C.c_int, C.c_int]
+    L.pb2h_sim_set_sparse_allocation.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -248,6 +255,17 @@ def _leaves(leaves):
 
 
 FIELD_DATA, FIELD_FLUX1, FIELD_FLUX2, FIELD_FLUX3, FIELD_COARSE = 0, 1, 2, 3, 4
+
+
+class SparsePackPOD(C.Structure):
+    """pb2_sparse_pack of include/parthenon_b200_pack.h"""
+    _fields_ = [("ptr", C.c_void_p), ("bounds", C.c_void_p), ("coords", C.c_void_p),
+                ("nblocks", C.c_int32), ("nblocks_md", C.c_int32), ("maxvars", C.c_int32),
+                ("nvar", C.c_int32), ("size", C.c_int32), ("flat", C.c_int32),
+                ("with_fluxes", C.c_int32), ("coarse", C.c_int32),
+                ("ni", C.c_int32), ("nj", C.c_int32), ("nk", C.c_int32),
+                ("is_", C.c_int32), ("ie", C.c_int32), ("js", C.c_int32), ("je", C.c_int32),
+                ("ks", C.c_int32), ("ke", C.c_int32)]
 
 
 class _Base:
@@ -453,6 +471,32 @@ class Simulation(_Base):
         a = np.ascontiguousarray(array, dtype=np.float64)
         check(lib().pb2h_sim_set_field(self.h, container.encode(), field.encode(), which,
                                        a.ctypes.data, a.size))
+
+    def sparse_pack(self, container, names, flags=(), with_fluxes=False, coarse=False,
+                    flatten=False):
+        """parthenon::MakePackDescriptor(...).GetPack(container) -> (POD a kernel takes by value,
+        host bounds [2][nblocks][nvar+1]).  names: variable / sparse-pool names ("re:<regex>" for a
+        regular expression), flags: Metadata flag names"""
+        pod = SparsePackPOD()
+        opt = int(with_fluxes) | 2 * int(coarse) | 4 * int(flatten)
+        nb = self.info()["nblocks"]
+        bounds = np.zeros(2 * max(nb, 1) * (len(names) + 1), dtype=np.int32)
+        check(lib().pb2h_sim_sparse_pack(self.h, container.encode(), "\n".join(names).encode(),
+                                         "\n".join(flags).encode(), opt, C.byref(pod),
+                                         bounds.ctypes.data_as(C.POINTER(C.c_int32)), bounds.size))
+        n = 2 * pod.nblocks_md * (pod.nvar + 1)
+        return pod, bounds[:n].reshape(2, pod.nblocks_md, pod.nvar + 1)
+
+    def sparse_pack_label(self, container, names, b, idx, flags=(), with_fluxes=False,
+                          flatten=False):
+        opt = int(with_fluxes) | 4 * int(flatten)
+        lib().pb2h_sim_sparse_pack_label.restype = C.c_char_p
+        return lib().pb2h_sim_sparse_pack_label(self.h, container.encode(),
+                                                "\n".join(names).encode(),
+                                                "\n".join(flags).encode(), opt, b, idx).decode()
+
+    def set_sparse_allocation(self, field, lid, allocated):
+        check(lib().pb2h_sim_set_sparse_allocation(self.h, field.encode(), lid, int(allocated)))
 
     def interior_size(self, container, field):
         shape = self.field_shape(container, field)

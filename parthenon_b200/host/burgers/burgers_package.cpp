@@ -68,9 +68,10 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
   cfg.math = math == "strict" ? PB2_MATH_STRICT : PB2_MATH_FAST;
   pkg->AddParam("kernel_config", cfg);
   pkg->AddParam("fused_stage", pin->GetOrAddBoolean("pb2", "fused_stage", true));
-  // fast fused stage on a uniform mesh: the last direction sweep stores the same-device ghost
-  // cells itself (pb2_burgers_args::push_nbr) instead of a ghost-exchange pass after the stage
-  pkg->AddParam("ghost_push", pin->GetOrAddBoolean("pb2", "ghost_push", true));
+  // fast fused stage on a uniform mesh: the sweeps read same-device neighbours directly
+  // (pb2_burgers_args::nbr_direct) and the same-device ghost exchange leaves the cycle; ghost
+  // cells are refreshed when something else reads them
+  pkg->AddParam("lazy_ghosts", pin->GetOrAddBoolean("pb2", "lazy_ghosts", true));
 
   const int num_scalars = pin->GetOrAddInteger("burgers", "num_scalars", 1);
   pkg->AddParam("num_scalars", num_scalars);
@@ -110,6 +111,7 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
 }
 
 TaskStatus CalculateFluxes(MeshData<Real> *md) {
+  EnsureLocalGhosts(md);
   Variable &u = md->Get("U");
   pb2_burgers_args a = MakeArgs(md, u);
   for (int d = 0; d < a.geom.ndim; ++d) a.flux[d] = u.flux(d + 1);
@@ -169,12 +171,21 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   BvarsCache &bc = GetBvarsCache(mc1);
   const bool split = a.math == PB2_MATH_FAST && !pm->multilevel && bc.n_boundary > 0 &&
                      bc.n_interior > 0 && bc.plan.send_elements > 0;
-  if (a.math == PB2_MATH_FAST && !flxcor && bc.uniform_halo && bc.vars.size() == 1 &&
-      bc.vars[0] == &mc1->Get("U") && a.geom.ndim >= 2 && pkg->Param<bool>("ghost_push") &&
-      std::min({a.geom.nx[0], a.geom.nx[1], a.geom.ndim > 2 ? a.geom.nx[2] : a.geom.nx[1]}) >=
-          2 * a.geom.ng) {
-    a.push_nbr = bc.halo_nbr.get<int32_t>();
-    bc.ghosts_pushed = true;
+  // Ghost cells across same-device faces: the fast sweeps read the neighbour's interior instead
+  // (pb2_burgers_args::nbr_direct), so neither the input's local ghosts need to be current nor
+  // do the output's have to be filled before the next stage — the local exchange of mc1 is
+  // deferred until something else reads its ghost cells (EnsureLocalGhosts).
+  BvarsCache &bc0 = GetBvarsCache(mc0);
+  const bool direct = a.math == PB2_MATH_FAST && !flxcor && !pm->multilevel &&
+                      pkg->Param<bool>("lazy_ghosts") && bc0.uniform_halo && bc.uniform_halo &&
+                      bc0.vars.size() == 1 && bc0.vars[0] == &u && bc.vars.size() == 1 &&
+                      bc.vars[0] == &mc1->Get("U");
+  if (direct) {
+    a.nbr_direct = bc0.halo_nbr.get<int32_t>();
+    bc.defer_local = true;
+  } else {
+    EnsureLocalGhosts(mc0);
+    if (mbase != mc0) EnsureLocalGhosts(mbase);
   }
   if (flxcor) {
     // CalculateFluxes -> flux correction -> FluxDivergence + update (burgers_driver.cpp:92-104).

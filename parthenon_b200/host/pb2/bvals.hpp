@@ -127,9 +127,12 @@ struct BvarsCache {
   // one descriptor-free launch per field pulls every ghost cell from the owning neighbour
   // (pb2_halo_copy_uniform); halo_nbr is [nblocks][27] on the device
   bool uniform_halo = false;
-  // the producer of this container's data already stored the same-device ghosts (the last sweep
-  // of the fused burgers stage, pb2_burgers_args::push_nbr): SetBounds<local> has nothing to copy
-  bool ghosts_pushed = false;
+  // Lazy same-device ghosts.  A consumer that reads its neighbours' interiors directly (the fast
+  // burgers stage, pb2_burgers_args::nbr_direct) does not need the same-device ghost cells of
+  // its input: the producer of this container sets `defer_local`, the next SetBounds<local>
+  // then skips its copy and leaves `local_ghosts_stale` set.  Anything else that reads ghost
+  // cells calls EnsureLocalGhosts first (host field access, outputs, the bit-exact stage ...).
+  bool defer_local = false, local_ghosts_stale = false;
   DeviceBuffer halo_nbr;
   pb2_bnd_table *pack = nullptr, *unpack = nullptr;
   // [0]: regions whose neighbour is local, [1]: nonlocal
@@ -236,6 +239,11 @@ void FluxCorrection(MeshData<Real> *md);
 // the MD forms.
 TaskStatus ApplyBoundaryConditions(std::shared_ptr<MeshBlockData<Real>> &rc);
 TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md);
+// run the deferred same-device ghost copy of md (and the physical boundary fill that follows an
+// exchange) if its ghost cells are stale; no-op otherwise
+void EnsureLocalGhosts(MeshData<Real> *md);
+// ... of every container of the mesh
+void EnsureLocalGhosts(Mesh *pm);
 TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &md,
                                                    bool coarse);
 

@@ -23,6 +23,7 @@
 namespace parthenon {
 
 struct BvarsCache; // ghost-exchange tables of one MeshData (bvals.hpp)
+struct SparsePackStorage; // device tables of one resolved SparsePack (sparse_pack.hpp)
 
 // One field over every block of a MeshData batch.
 class Variable {
@@ -151,6 +152,10 @@ class MeshData {
   }
 
   BvarsCache &bvars() { return *bvars_; }
+  // resolved SparsePacks by descriptor identifier (MeshData::GetSparsePackCache)
+  std::map<std::string, std::shared_ptr<SparsePackStorage>> &GetSparsePackCache() {
+    return sparse_pack_cache_;
+  }
   // bumped whenever an allocation status changes; the exchange tables are rebuilt when
   // their generation differs (replaces the per-call host walk of
   // CheckSendBufferCacheForRebuild, bvals_utils.hpp:140-202)
@@ -165,6 +170,7 @@ class MeshData {
   std::vector<std::shared_ptr<Variable>> order_;
   std::map<std::string, std::unique_ptr<VariablePack>> pack_cache_;
   DeviceBuffer dx_, xmin_, dt_cell_;
+  std::map<std::string, std::shared_ptr<SparsePackStorage>> sparse_pack_cache_;
   std::unique_ptr<BvarsCache> bvars_;
 };
 

@@ -713,13 +713,17 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
   Mesh *pm = md->GetMeshPointer();
   pb2_stream_t st = md->stream();
   if (DoesLocal(bt)) {
-    if (c.uniform_halo && c.ghosts_pushed) {
-      c.ghosts_pushed = false; // this exchange's copies were the producer's own stores
+    if (c.uniform_halo && c.defer_local) {
+      // the consumer reads its neighbours' interiors: the copy happens only if someone else
+      // asks for these ghost cells (EnsureLocalGhosts)
+      c.defer_local = false;
+      c.local_ghosts_stale = true;
     } else if (c.uniform_halo) {
       for (Variable *v : c.vars) {
         const pb2_pack_geom g = md->Geometry(*v);
         PB2_CHECK(pb2_halo_copy_uniform(&g, v->data(), c.halo_nbr.get<int32_t>(), st));
       }
+      c.local_ghosts_stale = false;
     } else if (c.sparse) {
       // (Cache() above rebuilt the tables if ReceiveBoundBufs allocated anything; the flags
       // are indexed by channel, which allocation does not change)
@@ -1046,6 +1050,26 @@ TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real
 }
 TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md) {
   return ApplyBoundaryConditionsOnCoarseOrFineMD(md, false);
+}
+
+void EnsureLocalGhosts(MeshData<Real> *md) {
+  BvarsCache &c = md->bvars();
+  if (!c.local_ghosts_stale) return;
+  PARTHENON_REQUIRE(c.uniform_halo, "stale ghosts on a container without the uniform ghost fill");
+  for (Variable *v : c.vars) {
+    const pb2_pack_geom g = md->Geometry(*v);
+    PB2_CHECK(pb2_halo_copy_uniform(&g, v->data(), c.halo_nbr.get<int32_t>(), md->stream()));
+  }
+  c.local_ghosts_stale = false;
+  // physical boundaries copy from cells the exchange fills (edges and corners next to a
+  // neighbour): same order as after every exchange
+  Mesh *pm = md->GetMeshPointer();
+  auto &sp = pm->mesh_data.GetOrAdd(md->label(), md->partition_id());
+  ApplyBoundaryConditionsOnCoarseOrFineMD(sp, false);
+}
+
+void EnsureLocalGhosts(Mesh *pm) {
+  for (auto &kv : pm->mesh_data.All()) EnsureLocalGhosts(kv.second.get());
 }
 
 TaskID AddBoundaryExchangeTasks(TaskID dependency, TaskList &tl,

@@ -14,6 +14,7 @@
 #include "../burgers/burgers_package.hpp"
 #include "../tecomm/tecomm_app.hpp"
 #include "parthenon_b200_host.h"
+#include "pb2/sparse_pack.hpp"
 #include "pb2/parthenon.hpp"
 
 using namespace parthenon;
@@ -412,7 +413,9 @@ int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t 
 static Variable &FindVar(pb2h_sim *sim, const char *container, const char *field) {
   PARTHENON_REQUIRE(sim->pm()->DefaultNumPartitions() == 1,
                     "field access through the C interface needs pack_size = -1");
-  return sim->pm()->mesh_data.GetOrAdd(container, 0)->Get(field);
+  auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+  EnsureLocalGhosts(md.get()); // whoever looks at a field sees current ghost cells
+  return md->Get(field);
 }
 
 int pb2h_sim_field_ptr(pb2h_sim *sim, const char *container, const char *field, int which,
@@ -639,6 +642,84 @@ int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t
     total = p.local_elements + p.recv_elements;
   });
   return total;
+}
+
+namespace {
+MetadataFlag FlagByName(const std::string &n) {
+  static const std::map<std::string, MetadataFlag> m = {
+      {"Cell", Metadata::Cell}, {"Face", Metadata::Face}, {"Edge", Metadata::Edge},
+      {"Node", Metadata::Node}, {"Independent", Metadata::Independent},
+      {"Derived", Metadata::Derived}, {"OneCopy", Metadata::OneCopy},
+      {"FillGhost", Metadata::FillGhost}, {"WithFluxes", Metadata::WithFluxes},
+      {"Sparse", Metadata::Sparse}, {"Vector", Metadata::Vector},
+      {"Conserved", Metadata::Conserved}, {"Intensive", Metadata::Intensive}};
+  auto it = m.find(n);
+  PARTHENON_REQUIRE(it != m.end(), "unknown Metadata flag " + n);
+  return it->second;
+}
+SparsePack MakePack(pb2h_sim *sim, const char *container, const char *names, const char *flags,
+                    int options) {
+  PARTHENON_REQUIRE(sim->pm()->DefaultNumPartitions() == 1,
+                    "packs through the C interface need pack_size = -1");
+  auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+  EnsureLocalGhosts(md.get());
+  std::vector<std::string> vars;
+  std::vector<bool> regex;
+  for (const std::string &n : SplitLines(names)) {
+    const bool re = n.compare(0, 3, "re:") == 0;
+    vars.push_back(re ? n.substr(3) : n);
+    regex.push_back(re);
+  }
+  std::vector<MetadataFlag> fl;
+  for (const std::string &f : SplitLines(flags)) fl.push_back(FlagByName(f));
+  std::set<PDOpt> opt;
+  if (options & 1) opt.insert(PDOpt::WithFluxes);
+  if (options & 2) opt.insert(PDOpt::Coarse);
+  if (options & 4) opt.insert(PDOpt::Flatten);
+  std::vector<const StateDescriptor *> pk;
+  const Packages_t &packages = sim->pm()->packages;
+  for (const std::string &name : packages.Order()) pk.push_back(packages.Get(name).get());
+  return MakePackDescriptor(pk, vars, regex, fl, opt).GetPack(md.get());
+}
+} // namespace
+
+int pb2h_sim_sparse_pack(pb2h_sim *sim, const char *container, const char *names,
+                         const char *flags, int options, pb2_sparse_pack *pack,
+                         int32_t *host_bounds, int64_t host_bounds_len) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(pack != nullptr, "null pack");
+    SparsePack p = MakePack(sim, container, names, flags, options);
+    *pack = p.pod();
+    if (host_bounds) {
+      const int64_t n = 2ll * pack->nblocks_md * (pack->nvar + 1);
+      PARTHENON_REQUIRE(host_bounds_len >= n, "bounds buffer too small");
+      for (int w = 0; w < 2; ++w)
+        for (int b = 0; b < pack->nblocks_md; ++b) {
+          for (int v = 0; v < pack->nvar; ++v)
+            host_bounds[(static_cast<int64_t>(w) * pack->nblocks_md + b) * (pack->nvar + 1) + v] =
+                w == 0 ? p.GetLowerBoundHost(b, PackIdx(v)) : p.GetUpperBoundHost(b, PackIdx(v));
+          host_bounds[(static_cast<int64_t>(w) * pack->nblocks_md + b) * (pack->nvar + 1) +
+                      pack->nvar] = w == 0 ? p.GetLowerBoundHost(b) : p.GetUpperBoundHost(b);
+        }
+    }
+  });
+}
+
+const char *pb2h_sim_sparse_pack_label(pb2h_sim *sim, const char *container, const char *names,
+                                       const char *flags, int options, int b, int idx) {
+  static std::string label;
+  label.clear();
+  Guard([&] { label = MakePack(sim, container, names, flags, options).LabelHost(b, idx); });
+  return label.c_str();
+}
+
+int pb2h_sim_set_sparse_allocation(pb2h_sim *sim, const char *field, int lid, int allocated) {
+  return Guard([&] {
+    if (allocated)
+      sim->pm()->AllocateSparse(field, lid);
+    else
+      sim->pm()->DeallocateSparse(field, lid);
+  });
 }
 
 int pb2h_sim_history(pb2h_sim *sim, double out[8]) {

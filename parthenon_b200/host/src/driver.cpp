@@ -1,6 +1,8 @@
 // driver.cpp — evolution loop and integrator tables (see pb2/driver.hpp).
 #include "pb2/driver.hpp"
 
+#include "pb2/bvals.hpp"
+
 #include <algorithm>
 #include <cstdio>
 #include <iostream>
@@ -241,6 +243,7 @@ DriverStatus EvolutionDriver::Execute() {
       return DriverStatus::failed;
     }
   }
+  EnsureLocalGhosts(pmesh); // deferred same-device ghost copies, before anyone looks
   PB2_CHECK(pb2_stream_sync(pmesh->stream));
   const double zcps = ZoneCyclesPerSecond();
   if (app_input && app_input->UserWorkAfterLoop) app_input->UserWorkAfterLoop(pmesh, pinput, tm);

@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, GPU session B: cp.async-staged march kernels with inline ghost push
+# round 2, GPU session E: new WENO algebra; full suite; full bench line
 set -u
-OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r02b}
-timeout 600 python -m pytest tests/test_cabi_kernels_gpu.py tests/test_burgers_sim_gpu.py -m gpu -x -q 2>&1 | tail -25 > $OUT/pytest_${TAG}_new.log
-tail -6 $OUT/pytest_${TAG}_new.log
+OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r02e}
+timeout 600 python -m pytest tests/test_cabi_kernels_gpu.py tests/test_burgers_sim_gpu.py tests/test_sparse_pack_gpu.py -m gpu -x -q 2>&1 | tail -25 > $OUT/pytest_${TAG}_new.log
+tail -8 $OUT/pytest_${TAG}_new.log
 run() { # name, extra bench args
   local v=$1; shift
   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-parity "$@" > $OUT/bench_${TAG}_$v.json 2> $OUT/bench_${TAG}_$v.err
@@ -19,12 +19,22 @@ except Exception as e:
 PY
 }
 run lazy
-run eager --set pb2/lazy_ghosts=false
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'sweep_xpair|sweep_chunk' -s 12 -c 3 \
   -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $OUT/ncu_full_$TAG.log 2>&1
 tail -1 $OUT/ncu_full_$TAG.log
-for v in "-DPB2_CHUNK=6 -DPB2_CHUNK_MINB=3" "-DPB2_CHUNK=5" ; do
+for v in "-DPB2_CHUNK=6 -DPB2_CHUNK_MINB=3" "-DPB2_XPAIR_MINB=3"; do
   rm -f parthenon_b200/csrc/burgers_sweep.o
   make -C parthenon_b200/csrc -s -j8 EXTRA="$v" > /dev/null 2>&1 || { echo build failed $v; continue; }
   run "var$(echo $v | tr -c 'A-Za-z0-9\n' '_')"
 done
+rm -f parthenon_b200/csrc/burgers_sweep.o; make -C parthenon_b200/csrc -s -j8 > /dev/null 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $OUT/pytest_$TAG.log
+tail -4 $OUT/pytest_$TAG.log
+timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+python - <<PY
+import json
+d=json.loads(open("$OUT/bench_$TAG.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step","parity","cpu_baseline","clocks")})
+print("e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "roofline", d["roofline"])
+PY
+tail -3 $OUT/bench_$TAG.err

@@ -243,7 +243,7 @@ def test_multilevel_fast_cycles_within_tolerance(name, nx_mesh, nx_block, ndim):
 
 def test_benchmark_kernels_elementwise_vs_strict_25_cycles():
     """The instantiations bench.py times (pb2/math = fast, 11 components, 32^3 blocks: compile-time
-    geometry, ghosts pushed by the last sweep) on a 128^3 mesh over the benchmark's 25 cycles,
+    geometry, neighbours read directly) on a 128^3 mesh over the benchmark's 25 cycles,
     element by element against the same run with pb2/math = strict — which is bit-exact to the
     reference (test_strict_cycles_bit_exact_vs_reference_dumps).  Tolerance: per element
     |fast - strict| <= 1e-12 * max(|strict|, floor) with floor = 1e-3 of the component's largest
@@ -270,26 +270,47 @@ def test_benchmark_kernels_elementwise_vs_strict_25_cycles():
     assert abs(runs["fast"][2] - runs["strict"][2]) <= TOL * runs["strict"][2]
 
 
-@pytest.mark.parametrize("push", ["true", "false"])
-def test_ghost_push_matches_exchange_pass(push):
-    """fast stage with the ghosts stored by the last sweep (default) against pb2/ghost_push =
-    false (ghost-exchange kernel after the stage): identical bits after several cycles, also on
-    the slab path forced by virtual ranks (pushed ghosts and unpacked ghosts are disjoint)"""
-    ref = host.Simulation(overrides=burgers_overrides(8, 4, 4, 8, "weno5", "fast", True,
-                                                      {"pb2/ghost_push": "false"}))
+@pytest.mark.parametrize("nx,nrb", [(8, 4), (32, 2)])
+def test_lazy_local_ghosts_match_exchange_every_stage(nx, nrb):
+    """fast stage reading same-device neighbours directly, local ghost exchange deferred until
+    someone looks (default), against pb2/lazy_ghosts = false (ghost-exchange kernel after every
+    stage): identical bits after several cycles — ghost cells included, they are refreshed when
+    the field is read — also on the slab path forced by virtual ranks (faces to "other ranks"
+    keep their unpacked ghost cells)"""
+    ref = host.Simulation(overrides=burgers_overrides(nx, nrb, 4, 8, "weno5", "fast", True,
+                                                      {"pb2/lazy_ghosts": "false"}))
     ref.pre_execute()
     ref.cycle(4)
     want = ref.get_field("base", "U")
     for extra in ({}, {"pb2/virtual_ranks": 3}):
-        extra = dict(extra)
-        extra["pb2/ghost_push"] = push
-        sim = host.Simulation(overrides=burgers_overrides(8, 4, 4, 8, "weno5", "fast", True, extra))
+        sim = host.Simulation(overrides=burgers_overrides(nx, nrb, 4, 8, "weno5", "fast", True, extra))
         sim.pre_execute()
-        sim.cycle(4)
+        sim.cycle(2)
+        mid = sim.get_field("base", "U")  # a flush in the middle must not disturb the run
+        assert np.all(np.isfinite(mid))
+        sim.cycle(2)
         assert np.array_equal(sim.get_field("base", "U"), want), extra
         assert sim.dt == ref.dt and sim.time == ref.time
         sim.close()
     ref.close()
+
+
+def test_lazy_local_ghosts_with_physical_boundaries():
+    """outflow x1 / reflecting x2 / periodic x3: faces on a physical boundary keep reading the
+    block's own ghost cells (filled by the boundary kernel every stage), the others read their
+    neighbours; the deferred copy re-applies the boundary fill so edges and corners agree too"""
+    bc = {"parthenon/mesh/ix1_bc": "outflow", "parthenon/mesh/ox1_bc": "outflow",
+          "parthenon/mesh/ix2_bc": "reflecting", "parthenon/mesh/ox2_bc": "reflecting"}
+    outs = []
+    for lazy in ("false", "true"):
+        ov = burgers_overrides(8, 2, 4, 8, "weno5", "fast", True, dict(bc))
+        ov["pb2/lazy_ghosts"] = lazy
+        sim = host.Simulation(overrides=ov)
+        sim.pre_execute()
+        sim.cycle(3)
+        outs.append(sim.get_field("base", "U"))
+        sim.close()
+    assert np.array_equal(outs[0], outs[1])
 
 
 def test_full_block_shape_conservation_and_idempotence():
