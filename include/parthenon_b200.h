@@ -45,6 +45,10 @@ int pb2_set_device(int device);
 int pb2_device_sm_count(int *count);
 int pb2_malloc(void **ptr, size_t bytes);
 int pb2_free(void *ptr);
+/* pb2_malloc recycles large allocations through an exact-size cache per device (adaptive runs
+ * re-create multi-GB slabs on every remesh); this returns everything it holds to the driver.
+ * PB2_ALLOC_CACHE_GB (default 48) bounds what the cache may keep. */
+int pb2_cache_trim(void);
 int pb2_host_alloc(void **ptr, size_t bytes); /* pinned */
 int pb2_host_free(void *ptr);
 int pb2_memset(void *ptr, int value, size_t bytes, pb2_stream_t stream);
@@ -448,6 +452,8 @@ int pb2_comm_exchange(pb2_comm *comm, const double *send_slab, const int64_t *se
 int pb2_comm_allreduce_min(pb2_comm *comm, double *dev_value, pb2_stream_t stream);
 /* in-place sum all-reduce of n doubles (history reductions, MPI_Reduce in outputs/history.cpp) */
 int pb2_comm_allreduce_sum(pb2_comm *comm, double *dev_values, int64_t n, pb2_stream_t stream);
+/* all ranks: returns once everything every rank enqueued on `stream` before the call has
+ * completed (an all-reduce followed by a stream synchronisation) */
 int pb2_comm_barrier(pb2_comm *comm, pb2_stream_t stream);
 
 #ifdef __cplusplus

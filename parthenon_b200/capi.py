@@ -86,7 +86,7 @@ _lib = None
 # every symbol include/parthenon_b200.h declares
 SYMBOLS = [
     "pb2_version", "pb2_last_error", "pb2_device_count", "pb2_set_device",
-    "pb2_device_sm_count", "pb2_malloc", "pb2_free", "pb2_host_alloc", "pb2_host_free",
+    "pb2_device_sm_count", "pb2_malloc", "pb2_free", "pb2_cache_trim", "pb2_host_alloc", "pb2_host_free",
     "pb2_memset", "pb2_memcpy_h2d", "pb2_memcpy_d2h", "pb2_memcpy_d2d", "pb2_stream_create",
     "pb2_stream_destroy", "pb2_stream_sync", "pb2_device_sync", "pb2_event_create",
     "pb2_event_destroy", "pb2_event_record", "pb2_event_sync", "pb2_event_query",

@@ -88,6 +88,7 @@ static int load_nccl() {
 struct pb2_comm {
   pb2::ncclComm_p comm;
   int rank, nranks;
+  double *barrier_scratch = nullptr; // one device double of this communicator's device
 };
 
 using namespace pb2;
@@ -119,6 +120,7 @@ int pb2_comm_create(pb2_comm **comm, int rank, int nranks,
 int pb2_comm_destroy(pb2_comm *comm) {
   if (!comm) return PB2_OK;
   if (g_nccl.CommDestroy) g_nccl.CommDestroy(comm->comm);
+  if (comm->barrier_scratch) cudaFree(comm->barrier_scratch);
   delete comm;
   return PB2_OK;
 }
@@ -127,17 +129,27 @@ int pb2_comm_exchange(pb2_comm *comm, const double *send_slab, const int64_t *se
                       double *recv_slab, const int64_t *recv_off, pb2_stream_t stream) {
   PB2_REQUIRE(comm && send_off && recv_off, "bad arguments");
   PB2_NCCL_CHECK(g_nccl.GroupStart());
-  for (int p = 0; p < comm->nranks; ++p) {
+  // an error inside the group must still close it, or every later call on this thread hangs
+  int bad = 0;
+  const char *what = "";
+  for (int p = 0; p < comm->nranks && !bad; ++p) {
     if (p == comm->rank) continue;
     const int64_t ns = send_off[p + 1] - send_off[p], nr = recv_off[p + 1] - recv_off[p];
-    if (ns > 0)
-      PB2_NCCL_CHECK(g_nccl.Send(send_slab + send_off[p], static_cast<size_t>(ns),
-                                 kNcclFloat64, p, comm->comm, as_stream(stream)));
-    if (nr > 0)
-      PB2_NCCL_CHECK(g_nccl.Recv(recv_slab + recv_off[p], static_cast<size_t>(nr),
-                                 kNcclFloat64, p, comm->comm, as_stream(stream)));
+    if (ns > 0 && (bad = g_nccl.Send(send_slab + send_off[p], static_cast<size_t>(ns),
+                                     kNcclFloat64, p, comm->comm, as_stream(stream))) != 0)
+      what = "ncclSend";
+    if (!bad && nr > 0 &&
+        (bad = g_nccl.Recv(recv_slab + recv_off[p], static_cast<size_t>(nr), kNcclFloat64, p,
+                           comm->comm, as_stream(stream))) != 0)
+      what = "ncclRecv";
   }
-  PB2_NCCL_CHECK(g_nccl.GroupEnd());
+  const int end = g_nccl.GroupEnd();
+  if (bad || end) {
+    const int r = bad ? bad : end;
+    set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, bad ? what : "ncclGroupEnd",
+              g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return PB2_ERR_NCCL;
+  }
   return PB2_OK;
 }
 
@@ -158,13 +170,14 @@ int pb2_comm_allreduce_sum(pb2_comm *comm, double *dev_values, int64_t n, pb2_st
 
 int pb2_comm_barrier(pb2_comm *comm, pb2_stream_t stream) {
   PB2_REQUIRE(comm, "bad arguments");
-  static double *scratch = nullptr;
-  if (!scratch) {
-    PB2_CUDA_CHECK(cudaMalloc(&scratch, sizeof(double)));
-    PB2_CUDA_CHECK(cudaMemset(scratch, 0, sizeof(double)));
+  if (!comm->barrier_scratch) {
+    PB2_CUDA_CHECK(cudaMalloc(&comm->barrier_scratch, sizeof(double)));
+    PB2_CUDA_CHECK(cudaMemset(comm->barrier_scratch, 0, sizeof(double)));
   }
-  PB2_NCCL_CHECK(g_nccl.AllReduce(scratch, scratch, 1, kNcclFloat64, kNcclMin, comm->comm,
-                                  as_stream(stream)));
+  PB2_NCCL_CHECK(g_nccl.AllReduce(comm->barrier_scratch, comm->barrier_scratch, 1, kNcclFloat64,
+                                  kNcclMin, comm->comm, as_stream(stream)));
+  // a barrier for the HOST: every rank's work enqueued before it on `stream` has completed
+  PB2_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
   return PB2_OK;
 }
 

@@ -512,7 +512,7 @@ int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regi
 int pb2_restrict(const pb2_bnd_table *table, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "restrict needs a prores table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_RESTRICT, as_stream(stream));
+  ProfScope prof(K_RESTRICT, as_stream(stream), static_cast<double>(table->elements));
   restrict_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                     as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
@@ -523,7 +523,7 @@ int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
   PB2_REQUIRE(op >= 0 && op <= 2, "unknown prolongation operator");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  ProfScope prof(K_PROLONGATE, as_stream(stream), static_cast<double>(table->elements));
   prolongate_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                       as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
   PB2_LAUNCH_CHECK();
@@ -533,7 +533,7 @@ int pb2_prolongate(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
 int pb2_restrict_te(const pb2_bnd_table *table, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "restrict needs a prores table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_RESTRICT, as_stream(stream));
+  ProfScope prof(K_RESTRICT, as_stream(stream), static_cast<double>(table->elements));
   restrict_te_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                        as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
@@ -544,7 +544,7 @@ int pb2_prolongate_te(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
   PB2_REQUIRE(op >= 0 && op <= 2, "unknown prolongation operator");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  ProfScope prof(K_PROLONGATE, as_stream(stream), static_cast<double>(table->elements));
   prolongate_te_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                          as_stream(stream)>>>(table->d_prores, table->d_chunks, op);
   PB2_LAUNCH_CHECK();
@@ -554,7 +554,7 @@ int pb2_prolongate_te(const pb2_bnd_table *table, int op, pb2_stream_t stream) {
 int pb2_prolongate_internal(const pb2_bnd_table *table, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  ProfScope prof(K_PROLONGATE, as_stream(stream), static_cast<double>(table->elements));
   prolongate_internal_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                                as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
@@ -564,7 +564,7 @@ int pb2_prolongate_internal(const pb2_bnd_table *table, pb2_stream_t stream) {
 int pb2_prolongate_toth_roe(const pb2_bnd_table *table, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kProRes, "prolongate needs a prores table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_PROLONGATE, as_stream(stream));
+  ProfScope prof(K_PROLONGATE, as_stream(stream), static_cast<double>(table->elements));
   prolongate_toth_roe_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                                as_stream(stream)>>>(table->d_prores, table->d_chunks);
   PB2_LAUNCH_CHECK();
@@ -620,7 +620,7 @@ int pb2_flxcor_table_create(pb2_bnd_table **table, const pb2_flxcor_region *regi
 int pb2_flux_correct(const pb2_bnd_table *table, double *slab, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kFlxCor, "flux correction needs a flxcor table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_FLUX_CORRECT, as_stream(stream));
+  ProfScope prof(K_FLUX_CORRECT, as_stream(stream), static_cast<double>(table->elements));
   flux_correct_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0,
                         as_stream(stream)>>>(table->d_flxcor, table->d_chunks, slab);
   PB2_LAUNCH_CHECK();
@@ -680,7 +680,7 @@ int pb2_bc_table_create(pb2_bnd_table **table, const pb2_bc_region *regions, int
 int pb2_apply_bcs(const pb2_bnd_table *table, pb2_stream_t stream) {
   PB2_REQUIRE(table && table->kind == kBc, "apply_bcs needs a boundary-condition table");
   if (table->nchunks == 0) return PB2_OK;
-  ProfScope prof(K_APPLY_BC, as_stream(stream));
+  ProfScope prof(K_APPLY_BC, as_stream(stream), static_cast<double>(table->elements));
   apply_bc_kernel<<<static_cast<unsigned>(table->nchunks), kPrThreads, 0, as_stream(stream)>>>(
       table->d_bc, table->d_chunks);
   PB2_LAUNCH_CHECK();

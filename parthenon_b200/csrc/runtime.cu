@@ -5,6 +5,8 @@
 #include <map>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pb2 {
@@ -211,26 +213,53 @@ int pb2_device_sm_count(int *count) {
 // again.  The cache is bounded; beyond the bound memory really is returned.
 namespace {
 constexpr size_t kCacheMinBytes = size_t(1) << 20;
-constexpr size_t kCacheMaxBytes = size_t(48) << 30;
 constexpr size_t kCacheMaxEntries = 96;
+// upper bound of what the cache may hold back from other users of the device (torch, NCCL):
+// PB2_ALLOC_CACHE_GB, default 48
+size_t cache_max_bytes() {
+  static const size_t v = [] {
+    const char *e = std::getenv("PB2_ALLOC_CACHE_GB");
+    const double gb = e ? std::atof(e) : 48.0;
+    return static_cast<size_t>((gb < 0 ? 0 : gb) * double(size_t(1) << 30));
+  }();
+  return v;
+}
+struct Live {
+  size_t bytes;
+  int device;
+};
 std::mutex g_cache_mu;
-std::multimap<size_t, void *> g_cache;           // size -> free pointer
-std::unordered_map<void *, size_t> g_live_sizes; // every live pointer handed out by pb2_malloc
+std::multimap<std::pair<int, size_t>, void *> g_cache; // (device, size) -> free pointer
+std::unordered_map<void *, Live> g_live;               // every live pointer of pb2_malloc
 size_t g_cache_bytes = 0;
+
+void cache_release_all_locked() {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto &kv : g_cache) {
+    cudaSetDevice(kv.first.first);
+    cudaFree(kv.second);
+  }
+  cudaSetDevice(cur);
+  g_cache.clear();
+  g_cache_bytes = 0;
+}
 } // namespace
 
 int pb2_malloc(void **ptr, size_t bytes) {
   PB2_REQUIRE(ptr, "null argument");
   if (int rc = require_device()) return rc;
   if (bytes == 0) bytes = 1;
+  int dev = 0;
+  PB2_CUDA_CHECK(cudaGetDevice(&dev));
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    auto it = g_cache.find(bytes);
+    auto it = g_cache.find({dev, bytes});
     if (it != g_cache.end()) {
       *ptr = it->second;
       g_cache_bytes -= bytes;
       g_cache.erase(it);
-      g_live_sizes[*ptr] = bytes;
+      g_live[*ptr] = Live{bytes, dev};
       return PB2_OK;
     }
   }
@@ -238,37 +267,46 @@ int pb2_malloc(void **ptr, size_t bytes) {
   if (e == cudaErrorMemoryAllocation) { // give the cache back and try once more
     cudaGetLastError();
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (auto &kv : g_cache) cudaFree(kv.second);
-    g_cache.clear();
-    g_cache_bytes = 0;
+    cache_release_all_locked();
     e = cudaMalloc(ptr, bytes);
   }
   PB2_CUDA_CHECK(e);
   std::lock_guard<std::mutex> lk(g_cache_mu);
-  g_live_sizes[*ptr] = bytes;
+  g_live[*ptr] = Live{bytes, dev};
   return PB2_OK;
 }
 int pb2_free(void *ptr) {
   if (!ptr) return PB2_OK;
-  size_t bytes = 0;
+  Live live{0, -1};
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    auto it = g_live_sizes.find(ptr);
-    if (it != g_live_sizes.end()) {
-      bytes = it->second;
-      g_live_sizes.erase(it);
+    auto it = g_live.find(ptr);
+    if (it != g_live.end()) {
+      live = it->second;
+      g_live.erase(it);
     }
   }
-  if (bytes >= kCacheMinBytes) {
-    PB2_CUDA_CHECK(cudaDeviceSynchronize()); // what cudaFree would have waited for
+  if (live.bytes >= kCacheMinBytes && live.device >= 0) {
+    // what cudaFree would have waited for: the device that OWNS the pointer
+    int cur = 0;
+    PB2_CUDA_CHECK(cudaGetDevice(&cur));
+    if (cur != live.device) PB2_CUDA_CHECK(cudaSetDevice(live.device));
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (cur != live.device) cudaSetDevice(cur);
+    PB2_CUDA_CHECK(e);
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    if (g_cache_bytes + bytes <= kCacheMaxBytes && g_cache.size() < kCacheMaxEntries) {
-      g_cache.emplace(bytes, ptr);
-      g_cache_bytes += bytes;
+    if (g_cache_bytes + live.bytes <= cache_max_bytes() && g_cache.size() < kCacheMaxEntries) {
+      g_cache.emplace(std::make_pair(live.device, live.bytes), ptr);
+      g_cache_bytes += live.bytes;
       return PB2_OK;
     }
   }
   PB2_CUDA_CHECK(cudaFree(ptr));
+  return PB2_OK;
+}
+int pb2_cache_trim(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  cache_release_all_locked();
   return PB2_OK;
 }
 int pb2_host_alloc(void **ptr, size_t bytes) {

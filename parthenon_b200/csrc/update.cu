@@ -273,7 +273,7 @@ int pb2_weighted_sum(const double *x, const double *y, double w1, double w2, dou
   int64_t ctas = (n / 2 + 255) / 256;
   if (ctas > 148 * 16) ctas = 148 * 16;
   if (ctas < 1) ctas = 1;
-  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream), static_cast<double>(n));
   weighted_sum_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(x, y, w1, w2,
                                                                                  z, n);
   PB2_LAUNCH_CHECK();
@@ -307,7 +307,7 @@ int pb2_weighted_sum_ghosts_blocks(const pb2_pack_geom *pg, const double *x, con
   const int64_t total = (int64_t)g.nblocks * g.ncomp * g.sc;
   if (total == 0) return PB2_OK;
   const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
-  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream), static_cast<double>(total));
   weighted_sum_ghost_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, x, y, w1, w2, z, total,
                                                                  block_ids);
   PB2_LAUNCH_CHECK();
@@ -335,7 +335,7 @@ static int interior_copy(const pb2_pack_geom *pg, double *field, double *packed,
   const int64_t total = (int64_t)g.nblocks * g.ncomp * g.nx[0] * g.nx[1] * g.nx[2];
   if (total == 0) return PB2_OK;
   const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
-  ProfScope prof(K_INTERIOR, as_stream(stream));
+  ProfScope prof(K_INTERIOR, as_stream(stream), static_cast<double>(total));
   if (scatter)
     interior_kernel<true><<<ctas, 256, 0, as_stream(stream)>>>(g, field, packed, total);
   else
@@ -384,7 +384,7 @@ int pb2_advection_fluxes_blocks(const pb2_pack_geom *pg, const double *u, double
                         (g.nx[0] + 1) * (g.nx[1] + (g.ndim > 1)) * (g.nx[2] + (g.ndim > 2));
   if (total == 0) return PB2_OK;
   const unsigned ctas = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 32));
-  ProfScope prof(K_ADVECTION_FLUX, as_stream(stream));
+  ProfScope prof(K_ADVECTION_FLUX, as_stream(stream), static_cast<double>(total));
   advection_flux_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, u, flux[0], flux[1], flux[2],
                                                             v[0], v[1], v[2], total, block_mask,
                                                             pg->block_list);
@@ -406,8 +406,8 @@ int pb2_weighted_sum_blocks(const pb2_pack_geom *pg, const double *x, const doub
   int64_t per_block = pg->ncomp;
   for (int d = 0; d < 3; ++d) per_block *= d >= pg->ndim ? 1 : pg->nx[d] + 2 * pg->ng;
   const int cpb = static_cast<int>(std::min<int64_t>((per_block + 255) / 256, 64));
-  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream));
   const int nslots = pg->block_list ? pg->nlist : pg->nblocks;
+  ProfScope prof(K_WEIGHTED_SUM, as_stream(stream), static_cast<double>(per_block) * nslots);
   if (nslots == 0) return PB2_OK;
   weighted_sum_blocks_kernel<<<nslots * cpb, 256, 0, as_stream(stream)>>>(
       x, y, w1, w2, z, pg->block_stride, per_block, block_mask, cpb, pg->block_list);
@@ -495,7 +495,8 @@ int pb2_flux_divergence_blocks(const pb2_pack_geom *pg, const double *const flux
   const int ncell = g.nx[0] * g.nx[1] * g.nx[2];
   const int ctas = (pg->block_list ? pg->nlist : g.nblocks) * ((ncell + 255) / 256);
   if (ctas == 0) return PB2_OK;
-  ProfScope prof(K_FLUX_DIV, as_stream(stream));
+  ProfScope prof(K_FLUX_DIV, as_stream(stream), static_cast<double>(ncell) * g.ncomp *
+                                                    (pg->block_list ? pg->nlist : g.nblocks));
   flux_div_kernel<<<ctas, 256, 0, as_stream(stream)>>>(g, flux[0], flux[1], flux[2], pg->dx,
                                                       dudt, block_mask, pg->block_list);
   PB2_LAUNCH_CHECK();

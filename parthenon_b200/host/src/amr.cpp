@@ -657,13 +657,21 @@ TaskStatus Tag(MeshData<Real> *rc) {
     dev.Allocate(sizeof(Real) * nb, rc->stream());
     std::vector<Real> maxd(nb);
     for (const auto &c : pm->amr_criteria) {
-      if (!rc->HasVariable(c.field)) continue; // AmrTag::same: no vote beyond the default
+      if (!rc->HasVariable(c.field)) {
+        // amr_criteria.cpp:89-91: a block without the field votes "same" (not "derefine")
+        for (int b = 0; b < nb; ++b) tags[b] = std::max(tags[b], AmrTag::same);
+        continue;
+      }
       Variable &v = rc->Get(c.field);
       const pb2_pack_geom g = rc->Geometry(v);
       PB2_CHECK(pb2_block_derivative(&g, v.data(), c.comp, c.order, dev.get<Real>(), rc->stream()));
       PB2_CHECK(pb2_memcpy_d2h(maxd.data(), dev.get(), sizeof(Real) * nb, rc->stream()));
       PB2_CHECK(pb2_stream_sync(rc->stream()));
       for (int b = 0; b < nb; ++b) {
+        if (!v.IsAllocated(b)) { // ... and so does a block on which it is not allocated
+          tags[b] = std::max(tags[b], AmrTag::same);
+          continue;
+        }
         AmrTag t = maxd[b] > c.refine_criteria
                        ? AmrTag::refine
                        : (maxd[b] < c.derefine_criteria ? AmrTag::derefine : AmrTag::same);
