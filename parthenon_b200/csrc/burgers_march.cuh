@@ -37,6 +37,9 @@ namespace PB2_SWEEP_NS {
 #ifndef PB2_CHUNK
 #define PB2_CHUNK 4
 #endif
+#ifndef PB2_L2_HINTS
+#define PB2_L2_HINTS 0
+#endif
 #ifndef PB2_CHUNK_MINB
 #define PB2_CHUNK_MINB 4
 #endif
@@ -95,6 +98,26 @@ __device__ __forceinline__ void face_pq(const double upl, const double upr, doub
 __device__ __forceinline__ void cp_async8(const uint32_t saddr, const void *g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
 }
+// ... with an L2 eviction priority: the rows two consecutive chunks share are fetched
+// "evict_last" the first time and "evict_first" the second (their last use), everything that is
+// read once streams through "evict_first" — the re-read of a row then finds it in L2 even though
+// the rows all resident CTAs touch between the two reads (~100 MB) are as large as the L2
+__device__ __forceinline__ void cp_async8_hint(const uint32_t saddr, const void *g,
+                                               const uint64_t policy) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -119,7 +142,8 @@ template <int RECON, int CH, bool EDGE>
 __device__ __forceinline__ void stage_issue(const uint32_t st, const double *__restrict__ pu,
                                             const double *po, const int64_t sd, const int s0,
                                             const int nd, const long long dlo,
-                                            const long long dhi) {
+                                            const long long dhi, const uint64_t keep,
+                                            const uint64_t stream) {
   constexpr int lo = StencilRows<RECON>::kLo, nrow = CH + StencilRows<RECON>::kExtra;
 #pragma unroll
   for (int r = 0; r < nrow; ++r) {
@@ -128,11 +152,22 @@ __device__ __forceinline__ void stage_issue(const uint32_t st, const double *__r
       const int rr = s0 + lo + r;
       src += rr < 0 ? dlo : (rr >= nd ? dhi : 0);
     }
+    // the last kExtra rows are the first rows of the next chunk
+#if PB2_L2_HINTS
+    cp_async8_hint(st + r * kThreads * 8, src, r >= CH ? keep : stream);
+#else
     cp_async8(st + r * kThreads * 8, src);
+#endif
   }
 #pragma unroll
   for (int t = 0; t < CH; ++t)
-    if (s0 + t >= 1) cp_async8(st + (kURows + t) * kThreads * 8, po + (t - 1) * sd);
+    if (s0 + t >= 1) {
+#if PB2_L2_HINTS
+      cp_async8_hint(st + (kURows + t) * kThreads * 8, po + (t - 1) * sd, stream);
+#else
+      cp_async8(st + (kURows + t) * kThreads * 8, po + (t - 1) * sd);
+#endif
+    }
 }
 
 // ---- the marching stencil of one component -------------------------------------------------
@@ -204,10 +239,20 @@ struct MarchStencil<PB2_RECON_LINEAR> {
 // Cell s gives face s its right state and cell s-1 its last flux; the previous cell's left
 // state L and the previous face's flux F come in and go out.  po points at the component's
 // row of cell s0 in `out`.
+__device__ __forceinline__ void st_stream(double *p, const double v, const uint64_t policy) {
+#if PB2_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy)
+               : "memory");
+#else
+  *p = v;
+#endif
+}
+
 template <int RECON, bool COEF, int CH>
 __device__ __forceinline__ void comp_chunk(const double *st, double *po, const int64_t sd,
                                            const int s0, const double cd, double &L, double &F,
-                                           double (&P)[CH], double (&Q)[CH]) {
+                                           double (&P)[CH], double (&Q)[CH],
+                                           const uint64_t stream) {
   MarchStencil<RECON> ms;
   ms.init(st);
 #pragma unroll
@@ -217,7 +262,7 @@ __device__ __forceinline__ void comp_chunk(const double *st, double *po, const i
     if (COEF) face_pq(L, qr, P[t], Q[t]);
     const double f = fma(P[t], L, Q[t] * qr);
     if (s0 + t >= 1) // face s and face s-1 are known: cell s-1 is complete
-      po[(t - 1) * sd] = fma(cd, f - F, st[(kURows + t) * kThreads]);
+      st_stream(po + (t - 1) * sd, fma(cd, f - F, st[(kURows + t) * kThreads]), stream);
     F = f;
     L = ql;
     if (t + 1 < CH) ms.advance(st, t);
@@ -263,6 +308,7 @@ struct ColumnCtx {
   double *sL, *sF;  // per-thread carry columns in shared memory (+ n * kThreads)
   double *stage;    // per-thread stage columns: [2][kStageDoubles] (+ i * kThreads)
   long long dlo, dhi; // ghost rows below / above the block: offset to the neighbour's rows
+  uint64_t keep, stream; // L2 eviction policies (cp_async8_hint)
   int64_t col0;
   int b, nc, nd;
   double cdir, idx0, idx1, idx2;
@@ -287,11 +333,14 @@ __device__ __forceinline__ void issue_item(const GeoT<GEO> &G, const ColumnCtx &
   constexpr int lo = StencilRows<RECON>::kLo, extra = StencilRows<RECON>::kExtra;
   if (c.nd + 1 - s0n >= kChunk) {
     if (s0n + lo < 0 || s0n + lo + kChunk + extra > c.nd)
-      stage_issue<RECON, kChunk, true>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, c.dlo, c.dhi);
+      stage_issue<RECON, kChunk, true>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, c.dlo, c.dhi,
+                                       c.keep, c.stream);
     else
-      stage_issue<RECON, kChunk, false>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, 0, 0);
+      stage_issue<RECON, kChunk, false>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, 0, 0, c.keep,
+                                        c.stream);
   } else {
-    stage_issue<RECON, 1, true>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, c.dlo, c.dhi);
+    stage_issue<RECON, 1, true>(st, c.ub + off, c.ob + off, sd, s0n, c.nd, c.dlo, c.dhi, c.keep,
+                                c.stream);
   }
   cp_async_commit();
 }
@@ -321,9 +370,9 @@ __device__ __forceinline__ void run_chunk(const Args &a, const GeoT<GEO> &G, con
     const double cd = n < 3 ? 0.5 * c.cdir : c.cdir;
     double *po = c.ob + n * G.sc() + row0;
     if (m == 0)
-      comp_chunk<RECON, true, CH>(st, po, sd, s0, cd, L, F, P, Q);
+      comp_chunk<RECON, true, CH>(st, po, sd, s0, cd, L, F, P, Q, c.stream);
     else
-      comp_chunk<RECON, false, CH>(st, po, sd, s0, cd, L, F, P, Q);
+      comp_chunk<RECON, false, CH>(st, po, sd, s0, cd, L, F, P, Q, c.stream);
     c.sL[n * kThreads] = L;
     c.sF[n * kThreads] = F;
     buf ^= 1;
@@ -372,6 +421,8 @@ __global__ void __launch_bounds__(kThreads, PB2_CHUNK_MINB) sweep_chunk_kernel(c
     c.stage = c.sF + (size_t)c.nc * kThreads;
     c.dlo = 0;
     c.dhi = 0;
+    c.keep = l2_policy_evict_last();
+    c.stream = l2_policy_evict_first();
     if (a.nbr) {
       // rows beyond the block's ends: the same columns of the face neighbour's interior
       const int nlo = a.nbr[b * 27 + face_slot(DIR, 0)], nhi = a.nbr[b * 27 + face_slot(DIR, 1)];

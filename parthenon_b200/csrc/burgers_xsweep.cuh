@@ -81,29 +81,38 @@ __device__ __forceinline__ PairShift pair_shift(const int c0, const int nx, cons
   return s;
 }
 
-template <int RECON, int GEO>
-__device__ __forceinline__ void load_pair(PairStencil<RECON> &s, const double *__restrict__ p,
-                                          const PairShift &sh) {
-  // p -> cell c0 of the pair (odd element index when the ghost width is even)
+// ---- staging: the stencil of a pair (and the pair's two `base` values) travel global ->
+// per-thread shared-memory column with cp.async, kXAhead components ahead of the arithmetic
+constexpr int kXStages = 3, kXAhead = kXStages - 1, kXSlots = 8;
+
+// what a lane needs to address one (pass, component) item
+struct PairItem {
+  int64_t off;   // element offset of the pair's first cell inside a component
+  PairShift sh;  // ... and where its four load groups really come from
+  bool ldb;      // the pair completes two cells whose `base` values are needed
+};
+
+template <int RECON>
+__device__ __forceinline__ void issue_pair(const uint32_t st, const double *__restrict__ ub,
+                                           const double *bb, const int64_t sc, const int n,
+                                           const PairItem &it) {
+  const double *p = ub + n * sc + it.off;
+  constexpr uint32_t K = kThreads * 8;
   if (RECON == PB2_RECON_WENO5) {
-    s.q[0] = __ldg(p + sh.o[0] - 2);
-    if (GEO == 32) { // c0 - 1 is 16-byte aligned: (c0-1, c0) and (c0+1, c0+2) as vectors
-      const double2 a = __ldg(reinterpret_cast<const double2 *>(p + sh.o[1] - 1));
-      const double2 b = __ldg(reinterpret_cast<const double2 *>(p + sh.o[2] + 1));
-      s.q[1] = a.x;
-      s.q[2] = a.y;
-      s.q[3] = b.x;
-      s.q[4] = b.y;
-    } else {
-      s.q[1] = __ldg(p + sh.o[1] - 1);
-      s.q[2] = __ldg(p + sh.o[1]);
-      s.q[3] = __ldg(p + sh.o[2] + 1);
-      s.q[4] = __ldg(p + sh.o[2] + 2);
-    }
-    s.q[5] = __ldg(p + sh.o[3] + 3);
+    cp_async8(st, p + it.sh.o[0] - 2);
+    cp_async8(st + K, p + it.sh.o[1] - 1);
+    cp_async8(st + 2 * K, p + it.sh.o[1]);
+    cp_async8(st + 3 * K, p + it.sh.o[2] + 1);
+    cp_async8(st + 4 * K, p + it.sh.o[2] + 2);
+    cp_async8(st + 5 * K, p + it.sh.o[3] + 3);
   } else {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) s.q[t] = __ldg(p + sh.o[t] - 1 + t);
+    for (int t = 0; t < 4; ++t) cp_async8(st + t * K, p + it.sh.o[t] - 1 + t);
+  }
+  if (it.ldb) {
+    const double *q = bb + n * sc + it.off;
+    cp_async8(st + 6 * K, q - 1);
+    cp_async8(st + 7 * K, q);
   }
 }
 
@@ -118,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
   const int bi = warp_global / warps_per_block;
   double rate = 0.0;
   __shared__ double sL[kThreads / 32][kMaxComp], sF[kThreads / 32][kMaxComp];
+  __shared__ double xs[kXStages][kXSlots][kThreads];
   if (bi < a.g.nblocks) { // whole warp together
     const int b = a.block_ids ? a.block_ids[bi] : bi;
     const int row0 = (warp_global % warps_per_block) * kXRows;
@@ -146,7 +156,11 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
       sF[wid][lane] = 0.0;
     }
     __syncwarp();
-    for (int f0 = 0; f0 < items; f0 += 32) {
+    const uint32_t xs0 = static_cast<uint32_t>(__cvta_generic_to_shared(&xs[0][0][threadIdx.x]));
+    constexpr uint32_t kStageBytes = kXSlots * kThreads * 8;
+
+    // the lane's item of pass f0: which pair of which row, where its cells live
+    auto item_of = [&](const int f0, PairItem &it, int &p_out, bool &upd_out) {
       const int f = f0 + lane;
       const bool live = f < items;
       const int fr = live ? f : items - 1; // inactive lanes recompute a valid item
@@ -168,59 +182,58 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
         rj = row - rk * G.nx(1);
       }
       // element offset of cell c0 = 2p - 1 inside a component
-      const int64_t off = (int64_t)(G.is(2) + rk) * G.sk() + (int64_t)(G.is(1) + rj) * G.sj() +
-                          (G.is(0) + 2 * p - 1);
-      const bool upd = live && p >= 1; // this lane completes cells 2p-2 and 2p-1
-      const bool ldb = use_base && upd;
-      if (f0 + 32 < items) {
-        // the lines of the NEXT pass start their trip now (64 cells further along the rows)
-        const int f2 = min(f + 32, items - 1);
-        int r2, p2;
-        if (GEO == 32) {
-          r2 = f2 / 17;
-          p2 = f2 - r2 * 17;
-        } else {
-          r2 = (int)a.dnpair.div((uint32_t)f2);
-          p2 = f2 - r2 * npair;
-        }
-        const int row2 = row0 + r2;
-        int rk2, rj2;
-        if (GEO == 32) {
-          rk2 = row2 >> 5;
-          rj2 = row2 & 31;
-        } else {
-          rk2 = (int)a.dnx1.div((uint32_t)row2);
-          rj2 = row2 - rk2 * G.nx(1);
-        }
-        const int64_t off2 = (int64_t)(G.is(2) + rk2) * G.sk() +
-                             (int64_t)(G.is(1) + rj2) * G.sj() + (G.is(0) + 2 * p2 - 1);
-        for (int n = 0; n < nc; ++n) prefetch_l1(ub + n * sc + off2);
-        if (use_base)
-          for (int n = 0; n < nc; ++n) prefetch_l1(bb + n * sc + off2);
-      }
+      it.off = (int64_t)(G.is(2) + rk) * G.sk() + (int64_t)(G.is(1) + rj) * G.sj() +
+               (G.is(0) + 2 * p - 1);
+      it.sh = pair_shift<RECON>(2 * p - 1, G.nx(0), dlo, dhi);
+      upd_out = live && p >= 1; // this lane completes cells 2p-2 and 2p-1
+      it.ldb = use_base && upd_out;
+      p_out = p;
+    };
 
-      // x velocity: states, wave-speed coefficients of faces 2p-1 and 2p
-      PairStencil<RECON> cur, nxt;
+    PairItem cur, nxt;
+    int p, pn;
+    bool upd, updn;
+    item_of(0, cur, p, upd);
+    nxt = cur;
+    // fill the pipeline: the first kXAhead components of the first pass
+    int qs = 0; // stage of the item about to be computed
+#pragma unroll
+    for (int k = 0; k < kXAhead; ++k) {
+      if (k < nc) issue_pair<RECON>(xs0 + k * kStageBytes, ub, bb, sc, k, cur);
+      cp_async_commit();
+    }
+    for (int f0 = 0; f0 < items; f0 += 32) {
+      const bool more = f0 + 32 < items;
+      if (more) item_of(f0 + 32, nxt, pn, updn);
       double P0, Q0, P1, Q1;
       double sq0 = 0.0, sq1 = 0.0; // LAST (1-D meshes): sum of squared velocities, cells 2p-2 / 2p-1
-      const PairShift sh = pair_shift<RECON>(2 * p - 1, G.nx(0), dlo, dhi);
-      load_pair<RECON, GEO>(cur, ub + off, sh);
-#pragma unroll 2
+      const int64_t off = cur.off;
+#pragma unroll 1
       for (int n = 0; n < nc; ++n) {
-        if (n + 1 < nc) load_pair<RECON, GEO>(nxt, ub + (n + 1) * sc + off, sh);
-        double b0 = 0.0, b1 = 0.0;
-        if (ldb) {
-          if (GEO == 32) {
-            const double2 t = *reinterpret_cast<const double2 *>(bb + n * sc + off - 1);
-            b0 = t.x;
-            b1 = t.y;
-          } else {
-            b0 = bb[n * sc + off - 1];
-            b1 = bb[n * sc + off];
-          }
+        // item kXAhead ahead: a later component of this pass or an early one of the next
+        {
+          const int na = n + kXAhead;
+          int sa = qs + kXAhead;
+          if (sa >= kXStages) sa -= kXStages;
+          if (na < nc)
+            issue_pair<RECON>(xs0 + sa * kStageBytes, ub, bb, sc, na, cur);
+          else if (more && na - nc < nc)
+            issue_pair<RECON>(xs0 + sa * kStageBytes, ub, bb, sc, na - nc, nxt);
+          cp_async_commit();
+          cp_async_wait<kXAhead>();
         }
+        const double *st = &xs[qs][0][threadIdx.x];
+        PairStencil<RECON> q;
+#pragma unroll
+        for (int t = 0; t < PairStencil<RECON>::kN; ++t) q.q[t] = st[t * kThreads];
+        double b0 = 0.0, b1 = 0.0;
+        if (cur.ldb) {
+          b0 = st[6 * kThreads];
+          b1 = st[7 * kThreads];
+        }
+        if (++qs == kXStages) qs = 0;
         double l0, r0, l1, r1;
-        cur.recon(l0, r0, l1, r1);
+        q.recon(l0, r0, l1, r1);
         // left state of cell 2p-2 from the previous lane (lane 31's value of the previous pass
         // for lane 0)
         const double cL = sL[wid][n], cF = sF[wid][n];
@@ -240,8 +253,8 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
         __syncwarp();
         if (upd) {
           const double cd = n < 3 ? 0.5 * cdir : cdir;
-          const double o0 = fma(cd, fa - Fp, fma(a.w2, b0, a.beta * cur.u0()));
-          const double o1 = fma(cd, fb - fa, fma(a.w2, b1, a.beta * cur.u1()));
+          const double o0 = fma(cd, fa - Fp, fma(a.w2, b0, a.beta * q.u0()));
+          const double o1 = fma(cd, fb - fa, fma(a.w2, b1, a.beta * q.u1()));
           if (GEO == 32) {
             *reinterpret_cast<double2 *>(ob + n * sc + off - 1) = make_double2(o0, o1);
           } else {
@@ -259,9 +272,13 @@ __global__ void __launch_bounds__(kThreads, PB2_XPAIR_MINB) sweep_xpair_kernel(c
             }
           }
         }
-        cur = nxt;
       }
+      cur = nxt;
+      p = pn;
+      upd = updn;
     }
+    cp_async_wait<0>();
+    (void)p;
   }
   if (LAST) reduce_dt(a, rate);
 }

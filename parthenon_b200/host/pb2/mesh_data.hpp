@@ -76,6 +76,7 @@ class Variable {
   std::string label_;
   Metadata m_;
   int sparse_id_, ncomp_, nblocks_, capacity_;
+  int data_shift_ = 0; // see Variable::data()
   TopologicalType tt_ = TopologicalType::Cell;
   int nel_ = 1;
   bool multilevel_;
