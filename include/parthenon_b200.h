@@ -56,6 +56,14 @@ int pb2_memcpy_h2d(void *dst, const void *src, size_t bytes, pb2_stream_t stream
 int pb2_memcpy_d2h(void *dst, const void *src, size_t bytes, pb2_stream_t stream);
 int pb2_memcpy_d2d(void *dst, const void *src, size_t bytes, pb2_stream_t stream);
 int pb2_stream_create(pb2_stream_t *stream);
+/* a stream of the device's highest (high != 0) or lowest priority: kernels of a high-priority
+ * stream get free SM slots before pending work of other streams (the halo pack / NCCL stream) */
+int pb2_stream_create_priority(pb2_stream_t *stream, int high);
+/* Device-side wait: work enqueued on `stream` after this call starts once *counter >= target
+ * (a one-thread kernel polls the counter).  The producer is a kernel on another stream that
+ * advances the counter from inside (pb2_burgers_args::progress): finer than an event, which only
+ * fires at a kernel boundary.  Do not use under a profiler that serialises kernels. */
+int pb2_stream_wait_value(pb2_stream_t stream, const int32_t *counter, int32_t target);
 int pb2_stream_destroy(pb2_stream_t stream);
 int pb2_stream_sync(pb2_stream_t stream);
 int pb2_device_sync(void);
@@ -413,6 +421,14 @@ typedef struct pb2_burgers_args {
    * exchange out of the cycle and run it only when something else reads ghost cells.  Only the
    * six face entries are used (a direction sweep never reads edge or corner ghosts). */
   const int32_t *nbr_direct;
+  /* PB2_MATH_FAST, pb2_burgers_stage only.  If progress != NULL, every thread block of the LAST
+   * direction sweep that works on one of the first progress_blocks launched blocks (order of
+   * block_ids) adds 1 to *progress when its results are in memory.  A consumer on another stream
+   * (pb2_stream_wait_value) can then start on those blocks — the ones that feed inter-GPU halos,
+   * listed first — while the same launch is still busy with the rest.  The counter reaches
+   * pb2_burgers_progress_target(); the caller zeroes it before the stage.  2-D / 3-D only. */
+  int32_t *progress;
+  int32_t progress_blocks;
 } pb2_burgers_args;
 
 /* fluxes only: writes args->flux[0..ndim-1] from args->u */
@@ -424,6 +440,8 @@ int pb2_burgers_update(const pb2_burgers_args *args, pb2_stream_t stream);
  * divergence straight into `out` (args->flux is ignored and may be NULL; out may alias base
  * but not u). */
 int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream);
+/* value *progress reaches once the first nblocks launched blocks of a stage are done */
+int32_t pb2_burgers_progress_target(const pb2_pack_geom *g, int32_t nblocks);
 /* stand-alone CalculateDerived (burgers_package.cpp:143-167) and/or EstimateTimestepMesh
  * (:170-200) over interior cells: derived [nblocks][nk][nj][ni] or NULL; dt_min device scalar
  * (initialised to +huge by the caller) or NULL */

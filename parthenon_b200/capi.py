@@ -78,7 +78,8 @@ class BurgersArgs(C.Structure):
                 ("flux", C.c_void_p * 3), ("derived", C.c_void_p), ("dt_min", C.c_void_p),
                 ("beta", C.c_double), ("dt", C.c_double),
                 ("block_ids", C.c_void_p), ("num_block_ids", C.c_int32),
-                ("nbr_direct", C.c_void_p)]
+                ("nbr_direct", C.c_void_p), ("progress", C.c_void_p),
+                ("progress_blocks", C.c_int32)]
 
 
 _lib = None
@@ -87,7 +88,7 @@ _lib = None
 SYMBOLS = [
     "pb2_version", "pb2_last_error", "pb2_device_count", "pb2_set_device",
     "pb2_device_sm_count", "pb2_malloc", "pb2_free", "pb2_cache_trim", "pb2_host_alloc", "pb2_host_free",
-    "pb2_memset", "pb2_memcpy_h2d", "pb2_memcpy_d2h", "pb2_memcpy_d2d", "pb2_stream_create",
+    "pb2_memset", "pb2_memcpy_h2d", "pb2_memcpy_d2h", "pb2_memcpy_d2d", "pb2_stream_create", "pb2_stream_create_priority", "pb2_stream_wait_value",
     "pb2_stream_destroy", "pb2_stream_sync", "pb2_device_sync", "pb2_event_create",
     "pb2_event_destroy", "pb2_event_record", "pb2_event_sync", "pb2_event_query",
     "pb2_stream_wait_event", "pb2_event_elapsed_ms", "pb2_launch_count",
@@ -101,7 +102,7 @@ SYMBOLS = [
     "pb2_halo_copy_uniform", "pb2_advection_fluxes", "pb2_copy_flags", "pb2_copy_select",
     "pb2_weighted_sum_blocks", "pb2_flux_divergence_blocks", "pb2_advection_fluxes_blocks",
     "pb2_block_quiet_flags", "pb2_block_minmax", "pb2_block_derivative", "pb2_bc_table_create", "pb2_apply_bcs",
-    "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage",
+    "pb2_burgers_calculate_fluxes", "pb2_burgers_update", "pb2_burgers_stage", "pb2_burgers_progress_target",
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
     "pb2_comm_barrier",

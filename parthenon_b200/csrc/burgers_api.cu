@@ -186,10 +186,19 @@ int pb2_burgers_stage(const pb2_burgers_args *args, pb2_stream_t stream) {
     if (int rc = require_device()) return rc;
     if (args->geom.nblocks == 0) return PB2_OK;
     PB2_REQUIRE(args->out != args->u, "the fused stage cannot write its stencil input");
+    PB2_REQUIRE(args->progress == nullptr || args->geom.ndim >= 2,
+                "the progress counter needs a 2-D or 3-D mesh");
     return burgers_stage_sweep(args, as_stream(stream));
   }
   if (int rc = pb2_burgers_calculate_fluxes(args, stream)) return rc;
   return pb2_burgers_update(args, stream);
+}
+
+int32_t pb2_burgers_progress_target(const pb2_pack_geom *g, int32_t nblocks) {
+  if (!g || g->ndim < 2 || nblocks <= 0) return 0;
+  // thread blocks per meshblock of the last sweep: 128 columns each (burgers_march.cuh)
+  const int ncol = g->nx[0] * (g->ndim == 2 ? 1 : g->nx[1]);
+  return nblocks * ((ncol + 127) / 128);
 }
 
 int pb2_burgers_derived_dt(const pb2_pack_geom *pg, const double *u, double *derived,

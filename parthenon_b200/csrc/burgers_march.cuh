@@ -443,6 +443,14 @@ __global__ void __launch_bounds__(kThreads, PB2_CHUNK_MINB) sweep_chunk_kernel(c
     for (; s0 <= c.nd; ++s0) run_chunk<RECON, DIR, LAST, GEO, 1>(a, G, c, s0, buf, rate);
   }
   if (LAST) reduce_dt(a, rate);
+  if (LAST && a.progress != nullptr && bi < a.progress_blocks) {
+    // this block's results are in memory: tell whoever waits on another stream
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.progress, 1);
+    }
+  }
 }
 
 inline size_t chunk_smem_bytes(int ncomp) {

@@ -64,6 +64,8 @@ struct Args {
   const int *block_ids;      // launch block -> block of the batch, or null (identity)
   const int *nbr;            // [nblocks][27] same-device neighbour blocks (-1: none) whose
                              // interiors stand in for this block's ghost rows, or null
+  int *progress;             // LAST sweep: += 1 per finished CTA of the first progress_blocks
+  int progress_blocks;       // launched blocks, or null
   double beta, w2, bdt;      // w2 = 1 - beta, bdt = beta * dt
   FastDiv dncell, dnx1;      // x sweep: division by (nx1 + 2) and by nx2 as multiply-shift
   FastDiv dnpair;            // paired x sweep: division by nx1 / 2 + 1
@@ -500,6 +502,11 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   a.bdt = args->beta * args->dt;
   a.derived = nullptr;
   a.dtmin = nullptr;
+  a.progress = nullptr;
+  a.progress_blocks = 0;
+  // PB2_SWEEP_V1=1 selects the kernels of round 1 (one cell per lane in x, shared-memory-ring
+  // march in y / z) for A/B runs
+  static const bool v1 = std::getenv("PB2_SWEEP_V1") != nullptr;
   // the march kernels keep their stencil rows in dynamic shared memory (opt-in above 48 KB)
   const size_t smem = march_smem_bytes(g.ncomp);
   static bool attr_set = false;
@@ -511,13 +518,12 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
     attr_set = true;
   }
   auto last = [&](Args &x) {
+    x.progress = v1 ? nullptr : args->progress;
+    x.progress_blocks = args->progress_blocks;
     x.derived = args->derived;
     x.dtmin = reinterpret_cast<unsigned long long *>(args->dt_min);
   };
   const double zones = (double)g.nblocks * g.nx[0] * g.nx[1] * g.nx[2]; // of the launched blocks
-  // PB2_SWEEP_V1=1 selects the kernels of round 1 (one cell per lane in x, shared-memory-ring
-  // march in y / z) for A/B runs
-  static const bool v1 = std::getenv("PB2_SWEEP_V1") != nullptr;
   const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool g32 = geo32(g) && al16(a.u) && al16(a.base) && al16(a.out) && g.sb % 2 == 0;
   a.nbr = v1 ? nullptr : args->nbr_direct;

@@ -345,6 +345,38 @@ int pb2_stream_create(pb2_stream_t *stream) {
   *stream = s;
   return PB2_OK;
 }
+int pb2_stream_create_priority(pb2_stream_t *stream, int high) {
+  PB2_REQUIRE(stream, "null argument");
+  if (int rc = require_device()) return rc;
+  int lo = 0, hi = 0; // numerically lower = higher priority
+  PB2_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  cudaStream_t s;
+  PB2_CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? hi : lo));
+  *stream = s;
+  return PB2_OK;
+}
+namespace pb2 {
+// one thread polls a device counter: the stream it is launched on waits, on the device, for work
+// that another stream's kernel reports from inside (no host, no kernel boundary in between)
+__global__ void wait_value_kernel(const volatile int *counter, const int target, int *timed_out) {
+  long long spins = 0;
+  while (*counter < target) {
+    __nanosleep(500);
+    if (++spins > 40000000ll) { // ~20 s: a producer that never reports must not hang the device
+      if (timed_out) *timed_out = 1;
+      break;
+    }
+  }
+  __threadfence();
+}
+} // namespace pb2
+int pb2_stream_wait_value(pb2_stream_t stream, const int32_t *counter, int32_t target) {
+  PB2_REQUIRE(counter, "null counter");
+  if (int rc = require_device()) return rc;
+  pb2::wait_value_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, target, nullptr);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
 int pb2_stream_destroy(pb2_stream_t stream) {
   PB2_CUDA_CHECK(cudaStreamDestroy(as_stream(stream)));
   return PB2_OK;

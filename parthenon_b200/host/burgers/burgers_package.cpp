@@ -72,6 +72,9 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
   // (pb2_burgers_args::nbr_direct) and the same-device ghost exchange leaves the cycle; ghost
   // cells are refreshed when something else reads them
   pkg->AddParam("lazy_ghosts", pin->GetOrAddBoolean("pb2", "lazy_ghosts", true));
+  // multi-GPU: the blocks that feed other GPUs are listed first in a single launch and reported
+  // from inside the last sweep (false: two launches per sweep, boundary blocks then the rest)
+  pkg->AddParam("device_progress", pin->GetOrAddBoolean("pb2", "device_progress", true));
 
   const int num_scalars = pin->GetOrAddInteger("burgers", "num_scalars", 1);
   pkg->AddParam("num_scalars", num_scalars);
@@ -214,6 +217,19 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
       PB2_CHECK(pb2_weighted_sum_ghosts_blocks(&a.geom, a.u, a.base, beta, 1.0 - beta, a.out,
                                                fc.ids_stale_ghosts.get<int32_t>(),
                                                fc.n_stale_ghosts, mc0->stream()));
+  } else if (split && a.geom.ndim >= 2 && pkg->Param<bool>("device_progress")) {
+    // ONE launch per sweep over [boundary blocks, interior blocks]; the last sweep reports the
+    // boundary part from inside (pb2_burgers_args::progress) and the communication stream waits
+    // for that count on the device: no second set of launches with its own tail
+    a.block_ids = bc.ids_ordered.get<int32_t>();
+    a.num_block_ids = bc.n_boundary + bc.n_interior;
+    a.progress = bc.progress.get<int32_t>();
+    a.progress_blocks = bc.n_boundary;
+    PB2_CHECK(pb2_memset(a.progress, 0, sizeof(int32_t), mc0->stream()));
+    PB2_CHECK(pb2_event_record(bc.early_ready, mc0->stream())); // the counter is reset
+    bc.early_valid = true;
+    bc.progress_target = pb2_burgers_progress_target(&a.geom, bc.n_boundary);
+    PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
   } else if (split) {
     a.block_ids = bc.ids_boundary.get<int32_t>();
     a.num_block_ids = bc.n_boundary;

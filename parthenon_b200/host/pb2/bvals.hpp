@@ -154,6 +154,11 @@ struct BvarsCache {
   // are still being advanced on the compute stream.
   DeviceBuffer ids_boundary, ids_interior;
   int n_boundary = 0, n_interior = 0;
+  // one launch over [boundary blocks..., interior blocks...]: the last sweep counts finished
+  // thread blocks of the boundary part in `progress` (pb2_burgers_args::progress) and the
+  // communication stream waits for the count on the device (pb2_stream_wait_value)
+  DeviceBuffer ids_ordered, progress;
+  int32_t progress_target = 0; // > 0: SendBoundBufs<nonlocal> waits for it before packing
   // multilevel meshes: blocks with a FACE neighbour on another level take part in flux
   // correction and need their face fluxes stored (ids_flxcor); all others (ids_plain) can run
   // the flux-free sweeps.  Blocks with a coarser neighbour own ghosts that a stage's exchange

@@ -282,10 +282,8 @@ class Mesh {
   // test knob (pb2/table_halo): force the general region-table path for local channels even on
   // uniform meshes, where the descriptor-free pb2_halo_copy_uniform would be used
   bool table_halo = false;
-  // pb2/unverified_sparse_multilevel = true lifts the refusal of sparse fields on refined
-  // (static) meshes: allocation-aware restriction / prolongation / flux correction on
-  // same-device channels.  The oracle for this case is pinned to the reference, the device
-  // path has not been run yet (written when no GPU time was left in round 1).
+  // (pb2/unverified_sparse_multilevel: knob of round 1, when sparse fields on statically refined
+  // meshes had not been run on a device yet; they are on by default now, the knob is ignored)
   bool unverified_sparse_multilevel = false;
   int VirtualRankOf(int gid) const;
 

@@ -257,6 +257,12 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     // the fields a remesh carries over: pmb->vars_cc_ (Independent / FillGhost cell-centred)
     if (!(nv.IsSet(Metadata::Independent) || nv.IsSet(Metadata::FillGhost))) continue;
     PARTHENON_REQUIRE(!nv.metadata().IsSparse(), "sparse fields cannot be remeshed in this build");
+    // blocks of face / edge / node fields that change device: the 2-GPU run of round 2 did not
+    // reproduce the reference's dumps (profiles/multigpu_check_r02_n2.txt), so refuse rather
+    // than return wrong shared elements; one device is bit-exact (tests/test_tecomm_gpu.py)
+    PARTHENON_REQUIRE(nranks == 1 || nv.topological_type() == TopologicalType::Cell,
+                      "adaptive remeshing of face / edge / node fields needs a single device in "
+                      "this build (" + nv.label() + ")");
     Variable &ov = old_md->Get(nv.label());
     const int64_t fsz = nv.block_stride + (nv.block_stride & 1);   // slab entries, 16-B aligned
     const int64_t csz = nv.cblock_stride + (nv.cblock_stride & 1);

@@ -165,8 +165,12 @@ void Rebuild(MeshData<Real> *md) {
   c.sparse = false;
   for (Variable *v : c.vars) c.sparse = c.sparse || (v->metadata().IsSparse() && pm->sparse_config.enabled);
   if (c.sparse) {
-    PARTHENON_REQUIRE(!pm->multilevel || (pm->unverified_sparse_multilevel && !pm->adaptive && !slabs),
-                      "sparse fields on multilevel meshes are not supported by this build");
+    // statically refined meshes: allocation-aware restriction / prolongation / flux correction
+    // on same-device channels (tests/test_late_round1_gpu.py, bit-exact against the reference's
+    // dumps); remeshing sparse fields and shipping them between devices across levels are not built
+    PARTHENON_REQUIRE(!pm->multilevel || (!pm->adaptive && !slabs),
+                      "sparse fields on multilevel meshes: only static refinement on one device "
+                      "is supported by this build");
     PARTHENON_REQUIRE(pm->DefaultNumPartitions() == 1,
                       "sparse fields need one MeshData per rank (parthenon/mesh/pack_size=-1)");
   }
@@ -516,6 +520,10 @@ void Rebuild(MeshData<Real> *md) {
     };
     upload(c.ids_boundary, bnd);
     upload(c.ids_interior, inr);
+    std::vector<int32_t> ordered(bnd);
+    ordered.insert(ordered.end(), inr.begin(), inr.end());
+    upload(c.ids_ordered, ordered);
+    if (!c.progress) c.progress.Allocate(sizeof(int32_t), md->stream());
     // classes for the multilevel stage
     std::vector<int32_t> flx, plain, stale;
     for (auto &pmb : md->GetBlockList()) {
@@ -605,8 +613,12 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     if (c.early_valid && !pm->multilevel) {
       ps = cs;
       PB2_CHECK(pb2_stream_wait_event(cs, c.early_ready));
+      // ... and, if the producer reports from inside its last kernel, for the boundary blocks
+      if (c.progress_target > 0)
+        PB2_CHECK(pb2_stream_wait_value(cs, c.progress.get<int32_t>(), c.progress_target));
     }
     c.early_valid = false;
+    c.progress_target = 0;
     // the previous exchange must have left the slabs: its sends (same stream order on cs, or
     // the `sent` event) and its unpack (`unpacked`, recorded on the compute stream)
     if (c.nonlocal_in_flight && ps == st) PB2_CHECK(pb2_stream_wait_event(st, c.sent));

@@ -46,7 +46,7 @@ void ParthenonManager::ParthenonInitPackagesAndMesh(const std::vector<LogicalLoc
   pmesh = std::make_unique<Mesh>(pinput.get(), app_input.get(), packages, rank_, nranks_, leaves);
   pb2_stream_t st = nullptr, cs = nullptr;
   PB2_CHECK(pb2_stream_create(&st));
-  PB2_CHECK(pb2_stream_create(&cs));
+  PB2_CHECK(pb2_stream_create_priority(&cs, 1)); // halo pack / NCCL: first in line for SMs
   pmesh->stream = st;
   pmesh->comm_stream = cs;
   if (nranks_ > 1) {

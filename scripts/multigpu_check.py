@@ -143,31 +143,24 @@ def main():
               f"{g['U_0'].shape[0]}: {'bit-exact' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
         sim.close()
-    # adaptive remesh of face / edge / node fields across devices (blocks of such fields migrate
-    # between GPUs; NOT RUN YET on more than one device: written when no GPU time was left)
-    for name, ndim, nx, nb, numlevel in H.TEAMR:
+    # adaptive remesh of face / edge / node fields across devices: NOT supported (the 2-GPU run of
+    # round 2 did not reproduce the reference's dumps); the build must refuse it loudly
+    for name, ndim, nx, nb, numlevel in H.TEAMR[:1]:
         nccl_id = new_id()
-        g = np.load(os.path.join(gold, name + ".npz"))
-        full = lambda n: (n,) * ndim + (1,) * (3 - ndim)
         ov = deck_overrides(ndim, (nb,) * 3, 2, (nx // nb,) * 3, refinement="adaptive")
         ov.update({"parthenon/mesh/numlevel": numlevel, "parthenon/mesh/derefine_count": 2})
-        sim = host.Simulation(app="tecomm", overrides=ov, rank=rank, nranks=world, nccl_id=nccl_id)
-        good = True
-        for c in range(int(g["ncycles"]) + 1):
-            if c:
+        refused = False
+        try:
+            sim = host.Simulation(app="tecomm", overrides=ov, rank=rank, nranks=world,
+                                  nccl_id=nccl_id)
+            for c in (1, 2, 3):
                 sim.tag_and_remesh(c)
-            info = sim.info()
-            lo, hi = info["first_gid"], info["first_gid"] + info["nblocks"]
-            leaves, _ = H.leaves_from_bounds(g[f"bounds_{c}"], full(nx), full(nb))
-            locs = np.array([sim.block(b)["loc"] for b in range(info["nblocks"])])
-            good = good and info["nbtotal"] == len(leaves) and np.array_equal(locs, leaves[lo:hi])
-            for f, field in enumerate(("face", "edge", "node")):
-                good = good and np.array_equal(H.block_crcs(sim.get_field("base", field)),
-                                               g[f"crc_{c}_{f}"][lo:hi])
-        print(f"rank {rank}/{world}: {name}, adaptive face / edge / node fields: "
-              f"{'bit-exact' if good else 'MISMATCH'}", flush=True)
-        ok = ok and good
-        sim.close()
+            sim.close()
+        except RuntimeError as e:
+            refused = "single device" in str(e)
+        print(f"rank {rank}/{world}: {name}, adaptive face / edge / node fields on {world} devices: "
+              f"{'refused as documented' if refused else 'NOT REFUSED'}", flush=True)
+        ok = ok and refused
     # sparse fields across devices: null-message flags travel with the slabs, a block allocates a
     # field when a non-null message arrives from another GPU
     from tests.test_oracle_golden import SPARSE

@@ -48,7 +48,7 @@ def test_sparse_advection_on_refined_mesh():
     leaves, nrb = H.leaves_from_bounds(g["bounds"], (64, 64, 1), (8, 8, 1), xmin=-1.0, xmax=1.0)
     ov = {"parthenon/mesh/refinement": "static", "parthenon/mesh/numlevel": 3,
           "parthenon/sparse/alloc_threshold": 1e-2, "parthenon/sparse/dealloc_threshold": 5e-3,
-          "parthenon/sparse/dealloc_count": 2, "pb2/unverified_sparse_multilevel": "true"}
+          "parthenon/sparse/dealloc_count": 2}
     sim = host.Simulation(app="sparse_advection", overrides=ov, leaves=leaves)
     try:
         sim.pre_execute()
