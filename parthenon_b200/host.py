@@ -73,6 +73,13 @@ recon = weno5
 num_scalars = 8
 """
 
+# the field-only test application (face / edge / node fields): the burgers deck's mesh and time
+# blocks without its <parthenon/refinement0> criterion — that criterion names the field U, which
+# this application does not have, and a criterion on a missing field votes "same"
+# (amr_criteria.cpp:89-91), i.e. it would veto every derefinement
+TECOMM_DECK = BURGERS_DECK[:BURGERS_DECK.index("<parthenon/refinement0>")] + \
+    BURGERS_DECK[BURGERS_DECK.index("<burgers>"):]
+
 # example/advection: the values of the reference's parthinput.advection that matter on this
 # path (outputs and the derived demo fields are off)
 ADVECTION_DECK = """
@@ -381,7 +388,8 @@ class Simulation(_Base):
                  nccl_id=None, leaves=None):
         if deck is None:
             deck = {"advection": ADVECTION_DECK,
-                    "sparse_advection": SPARSE_ADVECTION_DECK}.get(app, BURGERS_DECK)
+                    "sparse_advection": SPARSE_ADVECTION_DECK,
+                    "tecomm": TECOMM_DECK}.get(app, BURGERS_DECK)
         self.h = C.c_void_p()
         la, n = _leaves(leaves)
         check(lib().pb2h_sim_create(C.byref(self.h), app.encode(), deck.encode(),
