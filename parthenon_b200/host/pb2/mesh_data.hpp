@@ -152,6 +152,13 @@ class MeshData {
     return dt_cell_.get<Real>();
   }
 
+  // a device scratch buffer of at least `bytes` that lives as long as the batch (per-cycle flag
+  // reductions of sparse fields: no allocation / free inside the cycle)
+  DeviceBuffer &SparseScratch(size_t bytes) {
+    if (sparse_scratch_.bytes() < bytes) sparse_scratch_.Allocate(bytes, stream());
+    return sparse_scratch_;
+  }
+
   BvarsCache &bvars() { return *bvars_; }
   // resolved SparsePacks by descriptor identifier (MeshData::GetSparsePackCache)
   std::map<std::string, std::shared_ptr<SparsePackStorage>> &GetSparsePackCache() {
@@ -170,7 +177,7 @@ class MeshData {
   std::map<std::string, std::shared_ptr<Variable>> vars_;
   std::vector<std::shared_ptr<Variable>> order_;
   std::map<std::string, std::unique_ptr<VariablePack>> pack_cache_;
-  DeviceBuffer dx_, xmin_, dt_cell_;
+  DeviceBuffer dx_, xmin_, dt_cell_, sparse_scratch_;
   std::map<std::string, std::shared_ptr<SparsePackStorage>> sparse_pack_cache_;
   std::unique_ptr<BvarsCache> bvars_;
 };

@@ -76,19 +76,27 @@ TaskStatus SparseDealloc(MeshData<Real> *md) {
   Mesh *pm = md->GetMeshPointer();
   if (!pm->sparse_config.enabled || md->NumBlocks() == 0) return TaskStatus::complete;
   const int nb = md->NumBlocks();
-  std::vector<int32_t> quiet(nb);
-  for (Variable *v : md->GetVariablesByFlag({Metadata::Sparse})) {
+  // one flag buffer, one read-back and one synchronisation for ALL sparse fields (the reference
+  // reduces per (block, variable) team, update.cpp:161-186)
+  const std::vector<Variable *> vars = md->GetVariablesByFlag({Metadata::Sparse});
+  if (vars.empty()) return TaskStatus::complete;
+  const size_t need = sizeof(int32_t) * static_cast<size_t>(nb) * vars.size();
+  DeviceBuffer &flags = md->SparseScratch(need);
+  std::vector<int32_t> quiet(static_cast<size_t>(nb) * vars.size());
+  for (size_t iv = 0; iv < vars.size(); ++iv) {
+    Variable *v = vars[iv];
     const pb2_pack_geom g = md->Geometry(*v);
-    DeviceBuffer flags;
-    flags.Allocate(sizeof(int32_t) * nb, md->stream());
     PB2_CHECK(pb2_block_quiet_flags(&g, v->data(), v->metadata().GetDeallocationThreshold(),
-                                    v->DeviceMask(), flags.get<int32_t>(), md->stream()));
-    PB2_CHECK(pb2_memcpy_d2h(quiet.data(), flags.get(), sizeof(int32_t) * nb, md->stream()));
-    PB2_CHECK(pb2_stream_sync(md->stream()));
+                                    v->DeviceMask(), flags.get<int32_t>() + iv * nb, md->stream()));
+  }
+  PB2_CHECK(pb2_memcpy_d2h(quiet.data(), flags.get(), need, md->stream()));
+  PB2_CHECK(pb2_stream_sync(md->stream()));
+  for (size_t iv = 0; iv < vars.size(); ++iv) {
+    Variable *v = vars[iv];
     for (int b = 0; b < nb; ++b) {
       if (!v->IsAllocated(b)) continue;
       int &counter = v->dealloc_count(b);
-      counter = quiet[b] ? counter + 1 : 0;
+      counter = quiet[iv * nb + b] ? counter + 1 : 0;
       if (counter > pm->sparse_config.deallocation_count) {
         counter = 0;
         pm->DeallocateSparse(v->label(), md->GetBlock(b)->lid);
