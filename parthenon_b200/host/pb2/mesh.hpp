@@ -274,6 +274,10 @@ class Mesh {
   bool HasFineCoarseFaces() const;
   mutable int fine_coarse_faces_ = -1; // cached answer (static meshes)
 
+  // exchange plans are pure topology: containers ("base", "1", ...) that exchange the same fields
+  // over the same blocks share one (key: field signature + partition); a new block list drops them
+  std::map<std::string, std::shared_ptr<const void>> plan_cache;
+
   pb2_comm *comm = nullptr; // NCCL communicator (nranks > 1), owned by the creator
   // test knob: split this rank's blocks over `virtual_ranks` pretend devices so the
   // slab (nonlocal) path runs on one GPU (the reference tests its MPI path the same way

@@ -3,6 +3,10 @@
 // See pb2/bvals.hpp for the design and the reference files each piece replaces.
 #include "pb2/bvals.hpp"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <tuple>
 
@@ -153,10 +157,21 @@ void Rebuild(MeshData<Real> *md) {
   // the plan is pure topology: the block list and the FillGhost fields of a MeshData never
   // change during its life (a remesh builds new MeshData), so a rebuild after a sparse
   // (de)allocation reuses it — only region statuses and tables change
+  static const bool timing = std::getenv("PB2_TIME_REMESH") != nullptr;
+  const auto tr0 = std::chrono::steady_clock::now();
   if (!c.plan_built) {
-    c.plan = BuildExchangePlan(pm, md->GetBlockList(), pvars);
+    std::string key = "p" + std::to_string(md->partition_id());
+    for (const PlanVar &pv : pvars)
+      key += "|" + std::to_string(pv.ncomp) + ":" + std::to_string(static_cast<int>(pv.tt));
+    auto it = pm->plan_cache.find(key);
+    if (it == pm->plan_cache.end()) {
+      auto sp = std::make_shared<ExchangePlan>(BuildExchangePlan(pm, md->GetBlockList(), pvars));
+      it = pm->plan_cache.emplace(key, std::static_pointer_cast<const void>(sp)).first;
+    }
+    c.plan = *static_cast<const ExchangePlan *>(it->second.get());
     c.plan_built = true;
   }
+  const auto tr1 = std::chrono::steady_clock::now();
   const bool slabs = c.plan.send_elements > 0 || c.plan.recv_elements > 0;
   PARTHENON_REQUIRE(!slabs || pm->DefaultNumPartitions() == 1,
                     "inter-device halos need one MeshData per rank (parthenon/mesh/pack_size=-1)");
@@ -551,6 +566,12 @@ void Rebuild(MeshData<Real> *md) {
     PB2_CHECK(pb2_event_create(&c.sent));
   }
   c.built_generation = md->alloc_generation;
+  if (timing) {
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "rebuild %s: plan %.2f ms, tables %.2f ms (%zu local, %zu send channels)\n",
+                 md->label().c_str(), ms(tr0, tr1), ms(tr1, std::chrono::steady_clock::now()),
+                 c.plan.local.size(), c.plan.send.size());
+  }
 }
 
 inline BvarsCache &Cache(std::shared_ptr<MeshData<Real>> &md) {

@@ -310,7 +310,21 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
       }
     }
   };
-  for (auto &pmb : blocks) {
+  // Channels of different blocks are independent: built on all host threads into per-block
+  // lists that are concatenated in block order (the order of the serial loop).  Face / edge /
+  // node fields consult the lazily filled ownership cache of the mesh, so they stay serial.
+  bool all_cell = true;
+  for (const PlanVar &pv : vars) all_cell = all_cell && pv.tt == TopologicalType::Cell;
+  const int nblk = static_cast<int>(blocks.size());
+  std::vector<std::vector<Channel>> local_b(nblk);
+  std::vector<std::vector<std::pair<int, Channel>>> send_b(nblk), recv_b(nblk);
+  std::string failure;
+#pragma omp parallel for schedule(dynamic, 16) if (all_cell && nblk > 256)
+  for (int ib = 0; ib < nblk; ++ib) {
+   try {
+    const auto &pmb = blocks[ib];
+    std::vector<Channel> &local_out = local_b[ib];
+    std::vector<std::pair<int, Channel>> &send = send_b[ib], &recv = recv_b[ib];
     const int my_vr = pm->VirtualRankOf(pmb->gid);
     for (auto &nb : pmb->neighbors) {
       const int nb_vr = nb.rank == pm->my_rank ? pm->VirtualRankOf(nb.gid) : 0;
@@ -336,10 +350,7 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
           const MeshBlock *sender = pm->block_list[nb.lid].get();
           const NeighborBlock *q = MatchingNeighbor(sender, pmb->gid, nb.offsets);
           PARTHENON_REQUIRE(q != nullptr, "no matching send region for a local channel");
-          auto emit = [&](const Channel &c) {
-            plan.local_elements += c.recv_box.size() * c.ncomp;
-            plan.local.push_back(c);
-          };
+          auto emit = [&](const Channel &c) { local_out.push_back(c); };
           if (cell) {
             rc.send_box = CalcIndices(*q, sender, IndexRangeType::BoundaryInteriorSend, false);
             for (int d = 0; d < 3; ++d)
@@ -382,6 +393,19 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
         }
       }
     }
+   } catch (const std::exception &e) {
+#pragma omp critical
+    failure = e.what();
+   }
+  }
+  PARTHENON_REQUIRE(failure.empty(), failure);
+  for (int ib = 0; ib < nblk; ++ib) {
+    for (const Channel &c : local_b[ib]) {
+      plan.local_elements += c.recv_box.size() * c.ncomp;
+      plan.local.push_back(c);
+    }
+    send.insert(send.end(), send_b[ib].begin(), send_b[ib].end());
+    recv.insert(recv.end(), recv_b[ib].begin(), recv_b[ib].end());
   }
   // both sides of a peer segment order its channels by the same key, so slab offsets agree
   // without any handshake

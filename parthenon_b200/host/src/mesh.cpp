@@ -496,8 +496,12 @@ void Mesh::BuildBlockList(const BlockList_t *keep) {
   std::unordered_map<LogicalLocation, std::shared_ptr<MeshBlock>, LogicalLocationHash> old;
   if (keep)
     for (auto &pmb : *keep) old[pmb->loc] = pmb;
-  BlockList_t blocks;
-  for (int gid = nslist[rank]; gid < nslist[rank] + nblist[rank]; ++gid) {
+  // every block's geometry and neighbour search is independent of the others (the tree is only
+  // read): the rebuild after a remesh of thousands of blocks runs on all host threads
+  BlockList_t blocks(static_cast<size_t>(nblist[rank]));
+  const int gid0 = nslist[rank], gid1 = nslist[rank] + nblist[rank];
+#pragma omp parallel for schedule(static) if (gid1 - gid0 > 256)
+  for (int gid = gid0; gid < gid1; ++gid) {
     auto it = old.find(loclist[gid]);
     auto mb = it != old.end() ? it->second : std::make_shared<MeshBlock>();
     mb->gid = gid;
@@ -522,10 +526,11 @@ void Mesh::BuildBlockList(const BlockList_t *keep) {
     mb->partition = mb->lid / ps;
     mb->pack_index = mb->lid % ps;
     FindNeighbors(*mb);
-    blocks.push_back(mb);
+    blocks[gid - gid0] = mb;
   }
   block_list = std::move(blocks);
   fine_coarse_faces_ = -1;
+  plan_cache.clear();
 }
 
 Mesh::~Mesh() = default;
