@@ -429,6 +429,11 @@ typedef struct pb2_burgers_args {
    * pb2_burgers_progress_target(); the caller zeroes it before the stage.  2-D / 3-D only. */
   int32_t *progress;
   int32_t progress_blocks;
+  /* PB2_MATH_FAST, pb2_burgers_stage only.  Which direction sweeps this call runs: bit 0 = x1,
+   * bit 1 = x2, bit 2 = x3; 0 = all of them.  Lets a caller run the first sweep of a stage on the
+   * blocks whose ghost cells are complete while the inter-GPU halo of the others is still in
+   * flight, then the rest.  A stage must run its sweeps in the order x1, x2, x3 over every block. */
+  int32_t sweeps;
 } pb2_burgers_args;
 
 /* fluxes only: writes args->flux[0..ndim-1] from args->u */

@@ -79,7 +79,7 @@ class BurgersArgs(C.Structure):
                 ("beta", C.c_double), ("dt", C.c_double),
                 ("block_ids", C.c_void_p), ("num_block_ids", C.c_int32),
                 ("nbr_direct", C.c_void_p), ("progress", C.c_void_p),
-                ("progress_blocks", C.c_int32)]
+                ("progress_blocks", C.c_int32), ("sweeps", C.c_int32)]
 
 
 _lib = None

@@ -527,7 +527,11 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool g32 = geo32(g) && al16(a.u) && al16(a.base) && al16(a.out) && g.sb % 2 == 0;
   a.nbr = v1 ? nullptr : args->nbr_direct;
-  if (!v1 && g.nx[0] % 2 == 0) {
+  const int sweeps = args->sweeps ? args->sweeps : 7;
+  PB2_REQUIRE(!v1 || sweeps == 7, "PB2_SWEEP_V1 kernels run whole stages only");
+  if (!(sweeps & 1)) {
+    // x1 sweep done by an earlier call
+  } else if (!v1 && g.nx[0] % 2 == 0) {
     const int nrows = g.nx[1] * g.nx[2];
     const int warps = g.nblocks * ((nrows + kXRows - 1) / kXRows);
     const int wpc = kThreads / 32;
@@ -560,6 +564,7 @@ int launch_nc(const pb2_burgers_args *args, cudaStream_t st) {
   // y / z sweeps: chunked register march (burgers_march.cuh)
   if (!v1) {
     auto march = [&](auto kern, int dir, bool is_last) -> int {
+      if (!(sweeps & (1 << dir))) return PB2_OK;
       const int ncol = g.nx[dir == 1 ? 2 : 1] * g.nx[0];
       const int ctas = g.nblocks * ((ncol + kThreads - 1) / kThreads);
       if (is_last) last(a);

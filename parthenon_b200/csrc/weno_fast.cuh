@@ -69,12 +69,54 @@ PB2_HD bool same_sign(double a, double b) {
 #endif
 }
 
+PB2_HD int64_t dbits(double a) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(a);
+#else
+  int64_t x;
+  std::memcpy(&x, &a, 8);
+  return x;
+#endif
+}
+PB2_HD double from_dbits(int64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(x);
+#else
+  double a;
+  std::memcpy(&a, &x, 8);
+  return a;
+#endif
+}
+
 // 0.5 * mc(dm, dp) of recon.hpp:27-32 given s = dm + dp:
 //   copysign(min(|s|/4, min(|dm|, |dp|)), s) when dm and dp have the same sign, else 0
-// (exact: only powers of two are moved through the min; a zero difference gives 0 either way)
+// (exact: only powers of two are moved through the min; a zero difference gives 0 either way).
+// PB2_INT_LIMITER = 1 does it entirely on the bit patterns (magnitudes of doubles order like
+// integers, |s|/4 is an exponent decrement; |s| < 2^-1020 is flushed to 0) so that the limiter
+// costs no FP64-pipe instruction.
+// A/B on one B200 (profiles/README.md, session r02l): the integer limiter LOSES 1.2 % (the extra
+// integer instructions cost more issue slots than the three FP64 instructions they replace
+// free on the pipe), the power-of-two scaling is neutral to +0.5 %: off / on by default.
+#ifndef PB2_INT_LIMITER
+#define PB2_INT_LIMITER 0
+#endif
+#ifndef PB2_POW2_SCALE
+#define PB2_POW2_SCALE 1
+#endif
 PB2_HD double half_mc(double dm, double dp, double s) {
-  const double m = min_std(min_std(fabs(dm), fabs(dp)), 0.25 * fabs(s));
-  return same_sign(dm, dp) ? copysign(m, s) : 0.0;
+#if !PB2_INT_LIMITER
+  const double mm = min_std(min_std(fabs(dm), fabs(dp)), 0.25 * fabs(s));
+  return same_sign(dm, dp) ? copysign(mm, s) : 0.0;
+#else
+  constexpr int64_t kMag = 0x7fffffffffffffffll;
+  const int64_t bm = dbits(dm), bp = dbits(dp), bs = dbits(s);
+  const int64_t am = bm & kMag, ap = bp & kMag;
+  int64_t as = bs & kMag;
+  as = as >= (int64_t(3) << 52) ? as - (int64_t(2) << 52) : 0;
+  int64_t m = am < ap ? am : ap;
+  m = as < m ? as : m;
+  return from_dbits((bm ^ bp) >= 0 ? (m | (bs & ~kMag)) : 0);
+#endif
 }
 
 PB2_HD void Linear(const double qm, const double q0, const double qp, double &ql, double &qr) {
@@ -127,10 +169,19 @@ PB2_HD void WENO5Z_diff(const double d1, const double d2, const double d3, const
   const double b2 = fma(b, b, A2);
   const double tau5 = fabs(b2 - b0);
 
-  // r_k = (b_k + tau5) / b_k = 1 + tau5 * (product of the other two) / (b0 b1 b2)
+  // r_k = (b_k + tau5) / b_k = 1 + tau5 * (product of the other two) / (b0 b1 b2).  Everything
+  // below is homogeneous of degree 0 in (r0, r1, r2), so the division by B = b0 b1 b2 is
+  // replaced by a scaling with the power of two that brings B into [1, 2) (two multiplies and
+  // three integer operations instead of a reciprocal): r_k here is B' times the reference's ratio
   const double b01 = b0 * b1, b12 = b1 * b2, b02 = b0 * b2;
-  const double t = tau5 * rcp_fast(b01 * b2);
-  const double r0 = fma(t, b12, 1.0), r1 = fma(t, b02, 1.0), r2 = fma(t, b01, 1.0);
+  const double B = b01 * b2;
+#if PB2_POW2_SCALE
+  const double sc = from_dbits((int64_t(0x7fe) << 52) - (dbits(B) & (int64_t(0x7ff) << 52)));
+  const double t = tau5 * sc, Bs = B * sc;
+#else
+  const double t = tau5 * rcp_fast(B), Bs = 1.0;
+#endif
+  const double r0 = fma(t, b12, Bs), r1 = fma(t, b02, Bs), r2 = fma(t, b01, Bs);
 
   // SIX times (candidate value - q2): the rows of w5alpha applied to the differences have
   // small integer coefficients (short immediates, and a coefficient 1 costs no multiply)

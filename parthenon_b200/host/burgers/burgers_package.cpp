@@ -186,6 +186,7 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   if (direct) {
     a.nbr_direct = bc0.halo_nbr.get<int32_t>();
     bc.defer_local = true;
+    if (!(split && a.geom.ndim >= 2 && pkg->Param<bool>("device_progress"))) EnsureRemoteGhosts(mc0);
   } else {
     EnsureLocalGhosts(mc0);
     if (mbase != mc0) EnsureLocalGhosts(mbase);
@@ -221,8 +222,24 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
     // ONE launch per sweep over [boundary blocks, interior blocks]; the last sweep reports the
     // boundary part from inside (pb2_burgers_args::progress) and the communication stream waits
     // for that count on the device: no second set of launches with its own tail
-    a.block_ids = bc.ids_ordered.get<int32_t>();
-    a.num_block_ids = bc.n_boundary + bc.n_interior;
+    const int32_t *ordered = bc.ids_ordered.get<int32_t>();
+    const int nall = bc.n_boundary + bc.n_interior;
+    if (direct && bc0.remote_pending) {
+      // the input's inter-GPU ghosts are still being unpacked on the communication stream: the
+      // first sweep starts on the blocks that have no remote face (they read neighbours'
+      // interiors only), the compute stream waits for the unpack, then the other blocks follow
+      a.sweeps = 1;
+      a.block_ids = bc.ids_interior.get<int32_t>();
+      a.num_block_ids = bc.n_interior;
+      PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+      EnsureRemoteGhosts(mc0);
+      a.block_ids = bc.ids_boundary.get<int32_t>();
+      a.num_block_ids = bc.n_boundary;
+      PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+      a.sweeps = 6;
+    }
+    a.block_ids = ordered;
+    a.num_block_ids = nall;
     a.progress = bc.progress.get<int32_t>();
     a.progress_blocks = bc.n_boundary;
     PB2_CHECK(pb2_memset(a.progress, 0, sizeof(int32_t), mc0->stream()));
@@ -230,6 +247,9 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
     bc.early_valid = true;
     bc.progress_target = pb2_burgers_progress_target(&a.geom, bc.n_boundary);
     PB2_CHECK(pb2_burgers_stage(&a, mc0->stream()));
+    // the unpack of this stage's inter-GPU halo may run behind the exchange on the communication
+    // stream: whoever reads mc1's ghost cells next waits for it (EnsureRemoteGhosts)
+    if (direct) bc.defer_remote = true;
   } else if (split) {
     a.block_ids = bc.ids_boundary.get<int32_t>();
     a.num_block_ids = bc.n_boundary;

@@ -133,6 +133,12 @@ struct BvarsCache {
   // then skips its copy and leaves `local_ghosts_stale` set.  Anything else that reads ghost
   // cells calls EnsureLocalGhosts first (host field access, outputs, the bit-exact stage ...).
   bool defer_local = false, local_ghosts_stale = false;
+  // Deferred inter-GPU unpack: a consumer that starts a stage on the blocks WITHOUT remote faces
+  // (burgers FusedStage) lets SetBounds<nonlocal> unpack on the communication stream right
+  // behind the NCCL exchange and waits for `unpacked` only before it touches the other blocks.
+  // `defer_remote` is set by the producer; `remote_pending`: the compute stream has not waited yet
+  // (EnsureLocalGhosts makes it wait for anyone else who reads ghost cells).
+  bool defer_remote = false, remote_pending = false;
   DeviceBuffer halo_nbr;
   pb2_bnd_table *pack = nullptr, *unpack = nullptr;
   // [0]: regions whose neighbour is local, [1]: nonlocal
@@ -247,6 +253,8 @@ TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md);
 // run the deferred same-device ghost copy of md (and the physical boundary fill that follows an
 // exchange) if its ghost cells are stale; no-op otherwise
 void EnsureLocalGhosts(MeshData<Real> *md);
+// make the compute stream wait for a deferred inter-GPU unpack of md (see BvarsCache::defer_remote)
+void EnsureRemoteGhosts(MeshData<Real> *md);
 // ... of every container of the mesh
 void EnsureLocalGhosts(Mesh *pm);
 TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real>> &md,

@@ -72,6 +72,9 @@ class EvolutionDriver : public Driver {
   Real dt_init = std::numeric_limits<Real>::max(), dt_user = std::numeric_limits<Real>::max(),
        dt_force = -1.0, dt_factor = 2.0, dt_floor = std::numeric_limits<Real>::min(),
        dt_ceil = std::numeric_limits<Real>::max();
+  // "off the rails" guards of driver.cpp:243-263
+  Real dt_min = std::numeric_limits<Real>::min(), dt_max = std::numeric_limits<Real>::max();
+  int dt_min_count = 0, dt_max_count = 0, dt_min_count_max = 10, dt_max_count_max = 1;
   bool dt_init_force = false;
   int perf_cycle_offset = 0;
   std::chrono::steady_clock::time_point timer_main_;

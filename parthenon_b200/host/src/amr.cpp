@@ -255,7 +255,10 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
   for (auto &nvp : new_md->GetVariableVector()) {
     Variable &nv = *nvp;
     // the fields a remesh carries over: pmb->vars_cc_ (Independent / FillGhost cell-centred)
-    if (!(nv.IsSet(Metadata::Independent) || nv.IsSet(Metadata::FillGhost))) continue;
+    // (+ Metadata::ForceRemeshComm, mesh-amr_loadbalance.cpp:680-690)
+    if (!(nv.IsSet(Metadata::Independent) || nv.IsSet(Metadata::FillGhost) ||
+          nv.IsSet(Metadata::ForceRemeshComm)))
+      continue;
     PARTHENON_REQUIRE(!nv.metadata().IsSparse(), "sparse fields cannot be remeshed in this build");
     // blocks of face / edge / node fields that change device: the 2-GPU run of round 2 did not
     // reproduce the reference's dumps (profiles/multigpu_check_r02_n2.txt), so refuse rather

@@ -776,10 +776,20 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
     }
   }
   if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
-    PB2_CHECK(pb2_stream_wait_event(st, c.received));
-    PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(),
-                         c.sparse ? c.recv_flags.get<int32_t>() : nullptr, st));
-    PB2_CHECK(pb2_event_record(c.unpacked, st));
+    if (c.defer_remote && !pm->multilevel && !c.sparse) {
+      // unpack on the communication stream, in order behind the exchange that fills the slab;
+      // the compute stream keeps going and waits for `unpacked` when it needs these ghosts
+      c.defer_remote = false;
+      pb2_stream_t cs = pm->comm_stream;
+      PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(), nullptr, cs));
+      PB2_CHECK(pb2_event_record(c.unpacked, cs));
+      c.remote_pending = true;
+    } else {
+      PB2_CHECK(pb2_stream_wait_event(st, c.received));
+      PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(),
+                           c.sparse ? c.recv_flags.get<int32_t>() : nullptr, st));
+      PB2_CHECK(pb2_event_record(c.unpacked, st));
+    }
     c.unpacked_valid = true;
     c.elements_nonlocal = c.plan.recv_elements;
     if (pm->multilevel) {
@@ -1074,6 +1084,7 @@ TaskStatus ApplyBoundaryConditionsOnCoarseOrFineMD(std::shared_ptr<MeshData<Real
   // faces in BoundaryFace order; inner and outer slabs of one direction are disjoint, so the
   // stock conditions of a direction are one launch (boundary_conditions.cpp:47-55); user
   // conditions of that direction follow before the next direction reads their ghosts
+  if (c.has_bcs) EnsureRemoteGhosts(md.get()); // edges next to a remote face copy unpacked cells
   for (int d = 0; d < pm->ndim; ++d) {
     if (c.has_bcs) PB2_CHECK(pb2_apply_bcs(c.bc[coarse ? 1 : 0][d], md->stream()));
     for (int f = 2 * d; f < 2 * d + 2; ++f)
@@ -1085,7 +1096,15 @@ TaskStatus ApplyBoundaryConditionsMD(std::shared_ptr<MeshData<Real>> &md) {
   return ApplyBoundaryConditionsOnCoarseOrFineMD(md, false);
 }
 
+void EnsureRemoteGhosts(MeshData<Real> *md) {
+  BvarsCache &c = md->bvars();
+  if (!c.remote_pending) return;
+  PB2_CHECK(pb2_stream_wait_event(md->stream(), c.unpacked));
+  c.remote_pending = false;
+}
+
 void EnsureLocalGhosts(MeshData<Real> *md) {
+  EnsureRemoteGhosts(md);
   BvarsCache &c = md->bvars();
   if (!c.local_ghosts_stale) return;
   PARTHENON_REQUIRE(c.uniform_halo, "stale ghosts on a container without the uniform ghost fill");

@@ -62,6 +62,10 @@ EvolutionDriver::EvolutionDriver(ParameterInput *pin, ApplicationInput *app_in, 
   dt_factor = pin->GetOrAddReal("parthenon/time", "dt_factor", 2.0);
   dt_floor = pin->GetOrAddReal("parthenon/time", "dt_floor", dt_floor);
   dt_ceil = pin->GetOrAddReal("parthenon/time", "dt_ceil", dt_ceil);
+  dt_min = pin->GetOrAddReal("parthenon/time", "dt_min", dt_min);
+  dt_max = pin->GetOrAddReal("parthenon/time", "dt_max", dt_max);
+  dt_min_count_max = pin->GetOrAddInteger("parthenon/time", "dt_min_cycle_limit", 10);
+  dt_max_count_max = pin->GetOrAddInteger("parthenon/time", "dt_max_cycle_limit", 1);
   perf_cycle_offset = pin->GetOrAddInteger("parthenon/time", "perf_cycle_offset", 0);
   const std::string problem_id = pin->GetOrAddString("parthenon/job", "problem_id", "parthenon");
   for (auto &b : pin->BlockNames()) {
@@ -107,6 +111,24 @@ void EvolutionDriver::SetGlobalTimeStep() {
       PB2_CHECK(pb2_stream_sync(pmesh->stream));
     }
   }
+  // Check that we have not gone off the rails (driver.cpp:243-263)
+  if (tm.dt <= dt_min) {
+    PARTHENON_REQUIRE(++dt_min_count < dt_min_count_max,
+                      "Timesetep has fallen bellow minimum (parthenon/time/dt_min=" +
+                          std::to_string(dt_min) + ") for more than " +
+                          std::to_string(dt_min_count_max) + " steps");
+  } else {
+    dt_min_count = 0;
+  }
+  if (tm.dt >= dt_max) {
+    PARTHENON_REQUIRE(++dt_max_count < dt_max_count_max,
+                      "Timesetep has risen above maximum (parthenon/time/dt_max=" +
+                          std::to_string(dt_max) + ") for more than " +
+                          std::to_string(dt_max_count_max) + " steps");
+  } else {
+    dt_max_count = 0;
+  }
+  // after the bounds check so that a step that lands epsilon before tlim does not fail
   if (tm.time < tm.tlim && (tm.tlim - tm.time) < tm.dt) tm.dt = tm.tlim - tm.time;
 }
 
