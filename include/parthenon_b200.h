@@ -119,6 +119,19 @@ typedef struct pb2_bnd_region {
                         says whether the buffer holds data (<0: always data) */
   uint32_t status;   /* PB2_REGION_* */
   double value;      /* send: allocation threshold; recv: sparse default value */
+  /* RECEIVE regions only: the neighbour's LogicalCoordinateTransformation (trees of a forest
+   * that meet with different orientations, mesh/forest/logical_coordinate_transformation.hpp:
+   * 36-112).  If lcoord_on != 0 the buffer element of box cell (i, j, k) — start s, extent n, in
+   * the SENDER's orientation — lands at InverseTransform({i, j, k}) (:90-99):
+   *   out[d] = lcoord_flip[d] ? lcoord_ncell - 1 - in[lcoord_dir[d]] : in[lcoord_dir[d]]
+   * and is multiplied by `fac` (the sign a vector component picks up, :66-77), exactly what
+   * SetBounds does per element (boundary_communication.cpp:282-308).  lcoord_dir = |dir_connection|,
+   * lcoord_ncell = the array's extent GetDim(1) (bnd_info.cpp:297).  All zero = identity. */
+  int32_t lcoord_on;
+  int32_t lcoord_dir[3];
+  int32_t lcoord_flip[3];
+  int32_t lcoord_ncell;
+  double fac;
 } pb2_bnd_region;
 
 /* Fused same-device channel: sender box -> receiver box with no intermediate buffer

@@ -688,3 +688,20 @@ def weno5z(q):
     ql, qr = C.c_double(), C.c_double()
     lib().orc_weno5z(*[float(x) for x in q], C.byref(ql), C.byref(qr))
     return ql.value, qr.value
+
+
+def unpack_box_transformed(var, s, n, buf, dir_connection, dir_flip, ncell, fac):
+    """SetBounds of ONE box of one block's array var[ncomp][nk][nj][ni] (modified in place)
+    through a LogicalCoordinateTransformation (boundary_communication.cpp:282-308)"""
+    assert var.dtype == np.float64 and var.flags.c_contiguous and var.ndim == 4
+    ncomp, nk, nj, ni = var.shape
+    i3 = C.c_int * 3
+    b = np.ascontiguousarray(buf, dtype=np.float64)
+    L = lib()
+    L.orc_unpack_box_transformed.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, i3, i3,
+                                             C.c_int, C.c_void_p, i3, i3, C.c_int, C.c_double]
+    L.orc_unpack_box_transformed.restype = None
+    L.orc_unpack_box_transformed(var.ctypes.data, ni, ni * nj, ni * nj * nk, i3(*s), i3(*n), ncomp,
+                                 b.ctypes.data, i3(*dir_connection), i3(*[int(f) for f in dir_flip]),
+                                 ncell, float(fac))
+    return var

@@ -3579,3 +3579,35 @@ int orc_get_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* SetBounds through a LogicalCoordinateTransformation (trees of a forest that meet with
+ * different orientations): boundary_communication.cpp:282-308 with
+ * LogicalCoordinateTransformation::InverseTransform(std::array<int,3>)
+ * (mesh/forest/logical_coordinate_transformation.hpp:90-99):
+ *   for every box cell (i, j, k) in buffer order (i fastest, then j, k, component slowest)
+ *     out[dir] = dir_flip[dir] ? ncell - 1 - in[|dir_connection[dir]|] : in[...]
+ *     var(c, out[2], out[1], out[0]) = fac * buf[m]
+ * var: one block's array [ncomp][nk][nj][ni] given by its strides; s / n: box start / extent.
+ * The reference has no test or fixture for this kernel other than example/boundary_exchange
+ * (HDF5 gold file, not in the tree): this restatement is pinned by its properties only
+ * (identity = plain unpack, a flip applied twice, an axis permutation and its inverse). */
+void orc_unpack_box_transformed(double *var, int64_t stride_j, int64_t stride_k, int64_t stride_c,
+                                const int s[3], const int n[3], int ncomp, const double *buf,
+                                const int dir_connection[3], const int dir_flip[3], int ncell,
+                                double fac) {
+  int64_t m = 0;
+  for (int c = 0; c < ncomp; ++c)
+    for (int k = 0; k < n[2]; ++k)
+      for (int j = 0; j < n[1]; ++j)
+        for (int i = 0; i < n[0]; ++i, ++m) {
+          const int in[3] = {s[0] + i, s[1] + j, s[2] + k};
+          int out[3];
+          for (int dir = 0; dir < 3; ++dir) {
+            const int indir = abs(dir_connection[dir]);
+            out[dir] = dir_flip[dir] ? ncell - 1 - in[indir] : in[indir];
+          }
+          var[(int64_t)c * stride_c + (int64_t)out[2] * stride_k + (int64_t)out[1] * stride_j +
+              out[0]] = fac * buf[m];
+        }
+}

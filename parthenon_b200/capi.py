@@ -24,7 +24,9 @@ class BndRegion(C.Structure):
     _fields_ = [("var", C.c_void_p), ("buf_off", C.c_int64), ("s", C.c_int32 * 3),
                 ("n", C.c_int32 * 3), ("ncomp", C.c_int32), ("stride_j", C.c_int32),
                 ("stride_k", C.c_int32), ("stride_c", C.c_int32), ("flag_slot", C.c_int32),
-                ("status", C.c_uint32), ("value", C.c_double)]
+                ("status", C.c_uint32), ("value", C.c_double),
+                ("lcoord_on", C.c_int32), ("lcoord_dir", C.c_int32 * 3),
+                ("lcoord_flip", C.c_int32 * 3), ("lcoord_ncell", C.c_int32), ("fac", C.c_double)]
 
 
 class CopyRegion(C.Structure):

@@ -120,6 +120,32 @@ __device__ __forceinline__ void unpack_chunk(const DevRegion &r, uint32_t first,
   }
 }
 
+// ... through the neighbour tree's LogicalCoordinateTransformation: the box is enumerated in
+// the sender's orientation, every element goes to InverseTransform({i, j, k}) times `fac`
+// (boundary_communication.cpp:282-308, logical_coordinate_transformation.hpp:90-99).  Scalar
+// accesses: a permuted box is not contiguous along i.
+__device__ __forceinline__ void unpack_chunk_transformed(const DevRegion &r, uint32_t first,
+                                                         const double *buf, bool has_data) {
+  const double *in = buf + r.buf_off;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const uint32_t v = first + u * kThreads + threadIdx.x;
+    if (v < r.total_vec) {
+      const double x = has_data ? r.fac * __ldcs(in + v) : r.value;
+      uint32_t c, k, j, i;
+      decompose(r, v, c, k, j, i);
+      const int lin[3] = {r.s[0] + (int)i, r.s[1] + (int)j, r.s[2] + (int)k};
+      int out[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int q = lin[r.tr_dir[d]];
+        out[d] = r.tr_flip[d] ? r.tr_ncell - 1 - q : q;
+      }
+      r.var[(int64_t)c * r.sc + (int64_t)out[2] * r.sk + (int64_t)out[1] * r.sj + out[0]] = x;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
     unpack_kernel(const DevRegion *__restrict__ regions, const Chunk *__restrict__ chunks,
                   const double *__restrict__ buf, const int32_t *__restrict__ data_flags) {
@@ -129,7 +155,9 @@ __global__ void __launch_bounds__(kThreads)
   if (!(r.status & PB2_REGION_ALLOCATED)) return; // :290,:311
   bool has_data = (r.status & PB2_REGION_BUF_ALLOCATED) != 0;
   if (data_flags != nullptr && r.flag_slot >= 0) has_data = data_flags[r.flag_slot] != 0;
-  if (r.vec == 2)
+  if (r.tr_on)
+    unpack_chunk_transformed(r, ch.first_vec, buf, has_data);
+  else if (r.vec == 2)
     unpack_chunk<2>(r, ch.first_vec, buf, has_data);
   else
     unpack_chunk<1>(r, ch.first_vec, buf, has_data);
@@ -356,7 +384,20 @@ int pb2_bnd_table_create(pb2_bnd_table **table, const pb2_bnd_region *regions, i
     d.sc = a.stride_c;
     const bool v2 = (a.n[0] % 2 == 0) && (a.s[0] % 2 == 0) && (a.stride_j % 2 == 0) &&
                     (a.stride_k % 2 == 0) && (a.stride_c % 2 == 0) && (a.buf_off % 2 == 0) &&
-                    aligned16(a.var);
+                    aligned16(a.var) && !a.lcoord_on;
+    if (a.lcoord_on) {
+      bool used[3] = {false, false, false};
+      for (int q = 0; q < 3; ++q) {
+        PB2_REQUIRE(a.lcoord_dir[q] >= 0 && a.lcoord_dir[q] < 3 && !used[a.lcoord_dir[q]],
+                    "lcoord_dir must be a permutation of 0, 1, 2");
+        used[a.lcoord_dir[q]] = true;
+        d.tr_dir[q] = a.lcoord_dir[q];
+        d.tr_flip[q] = a.lcoord_flip[q] != 0;
+      }
+      d.tr_on = 1;
+      d.tr_ncell = a.lcoord_ncell;
+      d.fac = a.fac;
+    }
     d.vec = v2 ? 2 : 1;
     d.dni.init(static_cast<uint32_t>(a.n[0] / (int)d.vec > 0 ? a.n[0] / (int)d.vec : 1));
     d.dnj.init(static_cast<uint32_t>(a.n[1] > 0 ? a.n[1] : 1));

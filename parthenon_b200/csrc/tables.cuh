@@ -24,6 +24,9 @@ struct DevRegion {
   uint32_t status;
   double value;
   double default_value;
+  // unpack through a LogicalCoordinateTransformation (pb2_bnd_region::lcoord_*)
+  int32_t tr_on, tr_dir[3], tr_flip[3], tr_ncell;
+  double fac;
 };
 
 struct Chunk {

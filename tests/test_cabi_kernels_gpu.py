@@ -67,6 +67,52 @@ def test_pack_unpack_copy_uniform(ndim, nx, ng, nrb, ncomp):
     assert np.array_equal(Ud3.cpu().numpy(), Uref)
 
 
+def test_unpack_through_logical_coordinate_transformation():
+    """pb2_unpack of regions that carry a neighbour tree's LogicalCoordinateTransformation
+    (boundary_communication.cpp:282-308): every axis permutation x flip combination, two boxes
+    per table (one of them with a sign factor), against the oracle's restatement, bit for bit;
+    a region without a transformation in the same table still takes the vector path"""
+    import itertools
+    rng = np.random.default_rng(21)
+    n, ncomp = 12, 3
+    s1, e1 = (2, 3, 1), (5, 4, 6)
+    s2, e2 = (0, 2, 4), (4, 6, 2)
+    for perm in itertools.permutations(range(3)):
+        for flip in itertools.product((0, 1), repeat=3):
+            U = rng.standard_normal((3, ncomp, n, n, n))
+            n1, n2 = ncomp * int(np.prod(e1)), ncomp * int(np.prod(e2))
+            buf = rng.standard_normal(n1 + n2 + n2)
+            ref = U.copy()
+            oracle.unpack_box_transformed(ref[0], s1, e1, buf[:n1], perm, flip, n, 1.0)
+            oracle.unpack_box_transformed(ref[1], s2, e2, buf[n1:n1 + n2], perm, flip, n, -1.0)
+            ref[2][:, s2[2]:s2[2] + e2[2], s2[1]:s2[1] + e2[1], s2[0]:s2[0] + e2[0]] = \
+                buf[n1 + n2:].reshape(ncomp, e2[2], e2[1], e2[0])
+            Ud = torch.from_numpy(U).to(DEV)
+            regs = []
+            for b, (s, e, off, fac, on) in enumerate([(s1, e1, 0, 1.0, 1), (s2, e2, n1, -1.0, 1),
+                                                      (s2, e2, n1 + n2, 1.0, 0)]):
+                r = capi.BndRegion()
+                r.var = Ud.data_ptr() + 8 * b * ncomp * n * n * n
+                r.buf_off = off
+                r.s[:] = s
+                r.n[:] = e
+                r.ncomp = ncomp
+                r.stride_j, r.stride_k, r.stride_c = n, n * n, n * n * n
+                r.flag_slot = -1
+                r.status = capi.REGION_ALLOCATED | capi.REGION_BUF_ALLOCATED
+                r.lcoord_on = on
+                r.lcoord_dir[:] = perm
+                r.lcoord_flip[:] = flip
+                r.lcoord_ncell = n
+                r.fac = fac
+                regs.append(r)
+            t = capi.Table(regs, "bnd")
+            bd = torch.from_numpy(buf).to(DEV)
+            capi.check(capi.lib().pb2_unpack(t.h, bd.data_ptr(), None, None))
+            torch.cuda.synchronize()
+            assert np.array_equal(Ud.cpu().numpy(), ref), (perm, flip)
+
+
 def test_halo_uniform_skips_missing_neighbours():
     """ghosts whose owner is not on this device (table entry < 0) are left untouched — they
     belong to pb2_unpack — while every other ghost is filled"""
