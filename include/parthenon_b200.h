@@ -492,6 +492,44 @@ int pb2_comm_allreduce_sum(pb2_comm *comm, double *dev_values, int64_t n, pb2_st
  * completed (an all-reduce followed by a stream synchronisation) */
 int pb2_comm_barrier(pb2_comm *comm, pb2_stream_t stream);
 
+/* ---- peer push: the inter-GPU halo without slabs, NCCL or an unpack ---------------------------
+ * CommBuffer's Send / TryReceive (utils/communication_buffer.hpp:209-406) for GPUs of one
+ * NVLink / NVSwitch domain: the SENDER's copy kernel stores each region straight into the ghost
+ * cells of the receiving block in the peer's memory (the peer's field slab is mapped into this
+ * process through CUDA IPC) and the last thread block of the launch raises an arrival flag in
+ * the peer's memory; the receiver only waits for its flags.  One launch replaces pack ->
+ * ncclSend / ncclRecv -> unpack, and the transfer overlaps whatever else runs.
+ *
+ * Flags: every rank owns int32 flags[2][nranks] in device memory (zeroed), mapped by its peers:
+ *   flags[0][p] = s : rank p is ready for exchange number s — nothing on p reads the ghost cells
+ *                     of exchange s - 1 any more, they may be overwritten (receiver -> sender);
+ *   flags[1][p] = s : the halo of exchange s from rank p has landed (sender -> receiver).
+ * Exchange numbers grow by one per exchange of a container, the same on every rank. */
+typedef struct pb2_ipc_handle {
+  uint8_t bytes[64]; /* cudaIpcMemHandle_t of the allocation that holds the pointer */
+  int64_t offset;    /* of the pointer inside that allocation, in bytes */
+} pb2_ipc_handle;
+/* handle of device memory of THIS process (memory from pb2_malloc), to be sent to a peer */
+int pb2_ipc_export(const void *ptr, pb2_ipc_handle *handle);
+/* map a peer's memory into this process (peer access is enabled on demand); mappings are cached
+ * per allocation and reference counted, pb2_ipc_close drops one reference */
+int pb2_ipc_open(const pb2_ipc_handle *handle, void **ptr);
+int pb2_ipc_close(const pb2_ipc_handle *handle);
+/* Step 1 on `stream`: tell every peer "ready for exchange seq" (peer_flags[i][0 * nranks + me] =
+ * seq) and wait until every peer said the same to us (my_flags[0 * nranks + peers[i]] >= seq).
+ * peer_flags: DEVICE array of npeers pointers to the peers' flag arrays; peers: DEVICE array of
+ * their ranks.  One small kernel. */
+int pb2_peer_handshake(int32_t *const *peer_flags, const int32_t *my_flags, const int32_t *peers,
+                       int npeers, int me, int nranks, int32_t seq, pb2_stream_t stream);
+/* Step 2: pb2_copy whose destinations may lie in peer memory; when the last thread block of the
+ * launch has stored its part (system-scope fence), peer_flags[i][1 * nranks + me] = seq for every
+ * peer.  `counter`: one zeroed device int32 owned by the caller (left at zero). */
+int pb2_copy_signal(const pb2_bnd_table *table, int32_t *counter, int32_t *const *peer_flags,
+                    int npeers, int me, int nranks, int32_t seq, pb2_stream_t stream);
+/* Step 3 (receiver) on `stream`: wait until my_flags[1 * nranks + peers[i]] >= seq for all i */
+int pb2_peer_wait(const int32_t *my_flags, const int32_t *peers, int npeers, int nranks,
+                  int32_t seq, pb2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,49 @@ struct pb2_comm {
   double *barrier_scratch = nullptr; // one device double of this communicator's device
 };
 
+// ---- peer push (include/parthenon_b200.h): CUDA IPC mappings and the flag kernels --------------
+#include <map>
+#include <mutex>
+
+namespace pb2 {
+struct IpcMapping {
+  void *base = nullptr;
+  int refs = 0;
+};
+static std::mutex g_ipc_mutex;
+static std::map<std::string, IpcMapping> g_ipc_map; // key: the 64 handle bytes
+
+// thread i: "ready for exchange seq" into peer i's flags, then wait for peer i's own ready flag
+__global__ void peer_handshake_kernel(int32_t *const *__restrict__ peer_flags,
+                                      const int32_t *my_flags, const int32_t *__restrict__ peers,
+                                      int npeers, int me, int32_t seq) {
+  const int i = threadIdx.x;
+  if (i >= npeers) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile int32_t *>(peer_flags[i] + me) = seq;
+  const volatile int32_t *f = my_flags + peers[i];
+  long long spins = 0;
+  while (*f < seq) {
+    __nanosleep(200);
+    if (++spins > 100000000ll) break; // ~20 s: never hang the device on a lost peer
+  }
+  __threadfence_system();
+}
+
+__global__ void peer_wait_kernel(const int32_t *my_flags, const int32_t *__restrict__ peers,
+                                 int npeers, int32_t seq) {
+  const int i = threadIdx.x;
+  if (i >= npeers) return;
+  const volatile int32_t *f = my_flags + peers[i];
+  long long spins = 0;
+  while (*f < seq) {
+    __nanosleep(200);
+    if (++spins > 100000000ll) break;
+  }
+  __threadfence_system();
+}
+} // namespace pb2
+
 using namespace pb2;
 
 extern "C" {
@@ -178,6 +221,89 @@ int pb2_comm_barrier(pb2_comm *comm, pb2_stream_t stream) {
                                   kNcclMin, comm->comm, as_stream(stream)));
   // a barrier for the HOST: every rank's work enqueued before it on `stream` has completed
   PB2_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+  return PB2_OK;
+}
+
+int pb2_ipc_export(const void *ptr, pb2_ipc_handle *handle) {
+  PB2_REQUIRE(ptr && handle, "bad arguments");
+  if (int rc = require_device()) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(handle->bytes), "handle size");
+  cudaIpcMemHandle_t h;
+  PB2_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+  memcpy(handle->bytes, &h, sizeof(h));
+  // the handle names the whole allocation: find the pointer's offset inside it
+  typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  PB2_CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  PB2_REQUIRE(fn != nullptr, "cuMemGetAddressRange is not available");
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int rc = reinterpret_cast<range_fn>(fn)(&base, &size,
+                                                reinterpret_cast<unsigned long long>(ptr));
+  PB2_REQUIRE(rc == 0, "cuMemGetAddressRange failed");
+  handle->offset = static_cast<int64_t>(reinterpret_cast<unsigned long long>(ptr) - base);
+  return PB2_OK;
+}
+
+int pb2_ipc_open(const pb2_ipc_handle *handle, void **ptr) {
+  PB2_REQUIRE(handle && ptr, "bad arguments");
+  if (int rc = require_device()) return rc;
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  const std::string key(reinterpret_cast<const char *>(handle->bytes), sizeof(handle->bytes));
+  IpcMapping &m = g_ipc_map[key];
+  if (m.refs == 0) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof(h));
+    void *base = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      g_ipc_map.erase(key);
+      (void)cudaGetLastError();
+      set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+      return PB2_ERR_CUDA;
+    }
+    m.base = base;
+  }
+  m.refs++;
+  *ptr = static_cast<char *>(m.base) + handle->offset;
+  return PB2_OK;
+}
+
+int pb2_ipc_close(const pb2_ipc_handle *handle) {
+  PB2_REQUIRE(handle, "bad arguments");
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  const std::string key(reinterpret_cast<const char *>(handle->bytes), sizeof(handle->bytes));
+  auto it = g_ipc_map.find(key);
+  if (it == g_ipc_map.end()) return PB2_OK;
+  if (--it->second.refs <= 0) {
+    PB2_CUDA_CHECK(cudaIpcCloseMemHandle(it->second.base));
+    g_ipc_map.erase(it);
+  }
+  return PB2_OK;
+}
+
+int pb2_peer_handshake(int32_t *const *peer_flags, const int32_t *my_flags, const int32_t *peers,
+                       int npeers, int me, int nranks, int32_t seq, pb2_stream_t stream) {
+  PB2_REQUIRE(npeers >= 0 && npeers <= 1024 && me >= 0 && me < nranks, "bad arguments");
+  if (npeers == 0) return PB2_OK;
+  PB2_REQUIRE(peer_flags && my_flags && peers, "null argument");
+  if (int rc = require_device()) return rc;
+  peer_handshake_kernel<<<1, ((npeers + 31) / 32) * 32, 0, as_stream(stream)>>>(
+      peer_flags, my_flags, peers, npeers, me, seq);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_peer_wait(const int32_t *my_flags, const int32_t *peers, int npeers, int nranks,
+                  int32_t seq, pb2_stream_t stream) {
+  PB2_REQUIRE(npeers >= 0 && npeers <= 1024 && nranks >= 1, "bad arguments");
+  if (npeers == 0) return PB2_OK;
+  PB2_REQUIRE(my_flags && peers, "null argument");
+  if (int rc = require_device()) return rc;
+  peer_wait_kernel<<<1, ((npeers + 31) / 32) * 32, 0, as_stream(stream)>>>(my_flags + nranks, peers,
+                                                                         npeers, seq);
+  PB2_LAUNCH_CHECK();
   return PB2_OK;
 }
 

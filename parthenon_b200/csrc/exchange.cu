@@ -227,6 +227,36 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 
+// ---- peer push: copy whose destinations lie in the memory of other GPUs, with arrival flags ---
+// Same chunks as copy_kernel<0>.  Every thread fences its stores at system scope; the thread
+// block that finishes last (device counter) writes the exchange number into the arrival flag of
+// every peer, so a peer that sees its flag also sees the ghost cells (threadFenceReduction
+// pattern across NVLink).
+__global__ void __launch_bounds__(kThreads)
+    copy_signal_kernel(const DevRegion *__restrict__ regions, const Chunk *__restrict__ chunks,
+                       int32_t *counter, int32_t *const *__restrict__ peer_flags, int npeers,
+                       int slot, int32_t seq) {
+  __shared__ int s_last;
+  const Chunk ch = chunks[blockIdx.x];
+  const DevRegion &r = regions[ch.region];
+  if (!(r.status & PB2_REGION_SAME_TO_SAME)) {
+    if (r.vec == 2)
+      copy_chunk<2, 0>(r, ch.first_vec, nullptr);
+    else
+      copy_chunk<1, 0>(r, ch.first_vec, nullptr);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  for (int p = threadIdx.x; p < npeers; p += kThreads)
+    *reinterpret_cast<volatile int32_t *>(peer_flags[p] + slot) = seq;
+  if (threadIdx.x == 0) *counter = 0;
+}
+
+
 // ---- uniform meshes: descriptor-free ghost fill ---------------------------------------------
 // One CTA per (block, component, part of the ghost shell).  The shell is enumerated as
 //   [low k planes][high k planes][per interior plane: low j rows, high j rows, x pieces]
@@ -496,6 +526,20 @@ int pb2_copy(const pb2_bnd_table *table, int32_t *nonzero_flags, pb2_stream_t st
   ProfScope prof(K_COPY, as_stream(stream), static_cast<double>(table->elements));
   copy_kernel<0><<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
       table->d_regions, table->d_chunks, nonzero_flags);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_copy_signal(const pb2_bnd_table *table, int32_t *counter, int32_t *const *peer_flags,
+                    int npeers, int me, int nranks, int32_t seq, pb2_stream_t stream) {
+  PB2_REQUIRE(table && table->kind == kCopy, "copy_signal needs a copy table");
+  PB2_REQUIRE(counter && (peer_flags || npeers == 0) && npeers >= 0 && me >= 0 && me < nranks,
+              "bad arguments");
+  PB2_REQUIRE(table->nchunks > 0 || npeers == 0, "peers to signal but nothing to copy");
+  if (table->nchunks == 0) return PB2_OK;
+  ProfScope prof(K_COPY, as_stream(stream), static_cast<double>(table->elements));
+  copy_signal_kernel<<<static_cast<unsigned>(table->nchunks), kThreads, 0, as_stream(stream)>>>(
+      table->d_regions, table->d_chunks, counter, peer_flags, npeers, nranks + me, seq);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

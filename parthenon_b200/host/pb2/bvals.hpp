@@ -152,6 +152,16 @@ struct BvarsCache {
   pb2_bnd_table *te_internal[2] = {nullptr, nullptr};
   pb2_bnd_table *te_toth_roe[2] = {nullptr, nullptr}; // ProlongateInternalTothAndRoe (faces)
   DeviceBuffer send_slab, recv_slab;
+  // Peer push (include/parthenon_b200.h "peer push"): on uniform meshes with dense fields the
+  // inter-GPU halo is ONE copy launch whose destinations are the ghost cells in the peers'
+  // memory (field slabs mapped through CUDA IPC), with ready / arrival flags instead of NCCL
+  // send / recv — no slabs, no unpack.  push_peers: the ranks this MeshData exchanges with.
+  bool push_mode = false;
+  pb2_bnd_table *push = nullptr;
+  DeviceBuffer push_flags, push_counter, push_peer_flags, push_peer_ids;
+  std::vector<pb2_ipc_handle> push_opened; // mappings this cache holds a reference to
+  int push_npeers = 0;
+  int32_t push_seq = 0;
   pb2_event_t packed = nullptr, received = nullptr, sent = nullptr;
   bool nonlocal_in_flight = false;
   // Overlap of inter-GPU halos with interior work (uniform meshes): blocks with a nonlocal

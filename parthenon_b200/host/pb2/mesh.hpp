@@ -286,6 +286,10 @@ class Mesh {
   // test knob (pb2/table_halo): force the general region-table path for local channels even on
   // uniform meshes, where the descriptor-free pb2_halo_copy_uniform would be used
   bool table_halo = false;
+  // pb2/peer_push (default: on for more than one rank): inter-GPU halos of uniform meshes with
+  // dense fields are stored straight into the peers' ghost cells (BvarsCache::push_mode); false
+  // keeps the slab + NCCL send / recv path.  With virtual ranks it must be asked for explicitly.
+  bool peer_push = true;
   // (pb2/unverified_sparse_multilevel: knob of round 1, when sparse fields on statically refined
   // meshes had not been run on a device yet; they are on by default now, the knob is ignored)
   bool unverified_sparse_multilevel = false;

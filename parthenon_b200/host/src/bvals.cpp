@@ -35,6 +35,11 @@ void BvarsCache::Clear() {
       prolongate[c][o] = nullptr;
     }
   }
+  pb2_bnd_table_destroy(push);
+  push = nullptr;
+  for (const pb2_ipc_handle &h : push_opened) pb2_ipc_close(&h);
+  push_opened.clear();
+  push_mode = false;
   pb2_bnd_table_destroy(copy_local);
   pb2_bnd_table_destroy(pack);
   pb2_bnd_table_destroy(unpack);
@@ -141,6 +146,131 @@ pb2_bc_region MakeBcRegion(Variable &v, const MeshBlock *pmb, int face, int type
   r.flip_mask = v.IsSet(Metadata::Vector) && d < r.ncomp ? (1u << d) : 0u;
   return r;
 }
+
+namespace {
+// Peer push tables of a MeshData (BvarsCache::push_mode): every rank publishes CUDA IPC handles of
+// its FillGhost field slabs and of its flag array, maps those of the ranks it exchanges with and
+// turns its send channels into copy regions whose destination is the receiving block's ghost box
+// in the peer's slab.  Collective over the ranks (every rank rebuilds a container's cache at the
+// same point of the program); if any rank cannot map a peer, all fall back to slabs + NCCL.
+void BuildPeerPush(MeshData<Real> *md, BvarsCache &c) {
+  Mesh *pm = md->GetMeshPointer();
+  pb2_stream_t st = md->stream();
+  const int R = pm->nranks, me = pm->my_rank;
+  const bool real = R > 1;
+  const int nv = static_cast<int>(c.vars.size());
+  if (!c.push_flags) {
+    c.push_flags.Allocate(sizeof(int32_t) * 2 * R, st);
+    c.push_counter.Allocate(sizeof(int32_t), st);
+    c.push_seq = 0;
+    PB2_CHECK(pb2_stream_sync(st));
+  }
+  // ranks this MeshData exchanges with (virtual ranks: the device itself)
+  std::vector<int32_t> peers;
+  if (real) {
+    std::vector<char> is_peer(R, 0);
+    for (const Channel &ch : c.plan.send) is_peer[ch.receiver_rank] = 1;
+    for (const Channel &ch : c.plan.recv) is_peer[ch.sender_rank] = 1;
+    for (int p = 0; p < R; ++p)
+      if (is_peer[p] && p != me) peers.push_back(p);
+  } else {
+    peers.push_back(0);
+  }
+  // all-gather of (nv + 1) handles per rank, one byte per Real through the sum all-reduce
+  constexpr int HB = static_cast<int>(sizeof(pb2_ipc_handle));
+  std::vector<pb2_ipc_handle> mine(nv + 1), all(static_cast<size_t>(R) * (nv + 1));
+  std::vector<std::vector<Real *>> peer_var(R, std::vector<Real *>(nv, nullptr));
+  std::vector<int32_t *> peer_flags(R, nullptr);
+  int failed = 0;
+  if (real) {
+    for (int iv = 0; iv < nv && !failed; ++iv)
+      failed = pb2_ipc_export(c.vars[iv]->data(), &mine[iv]) != PB2_OK;
+    if (!failed) failed = pb2_ipc_export(c.push_flags.get(), &mine[nv]) != PB2_OK;
+    std::vector<Real> wire(static_cast<size_t>(R) * (nv + 1) * HB, 0.0);
+    if (!failed) {
+      const unsigned char *b = reinterpret_cast<const unsigned char *>(mine.data());
+      for (size_t i = 0; i < static_cast<size_t>(nv + 1) * HB; ++i)
+        wire[static_cast<size_t>(me) * (nv + 1) * HB + i] = b[i];
+    }
+    pm->AllReduceSum(wire);
+    unsigned char *a = reinterpret_cast<unsigned char *>(all.data());
+    for (size_t i = 0; i < wire.size(); ++i) a[i] = static_cast<unsigned char>(wire[i]);
+    for (int p : peers) {
+      for (int iv = 0; iv <= nv && !failed; ++iv) {
+        const pb2_ipc_handle &h = all[static_cast<size_t>(p) * (nv + 1) + iv];
+        void *ptr = nullptr;
+        if (pb2_ipc_open(&h, &ptr) != PB2_OK) {
+          failed = 1;
+          break;
+        }
+        c.push_opened.push_back(h);
+        if (iv < nv)
+          peer_var[p][iv] = static_cast<Real *>(ptr);
+        else
+          peer_flags[p] = static_cast<int32_t *>(ptr);
+      }
+    }
+    std::vector<Real> nfail(1, static_cast<Real>(failed));
+    pm->AllReduceSum(nfail);
+    if (nfail[0] > 0.0) {
+      for (const pb2_ipc_handle &h : c.push_opened) pb2_ipc_close(&h);
+      c.push_opened.clear();
+      if (me == 0)
+        std::fprintf(stderr, "[pb2] peer push unavailable (%s); inter-GPU halos use slabs + NCCL\n",
+                     pb2_last_error());
+      return;
+    }
+  } else {
+    for (int iv = 0; iv < nv; ++iv) peer_var[0][iv] = c.vars[iv]->data();
+    peer_flags[0] = c.push_flags.get<int32_t>();
+  }
+  std::vector<pb2_copy_region> regs;
+  regs.reserve(c.plan.send.size());
+  for (const Channel &ch : c.plan.send) {
+    PARTHENON_REQUIRE(!ch.send_coarse && !ch.recv_coarse, "peer push is for uniform meshes");
+    const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
+    Variable &v = *c.vars[ch.var];
+    const int rrank = real ? ch.receiver_rank : 0;
+    const int64_t rindex = real ? ch.receiver_gid - pm->nslist[ch.receiver_rank]
+                                : pm->block_list[pm->GetLid(ch.receiver_gid)]->pack_index;
+    pb2_copy_region r{};
+    r.src = v.data() + sb->pack_index * v.block_stride + ch.comp0 * v.comp_stride;
+    r.dst = peer_var[rrank][ch.var] + rindex * v.block_stride + ch.comp0 * v.comp_stride;
+    r.src_stride_j = r.dst_stride_j = v.ni;
+    r.src_stride_k = r.dst_stride_k = v.ni * v.nj;
+    r.src_stride_c = r.dst_stride_c = static_cast<int32_t>(v.comp_stride);
+    // the receiver's box (a send channel of the plan carries only the sender's): on a uniform mesh
+    // it is CalcIndices of a block of the same shape that sees the sender at the mirrored offsets
+    NeighborBlock rev;
+    rev.loc = rev.origin_loc = sb->loc;
+    for (int d = 0; d < 3; ++d) rev.offsets[d] = -((ch.offset_index / (d == 0 ? 1 : d == 1 ? 3 : 9)) % 3 - 1);
+    const IndexBox rbox = CalcIndices(rev, sb, IndexRangeType::BoundaryExteriorRecv, false);
+    for (int d = 0; d < 3; ++d) {
+      PARTHENON_REQUIRE(rbox.n(d) == ch.send_box.n(d), "send/receive extents of a channel differ");
+      r.ss[d] = ch.send_box.s[d];
+      r.ds[d] = rbox.s[d];
+      r.n[d] = rbox.n(d);
+    }
+    r.ncomp = ch.ncomp;
+    r.flag_slot = -1;
+    r.status = PB2_REGION_ALLOCATED;
+    r.default_value = v.metadata().GetDefaultValue();
+    regs.push_back(r);
+  }
+  pb2_bnd_table_destroy(c.push);
+  c.push = nullptr;
+  PB2_CHECK(pb2_copy_table_create(&c.push, regs.data(), static_cast<int64_t>(regs.size())));
+  std::vector<int32_t *> pf;
+  for (int p : peers) pf.push_back(peer_flags[p]);
+  c.push_npeers = static_cast<int>(peers.size());
+  c.push_peer_flags.Allocate(sizeof(int32_t *) * std::max<size_t>(pf.size(), 1), st);
+  c.push_peer_ids.Allocate(sizeof(int32_t) * std::max<size_t>(peers.size(), 1), st);
+  PB2_CHECK(pb2_memcpy_h2d(c.push_peer_flags.get(), pf.data(), sizeof(int32_t *) * pf.size(), st));
+  PB2_CHECK(pb2_memcpy_h2d(c.push_peer_ids.get(), peers.data(), sizeof(int32_t) * peers.size(), st));
+  PB2_CHECK(pb2_stream_sync(st));
+  c.push_mode = true;
+}
+} // namespace
 
 namespace {
 void Rebuild(MeshData<Real> *md) {
@@ -342,12 +472,21 @@ void Rebuild(MeshData<Real> *md) {
   }
   PB2_CHECK(pb2_bnd_table_create(&c.pack, packs.data(), static_cast<int64_t>(packs.size())));
   PB2_CHECK(pb2_bnd_table_create(&c.unpack, unpacks.data(), static_cast<int64_t>(unpacks.size())));
+  // uniform meshes, dense fields: store the halo straight into the peers' ghost cells
+  // (a rebuild keeps the flag array and the exchange number: Clear() drops only the table)
+  // (cell-centred only: send boxes are interior cells and receive boxes ghost cells, so stores
+  // of one channel never touch what another channel reads; shared faces / edges / nodes of other
+  // fields are both, and need every pack to precede every unpack)
+  if (pm->peer_push && slabs && all_cell && !pm->multilevel && !pm->adaptive && !c.sparse &&
+      (pm->nranks > 1 || pm->virtual_ranks > 1)) {
+    BuildPeerPush(md, c);
+  }
   // slabs of an unchanged size survive a rebuild: allocate-on-receive rebuilds the tables
   // between the arrival of a slab and its unpack
-  if (c.plan.send_elements > 0 &&
+  if (!c.push_mode && c.plan.send_elements > 0 &&
       c.send_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.send_elements))
     c.send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.send_elements), md->stream());
-  if (c.plan.recv_elements > 0 &&
+  if (!c.push_mode && c.plan.recv_elements > 0 &&
       c.recv_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.recv_elements))
     c.recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.recv_elements), md->stream());
 
@@ -643,6 +782,22 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     // the previous exchange must have left the slabs: its sends (same stream order on cs, or
     // the `sent` event) and its unpack (`unpacked`, recorded on the compute stream)
     if (c.nonlocal_in_flight && ps == st) PB2_CHECK(pb2_stream_wait_event(st, c.sent));
+    if (c.push_mode) {
+      // peer push: tell the peers this rank's ghost cells may be overwritten, wait for the same
+      // from them, store the halo into their ghost cells and raise the arrival flags — one
+      // handshake kernel and one copy launch on `ps`; nothing to receive or unpack afterwards
+      c.push_seq++;
+      const int me = pm->nranks > 1 ? pm->my_rank : 0;
+      PB2_CHECK(pb2_peer_handshake(c.push_peer_flags.get<int32_t *>(), c.push_flags.get<int32_t>(),
+                                   c.push_peer_ids.get<int32_t>(), c.push_npeers, me, pm->nranks,
+                                   c.push_seq, ps));
+      PB2_CHECK(pb2_copy_signal(c.push, c.push_counter.get<int32_t>(),
+                                c.push_peer_flags.get<int32_t *>(), c.push_npeers, me, pm->nranks,
+                                c.push_seq, ps));
+      PB2_CHECK(pb2_event_record(c.sent, ps));
+      c.nonlocal_in_flight = true;
+      return TaskStatus::complete;
+    }
     if (c.sparse) {
       // which messages are null (:95-157): flags out of the pack, as Reals into the flag slab
       PB2_CHECK(pb2_memset(c.send_flags.get(), 0, sizeof(int32_t) * c.send_flags_h.size(), ps));
@@ -776,6 +931,21 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
     }
   }
   if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
+    if (c.push_mode) {
+      // the peers stored this halo into our ghost cells themselves: wait for their arrival flags,
+      // on the communication stream if the consumer defers (it waits for `unpacked` when it
+      // reaches the blocks with remote faces), else on the compute stream
+      const bool defer = c.defer_remote;
+      c.defer_remote = false;
+      pb2_stream_t ws = defer ? pm->comm_stream : st;
+      PB2_CHECK(pb2_peer_wait(c.push_flags.get<int32_t>(), c.push_peer_ids.get<int32_t>(),
+                              c.push_npeers, pm->nranks, c.push_seq, ws));
+      PB2_CHECK(pb2_event_record(c.unpacked, ws));
+      if (defer) c.remote_pending = true;
+      c.unpacked_valid = true;
+      c.elements_nonlocal = c.plan.recv_elements;
+      return TaskStatus::complete;
+    }
     if (c.defer_remote && !pm->multilevel && !c.sparse) {
       // unpack on the communication stream, in order behind the exchange that fills the slab;
       // the compute stream keeps going and waits for `unpacked` when it needs these ghosts

@@ -104,7 +104,12 @@ def test_sim_matches_oracle_multiblock_strict():
     B.init()
     sims = [host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True)),
             host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
-                                                        {"pb2/virtual_ranks": 3}))]
+                                                        {"pb2/virtual_ranks": 3})),
+            # ... and the peer-push form of it (the sender stores into the receiver's ghost cells
+            # and raises arrival flags; no slab, no unpack)
+            host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
+                                                        {"pb2/virtual_ranks": 3,
+                                                         "pb2/peer_push": "true"}))]
     lo, nl = sims[1].exchange_elements("base")
     assert nl > 0 and lo > 0 and lo + nl == sum(sims[0].exchange_elements("base"))
     for s in sims:
@@ -282,7 +287,7 @@ def test_lazy_local_ghosts_match_exchange_every_stage(nx, nrb):
     ref.pre_execute()
     ref.cycle(4)
     want = ref.get_field("base", "U")
-    for extra in ({}, {"pb2/virtual_ranks": 3}):
+    for extra in ({}, {"pb2/virtual_ranks": 3}, {"pb2/virtual_ranks": 3, "pb2/peer_push": "true"}):
         sim = host.Simulation(overrides=burgers_overrides(nx, nrb, 4, 8, "weno5", "fast", True, extra))
         sim.pre_execute()
         sim.cycle(2)
@@ -402,15 +407,18 @@ def test_overlapped_halo_path_is_bit_identical():
     still being advanced; the result must not differ by a single bit from the one-rank run"""
     ov1 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True)
     ov2 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True, {"pb2/virtual_ranks": 2})
-    a, b = host.Simulation(overrides=ov1), host.Simulation(overrides=ov2)
+    ov3 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True,
+                            {"pb2/virtual_ranks": 2, "pb2/peer_push": "true"})
+    a, b, p = (host.Simulation(overrides=o) for o in (ov1, ov2, ov3))
     lo, nl = b.exchange_elements("base")
     assert nl > 0 and lo > 0
-    for s in (a, b):
+    for s in (a, b, p):
         s.pre_execute()
         s.cycle(3)
-    assert a.dt == b.dt and a.time == b.time
-    assert np.array_equal(a.get_field("base", "U"), b.get_field("base", "U"))
-    assert np.array_equal(a.get_field("base", "derived"), b.get_field("base", "derived"))
+    for s in (b, p):  # p: the same overlap with the peer-push exchange instead of slabs
+        assert a.dt == s.dt and a.time == s.time
+        assert np.array_equal(a.get_field("base", "U"), s.get_field("base", "U"))
+        assert np.array_equal(a.get_field("base", "derived"), s.get_field("base", "derived"))
 
 
 @pytest.mark.parametrize("math,fused", [("strict", True), ("strict", False)])

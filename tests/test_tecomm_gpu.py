@@ -17,11 +17,13 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 FIELDS = {"face": ("U_0", 3, 2), "edge": ("U_1", 3, 1), "node": ("U_2", 1, 1)}
 
 
-@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 2}, {"pb2/virtual_ranks": 3}])
+@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 2}, {"pb2/virtual_ranks": 3},
+                                   {"pb2/virtual_ranks": 3, "pb2/peer_push": "true"}])
 @pytest.mark.parametrize("name,ndim,nx,nb,ng", H.TECOMM)
 def test_non_cell_centred_exchange_bit_exact(name, ndim, nx, nb, ng, extra):
     """extra = pb2/virtual_ranks splits the blocks of the one GPU into groups that talk through
-    the pack -> slab -> unpack path of inter-device channels instead of the fused copy"""
+    the pack -> slab -> unpack path of inter-device channels instead of the fused copy;
+    with pb2/peer_push through stores into the receiver's ghost cells + arrival flags"""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     ov = deck_overrides(ndim, (nb,) * 3, ng, (nx // nb,) * 3)
     ov.update(extra or {})
