@@ -209,6 +209,23 @@ class Mesh:
         self.dims = tuple(int(x) for x in d)    # (nk, nj, ni)
         self.cdims = tuple(int(x) for x in c)
 
+    @classmethod
+    def from_handle(cls, h, ndim=2):
+        """wrap a mesh the C oracle already built (oracle/forest.py: orc_mesh_create_custom)"""
+        self = cls.__new__(cls)
+        L = lib()
+        self.h = h
+        self.bcs = None
+        self.ndim = ndim
+        self.nblocks = L.orc_mesh_nblocks(self.h)
+        self.multilevel = bool(L.orc_mesh_multilevel(self.h))
+        d = np.zeros(3, dtype=np.int32)
+        c = np.zeros(3, dtype=np.int32)
+        L.orc_mesh_dims(self.h, _ip(d), _ip(c))
+        self.dims = tuple(int(x) for x in d)
+        self.cdims = tuple(int(x) for x in c)
+        return self
+
     def __del__(self):
         try:
             lib().orc_mesh_destroy(self.h)

@@ -31,6 +31,9 @@ typedef struct {
   Loc loc;        /* wrapped location (as stored in the tree) */
   Loc origin_loc; /* location in the frame of the owning block (may lie outside) */
   int off[3];
+  /* forests of differently oriented trees: NeighborBlock::lcoord_trans
+   * (logical_coordinate_transformation.hpp:36-112); tr_on == 0: identity */
+  int tr_on, tr_dir[3], tr_flip[3];
 } Neighbor;
 
 typedef struct {
@@ -41,6 +44,7 @@ typedef struct {
   double dx[3];            /* UniformCartesian dx_ */
   double cxmin[3];         /* UniformCartesian xmin_ (includes ghost offset) */
   double ccxmin[3], cdx[3]; /* coarse coords (uniform_cartesian.hpp:41-55) */
+  int bc[6]; /* custom (forest) meshes: MeshBlock::boundary_flag per face, 0 = none */
 } Block;
 
 struct OrcMesh {
@@ -48,6 +52,8 @@ struct OrcMesh {
   int periodic[3];
   int bc[6]; /* per mesh face (inner_x1, outer_x1, ...): 0 periodic, 1 outflow, 2 reflect */
   double xmin[3], xmax[3];
+  int custom;          /* blocks, neighbours and block boundary flags were supplied (forest) */
+  int prolong_constant; /* cell-centred prolongation is ProlongatePiecewiseConstant */
   int is[3], ie[3], n[3];    /* fine interior bounds and full extents (i,j,k order) */
   int cis[3], cie[3], cn[3]; /* coarse */
   Block *blocks;
@@ -342,6 +348,78 @@ OrcMesh *orc_mesh_create_uniform(int ndim, const int nx[3], int ng, const int nr
   return m;
 }
 
+/* A mesh given block by block (test infrastructure for forests of differently oriented
+ * trees, mesh/forest/forest.cpp:204-297): the caller — oracle/forest.py, which restates the
+ * forest topology — supplies every block's location, boundary flags and neighbour list with
+ * each neighbour's LogicalCoordinateTransformation; everything downstream (index boxes, pack,
+ * unpack, restriction, prolongation, physical boundaries) is the code pinned on single trees.
+ * blocks: nblocks x 4 ints (level, lx1, lx2, lx3) in gid order; block_bc: nblocks x 6;
+ * nnb: neighbours per block; nbs: per neighbour 18 ints
+ *   gid, level, lx[3] (as stored), origin level, origin lx[3], tr_on, tr_dir[3], tr_flip[3],
+ * and two spares, in the order the reference's FindNeighbors lists them. */
+OrcMesh *orc_mesh_create_custom(int ndim, const int nx[3], int ng, int nblocks, const int *blocks,
+                                const int *block_bc, const int *nnb, const int *nbs,
+                                int multilevel, int prolong_constant) {
+  OrcMesh *m = (OrcMesh *)calloc(1, sizeof(OrcMesh));
+  m->ndim = ndim;
+  m->ng = ng;
+  m->custom = 1;
+  m->multilevel = multilevel;
+  m->prolong_constant = prolong_constant;
+  m->nblocks = nblocks;
+  for (int d = 0; d < 3; ++d) {
+    m->nx[d] = d < ndim ? nx[d] : 1;
+    m->nrb[d] = 1;
+    m->xmin[d] = 0.0;
+    m->xmax[d] = 1.0;
+    int sym = d >= ndim;
+    m->is[d] = sym ? 0 : ng;
+    m->ie[d] = sym ? 0 : ng + m->nx[d] - 1;
+    m->n[d] = sym ? 1 : m->nx[d] + 2 * ng;
+    int cnx = sym ? 0 : (m->nx[d] / 2 > 1 ? m->nx[d] / 2 : 1);
+    m->cis[d] = sym ? 0 : ng;
+    m->cie[d] = sym ? 0 : ng + cnx - 1;
+    m->cn[d] = sym ? 1 : cnx + 2 * ng;
+  }
+  m->blocks = (Block *)calloc((size_t)nblocks, sizeof(Block));
+  const int *q = nbs;
+  for (int b = 0; b < nblocks; ++b) {
+    Block *blk = &m->blocks[b];
+    blk->loc.level = blocks[4 * b];
+    for (int d = 0; d < 3; ++d) {
+      blk->loc.lx[d] = blocks[4 * b + 1 + d];
+      blk->xmin[d] = 0.0; /* unit blocks: coordinates play no role in what this mesh is for */
+      blk->xmax[d] = 1.0;
+      blk->dx[d] = 1.0 / m->nx[d];
+      int istart = d < ndim ? ng : 0;
+      blk->cxmin[d] = -istart * blk->dx[d];
+      blk->ccxmin[d] = blk->cxmin[d] + istart * blk->dx[d] * (1 - 2);
+      blk->cdx[d] = blk->dx[d] * ((d == 0 || istart > 0) ? 2 : 1);
+    }
+    for (int f = 0; f < 6; ++f) blk->bc[f] = block_bc[6 * b + f];
+    if (nnb[b] > MAXNB) {
+      fprintf(stderr, "oracle: too many neighbors\n");
+      abort();
+    }
+    blk->nnb = nnb[b];
+    for (int n = 0; n < nnb[b]; ++n, q += 18) {
+      Neighbor *nb = &blk->nb[n];
+      nb->gid = q[0];
+      nb->loc.level = q[1];
+      nb->origin_loc.level = q[5];
+      for (int d = 0; d < 3; ++d) {
+        nb->loc.lx[d] = q[2 + d];
+        nb->origin_loc.lx[d] = q[6 + d];
+        nb->tr_dir[d] = q[10 + d];
+        nb->tr_flip[d] = q[13 + d];
+      }
+      nb->tr_on = q[9];
+      same_level_offsets(&blk->loc, &nb->origin_loc, nb->off); /* mesh-gmg.cpp:64 */
+    }
+  }
+  return m;
+}
+
 void orc_mesh_destroy(OrcMesh *m) {
   if (!m) return;
   free(m->blocks);
@@ -544,12 +622,19 @@ void orc_unpack(const OrcMesh *m, double *U, double *Uc, int ncomp, const double
     const Block *blk = &m->blocks[b];
     for (int n = 0; n < blk->nnb; ++n) {
       const Neighbor *nb = &blk->nb[n];
-      /* find the sender's matching region */
+      /* find the sender's matching region: the receive key carries the offsets transformed
+       * into the sender's frame, reversed (ReceiveKey, bvals_utils.hpp:57-67;
+       * LogicalCoordinateTransformation::Transform(CellCentOffsets),
+       * logical_coordinate_transformation.cpp:92-99) */
+      int toff[3] = {nb->off[0], nb->off[1], nb->off[2]};
+      if (nb->tr_on)
+        for (int d = 0; d < 3; ++d)
+          toff[nb->tr_dir[d]] = nb->tr_flip[d] ? -nb->off[d] : nb->off[d];
       const Block *sb = &m->blocks[nb->gid];
       int sn = -1;
       for (int q = 0; q < sb->nnb; ++q)
-        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
-            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -toff[0] &&
+            sb->nb[q].off[1] == -toff[1] && sb->nb[q].off[2] == -toff[2]) {
           sn = q;
           break;
         }
@@ -568,6 +653,39 @@ void orc_unpack(const OrcMesh *m, double *U, double *Uc, int ncomp, const double
       }
       int coarse = nb->origin_loc.level < blk->loc.level;
       const double *p = buf + buf_off[r];
+      if (nb->tr_on) {
+        /* bnd_info.cpp:216-228: the box goes to the sender's logical coordinates (Transform of
+         * both corners with ncell = var.GetDim(1), re-sorted), SetBounds walks it in buffer
+         * order and writes every element at InverseTransform (boundary_communication.cpp:
+         * 282-308; cell-centred fields: no sign factor) */
+        const int ncell = coarse ? m->cn[0] : m->n[0];
+        int ts[3], te[3];
+        for (int d = 0; d < 3; ++d) {
+          const int o = nb->tr_dir[d];
+          ts[o] = nb->tr_flip[d] ? ncell - 1 - s[d] : s[d];
+          te[o] = nb->tr_flip[d] ? ncell - 1 - e[d] : e[d];
+        }
+        for (int d = 0; d < 3; ++d)
+          if (ts[d] > te[d]) {
+            const int t = ts[d];
+            ts[d] = te[d];
+            te[d] = t;
+          }
+        for (int c = 0; c < ncomp; ++c)
+          for (int k = ts[2]; k <= te[2]; ++k)
+            for (int j = ts[1]; j <= te[1]; ++j)
+              for (int i = ts[0]; i <= te[0]; ++i) {
+                const int in[3] = {i, j, k};
+                int out[3];
+                for (int d = 0; d < 3; ++d)
+                  out[d] = nb->tr_flip[d] ? ncell - 1 - in[nb->tr_dir[d]] : in[nb->tr_dir[d]];
+                if (coarse)
+                  Uc[cidx(m, ncomp, b, c, out[2], out[1], out[0])] = *p++;
+                else
+                  U[fidx(m, ncomp, b, c, out[2], out[1], out[0])] = *p++;
+              }
+        continue;
+      }
       for (int c = 0; c < ncomp; ++c)
         for (int k = s[2]; k <= e[2]; ++k)
           for (int j = s[1]; j <= e[1]; ++j)
@@ -637,6 +755,9 @@ static void prolongate_cell(const OrcMesh *m, double *U, const double *Uc, int n
     const double fm = Uc[cidx(m, ncomp, b, c, k - o[2], j - o[1], i - o[0])];
     const double fp = Uc[cidx(m, ncomp, b, c, k + o[2], j + o[1], i + o[0])];
     g[d] = grad_minmod(fc, fm, fp, dxm, dxp);
+    /* ProlongatePiecewiseConstant = ProlongateSharedGeneral<false, true>: zero slopes
+     * (pr_ops.hpp:206-262) */
+    if (m->prolong_constant) g[d] = 0.0;
   }
   const double gx1m = g[0], gx1p = g[0], gx2m = g[1], gx2p = g[1], gx3m = g[2], gx3p = g[2];
   const double dx1fm = dxfm[0], dx1fp = dxfp[0], dx2fm = dxfm[1], dx2fp = dxfp[1],
@@ -1523,10 +1644,16 @@ static void apply_bcs_generic(const OrcMesh *m, double *A, int ncomp, int coarse
     const Block *blk = &m->blocks[b];
     for (int face = 0; face < 6; ++face) {
       const int d = face / 2, inner = (face % 2) == 0;
-      if (d >= m->ndim || m->bc[face] == 0) continue;
-      /* MeshBlock::boundary_flag: the mesh flag where the block touches the mesh boundary */
-      const long nb_d = nblocks_at(m, blk->loc.level, d);
-      if (inner ? blk->loc.lx[d] != 0 : blk->loc.lx[d] != nb_d - 1) continue;
+      int flag = m->bc[face];
+      if (m->custom) {
+        flag = blk->bc[face]; /* the block's own flags (Tree::GetBlockBCs, tree.cpp:320-332) */
+        if (d >= m->ndim || flag == 0) continue;
+      } else {
+        if (d >= m->ndim || m->bc[face] == 0) continue;
+        /* MeshBlock::boundary_flag: the mesh flag where the block touches the mesh boundary */
+        const long nb_d = nblocks_at(m, blk->loc.level, d);
+        if (inner ? blk->loc.lx[d] != 0 : blk->loc.lx[d] != nb_d - 1) continue;
+      }
       const int ref = inner ? is[d] : ie[d];
       const int offset = 2 * ref + (inner ? -1 : 1);
       int lo[3] = {0, 0, 0}, hi[3] = {nn[0] - 1, nn[1] - 1, nn[2] - 1};
@@ -1539,7 +1666,7 @@ static void apply_bcs_generic(const OrcMesh *m, double *A, int ncomp, int coarse
           for (int j = lo[1]; j <= hi[1]; ++j)
             for (int i = lo[0]; i <= hi[0]; ++i) {
               int s[3] = {i, j, k};
-              s[d] = m->bc[face] == 2 ? offset - s[d] : ref;
+              s[d] = flag == 2 ? offset - s[d] : ref;
               if (coarse)
                 A[cidx(m, ncomp, b, c, k, j, i)] = A[cidx(m, ncomp, b, c, s[2], s[1], s[0])];
               else

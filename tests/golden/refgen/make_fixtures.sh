@@ -46,6 +46,10 @@ if [ ! -x "$WORK/tecomm_dump" ] || [ "$HERE/tecomm_dump_main.cpp" -nt "$WORK/tec
   $CXX $FLAGS $INC "$HERE/tecomm_dump_main.cpp" $LIBS -o "$WORK/tecomm_dump"
 fi
 
+if [ ! -x "$WORK/forest_dump" ] || [ "$HERE/forest_dump_main.cpp" -nt "$WORK/forest_dump" ]; then
+  $CXX $FLAGS $INC "$HERE/forest_dump_main.cpp" $LIBS -o "$WORK/forest_dump"
+fi
+
 export OMP_NUM_THREADS=${OMP_NUM_THREADS:-8} OMP_PROC_BIND=false
 
 run_burgers () { # name nx nb nscal recon nlim extra...
@@ -319,3 +323,19 @@ run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4
 }
 run_hst burgers_u64_b32_s8_weno5 64 32 10
 echo "fixtures written to $OUT"
+
+# forests of differently oriented trees (ForestDefinition as in example/boundary_exchange): the
+# ghost exchange through LogicalCoordinateTransformations; variants in forest_dump_main.cpp
+run_forest () { # name variant nb ng
+  local name=$1 variant=$2 nb=$3 ng=$4
+  local d="$WORK/$name"; rm -rf "$d"; mkdir -p "$d"; cd "$d"
+  printf '<parthenon/job>\nproblem_id = forest\n<parthenon/mesh>\nrefinement = static\nnumlevel = 1\nnghost = %d\n<parthenon/meshblock>\nnx1 = %d\nnx2 = %d\nnx3 = 1\n' $ng $nb $nb > deck.pin
+  PB2_FOREST_VARIANT=$variant PB2_DUMP_PREFIX="$d/U" "$WORK/forest_dump" -i deck.pin > run.log 2>&1
+  python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
+}
+if [ -z "${SKIP_FOREST:-}" ]; then
+run_forest forest_v0_b4_g2 0 4 2
+run_forest forest_v1_b4_g2 1 4 2
+run_forest forest_v2_b8_g2 2 8 2
+run_forest forest_v3_b8_g4 3 8 4
+fi
