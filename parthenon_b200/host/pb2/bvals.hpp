@@ -156,7 +156,7 @@ struct BvarsCache {
   // inter-GPU halo is ONE copy launch whose destinations are the ghost cells in the peers'
   // memory (field slabs mapped through CUDA IPC), with ready / arrival flags instead of NCCL
   // send / recv — no slabs, no unpack.  push_peers: the ranks this MeshData exchanges with.
-  bool push_mode = false;
+  bool push_mode = false, push_direct = false;
   pb2_bnd_table *push = nullptr;
   DeviceBuffer push_flags, push_counter, push_peer_flags, push_peer_ids;
   std::vector<pb2_ipc_handle> push_opened; // mappings this cache holds a reference to

@@ -290,6 +290,9 @@ class Mesh {
   // dense fields are stored straight into the peers' ghost cells (BvarsCache::push_mode); false
   // keeps the slab + NCCL send / recv path.  With virtual ranks it must be asked for explicitly.
   bool peer_push = true;
+  // pb2/peer_push_direct: skip the receive slab too and store into the peers' ghost cells
+  // (measured slower at 8 GPUs: 32-byte x-face rows make poor NVLink packets)
+  bool peer_push_direct = false;
   // (pb2/unverified_sparse_multilevel: knob of round 1, when sparse fields on statically refined
   // meshes had not been run on a device yet; they are on by default now, the knob is ignored)
   bool unverified_sparse_multilevel = false;

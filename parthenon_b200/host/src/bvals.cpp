@@ -153,12 +153,17 @@ namespace {
 // turns its send channels into copy regions whose destination is the receiving block's ghost box
 // in the peer's slab.  Collective over the ranks (every rank rebuilds a container's cache at the
 // same point of the program); if any rank cannot map a peer, all fall back to slabs + NCCL.
-void BuildPeerPush(MeshData<Real> *md, BvarsCache &c) {
+void BuildPeerPush(MeshData<Real> *md, BvarsCache &c, bool direct) {
   Mesh *pm = md->GetMeshPointer();
   pb2_stream_t st = md->stream();
   const int R = pm->nranks, me = pm->my_rank;
   const bool real = R > 1;
-  const int nv = static_cast<int>(c.vars.size());
+  // direct: destinations are the ghost boxes in the peers' field slabs; else the peers' receive
+  // slabs (contiguous stores: full NVLink packets), which they unpack themselves
+  const int nv = direct ? static_cast<int>(c.vars.size()) : 1;
+  auto exported = [&](int iv) -> void * {
+    return direct ? static_cast<void *>(c.vars[iv]->data()) : c.recv_slab.get();
+  };
   if (!c.push_flags) {
     c.push_flags.Allocate(sizeof(int32_t) * 2 * R, st);
     c.push_counter.Allocate(sizeof(int32_t), st);
@@ -184,7 +189,7 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c) {
   int failed = 0;
   if (real) {
     for (int iv = 0; iv < nv && !failed; ++iv)
-      failed = pb2_ipc_export(c.vars[iv]->data(), &mine[iv]) != PB2_OK;
+      failed = pb2_ipc_export(exported(iv), &mine[iv]) != PB2_OK;
     if (!failed) failed = pb2_ipc_export(c.push_flags.get(), &mine[nv]) != PB2_OK;
     std::vector<Real> wire(static_cast<size_t>(R) * (nv + 1) * HB, 0.0);
     if (!failed) {
@@ -221,24 +226,63 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c) {
       return;
     }
   } else {
-    for (int iv = 0; iv < nv; ++iv) peer_var[0][iv] = c.vars[iv]->data();
+    for (int iv = 0; iv < nv; ++iv) peer_var[0][iv] = static_cast<Real *>(exported(iv));
     peer_flags[0] = c.push_flags.get<int32_t>();
+  }
+  // slab variant: where our segment starts inside each peer's receive slab (its recv_off[me])
+  std::vector<Real> peer_recv_off(static_cast<size_t>(R) * R, 0.0);
+  if (!direct && real) {
+    for (int p = 0; p < R; ++p) peer_recv_off[static_cast<size_t>(me) * R + p] = static_cast<Real>(c.plan.recv_off[p]);
+    pm->AllReduceSum(peer_recv_off);
   }
   std::vector<pb2_copy_region> regs;
   regs.reserve(c.plan.send.size());
   for (const Channel &ch : c.plan.send) {
-    PARTHENON_REQUIRE(!ch.send_coarse && !ch.recv_coarse, "peer push is for uniform meshes");
+    PARTHENON_REQUIRE(!direct || (!ch.send_coarse && !ch.recv_coarse),
+                      "direct peer push is for uniform meshes");
     const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
     Variable &v = *c.vars[ch.var];
     const int rrank = real ? ch.receiver_rank : 0;
     const int64_t rindex = real ? ch.receiver_gid - pm->nslist[ch.receiver_rank]
                                 : pm->block_list[pm->GetLid(ch.receiver_gid)]->pack_index;
     pb2_copy_region r{};
-    r.src = v.data() + sb->pack_index * v.block_stride + ch.comp0 * v.comp_stride;
+    if (ch.send_coarse) {
+      r.src = v.coarse() + sb->pack_index * v.cblock_stride + ch.comp0 * v.ccomp_stride;
+      r.src_stride_j = v.cni;
+      r.src_stride_k = v.cni * v.cnj;
+      r.src_stride_c = static_cast<int32_t>(v.ccomp_stride);
+    } else {
+      r.src = v.data() + sb->pack_index * v.block_stride + ch.comp0 * v.comp_stride;
+      r.src_stride_j = v.ni;
+      r.src_stride_k = v.ni * v.nj;
+      r.src_stride_c = static_cast<int32_t>(v.comp_stride);
+    }
+    if (!direct) {
+      // the channel's place in the receiver's slab: same offset inside the peer segment on both
+      // sides (BuildExchangePlan), the segment at the receiver's recv_off[this rank]; with
+      // virtual ranks the send and the receive slab of the device have the same layout
+      const int64_t seg0 = real ? c.plan.send_off[ch.receiver_rank] : 0;
+      const int64_t base = real ? static_cast<int64_t>(peer_recv_off[static_cast<size_t>(ch.receiver_rank) * R + me]) : 0;
+      r.dst = peer_var[rrank][0] + base + (ch.slab_off - seg0);
+      for (int d = 0; d < 3; ++d) {
+        r.ss[d] = ch.send_box.s[d];
+        r.ds[d] = 0;
+        r.n[d] = ch.send_box.n(d);
+      }
+      r.dst_stride_j = r.n[0];
+      r.dst_stride_k = r.n[0] * r.n[1];
+      r.dst_stride_c = r.n[0] * r.n[1] * r.n[2];
+      r.ncomp = ch.ncomp;
+      r.flag_slot = -1;
+      r.status = PB2_REGION_ALLOCATED;
+      r.default_value = v.metadata().GetDefaultValue();
+      regs.push_back(r);
+      continue;
+    }
     r.dst = peer_var[rrank][ch.var] + rindex * v.block_stride + ch.comp0 * v.comp_stride;
-    r.src_stride_j = r.dst_stride_j = v.ni;
-    r.src_stride_k = r.dst_stride_k = v.ni * v.nj;
-    r.src_stride_c = r.dst_stride_c = static_cast<int32_t>(v.comp_stride);
+    r.dst_stride_j = v.ni;
+    r.dst_stride_k = v.ni * v.nj;
+    r.dst_stride_c = static_cast<int32_t>(v.comp_stride);
     // the receiver's box (a send channel of the plan carries only the sender's): on a uniform mesh
     // it is CalcIndices of a block of the same shape that sees the sender at the mirrored offsets
     NeighborBlock rev;
@@ -269,6 +313,7 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c) {
   PB2_CHECK(pb2_memcpy_h2d(c.push_peer_ids.get(), peers.data(), sizeof(int32_t) * peers.size(), st));
   PB2_CHECK(pb2_stream_sync(st));
   c.push_mode = true;
+  c.push_direct = direct;
 }
 } // namespace
 
@@ -472,23 +517,24 @@ void Rebuild(MeshData<Real> *md) {
   }
   PB2_CHECK(pb2_bnd_table_create(&c.pack, packs.data(), static_cast<int64_t>(packs.size())));
   PB2_CHECK(pb2_bnd_table_create(&c.unpack, unpacks.data(), static_cast<int64_t>(unpacks.size())));
-  // uniform meshes, dense fields: store the halo straight into the peers' ghost cells
-  // (a rebuild keeps the flag array and the exchange number: Clear() drops only the table)
-  // (cell-centred only: send boxes are interior cells and receive boxes ghost cells, so stores
-  // of one channel never touch what another channel reads; shared faces / edges / nodes of other
-  // fields are both, and need every pack to precede every unpack)
-  if (pm->peer_push && slabs && all_cell && !pm->multilevel && !pm->adaptive && !c.sparse &&
-      (pm->nranks > 1 || pm->virtual_ranks > 1)) {
-    BuildPeerPush(md, c);
-  }
   // slabs of an unchanged size survive a rebuild: allocate-on-receive rebuilds the tables
   // between the arrival of a slab and its unpack
+  const bool want_push = pm->peer_push && slabs && !pm->adaptive && !c.sparse &&
+                         (pm->nranks > 1 || pm->virtual_ranks > 1);
+  // direct variant — cell-centred fields of uniform meshes only: send boxes are interior cells
+  // and receive boxes ghost cells, so stores of one channel never touch what another channel
+  // reads (shared faces / edges / nodes are both and need every pack to precede every unpack)
+  const bool want_direct = want_push && pm->peer_push_direct && all_cell && !pm->multilevel;
+  if (want_direct) BuildPeerPush(md, c, true);
   if (!c.push_mode && c.plan.send_elements > 0 &&
       c.send_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.send_elements))
     c.send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.send_elements), md->stream());
   if (!c.push_mode && c.plan.recv_elements > 0 &&
       c.recv_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.recv_elements))
     c.recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.recv_elements), md->stream());
+  // slab variant: the pack writes straight into the peers' receive slabs (no send slab needed,
+  // it is kept for the fallback), the unpack stays with the receiver
+  if (want_push && !c.push_mode && c.plan.recv_elements > 0) BuildPeerPush(md, c, false);
 
   // restriction / prolongation regions (ProResInfo::GetSend / GetSet, bnd_info.cpp:387-448),
   // split by whether the neighbour is local so the local / nonlocal task split still works
@@ -787,6 +833,9 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
       // from them, store the halo into their ghost cells and raise the arrival flags — one
       // handshake kernel and one copy launch on `ps`; nothing to receive or unpack afterwards
       c.push_seq++;
+      // "ready" below promises that our receive slab / ghost cells of the previous exchange are
+      // not in use any more: its unpack may have run on the other stream
+      if (c.unpacked_valid) PB2_CHECK(pb2_stream_wait_event(ps, c.unpacked));
       const int me = pm->nranks > 1 ? pm->my_rank : 0;
       PB2_CHECK(pb2_peer_handshake(c.push_peer_flags.get<int32_t *>(), c.push_flags.get<int32_t>(),
                                    c.push_peer_ids.get<int32_t>(), c.push_npeers, me, pm->nranks,
@@ -932,21 +981,19 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
   }
   if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
     if (c.push_mode) {
-      // the peers stored this halo into our ghost cells themselves: wait for their arrival flags,
-      // on the communication stream if the consumer defers (it waits for `unpacked` when it
-      // reaches the blocks with remote faces), else on the compute stream
+      // the peers stored this halo into our receive slab (or, direct variant, into our ghost
+      // cells) themselves: wait for their arrival flags and unpack, on the communication stream
+      // if the consumer defers (it waits for `unpacked` when it reaches the blocks with remote
+      // faces), else on the compute stream
       const bool defer = c.defer_remote;
       c.defer_remote = false;
       pb2_stream_t ws = defer ? pm->comm_stream : st;
       PB2_CHECK(pb2_peer_wait(c.push_flags.get<int32_t>(), c.push_peer_ids.get<int32_t>(),
                               c.push_npeers, pm->nranks, c.push_seq, ws));
+      if (!c.push_direct) PB2_CHECK(pb2_unpack(c.unpack, c.recv_slab.get<Real>(), nullptr, ws));
       PB2_CHECK(pb2_event_record(c.unpacked, ws));
       if (defer) c.remote_pending = true;
-      c.unpacked_valid = true;
-      c.elements_nonlocal = c.plan.recv_elements;
-      return TaskStatus::complete;
-    }
-    if (c.defer_remote && !pm->multilevel && !c.sparse) {
+    } else if (c.defer_remote && !pm->multilevel && !c.sparse) {
       // unpack on the communication stream, in order behind the exchange that fills the slab;
       // the compute stream keeps going and waits for `unpacked` when it needs these ghosts
       c.defer_remote = false;

@@ -414,6 +414,7 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &pkgs, int 
   virtual_ranks = pin->GetOrAddInteger("pb2", "virtual_ranks", 1);
   table_halo = pin->GetOrAddBoolean("pb2", "table_halo", false);
   peer_push = pin->GetOrAddBoolean("pb2", "peer_push", nranks > 1);
+  peer_push_direct = pin->GetOrAddBoolean("pb2", "peer_push_direct", false);
   unverified_sparse_multilevel = pin->GetOrAddBoolean("pb2", "unverified_sparse_multilevel", false);
   sparse_config.enabled = pin->GetOrAddBoolean("parthenon/sparse", "enable_sparse", true);
   sparse_config.allocation_threshold = pin->GetOrAddReal("parthenon/sparse", "alloc_threshold", 1e-12);

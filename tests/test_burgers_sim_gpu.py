@@ -105,11 +105,15 @@ def test_sim_matches_oracle_multiblock_strict():
     sims = [host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True)),
             host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
                                                         {"pb2/virtual_ranks": 3})),
-            # ... and the peer-push form of it (the sender stores into the receiver's ghost cells
-            # and raises arrival flags; no slab, no unpack)
+            # ... and the peer-push forms of it (the sender stores into the receiver's slab — or,
+            # direct, into its ghost cells — and raises arrival flags; no NCCL send / recv)
             host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
                                                         {"pb2/virtual_ranks": 3,
-                                                         "pb2/peer_push": "true"}))]
+                                                         "pb2/peer_push": "true"})),
+            host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
+                                                        {"pb2/virtual_ranks": 3,
+                                                         "pb2/peer_push": "true",
+                                                         "pb2/peer_push_direct": "true"}))]
     lo, nl = sims[1].exchange_elements("base")
     assert nl > 0 and lo > 0 and lo + nl == sum(sims[0].exchange_elements("base"))
     for s in sims:
@@ -139,7 +143,7 @@ def test_multilevel_exchange_matches_oracle():
     U = rng.standard_normal((m.nblocks, ncomp) + m.dims)
     Uref, Ucref = U.copy(), np.zeros((m.nblocks, ncomp) + m.cdims)
     m.exchange(Uref, Ucref, prolongate=True)
-    for extra in (None, {"pb2/virtual_ranks": 2}):
+    for extra in (None, {"pb2/virtual_ranks": 2}, {"pb2/virtual_ranks": 2, "pb2/peer_push": "true"}):
         ov = burgers_overrides(8, nrb, ng, 1, "weno5", "strict", True, extra)
         ov["parthenon/mesh/refinement"] = "static"
         sim = host.Simulation(overrides=ov, leaves=leaves)
@@ -287,7 +291,8 @@ def test_lazy_local_ghosts_match_exchange_every_stage(nx, nrb):
     ref.pre_execute()
     ref.cycle(4)
     want = ref.get_field("base", "U")
-    for extra in ({}, {"pb2/virtual_ranks": 3}, {"pb2/virtual_ranks": 3, "pb2/peer_push": "true"}):
+    for extra in ({}, {"pb2/virtual_ranks": 3}, {"pb2/virtual_ranks": 3, "pb2/peer_push": "true"},
+                  {"pb2/virtual_ranks": 3, "pb2/peer_push": "true", "pb2/peer_push_direct": "true"}):
         sim = host.Simulation(overrides=burgers_overrides(nx, nrb, 4, 8, "weno5", "fast", True, extra))
         sim.pre_execute()
         sim.cycle(2)
@@ -409,13 +414,16 @@ def test_overlapped_halo_path_is_bit_identical():
     ov2 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True, {"pb2/virtual_ranks": 2})
     ov3 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True,
                             {"pb2/virtual_ranks": 2, "pb2/peer_push": "true"})
-    a, b, p = (host.Simulation(overrides=o) for o in (ov1, ov2, ov3))
+    ov4 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True,
+                            {"pb2/virtual_ranks": 2, "pb2/peer_push": "true",
+                             "pb2/peer_push_direct": "true"})
+    a, b, p, q = (host.Simulation(overrides=o) for o in (ov1, ov2, ov3, ov4))
     lo, nl = b.exchange_elements("base")
     assert nl > 0 and lo > 0
-    for s in (a, b, p):
+    for s in (a, b, p, q):
         s.pre_execute()
         s.cycle(3)
-    for s in (b, p):  # p: the same overlap with the peer-push exchange instead of slabs
+    for s in (b, p, q):  # p, q: the same overlap with the peer-push exchanges instead of NCCL
         assert a.dt == s.dt and a.time == s.time
         assert np.array_equal(a.get_field("base", "U"), s.get_field("base", "U"))
         assert np.array_equal(a.get_field("base", "derived"), s.get_field("base", "derived"))
