@@ -526,6 +526,11 @@ int pb2_peer_handshake(int32_t *const *peer_flags, const int32_t *my_flags, cons
  * peer.  `counter`: one zeroed device int32 owned by the caller (left at zero). */
 int pb2_copy_signal(const pb2_bnd_table *table, int32_t *counter, int32_t *const *peer_flags,
                     int npeers, int me, int nranks, int32_t seq, pb2_stream_t stream);
+/* Step 2, copy-engine form: after the caller has enqueued its own transfers on `stream` (e.g.
+ * pb2_memcpy_d2d from a packed send slab into the peers' receive slabs: DMA engines, no SMs),
+ * one small kernel raises the arrival flags peer_flags[i][1 * nranks + me] = seq. */
+int pb2_peer_signal(int32_t *const *peer_flags, int npeers, int me, int nranks, int32_t seq,
+                    pb2_stream_t stream);
 /* Step 3 (receiver) on `stream`: wait until my_flags[1 * nranks + peers[i]] >= seq for all i */
 int pb2_peer_wait(const int32_t *my_flags, const int32_t *peers, int npeers, int nranks,
                   int32_t seq, pb2_stream_t stream);

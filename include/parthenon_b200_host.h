@@ -68,8 +68,16 @@ double pb2h_sim_zone_cycles_per_second(pb2h_sim *sim);
 /* out: ndim, nbtotal, nblocks on this rank, ni, nj, nk (with ghosts), coarse ni, nj, nk,
  * multilevel, first gid of this rank, nghost */
 int pb2h_sim_info(pb2h_sim *sim, int out[12]);
+/* loc: level, lx1, lx2, lx3 — on a forest (2-D, lx3 = 0) the last slot holds the tree id */
 int pb2h_sim_block(pb2h_sim *sim, int lid, int loc[4], double xmin[3], double xmax[3],
                    int *gid, int *nneighbors);
+/* MeshBlock::boundary_flag per face (inner_x1, outer_x1, ...): -1 block, 1 reflect, 2 outflow,
+ * 3 periodic, 4 user */
+int pb2h_sim_block_bcs(pb2h_sim *sim, int lid, int out[6]);
+/* topology of the forest application (host/forest/forest_app.hpp: the 2 x 2 forests of
+ * example/boundary_exchange, `variant` 0..3), no device touched */
+int pb2h_topology_create_forest(pb2h_sim **sim, const char *deck, const char *overrides,
+                                int variant, int rank, int nranks);
 /* out: gid, level, ox1, ox2, ox3, rank */
 int pb2h_sim_neighbor(pb2h_sim *sim, int lid, int n, int out[6]);
 /* ir_type 0 = BoundaryInteriorSend, 1 = BoundaryExteriorRecv (bnd_info.cpp:105-252) */
@@ -84,7 +92,11 @@ int64_t pb2h_sim_plan(pb2h_sim *sim, int ncomp, int kind, int64_t *rows, int64_t
 /* the same for one field of topological type tt (0 cell, 1 face, 2 edge, 3 node) with `ncomp`
  * tensor components, index boxes included: rows of 18 int64 [sender_gid, receiver_gid,
  * offset_index, piece, comp0, ncomp, send_s(i,j,k), recv_s(i,j,k), n(i,j,k), slab_off, peer,
- * coarse flags (bit 0: the sender reads its coarse buffer, bit 1: the receiver writes its)].
+ * coarse flags (bit 0: the sender reads its coarse buffer, bit 1: the receiver writes its;
+ * forests: bit 2 = the sender's tree is oriented differently — the receive box is then given in
+ * the SENDER's logical coordinates and element (i, j, k) of it lands at
+ * out[d] = flip[d] ? ncell - 1 - in[dir[d]] : in[dir[d]], with dir[d] in bits 3+2d..4+2d,
+ * flip[d] in bit 9+d and ncell in bits 12 and up)].
  * Channels of non-cell-centred fields come in pieces: one per topological element and active
  * sub-box of the sender's ownership mask (block_ownership.cpp:85-140). */
 int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t *rows,

@@ -120,6 +120,14 @@ __global__ void peer_handshake_kernel(int32_t *const *__restrict__ peer_flags,
   __threadfence_system();
 }
 
+__global__ void peer_signal_kernel(int32_t *const *__restrict__ peer_flags, int npeers, int slot,
+                                   int32_t seq) {
+  const int i = threadIdx.x;
+  if (i >= npeers) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile int32_t *>(peer_flags[i] + slot) = seq;
+}
+
 __global__ void peer_wait_kernel(const int32_t *my_flags, const int32_t *__restrict__ peers,
                                  int npeers, int32_t seq) {
   const int i = threadIdx.x;
@@ -291,6 +299,18 @@ int pb2_peer_handshake(int32_t *const *peer_flags, const int32_t *my_flags, cons
   if (int rc = require_device()) return rc;
   peer_handshake_kernel<<<1, ((npeers + 31) / 32) * 32, 0, as_stream(stream)>>>(
       peer_flags, my_flags, peers, npeers, me, seq);
+  PB2_LAUNCH_CHECK();
+  return PB2_OK;
+}
+
+int pb2_peer_signal(int32_t *const *peer_flags, int npeers, int me, int nranks, int32_t seq,
+                    pb2_stream_t stream) {
+  PB2_REQUIRE(npeers >= 0 && npeers <= 1024 && me >= 0 && me < nranks, "bad arguments");
+  if (npeers == 0) return PB2_OK;
+  PB2_REQUIRE(peer_flags, "null argument");
+  if (int rc = require_device()) return rc;
+  peer_signal_kernel<<<1, ((npeers + 31) / 32) * 32, 0, as_stream(stream)>>>(peer_flags, npeers,
+                                                                           nranks + me, seq);
   PB2_LAUNCH_CHECK();
   return PB2_OK;
 }

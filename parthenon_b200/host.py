@@ -19,7 +19,8 @@ SYMBOLS = [
     "pb2h_sim_destroy", "pb2h_sim_tag_and_remesh",
     "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
-    "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor",
+    "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor", "pb2h_sim_block_bcs",
+    "pb2h_topology_create_forest",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_plan_boxes",
     "pb2h_sim_field_ptr", "pb2h_sim_field_dims",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_allocation", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
@@ -79,6 +80,23 @@ num_scalars = 8
 # (amr_criteria.cpp:89-91), i.e. it would veto every derefinement
 TECOMM_DECK = BURGERS_DECK[:BURGERS_DECK.index("<parthenon/refinement0>")] + \
     BURGERS_DECK[BURGERS_DECK.index("<burgers>"):]
+
+# the forest application (host/forest): example/boundary_exchange's deck (the mesh itself is a
+# forest built in code); the outer edges take the reference's default condition, outflow
+FOREST_DECK = """
+<parthenon/job>
+problem_id = forest
+<parthenon/mesh>
+refinement = static
+numlevel = 1
+nghost = 2
+<parthenon/meshblock>
+nx1 = 4
+nx2 = 4
+nx3 = 1
+<forest>
+variant = 0
+"""
 
 # example/advection: the values of the reference's parthinput.advection that matter on this
 # path (outputs and the derived demo fields are off)
@@ -207,6 +225,9 @@ def lib():
     L.pb2h_sim_set_dt.argtypes = [vp, C.c_double]
     L.pb2h_sim_info.argtypes = [vp, ip]
     L.pb2h_sim_block.argtypes = [vp, C.c_int, ip, dp, dp, ip, ip]
+    L.pb2h_sim_block_bcs.argtypes = [vp, C.c_int, ip]
+    L.pb2h_topology_create_forest.argtypes = [C.POINTER(vp), C.c_char_p, C.c_char_p, C.c_int,
+                                              C.c_int, C.c_int]
     L.pb2h_sim_neighbor.argtypes = [vp, C.c_int, C.c_int, ip]
     L.pb2h_sim_calc_indices.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
     L.pb2h_sim_ranklist.argtypes = [vp, ip, C.c_int]
@@ -292,6 +313,12 @@ class _Base:
         check(lib().pb2h_sim_block(self.h, lid, loc, lo, hi, C.byref(gid), C.byref(nn)))
         return dict(loc=tuple(loc), xmin=np.array(lo), xmax=np.array(hi), gid=gid.value,
                     nneighbors=nn.value)
+
+    def block_bcs(self, lid):
+        """MeshBlock::boundary_flag per face: -1 block, 1 reflect, 2 outflow, 3 periodic, 4 user"""
+        o = (C.c_int * 6)()
+        check(lib().pb2h_sim_block_bcs(self.h, lid, o))
+        return tuple(int(x) for x in o)
 
     def neighbors(self, lid):
         out = []
@@ -381,6 +408,16 @@ class Topology(_Base):
                                                   len(c), 1))
 
 
+class ForestTopology(_Base):
+    """Topology of the forest application (2 x 2 forests of example/boundary_exchange, variant
+    0..3); touches no device (CPU tests)."""
+
+    def __init__(self, variant, overrides=None, rank=0, nranks=1):
+        self.h = C.c_void_p()
+        check(lib().pb2h_topology_create_forest(C.byref(self.h), FOREST_DECK.encode(),
+                                                _overrides(overrides), variant, rank, nranks))
+
+
 class Simulation(_Base):
     """A running application on the GPU (ParthenonManager + BurgersDriver)."""
 
@@ -389,7 +426,7 @@ class Simulation(_Base):
         if deck is None:
             deck = {"advection": ADVECTION_DECK,
                     "sparse_advection": SPARSE_ADVECTION_DECK,
-                    "tecomm": TECOMM_DECK}.get(app, BURGERS_DECK)
+                    "tecomm": TECOMM_DECK, "forest": FOREST_DECK}.get(app, BURGERS_DECK)
         self.h = C.c_void_p()
         la, n = _leaves(leaves)
         check(lib().pb2h_sim_create(C.byref(self.h), app.encode(), deck.encode(),

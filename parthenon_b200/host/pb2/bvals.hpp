@@ -89,6 +89,12 @@ struct Channel {
   int sender_rank, receiver_rank;   // real ranks (GPUs)
   int sender_vrank, receiver_vrank; // virtual ranks inside one GPU (test knob)
   int64_t slab_off = -1;            // nonlocal: offset in Reals inside the peer segment
+  // forests: the sender lives in a differently oriented tree.  recv_box is then the box in the
+  // SENDER's logical coordinates (bnd_info.cpp:216-228) and the unpack writes each element at
+  // lcoord_trans.InverseTransform (pb2_bnd_region::lcoord_*); ncell = the array extent along x1
+  bool transformed = false;
+  forest::LogicalCoordinateTransformation lcoord_trans;
+  int ncell = 0;
 };
 
 // Everything one exchange of one MeshData needs, derived from topology alone.
@@ -156,7 +162,14 @@ struct BvarsCache {
   // inter-GPU halo is ONE copy launch whose destinations are the ghost cells in the peers'
   // memory (field slabs mapped through CUDA IPC), with ready / arrival flags instead of NCCL
   // send / recv — no slabs, no unpack.  push_peers: the ranks this MeshData exchanges with.
-  bool push_mode = false, push_direct = false;
+  bool push_mode = false, push_direct = false, push_ce = false;
+  // copy-engine form: per peer, where its segment of our send slab goes (the peer's receive slab
+  // at its recv_off[this rank]), where it starts in the send slab and how many Reals it holds
+  struct PushSegment {
+    Real *dst;
+    int64_t src_off, count;
+  };
+  std::vector<PushSegment> push_segments;
   pb2_bnd_table *push = nullptr;
   DeviceBuffer push_flags, push_counter, push_peer_flags, push_peer_ids;
   std::vector<pb2_ipc_handle> push_opened; // mappings this cache holds a reference to

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "device.hpp"
+#include "forest.hpp"
 #include "parameter_input.hpp"
 #include "state.hpp"
 #include "types.hpp"
@@ -30,48 +31,17 @@ namespace Globals {
 extern int my_rank, nranks, nghost;
 } // namespace Globals
 
-struct LogicalLocation {
-  int level = 0;
-  int64_t lx[3] = {0, 0, 0};
-  int64_t lx1() const { return lx[0]; }
-  int64_t lx2() const { return lx[1]; }
-  int64_t lx3() const { return lx[2]; }
-  bool operator==(const LogicalLocation &o) const {
-    return level == o.level && lx[0] == o.lx[0] && lx[1] == o.lx[1] && lx[2] == o.lx[2];
-  }
-  LogicalLocation GetParent() const {
-    LogicalLocation p;
-    p.level = level - 1;
-    for (int d = 0; d < 3; ++d) p.lx[d] = lx[d] >> 1;
-    return p;
-  }
-  // z-order key at `maxlevel` resolution, x in the lowest interleaved bit
-  // (utils/morton_number.hpp:43)
-  uint64_t MortonKey(int maxlevel) const;
-  // logical_location.cpp:98-108
-  std::array<int, 3> GetSameLevelOffsets(const LogicalLocation &neighbor) const;
-  // logical_location.cpp:110-129
-  bool IsNeighbor(const LogicalLocation &in) const;
-  // logical_location.cpp:131-158: does block `in` touch the topological element of this block
-  // at te_offset (a face, edge or node of the block; {0,0,0} is its volume)
-  bool IsNeighborOfTE(const LogicalLocation &in, const std::array<int, 3> &te_offset) const;
-};
-
-struct LogicalLocationHash {
-  size_t operator()(const LogicalLocation &l) const {
-    uint64_t h = static_cast<uint64_t>(l.level) * 0x9E3779B97F4A7C15ull;
-    for (int d = 0; d < 3; ++d)
-      h ^= (static_cast<uint64_t>(l.lx[d]) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
-    return static_cast<size_t>(h);
-  }
-};
-
 // bvals/neighbor_block.hpp:48: what a block knows about one neighbour
 struct NeighborBlock {
   int gid = -1, rank = 0, lid = -1; // lid: index on the owning rank
   LogicalLocation loc;              // wrapped location (as stored in the tree)
   LogicalLocation origin_loc;       // location in the frame of this block (may lie outside)
   int offsets[3] = {0, 0, 0};       // same-level offsets ox1, ox2, ox3
+  // forests: how this block's logical coordinates read in the neighbour's tree
+  // (neighbor_block.hpp:68); `transformed` = it is not the identity, i.e. what the neighbour
+  // sends arrives in ITS orientation and is unpacked through the transformation
+  forest::LogicalCoordinateTransformation lcoord_trans;
+  bool transformed = false;
   // index of the offset in the 27-cube, the channel key element "loc idx"
   // (cell_center_offsets.hpp:98)
   int OffsetIndex() const { return (offsets[0] + 1) + 3 * (offsets[1] + 1) + 9 * (offsets[2] + 1); }
@@ -204,6 +174,11 @@ class Mesh {
   // <parthenon/static_refinementN> regions
   Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &packages, int rank = 0,
        int nranks = 1, const std::vector<LogicalLocation> &leaves = {});
+  // a 2-D forest of trees given face by face (mesh.cpp:189-218): static meshes of cell-centred
+  // fields; trees may meet in any orientation
+  Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &packages,
+       const forest::ForestDefinition &forest_def, int rank = 0, int nranks = 1);
+  std::shared_ptr<forest::Forest> forest; // null on hyper-rectangular meshes
   ~Mesh();
 
   int ndim = 3;
@@ -290,9 +265,13 @@ class Mesh {
   // dense fields are stored straight into the peers' ghost cells (BvarsCache::push_mode); false
   // keeps the slab + NCCL send / recv path.  With virtual ranks it must be asked for explicitly.
   bool peer_push = true;
-  // pb2/peer_push_direct: skip the receive slab too and store into the peers' ghost cells
-  // (measured slower at 8 GPUs: 32-byte x-face rows make poor NVLink packets)
-  bool peer_push_direct = false;
+  // pb2/peer_push_mode: how the halo gets into the peers' memory —
+  //   ce      pack into the local send slab, then one device-to-device copy per peer into its
+  //           receive slab (copy engines: no SMs, full-size NVLink packets); default
+  //   sm      the pack kernel stores into the peers' receive slabs itself
+  //   direct  no slabs at all: the copy kernel stores into the peers' ghost cells (cell-centred
+  //           fields of uniform meshes; 32-byte x-face rows make poor NVLink packets)
+  enum class PeerPush { ce, sm, direct } peer_push_mode = PeerPush::ce;
   // (pb2/unverified_sparse_multilevel: knob of round 1, when sparse fields on statically refined
   // meshes had not been run on a device yet; they are on by default now, the knob is ignored)
   bool unverified_sparse_multilevel = false;
@@ -330,6 +309,9 @@ class Mesh {
   std::unordered_map<LogicalLocation, int, LogicalLocationHash> leaf_gid_;
   std::unordered_map<LogicalLocation, int, LogicalLocationHash> internal_;
   void BuildTree(ParameterInput *pin, const std::vector<LogicalLocation> &leaves);
+  // what both constructors share: knobs of the deck, rank assignment, block list, fields
+  void ReadKnobs(ParameterInput *pin);
+  void FinishConstruction(ParameterInput *pin);
   // (re)create this rank's MeshBlocks from loclist / ranklist; blocks of `keep` that sit at an
   // unchanged location are reused (they carry their refinement counters and time step)
   void BuildBlockList(const BlockList_t *keep);

@@ -52,12 +52,15 @@ class ParthenonManager {
                                              const std::vector<std::string> &overrides);
   void SetRank(int rank, int nranks, const unsigned char *nccl_id);
   void ParthenonInitPackagesAndMesh(const std::vector<LogicalLocation> &leaves = {});
+  // ... on a forest given face by face (parthenon_manager.cpp:170-190)
+  void ParthenonInitPackagesAndMesh(const forest::ForestDefinition &forest_def);
   ParthenonStatus ParthenonFinalize();
   std::unique_ptr<ParameterInput> pinput;
   std::unique_ptr<ApplicationInput> app_input;
   std::unique_ptr<Mesh> pmesh;
 
  private:
+  void FinishMesh();
   int rank_ = 0, nranks_ = 1;
   std::vector<unsigned char> nccl_id_;
   pb2_comm *comm_ = nullptr;

@@ -304,6 +304,21 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c, bool direct) {
   pb2_bnd_table_destroy(c.push);
   c.push = nullptr;
   PB2_CHECK(pb2_copy_table_create(&c.push, regs.data(), static_cast<int64_t>(regs.size())));
+  c.push_segments.clear();
+  c.push_ce = !direct && pm->peer_push_mode == Mesh::PeerPush::ce;
+  if (c.push_ce) {
+    if (real) {
+      for (int p : peers) {
+        const int64_t n = c.plan.send_off[p + 1] - c.plan.send_off[p];
+        if (n == 0) continue;
+        c.push_segments.push_back(
+            {peer_var[p][0] + static_cast<int64_t>(peer_recv_off[static_cast<size_t>(p) * R + me]),
+             c.plan.send_off[p], n});
+      }
+    } else {
+      c.push_segments.push_back({c.recv_slab.get<Real>(), 0, c.plan.send_elements});
+    }
+  }
   std::vector<int32_t *> pf;
   for (int p : peers) pf.push_back(peer_flags[p]);
   c.push_npeers = static_cast<int>(peers.size());
@@ -472,6 +487,15 @@ void Rebuild(MeshData<Real> *md) {
     r.flag_slot = -1;
     r.status = PB2_REGION_ALLOCATED | (send ? 0u : PB2_REGION_BUF_ALLOCATED);
     r.value = send ? v.metadata().GetAllocationThreshold() : v.metadata().GetDefaultValue();
+    if (!send && ch.transformed) {
+      r.lcoord_on = 1;
+      for (int d = 0; d < 3; ++d) {
+        r.lcoord_dir[d] = std::abs(ch.lcoord_trans.dir_connection[d]);
+        r.lcoord_flip[d] = ch.lcoord_trans.dir_flip[d] ? 1 : 0;
+      }
+      r.lcoord_ncell = ch.ncell;
+      r.fac = 1.0; // cell-centred fields carry no sign (logical_coordinate_transformation.hpp:66-77)
+    }
     return r;
   };
   std::vector<pb2_bnd_region> packs, unpacks;
@@ -524,7 +548,7 @@ void Rebuild(MeshData<Real> *md) {
   // direct variant — cell-centred fields of uniform meshes only: send boxes are interior cells
   // and receive boxes ghost cells, so stores of one channel never touch what another channel
   // reads (shared faces / edges / nodes are both and need every pack to precede every unpack)
-  const bool want_direct = want_push && pm->peer_push_direct && all_cell && !pm->multilevel;
+  const bool want_direct = want_push && pm->peer_push_mode == Mesh::PeerPush::direct && all_cell && !pm->multilevel;
   if (want_direct) BuildPeerPush(md, c, true);
   if (!c.push_mode && c.plan.send_elements > 0 &&
       c.send_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.send_elements))
@@ -561,8 +585,10 @@ void Rebuild(MeshData<Real> *md) {
         for (auto &nb : pmb->neighbors)
           restricted = restricted || nb.origin_loc.level == pmb->loc.level - 1;
       for (auto &nb : pmb->neighbors) {
+        // (same rule as BuildExchangePlan: neighbours in differently oriented trees are served
+        // by the slab path, their restriction / prolongation regions follow its unpack)
         const bool local =
-            nb.rank == pm->my_rank && pm->VirtualRankOf(nb.gid) == my_vr;
+            nb.rank == pm->my_rank && pm->VirtualRankOf(nb.gid) == my_vr && !nb.transformed;
         const int cls = local ? 0 : 1;
         for (Variable *v : c.vars) {
           if (v->topological_type() != TopologicalType::Cell) {
@@ -707,7 +733,8 @@ void Rebuild(MeshData<Real> *md) {
       const int my_vr = pm->VirtualRankOf(pmb->gid);
       bool nonlocal = false;
       for (auto &nb : pmb->neighbors)
-        nonlocal = nonlocal || nb.rank != pm->my_rank || pm->VirtualRankOf(nb.gid) != my_vr;
+        nonlocal = nonlocal || nb.rank != pm->my_rank || pm->VirtualRankOf(nb.gid) != my_vr ||
+                   nb.transformed;
       (nonlocal ? bnd : inr).push_back(pmb->pack_index);
     }
     c.n_boundary = static_cast<int>(bnd.size());
@@ -837,12 +864,26 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
       // not in use any more: its unpack may have run on the other stream
       if (c.unpacked_valid) PB2_CHECK(pb2_stream_wait_event(ps, c.unpacked));
       const int me = pm->nranks > 1 ? pm->my_rank : 0;
+      if (c.push_ce) {
+        // the previous exchange's copies have left the send slab (they may have run on the other
+        // stream); pack locally, then let the copy engines carry each peer's segment
+        if (c.nonlocal_in_flight) PB2_CHECK(pb2_stream_wait_event(ps, c.sent));
+        PB2_CHECK(pb2_pack(c.pack, c.send_slab.get<Real>(), nullptr, ps));
+      }
       PB2_CHECK(pb2_peer_handshake(c.push_peer_flags.get<int32_t *>(), c.push_flags.get<int32_t>(),
                                    c.push_peer_ids.get<int32_t>(), c.push_npeers, me, pm->nranks,
                                    c.push_seq, ps));
-      PB2_CHECK(pb2_copy_signal(c.push, c.push_counter.get<int32_t>(),
-                                c.push_peer_flags.get<int32_t *>(), c.push_npeers, me, pm->nranks,
-                                c.push_seq, ps));
+      if (c.push_ce) {
+        for (const BvarsCache::PushSegment &sg : c.push_segments)
+          PB2_CHECK(pb2_memcpy_d2d(sg.dst, c.send_slab.get<Real>() + sg.src_off,
+                                   sizeof(Real) * static_cast<size_t>(sg.count), ps));
+        PB2_CHECK(pb2_peer_signal(c.push_peer_flags.get<int32_t *>(), c.push_npeers, me,
+                                  pm->nranks, c.push_seq, ps));
+      } else {
+        PB2_CHECK(pb2_copy_signal(c.push, c.push_counter.get<int32_t>(),
+                                  c.push_peer_flags.get<int32_t *>(), c.push_npeers, me,
+                                  pm->nranks, c.push_seq, ps));
+      }
       PB2_CHECK(pb2_event_record(c.sent, ps));
       c.nonlocal_in_flight = true;
       return TaskStatus::complete;

@@ -245,6 +245,31 @@ const NeighborBlock *MatchingNeighbor(const MeshBlock *sender, int receiver_gid,
       return &q;
   return nullptr;
 }
+
+// The offsets of neighbour `nb` as the NEIGHBOUR's tree sees them (ReceiveKey,
+// bvals_utils.hpp:57-67: lcoord_trans.Transform(nb.offsets)): the sender's own offsets towards
+// the receiver are the reverse of these.
+std::array<int, 3> OffsetsInSenderFrame(const NeighborBlock &nb) {
+  std::array<int, 3> off{nb.offsets[0], nb.offsets[1], nb.offsets[2]};
+  return nb.transformed ? nb.lcoord_trans.Transform(off) : off;
+}
+
+// bnd_info.cpp:216-228: a receive box goes to the sender's logical coordinates — both corners
+// through LogicalCoordinateTransformation::Transform(ijk) (.hpp:79-88) with ncell = the array's
+// extent along x1, re-sorted — and SetBounds walks THAT box in buffer order, writing each element
+// at InverseTransform (boundary_communication.cpp:282-308)
+IndexBox TransformBox(const IndexBox &box, const forest::LogicalCoordinateTransformation &ct,
+                      int ncell) {
+  IndexBox out;
+  for (int d = 0; d < 3; ++d) {
+    const int o = std::abs(ct.dir_connection[d]);
+    out.s[o] = ct.dir_flip[d] ? ncell - 1 - box.s[d] : box.s[d];
+    out.e[o] = ct.dir_flip[d] ? ncell - 1 - box.e[d] : box.e[d];
+  }
+  for (int d = 0; d < 3; ++d)
+    if (out.s[d] > out.e[d]) std::swap(out.s[d], out.e[d]);
+  return out;
+}
 namespace {
 auto ChannelKey(const Channel &c) {
   return std::make_tuple(c.sender_gid, c.receiver_gid, c.var, c.offset_index, c.piece);
@@ -328,16 +353,28 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
     const int my_vr = pm->VirtualRankOf(pmb->gid);
     for (auto &nb : pmb->neighbors) {
       const int nb_vr = nb.rank == pm->my_rank ? pm->VirtualRankOf(nb.gid) : 0;
-      const bool local = nb.rank == pm->my_rank && nb_vr == my_vr;
+      // a neighbour in a differently oriented tree is unpacked through its transformation, which
+      // the fused same-device copy does not do: such channels take the slab path
+      const bool local = nb.rank == pm->my_rank && nb_vr == my_vr && !nb.transformed;
+      const std::array<int, 3> soff = OffsetsInSenderFrame(nb);
       for (int v = 0; v < nvar; ++v) {
+        PARTHENON_REQUIRE(!nb.transformed || vars[v].tt == TopologicalType::Cell,
+                          "forests of rotated trees exchange cell-centred fields only");
         // this block as RECEIVER of the channel nb -> pmb
         Channel rc;
         rc.sender_gid = nb.gid;
         rc.receiver_gid = pmb->gid;
         rc.var = v;
-        rc.offset_index = OffsetIndexOf(-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]);
+        rc.offset_index = OffsetIndexOf(-soff[0], -soff[1], -soff[2]);
         rc.recv_box = CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, false);
         rc.recv_coarse = nb.loc.level < pmb->loc.level; // bnd_info.cpp:285-289
+        if (nb.transformed) {
+          rc.transformed = true;
+          rc.lcoord_trans = nb.lcoord_trans;
+          const IndexShape &shape = rc.recv_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+          rc.ncell = shape.Bounds(0, IndexDomain::entire).e + 1; // var.GetDim(1), bnd_info.cpp:297
+          rc.recv_box = TransformBox(rc.recv_box, nb.lcoord_trans, rc.ncell);
+        }
         rc.send_coarse = pmb->loc.level < nb.loc.level;
         rc.sender_rank = nb.rank;
         rc.receiver_rank = pm->my_rank;
@@ -348,7 +385,8 @@ ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
         const bool cell = vars[v].tt == TopologicalType::Cell;
         if (local) {
           const MeshBlock *sender = pm->block_list[nb.lid].get();
-          const NeighborBlock *q = MatchingNeighbor(sender, pmb->gid, nb.offsets);
+          const int roff[3] = {soff[0], soff[1], soff[2]};
+          const NeighborBlock *q = MatchingNeighbor(sender, pmb->gid, roff);
           PARTHENON_REQUIRE(q != nullptr, "no matching send region for a local channel");
           auto emit = [&](const Channel &c) { local_out.push_back(c); };
           if (cell) {

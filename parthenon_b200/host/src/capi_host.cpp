@@ -13,6 +13,7 @@
 #include "../sparse_advection/sparse_advection_driver.hpp"
 #include "../burgers/burgers_package.hpp"
 #include "../tecomm/tecomm_app.hpp"
+#include "../forest/forest_app.hpp"
 #include "parthenon_b200_host.h"
 #include "pb2/sparse_pack.hpp"
 #include "pb2/parthenon.hpp"
@@ -125,8 +126,9 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
     PARTHENON_REQUIRE(sim && app && deck, "null argument");
     const std::string a(app);
     PARTHENON_REQUIRE(a == "burgers" || a == "advection" || a == "sparse_advection" ||
-                          a == "tecomm",
-                      "unknown application (have: burgers, advection, sparse_advection, tecomm)");
+                          a == "tecomm" || a == "forest",
+                      "unknown application (have: burgers, advection, sparse_advection, tecomm, "
+                      "forest)");
     auto s = std::make_unique<pb2h_sim>();
     if (a == "burgers") {
       s->pman.app_input->ProcessPackages = burgers_benchmark::ProcessPackages;
@@ -137,6 +139,9 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
     } else if (a == "tecomm") {
       s->pman.app_input->ProcessPackages = tecomm_example::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = tecomm_example::MeshProblemGenerator;
+    } else if (a == "forest") {
+      s->pman.app_input->ProcessPackages = forest_example::ProcessPackages;
+      s->pman.app_input->MeshProblemGenerator = forest_example::MeshProblemGenerator;
     } else {
       s->pman.app_input->ProcessPackages = sparse_advection_example::ProcessPackages;
       s->pman.app_input->MeshProblemGenerator = sparse_advection_example::MeshProblemGenerator;
@@ -145,7 +150,11 @@ int pb2h_sim_create(pb2h_sim **sim, const char *app, const char *deck, const cha
     tecomm_example::SetCriterionCycle(0);
     s->pman.ParthenonInitEnvFromString(deck, SplitLines(overrides));
     s->pman.SetRank(rank, nranks, nccl_id);
-    s->pman.ParthenonInitPackagesAndMesh(Leaves(leaves, nleaves));
+    if (a == "forest") // the mesh is a forest built in code, as example/boundary_exchange does
+      s->pman.ParthenonInitPackagesAndMesh(forest_example::MakeForest(
+          s->pman.pinput->GetOrAddInteger("forest", "variant", 0)));
+    else
+      s->pman.ParthenonInitPackagesAndMesh(Leaves(leaves, nleaves));
     std::unique_ptr<MultiStageDriver> drv;
     if (a == "burgers")
       drv = std::make_unique<burgers_benchmark::BurgersDriver>(
@@ -176,6 +185,30 @@ int pb2h_topology_create(pb2h_sim **sim, const char *deck, const char *overrides
     s->mesh = std::make_unique<Mesh>(s->pin.get(), nullptr, none, rank, nranks,
                                      Leaves(leaves, nleaves));
     *sim = s.release();
+  });
+}
+
+int pb2h_topology_create_forest(pb2h_sim **sim, const char *deck, const char *overrides,
+                                int variant, int rank, int nranks) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && deck, "null argument");
+    auto s = std::make_unique<pb2h_sim>();
+    s->topology_only = true;
+    s->pin = std::make_unique<ParameterInput>();
+    s->pin->LoadFromString(deck);
+    for (auto &o : SplitLines(overrides)) s->pin->ModifyFromString(o);
+    Packages_t none;
+    s->mesh = std::make_unique<Mesh>(s->pin.get(), nullptr, none,
+                                     forest_example::MakeForest(variant), rank, nranks);
+    *sim = s.release();
+  });
+}
+
+int pb2h_sim_block_bcs(pb2h_sim *sim, int lid, int out[6]) {
+  return Guard([&] {
+    Mesh *pm = sim->pm();
+    PARTHENON_REQUIRE(out && lid >= 0 && lid < pm->GetNumMeshBlocksThisRank(), "bad block index");
+    for (int f = 0; f < 6; ++f) out[f] = static_cast<int>(pm->block_list[lid]->boundary_flag[f]);
   });
 }
 
@@ -300,6 +333,7 @@ int pb2h_sim_block(pb2h_sim *sim, int lid, int loc[4], double xmin[3], double xm
       xmin[d] = mb.block_size.xmin_[d];
       xmax[d] = mb.block_size.xmax_[d];
     }
+    if (pm->forest) loc[3] = static_cast<int>(mb.loc.tree); // 2-D: lx3 is 0, the slot names the tree
     *gid = mb.gid;
     *nneighbors = static_cast<int>(mb.neighbors.size());
   });
@@ -405,6 +439,14 @@ int64_t pb2h_sim_plan_boxes(pb2h_sim *sim, int ncomp, int tt, int kind, int64_t 
       r[15] = c.slab_off;
       r[16] = kind == 1 ? c.receiver_rank : c.sender_rank;
       r[17] = (c.send_coarse ? 1 : 0) | (c.recv_coarse ? 2 : 0);
+      if (c.transformed) {
+        r[17] |= 4;
+        for (int d = 0; d < 3; ++d) {
+          r[17] |= static_cast<int64_t>(std::abs(c.lcoord_trans.dir_connection[d])) << (3 + 2 * d);
+          r[17] |= static_cast<int64_t>(c.lcoord_trans.dir_flip[d] ? 1 : 0) << (9 + d);
+        }
+        r[17] |= static_cast<int64_t>(c.ncell) << 12;
+      }
     }
   });
   return count;

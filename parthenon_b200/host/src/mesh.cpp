@@ -300,6 +300,24 @@ std::vector<NeighborBlock> Mesh::FindNeighbors(const LogicalLocation &loc) const
   struct {
     std::vector<NeighborBlock> neighbors;
   } mb;
+  if (forest) {
+    // mesh-gmg.cpp:48-101 over Forest::FindNeighbors: offsets come from the neighbour's location
+    // in THIS block's index space, the transformation says how to read what it sends
+    for (const forest::NeighborLocation &nl : forest->FindNeighbors(loc)) {
+      NeighborBlock nb;
+      nb.gid = leaf_gid_.at(nl.global_loc);
+      nb.rank = ranklist[nb.gid];
+      nb.lid = nb.gid - nslist[nb.rank];
+      nb.loc = nl.global_loc;
+      nb.origin_loc = nl.origin_loc;
+      const auto off = loc.GetSameLevelOffsets(nl.origin_loc);
+      for (int d = 0; d < 3; ++d) nb.offsets[d] = off[d];
+      nb.lcoord_trans = nl.lcoord_trans;
+      nb.transformed = !nl.lcoord_trans.IsIdentity();
+      mb.neighbors.push_back(nb);
+    }
+    return mb.neighbors;
+  }
   auto add = [&](int gid, const LogicalLocation &wrapped, const LogicalLocation &origin) {
     NeighborBlock nb;
     nb.gid = gid;
@@ -408,21 +426,84 @@ Mesh::Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &pkgs, int 
   for (int d = 0; d < ndim; ++d) maxrb = std::max(maxrb, nrbx[d]);
   root_level = 0;
   while ((1 << root_level) < maxrb) ++root_level;
+  ReadKnobs(pin);
+  BuildTree(pin, leaves);
+  FinishConstruction(pin);
+}
+
+// Mesh::Mesh(pin, app_in, packages, forest_def), mesh.cpp:189-218
+Mesh::Mesh(ParameterInput *pin, ApplicationInput *app_in, Packages_t &pkgs,
+           const forest::ForestDefinition &forest_def, int rank, int nranks_in)
+    : my_rank(rank), nranks(nranks_in), packages(pkgs) {
+  Globals::my_rank = rank;
+  Globals::nranks = nranks_in;
+  Globals::nghost = pin->GetOrAddInteger("parthenon/mesh", "nghost", 2);
+  ndim = 2;
+  mesh_size = RegionSize(); // {0,0,0}-{1,1,0}: the trees carry their own domains
+  mesh_size.symmetry_ = {false, false, true};
+  const char *bc_names[6] = {"ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc"};
+  for (int d = 0; d < 3; ++d) {
+    const std::string n = std::to_string(d + 1);
+    base_block_size.nx_[d] = d < ndim ? pin->GetOrAddInteger("parthenon/meshblock", "nx" + n, 1) : 1;
+    base_block_size.symmetry_[d] = d >= ndim;
+    nrbx[d] = 1;
+  }
+  PARTHENON_REQUIRE(base_block_size.nx_[0] == base_block_size.nx_[1],
+                    "blocks of a forest must be square: a neighbouring tree may swap the axes");
+  // edges flagged `user` take the deck's condition of that face, outflow unless named otherwise
+  // (Mesh::SetBCNames_ mesh.cpp:1179-1186, Tree::EnrollBndryFncts tree.cpp:388-406)
+  for (int f = 0; f < 6; ++f) {
+    const std::string name = pin->GetOrAddString("parthenon/mesh", bc_names[f], "outflow");
+    mesh_bcs[f] = f < 4 ? ParseBoundary(name) : BoundaryFlag::periodic;
+    PARTHENON_REQUIRE(f >= 4 || mesh_bcs[f] != BoundaryFlag::periodic,
+                      "periodic is not a condition for the outer edges of a forest");
+    if (f < 4 && mesh_bcs[f] == BoundaryFlag::user) {
+      const bool have = app_in != nullptr && app_in->boundary_conditions_[f].count(name) > 0;
+      PARTHENON_REQUIRE(have, "boundary condition '" + name + "' of " + bc_names[f] +
+                                  " is neither outflow / reflecting nor registered with "
+                                  "ApplicationInput::RegisterBoundaryCondition");
+      user_bcs[f] = app_in->boundary_conditions_[f].at(name);
+    }
+  }
+  root_level = 0;
+  ReadKnobs(pin);
+  PARTHENON_REQUIRE(!adaptive, "adaptive refinement of forests is not built");
+  forest = std::make_shared<forest::Forest>(forest_def);
+  loclist = forest->GetMeshBlockList();
+  leaf_gid_.clear();
+  current_level = 0;
+  for (size_t g = 0; g < loclist.size(); ++g) {
+    leaf_gid_[loclist[g]] = static_cast<int>(g);
+    current_level = std::max(current_level, loclist[g].level);
+  }
+  multilevel = current_level > 0;
+  nbtotal = static_cast<int>(loclist.size());
+  FinishConstruction(pin);
+}
+
+void Mesh::ReadKnobs(ParameterInput *pin) {
   const std::string refinement = pin->GetOrAddString("parthenon/mesh", "refinement", "none");
   adaptive = refinement == "adaptive";
   pack_size_ = pin->GetOrAddInteger("parthenon/mesh", "pack_size", -1);
   virtual_ranks = pin->GetOrAddInteger("pb2", "virtual_ranks", 1);
   table_halo = pin->GetOrAddBoolean("pb2", "table_halo", false);
   peer_push = pin->GetOrAddBoolean("pb2", "peer_push", nranks > 1);
-  peer_push_direct = pin->GetOrAddBoolean("pb2", "peer_push_direct", false);
+  {
+    const std::string mode = pin->GetOrAddString("pb2", "peer_push_mode", "ce");
+    PARTHENON_REQUIRE(mode == "ce" || mode == "sm" || mode == "direct",
+                      "pb2/peer_push_mode must be ce, sm or direct");
+    peer_push_mode = mode == "ce" ? PeerPush::ce : (mode == "sm" ? PeerPush::sm : PeerPush::direct);
+  }
   unverified_sparse_multilevel = pin->GetOrAddBoolean("pb2", "unverified_sparse_multilevel", false);
   sparse_config.enabled = pin->GetOrAddBoolean("parthenon/sparse", "enable_sparse", true);
   sparse_config.allocation_threshold = pin->GetOrAddReal("parthenon/sparse", "alloc_threshold", 1e-12);
   sparse_config.deallocation_threshold =
       pin->GetOrAddReal("parthenon/sparse", "dealloc_threshold", 1e-14);
   sparse_config.deallocation_count = pin->GetOrAddInteger("parthenon/sparse", "dealloc_count", 5);
+}
 
-  BuildTree(pin, leaves);
+void Mesh::FinishConstruction(ParameterInput *pin) {
+  const std::string refinement = pin->GetOrAddString("parthenon/mesh", "refinement", "none");
   if (refinement != "none") multilevel = true; // coarse buffers exist (mesh.cpp:118-140)
 
   std::vector<double> cost(nbtotal, 1.0);
@@ -510,6 +591,7 @@ void Mesh::BuildBlockList(const BlockList_t *keep) {
     mb->lid = gid - nslist[rank];
     mb->loc = loclist[gid];
     mb->block_size = GetBlockSize(mb->loc);
+    if (forest) forest->GetBlockDomain(mb->loc, mb->block_size.xmin_.data(), mb->block_size.xmax_.data());
     const int nx1 = base_block_size.nx_[0], nx2 = ndim > 1 ? base_block_size.nx_[1] : 0,
               nx3 = ndim > 2 ? base_block_size.nx_[2] : 0;
     mb->cellbounds = IndexShape(nx3, nx2, nx1, ng);
@@ -518,10 +600,17 @@ void Mesh::BuildBlockList(const BlockList_t *keep) {
                                   ndim > 1 ? std::max(1, nx2 / 2) : 0, std::max(1, nx1 / 2), ng);
     mb->coords = UniformCartesian(mb->block_size, ng);
     for (int f = 0; f < 6; ++f) mb->boundary_flag[f] = BoundaryFlag::block;
-    for (int d = 0; d < ndim; ++d) {
+    for (int d = 0; d < ndim && !forest; ++d) {
       if (mb->loc.lx[d] == 0) mb->boundary_flag[2 * d] = mesh_bcs[2 * d];
       if (mb->loc.lx[d] == BlocksAtLevel(mb->loc.level, d) - 1)
         mb->boundary_flag[2 * d + 1] = mesh_bcs[2 * d + 1];
+    }
+    if (forest) {
+      // the tree's flags where the block touches the tree boundary; an edge flagged `user` takes
+      // the deck's condition of that face (outflow unless the deck names another)
+      const auto bcs = forest->GetBlockBCs(mb->loc);
+      for (int f = 0; f < 4; ++f)
+        mb->boundary_flag[f] = bcs[f] == BoundaryFlag::user ? mesh_bcs[f] : bcs[f];
     }
     mb->pmy_mesh = this;
     const int ps = DefaultPackSizeFor(static_cast<int>(nblist[rank]));

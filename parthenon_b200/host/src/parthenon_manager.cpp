@@ -44,6 +44,18 @@ void ParthenonManager::ParthenonInitPackagesAndMesh(const std::vector<LogicalLoc
   pinput->GetOrAddInteger("parthenon/mesh", "nghost", 2);
   Packages_t packages = app_input->ProcessPackages(pinput);
   pmesh = std::make_unique<Mesh>(pinput.get(), app_input.get(), packages, rank_, nranks_, leaves);
+  FinishMesh();
+}
+
+void ParthenonManager::ParthenonInitPackagesAndMesh(const forest::ForestDefinition &forest_def) {
+  PARTHENON_REQUIRE(app_input->ProcessPackages != nullptr, "ProcessPackages must be set");
+  pinput->GetOrAddInteger("parthenon/mesh", "nghost", 2);
+  Packages_t packages = app_input->ProcessPackages(pinput);
+  pmesh = std::make_unique<Mesh>(pinput.get(), app_input.get(), packages, forest_def, rank_, nranks_);
+  FinishMesh();
+}
+
+void ParthenonManager::FinishMesh() {
   pb2_stream_t st = nullptr, cs = nullptr;
   PB2_CHECK(pb2_stream_create(&st));
   PB2_CHECK(pb2_stream_create_priority(&cs, 1)); // halo pack / NCCL: first in line for SMs

@@ -3,10 +3,10 @@
 # without it (in-run parity: N-rank result bit-identical to one rank) and the multi-GPU parity script
 set -u
 OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r02o}; N=${2:-2}
-timeout 600 python -m pytest tests -m gpu -x -q -k "multiblock_strict or lazy_local_ghosts_match or overlapped_halo or logical_coordinate or non_cell_centred_exchange_bit_exact or multilevel_exchange_matches" > $OUT/pytest_$TAG.log 2>&1; tail -5 $OUT/pytest_$TAG.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "multiblock_strict or lazy_local_ghosts_match or overlapped_halo or logical_coordinate or non_cell_centred_exchange_bit_exact or multilevel_exchange_matches or forest" > $OUT/pytest_$TAG.log 2>&1; tail -5 $OUT/pytest_$TAG.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
-for v in push nccl direct; do
-  EX=""; [ $v = nccl ] && EX="--set pb2/peer_push=false"; [ $v = direct ] && EX="--set pb2/peer_push_direct=true"
+for v in ce nccl sm; do
+  EX=""; [ $v = nccl ] && EX="--set pb2/peer_push=false"; [ $v = sm ] && EX="--set pb2/peer_push_mode=sm"
   timeout 400 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-e2e --no-cpu-baseline $EX > $OUT/bench_${TAG}_$v.json 2> $OUT/bench_${TAG}_$v.err
   python - <<PY
 import json

@@ -113,7 +113,11 @@ def test_sim_matches_oracle_multiblock_strict():
             host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
                                                         {"pb2/virtual_ranks": 3,
                                                          "pb2/peer_push": "true",
-                                                         "pb2/peer_push_direct": "true"}))]
+                                                         "pb2/peer_push_mode": "sm"})),
+            host.Simulation(overrides=burgers_overrides(8, 4, 4, 3, "weno5", "strict", True,
+                                                        {"pb2/virtual_ranks": 3,
+                                                         "pb2/peer_push": "true",
+                                                         "pb2/peer_push_mode": "direct"}))]
     lo, nl = sims[1].exchange_elements("base")
     assert nl > 0 and lo > 0 and lo + nl == sum(sims[0].exchange_elements("base"))
     for s in sims:
@@ -292,7 +296,8 @@ def test_lazy_local_ghosts_match_exchange_every_stage(nx, nrb):
     ref.cycle(4)
     want = ref.get_field("base", "U")
     for extra in ({}, {"pb2/virtual_ranks": 3}, {"pb2/virtual_ranks": 3, "pb2/peer_push": "true"},
-                  {"pb2/virtual_ranks": 3, "pb2/peer_push": "true", "pb2/peer_push_direct": "true"}):
+                  {"pb2/virtual_ranks": 3, "pb2/peer_push": "true", "pb2/peer_push_mode": "sm"},
+                  {"pb2/virtual_ranks": 3, "pb2/peer_push": "true", "pb2/peer_push_mode": "direct"}):
         sim = host.Simulation(overrides=burgers_overrides(nx, nrb, 4, 8, "weno5", "fast", True, extra))
         sim.pre_execute()
         sim.cycle(2)
@@ -416,7 +421,7 @@ def test_overlapped_halo_path_is_bit_identical():
                             {"pb2/virtual_ranks": 2, "pb2/peer_push": "true"})
     ov4 = burgers_overrides(8, 8, 4, 2, "weno5", "fast", True,
                             {"pb2/virtual_ranks": 2, "pb2/peer_push": "true",
-                             "pb2/peer_push_direct": "true"})
+                             "pb2/peer_push_mode": "direct"})
     a, b, p, q = (host.Simulation(overrides=o) for o in (ov1, ov2, ov3, ov4))
     lo, nl = b.exchange_elements("base")
     assert nl > 0 and lo > 0
