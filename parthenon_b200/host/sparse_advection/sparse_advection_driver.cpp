@@ -64,7 +64,9 @@ TaskCollection SparseAdvectionDriver::MakeTaskCollection(BlockList_t &blocks, co
     // if this is the last stage, check if we can deallocate any sparse variables
     if (stage == integrator->nstages) {
       auto dealloc = tl.AddTask(boundary, SparseDealloc, mc1.get());
-      tl.AddTask(dealloc, EstimateTimestep<MeshData<Real>>, mc1.get());
+      auto new_dt = tl.AddTask(dealloc, EstimateTimestep<MeshData<Real>>, mc1.get());
+      // update refinement (sparse_advection_driver.cpp:147-151)
+      if (pmesh->adaptive) tl.AddTask(new_dt, Refinement::Tag, mc1.get());
     }
   }
   (void)blocks;

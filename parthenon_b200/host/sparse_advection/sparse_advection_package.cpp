@@ -34,7 +34,44 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin) {
   pkg->AddSparsePool("sparse", m, ids);
 
   pkg->EstimateTimestepMesh = EstimateTimestepMesh;
+  pkg->CheckRefinementMesh = CheckRefinement;
   return pkg;
+}
+
+// CheckRefinement sparse_advection_package.cpp:110-143: minimum and maximum over the ALLOCATED
+// fields of a block (entire extents); a block on which nothing is allocated keeps the reduction's
+// identity (max = lowest) and is tagged for derefinement.  One device reduction per field for the
+// whole batch instead of one par_reduce per block.
+void CheckRefinement(MeshData<Real> *md, std::vector<AmrTag> &tags) {
+  auto pkg = md->GetMeshPointer()->packages.Get("sparse_advection_package");
+  const Real refine_tol = pkg->Param<Real>("refine_tol");
+  const Real derefine_tol = pkg->Param<Real>("derefine_tol");
+  const int nb = md->NumBlocks();
+  std::vector<Real> mn(nb, std::numeric_limits<Real>::max()),
+      mx(nb, std::numeric_limits<Real>::lowest());
+  DeviceBuffer dev;
+  dev.Allocate(sizeof(Real) * 2 * nb, md->stream());
+  std::vector<Real> h(2 * nb);
+  for (Variable *u : md->GetVariablesByFlag({Metadata::Sparse})) {
+    if (u->label().compare(0, 6, "sparse") != 0) continue;
+    const pb2_pack_geom g = md->Geometry(*u);
+    PB2_CHECK(pb2_block_minmax(&g, u->data(), u->DeviceMask(), dev.get<Real>(), md->stream()));
+    PB2_CHECK(pb2_memcpy_d2h(h.data(), dev.get(), sizeof(Real) * h.size(), md->stream()));
+    PB2_CHECK(pb2_stream_sync(md->stream()));
+    for (int b = 0; b < nb; ++b) {
+      if (!u->IsAllocated(b)) continue; // (the kernel leaves masked blocks untouched)
+      mn[b] = std::min(mn[b], h[2 * b]);
+      mx[b] = std::max(mx[b], h[2 * b + 1]);
+    }
+  }
+  for (int b = 0; b < nb; ++b) {
+    if (mx[b] > refine_tol && mn[b] < derefine_tol)
+      tags[b] = AmrTag::refine;
+    else if (mx[b] < derefine_tol)
+      tags[b] = AmrTag::derefine;
+    else
+      tags[b] = AmrTag::same;
+  }
 }
 
 TaskStatus CalculateFluxes(MeshData<Real> *md) {

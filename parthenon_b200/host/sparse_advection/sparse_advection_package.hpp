@@ -18,5 +18,7 @@ std::shared_ptr<StateDescriptor> Initialize(ParameterInput *pin);
 // (sparse_advection_package.cpp:173-258)
 TaskStatus CalculateFluxes(MeshData<Real> *md);
 Real EstimateTimestepMesh(MeshData<Real> *md); // :136-168
+// refinement tags from the allocated fields (:110-143)
+void CheckRefinement(MeshData<Real> *md, std::vector<AmrTag> &tags);
 
 } // namespace sparse_advection_package

@@ -259,7 +259,13 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     if (!(nv.IsSet(Metadata::Independent) || nv.IsSet(Metadata::FillGhost) ||
           nv.IsSet(Metadata::ForceRemeshComm)))
       continue;
-    PARTHENON_REQUIRE(!nv.metadata().IsSparse(), "sparse fields cannot be remeshed in this build");
+    // sparse fields (mesh-amr_loadbalance.cpp:700-1000 over allocated variables only): a kept
+    // block keeps its allocation status and deallocation counter, a new child exists where its
+    // parent did, a new parent where ANY daughter did (the quadrants of the others stay at the
+    // zero a fresh allocation holds)
+    const bool sparse = nv.metadata().IsSparse() && sparse_config.enabled;
+    PARTHENON_REQUIRE(!sparse || nranks == 1,
+                      "adaptive remeshing of sparse fields needs a single device in this build");
     // blocks of face / edge / node fields that change device: the 2-GPU run of round 2 did not
     // reproduce the reference's dumps (profiles/multigpu_check_r02_n2.txt), so refuse rather
     // than return wrong shared elements; one device is bit-exact (tests/test_tecomm_gpu.py)
@@ -382,6 +388,16 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
       const int src_rank = old_ranklist[pc.old_gid], dst_rank = ranklist[pc.new_gid];
       const bool mine_old = src_rank == my_rank, mine_new = dst_rank == my_rank;
       if (!mine_old && !mine_new) continue;
+      if (sparse) { // (single device: both sides are ours)
+        const int ol = old_local(pc.old_gid);
+        if (!ov.IsAllocated(ol)) continue;
+        const int nbi = block_list[pc.new_gid - nslist[my_rank]]->pack_index;
+        if (!nv.IsAllocated(nbi)) {
+          nv.SetAllocated(nbi, true); // the fresh slab is zero-filled
+          new_md->alloc_generation++;
+        }
+        if (pc.kind == 0) nv.dealloc_count(nbi) = ov.dealloc_count(ol);
+      }
       // -- sender side: merged children are restricted first (GetInteriorRestrict), then the
       //    data leaves in a slab if the new owner is another device
       if (mine_old && pc.kind == 2 && te) {

@@ -373,9 +373,8 @@ void Rebuild(MeshData<Real> *md) {
     // statically refined meshes: allocation-aware restriction / prolongation / flux correction
     // on same-device channels (tests/test_late_round1_gpu.py, bit-exact against the reference's
     // dumps); remeshing sparse fields and shipping them between devices across levels are not built
-    PARTHENON_REQUIRE(!pm->multilevel || (!pm->adaptive && !slabs),
-                      "sparse fields on multilevel meshes: only static refinement on one device "
-                      "is supported by this build");
+    PARTHENON_REQUIRE(!pm->multilevel || !slabs,
+                      "sparse fields on multilevel meshes: one device only in this build");
     PARTHENON_REQUIRE(pm->DefaultNumPartitions() == 1,
                       "sparse fields need one MeshData per rank (parthenon/mesh/pack_size=-1)");
   }

@@ -66,3 +66,43 @@ def test_sparse_advection_on_refined_mesh():
                 assert np.array_equal(state(), g[f"U_{c}"], equal_nan=True), f"cycle {c}"
     finally:
         sim.close()
+
+
+def test_sparse_advection_adaptive_as_shipped():
+    """example/sparse_advection as the reference ships it — refinement = adaptive, three levels,
+    40 cycles (220 -> 328 -> 280 blocks): tagging on the allocated fields only, remesh of sparse
+    fields on the device (a new child exists where its parent did, a new parent where any
+    daughter did), allocation-aware exchange on the new mesh; block list, allocation pattern and
+    every value against the reference's dumps (taken after Step, before that cycle's remesh)"""
+    g = np.load(os.path.join(GOLD, "sparse_a64_b8_l3_2d.npz"))
+    ov = {"parthenon/mesh/refinement": "adaptive", "parthenon/mesh/numlevel": 3,
+          "parthenon/sparse/alloc_threshold": 1e-2, "parthenon/sparse/dealloc_threshold": 5e-3,
+          "parthenon/sparse/dealloc_count": 2}
+    sim = host.Simulation(app="sparse_advection", overrides=ov)
+    try:
+        sim.pre_execute()
+
+        def state():
+            return np.stack([np.where(sim.allocation("base", f"sparse_{f}")[:, None, None, None],
+                                      sim.get_field("base", f"sparse_{f}")[:, 0], np.nan)
+                             for f in range(4)], axis=1)
+
+        dumped = {int(c): i for i, c in enumerate(g["cycles"])}
+        counts = set()
+        for c in range(41):
+            if c:
+                sim.step()
+            if c in dumped:
+                leaves, _ = H.leaves_from_bounds(g[f"bounds_{c}"], (64, 64, 1), (8, 8, 1), xmin=-1.0,
+                                                 xmax=1.0)
+                info = sim.info()
+                locs = np.array([sim.block(b)["loc"] for b in range(info["nblocks"])])
+                assert info["nbtotal"] == len(leaves) and np.array_equal(locs, leaves), f"cycle {c}"
+                assert sim.time == g["times"][dumped[c]]
+                assert np.array_equal(state(), g[f"U_{c}"], equal_nan=True), f"cycle {c}"
+                counts.add(info["nbtotal"])
+            if c:
+                sim.regrid()
+        assert len(counts) > 3
+    finally:
+        sim.close()
