@@ -641,7 +641,8 @@ def main():
             "math": args.math, "task_list": "reference-shaped" if args.unfused else "fused stage",
             "overrides": extra,
             "l2": "working set (>= 5.8 GB per GPU) exceeds the 126 MB L2; no flush needed",
-            "partition": f"Morton-contiguous gid ranges, {world} rank(s)"},
+            "partition": f"Morton-contiguous gid ranges, {world} rank(s)",
+            "inter_gpu_halo": sim.exchange_mode("base")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "ghost_exchange": ghost, "cycle_roofline": cycle_roof,
         "kernels": kernels, "parity": parity,

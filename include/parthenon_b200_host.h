@@ -148,6 +148,12 @@ int pb2h_sim_exchange_phase(pb2h_sim *sim, const char *container, int phase);
 /* Reals one exchange moves on this rank (ghost cells filled x components) */
 int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t *local,
                                    int64_t *nonlocal);
+/* how the inter-device halo of `container` travels: 0 no inter-device channels, 1 per-peer slabs
+ * + grouped ncclSend / ncclRecv, 2 peer push through the copy engines (pack, one device-to-device
+ * copy per peer into its receive slab, arrival flags), 3 peer push by the pack kernel (stores
+ * into the peers' receive slabs), 4 direct peer push (stores into the peers' ghost cells);
+ * -1 on error */
+int pb2h_sim_exchange_mode(pb2h_sim *sim, const char *container);
 /* the history columns "MS Mass 0..7" of the burgers benchmark, reduced over ranks */
 int pb2h_sim_history(pb2h_sim *sim, double out[8]);
 

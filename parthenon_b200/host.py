@@ -20,7 +20,7 @@ SYMBOLS = [
     "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor", "pb2h_sim_block_bcs",
-    "pb2h_topology_create_forest",
+    "pb2h_topology_create_forest", "pb2h_sim_exchange_mode",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_plan_boxes",
     "pb2h_sim_field_ptr", "pb2h_sim_field_dims",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_allocation", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
@@ -249,6 +249,7 @@ def lib():
     L.pb2h_sim_lane_sync.argtypes = [vp, C.c_int]
     L.pb2h_sim_exchange.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_phase.argtypes = [vp, C.c_char_p, C.c_int]
+    L.pb2h_sim_exchange_mode.argtypes = [vp, C.c_char_p]
     L.pb2h_sim_exchange_elements.restype = i64
     L.pb2h_sim_exchange_elements.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
     L.pb2h_sim_history.argtypes = [vp, dp]
@@ -588,6 +589,17 @@ class Simulation(_Base):
         if t < 0:
             check(-1)
         return lo.value, nl.value
+
+    def exchange_mode(self, container="base"):
+        """how the inter-device halo travels (include/parthenon_b200_host.h)"""
+        m = lib().pb2h_sim_exchange_mode(self.h, container.encode())
+        if m < 0:
+            check(-1)
+        return {0: "none", 1: "slabs + grouped ncclSend/ncclRecv",
+                2: "peer push: pack, copy-engine copies into the peers' receive slabs over "
+                   "NVLink (CUDA IPC), arrival flags, local unpack",
+                3: "peer push: pack kernel stores into the peers' receive slabs, arrival flags",
+                4: "peer push: copy kernel stores into the peers' ghost cells, arrival flags"}[m]
 
     def history(self):
         o = np.zeros(8)

@@ -635,6 +635,8 @@ void Mesh::RedistributeAndRefineMeshBlocks(const std::vector<LogicalLocation> &n
     // the regular ownership again (:992-996): plan and tables of the exchange are rebuilt
     newly_refined_.clear();
     ownership_.clear();
+    plan_cache.clear(); // (plans are shared through the mesh: the one just used ranked the new
+                        // blocks below the old ones and must not be found again)
     new_md->bvars().Invalidate();
   }
   // PreCommFillDerived; CommunicateBoundaries; FillDerived (:1000-1003)

@@ -686,6 +686,22 @@ int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t
   return total;
 }
 
+int pb2h_sim_exchange_mode(pb2h_sim *sim, const char *container) {
+  int mode = -1;
+  Guard([&] {
+    auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
+    BuildBoundaryBuffers(md);
+    const BvarsCache &c = md->bvars();
+    if (c.plan.send_elements + c.plan.recv_elements == 0)
+      mode = 0;
+    else if (!c.push_mode)
+      mode = 1;
+    else
+      mode = c.push_direct ? 4 : (c.push_ce ? 2 : 3);
+  });
+  return mode;
+}
+
 namespace {
 MetadataFlag FlagByName(const std::string &n) {
   static const std::map<std::string, MetadataFlag> m = {

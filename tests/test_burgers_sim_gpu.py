@@ -456,3 +456,27 @@ def test_adaptive_burgers_crc_vs_reference(math, fused):
     counts = check_against_crc_fixture("burgers_a32_b8_l2_crc", (32, 32, 32), (8, 8, 8), 24,
                                        state, sim.step, sim.regrid)
     assert counts == {120, 148, 176}
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_many_partitions_dt_and_history_match_one_partition(math):
+    """parthenon/mesh/pack_size = 1 on 64 blocks: 64 MeshData partitions per rank (more than the 32
+    scratch cells the per-partition minimum dt once shared), each with its own dt cell, local
+    channels between partitions through send / consumed generations.  The global time step of
+    every cycle must be the one-partition run's bit for bit, the mass histories agree to
+    summation order"""
+    one = host.Simulation(overrides=burgers_overrides(8, 4, 4, 2, "weno5", math, True))
+    many = host.Simulation(overrides=burgers_overrides(8, 4, 4, 2, "weno5", math, True,
+                                                       {"parthenon/mesh/pack_size": 1}))
+    try:
+        for s in (one, many):
+            s.pre_execute()
+        assert many.dt == one.dt
+        for c in range(4):
+            for s in (one, many):
+                s.cycle()
+            assert many.dt == one.dt and many.time == one.time, c
+        np.testing.assert_allclose(many.history(), one.history(), rtol=1e-13)
+    finally:
+        one.close()
+        many.close()
