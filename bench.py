@@ -402,6 +402,7 @@ def main():
                           rank=rank, nranks=world, nccl_id=nccl_id)
     info = sim.info()
     sim.pre_execute()
+    halo_mode = sim.exchange_mode("base")  # (every rank asks: building the tables is collective)
 
     def barrier():
         sim.sync()
@@ -642,7 +643,7 @@ def main():
             "overrides": extra,
             "l2": "working set (>= 5.8 GB per GPU) exceeds the 126 MB L2; no flush needed",
             "partition": f"Morton-contiguous gid ranges, {world} rank(s)",
-            "inter_gpu_halo": sim.exchange_mode("base")},
+            "inter_gpu_halo": halo_mode},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "ghost_exchange": ghost, "cycle_roofline": cycle_roof,
         "kernels": kernels, "parity": parity,

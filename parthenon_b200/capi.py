@@ -108,6 +108,8 @@ SYMBOLS = [
     "pb2_burgers_derived_dt", "pb2_burgers_history", "pb2_comm_unique_id", "pb2_comm_create", "pb2_comm_destroy",
     "pb2_comm_exchange", "pb2_comm_allreduce_min", "pb2_comm_allreduce_sum",
     "pb2_comm_barrier",
+    "pb2_ipc_export", "pb2_ipc_open", "pb2_ipc_close", "pb2_peer_handshake", "pb2_copy_signal",
+    "pb2_peer_signal", "pb2_peer_wait",
 ]
 
 
@@ -131,6 +133,11 @@ def lib():
     for f in ("pb2_memcpy_h2d", "pb2_memcpy_d2h", "pb2_memcpy_d2d"):
         getattr(L, f).argtypes = [vp, vp, C.c_size_t, vp]
     L.pb2_stream_sync.argtypes = [vp]
+    L.pb2_peer_handshake.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int32, vp]
+    L.pb2_copy_signal.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int32, vp]
+    L.pb2_peer_signal.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int32, vp]
+    L.pb2_peer_wait.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int32, vp]
+    L.pb2_ipc_export.argtypes = [vp, vp]
     L.pb2_bnd_table_create.argtypes = [C.POINTER(vp), C.POINTER(BndRegion), i64]
     L.pb2_copy_table_create.argtypes = [C.POINTER(vp), C.POINTER(CopyRegion), i64]
     L.pb2_prores_table_create.argtypes = [C.POINTER(vp), C.POINTER(ProResRegion), i64]

@@ -159,3 +159,52 @@ def test_sparse_exchange_halves():
     torch.cuda.synchronize()
     # ghost sources are interiors, which the exchange never writes: order does not matter
     assert np.array_equal(Ud.cpu().numpy(), ref)
+
+
+def test_peer_push_primitives_with_the_device_as_its_own_peer():
+    """pb2_peer_handshake / pb2_copy_signal / pb2_peer_signal / pb2_peer_wait through the C ABI,
+    one rank whose only peer is itself: the ready flag is raised and seen, the copy lands, the last
+    thread block raises the arrival flag and leaves the counter at zero, the wait returns; exchange
+    numbers only ever grow"""
+    from parthenon_b200 import capi
+    L = capi.lib()
+    n, ncomp = 12, 3
+    rng = np.random.default_rng(3)
+    src = torch.from_numpy(rng.standard_normal((ncomp, n, n, n))).to("cuda:0")
+    dst = torch.zeros_like(src)
+    r = capi.CopyRegion()
+    r.src, r.dst = src.data_ptr(), dst.data_ptr()
+    r.ss[:] = (1, 2, 3)
+    r.ds[:] = (4, 0, 5)
+    r.n[:] = (6, 7, 4)
+    r.ncomp = ncomp
+    r.src_stride_j = r.dst_stride_j = n
+    r.src_stride_k = r.dst_stride_k = n * n
+    r.src_stride_c = r.dst_stride_c = n * n * n
+    r.flag_slot = -1
+    r.status = capi.REGION_ALLOCATED
+    t = capi.Table([r], "copy")
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda:0")      # [ready][arrival] x 1 rank
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    peers = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    peer_flags = torch.tensor([flags.data_ptr()], dtype=torch.int64, device="cuda:0")
+    want = torch.zeros_like(src)
+    want[:, 5:9, 0:7, 4:10] = src[:, 3:7, 2:9, 1:7]
+    for seq in (1, 2, 3):
+        dst.zero_()
+        capi.check(L.pb2_peer_handshake(peer_flags.data_ptr(), flags.data_ptr(), peers.data_ptr(),
+                                        1, 0, 1, seq, None))
+        capi.check(L.pb2_copy_signal(t.h, counter.data_ptr(), peer_flags.data_ptr(), 1, 0, 1, seq,
+                                     None))
+        capi.check(L.pb2_peer_wait(flags.data_ptr(), peers.data_ptr(), 1, 1, seq, None))
+        torch.cuda.synchronize()
+        assert flags.tolist() == [seq, seq] and counter.item() == 0
+        assert torch.equal(dst, want)
+    # the copy-engine form: the caller moves the data itself, then signals
+    capi.check(L.pb2_peer_handshake(peer_flags.data_ptr(), flags.data_ptr(), peers.data_ptr(),
+                                    1, 0, 1, 4, None))
+    capi.check(L.pb2_memcpy_d2d(dst.data_ptr(), src.data_ptr(), src.numel() * 8, None))
+    capi.check(L.pb2_peer_signal(peer_flags.data_ptr(), 1, 0, 1, 4, None))
+    capi.check(L.pb2_peer_wait(flags.data_ptr(), peers.data_ptr(), 1, 1, 4, None))
+    torch.cuda.synchronize()
+    assert flags.tolist() == [4, 4] and torch.equal(dst, src)
