@@ -1,7 +1,10 @@
 /* pb2_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).  See pb2_oracle.h.
  *
  * Plain-C restatement of the reference's ghost-zone hot path: mesh topology for a
- * single-tree forest, boundary index boxes, pack/unpack, restriction/prolongation at
+ * single-tree forest (forests of differently oriented trees: topology in oracle/forest.py,
+ * handed over through orc_mesh_create_custom), boundary index boxes, pack/unpack — through the
+ * neighbour tree's LogicalCoordinateTransformation where there is one —,
+ * restriction/prolongation at
  * fine-coarse boundaries, flux correction, physical boundaries, the benchmarks/burgers RK2
  * cycle, example/advection and example/sparse_advection (uniform, statically and adaptively
  * refined meshes), and the exchange / remesh of face, edge and node fields with block
@@ -3716,8 +3719,9 @@ int orc_get_max_threads(void) {
  *     out[dir] = dir_flip[dir] ? ncell - 1 - in[|dir_connection[dir]|] : in[...]
  *     var(c, out[2], out[1], out[0]) = fac * buf[m]
  * var: one block's array [ncomp][nk][nj][ni] given by its strides; s / n: box start / extent.
- * The reference has no test or fixture for this kernel other than example/boundary_exchange
- * (HDF5 gold file, not in the tree): this restatement is pinned by its properties only
+ * Stand-alone form of what orc_unpack does for a transformed neighbour (that one is pinned
+ * against the reference's forest dumps, tests/golden/forest_*.npz); this entry serves the
+ * kernel-level tests of pb2_unpack over all 48 transformations and is checked by its properties
  * (identity = plain unpack, a flip applied twice, an axis permutation and its inverse). */
 void orc_unpack_box_transformed(double *var, int64_t stride_j, int64_t stride_k, int64_t stride_c,
                                 const int s[3], const int n[3], int ncomp, const double *buf,

@@ -782,7 +782,13 @@ int pb2h_sim_set_sparse_allocation(pb2h_sim *sim, const char *field, int lid, in
 
 int pb2h_sim_history(pb2h_sim *sim, double out[8]) {
   return Guard([&] {
-    auto v = burgers_package::MassHistory(sim->pm()->mesh_data.GetOrAdd("base", 0).get());
+    // one column per octant, summed over the MeshData batches of this rank (outputs/history.cpp:
+    // 47-200), then over the ranks
+    std::vector<Real> v(8, 0.0);
+    for (int p = 0; p < sim->pm()->DefaultNumPartitions(); ++p) {
+      const auto part = burgers_package::MassHistory(sim->pm()->mesh_data.GetOrAdd("base", p).get());
+      for (int o = 0; o < 8; ++o) v[o] += part[o];
+    }
     sim->pm()->ReduceHistory(v);
     for (int o = 0; o < 8; ++o) out[o] = v[o];
   });

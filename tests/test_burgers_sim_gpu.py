@@ -476,7 +476,7 @@ def test_many_partitions_dt_and_history_match_one_partition(math):
             for s in (one, many):
                 s.cycle()
             assert many.dt == one.dt and many.time == one.time, c
-        np.testing.assert_allclose(many.history(), one.history(), rtol=1e-13)
+        np.testing.assert_allclose(many.history(), one.history(), rtol=1e-12)
     finally:
         one.close()
         many.close()
