@@ -71,6 +71,8 @@ def lib():
                                                   C.c_int, C.c_int, ip, ip, ip]
         L.orc_exchange_te_ml_toth_roe.argtypes = [C.c_void_p, dp, dp, C.c_int]
         L.orc_exchange_te_ml_toth_roe.restype = C.c_int64
+        L.orc_flux_correct_edge.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_void_p]
+        L.orc_flux_correct_edge.restype = C.c_int64
         L.orc_flux_correct.restype = C.c_int64
         L.orc_flux_correct.argtypes = [C.c_void_p, C.POINTER(dp), C.c_int]
         L.orc_weno5z.argtypes = [C.c_double] * 5 + [dp, dp]
@@ -332,6 +334,22 @@ class Mesh:
         if shared_op:
             return lib().orc_exchange_te_ml_op(self.h, _dp(U), _dp(Uc), U.shape[2], kind, shared_op)
         return lib().orc_exchange_te_ml(self.h, _dp(U), _dp(Uc), U.shape[2], kind)
+
+    def flux_correct_edge(self, F, deliveries=None):
+        """flux correction of a FACE field: F is its edge-centred flux field
+        [nblocks][3 elements][ncomp][nk'][nj'][ni'] (te_extents(2)), corrected in place; returns
+        the number of Reals the fine blocks sent.  deliveries: optional int32 array of F's shape
+        that receives how often each entry was written (> 1: the reference is not deterministic
+        there, see pb2_oracle.c)"""
+        assert F.flags.c_contiguous and F.shape[1] == 3 and F.shape[3:] == self.te_extents(2)
+        cd = tuple(n + (1 if n > 1 else 0) for n in self.cdims)
+        Fc = np.zeros(F.shape[:3] + cd)
+        w = None
+        if deliveries is not None:
+            assert deliveries.dtype == np.int32 and deliveries.shape == F.shape
+            assert deliveries.flags.c_contiguous
+            w = deliveries.ctypes.data
+        return lib().orc_flux_correct_edge(self.h, _dp(F), _dp(Fc), F.shape[2], w)
 
     def flux_correct(self, F):
         """F: three face-flux arrays [nblocks][ncomp][nk][nj][ni], corrected in place"""

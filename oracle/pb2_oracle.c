@@ -1115,6 +1115,10 @@ static inline int te_active(const TeBox *bx, int k, int j, int i) {
 /* el is a TopologicalElement in its own right here (kind, el): the box of a cell / face /
  * edge / node element whatever the field holds (ProResInfo carries all ten, bnd_info.cpp:
  * 440-446) */
+/* flux = true in CalcIndices (bnd_info.cpp:207-218): fluxes are only communicated on the
+ * elements two blocks share — along a direction the neighbour is offset in, the box is the one
+ * plane of the element's interior range that lies on the boundary */
+static int g_te_flux_boxes = 0;
 static void calc_indices_te_general(const OrcMesh *m, int b, int n, int kind, int el,
                                     int ir_type, int prores, TeBox *out) {
   const Block *blk = &m->blocks[b];
@@ -1150,9 +1154,11 @@ static void calc_indices_te_general(const OrcMesh *m, int b, int n, int kind, in
     } else if (nb->off[d] > 0) {
       *s = be + (-interior_offset + 1 - top[d]);
       *e = be + exterior_offset;
+      if (g_te_flux_boxes) *s = *e = be;
     } else {
       *s = bs - exterior_offset;
       *e = bs + (interior_offset - 1 + top[d]);
+      if (g_te_flux_boxes) *s = *e = bs;
     }
   }
   for (int q = 0; q < 27; ++q) out->mask[q] = 1;
@@ -1622,6 +1628,150 @@ static int64_t exchange_te_impl(const OrcMesh *m, double *U, double *Uc, int nco
   return total;
 }
 #undef OWN
+
+/* ------------------------------------------------------------------------------------ */
+/* Flux correction of a FACE field: its flux is an EDGE field (Metadata::Flux | Edge,
+ * state_descriptor.cpp:313-318).  A fine block restricts (RestrictAverage per element) the edge
+ * fluxes it shares with a neighbour ONE level coarser — across a face the two edge elements
+ * tangent to it, across a block edge the one element along it (GetFluxCorrectionElements,
+ * bnd_info.cpp:71-103; neighbour filter of ForEachBoundary<flxcor_*>, loop_utils.hpp:134-158) —
+ * into its coarse buffer (ProResInfo::GetSend :387-403), sends them from there, and the coarse
+ * block writes those the sending block owns into its flux array (SetBounds<flxcor_recv> with
+ * the mask of block_ownership.cpp:85-140).  F: [block][3 elements][ncomp][k][j][i] with the
+ * extents of orc_te_extents(kind = edge); Fc: the coarse buffers. */
+static int te_flux_elements(const int off[3], int els[2]) {
+  const int nz = (off[0] != 0) + (off[1] != 0) + (off[2] != 0);
+  if (nz == 1) { /* face: E2,E3 | E3,E1 | E1,E2 */
+    if (off[0]) { els[0] = 1; els[1] = 2; }
+    if (off[1]) { els[0] = 2; els[1] = 0; }
+    if (off[2]) { els[0] = 0; els[1] = 1; }
+    return 2;
+  }
+  if (nz == 2) { /* edge: the element along it */
+    els[0] = off[0] == 0 ? 0 : (off[1] == 0 ? 1 : 2);
+    return 1;
+  }
+  return 0;
+}
+
+/* Where the reference is not deterministic: a coarse edge entry on the rim of a face can be
+ * delivered twice, by the fine block across the face and by a fine block across the block edge
+ * (2-D: corner) next to it.  The mask consults ownership only at the two ends of a box range; a
+ * range of ONE entry — every direction a flux box is offset in — counts as interior
+ * (indexer.hpp:171-173), so both messages are active, they carry the two fine blocks' own
+ * values, and SetBounds unpacks the messages in a shuffled order on parallel teams
+ * (bvals_utils.hpp:108-112).  Here the messages across faces are unpacked after those across
+ * block edges, so the face neighbour's value stays; wcount (optional, one int per entry of F)
+ * counts the deliveries, which lets a test leave doubly delivered entries out of a comparison
+ * with a reference dump. */
+int64_t orc_flux_correct_edge(const OrcMesh *m, double *F_, double *Fc, int ncomp, int *wcount) {
+  const int kind = ORC_TE_EDGE;
+  TeField F;
+  F.m = m;
+  F.U = F_;
+  F.Uc = Fc;
+  F.ncomp = ncomp;
+  F.nel = 3;
+  orc_te_extents(m, kind, F.pn);
+  for (int d = 0; d < 3; ++d) F.cpn[d] = m->cn[d] + (m->cn[d] > 1 ? 1 : 0);
+  F.blk_sz = (size_t)F.nel * ncomp * F.pn[2] * F.pn[1] * F.pn[0];
+  F.cblk_sz = (size_t)F.nel * ncomp * F.cpn[2] * F.cpn[1] * F.cpn[0];
+  if (!m->multilevel) return 0;
+  g_te_flux_boxes = 1;
+  TeBox bx;
+  int64_t *first = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m->nblocks + 1));
+  first[0] = 0;
+  for (int b = 0; b < m->nblocks; ++b) first[b + 1] = first[b] + m->blocks[b].nnb;
+  int64_t *off = (int64_t *)calloc((size_t)first[m->nblocks] + 1, sizeof(int64_t));
+  /* send side: restrict, then size and fill the buffers */
+  int64_t total = 0;
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      off[first[b] + n] = total;
+      const Neighbor *nb = &blk->nb[n];
+      int els[2];
+      const int ne = nb->loc.level == blk->loc.level - 1 ? te_flux_elements(nb->off, els) : 0;
+      for (int q = 0; q < ne; ++q) {
+        calc_indices_te_general(m, b, n, kind, els[q], IR_SEND, 1, &bx);
+        for (int c = 0; c < ncomp; ++c)
+          for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+            for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+              for (int i = bx.s[0]; i <= bx.e[0]; ++i) te_restrict(&F, kind, b, els[q], c, k, j, i);
+        calc_indices_te_general(m, b, n, kind, els[q], IR_SEND, 0, &bx);
+        total += (int64_t)ncomp * (bx.e[2] - bx.s[2] + 1) * (bx.e[1] - bx.s[1] + 1) *
+                 (bx.e[0] - bx.s[0] + 1);
+      }
+    }
+  }
+  double *buf = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      int els[2];
+      const int ne = nb->loc.level == blk->loc.level - 1 ? te_flux_elements(nb->off, els) : 0;
+      double *p = buf + off[first[b] + n];
+      for (int q = 0; q < ne; ++q) {
+        calc_indices_te_general(m, b, n, kind, els[q], IR_SEND, 0, &bx);
+        for (int c = 0; c < ncomp; ++c)
+          for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+            for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+              for (int i = bx.s[0]; i <= bx.e[0]; ++i) *p++ = *te_c(&F, b, els[q], c, k, j, i);
+      }
+    }
+  }
+  /* receive side: the coarser block, under the ownership mask of the sender; messages across
+   * block edges first, then those across faces */
+  for (int pass = 0; pass < 2; ++pass)
+  for (int b = 0; b < m->nblocks; ++b) {
+    const Block *blk = &m->blocks[b];
+    for (int n = 0; n < blk->nnb; ++n) {
+      const Neighbor *nb = &blk->nb[n];
+      int els[2];
+      const int ne = nb->loc.level == blk->loc.level + 1 ? te_flux_elements(nb->off, els) : 0;
+      if (ne == 0 || ne != pass + 1) continue; /* one element: block edge; two: face */
+      const Block *sb = &m->blocks[nb->gid];
+      int sn = -1;
+      for (int q = 0; q < sb->nnb; ++q)
+        if (sb->nb[q].gid == b && sb->nb[q].off[0] == -nb->off[0] &&
+            sb->nb[q].off[1] == -nb->off[1] && sb->nb[q].off[2] == -nb->off[2]) {
+          sn = q;
+          break;
+        }
+      if (sn < 0) {
+        fprintf(stderr, "oracle: no matching flux-correction sender (block %d nb %d)\n", b, n);
+        abort();
+      }
+      const double *p = buf + off[first[nb->gid] + sn];
+      for (int q = 0; q < ne; ++q) {
+        TeBox sx;
+        calc_indices_te_general(m, b, n, kind, els[q], IR_RECV, 0, &bx);
+        calc_indices_te_general(m, nb->gid, sn, kind, els[q], IR_SEND, 0, &sx);
+        for (int d = 0; d < 3; ++d)
+          if (bx.e[d] - bx.s[d] != sx.e[d] - sx.s[d]) {
+            fprintf(stderr, "oracle: flux-correction box mismatch (block %d nb %d el %d dir %d)\n",
+                    b, n, els[q], d);
+            abort();
+          }
+        for (int c = 0; c < ncomp; ++c)
+          for (int k = bx.s[2]; k <= bx.e[2]; ++k)
+            for (int j = bx.s[1]; j <= bx.e[1]; ++j)
+              for (int i = bx.s[0]; i <= bx.e[0]; ++i, ++p)
+                if (te_active(&bx, k, j, i)) {
+                  double *dst = te_f(&F, b, els[q], c, k, j, i);
+                  *dst = *p;
+                  if (wcount) wcount[dst - F.U]++;
+                }
+      }
+    }
+  }
+  g_te_flux_boxes = 0;
+  free(buf);
+  free(off);
+  free(first);
+  return total;
+}
 
 int64_t orc_exchange_te(const OrcMesh *m, double *U, int ncomp, int kind) {
   if (m->multilevel) {

@@ -213,7 +213,7 @@ run_tecomm () { # name ndim nx nb ng [numlevel "regions"]
       $n $lev $a $b $c $e $f $g >> deck.pin
     n=$((n+1))
   done
-  PB2_DUMP_PREFIX="$d/U" "$WORK/tecomm_dump" -i deck.pin ${TECOMM_ARGS:-} > run.log 2>&1
+  PB2_DUMP_PREFIX="$d/U" "${TECOMM_BIN:-$WORK/tecomm_dump}" -i deck.pin ${TECOMM_ARGS:-} > run.log 2>&1
   python3 "$HERE/pack_dumps.py" "$d" "$OUT/$name.npz"
 }
 if [ -z "${SKIP_TECOMM:-}" ]; then
@@ -323,6 +323,37 @@ run_hst () { local name=$1 nx=$2 nb=$3 nlim=$4
 }
 run_hst burgers_u64_b32_s8_weno5 64 32 10
 echo "fixtures written to $OUT"
+
+# flux correction of a FACE field (its flux is an edge field): restricted edge fluxes cross
+# fine-coarse faces and block edges, the owner's values land (teflux_dump_main.cpp)
+if [ ! -x "$WORK/teflux_dump" ] || [ "$HERE/teflux_dump_main.cpp" -nt "$WORK/teflux_dump" ]; then
+  $CXX $FLAGS $INC "$HERE/teflux_dump_main.cpp" $LIBS -o "$WORK/teflux_dump"
+fi
+run_teflux () { # name ndim nx nb ng numlevel "regions"
+  local name=$1
+  TECOMM_BIN="$WORK/teflux_dump" run_tecomm "$@"
+}
+if [ -z "${SKIP_TEFLUX:-}" ]; then
+run_teflux teflux_s16_b8_l2_3d 3 16 8 2 2 "1:0.05:0.2:0.05:0.2:0.05:0.2"
+run_teflux teflux_s32_b8_l3_2d 2 32 8 2 3 "1:-0.3:0.1:-0.2:0.2:0:0 2:-0.12:-0.05:0.02:0.12:0:0"
+run_teflux teflux_s16_b4_g4_l3_3d 3 16 4 4 3 "1:-0.3:0.1:-0.2:0.2:-0.1:0.3 2:-0.12:-0.05:0.02:0.12:0.05:0.12"
+# 197 blocks: kept as the entries the flux correction changed (flat index into U_0 and value;
+# every other entry still holds the generator's code).  Not a CRC: a handful of entries are
+# delivered twice and the reference keeps either value (see oracle/pb2_oracle.c)
+python3 - "$OUT/teflux_s16_b4_g4_l3_3d.npz" "$OUT/teflux_s16_b4_g4_l3_3d_sparse.npz" <<'PYEOF'
+import sys
+import numpy as np
+g = np.load(sys.argv[1])
+a = g["U_0"]
+nb, nc, nk, nj, ni = a.shape
+init = ((np.arange(nb).reshape(-1, 1, 1, 1, 1) + 1) * 1.0e6 + np.arange(3).reshape(1, -1, 1, 1, 1) * 1.0e5
+        + np.arange(nk * nj * ni).reshape(1, 1, nk, nj, ni)).astype(np.float64)
+ch = np.flatnonzero(a != init)
+np.savez_compressed(sys.argv[2], meta=g["meta"], bounds=g["bounds"], shape_0=np.array(a.shape),
+                    changed_idx=ch.astype(np.int64), changed_val=a.reshape(-1)[ch])
+PYEOF
+rm -f "$OUT/teflux_s16_b4_g4_l3_3d.npz"
+fi
 
 # forests of differently oriented trees (ForestDefinition as in example/boundary_exchange): the
 # ghost exchange through LogicalCoordinateTransformations; variants in forest_dump_main.cpp

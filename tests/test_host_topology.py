@@ -108,6 +108,22 @@ def plans_consistent(ov, nranks, ncomp, leaves=None):
         for row in rows:
             recvs.setdefault((int(row[6]), r), []).append((tuple(row[:4]), row[4] - seg[row[6]], row[5]))
     assert sends.keys() == recvs.keys()
+    # peer push: a sender addresses the receiver's slab as "the receiver's segment
+    # offset for me + the channel's offset inside my segment for it" — it must be where the
+    # receiver's own plan unpacks that channel from
+    recv_abs = {}
+    segs = []
+    for r, t in enumerate(tops):
+        rows, seg = t.plan(ncomp, "recv")
+        segs.append(seg)
+        for row in rows:
+            recv_abs[(r,) + tuple(int(x) for x in row[:4])] = int(row[4])
+    for r, t in enumerate(tops):
+        rows, seg = t.plan(ncomp, "send")
+        for row in rows:
+            peer = int(row[6])
+            dst = int(segs[peer][r]) + int(row[4] - seg[peer])
+            assert dst == recv_abs[(peer,) + tuple(int(x) for x in row[:4])]
     total = 0
     for key in sends:
         assert sends[key] == recvs[key], key
