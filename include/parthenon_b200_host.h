@@ -148,6 +148,16 @@ int pb2h_sim_exchange_phase(pb2h_sim *sim, const char *container, int phase);
 /* Reals one exchange moves on this rank (ghost cells filled x components) */
 int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t *local,
                                    int64_t *nonlocal);
+/* flux correction of a face field (edge-centred flux) as pure topology, rows of 13 int64:
+ * kind 0, restrictions on fine blocks: [gid, 0, element 0..2 (E1..E3), 0, s(i,j,k) in the coarse
+ * index space, 0, 0, 0, n(i,j,k)]; kind 1, deliveries: [sender gid, receiver gid, element, pass
+ * (0: across a block edge, 1: across a face, delivered second), send_s(i,j,k) in the sender's
+ * coarse buffer, recv_s(i,j,k) in the receiver's array, n(i,j,k)].  Returns the count. */
+int64_t pb2h_sim_edge_flux_plan(pb2h_sim *sim, int kind, int64_t *rows, int64_t max_rows);
+/* AddFluxCorrectionTasks (boundary_communication.cpp:454-461) on every partition of `container`:
+ * fine blocks restrict the fluxes they share with coarser neighbours, the coarser blocks take
+ * them — face fluxes of cell-centred fields and the edge-centred fluxes of face fields */
+int pb2h_sim_flux_correction(pb2h_sim *sim, const char *container);
 /* how the inter-device halo of `container` travels: 0 no inter-device channels, 1 per-peer slabs
  * + grouped ncclSend / ncclRecv, 2 peer push through the copy engines (pack, one device-to-device
  * copy per peer into its receive slab, arrival flags), 3 peer push by the pack kernel (stores

@@ -20,7 +20,7 @@ SYMBOLS = [
     "pb2h_sim_pre_execute", "pb2h_sim_cycle", "pb2h_sim_cycle_phase", "pb2h_sim_execute", "pb2h_sim_sync",
     "pb2h_sim_stream", "pb2h_sim_time", "pb2h_sim_dt", "pb2h_sim_ncycle", "pb2h_sim_set_dt",
     "pb2h_sim_zone_cycles_per_second", "pb2h_sim_info", "pb2h_sim_block", "pb2h_sim_neighbor", "pb2h_sim_block_bcs",
-    "pb2h_topology_create_forest", "pb2h_sim_exchange_mode",
+    "pb2h_topology_create_forest", "pb2h_sim_exchange_mode", "pb2h_sim_flux_correction", "pb2h_sim_edge_flux_plan",
     "pb2h_sim_calc_indices", "pb2h_sim_ranklist", "pb2h_sim_plan", "pb2h_sim_plan_boxes",
     "pb2h_sim_field_ptr", "pb2h_sim_field_dims",
     "pb2h_sim_get_field", "pb2h_sim_set_field", "pb2h_sim_allocation", "pb2h_sim_exchange", "pb2h_sim_exchange_phase",
@@ -250,6 +250,9 @@ def lib():
     L.pb2h_sim_exchange.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_phase.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb2h_sim_exchange_mode.argtypes = [vp, C.c_char_p]
+    L.pb2h_sim_flux_correction.argtypes = [vp, C.c_char_p]
+    L.pb2h_sim_edge_flux_plan.restype = i64
+    L.pb2h_sim_edge_flux_plan.argtypes = [vp, C.c_int, C.POINTER(i64), i64]
     L.pb2h_sim_exchange_elements.restype = i64
     L.pb2h_sim_exchange_elements.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]
     L.pb2h_sim_history.argtypes = [vp, dp]
@@ -362,6 +365,17 @@ class _Base:
             check(-1)
         rows = np.zeros((max(n, 1), 18), dtype=np.int64)
         lib().pb2h_sim_plan_boxes(self.h, ncomp, tt, k, rows.ctypes.data_as(C.POINTER(C.c_int64)), n)
+        return rows[:n]
+
+    def edge_flux_plan(self, kind):
+        """flux correction of a face field as topology: kind 'restrict' | 'deliver' -> rows[n, 13]
+        (include/parthenon_b200_host.h)"""
+        k = {"restrict": 0, "deliver": 1}[kind]
+        n = lib().pb2h_sim_edge_flux_plan(self.h, k, None, 0)
+        if n < 0:
+            check(-1)
+        rows = np.zeros((max(n, 1), 13), dtype=np.int64)
+        lib().pb2h_sim_edge_flux_plan(self.h, k, rows.ctypes.data_as(C.POINTER(C.c_int64)), n)
         return rows[:n]
 
     def close(self):
@@ -589,6 +603,11 @@ class Simulation(_Base):
         if t < 0:
             check(-1)
         return lo.value, nl.value
+
+    def flux_correction(self, container="base"):
+        """AddFluxCorrectionTasks on `container` (face fluxes of cell-centred fields, edge-centred
+        fluxes of face fields)"""
+        check(lib().pb2h_sim_flux_correction(self.h, container.encode()))
 
     def exchange_mode(self, container="base"):
         """how the inter-device halo travels (include/parthenon_b200_host.h)"""

@@ -113,6 +113,28 @@ struct PlanVar {
   int ncomp = 1;
   TopologicalType tt = TopologicalType::Cell;
 };
+// index boxes and elements of the flux correction of a face field, whose flux is an edge field
+// (bnd_info.cpp:71-103, :207-218)
+IndexBox CalcIndicesFluxTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
+                           IndexRangeType ir_type, bool prores);
+std::vector<TE> FluxCorrectionEdgeElements(const int off[3]);
+// The flux correction of a face field as pure topology: which coarse boxes of which element the
+// fine blocks restrict, and which (sender coarse-buffer box -> receiver box) pieces deliver them
+// — one piece per active sub-box of the sender's ownership mask; pass 0: across block edges,
+// pass 1: across faces (delivered second).  Same-device neighbours only.
+struct EdgeFluxRestrict {
+  int gid, el; // el: 0..2 = E1..E3
+  IndexBox box;
+};
+struct EdgeFluxPiece {
+  int sender_gid, receiver_gid, el, pass;
+  IndexBox send_box, recv_box;
+};
+struct EdgeFluxPlan {
+  std::vector<EdgeFluxRestrict> restricts;
+  std::vector<EdgeFluxPiece> pieces;
+};
+EdgeFluxPlan BuildEdgeFluxPlan(const Mesh *pm, const BlockList_t &blocks);
 ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
                                const std::vector<PlanVar> &vars);
 
@@ -224,6 +246,13 @@ struct BvarsCache {
   // fused restrict+deliver for same-device channels, restrict-into-slab + unpack for the rest
   bool flxcor_built = false;
   pb2_bnd_table *flxcor_local = nullptr, *flxcor_pack = nullptr, *flxcor_unpack = nullptr;
+  // ... of a FACE field: its flux is the edge field "bnd_flux::<name>".  Fine blocks restrict the
+  // shared edge elements into the flux field's coarse buffer (teflx_restrict), then they are
+  // copied into the coarser block's flux array under the sender's ownership mask, messages
+  // across block edges first ([0]), across faces second ([1]) — see oracle/pb2_oracle.c on why
+  // the order matters.  Same-device channels only.
+  pb2_bnd_table *teflx_restrict = nullptr, *teflx_copy[2] = {nullptr, nullptr};
+  int64_t teflx_elements = 0;
   std::vector<int64_t> flxcor_send_off, flxcor_recv_off; // [npeers + 1]
   int64_t flxcor_send_elements = 0, flxcor_recv_elements = 0, flxcor_local_elements = 0;
   DeviceBuffer flxcor_send_slab, flxcor_recv_slab;

@@ -207,6 +207,14 @@ class StateDescriptor {
   bool AddField(const std::string &field_name, const Metadata &m) {
     for (auto &f : fields_)
       if (f.name == field_name) return false;
+    // the flux of a face field is a field of its own, one topological type up: an edge field
+    // "bnd_flux::<name>" with Metadata::Flux, shared between the containers
+    // (state_descriptor.cpp:313-318, metadata.cpp:175-205).  Cell-centred fields keep their
+    // face fluxes inside the Variable (Variable::flux).
+    if (m.IsSet(Metadata::Face) && m.IsSet(Metadata::WithFluxes)) {
+      Metadata fm({Metadata::Edge, Metadata::Flux, Metadata::OneCopy, Metadata::Derived}, m.Shape());
+      fields_.push_back(FieldEntry{"bnd_flux::" + field_name, fm, -1});
+    }
     fields_.push_back(FieldEntry{field_name, m, -1});
     return true;
   }

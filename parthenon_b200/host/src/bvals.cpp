@@ -53,6 +53,10 @@ void BvarsCache::Clear() {
   pb2_bnd_table_destroy(flxcor_pack);
   pb2_bnd_table_destroy(flxcor_unpack);
   flxcor_local = flxcor_pack = flxcor_unpack = nullptr;
+  pb2_bnd_table_destroy(teflx_restrict);
+  pb2_bnd_table_destroy(teflx_copy[0]);
+  pb2_bnd_table_destroy(teflx_copy[1]);
+  teflx_restrict = teflx_copy[0] = teflx_copy[1] = nullptr;
   flxcor_built = false;
   built_generation = 0;
 }
@@ -1117,7 +1121,9 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
   Mesh *pm = md->GetMeshPointer();
   const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
   const int npeers = V > 1 ? V * V : pm->nranks;
-  std::vector<Variable *> vars = md->GetVariablesByFlag({Metadata::WithFluxes});
+  std::vector<Variable *> vars;
+  for (Variable *v : md->GetVariablesByFlag({Metadata::WithFluxes}))
+    if (v->topological_type() == TopologicalType::Cell) vars.push_back(v);
   std::vector<pb2_flxcor_region> local;
   std::vector<FlxChannel> send, recv;
   c.flxcor_local_elements = 0;
@@ -1258,6 +1264,60 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
     c.flxcor_send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.flxcor_send_elements), md->stream());
   if (c.flxcor_recv_elements > 0)
     c.flxcor_recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.flxcor_recv_elements), md->stream());
+
+  // ---- fluxes of face fields: edge-centred flux fields (Metadata::Flux | Edge) ----
+  std::vector<pb2_prores_region> te_restricts;
+  std::vector<pb2_copy_region> te_copies[2];
+  c.teflx_elements = 0;
+  std::array<bool, 27> all_true;
+  all_true.fill(true);
+  const std::vector<Variable *> fvars = md->GetVariablesByFlag({Metadata::Flux});
+  EdgeFluxPlan fplan;
+  if (!fvars.empty() && pm->multilevel) fplan = BuildEdgeFluxPlan(pm, md->GetBlockList());
+  for (Variable *fv : fvars) {
+    PARTHENON_REQUIRE(fv->topological_type() == TopologicalType::Edge,
+                      "flux fields other than the edge-centred flux of a face field are not built");
+    const TE edge_els[3] = {TE::E1, TE::E2, TE::E3};
+    const int nc = fv->TensorComponents();
+    for (const EdgeFluxRestrict &rr : fplan.restricts) {
+      // the fine sender may sit in another partition of this device; all partitions share the
+      // stream, so restricting its coarse buffer from here is ordered before the copies below
+      const MeshBlock *sb = pm->block_list[pm->GetLid(rr.gid)].get();
+      AddTeRegions(te_restricts, ContainerOf(md, sb)->Get(fv->label()), sb, rr.el,
+                   edge_els[rr.el], nullptr, rr.box, all_true, pm->ndim);
+    }
+    for (const EdgeFluxPiece &pc : fplan.pieces) {
+      const MeshBlock *sb = pm->block_list[pm->GetLid(pc.sender_gid)].get();
+      const MeshBlock *rb = pm->block_list[pm->GetLid(pc.receiver_gid)].get();
+      Variable &sv = ContainerOf(md, sb)->Get(fv->label());
+      pb2_copy_region r{};
+      r.src = sv.coarse() + sb->pack_index * sv.cblock_stride +
+              static_cast<int64_t>(pc.el) * nc * sv.ccomp_stride;
+      r.dst = fv->data() + rb->pack_index * fv->block_stride +
+              static_cast<int64_t>(pc.el) * nc * fv->comp_stride;
+      for (int d = 0; d < 3; ++d) {
+        r.ss[d] = pc.send_box.s[d];
+        r.ds[d] = pc.recv_box.s[d];
+        r.n[d] = pc.recv_box.n(d);
+      }
+      r.ncomp = nc;
+      r.src_stride_j = sv.cni;
+      r.src_stride_k = sv.cni * sv.cnj;
+      r.src_stride_c = static_cast<int32_t>(sv.ccomp_stride);
+      r.dst_stride_j = fv->ni;
+      r.dst_stride_k = fv->ni * fv->nj;
+      r.dst_stride_c = static_cast<int32_t>(fv->comp_stride);
+      r.flag_slot = -1;
+      r.status = PB2_REGION_ALLOCATED;
+      c.teflx_elements += static_cast<int64_t>(nc) * r.n[0] * r.n[1] * r.n[2];
+      te_copies[pc.pass].push_back(r);
+    }
+  }
+  PB2_CHECK(pb2_prores_table_create(&c.teflx_restrict, te_restricts.data(),
+                                    static_cast<int64_t>(te_restricts.size())));
+  for (int pass = 0; pass < 2; ++pass)
+    PB2_CHECK(pb2_copy_table_create(&c.teflx_copy[pass], te_copies[pass].data(),
+                                    static_cast<int64_t>(te_copies[pass].size())));
   if (!c.flxcor_packed) {
     PB2_CHECK(pb2_event_create(&c.flxcor_packed));
     PB2_CHECK(pb2_event_create(&c.flxcor_received));
@@ -1301,6 +1361,11 @@ void SetFluxCorrectionsImpl(MeshData<Real> *md) {
   BvarsCache &c = FlxCache(md);
   pb2_stream_t st = md->stream();
   PB2_CHECK(pb2_flux_correct(c.flxcor_local, nullptr, st));
+  // edge-centred fluxes of face fields: restrict on the fine blocks, then deliver — across block
+  // edges first, across faces second (BvarsCache::teflx_copy)
+  PB2_CHECK(pb2_restrict_te(c.teflx_restrict, st));
+  PB2_CHECK(pb2_copy(c.teflx_copy[0], nullptr, st));
+  PB2_CHECK(pb2_copy(c.teflx_copy[1], nullptr, st));
   if (c.flxcor_in_flight) {
     PB2_CHECK(pb2_stream_wait_event(st, c.flxcor_received));
     PB2_CHECK(pb2_unpack(c.flxcor_unpack, c.flxcor_recv_slab.get<Real>(), nullptr, st));

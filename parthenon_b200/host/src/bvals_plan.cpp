@@ -115,6 +115,35 @@ IndexBox CalcIndicesTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
   return box;
 }
 
+// bnd_info.cpp:105-252 with flux = true for one element of an edge-centred flux field (the flux
+// of a face field): along a direction the neighbour is offset in, the box is the one plane of
+// the element's interior range that lies on the boundary (:207-218); tangentially as above
+IndexBox CalcIndicesFluxTE(const NeighborBlock &nb, const MeshBlock *pmb, TE el,
+                           IndexRangeType ir_type, bool prores) {
+  IndexBox box = CalcIndicesTE(nb, pmb, el, ir_type, prores);
+  const bool use_coarse = prores || nb.loc.level < pmb->loc.level;
+  const IndexShape &shape = use_coarse ? pmb->c_cellbounds : pmb->cellbounds;
+  for (int d = 0; d < 3; ++d) {
+    if (nb.offsets[d] == 0) continue;
+    const IndexRange b = shape.Bounds(d, IndexDomain::interior, el);
+    box.s[d] = box.e[d] = nb.offsets[d] > 0 ? b.e : b.s;
+  }
+  return box;
+}
+
+// GetFluxCorrectionElements (bnd_info.cpp:71-103) for an edge-centred flux field: the two edge
+// elements tangent to a shared face, the one along a shared block edge; none across a corner
+std::vector<TE> FluxCorrectionEdgeElements(const int off[3]) {
+  const int nz = (off[0] != 0) + (off[1] != 0) + (off[2] != 0);
+  if (nz == 1) {
+    if (off[0]) return {TE::E2, TE::E3};
+    if (off[1]) return {TE::E3, TE::E1};
+    return {TE::E1, TE::E2};
+  }
+  if (nz == 2) return {off[0] == 0 ? TE::E1 : (off[1] == 0 ? TE::E2 : TE::E3)};
+  return {};
+}
+
 std::array<bool, 27> RecvMask(const Mesh *pm, const NeighborBlock &nb, const MeshBlock *pmb,
                               TE el) {
   int sox[3] = {-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]};
@@ -283,6 +312,52 @@ IndexBox SubBox(const IndexBox &box, const IndexBox &rel) {
   return b;
 }
 } // namespace
+
+EdgeFluxPlan BuildEdgeFluxPlan(const Mesh *pm, const BlockList_t &blocks) {
+  EdgeFluxPlan plan;
+  for (auto &pmb : blocks) {
+    for (auto &nb : pmb->neighbors) {
+      // ForEachBoundary<flxcor_*> (loop_utils.hpp:134-158): neighbours one level apart across a
+      // face or a block edge
+      if (std::abs(nb.loc.level - pmb->loc.level) != 1) continue;
+      const std::vector<TE> els = FluxCorrectionEdgeElements(nb.offsets);
+      if (els.empty()) continue;
+      PARTHENON_REQUIRE(nb.rank == pm->my_rank &&
+                            pm->VirtualRankOf(nb.gid) == pm->VirtualRankOf(pmb->gid),
+                        "flux correction of face fields across devices is not built");
+      const int pass = els.size() == 2 ? 1 : 0;
+      for (TE el : els) {
+        const int e = static_cast<int>(el) % 3; // E1, E2, E3 -> 0, 1, 2 in storage order
+        // the fine SENDER's half is listed from the receiver's side below, so that a partition's
+        // tables hold everything its own blocks need, in order
+        if (nb.loc.level == pmb->loc.level - 1) continue;
+        // coarse RECEIVER: the sender's coarse-buffer box -> this block's flux array, the
+        // entries the sender owns (bnd_info.cpp:232-248)
+        const MeshBlock *sb = pm->block_list[nb.lid].get();
+        const NeighborBlock *q = MatchingNeighbor(sb, pmb->gid, nb.offsets);
+        PARTHENON_REQUIRE(q != nullptr, "no matching flux-correction sender");
+        // the sender restricts (RestrictAverage) the shared elements into its coarse buffer
+        // (ProResInfo::GetSend, bnd_info.cpp:387-403)
+        plan.restricts.push_back(
+            {nb.gid, e, CalcIndicesFluxTE(*q, sb, el, IndexRangeType::BoundaryInteriorSend, true)});
+        const IndexBox rbox =
+            CalcIndicesFluxTE(nb, pmb.get(), el, IndexRangeType::BoundaryExteriorRecv, false);
+        const IndexBox sbox =
+            CalcIndicesFluxTE(*q, sb, el, IndexRangeType::BoundaryInteriorSend, false);
+        int n[3];
+        for (int d = 0; d < 3; ++d) {
+          n[d] = rbox.n(d);
+          PARTHENON_REQUIRE(sbox.n(d) == n[d], "flux-correction extents differ");
+        }
+        const int sox[3] = {-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]};
+        const auto mask = IndexRangeMask(el, pm->Ownership(nb.gid), sox);
+        for (const IndexBox &rel : ActivePieces(n, mask))
+          plan.pieces.push_back({nb.gid, pmb->gid, e, pass, SubBox(sbox, rel), SubBox(rbox, rel)});
+      }
+    }
+  }
+  return plan;
+}
 
 ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
                                const std::vector<PlanVar> &vars) {

@@ -686,6 +686,50 @@ int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t
   return total;
 }
 
+int64_t pb2h_sim_edge_flux_plan(pb2h_sim *sim, int kind, int64_t *rows, int64_t max_rows) {
+  int64_t count = -1;
+  Guard([&] {
+    Mesh *pm = sim->pm();
+    const EdgeFluxPlan plan = BuildEdgeFluxPlan(pm, pm->block_list);
+    count = static_cast<int64_t>(kind == 0 ? plan.restricts.size() : plan.pieces.size());
+    if (!rows) return;
+    for (int64_t i = 0; i < std::min<int64_t>(count, max_rows); ++i) {
+      int64_t *r = rows + 13 * i;
+      for (int q = 0; q < 13; ++q) r[q] = 0;
+      if (kind == 0) {
+        const EdgeFluxRestrict &x = plan.restricts[i];
+        r[0] = x.gid;
+        r[2] = x.el;
+        for (int d = 0; d < 3; ++d) {
+          r[4 + d] = x.box.s[d];
+          r[10 + d] = x.box.n(d);
+        }
+      } else {
+        const EdgeFluxPiece &x = plan.pieces[i];
+        r[0] = x.sender_gid;
+        r[1] = x.receiver_gid;
+        r[2] = x.el;
+        r[3] = x.pass;
+        for (int d = 0; d < 3; ++d) {
+          r[4 + d] = x.send_box.s[d];
+          r[7 + d] = x.recv_box.s[d];
+          r[10 + d] = x.recv_box.n(d);
+        }
+      }
+    }
+  });
+  return count;
+}
+
+int pb2h_sim_flux_correction(pb2h_sim *sim, const char *container) {
+  return Guard([&] {
+    PARTHENON_REQUIRE(sim && container, "null argument");
+    for (int p = 0; p < sim->pm()->DefaultNumPartitions(); ++p)
+      FluxCorrection(sim->pm()->mesh_data.GetOrAdd(container, p).get());
+    PB2_CHECK(pb2_stream_sync(sim->pm()->stream));
+  });
+}
+
 int pb2h_sim_exchange_mode(pb2h_sim *sim, const char *container) {
   int mode = -1;
   Guard([&] {

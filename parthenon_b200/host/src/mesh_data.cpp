@@ -24,9 +24,12 @@ Variable::Variable(const std::string &label, const Metadata &m, int sparse_id, i
   if (tt_ != TopologicalType::Cell) {
     // face, edge and node arrays are one longer in every non-symmetry direction
     // (metadata.cpp:383-387)
-    PARTHENON_REQUIRE(!m.IsSparse() && !m.IsSet(Metadata::WithFluxes),
-                      "non-cell-centred fields cannot be sparse or carry fluxes in this build (" +
-                          label + ")");
+    // (the flux of a face field is the separate edge field "bnd_flux::<name>",
+    // StateDescriptor::AddField; edge and node fields with fluxes are not built)
+    PARTHENON_REQUIRE(!m.IsSparse() &&
+                          (!m.IsSet(Metadata::WithFluxes) || tt_ == TopologicalType::Face),
+                      "non-cell-centred fields cannot be sparse, and only face fields carry "
+                      "fluxes in this build (" + label + ")");
     ni++;
     if (nj > 1) nj++;
     if (nk > 1) nk++;
@@ -91,6 +94,8 @@ Real *Variable::coarse() {
 
 Real *Variable::flux(int dir) {
   PARTHENON_REQUIRE(m_.IsSet(Metadata::WithFluxes), "field " + label_ + " has no fluxes");
+  PARTHENON_REQUIRE(tt_ == TopologicalType::Cell,
+                    "the flux of face field " + label_ + " is the edge field bnd_flux::" + label_);
   PARTHENON_REQUIRE(dir >= 1 && dir <= 3, "flux direction must be X1DIR..X3DIR");
   DeviceBuffer &f = flux_[dir - 1];
   if (!f)

@@ -180,7 +180,9 @@ std::shared_ptr<SparsePackStorage> Build(MeshData<Real> *md, const impl::PackDes
       const int comp = multi_el ? el * ntc + e.comp : e.comp;
       ptr[(static_cast<size_t>(el) * pack_blocks + pb) * maxvars + n] = base + b * bs + comp * cs;
     }
-    if (desc.with_fluxes && v.IsSet(Metadata::WithFluxes)) {
+    // (the flux of a face field is the separate edge field "bnd_flux::<name>": pack it by name)
+    if (desc.with_fluxes && v.IsSet(Metadata::WithFluxes) &&
+        v.topological_type() == TopologicalType::Cell) {
       for (int d = 1; d <= 3; ++d) {
         if (d > md->GetMeshPointer()->ndim) continue;
         ptr[(static_cast<size_t>(flx_idx + d - 1) * pack_blocks + pb) * maxvars + n] =

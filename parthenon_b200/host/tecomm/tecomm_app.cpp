@@ -52,6 +52,11 @@ Packages_t ProcessPackages(std::unique_ptr<ParameterInput> &pin) {
   pkg->AddField("face", mface);
   pkg->AddField("edge", medge);
   pkg->AddField("node", mnode);
+  // tecomm/flux_field = true: a face field B with fluxes — its flux is the edge field
+  // "bnd_flux::B" — for the flux-correction tests (tests/golden/refgen/teflux_dump_main.cpp)
+  if (pin->GetOrAddBoolean("tecomm", "flux_field", false))
+    pkg->AddField("B", Metadata({Metadata::Face, Metadata::Independent, Metadata::WithFluxes,
+                                 Metadata::FillGhost}));
   pkg->CheckRefinementMesh = TagByPosition;
   packages.Add(pkg);
   return packages;
