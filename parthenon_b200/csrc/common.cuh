@@ -44,6 +44,14 @@ inline cudaStream_t as_stream(pb2_stream_t s) { return reinterpret_cast<cudaStre
   } while (0)
 
 int require_device();
+// Device memory of region tables (exchange.cu, prores.cu).  An adaptive run destroys and
+// re-creates dozens of small tables on every remesh; cudaMalloc / cudaFree for each (the free
+// synchronises the device) is replaced by a pool of size classes (4 KB x 4^k) per device.
+// Semantics of cudaMalloc / cudaFree are kept: a pointer handed out is not referenced by any
+// work still in flight — a block freed since the pool last synchronised its device triggers ONE
+// cudaDeviceSynchronize on reuse, which clears every block freed before it.
+cudaError_t table_alloc(void **ptr, size_t bytes);
+void table_free(void *ptr);
 
 // ---- optional per-kernel timing with CUDA events (pb2_profile_* of the C ABI) ----------
 enum KernelId {

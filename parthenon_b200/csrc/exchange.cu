@@ -9,6 +9,7 @@
 // the flat buffer index into (c,k,j,i) with precomputed multiply-shift divisions.  The
 // buffer side is fully coalesced; the array side touches whole 32 B sectors (ghost rows of
 // 4 doubles are sector aligned because is, ie+1 and the row pitch are multiples of 4).
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -351,10 +352,40 @@ __global__ void __launch_bounds__(kThreads, PB2_HALO_MINB)
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int build_table(pb2_bnd_table **out, std::vector<DevRegion> &regs, int kind) {
+// Region tables are assembled in one pinned staging buffer (grown on demand, kept): an adaptive
+// mesh re-creates tables of tens of thousands of regions (several MB) on every remesh, and a
+// copy from pageable memory runs at a fraction of the PCIe rate.
+struct Stage {
+  std::mutex mu;
+  void *ptr = nullptr;
+  size_t cap = 0;
+  std::vector<DevRegion> fallback;
+  DevRegion *regions(size_t n) { // call with mu held
+    const size_t bytes = n * sizeof(DevRegion);
+    if (bytes > cap) {
+      if (ptr) cudaFreeHost(ptr);
+      ptr = nullptr;
+      cap = 0;
+      const size_t want = bytes + bytes / 2 + (size_t(1) << 20);
+      if (cudaMallocHost(&ptr, want) == cudaSuccess) {
+        cap = want;
+      } else {
+        cudaGetLastError();
+        ptr = nullptr;
+      }
+    }
+    if (ptr) return static_cast<DevRegion *>(ptr);
+    fallback.resize(n);
+    return fallback.data();
+  }
+};
+static Stage g_stage;
+
+static int build_table(pb2_bnd_table **out, const DevRegion *regs, size_t nregs, int kind) {
   std::vector<Chunk> chunks;
+  chunks.reserve(nregs + nregs / 4);
   int64_t elements = 0;
-  for (size_t r = 0; r < regs.size(); ++r) {
+  for (size_t r = 0; r < nregs; ++r) {
     const uint32_t per_chunk = kThreads * kUnroll;
     elements += (int64_t)regs[r].total_vec * regs[r].vec;
     for (uint32_t v = 0; v < regs[r].total_vec; v += per_chunk)
@@ -362,25 +393,24 @@ static int build_table(pb2_bnd_table **out, std::vector<DevRegion> &regs, int ki
   }
   auto *t = new pb2_bnd_table();
   t->kind = kind;
-  t->nregions = static_cast<int64_t>(regs.size());
+  t->nregions = static_cast<int64_t>(nregs);
   t->nchunks = static_cast<int64_t>(chunks.size());
   t->elements = elements;
   t->d_regions = nullptr;
   t->d_chunks = nullptr;
   t->d_prores = nullptr;
-  if (!regs.empty()) {
-    cudaError_t e = cudaMalloc(&t->d_regions, regs.size() * sizeof(DevRegion));
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+  if (nregs > 0) {
+    cudaError_t e = table_alloc(reinterpret_cast<void **>(&t->d_regions), nregs * sizeof(DevRegion));
+    if (e == cudaSuccess) e = table_alloc(reinterpret_cast<void **>(&t->d_chunks), (chunks.size() + 1) * sizeof(Chunk));
     if (e == cudaSuccess)
-      e = cudaMemcpy(t->d_regions, regs.data(), regs.size() * sizeof(DevRegion),
-                     cudaMemcpyHostToDevice);
+      e = cudaMemcpy(t->d_regions, regs, nregs * sizeof(DevRegion), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !chunks.empty())
       e = cudaMemcpy(t->d_chunks, chunks.data(), chunks.size() * sizeof(Chunk),
                      cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       set_error("table upload failed: %s", cudaGetErrorString(e));
-      cudaFree(t->d_regions);
-      cudaFree(t->d_chunks);
+      table_free(t->d_regions);
+      table_free(t->d_chunks);
       delete t;
       return PB2_ERR_CUDA;
     }
@@ -398,7 +428,8 @@ extern "C" {
 int pb2_bnd_table_create(pb2_bnd_table **table, const pb2_bnd_region *regions, int64_t n) {
   PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
   if (int rc = require_device()) return rc;
-  std::vector<DevRegion> regs(static_cast<size_t>(n));
+  std::lock_guard<std::mutex> stage_lock(g_stage.mu);
+  DevRegion *regs = g_stage.regions(static_cast<size_t>(n));
   for (int64_t i = 0; i < n; ++i) {
     const pb2_bnd_region &a = regions[i];
     DevRegion &d = regs[i];
@@ -437,13 +468,14 @@ int pb2_bnd_table_create(pb2_bnd_table **table, const pb2_bnd_region *regions, i
     d.status = a.status;
     d.value = a.value;
   }
-  return build_table(table, regs, kBnd);
+  return build_table(table, regs, static_cast<size_t>(n), kBnd);
 }
 
 int pb2_copy_table_create(pb2_bnd_table **table, const pb2_copy_region *regions, int64_t n) {
   PB2_REQUIRE(table && (regions || n == 0) && n >= 0, "bad arguments");
   if (int rc = require_device()) return rc;
-  std::vector<DevRegion> regs(static_cast<size_t>(n));
+  std::lock_guard<std::mutex> stage_lock(g_stage.mu);
+  DevRegion *regs = g_stage.regions(static_cast<size_t>(n));
   for (int64_t i = 0; i < n; ++i) {
     const pb2_copy_region &a = regions[i];
     DevRegion &d = regs[i];
@@ -478,16 +510,16 @@ int pb2_copy_table_create(pb2_bnd_table **table, const pb2_copy_region *regions,
     d.value = a.threshold;
     d.default_value = a.default_value;
   }
-  return build_table(table, regs, kCopy);
+  return build_table(table, regs, static_cast<size_t>(n), kCopy);
 }
 
 int pb2_bnd_table_destroy(pb2_bnd_table *table) {
   if (!table) return PB2_OK;
-  cudaFree(table->d_regions);
-  cudaFree(table->d_chunks);
-  cudaFree(table->d_prores);
-  cudaFree(table->d_flxcor);
-  cudaFree(table->d_bc);
+  table_free(table->d_regions);
+  table_free(table->d_chunks);
+  table_free(table->d_prores);
+  table_free(table->d_flxcor);
+  table_free(table->d_bc);
   delete table;
   return PB2_OK;
 }

@@ -489,8 +489,8 @@ int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regi
   t->d_chunks = nullptr;
   t->d_prores = nullptr;
   if (n > 0) {
-    cudaError_t e = cudaMalloc(&t->d_prores, n * sizeof(pb2_prores_region));
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    cudaError_t e = table_alloc(reinterpret_cast<void **>(&t->d_prores), n * sizeof(pb2_prores_region));
+    if (e == cudaSuccess) e = table_alloc(reinterpret_cast<void **>(&t->d_chunks), (chunks.size() + 1) * sizeof(Chunk));
     if (e == cudaSuccess)
       e = cudaMemcpy(t->d_prores, regions, n * sizeof(pb2_prores_region),
                      cudaMemcpyHostToDevice);
@@ -499,8 +499,8 @@ int pb2_prores_table_create(pb2_bnd_table **table, const pb2_prores_region *regi
                      cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       set_error("prores table upload failed: %s", cudaGetErrorString(e));
-      cudaFree(t->d_prores);
-      cudaFree(t->d_chunks);
+      table_free(t->d_prores);
+      table_free(t->d_chunks);
       delete t;
       return PB2_ERR_CUDA;
     }
@@ -597,8 +597,8 @@ int pb2_flxcor_table_create(pb2_bnd_table **table, const pb2_flxcor_region *regi
   t->d_prores = nullptr;
   t->d_flxcor = nullptr;
   if (n > 0) {
-    cudaError_t e = cudaMalloc(&t->d_flxcor, n * sizeof(pb2_flxcor_region));
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    cudaError_t e = table_alloc(reinterpret_cast<void **>(&t->d_flxcor), n * sizeof(pb2_flxcor_region));
+    if (e == cudaSuccess) e = table_alloc(reinterpret_cast<void **>(&t->d_chunks), (chunks.size() + 1) * sizeof(Chunk));
     if (e == cudaSuccess)
       e = cudaMemcpy(t->d_flxcor, regions, n * sizeof(pb2_flxcor_region),
                      cudaMemcpyHostToDevice);
@@ -607,8 +607,8 @@ int pb2_flxcor_table_create(pb2_bnd_table **table, const pb2_flxcor_region *regi
                      cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       set_error("flux-correction table upload failed: %s", cudaGetErrorString(e));
-      cudaFree(t->d_flxcor);
-      cudaFree(t->d_chunks);
+      table_free(t->d_flxcor);
+      table_free(t->d_chunks);
       delete t;
       return PB2_ERR_CUDA;
     }
@@ -658,8 +658,8 @@ int pb2_bc_table_create(pb2_bnd_table **table, const pb2_bc_region *regions, int
   t->d_chunks = nullptr;
   t->d_prores = nullptr;
   if (n > 0) {
-    cudaError_t e = cudaMalloc(&t->d_bc, n * sizeof(pb2_bc_region));
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_chunks, (chunks.size() + 1) * sizeof(Chunk));
+    cudaError_t e = table_alloc(reinterpret_cast<void **>(&t->d_bc), n * sizeof(pb2_bc_region));
+    if (e == cudaSuccess) e = table_alloc(reinterpret_cast<void **>(&t->d_chunks), (chunks.size() + 1) * sizeof(Chunk));
     if (e == cudaSuccess)
       e = cudaMemcpy(t->d_bc, regions, n * sizeof(pb2_bc_region), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !chunks.empty())
@@ -667,8 +667,8 @@ int pb2_bc_table_create(pb2_bnd_table **table, const pb2_bc_region *regions, int
                      cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       set_error("boundary-condition table upload failed: %s", cudaGetErrorString(e));
-      cudaFree(t->d_bc);
-      cudaFree(t->d_chunks);
+      table_free(t->d_bc);
+      table_free(t->d_chunks);
       delete t;
       return PB2_ERR_CUDA;
     }

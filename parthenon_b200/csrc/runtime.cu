@@ -114,6 +114,81 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 }
 } // namespace pb2
 
+// ---- pool behind table_alloc / table_free (common.cuh) ----
+namespace pb2 {
+namespace {
+struct TableBlock {
+  void *ptr;
+  uint64_t freed_epoch;
+};
+struct TableLive {
+  int device;
+  size_t cls;
+};
+std::mutex g_tp_mu;
+std::map<std::pair<int, size_t>, std::vector<TableBlock>> g_tp_free; // (device, class bytes)
+std::unordered_map<void *, TableLive> g_tp_live;
+std::unordered_map<int, uint64_t> g_tp_epoch; // per device: syncs the pool has done
+size_t g_tp_bytes = 0;
+constexpr size_t kTablePoolMaxBytes = size_t(2) << 30;
+// size classes 4 KB x 4^k: a table that grows with an adaptive mesh changes class (= one real
+// cudaMalloc, measured at tens of ms next to tens of GB of live slabs) once per factor of four
+size_t table_class(size_t bytes) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 2;
+  return c;
+}
+} // namespace
+
+cudaError_t table_alloc(void **ptr, size_t bytes) {
+  const size_t cls = table_class(bytes ? bytes : 1);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  {
+    std::lock_guard<std::mutex> lk(g_tp_mu);
+    auto it = g_tp_free.find({dev, cls});
+    if (it != g_tp_free.end() && !it->second.empty()) {
+      const TableBlock b = it->second.back();
+      it->second.pop_back();
+      g_tp_bytes -= cls;
+      uint64_t &epoch = g_tp_epoch[dev];
+      if (b.freed_epoch == epoch) { // freed since the last sync: kernels may still read it
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return e;
+        ++epoch;
+      }
+      g_tp_live[b.ptr] = TableLive{dev, cls};
+      *ptr = b.ptr;
+      return cudaSuccess;
+    }
+  }
+  e = cudaMalloc(ptr, cls);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_tp_mu);
+  g_tp_live[*ptr] = TableLive{dev, cls};
+  return cudaSuccess;
+}
+
+void table_free(void *ptr) {
+  if (!ptr) return;
+  std::lock_guard<std::mutex> lk(g_tp_mu);
+  auto it = g_tp_live.find(ptr);
+  if (it == g_tp_live.end()) { // not ours
+    cudaFree(ptr);
+    return;
+  }
+  const TableLive live = it->second;
+  g_tp_live.erase(it);
+  if (g_tp_bytes + live.cls > kTablePoolMaxBytes) {
+    cudaFree(ptr);
+    return;
+  }
+  g_tp_free[{live.device, live.cls}].push_back(TableBlock{ptr, g_tp_epoch[live.device]});
+  g_tp_bytes += live.cls;
+}
+} // namespace pb2
+
 using namespace pb2;
 
 extern "C" {

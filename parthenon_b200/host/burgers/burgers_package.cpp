@@ -173,7 +173,7 @@ TaskStatus FusedStage(MeshData<Real> *mc0, MeshData<Real> *mbase, MeshData<Real>
   // (the local / nonlocal overlap of burgers_driver.cpp:106-119, without host polling).
   BvarsCache &bc = GetBvarsCache(mc1);
   const bool split = a.math == PB2_MATH_FAST && !pm->multilevel && bc.n_boundary > 0 &&
-                     bc.n_interior > 0 && bc.plan.send_elements > 0;
+                     bc.n_interior > 0 && bc.plan->send_elements > 0;
   // Ghost cells across same-device faces: the fast sweeps read the neighbour's interior instead
   // (pb2_burgers_args::nbr_direct), so neither the input's local ghosts need to be current nor
   // do the output's have to be filled before the next stage — the local exchange of mc1 is

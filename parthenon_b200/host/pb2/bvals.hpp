@@ -142,7 +142,9 @@ struct BvarsCache {
   ~BvarsCache();
   void Clear();
   uint64_t built_generation = 0;
-  ExchangePlan plan;
+  // built once per block list and FillGhost signature, shared between the containers of a
+  // partition through Mesh::plan_cache; never null
+  std::shared_ptr<const ExchangePlan> plan = std::make_shared<const ExchangePlan>();
   bool plan_built = false;
   // the ownership of shared elements changed (end of a remesh): plan and tables are rebuilt
   void Invalidate() {

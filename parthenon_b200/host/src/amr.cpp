@@ -163,7 +163,10 @@ bool Mesh::UpdateMeshBlockTree(std::vector<LogicalLocation> &new_leaves, int &nn
 
 void Mesh::RebuildFromLeaves(const std::vector<LogicalLocation> &new_leaves,
                              const BlockList_t &old_blocks) {
+  static const bool timing = std::getenv("PB2_TIME_HOST") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   BuildTree(nullptr, new_leaves);
+  const auto t1 = std::chrono::steady_clock::now();
   multilevel = true;
   std::vector<double> cost(nbtotal, 1.0);
   AssignBlocks(cost, nranks, ranklist);
@@ -172,6 +175,11 @@ void Mesh::RebuildFromLeaves(const std::vector<LogicalLocation> &new_leaves,
   nslist.assign(nranks, 0);
   for (int r = 1; r < nranks; ++r) nslist[r] = nslist[r - 1] + nblist[r - 1];
   BuildBlockList(&old_blocks);
+  if (timing) {
+    const auto t2 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "[pb2 rebuild] tree %.2f ms, assign + block list %.2f ms\n", ms(t0, t1), ms(t1, t2));
+  }
 }
 
 // the host half of a remesh alone (tree update, re-partition, new block list): what
@@ -180,10 +188,18 @@ bool Mesh::RegridTopologyOnly() {
   PARTHENON_REQUIRE(nranks == 1, "topology-only regrid is a single-rank test facility");
   int nnew = 0, ndel = 0;
   std::vector<LogicalLocation> new_leaves;
+  static const bool timing = std::getenv("PB2_TIME_HOST") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   if (!UpdateMeshBlockTree(new_leaves, nnew, ndel)) return false;
+  const auto t1 = std::chrono::steady_clock::now();
   const BlockList_t old_blocks = block_list;
   std::unordered_set<LogicalLocation, LogicalLocationHash> old(loclist.begin(), loclist.end());
   RebuildFromLeaves(new_leaves, old_blocks);
+  if (timing) {
+    const auto t2 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "[pb2 regrid] tree update %.2f ms, rebuild from leaves %.2f ms\n", ms(t0, t1), ms(t1, t2));
+  }
   for (auto &pmb : block_list) {
     pmb->refine_flag = 0;
     if (!old.count(pmb->loc)) pmb->deref_count = 0;

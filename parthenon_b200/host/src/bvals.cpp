@@ -3,6 +3,9 @@
 // See pb2/bvals.hpp for the design and the reference files each piece replaces.
 #include "pb2/bvals.hpp"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -178,8 +181,8 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c, bool direct) {
   std::vector<int32_t> peers;
   if (real) {
     std::vector<char> is_peer(R, 0);
-    for (const Channel &ch : c.plan.send) is_peer[ch.receiver_rank] = 1;
-    for (const Channel &ch : c.plan.recv) is_peer[ch.sender_rank] = 1;
+    for (const Channel &ch : c.plan->send) is_peer[ch.receiver_rank] = 1;
+    for (const Channel &ch : c.plan->recv) is_peer[ch.sender_rank] = 1;
     for (int p = 0; p < R; ++p)
       if (is_peer[p] && p != me) peers.push_back(p);
   } else {
@@ -236,12 +239,12 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c, bool direct) {
   // slab variant: where our segment starts inside each peer's receive slab (its recv_off[me])
   std::vector<Real> peer_recv_off(static_cast<size_t>(R) * R, 0.0);
   if (!direct && real) {
-    for (int p = 0; p < R; ++p) peer_recv_off[static_cast<size_t>(me) * R + p] = static_cast<Real>(c.plan.recv_off[p]);
+    for (int p = 0; p < R; ++p) peer_recv_off[static_cast<size_t>(me) * R + p] = static_cast<Real>(c.plan->recv_off[p]);
     pm->AllReduceSum(peer_recv_off);
   }
   std::vector<pb2_copy_region> regs;
-  regs.reserve(c.plan.send.size());
-  for (const Channel &ch : c.plan.send) {
+  regs.reserve(c.plan->send.size());
+  for (const Channel &ch : c.plan->send) {
     PARTHENON_REQUIRE(!direct || (!ch.send_coarse && !ch.recv_coarse),
                       "direct peer push is for uniform meshes");
     const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
@@ -265,7 +268,7 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c, bool direct) {
       // the channel's place in the receiver's slab: same offset inside the peer segment on both
       // sides (BuildExchangePlan), the segment at the receiver's recv_off[this rank]; with
       // virtual ranks the send and the receive slab of the device have the same layout
-      const int64_t seg0 = real ? c.plan.send_off[ch.receiver_rank] : 0;
+      const int64_t seg0 = real ? c.plan->send_off[ch.receiver_rank] : 0;
       const int64_t base = real ? static_cast<int64_t>(peer_recv_off[static_cast<size_t>(ch.receiver_rank) * R + me]) : 0;
       r.dst = peer_var[rrank][0] + base + (ch.slab_off - seg0);
       for (int d = 0; d < 3; ++d) {
@@ -313,14 +316,14 @@ void BuildPeerPush(MeshData<Real> *md, BvarsCache &c, bool direct) {
   if (c.push_ce) {
     if (real) {
       for (int p : peers) {
-        const int64_t n = c.plan.send_off[p + 1] - c.plan.send_off[p];
+        const int64_t n = c.plan->send_off[p + 1] - c.plan->send_off[p];
         if (n == 0) continue;
         c.push_segments.push_back(
             {peer_var[p][0] + static_cast<int64_t>(peer_recv_off[static_cast<size_t>(p) * R + me]),
-             c.plan.send_off[p], n});
+             c.plan->send_off[p], n});
       }
     } else {
-      c.push_segments.push_back({c.recv_slab.get<Real>(), 0, c.plan.send_elements});
+      c.push_segments.push_back({c.recv_slab.get<Real>(), 0, c.plan->send_elements});
     }
   }
   std::vector<int32_t *> pf;
@@ -362,11 +365,12 @@ void Rebuild(MeshData<Real> *md) {
       auto sp = std::make_shared<ExchangePlan>(BuildExchangePlan(pm, md->GetBlockList(), pvars));
       it = pm->plan_cache.emplace(key, std::static_pointer_cast<const void>(sp)).first;
     }
-    c.plan = *static_cast<const ExchangePlan *>(it->second.get());
+    // shared, not copied: a plan of a few thousand blocks is tens of MB
+    c.plan = std::static_pointer_cast<const ExchangePlan>(it->second);
     c.plan_built = true;
   }
   const auto tr1 = std::chrono::steady_clock::now();
-  const bool slabs = c.plan.send_elements > 0 || c.plan.recv_elements > 0;
+  const bool slabs = c.plan->send_elements > 0 || c.plan->recv_elements > 0;
   PARTHENON_REQUIRE(!slabs || pm->DefaultNumPartitions() == 1,
                     "inter-device halos need one MeshData per rank (parthenon/mesh/pack_size=-1)");
   // sparse fields: allocation-aware exchange (null messages, allocate-on-receive), built for
@@ -383,14 +387,40 @@ void Rebuild(MeshData<Real> *md) {
                       "sparse fields need one MeshData per rank (parthenon/mesh/pack_size=-1)");
   }
 
-  // fused local channels: receiver ghost box <- sender interior box
-  std::vector<pb2_copy_region> copies;
-  copies.reserve(c.plan.local.size());
-  for (const Channel &ch : c.plan.local) {
+  // fused local channels: receiver ghost box <- sender interior box.  One region per channel,
+  // built on all host threads: the variables of every partition a sender lives in are looked up
+  // (and their lazily allocated arrays touched) once, before the loop
+  const auto tr2 = std::chrono::steady_clock::now();
+  const std::vector<Channel> &local_chs = c.plan->local;
+  const int64_t nlocal = static_cast<int64_t>(local_chs.size());
+  const int nvars = static_cast<int>(c.vars.size());
+  std::vector<std::vector<Variable *>> part_vars(static_cast<size_t>(pm->DefaultNumPartitions()));
+  auto touch = [&](Variable *v) {
+    v->data();
+    if (pm->multilevel) v->coarse();
+  };
+  auto fill_partition = [&](int p) {
+    if (!part_vars[p].empty() || nvars == 0) return;
+    MeshData<Real> *pmd =
+        p == md->partition_id() ? md : pm->mesh_data.GetOrAdd(md->label(), p).get();
+    for (Variable *v : c.vars) {
+      part_vars[p].push_back(p == md->partition_id() ? v : &pmd->Get(v->label()));
+      touch(part_vars[p].back());
+    }
+  };
+  fill_partition(md->partition_id());
+  if (part_vars.size() > 1)
+    for (const Channel &ch : local_chs)
+      fill_partition(pm->block_list[pm->GetLid(ch.sender_gid)]->partition);
+  std::vector<pb2_copy_region> copies(static_cast<size_t>(nlocal));
+  std::vector<char> keep(static_cast<size_t>(nlocal), 1);
+#pragma omp parallel for schedule(static) if (nlocal > 4096)
+  for (int64_t i = 0; i < nlocal; ++i) {
+    const Channel &ch = local_chs[i];
     const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
     const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
     Variable &rv = *c.vars[ch.var];
-    Variable &sv = ContainerOf(md, sb)->Get(rv.label());
+    Variable &sv = *part_vars[sb->partition][ch.var];
     pb2_copy_region r{};
     if (ch.send_coarse) {
       r.src = sv.coarse() + sb->pack_index * sv.cblock_stride + ch.comp0 * sv.ccomp_stride;
@@ -430,27 +460,35 @@ void Rebuild(MeshData<Real> *md) {
       // need a default fill, so it gets no region at all (its flag stays 0): with a few percent
       // of the fields allocated the launches shrink by the same factor
       const bool src_alloc = sv.IsAllocated(sb->pack_index), dst_alloc = rv.IsAllocated(rb->pack_index);
-      if (!src_alloc && !dst_alloc) continue;
-      r.flag_slot = static_cast<int32_t>(&ch - c.plan.local.data());
+      if (!src_alloc && !dst_alloc) keep[i] = 0;
+      r.flag_slot = static_cast<int32_t>(i);
       r.status = (src_alloc ? PB2_REGION_ALLOCATED : 0u) |
                  (dst_alloc ? 0u : PB2_REGION_DST_UNALLOCATED);
       r.threshold = rv.metadata().GetAllocationThreshold();
     }
-    copies.push_back(r);
+    copies[i] = r;
   }
+  if (c.sparse) { // drop the channels without a region, order kept
+    size_t w = 0;
+    for (int64_t i = 0; i < nlocal; ++i)
+      if (keep[i]) copies[w++] = copies[i];
+    copies.resize(w);
+  }
+  const auto tr3 = std::chrono::steady_clock::now();
   if (c.sparse && !c.sparse_flags) {
-    c.sparse_flags.Allocate(sizeof(int32_t) * std::max<size_t>(c.plan.local.size(), 1), md->stream());
-    c.sparse_flags_h.assign(c.plan.local.size(), 0);
+    c.sparse_flags.Allocate(sizeof(int32_t) * std::max<size_t>(c.plan->local.size(), 1), md->stream());
+    c.sparse_flags_h.assign(c.plan->local.size(), 0);
   }
   PB2_CHECK(pb2_copy_table_create(&c.copy_local, copies.data(), static_cast<int64_t>(copies.size())));
+  const auto tr4 = std::chrono::steady_clock::now();
 
   // uniform fast path: all local channels are same-level boxes between blocks of this batch
-  c.uniform_halo = !pm->multilevel && pm->DefaultNumPartitions() == 1 && !c.plan.local.empty() &&
+  c.uniform_halo = !pm->multilevel && pm->DefaultNumPartitions() == 1 && !c.plan->local.empty() &&
                    !pm->table_halo && all_cell;
   for (Variable *v : c.vars) c.uniform_halo = c.uniform_halo && !v->metadata().IsSparse();
   if (c.uniform_halo) {
     std::vector<int32_t> nbr(static_cast<size_t>(md->NumBlocks()) * 27, -1);
-    for (const Channel &ch : c.plan.local) {
+    for (const Channel &ch : c.plan->local) {
       if (ch.var != 0) continue; // the topology is the same for every field
       const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
       const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
@@ -502,36 +540,36 @@ void Rebuild(MeshData<Real> *md) {
     return r;
   };
   std::vector<pb2_bnd_region> packs, unpacks;
-  for (const Channel &ch : c.plan.send) packs.push_back(bnd(ch, true));
-  for (const Channel &ch : c.plan.recv) unpacks.push_back(bnd(ch, false));
+  for (const Channel &ch : c.plan->send) packs.push_back(bnd(ch, true));
+  for (const Channel &ch : c.plan->recv) unpacks.push_back(bnd(ch, false));
   if (c.sparse) {
     // every inter-device channel gets a flag slot; BndInfo::allocated is this side's own field
     // (bnd_info.cpp:277): an unallocated sender packs nothing and its flag stays 0 (a null
     // message), an unallocated receiver is skipped by the unpack
     for (size_t i = 0; i < packs.size(); ++i) {
-      const Channel &ch = c.plan.send[i];
+      const Channel &ch = c.plan->send[i];
       const MeshBlock *pmb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
       packs[i].flag_slot = static_cast<int32_t>(i);
       packs[i].status = c.vars[ch.var]->IsAllocated(pmb->pack_index) ? PB2_REGION_ALLOCATED : 0u;
     }
     for (size_t i = 0; i < unpacks.size(); ++i) {
-      const Channel &ch = c.plan.recv[i];
+      const Channel &ch = c.plan->recv[i];
       const MeshBlock *pmb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
       unpacks[i].flag_slot = static_cast<int32_t>(i);
       unpacks[i].status = c.vars[ch.var]->IsAllocated(pmb->pack_index) ? PB2_REGION_ALLOCATED : 0u;
     }
     auto counts = [&](const std::vector<Channel> &chs, bool send, std::vector<int64_t> &off) {
       const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
-      off.assign(c.plan.npeers + 1, 0);
+      off.assign(c.plan->npeers + 1, 0);
       for (const Channel &ch : chs) {
         const int seg = V > 1 ? ch.sender_vrank * V + ch.receiver_vrank
                               : (send ? ch.receiver_rank : ch.sender_rank);
         off[seg + 1]++;
       }
-      for (int p = 0; p < c.plan.npeers; ++p) off[p + 1] += off[p];
+      for (int p = 0; p < c.plan->npeers; ++p) off[p + 1] += off[p];
     };
-    counts(c.plan.send, true, c.send_flag_off);
-    counts(c.plan.recv, false, c.recv_flag_off);
+    counts(c.plan->send, true, c.send_flag_off);
+    counts(c.plan->recv, false, c.recv_flag_off);
     auto ensure = [&](DeviceBuffer &b, size_t bytes) {
       if (b.bytes() != std::max<size_t>(bytes, 8)) b.Allocate(std::max<size_t>(bytes, 8), md->stream());
     };
@@ -553,21 +591,24 @@ void Rebuild(MeshData<Real> *md) {
   // reads (shared faces / edges / nodes are both and need every pack to precede every unpack)
   const bool want_direct = want_push && pm->peer_push_mode == Mesh::PeerPush::direct && all_cell && !pm->multilevel;
   if (want_direct) BuildPeerPush(md, c, true);
-  if (!c.push_mode && c.plan.send_elements > 0 &&
-      c.send_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.send_elements))
-    c.send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.send_elements), md->stream());
-  if (!c.push_mode && c.plan.recv_elements > 0 &&
-      c.recv_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan.recv_elements))
-    c.recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan.recv_elements), md->stream());
+  if (!c.push_mode && c.plan->send_elements > 0 &&
+      c.send_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan->send_elements))
+    c.send_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan->send_elements), md->stream());
+  if (!c.push_mode && c.plan->recv_elements > 0 &&
+      c.recv_slab.bytes() != sizeof(Real) * static_cast<size_t>(c.plan->recv_elements))
+    c.recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.plan->recv_elements), md->stream());
   // slab variant: the pack writes straight into the peers' receive slabs (no send slab needed,
   // it is kept for the fallback), the unpack stays with the receiver
-  if (want_push && !c.push_mode && c.plan.recv_elements > 0) BuildPeerPush(md, c, false);
+  if (want_push && !c.push_mode && c.plan->recv_elements > 0) BuildPeerPush(md, c, false);
 
+  const auto tr5 = std::chrono::steady_clock::now();
   // restriction / prolongation regions (ProResInfo::GetSend / GetSet, bnd_info.cpp:387-448),
   // split by whether the neighbour is local so the local / nonlocal task split still works
   if (pm->multilevel) {
-    std::vector<pb2_prores_region> rsend[2], rset[2], pro[2][3];
-    std::vector<pb2_prores_region> te_rsend[2], te_rset[2], te_pro[2][3], te_int[2], te_tr[2];
+    struct ProResLists {
+      std::vector<pb2_prores_region> rsend[2], rset[2], pro[2][3];
+      std::vector<pb2_prores_region> te_rsend[2], te_rset[2], te_pro[2][3], te_int[2], te_tr[2];
+    };
     std::array<bool, 27> all_true;
     all_true.fill(true);
     // containers of the internal prolongation in the order the reference visits them
@@ -581,7 +622,7 @@ void Rebuild(MeshData<Real> *md) {
       }
       return more > 0;
     };
-    for (auto &pmb : md->GetBlockList()) {
+    auto collect = [&](const std::shared_ptr<MeshBlock> &pmb, ProResLists &L) {
       const int my_vr = pm->VirtualRankOf(pmb->gid);
       bool restricted = false;
       if (pmb->loc.level > 0)
@@ -600,11 +641,11 @@ void Rebuild(MeshData<Real> *md) {
             for (size_t e = 0; e < els.size(); ++e) {
               const int ei = static_cast<int>(e);
               if (nb.origin_loc.level < pmb->loc.level) {
-                AddTeRegions(te_rsend[cls], *v, pmb.get(), ei, els[e], nullptr,
+                AddTeRegions(L.te_rsend[cls], *v, pmb.get(), ei, els[e], nullptr,
                              CalcIndicesTE(nb, pmb.get(), els[e],
                                            IndexRangeType::BoundaryInteriorSend, true),
                              all_true, pm->ndim);
-                AddTeRegions(te_pro[cls][op], *v, pmb.get(), ei, els[e], nullptr,
+                AddTeRegions(L.te_pro[cls][op], *v, pmb.get(), ei, els[e], nullptr,
                              CalcIndicesTE(nb, pmb.get(), els[e],
                                            IndexRangeType::BoundaryExteriorRecv, true),
                              RecvMask(pm, nb, pmb.get(), els[e]), pm->ndim);
@@ -614,24 +655,24 @@ void Rebuild(MeshData<Real> *md) {
                   PARTHENON_REQUIRE(v->topological_type() == TopologicalType::Face,
                                     "ProlongateInternalTothAndRoe is defined for face fields");
                   const TE cc = TE::CC;
-                  const size_t first = te_tr[cls].size();
-                  AddTeRegions(te_tr[cls], *v, pmb.get(), ei, els[e], &cc,
+                  const size_t first = L.te_tr[cls].size();
+                  AddTeRegions(L.te_tr[cls], *v, pmb.get(), ei, els[e], &cc,
                                CalcIndicesTE(nb, pmb.get(), cc,
                                              IndexRangeType::BoundaryExteriorRecv, true),
                                RecvMask(pm, nb, pmb.get(), cc), pm->ndim);
-                  for (size_t q = first; q < te_tr[cls].size(); ++q)
-                    te_tr[cls][q].fine -=
+                  for (size_t q = first; q < L.te_tr[cls].size(); ++q)
+                    L.te_tr[cls][q].fine -=
                         static_cast<int64_t>(ei) * v->TensorComponents() * v->comp_stride;
                 } else {
                   for (const TE &cel : containers)
                     if (is_submanifold(els[e], cel))
-                      AddTeRegions(te_int[cls], *v, pmb.get(), ei, els[e], &cel,
+                      AddTeRegions(L.te_int[cls], *v, pmb.get(), ei, els[e], &cel,
                                    CalcIndicesTE(nb, pmb.get(), cel,
                                                  IndexRangeType::BoundaryExteriorRecv, true),
                                    RecvMask(pm, nb, pmb.get(), cel), pm->ndim);
                 }
               } else if (restricted) {
-                AddTeRegions(te_rset[cls], *v, pmb.get(), ei, els[e], nullptr,
+                AddTeRegions(L.te_rset[cls], *v, pmb.get(), ei, els[e], nullptr,
                              CalcIndicesTE(nb, pmb.get(), els[e],
                                            IndexRangeType::BoundaryExteriorRecv, true),
                              RecvMask(pm, nb, pmb.get(), els[e]), pm->ndim);
@@ -640,20 +681,71 @@ void Rebuild(MeshData<Real> *md) {
             continue;
           }
           if (nb.origin_loc.level < pmb->loc.level) {
-            rsend[cls].push_back(MakeProRes(
+            L.rsend[cls].push_back(MakeProRes(
                 *v, pmb.get(),
                 CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryInteriorSend, true), pm->ndim));
-            pro[cls][v->metadata().ProlongationOp()].push_back(MakeProRes(
+            L.pro[cls][v->metadata().ProlongationOp()].push_back(MakeProRes(
                 *v, pmb.get(),
                 CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, true), pm->ndim));
           } else if (restricted) {
-            rset[cls].push_back(MakeProRes(
+            L.rset[cls].push_back(MakeProRes(
                 *v, pmb.get(),
                 CalcIndices(nb, pmb.get(), IndexRangeType::BoundaryExteriorRecv, true), pm->ndim));
           }
         }
       }
+    };
+    // blocks are independent: cell-centred fields are collected on all host threads, each thread
+    // a contiguous range of blocks, and the lists are joined in thread order (the serial order).
+    // Face / edge / node fields consult the lazily filled ownership cache and stay serial.
+    const BlockList_t &blist = md->GetBlockList();
+    const int nblk_pr = static_cast<int>(blist.size());
+    int nthreads_pr = 1;
+#ifdef _OPENMP
+    if (all_cell && nblk_pr > 256) nthreads_pr = omp_get_max_threads();
+#endif
+    std::vector<ProResLists> lists(static_cast<size_t>(nthreads_pr));
+    std::string pr_failure;
+#pragma omp parallel num_threads(nthreads_pr) if (nthreads_pr > 1)
+    {
+#ifdef _OPENMP
+      const int tid = nthreads_pr > 1 ? omp_get_thread_num() : 0;
+      const int nth = nthreads_pr > 1 ? omp_get_num_threads() : 1;
+#else
+      const int tid = 0, nth = 1;
+#endif
+      const int lo = static_cast<int>(static_cast<int64_t>(nblk_pr) * tid / nth);
+      const int hi = static_cast<int>(static_cast<int64_t>(nblk_pr) * (tid + 1) / nth);
+      try {
+        for (int ib = lo; ib < hi; ++ib) collect(blist[ib], lists[tid]);
+      } catch (const std::exception &e) {
+#pragma omp critical
+        pr_failure = e.what();
+      }
     }
+    PARTHENON_REQUIRE(pr_failure.empty(), pr_failure);
+    ProResLists &L0 = lists[0];
+    auto join = [&](auto member) {
+      for (int t = 1; t < nthreads_pr; ++t) {
+        auto &src = member(lists[t]);
+        auto &dst = member(L0);
+        dst.insert(dst.end(), src.begin(), src.end());
+      }
+    };
+    for (int cls = 0; cls < 2; ++cls) {
+      join([cls](ProResLists &l) -> std::vector<pb2_prores_region> & { return l.rsend[cls]; });
+      join([cls](ProResLists &l) -> std::vector<pb2_prores_region> & { return l.rset[cls]; });
+      for (int o = 0; o < 3; ++o)
+        join([cls, o](ProResLists &l) -> std::vector<pb2_prores_region> & { return l.pro[cls][o]; });
+    }
+    auto &rsend = L0.rsend;
+    auto &rset = L0.rset;
+    auto &pro = L0.pro;
+    auto &te_rsend = L0.te_rsend;
+    auto &te_rset = L0.te_rset;
+    auto &te_pro = L0.te_pro;
+    auto &te_int = L0.te_int;
+    auto &te_tr = L0.te_tr;
     for (int cls = 0; cls < 2; ++cls) {
       PB2_CHECK(pb2_prores_table_create(&c.restrict_send[cls], rsend[cls].data(),
                                         static_cast<int64_t>(rsend[cls].size())));
@@ -675,6 +767,7 @@ void Rebuild(MeshData<Real> *md) {
                                           static_cast<int64_t>(te_pro[cls][o].size())));
     }
   }
+  const auto tr6 = std::chrono::steady_clock::now();
   // physical boundary conditions: blocks on a non-periodic mesh face
   {
     std::vector<pb2_bc_region> regs[2][3];
@@ -729,6 +822,7 @@ void Rebuild(MeshData<Real> *md) {
         PB2_CHECK(pb2_bc_table_create(&c.bc[cf][d], regs[cf][d].data(),
                                       static_cast<int64_t>(regs[cf][d].size())));
   }
+  const auto tr7 = std::chrono::steady_clock::now();
   // boundary / interior split of the batch for comm-compute overlap
   {
     std::vector<int32_t> bnd, inr;
@@ -783,9 +877,13 @@ void Rebuild(MeshData<Real> *md) {
   c.built_generation = md->alloc_generation;
   if (timing) {
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    std::fprintf(stderr, "rebuild %s: plan %.2f ms, tables %.2f ms (%zu local, %zu send channels)\n",
-                 md->label().c_str(), ms(tr0, tr1), ms(tr1, std::chrono::steady_clock::now()),
-                 c.plan.local.size(), c.plan.send.size());
+    const auto tr8 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "rebuild %s: plan %.2f ms, tables %.2f ms (%zu local, %zu send channels): "
+                         "copy regions %.2f, copy table %.2f, slab tables %.2f, prores %.2f, bcs %.2f, "
+                         "block classes %.2f\n",
+                 md->label().c_str(), ms(tr0, tr1), ms(tr1, tr8), c.plan->local.size(),
+                 c.plan->send.size(), ms(tr2, tr3), ms(tr3, tr4), ms(tr4, tr5), ms(tr5, tr6),
+                 ms(tr6, tr7), ms(tr7, tr8));
   }
 }
 
@@ -835,7 +933,7 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     }
     c.send_generation++; // the copy itself happens in SetBounds<local> of the receiver
   }
-  if (DoesNonlocal(bt) && c.plan.send_elements + c.plan.recv_elements > 0) {
+  if (DoesNonlocal(bt) && c.plan->send_elements + c.plan->recv_elements > 0) {
     if (pm->multilevel) {
       PB2_CHECK(pb2_restrict(c.restrict_send[1], st));
       PB2_CHECK(pb2_restrict_te(c.te_restrict_send[1], st));
@@ -912,8 +1010,8 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     if (c.unpacked_valid) PB2_CHECK(pb2_stream_wait_event(cs, c.unpacked));
     if (pm->nranks > 1) {
       PARTHENON_REQUIRE(pm->comm != nullptr, "multi-rank mesh without a communicator");
-      PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_slab.get<Real>(), c.plan.send_off.data(),
-                                  c.recv_slab.get<Real>(), c.plan.recv_off.data(), cs));
+      PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_slab.get<Real>(), c.plan->send_off.data(),
+                                  c.recv_slab.get<Real>(), c.plan->recv_off.data(), cs));
       if (c.sparse)
         PB2_CHECK(pb2_comm_exchange(pm->comm, c.send_flag_slab.get<Real>(),
                                     c.send_flag_off.data(), c.recv_flag_slab.get<Real>(),
@@ -921,7 +1019,7 @@ TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     } else {
       // virtual ranks on one device: the "wire" is a device-to-device copy of the slab
       PB2_CHECK(pb2_memcpy_d2d(c.recv_slab.get(), c.send_slab.get(),
-                               sizeof(Real) * static_cast<size_t>(c.plan.send_elements), cs));
+                               sizeof(Real) * static_cast<size_t>(c.plan->send_elements), cs));
       if (c.sparse)
         PB2_CHECK(pb2_memcpy_d2d(c.recv_flag_slab.get(), c.send_flag_slab.get(),
                                  sizeof(Real) * c.send_flags_h.size(), cs));
@@ -940,7 +1038,7 @@ TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
   if (DoesLocal(bt)) {
     // every partition that sends to us must have published this exchange
     // (CommBuffer::TryReceive for same-rank buffers, communication_buffer.hpp:390-400)
-    for (const Channel &ch : c.plan.local) {
+    for (const Channel &ch : c.plan->local) {
       const MeshBlock *sb = pm->block_list[pm->GetLid(ch.sender_gid)].get();
       if (sb->partition == md->partition_id()) continue;
       MeshData<Real> *smd = ContainerOf(md.get(), sb);
@@ -954,8 +1052,8 @@ TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
       PB2_CHECK(pb2_memcpy_d2h(c.sparse_flags_h.data(), c.sparse_flags.get(),
                                sizeof(int32_t) * c.sparse_flags_h.size(), md->stream()));
       PB2_CHECK(pb2_stream_sync(md->stream()));
-      for (size_t i = 0; i < c.plan.local.size(); ++i) {
-        const Channel &ch = c.plan.local[i];
+      for (size_t i = 0; i < c.plan->local.size(); ++i) {
+        const Channel &ch = c.plan->local[i];
         Variable &rv = *c.vars[ch.var];
         if (!rv.metadata().IsSparse() || !c.sparse_flags_h[i]) continue;
         const MeshBlock *rb = pm->block_list[pm->GetLid(ch.receiver_gid)].get();
@@ -971,8 +1069,8 @@ TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
     PB2_CHECK(pb2_memcpy_d2h(c.flag_slab_h.data(), c.recv_flag_slab.get(),
                              sizeof(Real) * c.flag_slab_h.size(), md->stream()));
     PB2_CHECK(pb2_stream_sync(md->stream()));
-    for (size_t i = 0; i < c.plan.recv.size(); ++i) {
-      const Channel &ch = c.plan.recv[i];
+    for (size_t i = 0; i < c.plan->recv.size(); ++i) {
+      const Channel &ch = c.plan->recv[i];
       Variable &rv = *c.vars[ch.var];
       c.recv_flags_h[i] = c.flag_slab_h[i] != 0.0 ? 1 : 0;
       if (!rv.metadata().IsSparse() || !c.recv_flags_h[i]) continue;
@@ -1012,7 +1110,7 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
     } else {
       PB2_CHECK(pb2_copy(c.copy_local, nullptr, st));
     }
-    c.elements_local = c.plan.local_elements;
+    c.elements_local = c.plan->local_elements;
     for (int p = 0; p < pm->DefaultNumPartitions(); ++p) {
       MeshData<Real> *smd =
           p == md->partition_id() ? md.get() : pm->mesh_data.GetOrAdd(md->label(), p).get();
@@ -1023,7 +1121,7 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
       PB2_CHECK(pb2_restrict_te(c.te_restrict_set[0], st));
     }
   }
-  if (DoesNonlocal(bt) && c.plan.recv_elements > 0) {
+  if (DoesNonlocal(bt) && c.plan->recv_elements > 0) {
     if (c.push_mode) {
       // the peers stored this halo into our receive slab (or, direct variant, into our ghost
       // cells) themselves: wait for their arrival flags and unpack, on the communication stream
@@ -1052,7 +1150,7 @@ TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
       PB2_CHECK(pb2_event_record(c.unpacked, st));
     }
     c.unpacked_valid = true;
-    c.elements_nonlocal = c.plan.recv_elements;
+    c.elements_nonlocal = c.plan->recv_elements;
     if (pm->multilevel) {
       PB2_CHECK(pb2_restrict(c.restrict_set[1], st));
       PB2_CHECK(pb2_restrict_te(c.te_restrict_set[1], st));

@@ -678,7 +678,7 @@ int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t
   Guard([&] {
     auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
     BuildBoundaryBuffers(md);
-    const ExchangePlan &p = md->bvars().plan;
+    const ExchangePlan &p = *md->bvars().plan;
     if (local) *local = p.local_elements;
     if (nonlocal) *nonlocal = p.recv_elements;
     total = p.local_elements + p.recv_elements;
@@ -736,7 +736,7 @@ int pb2h_sim_exchange_mode(pb2h_sim *sim, const char *container) {
     auto &md = sim->pm()->mesh_data.GetOrAdd(container, 0);
     BuildBoundaryBuffers(md);
     const BvarsCache &c = md->bvars();
-    if (c.plan.send_elements + c.plan.recv_elements == 0)
+    if (c.plan->send_elements + c.plan->recv_elements == 0)
       mode = 0;
     else if (!c.push_mode)
       mode = 1;

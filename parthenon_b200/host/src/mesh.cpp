@@ -664,8 +664,12 @@ void Mesh::AllReduceSum(std::vector<Real> &vals) {
 
 int Mesh::SlabCapacity(int nblocks) {
   if (!adaptive) return nblocks;
-  if (nblocks > slab_capacity_ || 2 * nblocks < slab_capacity_)
-    slab_capacity_ = (nblocks + nblocks / 4 + 63) / 64 * 64;
+  // grown by half when exceeded (shrunk when less than a third is used): every change of the
+  // capacity re-allocates all field slabs, and cudaMalloc of GB-sized slabs was measured at
+  // 30-270 ms per event on a B200 (profiles/README.md, session r03e) — rarer events matter more
+  // than the spare blocks
+  if (nblocks > slab_capacity_ || 3 * nblocks < slab_capacity_)
+    slab_capacity_ = (nblocks + nblocks / 2 + 63) / 64 * 64;
   return slab_capacity_;
 }
 
