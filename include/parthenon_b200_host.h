@@ -148,11 +148,17 @@ int pb2h_sim_exchange_phase(pb2h_sim *sim, const char *container, int phase);
 /* Reals one exchange moves on this rank (ghost cells filled x components) */
 int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t *local,
                                    int64_t *nonlocal);
-/* flux correction of a face field (edge-centred flux) as pure topology, rows of 13 int64:
- * kind 0, restrictions on fine blocks: [gid, 0, element 0..2 (E1..E3), 0, s(i,j,k) in the coarse
- * index space, 0, 0, 0, n(i,j,k)]; kind 1, deliveries: [sender gid, receiver gid, element, pass
- * (0: across a block edge, 1: across a face, delivered second), send_s(i,j,k) in the sender's
- * coarse buffer, recv_s(i,j,k) in the receiver's array, n(i,j,k)].  Returns the count. */
+/* flux correction of a face field (edge-centred flux) as pure topology, rows of 16 int64.
+ * kind 0, restrictions on fine blocks whose coarser neighbour is on the same device: [gid, 0,
+ * element 0..2 (E1..E3), 0, s(i,j,k) in the coarse index space, 0, 0, 0, n(i,j,k), 0, 0, 0];
+ * kind 1, same-device deliveries: [sender gid, receiver gid, element, pass (0: across a block
+ * edge, 1: across a face, delivered second), send_s(i,j,k) in the sender's coarse buffer,
+ * recv_s(i,j,k) in the receiver's array, n(i,j,k), -1, -1, key];
+ * kind 2: like 0 for this rank's fine blocks whose coarser neighbour is on another device;
+ * kind 3 / 4: pieces this rank sends / receives across devices, like kind 1 with only the send /
+ * receive start set, then [peer, offset in Reals inside the edge-flux part of the slab for one
+ * component per element, key] - both sides list a peer's pieces in the same order at the same
+ * offsets.  Returns the count. */
 int64_t pb2h_sim_edge_flux_plan(pb2h_sim *sim, int kind, int64_t *rows, int64_t max_rows);
 /* AddFluxCorrectionTasks (boundary_communication.cpp:454-461) on every partition of `container`:
  * fine blocks restrict the fluxes they share with coarser neighbours, the coarser blocks take

@@ -368,13 +368,14 @@ class _Base:
         return rows[:n]
 
     def edge_flux_plan(self, kind):
-        """flux correction of a face field as topology: kind 'restrict' | 'deliver' -> rows[n, 13]
-        (include/parthenon_b200_host.h)"""
-        k = {"restrict": 0, "deliver": 1}[kind]
+        """flux correction of a face field as topology: kind 'restrict' | 'deliver' (same-device
+        neighbours) | 'send_restrict' | 'send' | 'recv' (neighbours on another device)
+        -> rows[n, 16] (include/parthenon_b200_host.h)"""
+        k = {"restrict": 0, "deliver": 1, "send_restrict": 2, "send": 3, "recv": 4}[kind]
         n = lib().pb2h_sim_edge_flux_plan(self.h, k, None, 0)
         if n < 0:
             check(-1)
-        rows = np.zeros((max(n, 1), 13), dtype=np.int64)
+        rows = np.zeros((max(n, 1), 16), dtype=np.int64)
         lib().pb2h_sim_edge_flux_plan(self.h, k, rows.ctypes.data_as(C.POINTER(C.c_int64)), n)
         return rows[:n]
 

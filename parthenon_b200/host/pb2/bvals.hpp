@@ -121,7 +121,7 @@ std::vector<TE> FluxCorrectionEdgeElements(const int off[3]);
 // The flux correction of a face field as pure topology: which coarse boxes of which element the
 // fine blocks restrict, and which (sender coarse-buffer box -> receiver box) pieces deliver them
 // — one piece per active sub-box of the sender's ownership mask; pass 0: across block edges,
-// pass 1: across faces (delivered second).  Same-device neighbours only.
+// pass 1: across faces (delivered second).
 struct EdgeFluxRestrict {
   int gid, el; // el: 0..2 = E1..E3
   IndexBox box;
@@ -129,12 +129,27 @@ struct EdgeFluxRestrict {
 struct EdgeFluxPiece {
   int sender_gid, receiver_gid, el, pass;
   IndexBox send_box, recv_box;
+  // pieces between devices (or virtual ranks): the peer segment, the sender's offset index
+  // towards the receiver and the sub-box number (the sort key both sides share), and the offset
+  // in Reals inside the edge-flux part of the peer segment (for ncomp components per element)
+  int seg = -1, offset_index = 0, sub = 0;
+  int64_t slab_off = -1;
 };
 struct EdgeFluxPlan {
+  // same-device neighbours, listed from the coarse receiver's side: what its fine neighbours
+  // restrict, and the pieces that deliver it
   std::vector<EdgeFluxRestrict> restricts;
   std::vector<EdgeFluxPiece> pieces;
+  // neighbours on another device: what this rank's fine blocks restrict and send (send_box
+  // set), what its coarse blocks receive (recv_box set); both sorted by (segment, sender,
+  // receiver, offset index, element, sub-box) so that the two sides agree on the offsets
+  std::vector<EdgeFluxRestrict> send_restricts;
+  std::vector<EdgeFluxPiece> send, recv;
+  std::vector<int64_t> send_off, recv_off; // [npeers + 1], Reals, for `ncomp` components
+  int npeers = 1;
 };
-EdgeFluxPlan BuildEdgeFluxPlan(const Mesh *pm, const BlockList_t &blocks);
+// ncomp: tensor components per element of the flux field (sizes the slab offsets)
+EdgeFluxPlan BuildEdgeFluxPlan(const Mesh *pm, const BlockList_t &blocks, int ncomp = 1);
 ExchangePlan BuildExchangePlan(const Mesh *pm, const BlockList_t &blocks,
                                const std::vector<PlanVar> &vars);
 
@@ -252,8 +267,13 @@ struct BvarsCache {
   // shared edge elements into the flux field's coarse buffer (teflx_restrict), then they are
   // copied into the coarser block's flux array under the sender's ownership mask, messages
   // across block edges first ([0]), across faces second ([1]) — see oracle/pb2_oracle.c on why
-  // the order matters.  Same-device channels only.
+  // the order matters.
   pb2_bnd_table *teflx_restrict = nullptr, *teflx_copy[2] = {nullptr, nullptr};
+  // ... and across devices: this rank's fine blocks restrict (teflx_restrict_send) and pack the
+  // entries they own into the flux-correction slab behind the face fluxes of the peer segment;
+  // the receiver unpacks block-edge messages ([0]) before face messages ([1])
+  pb2_bnd_table *teflx_restrict_send = nullptr, *teflx_pack = nullptr,
+                *teflx_unpack[2] = {nullptr, nullptr};
   int64_t teflx_elements = 0;
   std::vector<int64_t> flxcor_send_off, flxcor_recv_off; // [npeers + 1]
   int64_t flxcor_send_elements = 0, flxcor_recv_elements = 0, flxcor_local_elements = 0;

@@ -56,10 +56,11 @@ void BvarsCache::Clear() {
   pb2_bnd_table_destroy(flxcor_pack);
   pb2_bnd_table_destroy(flxcor_unpack);
   flxcor_local = flxcor_pack = flxcor_unpack = nullptr;
-  pb2_bnd_table_destroy(teflx_restrict);
-  pb2_bnd_table_destroy(teflx_copy[0]);
-  pb2_bnd_table_destroy(teflx_copy[1]);
-  teflx_restrict = teflx_copy[0] = teflx_copy[1] = nullptr;
+  for (pb2_bnd_table **t : {&teflx_restrict, &teflx_copy[0], &teflx_copy[1], &teflx_restrict_send,
+                            &teflx_pack, &teflx_unpack[0], &teflx_unpack[1]}) {
+    pb2_bnd_table_destroy(*t);
+    *t = nullptr;
+  }
   flxcor_built = false;
   built_generation = 0;
 }
@@ -1329,25 +1330,45 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
       }
     }
   }
-  // both sides order a peer segment by the same key => identical slab offsets, no handshake
+  // fluxes of face fields: edge-centred flux fields (Metadata::Flux | Edge), one plan per field
+  // (the slab offsets depend on its components per element)
+  const std::vector<Variable *> fvars = md->GetVariablesByFlag({Metadata::Flux});
+  std::vector<EdgeFluxPlan> fplans;
+  if (pm->multilevel)
+    for (Variable *fv : fvars) {
+      PARTHENON_REQUIRE(fv->topological_type() == TopologicalType::Edge,
+                        "flux fields other than the edge-centred flux of a face field are not built");
+      fplans.push_back(BuildEdgeFluxPlan(pm, md->GetBlockList(), fv->TensorComponents()));
+    }
+  // a peer segment of the slabs: [face fluxes of cell-centred fields | edge fluxes of face field
+  // 0 | of face field 1 ...]; both sides order each part by the same key => identical offsets,
+  // no handshake
+  std::vector<int64_t> te_send_size(npeers, 0), te_recv_size(npeers, 0);
+  for (const EdgeFluxPlan &fp : fplans)
+    for (int p = 0; p < npeers; ++p) {
+      te_send_size[p] += fp.send_off[p + 1] - fp.send_off[p];
+      te_recv_size[p] += fp.recv_off[p + 1] - fp.recv_off[p];
+    }
+  std::vector<int64_t> cell_send_size, cell_recv_size;
   auto layout = [&](std::vector<FlxChannel> &chs, std::vector<int64_t> &seg_off, int64_t &total,
-                    bool is_send) {
+                    bool is_send, const std::vector<int64_t> &extra,
+                    std::vector<int64_t> &seg_size) {
     std::stable_sort(chs.begin(), chs.end(), [](const FlxChannel &a, const FlxChannel &b) {
       return std::make_tuple(a.seg, a.sender_gid, a.receiver_gid, a.var, a.offset_index) <
              std::make_tuple(b.seg, b.sender_gid, b.receiver_gid, b.var, b.offset_index);
     });
-    std::vector<int64_t> seg_size(npeers, 0);
+    seg_size.assign(npeers, 0);
     for (auto &ch : chs) {
       (is_send ? ch.send.buf_off : ch.recv.buf_off) = seg_size[ch.seg];
       seg_size[ch.seg] += ch.n + (ch.n & 1);
     }
     seg_off.assign(npeers + 1, 0);
-    for (int p = 0; p < npeers; ++p) seg_off[p + 1] = seg_off[p] + seg_size[p];
+    for (int p = 0; p < npeers; ++p) seg_off[p + 1] = seg_off[p] + seg_size[p] + extra[p];
     for (auto &ch : chs) (is_send ? ch.send.buf_off : ch.recv.buf_off) += seg_off[ch.seg];
     total = seg_off[npeers];
   };
-  layout(send, c.flxcor_send_off, c.flxcor_send_elements, true);
-  layout(recv, c.flxcor_recv_off, c.flxcor_recv_elements, false);
+  layout(send, c.flxcor_send_off, c.flxcor_send_elements, true, te_send_size, cell_send_size);
+  layout(recv, c.flxcor_recv_off, c.flxcor_recv_elements, false, te_recv_size, cell_recv_size);
   PARTHENON_REQUIRE(c.flxcor_send_elements + c.flxcor_recv_elements == 0 ||
                         pm->DefaultNumPartitions() == 1,
                     "inter-device flux correction needs one MeshData per rank");
@@ -1363,18 +1384,17 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
   if (c.flxcor_recv_elements > 0)
     c.flxcor_recv_slab.Allocate(sizeof(Real) * static_cast<size_t>(c.flxcor_recv_elements), md->stream());
 
-  // ---- fluxes of face fields: edge-centred flux fields (Metadata::Flux | Edge) ----
-  std::vector<pb2_prores_region> te_restricts;
+  // ---- edge-centred fluxes of face fields: regions of the plans built above ----
+  std::vector<pb2_prores_region> te_restricts, te_send_restricts;
   std::vector<pb2_copy_region> te_copies[2];
+  std::vector<pb2_bnd_region> te_packs, te_unpacks[2];
   c.teflx_elements = 0;
   std::array<bool, 27> all_true;
   all_true.fill(true);
-  const std::vector<Variable *> fvars = md->GetVariablesByFlag({Metadata::Flux});
-  EdgeFluxPlan fplan;
-  if (!fvars.empty() && pm->multilevel) fplan = BuildEdgeFluxPlan(pm, md->GetBlockList());
-  for (Variable *fv : fvars) {
-    PARTHENON_REQUIRE(fv->topological_type() == TopologicalType::Edge,
-                      "flux fields other than the edge-centred flux of a face field are not built");
+  std::vector<int64_t> te_send_base(npeers, 0), te_recv_base(npeers, 0); // of the current field
+  for (size_t ifv = 0; ifv < fplans.size(); ++ifv) {
+    Variable *fv = fvars[ifv];
+    const EdgeFluxPlan &fplan = fplans[ifv];
     const TE edge_els[3] = {TE::E1, TE::E2, TE::E3};
     const int nc = fv->TensorComponents();
     for (const EdgeFluxRestrict &rr : fplan.restricts) {
@@ -1383,6 +1403,57 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
       const MeshBlock *sb = pm->block_list[pm->GetLid(rr.gid)].get();
       AddTeRegions(te_restricts, ContainerOf(md, sb)->Get(fv->label()), sb, rr.el,
                    edge_els[rr.el], nullptr, rr.box, all_true, pm->ndim);
+    }
+    for (const EdgeFluxRestrict &rr : fplan.send_restricts) {
+      const MeshBlock *sb = pm->block_list[pm->GetLid(rr.gid)].get();
+      AddTeRegions(te_send_restricts, *fv, sb, rr.el, edge_els[rr.el], nullptr, rr.box, all_true,
+                   pm->ndim);
+    }
+    // pieces that cross devices: packed from the sender's coarse buffer, unpacked into the
+    // receiver's flux array — block-edge messages ([0]) before face messages ([1]), like the
+    // same-device copies
+    for (const EdgeFluxPiece &pc : fplan.send) {
+      const MeshBlock *sb = pm->block_list[pm->GetLid(pc.sender_gid)].get();
+      pb2_bnd_region r{};
+      r.var = fv->coarse() + sb->pack_index * fv->cblock_stride +
+              static_cast<int64_t>(pc.el) * nc * fv->ccomp_stride;
+      r.stride_j = fv->cni;
+      r.stride_k = fv->cni * fv->cnj;
+      r.stride_c = static_cast<int32_t>(fv->ccomp_stride);
+      r.buf_off = c.flxcor_send_off[pc.seg] + cell_send_size[pc.seg] + te_send_base[pc.seg] +
+                  pc.slab_off;
+      for (int d = 0; d < 3; ++d) {
+        r.s[d] = pc.send_box.s[d];
+        r.n[d] = pc.send_box.n(d);
+      }
+      r.ncomp = nc;
+      r.flag_slot = -1;
+      r.status = PB2_REGION_ALLOCATED;
+      te_packs.push_back(r);
+    }
+    for (const EdgeFluxPiece &pc : fplan.recv) {
+      const MeshBlock *rb = pm->block_list[pm->GetLid(pc.receiver_gid)].get();
+      pb2_bnd_region r{};
+      r.var = fv->data() + rb->pack_index * fv->block_stride +
+              static_cast<int64_t>(pc.el) * nc * fv->comp_stride;
+      r.stride_j = fv->ni;
+      r.stride_k = fv->ni * fv->nj;
+      r.stride_c = static_cast<int32_t>(fv->comp_stride);
+      r.buf_off = c.flxcor_recv_off[pc.seg] + cell_recv_size[pc.seg] + te_recv_base[pc.seg] +
+                  pc.slab_off;
+      for (int d = 0; d < 3; ++d) {
+        r.s[d] = pc.recv_box.s[d];
+        r.n[d] = pc.recv_box.n(d);
+      }
+      r.ncomp = nc;
+      r.flag_slot = -1;
+      r.status = PB2_REGION_ALLOCATED | PB2_REGION_BUF_ALLOCATED;
+      c.teflx_elements += static_cast<int64_t>(nc) * r.n[0] * r.n[1] * r.n[2];
+      te_unpacks[pc.pass].push_back(r);
+    }
+    for (int p = 0; p < npeers; ++p) {
+      te_send_base[p] += fplan.send_off[p + 1] - fplan.send_off[p];
+      te_recv_base[p] += fplan.recv_off[p + 1] - fplan.recv_off[p];
     }
     for (const EdgeFluxPiece &pc : fplan.pieces) {
       const MeshBlock *sb = pm->block_list[pm->GetLid(pc.sender_gid)].get();
@@ -1411,6 +1482,13 @@ void RebuildFluxCorrection(MeshData<Real> *md, BvarsCache &c) {
       te_copies[pc.pass].push_back(r);
     }
   }
+  PB2_CHECK(pb2_prores_table_create(&c.teflx_restrict_send, te_send_restricts.data(),
+                                    static_cast<int64_t>(te_send_restricts.size())));
+  PB2_CHECK(pb2_bnd_table_create(&c.teflx_pack, te_packs.data(),
+                                 static_cast<int64_t>(te_packs.size())));
+  for (int pass = 0; pass < 2; ++pass)
+    PB2_CHECK(pb2_bnd_table_create(&c.teflx_unpack[pass], te_unpacks[pass].data(),
+                                   static_cast<int64_t>(te_unpacks[pass].size())));
   PB2_CHECK(pb2_prores_table_create(&c.teflx_restrict, te_restricts.data(),
                                     static_cast<int64_t>(te_restricts.size())));
   for (int pass = 0; pass < 2; ++pass)
@@ -1438,6 +1516,10 @@ void SendFluxCorrections(MeshData<Real> *md) {
   if (c.flxcor_send_elements + c.flxcor_recv_elements == 0) return;
   pb2_stream_t st = md->stream(), cs = pm->comm_stream;
   PB2_CHECK(pb2_flux_correct(c.flxcor_pack, c.flxcor_send_slab.get<Real>(), st));
+  // edge-centred fluxes of face fields: restrict into the coarse buffers, pack what this rank's
+  // blocks own into the same slab
+  PB2_CHECK(pb2_restrict_te(c.teflx_restrict_send, st));
+  PB2_CHECK(pb2_pack(c.teflx_pack, c.flxcor_send_slab.get<Real>(), nullptr, st));
   PB2_CHECK(pb2_event_record(c.flxcor_packed, st));
   PB2_CHECK(pb2_stream_wait_event(cs, c.flxcor_packed));
   if (pm->nranks > 1) {
@@ -1461,12 +1543,17 @@ void SetFluxCorrectionsImpl(MeshData<Real> *md) {
   PB2_CHECK(pb2_flux_correct(c.flxcor_local, nullptr, st));
   // edge-centred fluxes of face fields: restrict on the fine blocks, then deliver — across block
   // edges first, across faces second (BvarsCache::teflx_copy)
+  // — whether a message came from this device (copy) or another one (unpack)
   PB2_CHECK(pb2_restrict_te(c.teflx_restrict, st));
-  PB2_CHECK(pb2_copy(c.teflx_copy[0], nullptr, st));
-  PB2_CHECK(pb2_copy(c.teflx_copy[1], nullptr, st));
-  if (c.flxcor_in_flight) {
-    PB2_CHECK(pb2_stream_wait_event(st, c.flxcor_received));
-    PB2_CHECK(pb2_unpack(c.flxcor_unpack, c.flxcor_recv_slab.get<Real>(), nullptr, st));
+  const bool remote = c.flxcor_in_flight;
+  if (remote) PB2_CHECK(pb2_stream_wait_event(st, c.flxcor_received));
+  const Real *slab = c.flxcor_recv_slab.get<Real>();
+  for (int pass = 0; pass < 2; ++pass) {
+    PB2_CHECK(pb2_copy(c.teflx_copy[pass], nullptr, st));
+    if (remote) PB2_CHECK(pb2_unpack(c.teflx_unpack[pass], slab, nullptr, st));
+  }
+  if (remote) {
+    PB2_CHECK(pb2_unpack(c.flxcor_unpack, slab, nullptr, st));
     c.flxcor_in_flight = false;
   }
 }

@@ -316,49 +316,100 @@ IndexBox SubBox(const IndexBox &box, const IndexBox &rel) {
 }
 } // namespace
 
-EdgeFluxPlan BuildEdgeFluxPlan(const Mesh *pm, const BlockList_t &blocks) {
+EdgeFluxPlan BuildEdgeFluxPlan(const Mesh *pm, const BlockList_t &blocks, int ncomp) {
   EdgeFluxPlan plan;
+  const int V = pm->virtual_ranks > 1 ? pm->virtual_ranks : 1;
+  plan.npeers = V > 1 ? V * V : pm->nranks;
   for (auto &pmb : blocks) {
+    const int my_vr = pm->VirtualRankOf(pmb->gid);
     for (auto &nb : pmb->neighbors) {
       // ForEachBoundary<flxcor_*> (loop_utils.hpp:134-158): neighbours one level apart across a
       // face or a block edge
       if (std::abs(nb.loc.level - pmb->loc.level) != 1) continue;
       const std::vector<TE> els = FluxCorrectionEdgeElements(nb.offsets);
       if (els.empty()) continue;
-      PARTHENON_REQUIRE(nb.rank == pm->my_rank &&
-                            pm->VirtualRankOf(nb.gid) == pm->VirtualRankOf(pmb->gid),
-                        "flux correction of face fields across devices is not built");
+      PARTHENON_REQUIRE(!nb.transformed, "flux correction of face fields on forests is not built");
+      const int nb_vr = nb.rank == pm->my_rank ? pm->VirtualRankOf(nb.gid) : 0;
+      const bool local = nb.rank == pm->my_rank && nb_vr == my_vr;
       const int pass = els.size() == 2 ? 1 : 0;
+      const bool pmb_sends = nb.loc.level == pmb->loc.level - 1;
+      // the fine SENDER's half of a same-device pair is listed from the receiver's side below, so
+      // that a partition's tables hold everything its own blocks need, in order
+      if (pmb_sends && local) continue;
       for (TE el : els) {
         const int e = static_cast<int>(el) % 3; // E1, E2, E3 -> 0, 1, 2 in storage order
-        // the fine SENDER's half is listed from the receiver's side below, so that a partition's
-        // tables hold everything its own blocks need, in order
-        if (nb.loc.level == pmb->loc.level - 1) continue;
+        if (pmb_sends) {
+          // fine block of this rank, coarser neighbour on another device: restrict the shared
+          // elements into the coarse buffer (ProResInfo::GetSend, bnd_info.cpp:387-403) and send
+          // the entries this block owns (bnd_info.cpp:232-248; the mask is taken in the sender's
+          // view of the receiver, the same numbers the receiver derives below)
+          plan.send_restricts.push_back(
+              {pmb->gid, e,
+               CalcIndicesFluxTE(nb, pmb.get(), el, IndexRangeType::BoundaryInteriorSend, true)});
+          const IndexBox sbox =
+              CalcIndicesFluxTE(nb, pmb.get(), el, IndexRangeType::BoundaryInteriorSend, false);
+          const int n[3] = {sbox.n(0), sbox.n(1), sbox.n(2)};
+          const auto mask = IndexRangeMask(el, pm->Ownership(pmb->gid), nb.offsets);
+          int sub = 0;
+          for (const IndexBox &rel : ActivePieces(n, mask)) {
+            EdgeFluxPiece pc{pmb->gid, nb.gid, e, pass, SubBox(sbox, rel), IndexBox{}};
+            pc.seg = V > 1 ? my_vr * V + nb_vr : nb.rank;
+            pc.offset_index = nb.OffsetIndex();
+            pc.sub = sub++;
+            plan.send.push_back(pc);
+          }
+          continue;
+        }
         // coarse RECEIVER: the sender's coarse-buffer box -> this block's flux array, the
-        // entries the sender owns (bnd_info.cpp:232-248)
+        // entries the sender owns
+        const IndexBox rbox =
+            CalcIndicesFluxTE(nb, pmb.get(), el, IndexRangeType::BoundaryExteriorRecv, false);
+        const int n[3] = {rbox.n(0), rbox.n(1), rbox.n(2)};
+        const int sox[3] = {-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]};
+        const auto mask = IndexRangeMask(el, pm->Ownership(nb.gid), sox);
+        if (!local) {
+          int sub = 0;
+          for (const IndexBox &rel : ActivePieces(n, mask)) {
+            EdgeFluxPiece pc{nb.gid, pmb->gid, e, pass, IndexBox{}, SubBox(rbox, rel)};
+            pc.seg = V > 1 ? nb_vr * V + my_vr : nb.rank;
+            pc.offset_index = OffsetIndexOf(sox[0], sox[1], sox[2]);
+            pc.sub = sub++;
+            plan.recv.push_back(pc);
+          }
+          continue;
+        }
         const MeshBlock *sb = pm->block_list[nb.lid].get();
         const NeighborBlock *q = MatchingNeighbor(sb, pmb->gid, nb.offsets);
         PARTHENON_REQUIRE(q != nullptr, "no matching flux-correction sender");
         // the sender restricts (RestrictAverage) the shared elements into its coarse buffer
-        // (ProResInfo::GetSend, bnd_info.cpp:387-403)
         plan.restricts.push_back(
             {nb.gid, e, CalcIndicesFluxTE(*q, sb, el, IndexRangeType::BoundaryInteriorSend, true)});
-        const IndexBox rbox =
-            CalcIndicesFluxTE(nb, pmb.get(), el, IndexRangeType::BoundaryExteriorRecv, false);
         const IndexBox sbox =
             CalcIndicesFluxTE(*q, sb, el, IndexRangeType::BoundaryInteriorSend, false);
-        int n[3];
-        for (int d = 0; d < 3; ++d) {
-          n[d] = rbox.n(d);
+        for (int d = 0; d < 3; ++d)
           PARTHENON_REQUIRE(sbox.n(d) == n[d], "flux-correction extents differ");
-        }
-        const int sox[3] = {-nb.offsets[0], -nb.offsets[1], -nb.offsets[2]};
-        const auto mask = IndexRangeMask(el, pm->Ownership(nb.gid), sox);
         for (const IndexBox &rel : ActivePieces(n, mask))
           plan.pieces.push_back({nb.gid, pmb->gid, e, pass, SubBox(sbox, rel), SubBox(rbox, rel)});
       }
     }
   }
+  // both sides order a peer segment by the same key => identical offsets, no handshake
+  auto layout = [&](std::vector<EdgeFluxPiece> &pcs, std::vector<int64_t> &seg_off, bool send) {
+    std::stable_sort(pcs.begin(), pcs.end(), [](const EdgeFluxPiece &a, const EdgeFluxPiece &b) {
+      return std::make_tuple(a.seg, a.sender_gid, a.receiver_gid, a.offset_index, a.el, a.sub) <
+             std::make_tuple(b.seg, b.sender_gid, b.receiver_gid, b.offset_index, b.el, b.sub);
+    });
+    std::vector<int64_t> seg_size(plan.npeers, 0);
+    for (EdgeFluxPiece &pc : pcs) {
+      const int64_t n = static_cast<int64_t>(ncomp) * (send ? pc.send_box : pc.recv_box).size();
+      pc.slab_off = seg_size[pc.seg];
+      seg_size[pc.seg] += n + (n & 1); // 16-byte aligned pieces
+    }
+    seg_off.assign(plan.npeers + 1, 0);
+    for (int p = 0; p < plan.npeers; ++p) seg_off[p + 1] = seg_off[p] + seg_size[p];
+  };
+  layout(plan.send, plan.send_off, true);
+  layout(plan.recv, plan.recv_off, false);
   return plan;
 }
 

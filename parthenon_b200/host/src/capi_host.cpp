@@ -689,15 +689,21 @@ int64_t pb2h_sim_exchange_elements(pb2h_sim *sim, const char *container, int64_t
 int64_t pb2h_sim_edge_flux_plan(pb2h_sim *sim, int kind, int64_t *rows, int64_t max_rows) {
   int64_t count = -1;
   Guard([&] {
+    PARTHENON_REQUIRE(kind >= 0 && kind <= 4, "kind: 0 restrict, 1 deliver, 2 send restrict, "
+                                               "3 send, 4 receive");
     Mesh *pm = sim->pm();
     const EdgeFluxPlan plan = BuildEdgeFluxPlan(pm, pm->block_list);
-    count = static_cast<int64_t>(kind == 0 ? plan.restricts.size() : plan.pieces.size());
+    const bool is_restrict = kind == 0 || kind == 2;
+    const std::vector<EdgeFluxRestrict> &rs = kind == 0 ? plan.restricts : plan.send_restricts;
+    const std::vector<EdgeFluxPiece> &ps =
+        kind == 1 ? plan.pieces : (kind == 3 ? plan.send : plan.recv);
+    count = static_cast<int64_t>(is_restrict ? rs.size() : ps.size());
     if (!rows) return;
     for (int64_t i = 0; i < std::min<int64_t>(count, max_rows); ++i) {
-      int64_t *r = rows + 13 * i;
-      for (int q = 0; q < 13; ++q) r[q] = 0;
-      if (kind == 0) {
-        const EdgeFluxRestrict &x = plan.restricts[i];
+      int64_t *r = rows + 16 * i;
+      for (int q = 0; q < 16; ++q) r[q] = 0;
+      if (is_restrict) {
+        const EdgeFluxRestrict &x = rs[i];
         r[0] = x.gid;
         r[2] = x.el;
         for (int d = 0; d < 3; ++d) {
@@ -705,16 +711,20 @@ int64_t pb2h_sim_edge_flux_plan(pb2h_sim *sim, int kind, int64_t *rows, int64_t 
           r[10 + d] = x.box.n(d);
         }
       } else {
-        const EdgeFluxPiece &x = plan.pieces[i];
+        const EdgeFluxPiece &x = ps[i];
         r[0] = x.sender_gid;
         r[1] = x.receiver_gid;
         r[2] = x.el;
         r[3] = x.pass;
+        const IndexBox &nbox = kind == 3 ? x.send_box : x.recv_box;
         for (int d = 0; d < 3; ++d) {
-          r[4 + d] = x.send_box.s[d];
-          r[7 + d] = x.recv_box.s[d];
-          r[10 + d] = x.recv_box.n(d);
+          r[4 + d] = kind == 4 ? 0 : x.send_box.s[d];
+          r[7 + d] = kind == 3 ? 0 : x.recv_box.s[d];
+          r[10 + d] = nbox.n(d);
         }
+        r[13] = x.seg;
+        r[14] = x.slab_off + (x.seg >= 0 ? (kind == 3 ? plan.send_off : plan.recv_off)[x.seg] : 0);
+        r[15] = x.offset_index * 64 + x.sub;
       }
     }
   });

@@ -195,8 +195,9 @@ TEFLUX = [("teflux_s16_b8_l2_3d", 3, 16, 8, 2), ("teflux_s32_b8_l3_2d", 2, 32, 8
           ("teflux_s16_b4_g4_l3_3d_sparse", 3, 16, 4, 4)]
 
 
+@pytest.mark.parametrize("extra", [None, {"pb2/virtual_ranks": 2}, {"pb2/virtual_ranks": 3}])
 @pytest.mark.parametrize("name,ndim,nx,nb,ng", TEFLUX)
-def test_flux_correction_of_a_face_field_bit_exact(name, ndim, nx, nb, ng):
+def test_flux_correction_of_a_face_field_bit_exact(name, ndim, nx, nb, ng, extra):
     """flux correction of a FACE field on the device: its flux is the edge field "bnd_flux::B"
     (StateDescriptor::AddField).  Fine blocks restrict the edge elements they share with coarser
     neighbours (restrict_te_kernel), the coarser blocks take the entries the sender owns
@@ -204,7 +205,9 @@ def test_flux_correction_of_a_face_field_bit_exact(name, ndim, nx, nb, ng):
     reference (tests/golden/refgen/teflux_dump_main.cpp: 3-D two levels, 2-D three levels, 3-D
     three levels of 4^3 blocks with 4 ghosts).  Entries the reference delivers twice in a
     shuffled order (see oracle/pb2_oracle.c) must hold the oracle's choice, every other entry
-    the reference's; a second correction changes nothing"""
+    the reference's; a second correction changes nothing.  extra = pb2/virtual_ranks: fine-coarse
+    pairs in different groups of blocks take the inter-device path (restrict, pack what the
+    sender owns into the flux-correction slab, unpack block-edge messages before face messages)"""
     import oracle
     from tests.test_oracle_golden import teflux_initial, teflux_reference
     g = np.load(os.path.join(GOLD, name + ".npz"))
@@ -219,9 +222,12 @@ def test_flux_correction_of_a_face_field_bit_exact(name, ndim, nx, nb, ng):
     once = w[:, :, 0] <= 1
     ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static")
     ov["tecomm/flux_field"] = "true"
+    ov.update(extra or {})
     sim = host.Simulation(app="tecomm", overrides=ov, leaves=leaves)
     try:
         assert sim.field_shape("base", "bnd_flux::B") == ref.shape
+        if extra:
+            assert len(sim.edge_flux_plan("send")) > 0
         sim.set_field("base", "bnd_flux::B", init)
         sim.flux_correction("base")
         got = sim.get_field("base", "bnd_flux::B")
