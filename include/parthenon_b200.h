@@ -157,6 +157,11 @@ typedef struct pb2_bnd_table pb2_bnd_table; /* opaque, device resident */
  * rebuild only (reference: RebuildBufferCache, src/bvals/comms/bvals_utils.hpp:212-260). */
 int pb2_bnd_table_create(pb2_bnd_table **table, const pb2_bnd_region *regions, int64_t n);
 int pb2_copy_table_create(pb2_bnd_table **table, const pb2_copy_region *regions, int64_t n);
+/* Destroying a table never waits for the device: launches that still read it stay valid, its
+ * device memory goes back to a pool (size classes 4 KB x 4^k per device) and is handed out again
+ * only after a device synchronisation that followed the destroy (csrc/runtime.cu: table_alloc).
+ * Tables of every kind (boundary, copy, prolongation / restriction, flux correction, boundary
+ * condition) are destroyed with this one call. */
 int pb2_bnd_table_destroy(pb2_bnd_table *table);
 /* total Reals covered by the table's boxes */
 int64_t pb2_bnd_table_elements(const pb2_bnd_table *table);
