@@ -518,3 +518,29 @@ def test_edge_flux_plan_across_ranks(name, ndim, nx, nb, ng, nranks):
                         slab[o:o + n].reshape(bk, bj, bi)
     assert not np.isnan(G).any()
     assert np.array_equal(G, F)
+
+
+def test_plan_is_the_same_on_one_and_on_many_host_threads():
+    """the exchange plan of a mesh of more than 256 blocks is built on all host threads (channels
+    per block, lists joined by prefix sums): channel order, boxes and slab offsets must equal the
+    single-threaded build, for same-device channels and for the slabs of a 2-rank partition"""
+    import ctypes as C
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+    except OSError:
+        pytest.skip("no libgomp")
+    leaves = H.refined_leaves(8, {(3, 3, 3), (4, 4, 4), (1, 6, 2)})
+    ov = deck_overrides(3, (8, 8, 8), 2, (8, 8, 8), "static")
+    got = {}
+    for nt in (1, 8):
+        gomp.omp_set_num_threads(nt)
+        rows = []
+        for rank, nranks in ((0, 1), (0, 2), (1, 2)):
+            t = host.Topology(overrides=ov, leaves=leaves, rank=rank, nranks=nranks)
+            assert t.info()["nbtotal"] > 512
+            rows += [t.plan_boxes(3, 0, kind) for kind in ("local", "send", "recv")]
+        got[nt] = rows
+    gomp.omp_set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    assert sum(len(r) for r in got[1]) > 10000
+    for a, b in zip(got[1], got[8]):
+        assert np.array_equal(a, b)
