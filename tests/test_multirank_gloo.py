@@ -184,3 +184,92 @@ def test_two_rank_face_edge_node_exchange_over_gloo():
     assert all(r[0] for r in res.values()), res
     assert sum(r[1] for r in res.values()) == 64
     assert res[0][2] > 0 and res[1][2] > 0
+
+
+# ---- flux correction of a face field: restricted edge fluxes cross ranks in one slab ----
+def _edge_flux_worker(rank, port, result):
+    """each process holds only the coarse buffers (restricted edge fluxes, from the oracle) and
+    the flux arrays of ITS blocks of a statically refined mesh, derives with the host library
+    what it sends and receives, ships one slab to its peer over gloo and applies same-device
+    copies and the received pieces in the two passes — block-edge messages, then face messages.
+    Its blocks must hold the oracle's corrected flux field (pinned to the reference's dump)"""
+    import ctypes as C
+    from tests import helpers as H
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        name, ndim, nx, nb, ng = "teflux_s16_b8_l2_3d", 3, 16, 8, 2
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+        leaves, nrb = H.leaves_from_bounds(g["bounds"], (nx,) * 3, (nb,) * 3)
+        ov = deck_overrides(ndim, (nb,) * 3, ng, nrb, refinement="static")
+        t = host.Topology(overrides=ov, leaves=leaves, rank=rank, nranks=WORLD)
+        info = t.info()
+        lo, hi = info["first_gid"], info["first_gid"] + info["nblocks"]
+        m = oracle.Mesh(ndim, (nb,) * ndim, ng, tuple(nrb[:ndim]), leaves=leaves)
+        nk, nj, ni = m.te_extents(2)
+        gid = np.arange(m.nblocks).reshape(-1, 1, 1, 1, 1, 1)
+        e = np.arange(3).reshape(1, -1, 1, 1, 1, 1)
+        F0 = ((gid + 1) * 1.0e6 + e * 1.0e5 +
+              np.arange(nk * nj * ni).reshape(1, 1, 1, nk, nj, ni)).astype(np.float64)
+        F = F0.copy()
+        cd = tuple(n + (1 if n > 1 else 0) for n in m.cdims)
+        Fc = np.zeros(F.shape[:3] + cd)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert oracle.lib().orc_flux_correct_edge(m.h, dp(F), dp(Fc), 1, None) > 0
+        # this process: its own blocks only
+        G = F0.copy()
+        for a in (G, Fc):
+            a[:lo] = np.nan
+            a[hi:] = np.nan
+        peer = 1 - rank
+        size = lambda r: int(r[10] * r[11] * r[12])
+        send_rows, recv_rows = t.edge_flux_plan("send"), t.edge_flux_plan("recv")
+        assert len(send_rows) + len(recv_rows) > 0
+        assert all(int(r[13]) == peer for r in list(send_rows) + list(recv_rows))
+        base_s = min([int(r[14]) for r in send_rows] + [0])
+        base_r = min([int(r[14]) for r in recv_rows] + [0])
+        send = np.full(max([int(r[14]) - base_s + size(r) for r in send_rows] + [1]), np.nan)
+        for r in send_rows:
+            sg, el = int(r[0]), int(r[2])
+            assert lo <= sg < hi
+            (si, sj, sk), (bi, bj, bk) = r[4:7], r[10:13]
+            o = int(r[14]) - base_s
+            send[o:o + size(r)] = Fc[sg, el, 0, sk:sk + bk, sj:sj + bj, si:si + bi].ravel()
+        recv = torch.full((max([int(r[14]) - base_r + size(r) for r in recv_rows] + [1]),), np.nan,
+                          dtype=torch.float64)
+        req = dist.isend(torch.from_numpy(send.copy()), peer)
+        dist.recv(recv, peer)
+        req.wait()
+        recv = recv.numpy()[:max([int(r[14]) - base_r + size(r) for r in recv_rows] + [0])] \
+            if len(recv_rows) else recv.numpy()[:0]
+        loc = t.edge_flux_plan("deliver")
+        for p in (0, 1):
+            for r in loc[loc[:, 3] == p]:
+                sg, rg, el = int(r[0]), int(r[1]), int(r[2])
+                (si, sj, sk), (ri, rj, rk), (bi, bj, bk) = r[4:7], r[7:10], r[10:13]
+                G[rg, el, 0, rk:rk + bk, rj:rj + bj, ri:ri + bi] = \
+                    Fc[sg, el, 0, sk:sk + bk, sj:sj + bj, si:si + bi]
+            for r in recv_rows[recv_rows[:, 3] == p] if len(recv_rows) else []:
+                rg, el = int(r[1]), int(r[2])
+                assert lo <= rg < hi
+                (ri, rj, rk), (bi, bj, bk) = r[7:10], r[10:13]
+                o = int(r[14]) - base_r
+                G[rg, el, 0, rk:rk + bk, rj:rj + bj, ri:ri + bi] = \
+                    recv[o:o + size(r)].reshape(bk, bj, bi)
+        ok = not np.isnan(G[lo:hi]).any() and np.array_equal(G[lo:hi], F[lo:hi])
+        result[rank] = (bool(ok), hi - lo, int(len(send_rows)), int(len(recv_rows)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_edge_flux_correction_over_gloo():
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        result = mgr.dict()
+        mp.spawn(_edge_flux_worker, args=(_free_port(), result), nprocs=WORLD, join=True)
+        res = dict(result)
+    assert set(res) == {0, 1}
+    assert all(r[0] for r in res.values()), res
+    assert sum(r[1] for r in res.values()) == 15
+    # what one rank sends the other receives
+    assert res[0][2] == res[1][3] and res[1][2] == res[0][3] and res[0][2] + res[1][2] > 0
