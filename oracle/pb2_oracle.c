@@ -5,7 +5,8 @@
  * handed over through orc_mesh_create_custom), boundary index boxes, pack/unpack — through the
  * neighbour tree's LogicalCoordinateTransformation where there is one —,
  * restriction/prolongation at
- * fine-coarse boundaries, flux correction, physical boundaries, the benchmarks/burgers RK2
+ * fine-coarse boundaries, flux correction (face fluxes of cell-centred fields and the
+ * edge-centred fluxes of face fields), physical boundaries, the benchmarks/burgers RK2
  * cycle, example/advection and example/sparse_advection (uniform, statically and adaptively
  * refined meshes), and the exchange / remesh of face, edge and node fields with block
  * ownership.  Every section is pinned against dumps of the reference (tests/golden/).
